@@ -1,0 +1,116 @@
+/* lumo_gpu.h — C ABI of liblumo_gpu.so, the B200 (sm_100a) implementation of lumo's rendering
+ * hot path.  This is the boundary a `lumo-gpu-sys` Rust crate binds (INTEGRATION.md shows the
+ * extern "C" block and the Renderer::render wiring).
+ *
+ * What it replaces in the reference (ekarpp/lumo v0.6.1, paths relative to the crate root):
+ *   - the generic executor seam `trait Executor<T,R> { fn exec(&mut self, task: T) -> R }`
+ *     (src/pool.rs:6-8) as instantiated by `RenderTaskExecutor` (src/renderer/task.rs:24-81) and
+ *     driven by `ThreadPool` from `Renderer::render` (src/renderer.rs:159-244);
+ *   - underneath it `Integrator::integrate` (src/tracer/integrator.rs:45-69), `Scene::hit /
+ *     hit_t / hit_light` (src/tracer/scene.rs:119-189), `BVH::_hit` (src/tracer/object/bvh.rs:
+ *     315-362), `KdTree::_hit` (src/tracer/object/kdtree.rs:101-169) and `Triangle::_hit`
+ *     (src/tracer/object/triangle.rs:63-187).
+ *
+ * Conventions: every function returns 0 on success and a negative lumo_status on failure; the
+ * message is available from lumo_gpu_last_error() (thread-local).  Nothing unwinds or aborts.
+ * All pointers are HOST pointers unless a name ends in `_dev`; the library copies in and out.
+ * A context is not re-entrant; different contexts may be used from different threads.
+ */
+#ifndef LUMO_GPU_H
+#define LUMO_GPU_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lumo_ctx lumo_ctx;     /* one per GPU: stream, scratch queues */
+typedef struct lumo_scene lumo_scene; /* an uploaded scene blob (csrc/common/scene_blob.h) */
+
+enum lumo_status {
+    LUMO_OK = 0,
+    LUMO_ERR_INVALID = -1,   /* bad argument / malformed blob */
+    LUMO_ERR_CUDA = -2,      /* CUDA runtime error, no device */
+    LUMO_ERR_OOM = -3,
+    LUMO_ERR_UNSUPPORTED = -4
+};
+
+/* Integrator::{PathTrace, DirectLight, BDPathTrace}  (src/tracer/integrator.rs:17-27) */
+enum lumo_integrator { LUMO_PATH_TRACE = 0, LUMO_DIRECT_LIGHT = 1, LUMO_BD_PATH_TRACE = 2 };
+/* SamplerType (src/samplers.rs:8-21); Sobol is not provided */
+enum lumo_sampler { LUMO_SAMPLER_UNIFORM = 0, LUMO_SAMPLER_JITTERED = 1, LUMO_SAMPLER_MULTI_JITTERED = 2 };
+/* ToneMap (src/tone_mapping.rs:13-20) */
+enum lumo_tone_map { LUMO_TONE_NONE = 0, LUMO_TONE_CLAMP = 1, LUMO_TONE_REINHARD = 2 };
+
+/* What Renderer::{samples,integrator,seed,sampler,tone_map} configure (src/renderer.rs:66-99).
+ * [spp_begin, spp_end) of total_spp lets several GPUs (or calls) share one render: the RNG is
+ * keyed by (pixel, global sample index), so the union of disjoint ranges equals one full call. */
+typedef struct lumo_render_params {
+    int32_t integrator;      /* lumo_integrator */
+    int32_t sampler;         /* lumo_sampler */
+    int32_t tone_map;        /* lumo_tone_map */
+    int32_t flags;           /* reserved, 0 */
+    double tone_map_arg;     /* Clamp(max) */
+    double rr_delta;         /* > 0: fixed Russian-roulette threshold; 0: per-tile pilot estimate */
+    uint64_t seed;           /* Renderer::seed */
+    uint32_t spp_begin, spp_end, total_spp;
+    uint32_t wave_paths;     /* paths in flight per wave; 0 = default */
+} lumo_render_params;
+
+/* Film accumulators (src/tracer/film.rs:52-76,92-100): the caller allocates pixels[W*H*4] =
+ * (sum r*w, sum g*w, sum b*w, sum w) and splats[W*H*3]; the library OVERWRITES them.  The host
+ * then finishes exactly like Film::rgb_image (film.rs:173-193). */
+typedef struct lumo_film_accum {
+    double* pixels;
+    double* splats;
+    uint64_t counters[8];    /* [0] camera paths, [1] closest-hit queries (Scene::hit), [2] occlusion /
+                                visibility queries, [3] reference-style cost (sum FilmSample.cost,
+                                renderer.rs:221), [4] kernels launched, [5] deepest path, [6] shadow
+                                rays queued, [7] reserved */
+    double* tile_deltas;     /* optional [ceil(W/16)*ceil(H/16)]: RR threshold used per 16x16 tile */
+    double device_ms;        /* CUDA-event time of the render on the context's stream */
+} lumo_film_accum;
+
+int32_t lumo_gpu_device_count(int32_t* n);
+int32_t lumo_gpu_ctx_create(int32_t device, lumo_ctx** ctx);
+int32_t lumo_gpu_ctx_destroy(lumo_ctx* ctx);
+
+/* Upload a scene blob (built once on the host from lumo's own kd-tree / BVH build; layout in
+ * csrc/common/scene_blob.h).  The caller keeps ownership of `blob`. */
+int32_t lumo_gpu_scene_upload(lumo_ctx* ctx, const void* blob, uint64_t len, lumo_scene** scene);
+int32_t lumo_gpu_scene_destroy(lumo_scene* scene);
+
+/* Scene::hit on a ray batch (src/tracer/scene.rs:119-147).  origin_xyz / dir_xyz: [n*3] f64 AoS;
+ * directions are used as given (Ray::new normalises — pass normalised directions).  t_max may be
+ * NULL (= +inf; the reference always uses +inf).  Outputs: obj_id = index in Scene.objects
+ * insertion order, lights offset by objects.len(); tri_id = index in that object's
+ * KdTree.objects (0 for spheres / loose triangles); both 0xFFFFFFFF on a miss; t = hit distance
+ * (+inf on miss); bary_uv[2i..] = first two barycentrics (edges/det) for triangles, (u,v) for
+ * spheres.  Bit-exact against the reference traversal. */
+int32_t lumo_gpu_trace_closest(lumo_scene* scene, const double* origin_xyz, const double* dir_xyz, const double* t_max,
+                               uint64_t n, uint32_t* obj_id, uint32_t* tri_id, double* t, double* bary_uv);
+
+/* The occlusion test of Scene::hit_light (src/tracer/scene.rs:180-186): occluded[i] = 1 iff some
+ * object or light is hit in (0, t_max[i]).  Pass t_max = t_light - 1e-10 as the reference does. */
+int32_t lumo_gpu_trace_any(lumo_scene* scene, const double* origin_xyz, const double* dir_xyz, const double* t_max,
+                           uint64_t n, uint8_t* occluded);
+
+/* Scene::hit_t (src/tracer/scene.rs:150-162): distance of the FIRST hit found in reference
+ * traversal order (not the nearest; BDPT's visible() depends on it), +inf on miss. */
+int32_t lumo_gpu_trace_first_found(lumo_scene* scene, const double* origin_xyz, const double* dir_xyz, uint64_t n, double* t);
+
+/* The whole hot path: camera rays -> integrator -> film accumulators, for sample indices
+ * [spp_begin, spp_end) of every pixel. */
+int32_t lumo_gpu_render(lumo_scene* scene, const lumo_render_params* params, lumo_film_accum* out);
+
+/* Device-resident variants used by bench.py's kernel-only timing (inputs already in HBM). */
+int32_t lumo_gpu_trace_closest_dev(lumo_scene* scene, const double* origin_dev, const double* dir_dev, uint64_t n,
+                                   uint32_t* obj_dev, uint32_t* tri_dev, double* t_dev, double* bary_dev, float* kernel_ms);
+
+const char* lumo_gpu_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

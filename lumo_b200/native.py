@@ -1,0 +1,206 @@
+"""ctypes bindings: liblumo_host.so (scene builder) and liblumo_gpu.so (the C ABI of
+include/lumo_gpu.h).  The GPU library is mandatory for every compute entry point: if it is missing
+or no CUDA device is present the call raises — there is no CPU fallback in this package."""
+import ctypes as C
+import os
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+HOST_SO = os.path.join(HERE, "liblumo_host.so")
+GPU_SO = os.path.join(HERE, "liblumo_gpu.so")
+
+SECTIONS = ["tlas_nodes", "tlas_leaf", "objects", "instances", "kd_trees", "kd_nodes", "kd_leaf", "tri_verts", "tri_shade",
+            "normals", "uvs", "rects", "spheres", "materials", "tables", "lights"]
+
+TLAS_NODE = np.dtype([("lo", "<f8", 3), ("hi", "<f8", 3), ("right", "<u4"), ("first", "<u4"), ("count", "<u4"), ("pad", "<u4")])
+OBJECT = np.dtype([("kind", "<u4"), ("geom", "<u4"), ("inst", "<i4"), ("material", "<i4"), ("rect", "<u4"), ("pad", "<u4", 3)])
+INSTANCE = np.dtype([("inv", "<f8", 12), ("m", "<f8", 12), ("nrm", "<f8", 9), ("pad", "<f8")])
+KD_TREE = np.dtype([("lo", "<f8", 3), ("hi", "<f8", 3), ("root", "<u4"), ("tri_base", "<u4"), ("n_tris", "<u4"), ("pad", "<u4")])
+KD_NODE = np.dtype([("point", "<f8"), ("a", "<u4"), ("b", "<u4")])
+TRI_VERTS = np.dtype([("a", "<f8", 3), ("b", "<f8", 3), ("c", "<f8", 3), ("pad", "<f8")])
+TRI_SHADE = np.dtype([("n", "<u4", 3), ("t", "<u4", 3), ("flags", "<u4"), ("pad", "<u4")])
+RECT = np.dtype([("origin", "<f8", 3), ("b0", "<f8", 3), ("b1", "<f8", 3), ("pad", "<f8")])
+SPHERE = np.dtype([("radius", "<f8"), ("pad", "<f8")])
+MATERIAL = np.dtype([("kind", "<u4"), ("flags", "<u4"), ("roughness", "<f8"), ("kd", "<f4", 4), ("ks", "<f4", 4), ("tf", "<f4", 4), ("ke", "<f4", 4),
+                     ("eta_table", "<u4"), ("k_table", "<u4"), ("illum_table", "<u4"), ("pad", "<u4"), ("scale", "<f8"), ("pad2", "<f8")])
+LIGHT = np.dtype([("alias_prob", "<f8"), ("pdf", "<f8"), ("area", "<f8"), ("alias", "<u4"), ("pad", "<u4")])
+CAMERA = np.dtype([("screen_to_raster_m", "<f8", 16), ("screen_to_raster_inv", "<f8", 16), ("camera_to_screen_m", "<f8", 16),
+                   ("camera_to_screen_inv", "<f8", 16), ("world_to_camera_m", "<f8", 16), ("world_to_camera_inv", "<f8", 16),
+                   ("lens_radius", "<f8"), ("focal_length", "<f8"), ("image_plane_area", "<f8"), ("lens_area", "<f8"),
+                   ("res_x", "<u4"), ("res_y", "<u4"), ("ortho", "<u4"), ("pad", "<u4")])
+FILM = np.dtype([("xyz_to_rgb", "<f8", 9), ("wb", "<f8", 9), ("filter_r", "<f8"), ("filter_p", "<f8"), ("filter_gr", "<f8"),
+                 ("filter_kind", "<u4"), ("r_disc", "<u4"), ("color_space", "<u4"), ("pad", "<u4")])
+PARAMS = np.dtype([("n_objects", "<u4"), ("n_lights", "<u4"), ("lights_root", "<u4"), ("n_shadow_rays", "<u4"),
+                   ("n_tlas_nodes", "<u4"), ("n_kd_trees", "<u4"), ("n_materials", "<u4"), ("n_tris", "<u4"),
+                   ("bounds_lo", "<f8", 3), ("bounds_hi", "<f8", 3), ("camera", CAMERA), ("film", FILM)])
+SECREF = np.dtype([("offset", "<u8"), ("bytes", "<u8"), ("count", "<u8"), ("pad", "<u8")])
+HEADER = np.dtype([("magic", "<u8"), ("version", "<u4"), ("n_sections", "<u4"), ("total_bytes", "<u8"), ("pad", "<u8"),
+                   ("params", PARAMS), ("sec", SECREF, len(SECTIONS))])
+_SEC_DTYPES = {"tlas_nodes": TLAS_NODE, "tlas_leaf": np.dtype("<u4"), "objects": OBJECT, "instances": INSTANCE, "kd_trees": KD_TREE,
+               "kd_nodes": KD_NODE, "kd_leaf": np.dtype("<u4"), "tri_verts": TRI_VERTS, "tri_shade": TRI_SHADE, "normals": np.dtype(("<f8", 3)),
+               "uvs": np.dtype(("<f8", 2)), "rects": RECT, "spheres": SPHERE, "materials": MATERIAL, "tables": np.dtype(("<f8", 96)), "lights": LIGHT}
+
+
+class Blob:
+    """Parsed view (numpy, zero-copy) of a device scene blob."""
+    def __init__(self, data):
+        self.data = data
+        self.header = np.frombuffer(data, dtype=HEADER, count=1)[0]
+        assert int(self.header["magic"]) == 0x31424F4C424D554C, "not a lumo scene blob"
+        self.params = self.header["params"]
+        for i, name in enumerate(SECTIONS):
+            ref = self.header["sec"][i]
+            dt = _SEC_DTYPES[name]
+            setattr(self, name, np.frombuffer(data, dtype=dt, count=int(ref["count"]), offset=int(ref["offset"])))
+
+    def __len__(self):
+        return len(self.data)
+
+
+_host = None
+
+
+def host_lib():
+    global _host
+    if _host is None:
+        if not os.path.exists(HOST_SO):
+            from . import build
+            build.build_host()
+        L = C.CDLL(HOST_SO)
+        L.lumo_host_build.restype = C.c_int32
+        L.lumo_host_build.argtypes = [C.c_char_p, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+        L.lumo_host_free.argtypes = [C.c_void_p]
+        L.lumo_host_last_error.restype = C.c_char_p
+        _host = L
+    return _host
+
+
+def build_blob(program_bytes):
+    """scene program -> device blob bytes (kd-trees, BVHs, alias table built natively)."""
+    L = host_lib()
+    p = C.c_void_p(); n = C.c_uint64()
+    rc = L.lumo_host_build(program_bytes, len(program_bytes), C.byref(p), C.byref(n))
+    if rc != 0:
+        raise RuntimeError("lumo_host_build: " + L.lumo_host_last_error().decode())
+    try:
+        return C.string_at(p, n.value)
+    finally:
+        L.lumo_host_free(p)
+
+
+# ---- GPU library ---------------------------------------------------------------------------------
+class RenderParams(C.Structure):        # include/lumo_gpu.h lumo_render_params
+    _fields_ = [("integrator", C.c_int32), ("sampler", C.c_int32), ("tone_map", C.c_int32), ("flags", C.c_int32),
+                ("tone_map_arg", C.c_double), ("rr_delta", C.c_double), ("seed", C.c_uint64),
+                ("spp_begin", C.c_uint32), ("spp_end", C.c_uint32), ("total_spp", C.c_uint32), ("wave_paths", C.c_uint32)]
+
+
+class FilmAccum(C.Structure):           # include/lumo_gpu.h lumo_film_accum
+    _fields_ = [("pixels", C.POINTER(C.c_double)), ("splats", C.POINTER(C.c_double)), ("counters", C.c_uint64 * 8),
+                ("tile_deltas", C.POINTER(C.c_double)), ("device_ms", C.c_double)]
+
+
+_gpu = None
+
+
+def gpu_lib():
+    """Loads liblumo_gpu.so.  Raises if it was not built — never falls back to anything else."""
+    global _gpu
+    if _gpu is None:
+        if not os.path.exists(GPU_SO):
+            raise RuntimeError("liblumo_gpu.so is not built (run `python -m lumo_b200.build gpu`); lumo_b200 has no CPU fallback")
+        L = C.CDLL(GPU_SO)
+        L.lumo_gpu_last_error.restype = C.c_char_p
+        vp = C.c_void_p
+        L.lumo_gpu_device_count.argtypes = [C.POINTER(C.c_int32)]
+        L.lumo_gpu_ctx_create.argtypes = [C.c_int32, C.POINTER(vp)]
+        L.lumo_gpu_ctx_destroy.argtypes = [vp]
+        L.lumo_gpu_scene_upload.argtypes = [vp, C.c_char_p, C.c_uint64, C.POINTER(vp)]
+        L.lumo_gpu_scene_destroy.argtypes = [vp]
+        dp, u32p, u8p = C.POINTER(C.c_double), C.POINTER(C.c_uint32), C.POINTER(C.c_uint8)
+        L.lumo_gpu_trace_closest.argtypes = [vp, dp, dp, dp, C.c_uint64, u32p, u32p, dp, dp]
+        L.lumo_gpu_trace_any.argtypes = [vp, dp, dp, dp, C.c_uint64, u8p]
+        L.lumo_gpu_trace_first_found.argtypes = [vp, dp, dp, C.c_uint64, dp]
+        L.lumo_gpu_render.argtypes = [vp, C.POINTER(RenderParams), C.POINTER(FilmAccum)]
+        for f in ("lumo_gpu_device_count", "lumo_gpu_ctx_create", "lumo_gpu_ctx_destroy", "lumo_gpu_scene_upload", "lumo_gpu_scene_destroy",
+                  "lumo_gpu_trace_closest", "lumo_gpu_trace_any", "lumo_gpu_trace_first_found", "lumo_gpu_render"):
+            getattr(L, f).restype = C.c_int32
+        _gpu = L
+    return _gpu
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise RuntimeError("%s failed (%d): %s" % (what, rc, gpu_lib().lumo_gpu_last_error().decode()))
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class GpuContext:
+    def __init__(self, device=0):
+        L = gpu_lib()
+        self.h = C.c_void_p()
+        _check(L.lumo_gpu_ctx_create(device, C.byref(self.h)), "lumo_gpu_ctx_create")
+
+    def close(self):
+        if self.h:
+            gpu_lib().lumo_gpu_ctx_destroy(self.h); self.h = None
+
+    def __del__(self):
+        try: self.close()
+        except Exception: pass
+
+
+class GpuScene:
+    """An uploaded scene blob; entry points mirror include/lumo_gpu.h one to one (host pointers)."""
+    def __init__(self, ctx, blob_bytes):
+        self.ctx = ctx
+        self.blob = Blob(blob_bytes)
+        self.h = C.c_void_p()
+        _check(gpu_lib().lumo_gpu_scene_upload(ctx.h, blob_bytes, len(blob_bytes), C.byref(self.h)), "lumo_gpu_scene_upload")
+        cam = self.blob.params["camera"]
+        self.res_x, self.res_y = int(cam["res_x"]), int(cam["res_y"])
+
+    def close(self):
+        if self.h:
+            gpu_lib().lumo_gpu_scene_destroy(self.h); self.h = None
+
+    def __del__(self):
+        try: self.close()
+        except Exception: pass
+
+    def trace_closest(self, o, d, t_max=None):
+        o = np.ascontiguousarray(o, np.float64); d = np.ascontiguousarray(d, np.float64); n = o.shape[0]
+        tm = np.full(n, np.inf) if t_max is None else np.ascontiguousarray(t_max, np.float64)
+        obj = np.zeros(n, np.uint32); tri = np.zeros(n, np.uint32); t = np.zeros(n); bary = np.zeros((n, 2))
+        _check(gpu_lib().lumo_gpu_trace_closest(self.h, _dp(o), _dp(d), _dp(tm), n, obj.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                                tri.ctypes.data_as(C.POINTER(C.c_uint32)), _dp(t), _dp(bary)), "lumo_gpu_trace_closest")
+        return obj, tri, t, bary
+
+    def trace_any(self, o, d, t_max):
+        o = np.ascontiguousarray(o, np.float64); d = np.ascontiguousarray(d, np.float64); tm = np.ascontiguousarray(t_max, np.float64); n = o.shape[0]
+        occ = np.zeros(n, np.uint8)
+        _check(gpu_lib().lumo_gpu_trace_any(self.h, _dp(o), _dp(d), _dp(tm), n, occ.ctypes.data_as(C.POINTER(C.c_uint8))), "lumo_gpu_trace_any")
+        return occ
+
+    def trace_first_found(self, o, d):
+        o = np.ascontiguousarray(o, np.float64); d = np.ascontiguousarray(d, np.float64); n = o.shape[0]
+        t = np.zeros(n)
+        _check(gpu_lib().lumo_gpu_trace_first_found(self.h, _dp(o), _dp(d), n, _dp(t)), "lumo_gpu_trace_first_found")
+        return t
+
+    def render(self, integrator=0, spp=1, seed=1, sampler=2, tone_map=0, tone_map_arg=0.0, rr_delta=0.0, spp_begin=0, spp_end=None,
+               total_spp=None, wave_paths=0, flags=0):
+        total = spp if total_spp is None else total_spp
+        end = total if spp_end is None else spp_end
+        P = RenderParams(integrator, sampler, tone_map, flags, tone_map_arg, rr_delta, seed, spp_begin, end, total, wave_paths)
+        W, H = self.res_x, self.res_y
+        pixels = np.zeros((H, W, 4)); splats = np.zeros((H, W, 3))
+        ntiles = ((W + 15) // 16) * ((H + 15) // 16)
+        deltas = np.zeros(ntiles)
+        out = FilmAccum(_dp(pixels), _dp(splats), (C.c_uint64 * 8)(), _dp(deltas), 0.0)
+        _check(gpu_lib().lumo_gpu_render(self.h, C.byref(P), C.byref(out)), "lumo_gpu_render")
+        names = ("camera_paths", "closest", "occlusion", "cost", "gpu_launches", "max_depth", "shadow_queued", "reserved")
+        return pixels, splats, dict(zip(names, (int(v) for v in out.counters))), deltas, out.device_ms
