@@ -66,8 +66,8 @@ typedef struct lumo_film_accum {
     double* splats;
     uint64_t counters[8];    /* [0] camera paths, [1] closest-hit queries (Scene::hit), [2] occlusion /
                                 visibility queries, [3] reference-style cost (sum FilmSample.cost,
-                                renderer.rs:221), [4] kernels launched, [5] deepest path, [6] shadow
-                                rays queued, [7] reserved */
+                                renderer.rs:221), [4] kernels launched, [5] deepest path, [6] wave
+                                iterations, [7] samples whose radiance was NaN/inf (tone_mapping.rs:42-56) */
     double* tile_deltas;     /* optional [ceil(W/16)*ceil(H/16)]: RR threshold used per 16x16 tile */
     double device_ms;        /* CUDA-event time of the render on the context's stream */
 } lumo_film_accum;
@@ -103,6 +103,18 @@ int32_t lumo_gpu_trace_first_found(lumo_scene* scene, const double* origin_xyz, 
 /* The whole hot path: camera rays -> integrator -> film accumulators, for sample indices
  * [spp_begin, spp_end) of every pixel. */
 int32_t lumo_gpu_render(lumo_scene* scene, const lumo_render_params* params, lumo_film_accum* out);
+
+/* Same as lumo_gpu_render but the film accumulators are DEVICE buffers of the caller (pixels_dev
+ * [W*H*4], splats_dev [W*H*3], overwritten): the multi-GPU path reduces them with one NCCL
+ * reduce over NVLink before the host reads anything. */
+int32_t lumo_gpu_render_dev(lumo_scene* scene, const lumo_render_params* params, double* pixels_dev, double* splats_dev,
+                            uint64_t* counters8, double* device_ms);
+
+/* Traversal visit counters (N_tlas, N_inst, N_kd, N_idx, N_tri, N_sphere of DESIGN.md's byte
+ * formula).  While enabled, the traversal kernels of this context run their counting instantiation;
+ * never enabled inside a timed region. */
+int32_t lumo_gpu_ctx_count_visits(lumo_ctx* ctx, int32_t enable);
+int32_t lumo_gpu_ctx_visits(lumo_ctx* ctx, uint64_t* out6);
 
 /* Device-resident variants used by bench.py's kernel-only timing (inputs already in HBM). */
 int32_t lumo_gpu_trace_closest_dev(lumo_scene* scene, const double* origin_dev, const double* dir_dev, uint64_t n,

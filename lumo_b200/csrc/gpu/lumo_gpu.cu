@@ -1,0 +1,380 @@
+// liblumo_gpu.so — the C ABI of include/lumo_gpu.h over the sm_100a kernels of this directory.
+// Host side only orchestrates: scene upload, wave allocation, the iteration loop (regen -> trace ->
+// shade -> occlude) and the copies in and out.  No computation of the hot path happens on the CPU.
+#include "lumo_gpu.h"
+#include "wavefront.cuh"
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace lumo_dev;
+
+static thread_local std::string g_err;
+static int32_t fail(int32_t code, const std::string& msg) { g_err = msg; return code; }
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(e_ == cudaErrorMemoryAllocation ? LUMO_ERR_OOM : LUMO_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+
+struct lumo_ctx {
+    int device = 0, sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // wave storage, grown on demand and reused across renders
+    void* wave_mem = nullptr; size_t wave_bytes = 0;
+    void* host_pinned = nullptr;   // IterCounters + RunCounters read-back
+    unsigned long long launches = 0;
+    Counters* d_visit = nullptr;   // traversal visit counters (CNT passes)
+    int count_visits = 0;
+};
+struct lumo_scene {
+    lumo_ctx* ctx = nullptr;
+    uint8_t* d_blob = nullptr; uint64_t len = 0;
+    DevScene S;
+    LumoBlobHeader H;
+};
+
+extern "C" const char* lumo_gpu_last_error(void) { return g_err.c_str(); }
+
+extern "C" int32_t lumo_gpu_device_count(int32_t* n) {
+    if (!n) return fail(LUMO_ERR_INVALID, "device_count: null pointer");
+    int c = 0; CU(cudaGetDeviceCount(&c)); *n = c; return LUMO_OK;
+}
+
+extern "C" int32_t lumo_gpu_ctx_create(int32_t device, lumo_ctx** out) {
+    if (!out) return fail(LUMO_ERR_INVALID, "ctx_create: null pointer");
+    int c = 0; CU(cudaGetDeviceCount(&c));
+    if (device < 0 || device >= c) return fail(LUMO_ERR_INVALID, "ctx_create: no such device");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(LUMO_ERR_UNSUPPORTED, "ctx_create: liblumo_gpu is built for sm_100a only");
+    lumo_ctx* ctx = new (std::nothrow) lumo_ctx();
+    if (!ctx) return fail(LUMO_ERR_OOM, "ctx_create: out of host memory");
+    ctx->device = device; ctx->sm_count = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&ctx->ev0)); CU(cudaEventCreate(&ctx->ev1));
+    CU(cudaMallocHost(&ctx->host_pinned, 4096));
+    CU(cudaMalloc(&ctx->d_visit, sizeof(Counters)));
+    CU(cudaMemset(ctx->d_visit, 0, sizeof(Counters)));
+    // f64 traversal keeps two explicit stacks per thread
+    cudaDeviceSetLimit(cudaLimitStackSize, 4096);
+    *out = ctx; return LUMO_OK;
+}
+extern "C" int32_t lumo_gpu_ctx_destroy(lumo_ctx* ctx) {
+    if (!ctx) return LUMO_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->wave_mem) cudaFree(ctx->wave_mem);
+    if (ctx->d_visit) cudaFree(ctx->d_visit);
+    if (ctx->host_pinned) cudaFreeHost(ctx->host_pinned);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx; return LUMO_OK;
+}
+// Switches the traversal kernels of this context to their visit-counting instantiation (same
+// traversal, plus per-thread counters of TLAS nodes / instance transforms / kd nodes / leaf entries /
+// triangle tests / sphere tests — the N_* of the byte formula in DESIGN.md).  Not for timed runs.
+extern "C" int32_t lumo_gpu_ctx_count_visits(lumo_ctx* ctx, int32_t enable) {
+    if (!ctx) return fail(LUMO_ERR_INVALID, "count_visits: null ctx");
+    CU(cudaSetDevice(ctx->device));
+    ctx->count_visits = enable ? 1 : 0;
+    CU(cudaMemset(ctx->d_visit, 0, sizeof(Counters)));
+    return LUMO_OK;
+}
+extern "C" int32_t lumo_gpu_ctx_visits(lumo_ctx* ctx, uint64_t* out6) {
+    if (!ctx || !out6) return fail(LUMO_ERR_INVALID, "visits: null pointer");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    Counters c; CU(cudaMemcpy(&c, ctx->d_visit, sizeof c, cudaMemcpyDeviceToHost));
+    out6[0] = c.tlas; out6[1] = c.inst; out6[2] = c.kd; out6[3] = c.leaf; out6[4] = c.tri; out6[5] = c.sphere;
+    return LUMO_OK;
+}
+
+// ---- scene -------------------------------------------------------------------------------------------
+static bool validate_blob(const uint8_t* b, uint64_t len, LumoBlobHeader& H, std::string& why) {
+    if (len < sizeof(LumoBlobHeader)) { why = "blob shorter than its header"; return false; }
+    std::memcpy(&H, b, sizeof H);
+    if (H.magic != LUMO_BLOB_MAGIC) { why = "bad blob magic"; return false; }
+    if (H.version != LUMO_BLOB_VERSION) { why = "unsupported blob version"; return false; }
+    if (H.n_sections != LSEC_COUNT || H.total_bytes != len) { why = "blob size / section count mismatch"; return false; }
+    static const size_t elem[LSEC_COUNT] = {sizeof(LumoTlasNode), 4, sizeof(LumoObject), sizeof(LumoInstance), sizeof(LumoKdTree), sizeof(LumoKdNode), 4,
+                                            sizeof(LumoTriVerts), sizeof(LumoTriShade), 24, 16, sizeof(LumoRect), sizeof(LumoSphere), sizeof(LumoMaterial), 96 * 8, sizeof(LumoLight)};
+    for (int s = 0; s < LSEC_COUNT; s++) {
+        const LumoSectionRef& r = H.sec[s];
+        if (r.offset % 16 || r.offset > len || r.bytes > len - r.offset || r.bytes != r.count * elem[s]) { why = "blob section " + std::to_string(s) + " is malformed"; return false; }
+    }
+    const LumoSceneParams& P = H.params;
+    if (P.n_objects == 0 || P.n_lights == 0) { why = "scene needs at least one object and one light"; return false; }
+    if (H.sec[LSEC_OBJECTS].count != (uint64_t)P.n_objects + P.n_lights || H.sec[LSEC_LIGHTS].count != P.n_lights) { why = "object / light counts disagree with sections"; return false; }
+    if (P.camera.res_x == 0 || P.camera.res_y == 0) { why = "camera resolution is zero"; return false; }
+    // index ranges (a malformed blob must not make a kernel read out of bounds)
+    const LumoObject* objs = (const LumoObject*)(b + H.sec[LSEC_OBJECTS].offset);
+    for (uint64_t i = 0; i < H.sec[LSEC_OBJECTS].count; i++) {
+        const LumoObject& o = objs[i];
+        const uint64_t lim = (o.kind == LOBJ_KD || o.kind == LOBJ_RECT) ? H.sec[LSEC_KD_TREES].count : (o.kind == LOBJ_SPHERE ? H.sec[LSEC_SPHERES].count : H.sec[LSEC_TRI_VERTS].count);
+        if (o.kind > LOBJ_TRI || o.geom >= lim || o.inst >= (int64_t)H.sec[LSEC_INSTANCES].count || o.material < 0 || (uint64_t)o.material >= H.sec[LSEC_MATERIALS].count ||
+            (o.kind == LOBJ_RECT && o.rect >= H.sec[LSEC_RECTS].count)) { why = "object record " + std::to_string(i) + " out of range"; return false; }
+    }
+    const LumoKdTree* kds = (const LumoKdTree*)(b + H.sec[LSEC_KD_TREES].offset);
+    for (uint64_t i = 0; i < H.sec[LSEC_KD_TREES].count; i++)
+        if (kds[i].root >= H.sec[LSEC_KD_NODES].count || (uint64_t)kds[i].tri_base + kds[i].n_tris > H.sec[LSEC_TRI_VERTS].count) { why = "kd tree record out of range"; return false; }
+    const LumoKdNode* kn = (const LumoKdNode*)(b + H.sec[LSEC_KD_NODES].offset);
+    for (uint64_t i = 0; i < H.sec[LSEC_KD_NODES].count; i++) {
+        if (kn[i].b & 0x80000000u) { if ((uint64_t)kn[i].a + (kn[i].b & 0x7FFFFFFFu) > H.sec[LSEC_KD_LEAF].count) { why = "kd leaf range out of bounds"; return false; } }
+        else if (kn[i].b > 2 || kn[i].a >= H.sec[LSEC_KD_NODES].count || i + 1 >= H.sec[LSEC_KD_NODES].count) { why = "kd inner node out of bounds"; return false; }
+    }
+    const LumoTlasNode* tn = (const LumoTlasNode*)(b + H.sec[LSEC_TLAS_NODES].offset);
+    if (P.lights_root >= H.sec[LSEC_TLAS_NODES].count) { why = "lights_root out of range"; return false; }
+    for (uint64_t i = 0; i < H.sec[LSEC_TLAS_NODES].count; i++)
+        if ((uint64_t)tn[i].first + tn[i].count > H.sec[LSEC_TLAS_LEAF].count) { why = "TLAS leaf range out of bounds"; return false; }
+    const LumoMaterial* mats = (const LumoMaterial*)(b + H.sec[LSEC_MATERIALS].offset);
+    for (uint64_t i = 0; i < H.sec[LSEC_MATERIALS].count; i++)
+        if (mats[i].eta_table >= H.sec[LSEC_TABLES].count || mats[i].k_table >= H.sec[LSEC_TABLES].count || mats[i].illum_table >= H.sec[LSEC_TABLES].count) { why = "material table index out of range"; return false; }
+    return true;
+}
+
+extern "C" int32_t lumo_gpu_scene_upload(lumo_ctx* ctx, const void* blob, uint64_t len, lumo_scene** out) {
+    if (!ctx || !blob || !out) return fail(LUMO_ERR_INVALID, "scene_upload: null pointer");
+    LumoBlobHeader H; std::string why;
+    if (!validate_blob((const uint8_t*)blob, len, H, why)) return fail(LUMO_ERR_INVALID, "scene_upload: " + why);
+    CU(cudaSetDevice(ctx->device));
+    lumo_scene* sc = new (std::nothrow) lumo_scene();
+    if (!sc) return fail(LUMO_ERR_OOM, "scene_upload: out of host memory");
+    sc->ctx = ctx; sc->len = len; sc->H = H;
+    cudaError_t e = cudaMalloc((void**)&sc->d_blob, len);
+    if (e != cudaSuccess) { delete sc; return fail(LUMO_ERR_OOM, std::string("scene_upload: cudaMalloc: ") + cudaGetErrorString(e)); }
+    e = cudaMemcpyAsync(sc->d_blob, blob, len, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { cudaFree(sc->d_blob); delete sc; return fail(LUMO_ERR_CUDA, std::string("scene_upload: copy: ") + cudaGetErrorString(e)); }
+    DevScene& S = sc->S;
+    auto at = [&](int s) { return sc->d_blob + H.sec[s].offset; };
+    S.tlas = (const LumoTlasNode*)at(LSEC_TLAS_NODES); S.tlas_leaf = (const uint32_t*)at(LSEC_TLAS_LEAF);
+    S.objects = (const LumoObject*)at(LSEC_OBJECTS); S.instances = (const LumoInstance*)at(LSEC_INSTANCES);
+    S.kd_trees = (const LumoKdTree*)at(LSEC_KD_TREES); S.kd_nodes = (const LumoKdNode*)at(LSEC_KD_NODES); S.kd_leaf = (const uint32_t*)at(LSEC_KD_LEAF);
+    S.tri_verts = (const LumoTriVerts*)at(LSEC_TRI_VERTS); S.tri_shade = (const LumoTriShade*)at(LSEC_TRI_SHADE);
+    S.normals = (const double*)at(LSEC_NORMALS); S.uvs = (const double*)at(LSEC_UVS);
+    S.rects = (const LumoRect*)at(LSEC_RECTS); S.spheres = (const LumoSphere*)at(LSEC_SPHERES);
+    S.materials = (const LumoMaterial*)at(LSEC_MATERIALS); S.tables = (const double*)at(LSEC_TABLES); S.lights = (const LumoLight*)at(LSEC_LIGHTS);
+    S.P = H.params;
+    *out = sc; return LUMO_OK;
+}
+extern "C" int32_t lumo_gpu_scene_destroy(lumo_scene* sc) {
+    if (!sc) return LUMO_OK;
+    cudaSetDevice(sc->ctx->device);
+    cudaFree(sc->d_blob);
+    delete sc; return LUMO_OK;
+}
+
+// ---- ray batches -----------------------------------------------------------------------------------
+static int trace_grid(const lumo_ctx* ctx) { return ctx->sm_count * 8; }
+
+template <int MODE>
+static int32_t launch_batch(lumo_scene* sc, const double* o_dev, const double* d_dev, const double* tmax_dev, uint64_t n, unsigned long long* next_dev,
+                            uint32_t* obj, uint32_t* tri, double* t, double* bary, uint8_t* occ) {
+    lumo_ctx* ctx = sc->ctx;
+    CU(cudaMemsetAsync(next_dev, 0, 8, ctx->stream));
+    if (ctx->count_visits) k_trace_batch<MODE, true><<<trace_grid(ctx), 128, 0, ctx->stream>>>(sc->S, o_dev, d_dev, tmax_dev, n, next_dev, obj, tri, t, bary, occ, ctx->d_visit);
+    else k_trace_batch<MODE, false><<<trace_grid(ctx), 128, 0, ctx->stream>>>(sc->S, o_dev, d_dev, tmax_dev, n, next_dev, obj, tri, t, bary, occ, nullptr);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return LUMO_OK;
+}
+
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t n) { return cudaMalloc(&p, n ? n : 16); }
+    template <class T> T* as() { return (T*)p; }
+};
+
+template <int MODE>
+static int32_t trace_host(lumo_scene* sc, const double* o, const double* d, const double* t_max, uint64_t n, uint32_t* obj, uint32_t* tri, double* t, double* bary, uint8_t* occ) {
+    if (!sc || !o || !d) return fail(LUMO_ERR_INVALID, "trace: null pointer");
+    if (MODE == 0 && (!obj || !tri || !t || !bary)) return fail(LUMO_ERR_INVALID, "trace_closest: null output");
+    if (MODE == 1 && (!occ || !t_max)) return fail(LUMO_ERR_INVALID, "trace_any: null t_max / output");
+    if (MODE == 2 && !t) return fail(LUMO_ERR_INVALID, "trace_first_found: null output");
+    if (n == 0) return LUMO_OK;
+    lumo_ctx* ctx = sc->ctx;
+    CU(cudaSetDevice(ctx->device));
+    DevBuf bo, bd, bt, bobj, btri, btt, bbary, bocc, bnext;
+    CU(bo.alloc(n * 24)); CU(bd.alloc(n * 24)); CU(bnext.alloc(8));
+    if (t_max) CU(bt.alloc(n * 8));
+    if (MODE == 0) { CU(bobj.alloc(n * 4)); CU(btri.alloc(n * 4)); CU(bbary.alloc(n * 16)); }
+    if (MODE != 1) CU(btt.alloc(n * 8)); else CU(bocc.alloc(n));
+    cudaStream_t st = ctx->stream;
+    CU(cudaMemcpyAsync(bo.p, o, n * 24, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(bd.p, d, n * 24, cudaMemcpyHostToDevice, st));
+    if (t_max) CU(cudaMemcpyAsync(bt.p, t_max, n * 8, cudaMemcpyHostToDevice, st));
+    int32_t rc = launch_batch<MODE>(sc, bo.as<double>(), bd.as<double>(), t_max ? bt.as<double>() : nullptr, n, bnext.as<unsigned long long>(),
+                                    bobj.as<uint32_t>(), btri.as<uint32_t>(), btt.as<double>(), bbary.as<double>(), bocc.as<uint8_t>());
+    if (rc != LUMO_OK) return rc;
+    if (MODE == 0) {
+        CU(cudaMemcpyAsync(obj, bobj.p, n * 4, cudaMemcpyDeviceToHost, st)); CU(cudaMemcpyAsync(tri, btri.p, n * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(bary, bbary.p, n * 16, cudaMemcpyDeviceToHost, st));
+    }
+    if (MODE != 1) CU(cudaMemcpyAsync(t, btt.p, n * 8, cudaMemcpyDeviceToHost, st)); else CU(cudaMemcpyAsync(occ, bocc.p, n, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return LUMO_OK;
+}
+
+extern "C" int32_t lumo_gpu_trace_closest(lumo_scene* sc, const double* o, const double* d, const double* t_max, uint64_t n, uint32_t* obj, uint32_t* tri, double* t, double* bary) {
+    return trace_host<0>(sc, o, d, t_max, n, obj, tri, t, bary, nullptr);
+}
+extern "C" int32_t lumo_gpu_trace_any(lumo_scene* sc, const double* o, const double* d, const double* t_max, uint64_t n, uint8_t* occluded) {
+    return trace_host<1>(sc, o, d, t_max, n, nullptr, nullptr, nullptr, nullptr, occluded);
+}
+extern "C" int32_t lumo_gpu_trace_first_found(lumo_scene* sc, const double* o, const double* d, uint64_t n, double* t) {
+    return trace_host<2>(sc, o, d, nullptr, n, nullptr, nullptr, t, nullptr, nullptr);
+}
+extern "C" int32_t lumo_gpu_trace_closest_dev(lumo_scene* sc, const double* o_dev, const double* d_dev, uint64_t n, uint32_t* obj_dev, uint32_t* tri_dev, double* t_dev,
+                                              double* bary_dev, float* kernel_ms) {
+    if (!sc || !o_dev || !d_dev || !obj_dev || !tri_dev || !t_dev || !bary_dev) return fail(LUMO_ERR_INVALID, "trace_closest_dev: null pointer");
+    lumo_ctx* ctx = sc->ctx;
+    CU(cudaSetDevice(ctx->device));
+    DevBuf bnext; CU(bnext.alloc(8));
+    CU(cudaEventRecord(ctx->ev0, ctx->stream));
+    int32_t rc = launch_batch<0>(sc, o_dev, d_dev, nullptr, n, bnext.as<unsigned long long>(), obj_dev, tri_dev, t_dev, bary_dev, nullptr);
+    if (rc != LUMO_OK) return rc;
+    CU(cudaEventRecord(ctx->ev1, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (kernel_ms) CU(cudaEventElapsedTime(kernel_ms, ctx->ev0, ctx->ev1));
+    return LUMO_OK;
+}
+
+// ---- render ----------------------------------------------------------------------------------------
+struct Carver {   // carves 256-byte aligned arrays out of one allocation
+    uint8_t* base; size_t off = 0;
+    template <class T> T* take(size_t n) { T* p = base ? (T*)(base + off) : nullptr; off = (off + n * sizeof(T) + 255) & ~(size_t)255; return p; }
+};
+static void carve_wave(Wave& W, Carver& c, uint32_t N, uint32_t shadow_cap, uint32_t n_tiles, size_t film_px) {
+    W.n_slots = N; W.shadow_cap = shadow_cap;
+    W.ox = c.take<double>(N); W.oy = c.take<double>(N); W.oz = c.take<double>(N); W.dx = c.take<double>(N); W.dy = c.take<double>(N); W.dz = c.take<double>(N);
+    W.ht = c.take<double>(N); W.hb0 = c.take<double>(N); W.hb1 = c.take<double>(N); W.hb2 = c.take<double>(N); W.hobj = c.take<uint32_t>(N); W.htri = c.take<uint32_t>(N);
+    W.gathered = c.take<double>(4 * (size_t)N); W.radiance = c.take<double>(4 * (size_t)N); W.lam = c.take<double>(4 * (size_t)N);
+    W.rx = c.take<double>(N); W.ry = c.take<double>(N);
+    W.pixel = c.take<uint32_t>(N); W.sample = c.take<uint32_t>(N); W.depth = c.take<uint32_t>(N); W.draws = c.take<uint32_t>(N); W.flags = c.take<uint32_t>(N); W.witem = c.take<uint32_t>(N);
+    W.active = c.take<uint32_t>(N);
+    const size_t C = shadow_cap;
+    W.sox = c.take<double>(C); W.soy = c.take<double>(C); W.soz = c.take<double>(C); W.sdx = c.take<double>(C); W.sdy = c.take<double>(C); W.sdz = c.take<double>(C);
+    W.stmax = c.take<double>(C); W.sc = c.take<double>(4 * C); W.sslot = c.take<uint32_t>(C);
+    W.it = c.take<IterCounters>(1); W.run = c.take<RunCounters>(1);
+    W.tile_delta = c.take<double>(n_tiles);
+    W.pilot_lum = c.take<double>((size_t)n_tiles * LUMO_PILOT_N); W.pilot_cost = c.take<uint32_t>((size_t)n_tiles * LUMO_PILOT_N);
+    (void)film_px;
+}
+
+struct HostCounters { IterCounters it; RunCounters run; };
+
+// Runs waves until the work counter is exhausted and no path is alive.
+static int32_t run_wave(lumo_scene* sc, const Wave& W, const WaveParams& P, uint64_t& iterations) {
+    lumo_ctx* ctx = sc->ctx;
+    cudaStream_t st = ctx->stream;
+    HostCounters* hc = (HostCounters*)ctx->host_pinned;
+    const int tgrid = trace_grid(ctx);
+    const int rgrid = (int)std::min<uint64_t>((W.n_slots + 255) / 256, (uint64_t)ctx->sm_count * 16);
+    const int sgrid = ctx->sm_count * 16;
+    CU(cudaMemsetAsync(W.flags, 0, (size_t)W.n_slots * 4, st));
+    CU(cudaMemsetAsync(&W.run->next_work, 0, 8, st));
+    for (;;) {
+        CU(cudaMemsetAsync(W.it, 0, sizeof(IterCounters), st));
+        k_regen<<<rgrid, 256, 0, st>>>(sc->S, W, P);
+        if (ctx->count_visits) k_wave_trace<true><<<tgrid, 128, 0, st>>>(sc->S, W, ctx->d_visit); else k_wave_trace<false><<<tgrid, 128, 0, st>>>(sc->S, W, nullptr);
+        k_wave_shade<<<sgrid, 128, 0, st>>>(sc->S, W, P);
+        if (ctx->count_visits) k_wave_occlude<true><<<tgrid, 128, 0, st>>>(sc->S, W, ctx->d_visit); else k_wave_occlude<false><<<tgrid, 128, 0, st>>>(sc->S, W, nullptr);
+        ctx->launches += 4; iterations++;
+        CU(cudaMemcpyAsync(hc, W.it, sizeof(IterCounters), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        CU(cudaGetLastError());
+        if (hc->it.n_active == 0) break;
+    }
+    // the last regen found nothing alive: every finished path has been retired into the film
+    return LUMO_OK;
+}
+
+static int32_t render_impl(lumo_scene* sc, const lumo_render_params* rp, double* pixels_dev, double* splats_dev, uint64_t* counters, double* tile_deltas_host, double* device_ms) {
+    lumo_ctx* ctx = sc->ctx;
+    const LumoSceneParams& SP = sc->S.P;
+    if (rp->integrator < 0 || rp->integrator > 2) return fail(LUMO_ERR_INVALID, "render: unknown integrator");
+    if (rp->integrator == LUMO_BD_PATH_TRACE) return fail(LUMO_ERR_UNSUPPORTED, "render: bidirectional path tracing is not implemented on the device yet");
+    if (rp->sampler < 0 || rp->sampler > 2) return fail(LUMO_ERR_INVALID, "render: unknown sampler");
+    if (rp->tone_map < 0 || rp->tone_map > 2) return fail(LUMO_ERR_INVALID, "render: unknown tone map");
+    if (rp->spp_end < rp->spp_begin || rp->spp_end > rp->total_spp || rp->total_spp == 0) return fail(LUMO_ERR_INVALID, "render: bad sample range");
+    if (!(rp->rr_delta >= 0.0)) return fail(LUMO_ERR_INVALID, "render: rr_delta must be >= 0");
+    const uint32_t Wd = SP.camera.res_x, Hd = SP.camera.res_y;
+    const uint32_t tiles_x = (Wd + 15) / 16, tiles_y = (Hd + 15) / 16, n_tiles = tiles_x * tiles_y;
+    const size_t film_px = (size_t)Wd * Hd;
+    const uint32_t spp = rp->spp_end - rp->spp_begin;
+    const unsigned long long main_work = (unsigned long long)n_tiles * 256ull * spp;
+    uint32_t N = rp->wave_paths ? rp->wave_paths : (1u << 20);
+    N = (uint32_t)std::min<unsigned long long>(N, std::max<unsigned long long>(main_work, (unsigned long long)n_tiles * LUMO_PILOT_N));
+    N = std::max(N, 1024u);
+    const uint32_t per_path = 2u * SP.n_shadow_rays;
+    const uint32_t shadow_cap = (uint32_t)std::min<unsigned long long>((unsigned long long)N * per_path, 0xFFFFFF00ull);
+    Wave W; std::memset(&W, 0, sizeof W);
+    { Carver dry{nullptr}; carve_wave(W, dry, N, shadow_cap, n_tiles, film_px);
+      if (dry.off > ctx->wave_bytes) {
+          if (ctx->wave_mem) { cudaFree(ctx->wave_mem); ctx->wave_mem = nullptr; ctx->wave_bytes = 0; }
+          CU(cudaMalloc(&ctx->wave_mem, dry.off)); ctx->wave_bytes = dry.off;
+      } }
+    Carver c{(uint8_t*)ctx->wave_mem}; carve_wave(W, c, N, shadow_cap, n_tiles, film_px);
+    W.pixels = pixels_dev; W.splats = splats_dev;
+    cudaStream_t st = ctx->stream;
+    const unsigned long long launches0 = ctx->launches;
+    CU(cudaEventRecord(ctx->ev0, st));
+    CU(cudaMemsetAsync(pixels_dev, 0, film_px * 32, st));
+    CU(cudaMemsetAsync(splats_dev, 0, film_px * 24, st));
+    CU(cudaMemsetAsync(W.run, 0, sizeof(RunCounters), st));
+    k_fill<<<64, 256, 0, st>>>(W.tile_delta, n_tiles, rp->rr_delta > 0.0 ? rp->rr_delta : 1e-5);
+    ctx->launches++;
+    WaveParams P; std::memset(&P, 0, sizeof P);
+    P.seed = rp->seed; P.integrator = (uint32_t)rp->integrator; P.sampler = (uint32_t)rp->sampler; P.tone_map = (uint32_t)rp->tone_map; P.tone_map_arg = rp->tone_map_arg;
+    P.spp_begin = rp->spp_begin; P.spp_count = spp; P.total_spp = rp->total_spp; P.tiles_x = tiles_x; P.tiles_y = tiles_y;
+    uint64_t iterations = 0;
+    if (rp->rr_delta <= 0.0 && rp->integrator != LUMO_DIRECT_LIGHT) {
+        // Per-tile Russian-roulette threshold (the role of task.rs:42-53): two pilot rounds, the second
+        // using the first round's estimate.  Pilot paths never touch the film or the reported counters.
+        DevBuf nd; CU(nd.alloc((size_t)n_tiles * 8));
+        for (uint32_t round = 0; round < 2; round++) {
+            P.mode = WM_PILOT; P.pilot_round = round; P.total_work = (unsigned long long)n_tiles * LUMO_PILOT_N;
+            int32_t rc = run_wave(sc, W, P, iterations); if (rc != LUMO_OK) return rc;
+            k_pilot_reduce<<<(n_tiles + 127) / 128, 128, 0, st>>>(W, n_tiles, nd.as<double>());
+            ctx->launches++;
+            CU(cudaMemcpyAsync(W.tile_delta, nd.p, (size_t)n_tiles * 8, cudaMemcpyDeviceToDevice, st));
+        }
+        CU(cudaStreamSynchronize(st));
+        CU(cudaMemsetAsync(W.run, 0, sizeof(RunCounters), st));
+    }
+    P.mode = WM_MAIN; P.total_work = main_work;
+    if (spp > 0) { int32_t rc = run_wave(sc, W, P, iterations); if (rc != LUMO_OK) return rc; }
+    CU(cudaEventRecord(ctx->ev1, st));
+    HostCounters* hc = (HostCounters*)ctx->host_pinned;
+    CU(cudaMemcpyAsync(&hc->run, W.run, sizeof(RunCounters), cudaMemcpyDeviceToHost, st));
+    if (tile_deltas_host) CU(cudaMemcpyAsync(tile_deltas_host, W.tile_delta, (size_t)n_tiles * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (hc->run.shadow_dropped) return fail(LUMO_ERR_CUDA, "render: shadow queue overflow (internal sizing error)");
+    float ms = 0; CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    if (device_ms) *device_ms = ms;
+    if (counters) {
+        counters[0] = hc->run.camera_paths; counters[1] = hc->run.closest; counters[2] = hc->run.occlusion; counters[3] = hc->run.cost;
+        counters[4] = ctx->launches - launches0; counters[5] = hc->run.max_depth; counters[6] = iterations; counters[7] = hc->run.nonfinite;
+    }
+    return LUMO_OK;
+}
+
+extern "C" int32_t lumo_gpu_render(lumo_scene* sc, const lumo_render_params* rp, lumo_film_accum* out) {
+    if (!sc || !rp || !out || !out->pixels || !out->splats) return fail(LUMO_ERR_INVALID, "render: null pointer");
+    lumo_ctx* ctx = sc->ctx;
+    CU(cudaSetDevice(ctx->device));
+    const size_t film_px = (size_t)sc->S.P.camera.res_x * sc->S.P.camera.res_y;
+    DevBuf px, sp; CU(px.alloc(film_px * 32)); CU(sp.alloc(film_px * 24));
+    int32_t rc = render_impl(sc, rp, px.as<double>(), sp.as<double>(), out->counters, out->tile_deltas, &out->device_ms);
+    if (rc != LUMO_OK) return rc;
+    CU(cudaMemcpyAsync(out->pixels, px.p, film_px * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(out->splats, sp.p, film_px * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return LUMO_OK;
+}
+extern "C" int32_t lumo_gpu_render_dev(lumo_scene* sc, const lumo_render_params* rp, double* pixels_dev, double* splats_dev, uint64_t* counters8, double* device_ms) {
+    if (!sc || !rp || !pixels_dev || !splats_dev) return fail(LUMO_ERR_INVALID, "render_dev: null pointer");
+    CU(cudaSetDevice(sc->ctx->device));
+    return render_impl(sc, rp, pixels_dev, splats_dev, counters8, nullptr, device_ms);
+}

@@ -165,7 +165,7 @@ __device__ __forceinline__ D3 propagate_fp_err(const LumoInstance* I, D3 xo, D3 
 // (rectangle.rs:73-85) and Instance::hit's world transform (instance.rs:84-99).
 __device__ __forceinline__ DevHit reconstruct_hit(const DevScene& S, const Ray& r, const HitRec& rec) {
     const LumoObject o = S.objects[rec.obj];
-    const Ray l = to_local(S, o, r);
+    const Ray l = to_local<false>(S, o, r, nullptr);
     DevHit h; h.t = rec.t; h.material = o.material;
     if (o.kind == LOBJ_SPHERE) {
         const double radius = S.spheres[o.geom].radius;
@@ -642,7 +642,7 @@ __device__ __forceinline__ DevHit light_sample_on(const DevScene& S, const LumoO
 // light.hit(r, 0, INF) for one light object: Object::hit + Hit reconstruction
 __device__ __forceinline__ bool light_hit(const DevScene& S, uint32_t obj_index, const Ray& r, DevHit& out) {
     HitRec rec;
-    if (!object_hit(S, S.objects[obj_index], r, 0.0, LUMO_INF, rec)) return false;
+    if (!object_hit<false>(S, S.objects[obj_index], r, 0.0, LUMO_INF, rec, nullptr)) return false;
     rec.obj = obj_index;
     out = reconstruct_hit(S, r, rec);
     return true;

@@ -67,6 +67,11 @@ __device__ __forceinline__ RayTri ray_tri_setup(const Ray& r) {
 
 struct TriHit { double t; D3 bary; };
 
+// Visit counters of one thread (same sites as the oracle's: SURVEY §8d byte formula).  Compiled in
+// only for CNT=true instantiations (the untimed counting pass of bench.py and the parity tests).
+struct Counters { unsigned long long tlas, inst, kd, leaf, tri, sphere; };
+#define LUMO_CNT(field) do { if (CNT) c->field++; } while (0)
+
 // 80-byte triangle record as five 16-byte loads through the read-only path
 __device__ __forceinline__ void load_tri(const LumoTriVerts* tv, D3& a, D3& b, D3& c) {
     const double2* p = reinterpret_cast<const double2*>(tv);
@@ -76,8 +81,9 @@ __device__ __forceinline__ void load_tri(const LumoTriVerts* tv, D3& a, D3& b, D
 
 // Triangle::_hit<GEO> (triangle.rs:63-187).  GEO=false: distance only; GEO=true adds the
 // conservative delta_t rejection and the barycentrics.
-template <bool GEO>
-__device__ __forceinline__ bool tri_hit(const LumoTriVerts* tv, const Ray& r, const RayTri& q, double t_min, double t_max, TriHit& out) {
+template <bool GEO, bool CNT>
+__device__ __forceinline__ bool tri_hit(const LumoTriVerts* tv, const Ray& r, const RayTri& q, double t_min, double t_max, TriHit& out, Counters* c) {
+    LUMO_CNT(tri);
     D3 A, B, C; load_tri(tv, A, B, C);
     D3 at = permute(A - r.o, q.kz), bt = permute(B - r.o, q.kz), ct = permute(C - r.o, q.kz);
     at = d3(at.x + q.sx * at.z, at.y + q.sy * at.z, at.z + q.sz * at.z);
@@ -118,17 +124,15 @@ __device__ __forceinline__ void box_intersect(const double* lo, const double* hi
     t_end = min_element(te) * (1.0 + 2.0 * gamma_n(3));
 }
 
-struct Counters { unsigned long long tlas, inst, kd, leaf, tri; };
-
 // KdTree::_hit<GEO> (kdtree.rs:101-169).
 // GEO=false: returns the distance of the first triangle found with t < t_end (any-hit), INF if none.
 // GEO=true : closest triangle by the reference's rules, then the full test of the winner
 //            (kdtree.rs:165) — returns false if that fails.
 struct KdStackEntry { uint32_t node; double t_start, t_end; };
 
-template <bool GEO>
+template <bool GEO, bool CNT>
 __device__ __forceinline__ bool kd_hit(const DevScene& S, const LumoKdTree* tree, const Ray& r, double t_min, double t_max,
-                                       double& t_out, uint32_t& tri_out, D3& bary_out) {
+                                       double& t_out, uint32_t& tri_out, D3& bary_out, Counters* c) {
     const RayTri q = ray_tri_setup(r);
     const D3 inv = d3(1.0 / r.d.x, 1.0 / r.d.y, 1.0 / r.d.z);
     KdStackEntry stack[64];
@@ -142,6 +146,7 @@ __device__ __forceinline__ bool kd_hit(const DevScene& S, const LumoKdTree* tree
     const LumoTriVerts* tris = S.tri_verts + tree->tri_base;
     while (true) {
         if (t_hit < t_start) break;
+        LUMO_CNT(kd);
         // 16-byte node: one vector load
         const double2 raw = __ldg(reinterpret_cast<const double2*>(S.kd_nodes + curr));
         const double point = raw.x;
@@ -151,8 +156,9 @@ __device__ __forceinline__ bool kd_hit(const DevScene& S, const LumoKdTree* tree
             const uint32_t count = nb & 0x7FFFFFFFu;
             for (uint32_t k = 0; k < count; k++) {
                 const uint32_t i = __ldg(S.kd_leaf + na + k);
+                LUMO_CNT(leaf);
                 TriHit th;
-                const double t = tri_hit<false>(tris + i, r, q, t_min, t_end, th) ? th.t : LUMO_INF;
+                const double t = tri_hit<false, CNT>(tris + i, r, q, t_min, t_end, th, c) ? th.t : LUMO_INF;
                 if (GEO) { if (t < t_end) { t_end = t; t_hit = t; idx = i; } }
                 else { if (t < t_end) { t_out = t; return true; } }
             }
@@ -179,7 +185,7 @@ __device__ __forceinline__ bool kd_hit(const DevScene& S, const LumoKdTree* tree
     if (!GEO) { t_out = LUMO_INF; return false; }
     if (idx == LUMO_NONE) return false;
     TriHit th;
-    if (!tri_hit<true>(tris + idx, r, q, t_min, t_max, th)) return false;
+    if (!tri_hit<true, CNT>(tris + idx, r, q, t_min, t_max, th, c)) return false;
     t_out = th.t; tri_out = idx; bary_out = th.bary;
     return true;
 }
@@ -197,8 +203,10 @@ __device__ __forceinline__ D3 xf_dir(const double* m, D3 v) {
               m[4] * v.x + m[5] * v.y + m[6] * v.z + m[7] * 0.0,
               m[8] * v.x + m[9] * v.y + m[10] * v.z + m[11] * 0.0);
 }
-__device__ __forceinline__ Ray to_local(const DevScene& S, const LumoObject& o, const Ray& r) {
+template <bool CNT>
+__device__ __forceinline__ Ray to_local(const DevScene& S, const LumoObject& o, const Ray& r, Counters* c) {
     if (o.inst < 0) return r;
+    LUMO_CNT(inst);
     const LumoInstance* I = S.instances + o.inst;
     Ray l; l.o = xf_point(I->inv, r.o); l.d = xf_dir(I->inv, r.d);
     return l;
@@ -278,18 +286,19 @@ __device__ __forceinline__ double sphere_hit(double radius, const Ray& r, double
 }
 
 // Object::hit_t for one object record (what the BVH leaf loop calls, bvh.rs:346)
-__device__ __forceinline__ double object_hit_t(const DevScene& S, const LumoObject& o, const Ray& r, double t_min, double t_max) {
-    const Ray l = to_local(S, o, r);
+template <bool CNT>
+__device__ __forceinline__ double object_hit_t(const DevScene& S, const LumoObject& o, const Ray& r, double t_min, double t_max, Counters* c) {
+    const Ray l = to_local<CNT>(S, o, r, c);
     switch (o.kind) {
     case LOBJ_KD: case LOBJ_RECT: {
         double t; uint32_t tri; D3 bary;
-        return kd_hit<false>(S, S.kd_trees + o.geom, l, t_min, t_max, t, tri, bary) ? t : LUMO_INF;
+        return kd_hit<false, CNT>(S, S.kd_trees + o.geom, l, t_min, t_max, t, tri, bary, c) ? t : LUMO_INF;
     }
-    case LOBJ_SPHERE: return sphere_hit_t(S.spheres[o.geom].radius, l, t_min, t_max);
+    case LOBJ_SPHERE: LUMO_CNT(sphere); return sphere_hit_t(S.spheres[o.geom].radius, l, t_min, t_max);
     default: {
         const RayTri q = ray_tri_setup(l);
         TriHit th;
-        return tri_hit<false>(S.tri_verts + o.geom, l, q, t_min, t_max, th) ? th.t : LUMO_INF;
+        return tri_hit<false, CNT>(S.tri_verts + o.geom, l, q, t_min, t_max, th, c) ? th.t : LUMO_INF;
     }
     }
 }
@@ -298,12 +307,14 @@ struct HitRec { double t; D3 bary; uint32_t obj, tri; };
 
 // Object::hit for one object record: distance + which triangle + barycentrics (the rest of `Hit`
 // is rebuilt from these by the shading kernels, shade.cuh reconstruct_hit).
-__device__ __forceinline__ bool object_hit(const DevScene& S, const LumoObject& o, const Ray& r, double t_min, double t_max, HitRec& h) {
-    const Ray l = to_local(S, o, r);
+template <bool CNT>
+__device__ __forceinline__ bool object_hit(const DevScene& S, const LumoObject& o, const Ray& r, double t_min, double t_max, HitRec& h, Counters* c) {
+    const Ray l = to_local<CNT>(S, o, r, c);
     switch (o.kind) {
     case LOBJ_KD: case LOBJ_RECT:
-        return kd_hit<true>(S, S.kd_trees + o.geom, l, t_min, t_max, h.t, h.tri, h.bary);
+        return kd_hit<true, CNT>(S, S.kd_trees + o.geom, l, t_min, t_max, h.t, h.tri, h.bary, c);
     case LOBJ_SPHERE: {
+        LUMO_CNT(sphere);
         double t = sphere_hit(S.spheres[o.geom].radius, l, t_min, t_max);
         if (!(t < LUMO_INF)) return false;
         h.t = t; h.tri = 0; h.bary = d3(0, 0, 0);
@@ -312,7 +323,7 @@ __device__ __forceinline__ bool object_hit(const DevScene& S, const LumoObject& 
     default: {
         const RayTri q = ray_tri_setup(l);
         TriHit th;
-        if (!tri_hit<true>(S.tri_verts + o.geom, l, q, t_min, t_max, th)) return false;
+        if (!tri_hit<true, CNT>(S.tri_verts + o.geom, l, q, t_min, t_max, th, c)) return false;
         h.t = th.t; h.tri = 0; h.bary = th.bary;
         return true;
     }
@@ -321,8 +332,8 @@ __device__ __forceinline__ bool object_hit(const DevScene& S, const LumoObject& 
 
 // BVH::_hit<GEO> (bvh.rs:315-362) over one of the two object BVHs.  obj_base = first object
 // record of this BVH (0 for Scene.objects, n_objects for Scene.lights).
-template <bool GEO>
-__device__ __forceinline__ uint32_t tlas_hit(const DevScene& S, uint32_t root, uint32_t obj_base, const Ray& r, double t_min, double t_max) {
+template <bool GEO, bool CNT>
+__device__ __forceinline__ uint32_t tlas_hit(const DevScene& S, uint32_t root, uint32_t obj_base, const Ray& r, double t_min, double t_max, Counters* c) {
     const D3 inv = d3(1.0 / r.d.x, 1.0 / r.d.y, 1.0 / r.d.z);
     uint32_t stack[64];
     int sp = 0;
@@ -330,6 +341,7 @@ __device__ __forceinline__ uint32_t tlas_hit(const DevScene& S, uint32_t root, u
     double tt = t_max;
     while (true) {
         const LumoTlasNode* node = S.tlas + root + curr;
+        LUMO_CNT(tlas);
         double t_start, t_end;
         box_intersect(node->lo, node->hi, r.o, inv, t_start, t_end);
         t_start = fmax(t_start, t_min); t_end = fmin(t_end, tt);
@@ -344,7 +356,7 @@ __device__ __forceinline__ uint32_t tlas_hit(const DevScene& S, uint32_t root, u
             const uint32_t first = node->first;
             for (uint32_t k = 0; k < count; k++) {
                 const uint32_t i = S.tlas_leaf[first + k];
-                const double t = object_hit_t(S, S.objects[obj_base + i], r, t_min, tt);
+                const double t = object_hit_t<CNT>(S, S.objects[obj_base + i], r, t_min, tt, c);
                 if (GEO) { if (t < tt) { tt = t; idx = i; } }
                 else { if (t < tt) return i; }
             }
@@ -356,41 +368,46 @@ __device__ __forceinline__ uint32_t tlas_hit(const DevScene& S, uint32_t root, u
 }
 
 // Object for BVH: hit / hit_t (bvh.rs:365-375)
-__device__ __forceinline__ bool bvh_hit(const DevScene& S, uint32_t root, uint32_t obj_base, const Ray& r, double t_min, double t_max, HitRec& h) {
-    const uint32_t idx = tlas_hit<true>(S, root, obj_base, r, t_min, t_max);
+template <bool CNT>
+__device__ __forceinline__ bool bvh_hit(const DevScene& S, uint32_t root, uint32_t obj_base, const Ray& r, double t_min, double t_max, HitRec& h, Counters* c) {
+    const uint32_t idx = tlas_hit<true, CNT>(S, root, obj_base, r, t_min, t_max, c);
     if (idx == LUMO_NONE) return false;
-    if (!object_hit(S, S.objects[obj_base + idx], r, t_min, t_max, h)) return false;
+    if (!object_hit<CNT>(S, S.objects[obj_base + idx], r, t_min, t_max, h, c)) return false;
     h.obj = obj_base + idx;
     return true;
 }
-__device__ __forceinline__ double bvh_hit_t(const DevScene& S, uint32_t root, uint32_t obj_base, const Ray& r, double t_min, double t_max) {
-    const uint32_t idx = tlas_hit<false>(S, root, obj_base, r, t_min, t_max);
+template <bool CNT>
+__device__ __forceinline__ double bvh_hit_t(const DevScene& S, uint32_t root, uint32_t obj_base, const Ray& r, double t_min, double t_max, Counters* c) {
+    const uint32_t idx = tlas_hit<false, CNT>(S, root, obj_base, r, t_min, t_max, c);
     if (idx == LUMO_NONE) return LUMO_INF;
-    return object_hit_t(S, S.objects[obj_base + idx], r, t_min, t_max);
+    return object_hit_t<CNT>(S, S.objects[obj_base + idx], r, t_min, t_max, c);
 }
 
-// Scene::hit (scene.rs:119-147): objects, then lights with t_max = h.t
-__device__ __forceinline__ bool scene_hit(const DevScene& S, const Ray& r, HitRec& h) {
-    double t_max = LUMO_INF;
-    bool have = bvh_hit(S, 0, 0, r, 0.0, t_max, h);
+// Scene::hit (scene.rs:119-147): objects, then lights with t_max = h.t.  The reference always
+// starts from t_max = +inf; the C ABI lets the caller pass a finite one.
+template <bool CNT>
+__device__ __forceinline__ bool scene_hit(const DevScene& S, const Ray& r, double t_max, HitRec& h, Counters* c) {
+    bool have = bvh_hit<CNT>(S, 0, 0, r, 0.0, t_max, h, c);
     if (have) t_max = h.t;
     if (S.P.n_lights) {
         HitRec hl;
-        if (bvh_hit(S, S.P.lights_root, S.P.n_objects, r, 0.0, t_max, hl)) { h = hl; have = true; }
+        if (bvh_hit<CNT>(S, S.P.lights_root, S.P.n_objects, r, 0.0, t_max, hl, c)) { h = hl; have = true; }
     }
     return have;
 }
 // Scene::hit_t (scene.rs:150-162)
-__device__ __forceinline__ double scene_hit_t(const DevScene& S, const Ray& r) {
+template <bool CNT>
+__device__ __forceinline__ double scene_hit_t(const DevScene& S, const Ray& r, Counters* c) {
     double t = LUMO_INF;
-    t = fmin(t, bvh_hit_t(S, 0, 0, r, 0.0, t));
-    if (S.P.n_lights) t = fmin(t, bvh_hit_t(S, S.P.lights_root, S.P.n_objects, r, 0.0, t));
+    t = fmin(t, bvh_hit_t<CNT>(S, 0, 0, r, 0.0, t, c));
+    if (S.P.n_lights) t = fmin(t, bvh_hit_t<CNT>(S, S.P.lights_root, S.P.n_objects, r, 0.0, t, c));
     return t;
 }
 // the two occlusion tests of Scene::hit_light (scene.rs:180-186)
-__device__ __forceinline__ bool scene_occluded(const DevScene& S, const Ray& r, double t_max) {
-    if (bvh_hit_t(S, 0, 0, r, 0.0, t_max) < t_max) return true;
-    if (S.P.n_lights && bvh_hit_t(S, S.P.lights_root, S.P.n_objects, r, 0.0, t_max) < t_max) return true;
+template <bool CNT>
+__device__ __forceinline__ bool scene_occluded(const DevScene& S, const Ray& r, double t_max, Counters* c) {
+    if (bvh_hit_t<CNT>(S, 0, 0, r, 0.0, t_max, c) < t_max) return true;
+    if (S.P.n_lights && bvh_hit_t<CNT>(S, S.P.lights_root, S.P.n_objects, r, 0.0, t_max, c) < t_max) return true;
     return false;
 }
 

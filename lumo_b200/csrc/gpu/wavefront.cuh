@@ -1,0 +1,381 @@
+// Wavefront pipeline: the GPU replacement of ThreadPool + RenderTaskExecutor::exec
+// (src/pool.rs:10-55, src/renderer/task.rs:25-81) and of the per-sample integrator loops
+// (src/tracer/integrator/path_trace.rs:5-82, direct_light.rs:5-73, integrator.rs:74-184).
+//
+// A wave is N path slots whose state lives in HBM as structure-of-arrays.  One iteration is
+//   regen  : retire finished paths into the film (tone map, XYZ->RGB, filter footprint clamped to
+//            the 16x16 tile, f64 atomics), refill free slots from the global work counter, and
+//            stream-compact the live slots into the active queue;
+//   trace  : Scene::hit for every queued ray (persistent warps pulling 32-ray batches);
+//   shade  : one bounce of the integrator per live path — Hit reconstruction, BSDF sampling, NEE
+//            (light sampling + MIS; occlusion rays are appended to the shadow queue with their
+//            already-weighted contribution), throughput update, Russian roulette;
+//   occlude: Scene::hit_light's occlusion test for every shadow-queue entry; unoccluded
+//            contributions are added to the owning path's radiance.
+// Random numbers are Philox streams keyed by (seed, pixel, global sample index) and consumed in the
+// reference's draw order, so a path is independent of wave size, scheduling and GPU
+// count.
+#pragma once
+#include "shade.cuh"
+#include <cooperative_groups.h>
+
+namespace lumo_dev {
+namespace cg = cooperative_groups;
+
+enum { PF_ALIVE = 1u, PF_LAST_SPECULAR = 2u, PF_DONE = 4u };
+enum { WM_MAIN = 0, WM_PILOT = 1 };
+#define LUMO_RR_DEPTH 5u           /* path_trace.rs:3 */
+#define LUMO_DL_MAX_RECURSION 50u  /* direct_light.rs:6 */
+#define LUMO_PILOT_N 64u
+
+struct IterCounters {   // zeroed before every iteration
+    uint32_t n_active, n_shadow, trace_next, shade_next, occl_next, pad[3];
+};
+struct RunCounters {    // zeroed once per render
+    unsigned long long next_work, camera_paths, closest, occlusion, cost, shadow_queued, shadow_dropped, nonfinite;
+    uint32_t max_depth, pad;
+};
+
+struct Wave {
+    uint32_t n_slots, shadow_cap;
+    // path state (SoA; colour arrays are [k * n_slots + slot])
+    double *ox, *oy, *oz, *dx, *dy, *dz;
+    double *ht, *hb0, *hb1, *hb2; uint32_t *hobj, *htri;
+    double *gathered, *radiance, *lam;
+    double *rx, *ry;
+    uint32_t *pixel, *sample, *depth, *draws, *flags, *witem;
+    uint32_t* active;
+    // shadow queue (SoA)
+    double *sox, *soy, *soz, *sdx, *sdy, *sdz, *stmax, *sc; uint32_t* sslot;
+    IterCounters* it; RunCounters* run;
+    // film + RR thresholds
+    double *pixels, *splats, *tile_delta;
+    double* pilot_lum; uint32_t* pilot_cost;
+};
+
+struct WaveParams {
+    unsigned long long seed, total_work;
+    uint32_t integrator, sampler, tone_map, mode;
+    double tone_map_arg;
+    uint32_t spp_begin, spp_count, total_spp, pilot_round;
+    uint32_t tiles_x, tiles_y, pad0, pad1;
+};
+
+__device__ __forceinline__ uint32_t agg_inc(uint32_t* ctr) {   // warp-aggregated atomicAdd(ctr, 1)
+    cg::coalesced_group g = cg::coalesced_threads();
+    uint32_t base = 0;
+    if (g.thread_rank() == 0) base = atomicAdd(ctr, g.size());
+    return g.shfl(base, 0) + g.thread_rank();
+}
+__device__ __forceinline__ unsigned long long agg_inc64(unsigned long long* ctr) {
+    cg::coalesced_group g = cg::coalesced_threads();
+    unsigned long long base = 0;
+    if (g.thread_rank() == 0) base = atomicAdd(ctr, (unsigned long long)g.size());
+    return g.shfl(base, 0) + g.thread_rank();
+}
+__device__ __forceinline__ uint32_t tile_of(const WaveParams& P, const DevScene& S, uint32_t pixel) {
+    const uint32_t W = S.P.camera.res_x;
+    return ((pixel / W) / 16u) * P.tiles_x + (pixel % W) / 16u;
+}
+__device__ __forceinline__ C4 load_c4(const double* a, uint32_t n, uint32_t slot) { C4 c; for (int k = 0; k < 4; k++) c.s[k] = a[(size_t)k * n + slot]; return c; }
+__device__ __forceinline__ void store_c4(double* a, uint32_t n, uint32_t slot, const C4& c) { for (int k = 0; k < 4; k++) a[(size_t)k * n + slot] = c.s[k]; }
+
+// Intra-pixel offset of sample s (samplers.rs:54-192).  Uniform and Jittered are the reference's
+// formulas; MultiJittered keeps the reference's two-level stratification (samplers.rs:178-189) but
+// the two Fisher-Yates tables become a keyed hash permutation, so that any sample index can be
+// produced independently.
+__device__ __forceinline__ void raster_jitter(const WaveParams& P, uint32_t pixel, uint32_t s, Rng& rng, double& jx, double& jy) {
+    if (P.sampler == 0) { jx = rng_float(rng); jy = rng_float(rng); return; }
+    const unsigned long long total = P.total_spp;
+    const unsigned long long dim = sat_u64(ceil(sqrt((double)total)));
+    const double s0x = 1.0 / (double)dim, s0y = (double)dim / (double)total;
+    const unsigned long long x0 = s % dim, y0 = s / dim;
+    const double o0x = s0x * (double)x0, o0y = s0y * (double)y0;
+    if (P.sampler == 1) { const double a = rng_float(rng), b = rng_float(rng); jx = s0x * a + o0x; jy = s0y * b + o0y; return; }
+    Rng keyr = rng_make(P.seed, pixel, 0xFFFFFFFFu, 1u, 0u);
+    const unsigned long long k = rng_u64(keyr);
+    const uint32_t kx = (uint32_t)k, ky = (uint32_t)(k >> 32);
+    const double s1x = s0x / (double)dim, s1y = s0y / (double)dim;
+    const uint32_t x1 = cmj_permute((uint32_t)y0, (uint32_t)dim, kx), y1 = cmj_permute((uint32_t)x0, (uint32_t)dim, ky);
+    const double o1x = s1x * (double)x1, o1y = s1y * (double)y1;
+    const double a = rng_float(rng), b = rng_float(rng);
+    jx = o0x + o1x + s1x * a; jy = o0y + o1y + s1y * b;
+}
+
+// ---- regen: retire, refill, compact -------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_regen(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P) {
+    const uint32_t N = W.n_slots;
+    for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < N; slot += gridDim.x * blockDim.x) {
+        uint32_t f = W.flags[slot];
+        if (f & PF_DONE) {
+            // RenderTaskExecutor::exec tail (task.rs:64-76)
+            Lam lam; for (int k = 0; k < 4; k++) lam.l[k] = W.lam[(size_t)k * N + slot];
+            const C4 rad = load_c4(W.radiance, N, slot);
+            const uint32_t depth = W.depth[slot];
+            const uint32_t cost = P.integrator == 1 ? depth + 1u : depth;
+            if (P.mode == WM_PILOT) {
+                const uint32_t w = W.witem[slot];
+                W.pilot_lum[w] = luminance(S, rad, lam); W.pilot_cost[w] = cost;
+            } else {
+                bool finite = true;
+                for (int k = 0; k < 4; k++) finite = finite && isfinite(rad.s[k]);
+                if (!finite) atomicAdd(&W.run->nonfinite, 1ull);
+                film_add_sample(S, W.pixels, W.splats, tone_map(S, (int)P.tone_map, P.tone_map_arg, rad, lam), lam, W.rx[slot], W.ry[slot], false);
+                atomicAdd(&W.run->cost, (unsigned long long)cost);
+                atomicAdd(&W.run->camera_paths, 1ull);
+                atomicMax(&W.run->max_depth, depth);
+            }
+            f = 0;
+        }
+        if (!(f & PF_ALIVE)) {
+            bool want = W.run->next_work < P.total_work;   // cheap pre-check; the atomic decides
+            if (want) {
+                const unsigned long long w = agg_inc64(&W.run->next_work);
+                if (w < P.total_work) {
+                    const uint32_t Wd = S.P.camera.res_x, Hd = S.P.camera.res_y;
+                    uint32_t px, py, sample; bool ok = true;
+                    if (P.mode == WM_PILOT) {                       // two pilot rounds of 64 paths per tile estimate the RR threshold
+                        const uint32_t tile = (uint32_t)(w / LUMO_PILOT_N), k = (uint32_t)(w % LUMO_PILOT_N);
+                        const uint32_t x0 = (tile % P.tiles_x) * 16u, y0 = (tile / P.tiles_x) * 16u;
+                        px = min(x0 + 2u * (k % 8u), Wd - 1u); py = min(y0 + 2u * (k / 8u), Hd - 1u);
+                        sample = 0xFFFFFF00u + P.pilot_round;
+                    } else {                                          // sample-major, tile by tile, 8x4 pixel blocks per warp
+                        const unsigned long long per_s = (unsigned long long)P.tiles_x * P.tiles_y * 256ull;
+                        const uint32_t si = (uint32_t)(w / per_s); const unsigned long long r = w % per_s;
+                        const uint32_t tile = (uint32_t)(r / 256ull), q = (uint32_t)(r % 256ull);
+                        const uint32_t blk = q / 32u, in = q % 32u;   // 8 blocks of 8x4 in a 16x16 tile
+                        px = (tile % P.tiles_x) * 16u + (blk % 2u) * 8u + (in % 8u);
+                        py = (tile / P.tiles_x) * 16u + (blk / 2u) * 4u + (in / 8u);
+                        sample = P.spp_begin + si;
+                        ok = px < Wd && py < Hd;
+                    }
+                    if (ok) {
+                        const uint32_t pixel = px + py * Wd;
+                        Rng rng = rng_make(P.seed, pixel, sample, 0u, 0u);
+                        double jx, jy;
+                        if (P.mode == WM_PILOT) { jx = rng_float(rng); jy = rng_float(rng); } else raster_jitter(P, pixel, sample, rng, jx, jy);
+                        const double rx = (double)px + jx, ry = (double)py + jy;
+                        const double l0 = rng_float(rng), l1 = rng_float(rng);                 // integrator.rs:56-57
+                        const Ray r = camera_generate_ray(S.P.camera, rx, ry, l0, l1);
+                        const Lam lam = lam_sample(rng_float(rng));
+                        W.ox[slot] = r.o.x; W.oy[slot] = r.o.y; W.oz[slot] = r.o.z; W.dx[slot] = r.d.x; W.dy[slot] = r.d.y; W.dz[slot] = r.d.z;
+                        for (int k = 0; k < 4; k++) { W.lam[(size_t)k * N + slot] = lam.l[k]; W.gathered[(size_t)k * N + slot] = 1.0; W.radiance[(size_t)k * N + slot] = 0.0; }
+                        W.rx[slot] = rx; W.ry[slot] = ry;
+                        W.pixel[slot] = pixel; W.sample[slot] = sample; W.depth[slot] = 0u; W.draws[slot] = rng.draws; W.witem[slot] = (uint32_t)w;
+                        f = PF_ALIVE | PF_LAST_SPECULAR;
+                    }
+                }
+            }
+        }
+        W.flags[slot] = f;
+        if (f & PF_ALIVE) W.active[agg_inc(&W.it->n_active)] = slot;
+    }
+}
+
+// ---- trace: Scene::hit over the active queue ------------------------------------------------------
+template <bool CNT>
+__global__ void __launch_bounds__(128) k_wave_trace(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, Counters* gc) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n = W.it->n_active;
+    Counters cnt = {0, 0, 0, 0, 0, 0};
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&W.it->trace_next, 32u);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= n) break;
+        const uint32_t i = base + lane;
+        if (i < n) {
+            const uint32_t slot = W.active[i];
+            Ray r; r.o = d3(W.ox[slot], W.oy[slot], W.oz[slot]); r.d = d3(W.dx[slot], W.dy[slot], W.dz[slot]);
+            HitRec h;
+            if (scene_hit<CNT>(S, r, LUMO_INF, h, &cnt)) {
+                W.ht[slot] = h.t; W.hb0[slot] = h.bary.x; W.hb1[slot] = h.bary.y; W.hb2[slot] = h.bary.z; W.hobj[slot] = h.obj; W.htri[slot] = h.tri;
+            } else W.hobj[slot] = LUMO_NONE;
+        }
+    }
+    if (lane == 0 && threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(&W.run->closest, (unsigned long long)n);
+    if (CNT) { atomicAdd(&gc->tlas, cnt.tlas); atomicAdd(&gc->inst, cnt.inst); atomicAdd(&gc->kd, cnt.kd); atomicAdd(&gc->leaf, cnt.leaf); atomicAdd(&gc->tri, cnt.tri); atomicAdd(&gc->sphere, cnt.sphere); }
+}
+
+// ---- occlude: the occlusion half of Scene::hit_light over the shadow queue ------------------------
+template <bool CNT>
+__global__ void __launch_bounds__(128) k_wave_occlude(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, Counters* gc) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n = min(W.it->n_shadow, W.shadow_cap);
+    const uint32_t N = W.n_slots, C = W.shadow_cap;
+    Counters cnt = {0, 0, 0, 0, 0, 0};
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&W.it->occl_next, 32u);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= n) break;
+        const uint32_t i = base + lane;
+        if (i < n) {
+            Ray r; r.o = d3(W.sox[i], W.soy[i], W.soz[i]); r.d = d3(W.sdx[i], W.sdy[i], W.sdz[i]);
+            if (!scene_occluded<CNT>(S, r, W.stmax[i], &cnt)) {
+                const uint32_t slot = W.sslot[i];
+                for (int k = 0; k < 4; k++) { const double v = W.sc[(size_t)k * C + i]; if (v != 0.0) atomicAdd(&W.radiance[(size_t)k * N + slot], v); }
+            }
+        }
+    }
+    if (lane == 0 && threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(&W.run->occlusion, (unsigned long long)n);
+    if (CNT) { atomicAdd(&gc->tlas, cnt.tlas); atomicAdd(&gc->inst, cnt.inst); atomicAdd(&gc->kd, cnt.kd); atomicAdd(&gc->leaf, cnt.leaf); atomicAdd(&gc->tri, cnt.tri); atomicAdd(&gc->sphere, cnt.sphere); }
+}
+
+// ---- shade ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void push_shadow(const Wave& W, uint32_t slot, const Ray& r, double t_max, const C4& c) {
+    const uint32_t i = agg_inc(&W.it->n_shadow);
+    if (i >= W.shadow_cap) { atomicAdd(&W.run->shadow_dropped, 1ull); return; }
+    W.sox[i] = r.o.x; W.soy[i] = r.o.y; W.soz[i] = r.o.z; W.sdx[i] = r.d.x; W.sdy[i] = r.d.y; W.sdz[i] = r.d.z;
+    W.stmax[i] = t_max; W.sslot[i] = slot;
+    for (int k = 0; k < 4; k++) W.sc[(size_t)k * W.shadow_cap + i] = c.s[k];
+}
+// integrator.rs:139-184
+__device__ __forceinline__ C4 mis_sample(const DevScene& S, const Mat& m, D3 wo, D3 wi, const DevHit& ho, const DevHit& hi, const Lam& lam, bool li, double p_lig, double p_sct) {
+    if (p_lig == 0.0 || p_sct == 0.0) return c4(0.0);
+    const C4 bsdf = bsdf_f(S, m, wo, wi, lam, 0, ho);
+    const double denom = p_lig * p_lig + p_sct * p_sct;
+    const double weight = li ? (p_lig * p_lig) / denom : (p_sct * p_sct) / denom;
+    const double p_denom = li ? p_lig : p_sct;
+    return bsdf * c4(1.0) * mat_emit(S, S.materials[hi.material], lam, hi.backface) * shading_cosine(m, wi, ho.ns) * weight / p_denom;
+}
+// integrator.rs:74-137: light pick -> light sample + BSDF sample, MIS-weighted; the occlusion half of
+// hit_light is deferred to k_wave_occlude with the finished contribution attached.
+__device__ __noinline__ void shadow_rays(const DevScene& S, const Wave& W, uint32_t slot, const Mat& m, D3 wo, const C4& gathered, Lam& lam, const DevHit& ho, Rng& rng) {
+    const uint32_t n = S.P.n_shadow_rays;
+    for (uint32_t i = 0; i < n; i++) {
+        const uint32_t li = sample_light(S, rng_float(rng));
+        const double pdf_light = S.lights[li].pdf;
+        const uint32_t lobj = S.P.n_objects + li;
+        const LumoObject lo = S.objects[lobj];
+        {
+            const double r0 = rng_float(rng), r1 = rng_float(rng);
+            const D3 wi = light_sample_towards(S, lo, ho.p, r0, r1);
+            const Ray ri = hit_generate_ray(ho, wi);
+            DevHit hi;
+            if (light_hit(S, lobj, ri, hi)) {
+                const double p_lig = light_sample_towards_pdf(S, lo, ri, hi.p, hi.ng);
+                const double p_sct = bsdf_pdf(S, m, wo, wi, ho, lam, false);
+                const C4 c = mis_sample(S, m, wo, wi, ho, hi, lam, true, p_lig, p_sct);
+                if (!is_black(c)) push_shadow(W, slot, ri, hi.t - LUMO_EPS, gathered * (c / pdf_light) / (double)n);
+            }
+        }
+        const double ru = rng_float(rng), r0 = rng_float(rng), r1 = rng_float(rng);
+        D3 wi;
+        if (bsdf_sample(S, m, wo, ho, lam, ru, r0, r1, wi)) {
+            const Ray ri = hit_generate_ray(ho, wi);
+            DevHit hi;
+            if (light_hit(S, lobj, ri, hi)) {
+                const double p_lig = light_sample_towards_pdf(S, lo, ri, hi.p, hi.ng);
+                const double p_sct = bsdf_pdf(S, m, wo, wi, ho, lam, false);
+                const C4 c = mis_sample(S, m, wo, wi, ho, hi, lam, false, p_lig, p_sct);
+                if (!is_black(c)) push_shadow(W, slot, ri, hi.t - LUMO_EPS, gathered * (c / pdf_light) / (double)n);
+            }
+        }
+    }
+}
+
+// One bounce of path_trace::integrate (path_trace.rs:18-78) or direct_light::integrate
+// (direct_light.rs:14-70) for every live path.
+__global__ void __launch_bounds__(128) k_wave_shade(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P) {
+    const uint32_t N = W.n_slots;
+    const uint32_t n = W.it->n_active;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t slot = W.active[i];
+        uint32_t f = W.flags[slot];
+        if (W.hobj[slot] == LUMO_NONE) { W.flags[slot] = PF_DONE; continue; }
+        Ray ro; ro.o = d3(W.ox[slot], W.oy[slot], W.oz[slot]); ro.d = d3(W.dx[slot], W.dy[slot], W.dz[slot]);
+        HitRec rec; rec.t = W.ht[slot]; rec.bary = d3(W.hb0[slot], W.hb1[slot], W.hb2[slot]); rec.obj = W.hobj[slot]; rec.tri = W.htri[slot];
+        const DevHit ho = reconstruct_hit(S, ro, rec);
+        const Mat& m = S.materials[ho.material];
+        const uint32_t pixel = W.pixel[slot];
+        Rng rng = rng_make(P.seed, pixel, W.sample[slot], 0u, W.draws[slot]);
+        Lam lam; for (int k = 0; k < 4; k++) lam.l[k] = W.lam[(size_t)k * N + slot];
+        C4 gathered = load_c4(W.gathered, N, slot);
+        uint32_t depth = W.depth[slot];
+        const D3 wo = -ro.d;
+        const double ru = rng_float(rng), r0 = rng_float(rng), r1 = rng_float(rng);
+        D3 wi;
+        bool done = false;
+        if (!bsdf_sample(S, m, wo, ho, lam, ru, r0, r1, wi)) {
+            if (P.integrator == 1 || (f & PF_LAST_SPECULAR)) {
+                const C4 e = gathered * mat_emit(S, m, lam, ho.backface);
+                if (!is_black(e)) { C4 rad = load_c4(W.radiance, N, slot); rad = rad + e; store_c4(W.radiance, N, slot, rad); }
+            }
+            done = true;
+        } else if (P.integrator == 1) {
+            if (!mat_is_specular(m)) { shadow_rays(S, W, slot, m, wo, gathered, lam, ho, rng); done = true; }
+            else if (depth >= LUMO_DL_MAX_RECURSION) done = true;
+        } else {
+            if (!mat_is_delta(S, m, lam)) shadow_rays(S, W, slot, m, wo, gathered, lam, ho, rng);
+        }
+        if (!done) {
+            const Ray ri = hit_generate_ray(ho, wi);
+            wi = ri.d;
+            const double p_scatter = bsdf_pdf(S, m, wo, wi, ho, lam, false);
+            if (p_scatter <= 0.0) done = true;
+            else {
+                const C4 bsdf = bsdf_f(S, m, wo, wi, lam, 0, ho);
+                gathered = gathered * (bsdf * shading_cosine(m, wi, ho.ns) / p_scatter);
+                if (P.integrator == 0 && depth >= LUMO_RR_DEPTH) {
+                    const double delta = W.tile_delta[tile_of(P, S, pixel)];
+                    const double lum = luminance(S, gathered, lam);
+                    const double rr = fmin(lum / delta, 1.0);
+                    if (rng_float(rng) > rr) done = true;
+                    else gathered = gathered / rr;
+                }
+                if (!done) {
+                    f = PF_ALIVE | (mat_is_specular(m) ? PF_LAST_SPECULAR : 0u);
+                    depth += 1u;
+                    W.ox[slot] = ri.o.x; W.oy[slot] = ri.o.y; W.oz[slot] = ri.o.z; W.dx[slot] = ri.d.x; W.dy[slot] = ri.d.y; W.dz[slot] = ri.d.z;
+                    store_c4(W.gathered, N, slot, gathered);
+                    W.depth[slot] = depth;
+                }
+            }
+        }
+        for (int k = 0; k < 4; k++) W.lam[(size_t)k * N + slot] = lam.l[k];
+        W.draws[slot] = rng.draws;
+        W.flags[slot] = done ? PF_DONE : f;
+    }
+}
+
+// RR threshold of a tile from its 64 pilot paths, summed in index order (task.rs:42-53 applied to
+// the pilot set): var = sum f^2 - (sum f)^2 / n; delta = var <= 0 ? 1e-5 : sqrt(var / sum cost)
+__global__ void k_pilot_reduce(const Wave W, uint32_t n_tiles, double* out) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    double f = 0.0, f2 = 0.0; unsigned long long cost = 0;
+    for (uint32_t k = 0; k < LUMO_PILOT_N; k++) { const double l = W.pilot_lum[t * LUMO_PILOT_N + k]; f += l; f2 += l * l; cost += W.pilot_cost[t * LUMO_PILOT_N + k]; }
+    const double var = f2 - f * f / (double)LUMO_PILOT_N;
+    out[t] = var <= 0.0 ? 1e-5 : sqrt(var / (double)cost);
+}
+__global__ void k_fill(double* p, size_t n, double v) { for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v; }
+
+// ---- batch entry points of the C ABI (parity kernels) ----------------------------------------------
+// mode 0: Scene::hit; 1: hit_light occlusion; 2: Scene::hit_t
+template <int MODE, bool CNT>
+__global__ void __launch_bounds__(128) k_trace_batch(const __grid_constant__ DevScene S, const double* __restrict__ o, const double* __restrict__ d,
+                                                     const double* __restrict__ t_max, unsigned long long n, unsigned long long* next,
+                                                     uint32_t* obj, uint32_t* tri, double* t, double* bary, uint8_t* occ, Counters* gc) {
+    const uint32_t lane = threadIdx.x & 31u;
+    Counters cnt = {0, 0, 0, 0, 0, 0};
+    for (;;) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(next, 32ull);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= n) break;
+        const unsigned long long i = base + lane;
+        if (i < n) {
+            Ray r; r.o = d3(o[3 * i], o[3 * i + 1], o[3 * i + 2]); r.d = d3(d[3 * i], d[3 * i + 1], d[3 * i + 2]);
+            if (MODE == 0) {
+                HitRec h;
+                if (scene_hit<CNT>(S, r, t_max ? t_max[i] : LUMO_INF, h, &cnt)) { obj[i] = h.obj; tri[i] = h.tri; t[i] = h.t; bary[2 * i] = h.bary.x; bary[2 * i + 1] = h.bary.y; }
+                else { obj[i] = LUMO_NONE; tri[i] = LUMO_NONE; t[i] = LUMO_INF; bary[2 * i] = 0.0; bary[2 * i + 1] = 0.0; }
+            } else if (MODE == 1) occ[i] = scene_occluded<CNT>(S, r, t_max[i], &cnt) ? 1 : 0;
+            else t[i] = scene_hit_t<CNT>(S, r, &cnt);
+        }
+    }
+    if (CNT) { atomicAdd(&gc->tlas, cnt.tlas); atomicAdd(&gc->inst, cnt.inst); atomicAdd(&gc->kd, cnt.kd); atomicAdd(&gc->leaf, cnt.leaf); atomicAdd(&gc->tri, cnt.tri); atomicAdd(&gc->sphere, cnt.sphere); }
+}
+
+}  // namespace lumo_dev

@@ -78,3 +78,23 @@ def cube10():
     v = np.array([[-1, -1, -1], [1, -1, -1], [1, 1, -1], [-1, 1, -1], [-1, -1, 1], [1, -1, 1], [1, 1, 1], [-1, 1, 1]], dtype=np.float64)
     f = np.array([[0, 1, 2], [0, 2, 3], [4, 6, 5], [4, 7, 6], [0, 4, 5], [0, 5, 1], [1, 5, 6], [1, 6, 2], [3, 2, 6], [3, 6, 7]], dtype=np.int64)
     return v, f
+
+
+def displaced_blob(nu, nv, seed, amplitude=0.2, squash=(1.0, 1.0, 1.0)):
+    """Closed displaced UV sphere with exactly 2*nu*(nv-1) triangles (a chunk of the synthetic
+    "conference" / "bistro" stand-ins)."""
+    u = np.arange(nu) / nu * 2 * np.pi
+    v = (np.arange(nv) + 0.5) / nv * np.pi
+    U, V = np.meshgrid(u, v, indexing="ij")
+    d = np.stack([np.sin(V) * np.cos(U), np.cos(V), np.sin(V) * np.sin(U)], -1).reshape(-1, 3)
+    r = 1.0 + amplitude * _value_noise3(d * 2.0 + 3.0 * seed, seed)
+    return d * r[:, None] * np.asarray(squash)[None, :], _grid_faces(nu, nv, True, False)
+
+
+def height_patch(nu, nv, seed, amplitude=0.05):
+    """Open height-field patch on [0,1]^2 (y up) with exactly 2*(nu-1)*(nv-1) triangles."""
+    x = np.arange(nu) / (nu - 1); z = np.arange(nv) / (nv - 1)
+    X, Z = np.meshgrid(x, z, indexing="ij")
+    p = np.stack([X, np.zeros_like(X), Z], -1).reshape(-1, 3)
+    p[:, 1] = amplitude * _value_noise3(p * 4.0 + 7.0 * seed, seed)
+    return p, _grid_faces(nu, nv, False, False)

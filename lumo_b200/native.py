@@ -101,6 +101,7 @@ class FilmAccum(C.Structure):           # include/lumo_gpu.h lumo_film_accum
 
 
 _gpu = None
+COUNTER_NAMES = ("camera_paths", "closest", "occlusion", "cost", "gpu_launches", "max_depth", "iterations", "nonfinite")
 
 
 def gpu_lib():
@@ -122,7 +123,11 @@ def gpu_lib():
         L.lumo_gpu_trace_any.argtypes = [vp, dp, dp, dp, C.c_uint64, u8p]
         L.lumo_gpu_trace_first_found.argtypes = [vp, dp, dp, C.c_uint64, dp]
         L.lumo_gpu_render.argtypes = [vp, C.POINTER(RenderParams), C.POINTER(FilmAccum)]
-        for f in ("lumo_gpu_device_count", "lumo_gpu_ctx_create", "lumo_gpu_ctx_destroy", "lumo_gpu_scene_upload", "lumo_gpu_scene_destroy",
+        L.lumo_gpu_render_dev.argtypes = [vp, C.POINTER(RenderParams), vp, vp, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
+        L.lumo_gpu_trace_closest_dev.argtypes = [vp, vp, vp, C.c_uint64, vp, vp, vp, vp, C.POINTER(C.c_float)]
+        L.lumo_gpu_ctx_count_visits.argtypes = [vp, C.c_int32]
+        L.lumo_gpu_ctx_visits.argtypes = [vp, C.POINTER(C.c_uint64)]
+        for f in ("lumo_gpu_render_dev", "lumo_gpu_trace_closest_dev", "lumo_gpu_ctx_count_visits", "lumo_gpu_ctx_visits","lumo_gpu_device_count", "lumo_gpu_ctx_create", "lumo_gpu_ctx_destroy", "lumo_gpu_scene_upload", "lumo_gpu_scene_destroy",
                   "lumo_gpu_trace_closest", "lumo_gpu_trace_any", "lumo_gpu_trace_first_found", "lumo_gpu_render"):
             getattr(L, f).restype = C.c_int32
         _gpu = L
@@ -147,6 +152,14 @@ class GpuContext:
     def close(self):
         if self.h:
             gpu_lib().lumo_gpu_ctx_destroy(self.h); self.h = None
+
+    def count_visits(self, enable):
+        _check(gpu_lib().lumo_gpu_ctx_count_visits(self.h, int(enable)), "lumo_gpu_ctx_count_visits")
+
+    def visits(self):
+        out = (C.c_uint64 * 6)()
+        _check(gpu_lib().lumo_gpu_ctx_visits(self.h, out), "lumo_gpu_ctx_visits")
+        return dict(zip(("tlas_nodes", "inst", "kd_nodes", "leaf_idx", "tri_tests", "sphere_tests"), (int(v) for v in out)))
 
     def __del__(self):
         try: self.close()
@@ -202,5 +215,20 @@ class GpuScene:
         deltas = np.zeros(ntiles)
         out = FilmAccum(_dp(pixels), _dp(splats), (C.c_uint64 * 8)(), _dp(deltas), 0.0)
         _check(gpu_lib().lumo_gpu_render(self.h, C.byref(P), C.byref(out)), "lumo_gpu_render")
-        names = ("camera_paths", "closest", "occlusion", "cost", "gpu_launches", "max_depth", "shadow_queued", "reserved")
-        return pixels, splats, dict(zip(names, (int(v) for v in out.counters))), deltas, out.device_ms
+        return pixels, splats, dict(zip(COUNTER_NAMES, (int(v) for v in out.counters))), deltas, out.device_ms
+
+    def render_dev(self, pixels_ptr, splats_ptr, integrator=0, spp=1, seed=1, sampler=2, tone_map=0, tone_map_arg=0.0, rr_delta=0.0,
+                   spp_begin=0, spp_end=None, total_spp=None, wave_paths=0):
+        """Film accumulators stay in the caller's DEVICE buffers (raw pointers, e.g. torch tensors' data_ptr())."""
+        total = spp if total_spp is None else total_spp
+        end = total if spp_end is None else spp_end
+        P = RenderParams(integrator, sampler, tone_map, 0, tone_map_arg, rr_delta, seed, spp_begin, end, total, wave_paths)
+        cnt = (C.c_uint64 * 8)(); ms = C.c_double(0.0)
+        _check(gpu_lib().lumo_gpu_render_dev(self.h, C.byref(P), C.c_void_p(pixels_ptr), C.c_void_p(splats_ptr), cnt, C.byref(ms)), "lumo_gpu_render_dev")
+        return dict(zip(COUNTER_NAMES, (int(v) for v in cnt))), ms.value
+
+    def trace_closest_dev(self, o_ptr, d_ptr, n, obj_ptr, tri_ptr, t_ptr, bary_ptr):
+        ms = C.c_float(0.0)
+        _check(gpu_lib().lumo_gpu_trace_closest_dev(self.h, C.c_void_p(o_ptr), C.c_void_p(d_ptr), n, C.c_void_p(obj_ptr), C.c_void_p(tri_ptr),
+                                                    C.c_void_p(t_ptr), C.c_void_p(bary_ptr), C.byref(ms)), "lumo_gpu_trace_closest_dev")
+        return ms.value
