@@ -86,7 +86,7 @@ int32_t lumo_gpu_scene_destroy(lumo_scene* scene);
  * NULL (= +inf; the reference always uses +inf).  Outputs: obj_id = index in Scene.objects
  * insertion order, lights offset by objects.len(); tri_id = index in that object's
  * KdTree.objects (0 for spheres / loose triangles); both 0xFFFFFFFF on a miss; t = hit distance
- * (+inf on miss); bary_uv[2i..] = first two barycentrics (edges/det) for triangles, (u,v) for
+ * (+inf on miss); bary_uv[2i..] = first two barycentrics (edges/det) for triangles, (0,0) for
  * spheres.  Bit-exact against the reference traversal. */
 int32_t lumo_gpu_trace_closest(lumo_scene* scene, const double* origin_xyz, const double* dir_xyz, const double* t_max,
                                uint64_t n, uint32_t* obj_id, uint32_t* tri_id, double* t, double* bary_uv);

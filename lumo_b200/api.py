@@ -410,3 +410,75 @@ class Scene:                                         # src/tracer/scene.rs:18-11
         s.add(TriangleMesh.new(np.array(SMALL_BOX), box_faces, [], [], small))
         s.add(TriangleMesh.new(np.array(BIG_BOX), box_faces, [], [], big))
         return s
+
+
+# ---- renderer ----------------------------------------------------------------------------------
+class Renderer:
+    """src/renderer.rs:24-99,159-244.  Same builder surface (`samples / integrator / seed / sampler /
+    threads / tone_map / render`); `render()` hands the whole tile x batch schedule to the GPU through
+    the C ABI (include/lumo_gpu.h) instead of a thread pool and returns a `Film`.  `threads` is
+    accepted for source compatibility and ignored.  Extra, GPU-only knobs: `device`, `wave_paths`,
+    `rr_delta`."""
+    def __init__(self, scene, camera):
+        assert scene.num_lights() != 0                                    # renderer.rs:42
+        self.scene, self.camera = scene, camera
+        self.resolution = camera.get_resolution()
+        self.num_samples = 1                                              # renderer.rs:20
+        self._integrator = Integrator.PathTrace
+        self._tone_map = ToneMap.NoMap
+        self._sampler = SamplerType.MultiJittered
+        self._threads = 4
+        import time
+        self._seed = int(time.time_ns()) & 0xFFFFFFFFFFFFFFFF              # rng.rs:7-22 (time-derived default)
+        self._device, self._wave_paths, self._rr_delta = 0, 0, 0.0
+        self._blob = None
+        self.quiet = False
+
+    @staticmethod
+    def new(scene, camera): return Renderer(scene, camera)
+    def tone_map(self, tm): self._tone_map = tm; return self
+    def samples(self, n): self.num_samples = int(n); return self
+    def integrator(self, ig): self._integrator = ig; return self
+    def seed(self, s): self._seed = int(s); return self
+    def sampler(self, s): self._sampler = s; return self
+    def threads(self, n): self._threads = int(n); return self
+    def device(self, d): self._device = int(d); return self
+    def wave_paths(self, n): self._wave_paths = int(n); return self
+    def rr_delta(self, d): self._rr_delta = float(d); return self
+
+    def blob(self):
+        """Scene::build (scene.rs:33-52) + flattening: built once, natively (csrc/host)."""
+        if self._blob is None:
+            from . import native
+            self._blob = native.build_blob(self.scene._program(self.camera))
+        return self._blob
+
+    def _banner(self, B):                                                 # renderer.rs:101-138
+        p = B.params
+        print("Starting to render the scene:\n"
+              "\t Resolution: %d x %d\n\t Samples: %d\n\t Shadow rays: %d\n\t Integrator: %s\n\t Primitives: %d\n\t Lights: %d\n"
+              "\t Seed: %d\n\t Device: cuda:%d" % (self.resolution[0], self.resolution[1], self.num_samples,
+                                                   1 if self._integrator == Integrator.BDPathTrace else int(p["n_shadow_rays"]),
+                                                   Integrator.NAMES[self._integrator], int(p["n_tris"]), int(p["n_lights"]), self._seed, self._device))
+
+    def render(self):
+        import time
+        from . import native
+        from .film import Film
+        start = time.time()
+        blob = self.blob()
+        ctx = native.GpuContext(self._device)
+        try:
+            gs = native.GpuScene(ctx, blob)
+            if not self.quiet:
+                self._banner(gs.blob)
+            px, sp, cnt, deltas, ms = gs.render(integrator=self._integrator, spp=self.num_samples, seed=self._seed, sampler=self._sampler,
+                                                tone_map=self._tone_map.kind, tone_map_arg=self._tone_map.arg, rr_delta=self._rr_delta,
+                                                wave_paths=self._wave_paths)
+            gs.close()
+        finally:
+            ctx.close()
+        if not self.quiet:                                                # renderer.rs:237-241
+            print("Finished rendering in %.3f s (%d camera rays, %d total rays)" % (time.time() - start, cnt["camera_paths"], cnt["cost"]))
+        return Film(px, sp, self.num_samples, self.camera._pixel_filter, self.camera._color_space, counters=cnt,
+                    stats={"device_ms": ms, "tile_deltas": deltas})

@@ -4,6 +4,7 @@
 #include "lumo_gpu.h"
 #include "wavefront.cuh"
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -328,6 +329,7 @@ static int32_t render_impl(lumo_scene* sc, const lumo_render_params* rp, double*
     WaveParams P; std::memset(&P, 0, sizeof P);
     P.seed = rp->seed; P.integrator = (uint32_t)rp->integrator; P.sampler = (uint32_t)rp->sampler; P.tone_map = (uint32_t)rp->tone_map; P.tone_map_arg = rp->tone_map_arg;
     P.spp_begin = rp->spp_begin; P.spp_count = spp; P.total_spp = rp->total_spp; P.tiles_x = tiles_x; P.tiles_y = tiles_y;
+    { const char* e = std::getenv("LUMO_DEBUG_PIXEL"); P.debug_pixel = e ? (uint32_t)std::atoll(e) : LUMO_NONE; }
     uint64_t iterations = 0;
     if (rp->rr_delta <= 0.0 && rp->integrator != LUMO_DIRECT_LIGHT) {
         // Per-tile Russian-roulette threshold (the role of task.rs:42-53): two pilot rounds, the second

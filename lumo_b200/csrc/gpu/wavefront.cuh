@@ -18,6 +18,7 @@
 #pragma once
 #include "shade.cuh"
 #include <cooperative_groups.h>
+#include <cstdio>
 
 namespace lumo_dev {
 namespace cg = cooperative_groups;
@@ -58,7 +59,7 @@ struct WaveParams {
     uint32_t integrator, sampler, tone_map, mode;
     double tone_map_arg;
     uint32_t spp_begin, spp_count, total_spp, pilot_round;
-    uint32_t tiles_x, tiles_y, pad0, pad1;
+    uint32_t tiles_x, tiles_y, debug_pixel, pad1;   // debug_pixel: LUMO_DEBUG_PIXEL env (printf trace of one pixel's paths), LUMO_NONE = off
 };
 
 __device__ __forceinline__ uint32_t agg_inc(uint32_t* ctr) {   // warp-aggregated atomicAdd(ctr, 1)
@@ -241,7 +242,7 @@ __device__ __forceinline__ C4 mis_sample(const DevScene& S, const Mat& m, D3 wo,
 }
 // integrator.rs:74-137: light pick -> light sample + BSDF sample, MIS-weighted; the occlusion half of
 // hit_light is deferred to k_wave_occlude with the finished contribution attached.
-__device__ __noinline__ void shadow_rays(const DevScene& S, const Wave& W, uint32_t slot, const Mat& m, D3 wo, const C4& gathered, Lam& lam, const DevHit& ho, Rng& rng) {
+__device__ __noinline__ void shadow_rays(const DevScene& S, const Wave& W, uint32_t slot, const Mat& m, D3 wo, const C4& gathered, Lam& lam, const DevHit& ho, Rng& rng, bool dbg) {
     const uint32_t n = S.P.n_shadow_rays;
     for (uint32_t i = 0; i < n; i++) {
         const uint32_t li = sample_light(S, rng_float(rng));
@@ -257,6 +258,7 @@ __device__ __noinline__ void shadow_rays(const DevScene& S, const Wave& W, uint3
                 const double p_lig = light_sample_towards_pdf(S, lo, ri, hi.p, hi.ng);
                 const double p_sct = bsdf_pdf(S, m, wo, wi, ho, lam, false);
                 const C4 c = mis_sample(S, m, wo, wi, ho, hi, lam, true, p_lig, p_sct);
+                if (dbg) printf("  [gpu] A vis t=%.17g p_lig=%.17g p_sct=%.17g c0=%.17g\n", hi.t, p_lig, p_sct, c.s[0]);
                 if (!is_black(c)) push_shadow(W, slot, ri, hi.t - LUMO_EPS, gathered * (c / pdf_light) / (double)n);
             }
         }
@@ -269,6 +271,7 @@ __device__ __noinline__ void shadow_rays(const DevScene& S, const Wave& W, uint3
                 const double p_lig = light_sample_towards_pdf(S, lo, ri, hi.p, hi.ng);
                 const double p_sct = bsdf_pdf(S, m, wo, wi, ho, lam, false);
                 const C4 c = mis_sample(S, m, wo, wi, ho, hi, lam, false, p_lig, p_sct);
+                if (dbg) printf("  [gpu] B vis t=%.17g p_lig=%.17g p_sct=%.17g c0=%.17g\n", hi.t, p_lig, p_sct, c.s[0]);
                 if (!is_black(c)) push_shadow(W, slot, ri, hi.t - LUMO_EPS, gathered * (c / pdf_light) / (double)n);
             }
         }
@@ -294,6 +297,8 @@ __global__ void __launch_bounds__(128) k_wave_shade(const __grid_constant__ DevS
         C4 gathered = load_c4(W.gathered, N, slot);
         uint32_t depth = W.depth[slot];
         const D3 wo = -ro.d;
+        const bool dbg = pixel == P.debug_pixel && P.mode == WM_MAIN;
+        if (dbg) printf("[gpu] depth=%u obj=%u tri=%u t=%.17g g0=%.17g rad0=%.17g\n", depth, rec.obj, rec.tri, rec.t, gathered.s[0], W.radiance[slot]);
         const double ru = rng_float(rng), r0 = rng_float(rng), r1 = rng_float(rng);
         D3 wi;
         bool done = false;
@@ -304,10 +309,10 @@ __global__ void __launch_bounds__(128) k_wave_shade(const __grid_constant__ DevS
             }
             done = true;
         } else if (P.integrator == 1) {
-            if (!mat_is_specular(m)) { shadow_rays(S, W, slot, m, wo, gathered, lam, ho, rng); done = true; }
+            if (!mat_is_specular(m)) { shadow_rays(S, W, slot, m, wo, gathered, lam, ho, rng, dbg); done = true; }
             else if (depth >= LUMO_DL_MAX_RECURSION) done = true;
         } else {
-            if (!mat_is_delta(S, m, lam)) shadow_rays(S, W, slot, m, wo, gathered, lam, ho, rng);
+            if (!mat_is_delta(S, m, lam)) shadow_rays(S, W, slot, m, wo, gathered, lam, ho, rng, dbg);
         }
         if (!done) {
             const Ray ri = hit_generate_ray(ho, wi);

@@ -384,6 +384,7 @@ static void render_counter(const Loaded& L, const RenderParams& P, FilmAccum& fi
             });
             delta = nd;
         }
+        { std::lock_guard<std::mutex> l(g_total_mu); g_total = Counters(); }   // reported ray counts cover the main pass only
     }
     if (deltas_out) *deltas_out = delta;
     run([&](size_t t) {
@@ -395,6 +396,7 @@ static void render_counter(const Loaded& L, const RenderParams& P, FilmAccum& fi
             uint32_t pixel = (uint32_t)(x + y * cam.res_x);
             for (uint32_t s = P.spp_begin; s < P.spp_end; s++) {
                 Rng rng = Rng::counter(P.seed, pixel, s, 0);
+                { const char* e = std::getenv("ORACLE_DEBUG_PIXEL"); g_dbg = e && (uint32_t)std::atoll(e) == pixel; }
                 Vec2 raster_xy = Vec2((Float)x, (Float)y) + counter_jitter(P, pixel, s, rng);
                 auto samples = integrate(L, P.integrator, rng, delta[t], raster_xy);
                 num_rays += samples.back().cost;

@@ -485,7 +485,7 @@ struct Sphere : Object {
         Float u = (std::atan2(-ni.z, ni.x) + PI) / (2.0 * PI);
         Float v = std::acos(-ni.y) / PI;
         out = hit_new(t.value, mat, r.dir, xi, err, ni, ni, Vec2(u, v));
-        out.tri = 0; out.bary = Vec3(u, v, 0);
+        out.tri = 0; out.bary = Vec3(0, 0, 0);   // the C ABI reports barycentrics for triangles only
         return true;
     }
     Float hit_t(const Ray& r, Float t_min, Float t_max) const override {                         // sphere.rs:77-96

@@ -766,6 +766,7 @@ struct Scene {
 };
 
 // ---- integrators (src/tracer/integrator.rs, integrator/path_trace.rs, direct_light.rs) --------
+static thread_local bool g_dbg = false;
 static inline Color mis_sample(const Scene&, Vec3 wo, Vec3 wi, const Hit& ho, const Hit& hi, const Lambda& lam, bool li, Float p_lig, Float p_sct) {  // integrator.rs:139-184
     if (p_lig == 0.0 || p_sct == 0.0) return BLACK;
     const Material* m = ho.material;
@@ -789,7 +790,9 @@ static inline Color single_shadow_ray(const Scene& sc, Vec3 wo, Lambda& lam, con
         if (sc.hit_light(ri, light, hi)) {
             Float p_lig = light->sample_towards_pdf(ri, hi.p, hi.ng);
             Float p_sct = m->bsdf_pdf(wo, wi, ho, lam, false);
-            radiance = radiance + mis_sample(sc, wo, wi, ho, hi, lam, true, p_lig, p_sct);
+            Color c_ = mis_sample(sc, wo, wi, ho, hi, lam, true, p_lig, p_sct);
+            if (g_dbg) std::printf("  [oracle] A vis t=%.17g p_lig=%.17g p_sct=%.17g c0=%.17g\n", hi.t, p_lig, p_sct, c_.s[0]);
+            radiance = radiance + c_;
         }
     }
     Float rand_u = rng.gen_float();
@@ -801,7 +804,9 @@ static inline Color single_shadow_ray(const Scene& sc, Vec3 wo, Lambda& lam, con
         if (sc.hit_light(ri, light, hi)) {
             Float p_lig = light->sample_towards_pdf(ri, hi.p, hi.ng);
             Float p_sct = m->bsdf_pdf(wo, wi, ho, lam, false);
-            radiance = radiance + mis_sample(sc, wo, wi, ho, hi, lam, false, p_lig, p_sct);
+            Color c_ = mis_sample(sc, wo, wi, ho, hi, lam, false, p_lig, p_sct);
+            if (g_dbg) std::printf("  [oracle] B vis t=%.17g p_lig=%.17g p_sct=%.17g c0=%.17g\n", hi.t, p_lig, p_sct, c_.s[0]);
+            radiance = radiance + c_;
         }
     }
     return radiance / pdf_light;
@@ -822,6 +827,7 @@ static inline FilmSample path_trace(const Scene& sc, Ray ro, Rng& rng, Lambda la
     while (sc.hit(ro, ho)) {
         const Material* m = ho.material;
         gathered = gathered * WHITE;   // transmittance without a medium (scene.rs:111-116)
+        if (g_dbg) std::printf("[oracle] depth=%zu obj=%d tri=%d t=%.17g g0=%.17g rad0=%.17g\n", depth, (int)ho.obj, (int)ho.tri, ho.t, gathered.s[0], radiance.s[0]);
         Vec3 wo = -ro.dir;
         Float ru = rng.gen_float(); Vec2 rs = rng.gen_vec2();
         Vec3 wi;
@@ -846,6 +852,7 @@ static inline FilmSample path_trace(const Scene& sc, Ray ro, Rng& rng, Lambda la
         depth += 1;
         ro = ri;
     }
+    if (g_dbg) std::printf("[oracle] end depth=%zu rad0=%.17g\n", depth, radiance.s[0]);
     return FilmSample{raster_xy, radiance, lam, false, depth};
 }
 static inline FilmSample direct_light(const Scene& sc, Ray ro, Rng& rng, Lambda lam, Vec2 raster_xy) {  // direct_light.rs:5-73

@@ -25,14 +25,18 @@ SMALL = {
 _cache = {}
 
 
-def small_scene(name):
-    """(program bytes, blob bytes, integrator) of the small version of a config, built once."""
-    if name not in _cache:
-        from lumo_b200 import scenes, native
+def small_scene(name, box_filter=False):
+    """(program bytes, blob bytes, integrator) of the small version of a config, built once.
+    box_filter: PixelFilter::square(0.5), i.e. a pixel only receives its own samples."""
+    key = (name, box_filter)
+    if key not in _cache:
+        from lumo_b200 import scenes, native, PixelFilter
         s, cam, ig = scenes.CONFIGS[name](**SMALL[name])
+        if box_filter:
+            cam._pixel_filter = PixelFilter.square(0.5)
         prog = s._program(cam)
-        _cache[name] = (prog, native.build_blob(prog), ig)
-    return _cache[name]
+        _cache[key] = (prog, native.build_blob(prog), ig)
+    return _cache[key]
 
 
 def ray_batches(oracle_scene, n, seed):
