@@ -75,6 +75,8 @@ typedef struct lumo_film_accum {
 int32_t lumo_gpu_device_count(int32_t* n);
 int32_t lumo_gpu_ctx_create(int32_t device, lumo_ctx** ctx);
 int32_t lumo_gpu_ctx_destroy(lumo_ctx* ctx);
+/* Run this context's later calls on the caller's CUDA stream (a cudaStream_t); NULL = the context's own. */
+int32_t lumo_gpu_ctx_set_stream(lumo_ctx* ctx, void* cuda_stream);
 
 /* Upload a scene blob (built once on the host from lumo's own kd-tree / BVH build; layout in
  * csrc/common/scene_blob.h).  The caller keeps ownership of `blob`. */
@@ -114,7 +116,10 @@ int32_t lumo_gpu_render_dev(lumo_scene* scene, const lumo_render_params* params,
  * formula).  While enabled, the traversal kernels of this context run their counting instantiation;
  * never enabled inside a timed region. */
 int32_t lumo_gpu_ctx_count_visits(lumo_ctx* ctx, int32_t enable);
-int32_t lumo_gpu_ctx_visits(lumo_ctx* ctx, uint64_t* out6);
+int32_t lumo_gpu_ctx_visits(lumo_ctx* ctx, uint64_t* out12);   /* 6 for the closest-hit kernels, then 6 for the occlusion kernels */
+/* Device time (ms, CUDA events on the launching stream) and launch count per kernel class of the last
+ * lumo_gpu_render*: [0] regen (film + refill + compaction), [1] closest-hit trace, [2] shade, [3] occlusion trace. */
+int32_t lumo_gpu_ctx_kernel_times(lumo_ctx* ctx, double* ms4, uint64_t* launches4);
 
 /* Device-resident variants used by bench.py's kernel-only timing (inputs already in HBM). */
 int32_t lumo_gpu_trace_closest_dev(lumo_scene* scene, const double* origin_dev, const double* dir_dev, uint64_t n,

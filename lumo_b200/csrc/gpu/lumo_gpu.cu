@@ -18,14 +18,17 @@ static int32_t fail(int32_t code, const std::string& msg) { g_err = msg; return 
 
 struct lumo_ctx {
     int device = 0, sm_count = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, own_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // wave storage, grown on demand and reused across renders
     void* wave_mem = nullptr; size_t wave_bytes = 0;
     void* host_pinned = nullptr;   // IterCounters + RunCounters read-back
     unsigned long long launches = 0;
-    Counters* d_visit = nullptr;   // traversal visit counters (CNT passes)
+    Counters* d_visit = nullptr;   // traversal visit counters (CNT passes): [0] closest-hit kernels, [1] occlusion kernels
     int count_visits = 0;
+    // per-kernel-class device time of the last render (CUDA events on the launching stream)
+    cudaEvent_t kev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    double kernel_ms[4] = {0, 0, 0, 0}; unsigned long long kernel_launches[4] = {0, 0, 0, 0};
 };
 struct lumo_scene {
     lumo_ctx* ctx = nullptr;
@@ -51,11 +54,13 @@ extern "C" int32_t lumo_gpu_ctx_create(int32_t device, lumo_ctx** out) {
     lumo_ctx* ctx = new (std::nothrow) lumo_ctx();
     if (!ctx) return fail(LUMO_ERR_OOM, "ctx_create: out of host memory");
     ctx->device = device; ctx->sm_count = prop.multiProcessorCount;
-    CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    ctx->stream = ctx->own_stream;
     CU(cudaEventCreate(&ctx->ev0)); CU(cudaEventCreate(&ctx->ev1));
     CU(cudaMallocHost(&ctx->host_pinned, 4096));
-    CU(cudaMalloc(&ctx->d_visit, sizeof(Counters)));
-    CU(cudaMemset(ctx->d_visit, 0, sizeof(Counters)));
+    CU(cudaMalloc(&ctx->d_visit, 2 * sizeof(Counters)));
+    CU(cudaMemset(ctx->d_visit, 0, 2 * sizeof(Counters)));
+    for (auto& e : ctx->kev) CU(cudaEventCreate(&e));
     // f64 traversal keeps two explicit stacks per thread
     cudaDeviceSetLimit(cudaLimitStackSize, 4096);
     *out = ctx; return LUMO_OK;
@@ -66,10 +71,20 @@ extern "C" int32_t lumo_gpu_ctx_destroy(lumo_ctx* ctx) {
     if (ctx->wave_mem) cudaFree(ctx->wave_mem);
     if (ctx->d_visit) cudaFree(ctx->d_visit);
     if (ctx->host_pinned) cudaFreeHost(ctx->host_pinned);
+    for (auto& e : ctx->kev) if (e) cudaEventDestroy(e);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx; return LUMO_OK;
+}
+// Runs every later call of this context on the caller's CUDA stream (e.g. the stream the caller's NCCL
+// reduce of the film is enqueued on).  NULL restores the context's own stream.
+extern "C" int32_t lumo_gpu_ctx_set_stream(lumo_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return fail(LUMO_ERR_INVALID, "set_stream: null ctx");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return LUMO_OK;
 }
 // Switches the traversal kernels of this context to their visit-counting instantiation (same
 // traversal, plus per-thread counters of TLAS nodes / instance transforms / kd nodes / leaf entries /
@@ -78,15 +93,22 @@ extern "C" int32_t lumo_gpu_ctx_count_visits(lumo_ctx* ctx, int32_t enable) {
     if (!ctx) return fail(LUMO_ERR_INVALID, "count_visits: null ctx");
     CU(cudaSetDevice(ctx->device));
     ctx->count_visits = enable ? 1 : 0;
-    CU(cudaMemset(ctx->d_visit, 0, sizeof(Counters)));
+    CU(cudaMemset(ctx->d_visit, 0, 2 * sizeof(Counters)));
     return LUMO_OK;
 }
-extern "C" int32_t lumo_gpu_ctx_visits(lumo_ctx* ctx, uint64_t* out6) {
-    if (!ctx || !out6) return fail(LUMO_ERR_INVALID, "visits: null pointer");
+// out12: six counters of the closest-hit kernels, then six of the occlusion kernels
+extern "C" int32_t lumo_gpu_ctx_visits(lumo_ctx* ctx, uint64_t* out12) {
+    if (!ctx || !out12) return fail(LUMO_ERR_INVALID, "visits: null pointer");
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
-    Counters c; CU(cudaMemcpy(&c, ctx->d_visit, sizeof c, cudaMemcpyDeviceToHost));
-    out6[0] = c.tlas; out6[1] = c.inst; out6[2] = c.kd; out6[3] = c.leaf; out6[4] = c.tri; out6[5] = c.sphere;
+    Counters c[2]; CU(cudaMemcpy(c, ctx->d_visit, sizeof c, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 2; k++) { uint64_t* o = out12 + 6 * k; o[0] = c[k].tlas; o[1] = c[k].inst; o[2] = c[k].kd; o[3] = c[k].leaf; o[4] = c[k].tri; o[5] = c[k].sphere; }
+    return LUMO_OK;
+}
+// Device time (ms) and launch count per kernel class of the last render: regen, trace, shade, occlude.
+extern "C" int32_t lumo_gpu_ctx_kernel_times(lumo_ctx* ctx, double* ms4, uint64_t* launches4) {
+    if (!ctx || !ms4 || !launches4) return fail(LUMO_ERR_INVALID, "kernel_times: null pointer");
+    for (int k = 0; k < 4; k++) { ms4[k] = ctx->kernel_ms[k]; launches4[k] = ctx->kernel_launches[k]; }
     return LUMO_OK;
 }
 
@@ -173,7 +195,7 @@ static int32_t launch_batch(lumo_scene* sc, const double* o_dev, const double* d
                             uint32_t* obj, uint32_t* tri, double* t, double* bary, uint8_t* occ) {
     lumo_ctx* ctx = sc->ctx;
     CU(cudaMemsetAsync(next_dev, 0, 8, ctx->stream));
-    if (ctx->count_visits) k_trace_batch<MODE, true><<<trace_grid(ctx), 128, 0, ctx->stream>>>(sc->S, o_dev, d_dev, tmax_dev, n, next_dev, obj, tri, t, bary, occ, ctx->d_visit);
+    if (ctx->count_visits) k_trace_batch<MODE, true><<<trace_grid(ctx), 128, 0, ctx->stream>>>(sc->S, o_dev, d_dev, tmax_dev, n, next_dev, obj, tri, t, bary, occ, ctx->d_visit + (MODE == 0 ? 0 : 1));
     else k_trace_batch<MODE, false><<<trace_grid(ctx), 128, 0, ctx->stream>>>(sc->S, o_dev, d_dev, tmax_dev, n, next_dev, obj, tri, t, bary, occ, nullptr);
     ctx->launches++;
     CU(cudaGetLastError());
@@ -277,14 +299,20 @@ static int32_t run_wave(lumo_scene* sc, const Wave& W, const WaveParams& P, uint
     CU(cudaMemsetAsync(&W.run->next_work, 0, 8, st));
     for (;;) {
         CU(cudaMemsetAsync(W.it, 0, sizeof(IterCounters), st));
+        CU(cudaEventRecord(ctx->kev[0], st));
         k_regen<<<rgrid, 256, 0, st>>>(sc->S, W, P);
+        CU(cudaEventRecord(ctx->kev[1], st));
         if (ctx->count_visits) k_wave_trace<true><<<tgrid, 128, 0, st>>>(sc->S, W, ctx->d_visit); else k_wave_trace<false><<<tgrid, 128, 0, st>>>(sc->S, W, nullptr);
+        CU(cudaEventRecord(ctx->kev[2], st));
         k_wave_shade<<<sgrid, 128, 0, st>>>(sc->S, W, P);
-        if (ctx->count_visits) k_wave_occlude<true><<<tgrid, 128, 0, st>>>(sc->S, W, ctx->d_visit); else k_wave_occlude<false><<<tgrid, 128, 0, st>>>(sc->S, W, nullptr);
+        CU(cudaEventRecord(ctx->kev[3], st));
+        if (ctx->count_visits) k_wave_occlude<true><<<tgrid, 128, 0, st>>>(sc->S, W, ctx->d_visit + 1); else k_wave_occlude<false><<<tgrid, 128, 0, st>>>(sc->S, W, nullptr);
+        CU(cudaEventRecord(ctx->kev[4], st));
         ctx->launches += 4; iterations++;
         CU(cudaMemcpyAsync(hc, W.it, sizeof(IterCounters), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         CU(cudaGetLastError());
+        if (P.mode == WM_MAIN) for (int k = 0; k < 4; k++) { float ms = 0; CU(cudaEventElapsedTime(&ms, ctx->kev[k], ctx->kev[k + 1])); ctx->kernel_ms[k] += ms; ctx->kernel_launches[k]++; }
         if (hc->it.n_active == 0) break;
     }
     // the last regen found nothing alive: every finished path has been retired into the film
@@ -320,6 +348,7 @@ static int32_t render_impl(lumo_scene* sc, const lumo_render_params* rp, double*
     W.pixels = pixels_dev; W.splats = splats_dev;
     cudaStream_t st = ctx->stream;
     const unsigned long long launches0 = ctx->launches;
+    for (int k = 0; k < 4; k++) { ctx->kernel_ms[k] = 0; ctx->kernel_launches[k] = 0; }
     CU(cudaEventRecord(ctx->ev0, st));
     CU(cudaMemsetAsync(pixels_dev, 0, film_px * 32, st));
     CU(cudaMemsetAsync(splats_dev, 0, film_px * 24, st));

@@ -84,21 +84,21 @@ __device__ __forceinline__ double lam_pdf_one(double l) {                       
     const double c = cosh(0.0072 * (l - 538.05));
     return 1.0 / (253.819 * (c * c));
 }
-__device__ __forceinline__ Lam lam_sample(double u) {                                                                           // wavelength.rs:35-44
+__device__ __noinline__ Lam lam_sample(double u) {                                                                           // wavelength.rs:35-44
     Lam r;
 #pragma unroll
     for (int i = 0; i < 4; i++) { double v = u + (double)i / 4.0; v = v > 1.0 ? v - 1.0 : v; r.l[i] = lam_sample_one(v); }
     return r;
 }
 __device__ __forceinline__ bool lam_terminated(const Lam& l) { return l.l[1] == 0.0 && l.l[2] == 0.0 && l.l[3] == 0.0; }
-__device__ __forceinline__ C4 lam_pdf(const Lam& l) {                                                                           // wavelength.rs:24-32
+__device__ __noinline__ C4 lam_pdf(const Lam& l) {                                                                           // wavelength.rs:24-32
     C4 c;
 #pragma unroll
     for (int i = 0; i < 4; i++) c.s[i] = lam_pdf_one(l.l[i]);
     if (lam_terminated(l)) c.s[0] /= 4.0;
     return c;
 }
-__device__ __forceinline__ double dense_one(const double* v, double lambda) {                                                   // dense_spectrum.rs:77-97
+__device__ __noinline__ double dense_one(const double* v, double lambda) {                                                   // dense_spectrum.rs:77-97
     const double STEP = (830.0 - 360.0) / (95.0 - 1.0);
     const unsigned long long b1 = sat_u64(ceil((lambda - 360.0) / STEP));
     const double l1 = 360.0 + STEP * (double)b1;
@@ -110,7 +110,7 @@ __device__ __forceinline__ double dense_one(const double* v, double lambda) {   
     return __ldg(v + b0) * x0 + __ldg(v + b1) * x1;
 }
 __device__ __forceinline__ C4 dense4(const double* v, const Lam& l) { C4 c; for (int i = 0; i < 4; i++) c.s[i] = dense_one(v, l.l[i]); return c; }
-__device__ __forceinline__ double spec_one(const float* c, double lambda) {                                                     // spectrum.rs:108-118
+__device__ __noinline__ double spec_one(const float* c, double lambda) {                                                     // spectrum.rs:108-118
     const float l = (float)lambda;
     const float x = __fadd_rn(__fadd_rn(__fmul_rn(__fmul_rn(c[0], l), l), __fmul_rn(c[1], l)), c[2]);
     const float sg = __fadd_rn(0.5f, __fdiv_rn(x, __fmul_rn(2.0f, __fsqrt_rn(__fadd_rn(1.0f, __fmul_rn(x, x))))));
@@ -119,11 +119,11 @@ __device__ __forceinline__ double spec_one(const float* c, double lambda) {     
 __device__ __forceinline__ C4 spec4(const float* c, const Lam& l) { C4 r; for (int i = 0; i < 4; i++) r.s[i] = spec_one(c, l.l[i]); return r; }
 #define LUMO_Y_INTEGRAL 106.856895
 __device__ __forceinline__ const double* table(const DevScene& S, uint32_t id) { return S.tables + 96ull * id; }
-__device__ __forceinline__ double luminance(const DevScene& S, C4 c, const Lam& l) {                                            // color.rs:88-91
+__device__ __noinline__ double luminance(const DevScene& S, C4 c, const Lam& l) {                                            // color.rs:88-91
     const C4 pdf = lam_pdf(l);
     return mean4(dense4(table(S, LTAB_Y), l) * c / pdf) / LUMO_Y_INTEGRAL;
 }
-__device__ __forceinline__ D3 color_xyz(const DevScene& S, C4 c, const Lam& l) {                                                // color.rs:93-101
+__device__ __noinline__ D3 color_xyz(const DevScene& S, C4 c, const Lam& l) {                                                // color.rs:93-101
     const C4 pdf = lam_pdf(l);
     return d3(mean4(dense4(table(S, LTAB_X), l) * c / pdf), mean4(dense4(table(S, LTAB_Y), l) * c / pdf), mean4(dense4(table(S, LTAB_Z), l) * c / pdf)) / LUMO_Y_INTEGRAL;
 }
@@ -143,7 +143,7 @@ __device__ __forceinline__ D3 hit_ray_origin(const DevHit& h, bool outside) {   
               off.y > 0.0 ? next_float(xi.y) : (off.y < 0.0 ? previous_float(xi.y) : xi.y),
               off.z > 0.0 ? next_float(xi.z) : (off.z < 0.0 ? previous_float(xi.z) : xi.z));
 }
-__device__ __forceinline__ Ray hit_generate_ray(const DevHit& h, D3 wi) {                                                       // hit.rs:115-122
+__device__ __noinline__ Ray hit_generate_ray(const DevHit& h, D3 wi) {                                                       // hit.rs:115-122
     Ray r; r.o = hit_ray_origin(h, dot(wi, h.ng) >= 0.0); r.d = normalize(wi); return r;
 }
 __device__ __forceinline__ D3 mul33(const double* m, D3 v) { return d3(dot(d3(m[0], m[1], m[2]), v), dot(d3(m[3], m[4], m[5]), v), dot(d3(m[6], m[7], m[8]), v)); }
@@ -163,7 +163,7 @@ __device__ __forceinline__ D3 propagate_fp_err(const LumoInstance* I, D3 xo, D3 
 // Rebuilds the reference's `Hit` from (object, triangle, t, barycentrics): the GEO tail of
 // Triangle::_hit (triangle.rs:155-186), Sphere::hit (sphere.rs:62-74), Rectangle::hit's uv override
 // (rectangle.rs:73-85) and Instance::hit's world transform (instance.rs:84-99).
-__device__ __forceinline__ DevHit reconstruct_hit(const DevScene& S, const Ray& r, const HitRec& rec) {
+__device__ __noinline__ DevHit reconstruct_hit(const DevScene& S, const Ray& r, const HitRec& rec) {
     const LumoObject o = S.objects[rec.obj];
     const Ray l = to_local<false>(S, o, r, nullptr);
     DevHit h; h.t = rec.t; h.material = o.material;
@@ -219,7 +219,7 @@ __device__ __forceinline__ DevHit reconstruct_hit(const DevScene& S, const Ray& 
 
 // ---- Onb (onb.rs:19-62, Duff et al.) ---------------------------------------------------------------
 struct Onb { D3 u, v, w; };
-__device__ __forceinline__ Onb onb_new(D3 w) {
+__device__ __noinline__ Onb onb_new(D3 w) {
     const double sgn = signum(w.z);
     const double a = -1.0 / (sgn + w.z);
     const double b = w.x * w.y * a;
@@ -239,7 +239,7 @@ __device__ __forceinline__ void square_to_disk(double r0, double r1, double& dx,
     if (fabs(ox) > fabs(oy)) { rr = ox; th = LUMO_PI * (oy / ox) / 4.0; } else { rr = oy; th = LUMO_PI * (0.5 - (ox / oy) / 4.0); }
     dx = rr * cos(th); dy = rr * sin(th);
 }
-__device__ __forceinline__ D3 square_to_cos_hemisphere(double r0, double r1) {
+__device__ __noinline__ D3 square_to_cos_hemisphere(double r0, double r1) {
     double dx, dy; square_to_disk(r0, r1, dx, dy);
     return d3(dx, dy, sqrt(fmax(1.0 - dx * dx - dy * dy, 0.0)));
 }
@@ -290,7 +290,7 @@ __device__ __forceinline__ double disney_diffuse(const Mat& m, double cwo, doubl
     const double fd90 = 0.5 * r2 + 2.0 * powi(cwh, 2) * r2;
     return f_schlick(1.0, fd90, cwo) * f_schlick(1.0, fd90, cwi) * (1.0 + r2 * (1.0 / 1.51 - 1.0));
 }
-__device__ __forceinline__ double ggx_d(const Mat& m, D3 wh) {                                                                  // microfacet.rs:147-176
+__device__ __noinline__ double ggx_d(const Mat& m, D3 wh) {                                                                  // microfacet.rs:147-176
     const double tan2 = tan2_theta(wh);
     if (isinf(tan2)) return 0.0;
     const double cos4 = powi(cos2_theta(wh), 2);
@@ -310,7 +310,7 @@ __device__ __forceinline__ Cx csqrt(Cx a) {                                     
     const double nr = sqrt(sqrt(a.re * a.re + a.im * a.im)), ar = atan2(a.im, a.re) / 2.0;
     return cx(nr * cos(ar), nr * sin(ar));
 }
-__device__ __forceinline__ double fr_complex(D3 wo, D3 wh, double eta_, double k_) {                                             // microfacet.rs:226-241
+__device__ __noinline__ double fr_complex(D3 wo, D3 wh, double eta_, double k_) {                                             // microfacet.rs:226-241
     const Cx eta = cx(eta_, k_);
     const double cos_o = clampd(dot(wo, wh), 0.0, 1.0);
     const double sin2_o = 1.0 - cos_o * cos_o;
@@ -322,7 +322,7 @@ __device__ __forceinline__ double fr_complex(D3 wo, D3 wh, double eta_, double k
     const Cx r_per = cdiv(cx(cos_o - eci.re, -eci.im), cx(cos_o + eci.re, eci.im));
     return ((r_par.re * r_par.re + r_par.im * r_par.im) + (r_per.re * r_per.re + r_per.im * r_per.im)) / 2.0;
 }
-__device__ __forceinline__ double fr_real(D3 wo, D3 wh, double eta_) {                                                           // microfacet.rs:244-265
+__device__ __noinline__ double fr_real(D3 wo, D3 wh, double eta_) {                                                           // microfacet.rs:244-265
     double cos_o = dot(wo, wh);
     const double eta = cos_o < 0.0 ? 1.0 / eta_ : eta_;
     cos_o = fabs(cos_o);
@@ -341,7 +341,7 @@ __device__ __forceinline__ double fresnel_at(const DevScene& S, const Mat& m, D3
 }
 __device__ __forceinline__ C4 fresnel4(const DevScene& S, const Mat& m, D3 wo, D3 wh, const Lam& l) { C4 c; for (int i = 0; i < 4; i++) c.s[i] = fresnel_at(S, m, wo, wh, l.l[i]); return c; }
 __device__ __forceinline__ bool chi_pass(D3 wo, D3 wh) { return signum(wh.z) * dot(wo, wh) * wo.z > LUMO_EPS; }                 // microfacet.rs:268-274
-__device__ __forceinline__ double ggx_lambda(const Mat& m, D3 w) {                                                              // microfacet.rs:296-311
+__device__ __noinline__ double ggx_lambda(const Mat& m, D3 w) {                                                              // microfacet.rs:296-311
     const double tan2 = tan2_theta(w);
     if (isinf(tan2)) return 0.0;
     const double cp = cos_phi(w), sp = sin_phi(w);
@@ -353,7 +353,7 @@ __device__ __forceinline__ double ggx_g1(const Mat& m, D3 wo, D3 wh) { return !c
 __device__ __forceinline__ double sample_normal_pdf(const Mat& m, D3 wh, D3 wo) {                                               // microfacet.rs:330-349
     return fmax(ggx_g1(m, wo, wh) * ggx_d(m, wh) * fabs(dot(wh, wo)) / fabs(wo.z), 0.0);
 }
-__device__ __forceinline__ D3 sample_normal(const Mat& m, D3 wo, double r0, double r1) {                                        // microfacet.rs:352-430 (Heitz 2018)
+__device__ __noinline__ D3 sample_normal(const Mat& m, D3 wo, double r0, double r1) {                                        // microfacet.rs:352-430 (Heitz 2018)
     D3 ws = normalize(d3(wo.x * m.roughness, wo.y * m.roughness, wo.z));
     if (ws.z < 0.0) ws = -ws;
     const D3 u = (1.0 - ws.z < LUMO_EPS) ? d3(1, 0, 0) : normalize(cross(ws, d3(0, 0, 1)));
@@ -595,7 +595,7 @@ __device__ __forceinline__ double base_sample_towards_pdf(const DevScene& S, con
     }
     return (1.0 / base_area(S, o)) * dist2(ri.o, xi) / fabs(dot(ng, ri.d));                                                    // object.rs:148-156
 }
-__device__ __forceinline__ D3 light_sample_towards(const DevScene& S, const LumoObject& o, D3 xo, double r0, double r1) {
+__device__ __noinline__ D3 light_sample_towards(const DevScene& S, const LumoObject& o, D3 xo, double r0, double r1) {
     if (o.inst < 0) return base_sample_towards(S, o, xo, r0, r1);
     const LumoInstance* I = S.instances + o.inst;                                                                               // instance.rs:163-168
     const D3 dl = base_sample_towards(S, o, xf_point(I->inv, xo), r0, r1);
@@ -606,7 +606,7 @@ __device__ __forceinline__ double det33(const double* m) {   // Mat3::det on the
     const double ng = m[2] * m[5] * m[8] + m[1] * m[4] * m[10] + m[0] * m[6] * m[9];
     return pos - ng;
 }
-__device__ __forceinline__ double light_sample_towards_pdf(const DevScene& S, const LumoObject& o, const Ray& ri, D3 xi, D3 ng) {
+__device__ __noinline__ double light_sample_towards_pdf(const DevScene& S, const LumoObject& o, const Ray& ri, D3 xi, D3 ng) {
     if (o.inst < 0) return base_sample_towards_pdf(S, o, ri, xi, ng);
     const LumoInstance* I = S.instances + o.inst;                                                                               // instance.rs:170-199
     // normal_transform.inv().transpose() (Mat3::inv, mat3.rs:64-72)
@@ -628,7 +628,7 @@ __device__ __forceinline__ double light_sample_towards_pdf(const DevScene& S, co
     return pdf_local * sa_conv / jacobian;
 }
 // Sampleable::sample_on through an optional Instance (instance.rs:148-161)
-__device__ __forceinline__ DevHit light_sample_on(const DevScene& S, const LumoObject& o, double r0, double r1) {
+__device__ __noinline__ DevHit light_sample_on(const DevScene& S, const LumoObject& o, double r0, double r1) {
     DevHit h = base_sample_on(S, o, r0, r1);
     if (o.inst >= 0) {
         const LumoInstance* I = S.instances + o.inst;
@@ -640,9 +640,10 @@ __device__ __forceinline__ DevHit light_sample_on(const DevScene& S, const LumoO
     return h;
 }
 // light.hit(r, 0, INF) for one light object: Object::hit + Hit reconstruction
-__device__ __forceinline__ bool light_hit(const DevScene& S, uint32_t obj_index, const Ray& r, DevHit& out) {
+__device__ __noinline__ bool light_hit(const DevScene& S, uint32_t obj_index, const Ray& r, DevHit& out) {
     HitRec rec;
-    if (!object_hit<false>(S, S.objects[obj_index], r, 0.0, LUMO_INF, rec, nullptr)) return false;
+    RayCtx w; make_ctx(r, w);
+    if (!object_hit<false>(S, S.objects[obj_index], w, 0.0, LUMO_INF, rec, nullptr)) return false;
     rec.obj = obj_index;
     out = reconstruct_hit(S, r, rec);
     return true;
@@ -669,7 +670,7 @@ __device__ __forceinline__ D3 xf4_dir(const double* m, D3 p) {
     if (w == 0.0) return d3(x, y, z);
     return d3(x / w, y / w, z / w);
 }
-__device__ __forceinline__ Ray camera_generate_ray(const LumoCamera& C, double rx, double ry, double l0, double l1) {           // camera.rs:221-268
+__device__ __noinline__ Ray camera_generate_ray(const LumoCamera& C, double rx, double ry, double l0, double l1) {           // camera.rs:221-268
     const D3 cam = xf4_point(C.camera_to_screen_inv, xf4_point(C.screen_to_raster_inv, d3(rx, ry, 0.0)));
     D3 xo_local, wi_local;
     if (!C.ortho) { xo_local = d3(0, 0, 0); wi_local = normalize(cam); } else { xo_local = cam; wi_local = d3(0, 0, 1); }
@@ -710,7 +711,7 @@ __device__ __forceinline__ C4 tone_map(const DevScene& S, int kind, double arg, 
 // full-frame buffers with f64 atomics.  Non-splat footprints are clamped to the sample's 16x16 tile
 // exactly like the reference's per-tile FilmTile (tile.rs:74-84), so the result equals
 // Film::add_tile of all tiles.
-__device__ __forceinline__ void film_add_sample(const DevScene& S, double* pixels, double* splats, C4 color, const Lam& l, double rx, double ry, bool splat) {
+__device__ __noinline__ void film_add_sample(const DevScene& S, double* pixels, double* splats, C4 color, const Lam& l, double rx, double ry, bool splat) {
     const LumoFilm& F = S.P.film;
     const D3 xyz = color_xyz(S, color, l);
     const D3 rgb = mul33(F.xyz_to_rgb, mul33(F.wb, xyz));

@@ -65,6 +65,16 @@ __device__ __forceinline__ RayTri ray_tri_setup(const Ray& r) {
     return q;
 }
 
+// Everything the traversal derives from a ray alone: reciprocal direction (bvh.rs:317, kdtree.rs:103 —
+// recomputed by the reference per BVH / kd-tree visit) and the Woop constants (triangle.rs:66-92 —
+// recomputed per triangle).  Same values, computed once per (ray, coordinate frame).
+struct RayCtx { Ray r; D3 inv; RayTri q; };
+__device__ __noinline__ void make_ctx(const Ray& r, RayCtx& c) {
+    c.r = r;
+    c.inv = d3(1.0 / r.d.x, 1.0 / r.d.y, 1.0 / r.d.z);
+    c.q = ray_tri_setup(r);
+}
+
 struct TriHit { double t; D3 bary; };
 
 // Visit counters of one thread (same sites as the oracle's: SURVEY §8d byte formula).  Compiled in
@@ -131,10 +141,11 @@ __device__ __forceinline__ void box_intersect(const double* lo, const double* hi
 struct KdStackEntry { uint32_t node; double t_start, t_end; };
 
 template <bool GEO, bool CNT>
-__device__ __forceinline__ bool kd_hit(const DevScene& S, const LumoKdTree* tree, const Ray& r, double t_min, double t_max,
-                                       double& t_out, uint32_t& tri_out, D3& bary_out, Counters* c) {
-    const RayTri q = ray_tri_setup(r);
-    const D3 inv = d3(1.0 / r.d.x, 1.0 / r.d.y, 1.0 / r.d.z);
+__device__ __noinline__ bool kd_hit(const DevScene& S, const LumoKdTree* tree, const RayCtx& ctx, double t_min, double t_max,
+                                    double& t_out, uint32_t& tri_out, D3& bary_out, Counters* c) {
+    const Ray r = ctx.r;
+    const RayTri q = ctx.q;
+    const D3 inv = ctx.inv;
     KdStackEntry stack[64];
     int sp = 0;
     double t_hit = LUMO_INF;
@@ -211,6 +222,12 @@ __device__ __forceinline__ Ray to_local(const DevScene& S, const LumoObject& o, 
     Ray l; l.o = xf_point(I->inv, r.o); l.d = xf_dir(I->inv, r.d);
     return l;
 }
+// the ray in the object's frame: the world context itself for un-instanced objects
+#define LUMO_LOCAL_CTX(S, o, wctx, c)                                                      \
+    RayCtx lctx_;                                                                          \
+    const RayCtx* lp_ = &(wctx);                                                           \
+    if ((o).inst >= 0) { make_ctx(to_local<CNT>(S, o, (wctx).r, c), lctx_); lp_ = &lctx_; } \
+    const RayCtx& l = *lp_
 
 // util::quadratic (object.rs:57-72)
 __device__ __forceinline__ bool quadratic(double a, double b, double c, double& t0, double& t1) {
@@ -222,7 +239,7 @@ __device__ __forceinline__ bool quadratic(double a, double b, double c, double& 
     return true;
 }
 // Sphere::hit_t (sphere.rs:77-96)
-__device__ __forceinline__ double sphere_hit_t(double radius, const Ray& r, double t_min, double t_max) {
+__device__ __noinline__ double sphere_hit_t(double radius, const Ray& r, double t_min, double t_max) {
     double a = dot(r.d, r.d), b = 2.0 * dot(r.d, r.o), c = dot(r.o, r.o) - radius * radius;
     double t0, t1;
     if (!quadratic(a, b, c, t0, t1)) return LUMO_INF;
@@ -267,7 +284,7 @@ __device__ __forceinline__ EF ef_div(EF a, EF b) {
 }
 __device__ __forceinline__ EF ef_sqrt(EF a) { return ef3(sqrt(a.v), previous_float(sqrt(a.lo)), next_float(sqrt(a.hi))); }
 // Sphere::hit distance selection (sphere.rs:28-60); returns INF when there is no hit
-__device__ __forceinline__ double sphere_hit(double radius, const Ray& r, double t_min, double t_max) {
+__device__ __noinline__ double sphere_hit(double radius, const Ray& r, double t_min, double t_max) {
     EF dx = ef(r.d.x), dy = ef(r.d.y), dz = ef(r.d.z), ox = ef(r.o.x), oy = ef(r.o.y), oz = ef(r.o.z);
     EF radius2 = ef_mul(ef(radius), ef(radius));
     EF a = ef_add(ef_add(ef_mul(dx, dx), ef_mul(dy, dy)), ef_mul(dz, dz));
@@ -287,18 +304,17 @@ __device__ __forceinline__ double sphere_hit(double radius, const Ray& r, double
 
 // Object::hit_t for one object record (what the BVH leaf loop calls, bvh.rs:346)
 template <bool CNT>
-__device__ __forceinline__ double object_hit_t(const DevScene& S, const LumoObject& o, const Ray& r, double t_min, double t_max, Counters* c) {
-    const Ray l = to_local<CNT>(S, o, r, c);
+__device__ __forceinline__ double object_hit_t(const DevScene& S, const LumoObject& o, const RayCtx& w, double t_min, double t_max, Counters* c) {
+    LUMO_LOCAL_CTX(S, o, w, c);
     switch (o.kind) {
     case LOBJ_KD: case LOBJ_RECT: {
         double t; uint32_t tri; D3 bary;
         return kd_hit<false, CNT>(S, S.kd_trees + o.geom, l, t_min, t_max, t, tri, bary, c) ? t : LUMO_INF;
     }
-    case LOBJ_SPHERE: LUMO_CNT(sphere); return sphere_hit_t(S.spheres[o.geom].radius, l, t_min, t_max);
+    case LOBJ_SPHERE: LUMO_CNT(sphere); return sphere_hit_t(S.spheres[o.geom].radius, l.r, t_min, t_max);
     default: {
-        const RayTri q = ray_tri_setup(l);
         TriHit th;
-        return tri_hit<false, CNT>(S.tri_verts + o.geom, l, q, t_min, t_max, th, c) ? th.t : LUMO_INF;
+        return tri_hit<false, CNT>(S.tri_verts + o.geom, l.r, l.q, t_min, t_max, th, c) ? th.t : LUMO_INF;
     }
     }
 }
@@ -308,22 +324,21 @@ struct HitRec { double t; D3 bary; uint32_t obj, tri; };
 // Object::hit for one object record: distance + which triangle + barycentrics (the rest of `Hit`
 // is rebuilt from these by the shading kernels, shade.cuh reconstruct_hit).
 template <bool CNT>
-__device__ __forceinline__ bool object_hit(const DevScene& S, const LumoObject& o, const Ray& r, double t_min, double t_max, HitRec& h, Counters* c) {
-    const Ray l = to_local<CNT>(S, o, r, c);
+__device__ __forceinline__ bool object_hit(const DevScene& S, const LumoObject& o, const RayCtx& w, double t_min, double t_max, HitRec& h, Counters* c) {
+    LUMO_LOCAL_CTX(S, o, w, c);
     switch (o.kind) {
     case LOBJ_KD: case LOBJ_RECT:
         return kd_hit<true, CNT>(S, S.kd_trees + o.geom, l, t_min, t_max, h.t, h.tri, h.bary, c);
     case LOBJ_SPHERE: {
         LUMO_CNT(sphere);
-        double t = sphere_hit(S.spheres[o.geom].radius, l, t_min, t_max);
+        double t = sphere_hit(S.spheres[o.geom].radius, l.r, t_min, t_max);
         if (!(t < LUMO_INF)) return false;
         h.t = t; h.tri = 0; h.bary = d3(0, 0, 0);
         return true;
     }
     default: {
-        const RayTri q = ray_tri_setup(l);
         TriHit th;
-        if (!tri_hit<true, CNT>(S.tri_verts + o.geom, l, q, t_min, t_max, th, c)) return false;
+        if (!tri_hit<true, CNT>(S.tri_verts + o.geom, l.r, l.q, t_min, t_max, th, c)) return false;
         h.t = th.t; h.tri = 0; h.bary = th.bary;
         return true;
     }
@@ -333,8 +348,9 @@ __device__ __forceinline__ bool object_hit(const DevScene& S, const LumoObject& 
 // BVH::_hit<GEO> (bvh.rs:315-362) over one of the two object BVHs.  obj_base = first object
 // record of this BVH (0 for Scene.objects, n_objects for Scene.lights).
 template <bool GEO, bool CNT>
-__device__ __forceinline__ uint32_t tlas_hit(const DevScene& S, uint32_t root, uint32_t obj_base, const Ray& r, double t_min, double t_max, Counters* c) {
-    const D3 inv = d3(1.0 / r.d.x, 1.0 / r.d.y, 1.0 / r.d.z);
+__device__ __noinline__ uint32_t tlas_hit(const DevScene& S, uint32_t root, uint32_t obj_base, const RayCtx& w, double t_min, double t_max, Counters* c) {
+    const Ray r = w.r;
+    const D3 inv = w.inv;
     uint32_t stack[64];
     int sp = 0;
     uint32_t curr = 0, idx = LUMO_NONE;
@@ -356,7 +372,7 @@ __device__ __forceinline__ uint32_t tlas_hit(const DevScene& S, uint32_t root, u
             const uint32_t first = node->first;
             for (uint32_t k = 0; k < count; k++) {
                 const uint32_t i = S.tlas_leaf[first + k];
-                const double t = object_hit_t<CNT>(S, S.objects[obj_base + i], r, t_min, tt, c);
+                const double t = object_hit_t<CNT>(S, S.objects[obj_base + i], w, t_min, tt, c);
                 if (GEO) { if (t < tt) { tt = t; idx = i; } }
                 else { if (t < tt) return i; }
             }
@@ -369,7 +385,7 @@ __device__ __forceinline__ uint32_t tlas_hit(const DevScene& S, uint32_t root, u
 
 // Object for BVH: hit / hit_t (bvh.rs:365-375)
 template <bool CNT>
-__device__ __forceinline__ bool bvh_hit(const DevScene& S, uint32_t root, uint32_t obj_base, const Ray& r, double t_min, double t_max, HitRec& h, Counters* c) {
+__device__ __forceinline__ bool bvh_hit(const DevScene& S, uint32_t root, uint32_t obj_base, const RayCtx& r, double t_min, double t_max, HitRec& h, Counters* c) {
     const uint32_t idx = tlas_hit<true, CNT>(S, root, obj_base, r, t_min, t_max, c);
     if (idx == LUMO_NONE) return false;
     if (!object_hit<CNT>(S, S.objects[obj_base + idx], r, t_min, t_max, h, c)) return false;
@@ -377,7 +393,7 @@ __device__ __forceinline__ bool bvh_hit(const DevScene& S, uint32_t root, uint32
     return true;
 }
 template <bool CNT>
-__device__ __forceinline__ double bvh_hit_t(const DevScene& S, uint32_t root, uint32_t obj_base, const Ray& r, double t_min, double t_max, Counters* c) {
+__device__ __forceinline__ double bvh_hit_t(const DevScene& S, uint32_t root, uint32_t obj_base, const RayCtx& r, double t_min, double t_max, Counters* c) {
     const uint32_t idx = tlas_hit<false, CNT>(S, root, obj_base, r, t_min, t_max, c);
     if (idx == LUMO_NONE) return LUMO_INF;
     return object_hit_t<CNT>(S, S.objects[obj_base + idx], r, t_min, t_max, c);
@@ -386,7 +402,8 @@ __device__ __forceinline__ double bvh_hit_t(const DevScene& S, uint32_t root, ui
 // Scene::hit (scene.rs:119-147): objects, then lights with t_max = h.t.  The reference always
 // starts from t_max = +inf; the C ABI lets the caller pass a finite one.
 template <bool CNT>
-__device__ __forceinline__ bool scene_hit(const DevScene& S, const Ray& r, double t_max, HitRec& h, Counters* c) {
+__device__ __forceinline__ bool scene_hit(const DevScene& S, const Ray& ray, double t_max, HitRec& h, Counters* c) {
+    RayCtx r; make_ctx(ray, r);
     bool have = bvh_hit<CNT>(S, 0, 0, r, 0.0, t_max, h, c);
     if (have) t_max = h.t;
     if (S.P.n_lights) {
@@ -397,7 +414,8 @@ __device__ __forceinline__ bool scene_hit(const DevScene& S, const Ray& r, doubl
 }
 // Scene::hit_t (scene.rs:150-162)
 template <bool CNT>
-__device__ __forceinline__ double scene_hit_t(const DevScene& S, const Ray& r, Counters* c) {
+__device__ __forceinline__ double scene_hit_t(const DevScene& S, const Ray& ray, Counters* c) {
+    RayCtx r; make_ctx(ray, r);
     double t = LUMO_INF;
     t = fmin(t, bvh_hit_t<CNT>(S, 0, 0, r, 0.0, t, c));
     if (S.P.n_lights) t = fmin(t, bvh_hit_t<CNT>(S, S.P.lights_root, S.P.n_objects, r, 0.0, t, c));
@@ -405,7 +423,8 @@ __device__ __forceinline__ double scene_hit_t(const DevScene& S, const Ray& r, C
 }
 // the two occlusion tests of Scene::hit_light (scene.rs:180-186)
 template <bool CNT>
-__device__ __forceinline__ bool scene_occluded(const DevScene& S, const Ray& r, double t_max, Counters* c) {
+__device__ __forceinline__ bool scene_occluded(const DevScene& S, const Ray& ray, double t_max, Counters* c) {
+    RayCtx r; make_ctx(ray, r);
     if (bvh_hit_t<CNT>(S, 0, 0, r, 0.0, t_max, c) < t_max) return true;
     if (S.P.n_lights && bvh_hit_t<CNT>(S, S.P.lights_root, S.P.n_objects, r, 0.0, t_max, c) < t_max) return true;
     return false;

@@ -232,7 +232,7 @@ __device__ __forceinline__ void push_shadow(const Wave& W, uint32_t slot, const 
     for (int k = 0; k < 4; k++) W.sc[(size_t)k * W.shadow_cap + i] = c.s[k];
 }
 // integrator.rs:139-184
-__device__ __forceinline__ C4 mis_sample(const DevScene& S, const Mat& m, D3 wo, D3 wi, const DevHit& ho, const DevHit& hi, const Lam& lam, bool li, double p_lig, double p_sct) {
+__device__ __noinline__ C4 mis_sample(const DevScene& S, const Mat& m, D3 wo, D3 wi, const DevHit& ho, const DevHit& hi, const Lam& lam, bool li, double p_lig, double p_sct) {
     if (p_lig == 0.0 || p_sct == 0.0) return c4(0.0);
     const C4 bsdf = bsdf_f(S, m, wo, wi, lam, 0, ho);
     const double denom = p_lig * p_lig + p_sct * p_sct;

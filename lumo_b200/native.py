@@ -126,6 +126,10 @@ def gpu_lib():
         L.lumo_gpu_render_dev.argtypes = [vp, C.POINTER(RenderParams), vp, vp, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
         L.lumo_gpu_trace_closest_dev.argtypes = [vp, vp, vp, C.c_uint64, vp, vp, vp, vp, C.POINTER(C.c_float)]
         L.lumo_gpu_ctx_count_visits.argtypes = [vp, C.c_int32]
+        L.lumo_gpu_ctx_set_stream.argtypes = [vp, vp]
+        L.lumo_gpu_ctx_kernel_times.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+        L.lumo_gpu_ctx_kernel_times.restype = C.c_int32
+        L.lumo_gpu_ctx_set_stream.restype = C.c_int32
         L.lumo_gpu_ctx_visits.argtypes = [vp, C.POINTER(C.c_uint64)]
         for f in ("lumo_gpu_render_dev", "lumo_gpu_trace_closest_dev", "lumo_gpu_ctx_count_visits", "lumo_gpu_ctx_visits","lumo_gpu_device_count", "lumo_gpu_ctx_create", "lumo_gpu_ctx_destroy", "lumo_gpu_scene_upload", "lumo_gpu_scene_destroy",
                   "lumo_gpu_trace_closest", "lumo_gpu_trace_any", "lumo_gpu_trace_first_found", "lumo_gpu_render"):
@@ -153,13 +157,23 @@ class GpuContext:
         if self.h:
             gpu_lib().lumo_gpu_ctx_destroy(self.h); self.h = None
 
+    def set_stream(self, cuda_stream_ptr):
+        _check(gpu_lib().lumo_gpu_ctx_set_stream(self.h, C.c_void_p(cuda_stream_ptr)), "lumo_gpu_ctx_set_stream")
+
     def count_visits(self, enable):
         _check(gpu_lib().lumo_gpu_ctx_count_visits(self.h, int(enable)), "lumo_gpu_ctx_count_visits")
 
     def visits(self):
-        out = (C.c_uint64 * 6)()
+        """(closest-hit kernels, occlusion kernels) visit counters"""
+        out = (C.c_uint64 * 12)()
         _check(gpu_lib().lumo_gpu_ctx_visits(self.h, out), "lumo_gpu_ctx_visits")
-        return dict(zip(("tlas_nodes", "inst", "kd_nodes", "leaf_idx", "tri_tests", "sphere_tests"), (int(v) for v in out)))
+        names = ("tlas_nodes", "inst", "kd_nodes", "leaf_idx", "tri_tests", "sphere_tests")
+        return dict(zip(names, (int(v) for v in out[:6]))), dict(zip(names, (int(v) for v in out[6:])))
+
+    def kernel_times(self):
+        ms = (C.c_double * 4)(); n = (C.c_uint64 * 4)()
+        _check(gpu_lib().lumo_gpu_ctx_kernel_times(self.h, ms, n), "lumo_gpu_ctx_kernel_times")
+        return {k: (ms[i], int(n[i])) for i, k in enumerate(("regen", "trace", "shade", "occlude"))}
 
     def __del__(self):
         try: self.close()

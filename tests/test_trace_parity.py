@@ -59,7 +59,7 @@ def test_visit_counters_equal_oracle(gpu_ctx):
     oc = O.counters(reset=True)
     gpu_ctx.count_visits(True)
     G.trace_closest(o, d)
-    gc = gpu_ctx.visits()
+    gc, _ = gpu_ctx.visits()
     gpu_ctx.count_visits(False)
     for k in ("tlas_nodes", "inst", "kd_nodes", "leaf_idx", "tri_tests", "sphere_tests"):
         assert oc[k] == gc[k], (k, oc[k], gc[k])
