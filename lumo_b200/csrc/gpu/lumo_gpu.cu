@@ -35,6 +35,7 @@ struct lumo_scene {
     uint8_t* d_blob = nullptr; uint64_t len = 0;
     DevScene S;
     LumoBlobHeader H;
+    uint32_t kind_mask = 0;   // bit k set: some Standard material of LumoMatKind k exists (which shade kernels to launch)
 };
 
 extern "C" const char* lumo_gpu_last_error(void) { return g_err.c_str(); }
@@ -178,6 +179,8 @@ extern "C" int32_t lumo_gpu_scene_upload(lumo_ctx* ctx, const void* blob, uint64
     S.rects = (const LumoRect*)at(LSEC_RECTS); S.spheres = (const LumoSphere*)at(LSEC_SPHERES);
     S.materials = (const LumoMaterial*)at(LSEC_MATERIALS); S.tables = (const double*)at(LSEC_TABLES); S.lights = (const LumoLight*)at(LSEC_LIGHTS);
     S.P = H.params;
+    { const LumoMaterial* mats = (const LumoMaterial*)((const uint8_t*)blob + H.sec[LSEC_MATERIALS].offset);
+      for (uint64_t i = 0; i < H.sec[LSEC_MATERIALS].count; i++) if (mats[i].kind < 32) sc->kind_mask |= 1u << mats[i].kind; }
     *out = sc; return LUMO_OK;
 }
 extern "C" int32_t lumo_gpu_scene_destroy(lumo_scene* sc) {
@@ -270,11 +273,15 @@ struct Carver {   // carves 256-byte aligned arrays out of one allocation
 };
 static void carve_wave(Wave& W, Carver& c, uint32_t N, uint32_t shadow_cap, uint32_t n_tiles, size_t film_px) {
     W.n_slots = N; W.shadow_cap = shadow_cap;
-    W.ox = c.take<double>(N); W.oy = c.take<double>(N); W.oz = c.take<double>(N); W.dx = c.take<double>(N); W.dy = c.take<double>(N); W.dz = c.take<double>(N);
+    for (int b = 0; b < 2; b++) {
+        W.ox[b] = c.take<double>(N); W.oy[b] = c.take<double>(N); W.oz[b] = c.take<double>(N); W.dx[b] = c.take<double>(N); W.dy[b] = c.take<double>(N); W.dz[b] = c.take<double>(N);
+        W.gathered[b] = c.take<double>(4 * (size_t)N); W.draws[b] = c.take<uint32_t>(N);
+    }
+    for (int k = 0; k < LUMO_N_CLASSES; k++) W.cls[k] = c.take<uint32_t>(N);
     W.ht = c.take<double>(N); W.hb0 = c.take<double>(N); W.hb1 = c.take<double>(N); W.hb2 = c.take<double>(N); W.hobj = c.take<uint32_t>(N); W.htri = c.take<uint32_t>(N);
-    W.gathered = c.take<double>(4 * (size_t)N); W.radiance = c.take<double>(4 * (size_t)N); W.lam = c.take<double>(4 * (size_t)N);
+    W.radiance = c.take<double>(4 * (size_t)N); W.lam = c.take<double>(4 * (size_t)N);
     W.rx = c.take<double>(N); W.ry = c.take<double>(N);
-    W.pixel = c.take<uint32_t>(N); W.sample = c.take<uint32_t>(N); W.depth = c.take<uint32_t>(N); W.draws = c.take<uint32_t>(N); W.flags = c.take<uint32_t>(N); W.witem = c.take<uint32_t>(N);
+    W.pixel = c.take<uint32_t>(N); W.sample = c.take<uint32_t>(N); W.depth = c.take<uint32_t>(N); W.flags = c.take<uint32_t>(N); W.witem = c.take<uint32_t>(N);
     W.active = c.take<uint32_t>(N);
     const size_t C = shadow_cap;
     W.sox = c.take<double>(C); W.soy = c.take<double>(C); W.soz = c.take<double>(C); W.sdx = c.take<double>(C); W.sdy = c.take<double>(C); W.sdz = c.take<double>(C);
@@ -288,32 +295,49 @@ static void carve_wave(Wave& W, Carver& c, uint32_t N, uint32_t shadow_cap, uint
 struct HostCounters { IterCounters it; RunCounters run; };
 
 // Runs waves until the work counter is exhausted and no path is alive.
-static int32_t run_wave(lumo_scene* sc, const Wave& W, const WaveParams& P, uint64_t& iterations) {
+template <int K>
+static void launch_shade_kind(lumo_scene* sc, const Wave& W, const WaveParams& P, int grid, int nee_grid, cudaStream_t st, unsigned long long& launches) {
+    if (!(sc->kind_mask & (1u << K))) return;
+    k_scatter<K><<<grid, 128, 0, st>>>(sc->S, W, P);
+    k_nee<K><<<nee_grid, 128, 0, st>>>(sc->S, W, P);
+    launches += 2;
+}
+
+// Runs waves until the work counter is exhausted and no path is alive.
+static int32_t run_wave(lumo_scene* sc, const Wave& W, WaveParams P, uint64_t& iterations) {
     lumo_ctx* ctx = sc->ctx;
     cudaStream_t st = ctx->stream;
     HostCounters* hc = (HostCounters*)ctx->host_pinned;
     const int tgrid = trace_grid(ctx);
     const int rgrid = (int)std::min<uint64_t>((W.n_slots + 255) / 256, (uint64_t)ctx->sm_count * 16);
     const int sgrid = ctx->sm_count * 16;
+    const int ngrid = (int)std::min<uint64_t>(((uint64_t)W.n_slots * 2 * sc->S.P.n_shadow_rays + 127) / 128, (uint64_t)ctx->sm_count * 32);
     CU(cudaMemsetAsync(W.flags, 0, (size_t)W.n_slots * 4, st));
     CU(cudaMemsetAsync(&W.run->next_work, 0, 8, st));
+    P.cur = 0;
     for (;;) {
         CU(cudaMemsetAsync(W.it, 0, sizeof(IterCounters), st));
         CU(cudaEventRecord(ctx->kev[0], st));
         k_regen<<<rgrid, 256, 0, st>>>(sc->S, W, P);
         CU(cudaEventRecord(ctx->kev[1], st));
-        if (ctx->count_visits) k_wave_trace<true><<<tgrid, 128, 0, st>>>(sc->S, W, ctx->d_visit); else k_wave_trace<false><<<tgrid, 128, 0, st>>>(sc->S, W, nullptr);
+        if (ctx->count_visits) k_wave_trace<true><<<tgrid, 128, 0, st>>>(sc->S, W, P.cur, ctx->d_visit); else k_wave_trace<false><<<tgrid, 128, 0, st>>>(sc->S, W, P.cur, nullptr);
         CU(cudaEventRecord(ctx->kev[2], st));
-        k_wave_shade<<<sgrid, 128, 0, st>>>(sc->S, W, P);
+        k_terminal<<<sgrid, 128, 0, st>>>(sc->S, W, P);
+        ctx->launches += 3;
+        launch_shade_kind<LMAT_LAMBERTIAN>(sc, W, P, sgrid, ngrid, st, ctx->launches);
+        launch_shade_kind<LMAT_MFDIFFUSE>(sc, W, P, sgrid, ngrid, st, ctx->launches);
+        launch_shade_kind<LMAT_MFCONDUCTOR>(sc, W, P, sgrid, ngrid, st, ctx->launches);
+        launch_shade_kind<LMAT_MFDIELECTRIC>(sc, W, P, sgrid, ngrid, st, ctx->launches);
         CU(cudaEventRecord(ctx->kev[3], st));
         if (ctx->count_visits) k_wave_occlude<true><<<tgrid, 128, 0, st>>>(sc->S, W, ctx->d_visit + 1); else k_wave_occlude<false><<<tgrid, 128, 0, st>>>(sc->S, W, nullptr);
         CU(cudaEventRecord(ctx->kev[4], st));
-        ctx->launches += 4; iterations++;
+        ctx->launches += 1; iterations++;
         CU(cudaMemcpyAsync(hc, W.it, sizeof(IterCounters), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         CU(cudaGetLastError());
         if (P.mode == WM_MAIN) for (int k = 0; k < 4; k++) { float ms = 0; CU(cudaEventElapsedTime(&ms, ctx->kev[k], ctx->kev[k + 1])); ctx->kernel_ms[k] += ms; ctx->kernel_launches[k]++; }
         if (hc->it.n_active == 0) break;
+        P.cur ^= 1u;
     }
     // the last regen found nothing alive: every finished path has been retired into the film
     return LUMO_OK;

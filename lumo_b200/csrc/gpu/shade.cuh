@@ -398,9 +398,13 @@ __device__ __forceinline__ double refl_pdf_half(const Mat& m, D3 wo, D3 wh) {
 }
 
 // BxDF::f (bxdf.rs:69-106), local frame
+// K = material kind known at compile time (the per-kind shade kernels), or -1 for a runtime switch.
+#define LUMO_KIND(K, m) ((K) < 0 ? (m).kind : (uint32_t)(K))
+template <int K>
 __device__ __noinline__ C4 bx_f(const DevScene& S, const Mat& m, D3 wo, D3 wi, const Lam& l, bool reflection, bool backface, int mode) {
-    if ((!reflection || backface) && bx_is_reflection(m)) return c4(0.0);
-    switch (m.kind) {
+    const uint32_t kind = LUMO_KIND(K, m);
+    if ((!reflection || backface) && kind != LMAT_MFDIELECTRIC) return c4(0.0);
+    switch (kind) {
     case LMAT_LAMBERTIAN: return spec4(m.kd, l) / LUMO_PI;
     case LMAT_MFDIFFUSE: {                                                                                                      // bxdf/microfacet.rs:131-156
         const D3 wh = normalize(wo + wi);
@@ -437,9 +441,11 @@ __device__ __noinline__ C4 bx_f(const DevScene& S, const Mat& m, D3 wo, D3 wi, c
     }
 }
 // BxDF::sample (bxdf.rs:108-131); may terminate the secondary wavelengths (dispersion)
+template <int K>
 __device__ __noinline__ bool bx_sample(const DevScene& S, const Mat& m, D3 wo, bool backface, Lam& l, double ru, double r0, double r1, D3& wi) {
-    if (backface && bx_is_reflection(m)) return false;
-    switch (m.kind) {
+    const uint32_t kind = LUMO_KIND(K, m);
+    if (backface && kind != LMAT_MFDIELECTRIC) return false;
+    switch (kind) {
     case LMAT_LAMBERTIAN: wi = square_to_cos_hemisphere(r0, r1); return true;
     case LMAT_MFDIFFUSE: {                                                                                                      // bxdf/microfacet.rs:159-177
         const double pr = f_schlick(0.04, 1.0, wo.z), ps = 1.0 - pr;
@@ -463,9 +469,11 @@ __device__ __noinline__ bool bx_sample(const DevScene& S, const Mat& m, D3 wo, b
     }
 }
 // BxDF::pdf (bxdf.rs:133-151)
+template <int K>
 __device__ __noinline__ double bx_pdf(const DevScene& S, const Mat& m, D3 wo, D3 wi, bool reflection, const Lam& l) {
-    if (!reflection && bx_is_reflection(m)) return 0.0;
-    switch (m.kind) {
+    const uint32_t kind = LUMO_KIND(K, m);
+    if (!reflection && kind != LMAT_MFDIELECTRIC) return 0.0;
+    switch (kind) {
     case LMAT_LAMBERTIAN: return lambertian_pdf(wo, wi);
     case LMAT_MFDIFFUSE: {                                                                                                      // bxdf/microfacet.rs:180-205
         if (!same_hemisphere(wi, wo)) return 0.0;
@@ -498,26 +506,28 @@ __device__ __noinline__ double bx_pdf(const DevScene& S, const Mat& m, D3 wo, D3
     default: return 0.0;
     }
 }
-// BSDF wrappers (bsdf.rs:28-90) + Material dispatch (material.rs:245-312)
+// BSDF wrappers (bsdf.rs:28-90) + Material dispatch (material.rs:245-312).  The shading frame is a
+// pure function of the shading normal (bsdf.rs:41-46 rebuilds it per call); callers that evaluate the
+// BSDF several times at one hit pass the frame in.
 __device__ __forceinline__ bool is_reflection(D3 wo, D3 wi, D3 ng) { return dot(ng, wi) * dot(ng, wo) >= 0.0; }
-__device__ __forceinline__ C4 bsdf_f(const DevScene& S, const Mat& m, D3 wo, D3 wi, const Lam& l, int mode, const DevHit& h) {
-    if (!mat_is_standard(m)) return c4(0.0);
-    const Onb uvw = onb_new(h.ns);
-    return bx_f(S, m, to_local(uvw, wo), to_local(uvw, wi), l, is_reflection(wo, wi, h.ng), h.backface, mode);
+template <int K>
+__device__ __forceinline__ C4 bsdf_f(const DevScene& S, const Mat& m, const Onb& uvw, D3 wo, D3 wi, const Lam& l, int mode, const DevHit& h) {
+    if (K < 0 && !mat_is_standard(m)) return c4(0.0);
+    return bx_f<K>(S, m, to_local(uvw, wo), to_local(uvw, wi), l, is_reflection(wo, wi, h.ng), h.backface, mode);
 }
-__device__ __forceinline__ bool bsdf_sample(const DevScene& S, const Mat& m, D3 wo, const DevHit& h, Lam& l, double ru, double r0, double r1, D3& wi) {
-    if (!mat_is_standard(m)) return false;
-    const Onb uvw = onb_new(h.ns);
+template <int K>
+__device__ __forceinline__ bool bsdf_sample(const DevScene& S, const Mat& m, const Onb& uvw, D3 wo, const DevHit& h, Lam& l, double ru, double r0, double r1, D3& wi) {
+    if (K < 0 && !mat_is_standard(m)) return false;
     D3 wl;
-    if (!bx_sample(S, m, to_local(uvw, wo), h.backface, l, ru, r0, r1, wl)) return false;
+    if (!bx_sample<K>(S, m, to_local(uvw, wo), h.backface, l, ru, r0, r1, wl)) return false;
     wi = to_world(uvw, wl);
     return true;
 }
-__device__ __forceinline__ double bsdf_pdf(const DevScene& S, const Mat& m, D3 wo, D3 wi, const DevHit& h, const Lam& l, bool swap_dir) {
+template <int K>
+__device__ __forceinline__ double bsdf_pdf(const DevScene& S, const Mat& m, const Onb& uvw, D3 wo, D3 wi, const DevHit& h, const Lam& l, bool swap_dir) {
     if (swap_dir) { const D3 t = wo; wo = wi; wi = t; }
-    if (!mat_is_standard(m)) return 0.0;
-    const Onb uvw = onb_new(h.ns);
-    return bx_pdf(S, m, to_local(uvw, wo), to_local(uvw, wi), is_reflection(wo, wi, h.ng), l);
+    if (K < 0 && !mat_is_standard(m)) return 0.0;
+    return bx_pdf<K>(S, m, to_local(uvw, wo), to_local(uvw, wi), is_reflection(wo, wi, h.ng), l);
 }
 
 // ---- lights: Sampleable (object.rs:98-157, rectangle.rs:107-133, triangle.rs:207-241, sphere.rs:104-207, instance.rs:132-199)

@@ -23,29 +23,36 @@
 namespace lumo_dev {
 namespace cg = cooperative_groups;
 
-enum { PF_ALIVE = 1u, PF_LAST_SPECULAR = 2u, PF_DONE = 4u };
+enum { PF_ALIVE = 1u, PF_LAST_SPECULAR = 2u, PF_DONE = 4u, PF_NEE = 8u };
 enum { WM_MAIN = 0, WM_PILOT = 1 };
 #define LUMO_RR_DEPTH 5u           /* path_trace.rs:3 */
 #define LUMO_DL_MAX_RECURSION 50u  /* direct_light.rs:6 */
 #define LUMO_PILOT_N 64u
+#define LUMO_N_CLASSES 5           /* shade queues: 0 = terminal (miss / light / blank), 1..4 = LumoMatKind of a Standard material */
 
 struct IterCounters {   // zeroed before every iteration
-    uint32_t n_active, n_shadow, trace_next, shade_next, occl_next, pad[3];
+    uint32_t n_active, n_shadow, trace_next, occl_next;
+    uint32_t n_class[LUMO_N_CLASSES], pad[3];
 };
 struct RunCounters {    // zeroed once per render
     unsigned long long next_work, camera_paths, closest, occlusion, cost, shadow_queued, shadow_dropped, nonfinite;
     uint32_t max_depth, pad;
 };
 
+// Path state, structure of arrays.  Ray, throughput and RNG position are double-buffered: the scatter
+// kernel writes the NEXT bounce's values into buffer cur^1 while the NEE kernel of the same iteration
+// still reads this bounce's values from buffer cur.
 struct Wave {
     uint32_t n_slots, shadow_cap;
-    // path state (SoA; colour arrays are [k * n_slots + slot])
-    double *ox, *oy, *oz, *dx, *dy, *dz;
+    double *ox[2], *oy[2], *oz[2], *dx[2], *dy[2], *dz[2];
+    double* gathered[2];                 // [k * n_slots + slot]
+    uint32_t* draws[2];
     double *ht, *hb0, *hb1, *hb2; uint32_t *hobj, *htri;
-    double *gathered, *radiance, *lam;
+    double *radiance, *lam;              // [k * n_slots + slot]
     double *rx, *ry;
-    uint32_t *pixel, *sample, *depth, *draws, *flags, *witem;
+    uint32_t *pixel, *sample, *depth, *flags, *witem;
     uint32_t* active;
+    uint32_t* cls[LUMO_N_CLASSES];       // per-class shade queues (slot indices)
     // shadow queue (SoA)
     double *sox, *soy, *soz, *sdx, *sdy, *sdz, *stmax, *sc; uint32_t* sslot;
     IterCounters* it; RunCounters* run;
@@ -59,8 +66,8 @@ struct WaveParams {
     uint32_t integrator, sampler, tone_map, mode;
     double tone_map_arg;
     uint32_t spp_begin, spp_count, total_spp, pilot_round;
-    uint32_t tiles_x, tiles_y, debug_pixel, pad1;   // debug_pixel: LUMO_DEBUG_PIXEL env (printf trace of one pixel's paths), LUMO_NONE = off
-};
+    uint32_t tiles_x, tiles_y, debug_pixel, cur;   // debug_pixel: LUMO_DEBUG_PIXEL env (printf trace of one pixel's paths), LUMO_NONE = off
+};                                                  // cur: which half of the double-buffered state holds this iteration's rays
 
 __device__ __forceinline__ uint32_t agg_inc(uint32_t* ctr) {   // warp-aggregated atomicAdd(ctr, 1)
     cg::coalesced_group g = cg::coalesced_threads();
@@ -105,7 +112,7 @@ __device__ __forceinline__ void raster_jitter(const WaveParams& P, uint32_t pixe
 
 // ---- regen: retire, refill, compact -------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_regen(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P) {
-    const uint32_t N = W.n_slots;
+    const uint32_t N = W.n_slots, c = P.cur;
     for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < N; slot += gridDim.x * blockDim.x) {
         uint32_t f = W.flags[slot];
         if (f & PF_DONE) {
@@ -159,10 +166,10 @@ __global__ void __launch_bounds__(256) k_regen(const __grid_constant__ DevScene 
                         const double l0 = rng_float(rng), l1 = rng_float(rng);                 // integrator.rs:56-57
                         const Ray r = camera_generate_ray(S.P.camera, rx, ry, l0, l1);
                         const Lam lam = lam_sample(rng_float(rng));
-                        W.ox[slot] = r.o.x; W.oy[slot] = r.o.y; W.oz[slot] = r.o.z; W.dx[slot] = r.d.x; W.dy[slot] = r.d.y; W.dz[slot] = r.d.z;
-                        for (int k = 0; k < 4; k++) { W.lam[(size_t)k * N + slot] = lam.l[k]; W.gathered[(size_t)k * N + slot] = 1.0; W.radiance[(size_t)k * N + slot] = 0.0; }
+                        W.ox[c][slot] = r.o.x; W.oy[c][slot] = r.o.y; W.oz[c][slot] = r.o.z; W.dx[c][slot] = r.d.x; W.dy[c][slot] = r.d.y; W.dz[c][slot] = r.d.z;
+                        for (int k = 0; k < 4; k++) { W.lam[(size_t)k * N + slot] = lam.l[k]; W.gathered[c][(size_t)k * N + slot] = 1.0; W.radiance[(size_t)k * N + slot] = 0.0; }
                         W.rx[slot] = rx; W.ry[slot] = ry;
-                        W.pixel[slot] = pixel; W.sample[slot] = sample; W.depth[slot] = 0u; W.draws[slot] = rng.draws; W.witem[slot] = (uint32_t)w;
+                        W.pixel[slot] = pixel; W.sample[slot] = sample; W.depth[slot] = 0u; W.draws[c][slot] = rng.draws; W.witem[slot] = (uint32_t)w;
                         f = PF_ALIVE | PF_LAST_SPECULAR;
                     }
                 }
@@ -173,9 +180,9 @@ __global__ void __launch_bounds__(256) k_regen(const __grid_constant__ DevScene 
     }
 }
 
-// ---- trace: Scene::hit over the active queue ------------------------------------------------------
+// ---- trace: Scene::hit over the active queue, then binning by what the shading stage has to do --------
 template <bool CNT>
-__global__ void __launch_bounds__(128) k_wave_trace(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, Counters* gc) {
+__global__ void __launch_bounds__(128) k_wave_trace(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, uint32_t cur, Counters* gc) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t n = W.it->n_active;
     Counters cnt = {0, 0, 0, 0, 0, 0};
@@ -185,13 +192,28 @@ __global__ void __launch_bounds__(128) k_wave_trace(const __grid_constant__ DevS
         base = __shfl_sync(0xFFFFFFFFu, base, 0);
         if (base >= n) break;
         const uint32_t i = base + lane;
+        uint32_t slot = 0, klass = LUMO_N_CLASSES;
         if (i < n) {
-            const uint32_t slot = W.active[i];
-            Ray r; r.o = d3(W.ox[slot], W.oy[slot], W.oz[slot]); r.d = d3(W.dx[slot], W.dy[slot], W.dz[slot]);
+            slot = W.active[i];
+            Ray r; r.o = d3(W.ox[cur][slot], W.oy[cur][slot], W.oz[cur][slot]); r.d = d3(W.dx[cur][slot], W.dy[cur][slot], W.dz[cur][slot]);
             HitRec h;
+            klass = 0;
             if (scene_hit<CNT>(S, r, LUMO_INF, h, &cnt)) {
                 W.ht[slot] = h.t; W.hb0[slot] = h.bary.x; W.hb1[slot] = h.bary.y; W.hb2[slot] = h.bary.z; W.hobj[slot] = h.obj; W.htri[slot] = h.tri;
+                const uint32_t kind = S.materials[S.objects[h.obj].material].kind;
+                if (kind >= LMAT_LAMBERTIAN && kind <= LMAT_MFDIELECTRIC) klass = kind;
             } else W.hobj[slot] = LUMO_NONE;
+        }
+        // stream compaction into the per-class shade queues (one atomic per class per warp)
+#pragma unroll
+        for (uint32_t c = 0; c < LUMO_N_CLASSES; c++) {
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, klass == c);
+            if (m) {
+                uint32_t b = 0;
+                if (lane == (uint32_t)(__ffs(m) - 1)) b = atomicAdd(&W.it->n_class[c], (uint32_t)__popc(m));
+                b = __shfl_sync(0xFFFFFFFFu, b, __ffs(m) - 1);
+                if (klass == c) W.cls[c][b + __popc(m & ((1u << lane) - 1u))] = slot;
+            }
         }
     }
     if (lane == 0 && threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(&W.run->closest, (unsigned long long)n);
@@ -224,6 +246,14 @@ __global__ void __launch_bounds__(128) k_wave_occlude(const __grid_constant__ De
 }
 
 // ---- shade ------------------------------------------------------------------------------------------
+// The shading stage of one iteration is three kinds of kernels over the per-class queues:
+//   k_terminal   class 0: the ray missed, or hit a Light / Blank material (bsdf_sample -> None):
+//                emission if the previous bounce was specular (path_trace.rs:24-29), path ends;
+//   k_scatter<K> class K: the BSDF sample of this bounce, throughput update, Russian roulette, next ray
+//                (path_trace.rs:23,42-78; direct_light.rs:23-68) — decides whether NEE runs;
+//   k_nee<K>     class K x shadow sample x {light sample, BSDF sample}: integrator.rs:74-184, one thread
+//                per MIS term; the occlusion half of hit_light goes to the shadow queue.
+// One material family per kernel keeps warps on one code path and the instruction footprint small.
 __device__ __forceinline__ void push_shadow(const Wave& W, uint32_t slot, const Ray& r, double t_max, const C4& c) {
     const uint32_t i = agg_inc(&W.it->n_shadow);
     if (i >= W.shadow_cap) { atomicAdd(&W.run->shadow_dropped, 1ull); return; }
@@ -231,116 +261,144 @@ __device__ __forceinline__ void push_shadow(const Wave& W, uint32_t slot, const 
     W.stmax[i] = t_max; W.sslot[i] = slot;
     for (int k = 0; k < 4; k++) W.sc[(size_t)k * W.shadow_cap + i] = c.s[k];
 }
-// integrator.rs:139-184
-__device__ __noinline__ C4 mis_sample(const DevScene& S, const Mat& m, D3 wo, D3 wi, const DevHit& ho, const DevHit& hi, const Lam& lam, bool li, double p_lig, double p_sct) {
-    if (p_lig == 0.0 || p_sct == 0.0) return c4(0.0);
-    const C4 bsdf = bsdf_f(S, m, wo, wi, lam, 0, ho);
-    const double denom = p_lig * p_lig + p_sct * p_sct;
-    const double weight = li ? (p_lig * p_lig) / denom : (p_sct * p_sct) / denom;
-    const double p_denom = li ? p_lig : p_sct;
-    return bsdf * c4(1.0) * mat_emit(S, S.materials[hi.material], lam, hi.backface) * shading_cosine(m, wi, ho.ns) * weight / p_denom;
+__device__ __forceinline__ void load_path(const Wave& W, uint32_t cur, uint32_t slot, Ray& ro, HitRec& rec) {
+    ro.o = d3(W.ox[cur][slot], W.oy[cur][slot], W.oz[cur][slot]); ro.d = d3(W.dx[cur][slot], W.dy[cur][slot], W.dz[cur][slot]);
+    rec.t = W.ht[slot]; rec.bary = d3(W.hb0[slot], W.hb1[slot], W.hb2[slot]); rec.obj = W.hobj[slot]; rec.tri = W.htri[slot];
 }
-// integrator.rs:74-137: light pick -> light sample + BSDF sample, MIS-weighted; the occlusion half of
-// hit_light is deferred to k_wave_occlude with the finished contribution attached.
-__device__ __noinline__ void shadow_rays(const DevScene& S, const Wave& W, uint32_t slot, const Mat& m, D3 wo, const C4& gathered, Lam& lam, const DevHit& ho, Rng& rng, bool dbg) {
-    const uint32_t n = S.P.n_shadow_rays;
-    for (uint32_t i = 0; i < n; i++) {
-        const uint32_t li = sample_light(S, rng_float(rng));
-        const double pdf_light = S.lights[li].pdf;
-        const uint32_t lobj = S.P.n_objects + li;
-        const LumoObject lo = S.objects[lobj];
-        {
-            const double r0 = rng_float(rng), r1 = rng_float(rng);
-            const D3 wi = light_sample_towards(S, lo, ho.p, r0, r1);
-            const Ray ri = hit_generate_ray(ho, wi);
-            DevHit hi;
-            if (light_hit(S, lobj, ri, hi)) {
-                const double p_lig = light_sample_towards_pdf(S, lo, ri, hi.p, hi.ng);
-                const double p_sct = bsdf_pdf(S, m, wo, wi, ho, lam, false);
-                const C4 c = mis_sample(S, m, wo, wi, ho, hi, lam, true, p_lig, p_sct);
-                if (dbg) printf("  [gpu] A vis t=%.17g p_lig=%.17g p_sct=%.17g c0=%.17g\n", hi.t, p_lig, p_sct, c.s[0]);
-                if (!is_black(c)) push_shadow(W, slot, ri, hi.t - LUMO_EPS, gathered * (c / pdf_light) / (double)n);
-            }
+// dispersion (bxdf/microfacet.rs:282-286): a dielectric with a non-constant eta keeps only the hero wavelength
+template <int K> __device__ __forceinline__ void maybe_terminate(const Mat& m, Lam& l) {
+    if (K == LMAT_MFDIELECTRIC && !(m.flags & LMF_ETA_CONST)) { l.l[1] = 0.0; l.l[2] = 0.0; l.l[3] = 0.0; }
+}
+
+__global__ void __launch_bounds__(128) k_terminal(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P) {
+    const uint32_t N = W.n_slots, n = W.it->n_class[0];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t slot = W.cls[0][i];
+        const uint32_t f = W.flags[slot];
+        if (W.hobj[slot] != LUMO_NONE && (P.integrator == 1 || (f & PF_LAST_SPECULAR))) {
+            Ray ro; HitRec rec; load_path(W, P.cur, slot, ro, rec);
+            const DevHit ho = reconstruct_hit(S, ro, rec);
+            const Mat& m = S.materials[ho.material];
+            Lam lam; for (int k = 0; k < 4; k++) lam.l[k] = W.lam[(size_t)k * N + slot];
+            const C4 e = load_c4(W.gathered[P.cur], N, slot) * mat_emit(S, m, lam, ho.backface);
+            if (!is_black(e)) { C4 rad = load_c4(W.radiance, N, slot); rad = rad + e; store_c4(W.radiance, N, slot, rad); }
         }
-        const double ru = rng_float(rng), r0 = rng_float(rng), r1 = rng_float(rng);
-        D3 wi;
-        if (bsdf_sample(S, m, wo, ho, lam, ru, r0, r1, wi)) {
-            const Ray ri = hit_generate_ray(ho, wi);
-            DevHit hi;
-            if (light_hit(S, lobj, ri, hi)) {
-                const double p_lig = light_sample_towards_pdf(S, lo, ri, hi.p, hi.ng);
-                const double p_sct = bsdf_pdf(S, m, wo, wi, ho, lam, false);
-                const C4 c = mis_sample(S, m, wo, wi, ho, hi, lam, false, p_lig, p_sct);
-                if (dbg) printf("  [gpu] B vis t=%.17g p_lig=%.17g p_sct=%.17g c0=%.17g\n", hi.t, p_lig, p_sct, c.s[0]);
-                if (!is_black(c)) push_shadow(W, slot, ri, hi.t - LUMO_EPS, gathered * (c / pdf_light) / (double)n);
-            }
-        }
+        W.flags[slot] = PF_DONE;
     }
 }
 
-// One bounce of path_trace::integrate (path_trace.rs:18-78) or direct_light::integrate
-// (direct_light.rs:14-70) for every live path.
-__global__ void __launch_bounds__(128) k_wave_shade(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P) {
-    const uint32_t N = W.n_slots;
-    const uint32_t n = W.it->n_active;
+template <int K>
+__global__ void __launch_bounds__(128) k_scatter(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P) {
+    const uint32_t N = W.n_slots, n = W.it->n_class[K], cur = P.cur, nxt = P.cur ^ 1u;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t slot = W.active[i];
-        uint32_t f = W.flags[slot];
-        if (W.hobj[slot] == LUMO_NONE) { W.flags[slot] = PF_DONE; continue; }
-        Ray ro; ro.o = d3(W.ox[slot], W.oy[slot], W.oz[slot]); ro.d = d3(W.dx[slot], W.dy[slot], W.dz[slot]);
-        HitRec rec; rec.t = W.ht[slot]; rec.bary = d3(W.hb0[slot], W.hb1[slot], W.hb2[slot]); rec.obj = W.hobj[slot]; rec.tri = W.htri[slot];
+        const uint32_t slot = W.cls[K][i];
+        Ray ro; HitRec rec; load_path(W, cur, slot, ro, rec);
         const DevHit ho = reconstruct_hit(S, ro, rec);
         const Mat& m = S.materials[ho.material];
+        const Onb uvw = onb_new(ho.ns);
         const uint32_t pixel = W.pixel[slot];
-        Rng rng = rng_make(P.seed, pixel, W.sample[slot], 0u, W.draws[slot]);
+        Rng rng = rng_make(P.seed, pixel, W.sample[slot], 0u, W.draws[cur][slot]);
         Lam lam; for (int k = 0; k < 4; k++) lam.l[k] = W.lam[(size_t)k * N + slot];
-        C4 gathered = load_c4(W.gathered, N, slot);
+        C4 gathered = load_c4(W.gathered[cur], N, slot);
         uint32_t depth = W.depth[slot];
         const D3 wo = -ro.d;
         const bool dbg = pixel == P.debug_pixel && P.mode == WM_MAIN;
         if (dbg) printf("[gpu] depth=%u obj=%u tri=%u t=%.17g g0=%.17g rad0=%.17g\n", depth, rec.obj, rec.tri, rec.t, gathered.s[0], W.radiance[slot]);
         const double ru = rng_float(rng), r0 = rng_float(rng), r1 = rng_float(rng);
         D3 wi;
-        bool done = false;
-        if (!bsdf_sample(S, m, wo, ho, lam, ru, r0, r1, wi)) {
-            if (P.integrator == 1 || (f & PF_LAST_SPECULAR)) {
-                const C4 e = gathered * mat_emit(S, m, lam, ho.backface);
-                if (!is_black(e)) { C4 rad = load_c4(W.radiance, N, slot); rad = rad + e; store_c4(W.radiance, N, slot, rad); }
-            }
-            done = true;
-        } else if (P.integrator == 1) {
-            if (!mat_is_specular(m)) { shadow_rays(S, W, slot, m, wo, gathered, lam, ho, rng, dbg); done = true; }
+        uint32_t f = 0;
+        bool done = false, nee = false;
+        if (!bsdf_sample<K>(S, m, uvw, wo, ho, lam, ru, r0, r1, wi)) done = true;   // a Standard material emits nothing (material.rs:220-231)
+        else if (P.integrator == 1) {
+            if (!mat_is_specular(m)) { nee = true; done = true; }
             else if (depth >= LUMO_DL_MAX_RECURSION) done = true;
-        } else {
-            if (!mat_is_delta(S, m, lam)) shadow_rays(S, W, slot, m, wo, gathered, lam, ho, rng, dbg);
-        }
+        } else nee = !mat_is_delta(S, m, lam);
+        if (nee) rng.draws += 6u * S.P.n_shadow_rays;      // the draws k_nee consumes (integrator.rs:96-118)
         if (!done) {
             const Ray ri = hit_generate_ray(ho, wi);
             wi = ri.d;
-            const double p_scatter = bsdf_pdf(S, m, wo, wi, ho, lam, false);
+            const double p_scatter = bsdf_pdf<K>(S, m, uvw, wo, wi, ho, lam, false);
             if (p_scatter <= 0.0) done = true;
             else {
-                const C4 bsdf = bsdf_f(S, m, wo, wi, lam, 0, ho);
+                const C4 bsdf = bsdf_f<K>(S, m, uvw, wo, wi, lam, 0, ho);
                 gathered = gathered * (bsdf * shading_cosine(m, wi, ho.ns) / p_scatter);
                 if (P.integrator == 0 && depth >= LUMO_RR_DEPTH) {
                     const double delta = W.tile_delta[tile_of(P, S, pixel)];
                     const double lum = luminance(S, gathered, lam);
                     const double rr = fmin(lum / delta, 1.0);
+                    rng = rng_make(P.seed, pixel, W.sample[slot], 0u, rng.draws);
                     if (rng_float(rng) > rr) done = true;
                     else gathered = gathered / rr;
                 }
                 if (!done) {
                     f = PF_ALIVE | (mat_is_specular(m) ? PF_LAST_SPECULAR : 0u);
-                    depth += 1u;
-                    W.ox[slot] = ri.o.x; W.oy[slot] = ri.o.y; W.oz[slot] = ri.o.z; W.dx[slot] = ri.d.x; W.dy[slot] = ri.d.y; W.dz[slot] = ri.d.z;
-                    store_c4(W.gathered, N, slot, gathered);
-                    W.depth[slot] = depth;
+                    W.ox[nxt][slot] = ri.o.x; W.oy[nxt][slot] = ri.o.y; W.oz[nxt][slot] = ri.o.z; W.dx[nxt][slot] = ri.d.x; W.dy[nxt][slot] = ri.d.y; W.dz[nxt][slot] = ri.d.z;
+                    store_c4(W.gathered[nxt], N, slot, gathered);
+                    W.depth[slot] = depth + 1u;
+                    W.draws[nxt][slot] = rng.draws;
                 }
             }
         }
-        for (int k = 0; k < 4; k++) W.lam[(size_t)k * N + slot] = lam.l[k];
-        W.draws[slot] = rng.draws;
-        W.flags[slot] = done ? PF_DONE : f;
+        if (K == LMAT_MFDIELECTRIC) for (int k = 1; k < 4; k++) W.lam[(size_t)k * N + slot] = lam.l[k];
+        W.flags[slot] = (done ? PF_DONE : f) | (nee ? PF_NEE : 0u);
+    }
+}
+
+// integrator.rs:139-184
+template <int K>
+__device__ __forceinline__ C4 mis_sample(const DevScene& S, const Mat& m, const Onb& uvw, D3 wo, D3 wi, const DevHit& ho, const DevHit& hi, const Lam& lam, bool li, double p_lig, double p_sct) {
+    if (p_lig == 0.0 || p_sct == 0.0) return c4(0.0);
+    const C4 bsdf = bsdf_f<K>(S, m, uvw, wo, wi, lam, 0, ho);
+    const double denom = p_lig * p_lig + p_sct * p_sct;
+    const double weight = li ? (p_lig * p_lig) / denom : (p_sct * p_sct) / denom;
+    const double p_denom = li ? p_lig : p_sct;
+    return bsdf * c4(1.0) * mat_emit(S, S.materials[hi.material], lam, hi.backface) * shading_cosine(m, wi, ho.ns) * weight / p_denom;
+}
+
+// One thread per MIS term of integrator.rs:89-137: item = (queue entry, shadow sample i, A = light sample | B = BSDF sample).
+template <int K>
+__global__ void __launch_bounds__(128) k_nee(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P) {
+    const uint32_t N = W.n_slots, nq = W.it->n_class[K], cur = P.cur;
+    const uint32_t ns = S.P.n_shadow_rays, per = 2u * ns;
+    const unsigned long long total = (unsigned long long)nq * per;
+    for (unsigned long long it = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; it < total; it += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t slot = W.cls[K][(uint32_t)(it / per)];
+        if (!(W.flags[slot] & PF_NEE)) continue;
+        const uint32_t j = (uint32_t)(it % per), i = j >> 1;
+        const bool b_term = (j & 1u) != 0u;
+        Ray ro; HitRec rec; load_path(W, cur, slot, ro, rec);
+        const DevHit ho = reconstruct_hit(S, ro, rec);
+        const Mat& m = S.materials[ho.material];
+        const Onb uvw = onb_new(ho.ns);
+        const uint32_t pixel = W.pixel[slot];
+        Lam lam; for (int k = 0; k < 4; k++) lam.l[k] = W.lam[(size_t)k * N + slot];   // already terminated by k_scatter if dispersive
+        const C4 gathered = load_c4(W.gathered[cur], N, slot);
+        const D3 wo = -ro.d;
+        const bool dbg = pixel == P.debug_pixel && P.mode == WM_MAIN;
+        // draws of this bounce: 3 for the scatter sample, then 6 per shadow sample: light pick, light point (2), BSDF sample (3)
+        Rng rng = rng_make(P.seed, pixel, W.sample[slot], 0u, W.draws[cur][slot] + 3u + 6u * i);
+        const uint32_t li = sample_light(S, rng_float(rng));
+        const double pdf_light = S.lights[li].pdf;
+        const uint32_t lobj = S.P.n_objects + li;
+        const LumoObject lo = S.objects[lobj];
+        D3 wi;
+        if (!b_term) {
+            const double r0 = rng_float(rng), r1 = rng_float(rng);
+            wi = light_sample_towards(S, lo, ho.p, r0, r1);
+        } else {
+            rng = rng_make(P.seed, pixel, W.sample[slot], 0u, W.draws[cur][slot] + 3u + 6u * i + 3u);
+            const double ru = rng_float(rng), r0 = rng_float(rng), r1 = rng_float(rng);
+            Lam l2 = lam;
+            if (!bsdf_sample<K>(S, m, uvw, wo, ho, l2, ru, r0, r1, wi)) continue;
+        }
+        const Ray ri = hit_generate_ray(ho, wi);
+        DevHit hi;
+        if (!light_hit(S, lobj, ri, hi)) continue;
+        const double p_lig = light_sample_towards_pdf(S, lo, ri, hi.p, hi.ng);
+        const double p_sct = bsdf_pdf<K>(S, m, uvw, wo, wi, ho, lam, false);
+        const C4 c = mis_sample<K>(S, m, uvw, wo, wi, ho, hi, lam, !b_term, p_lig, p_sct);
+        if (dbg) printf("  [gpu] %c vis t=%.17g p_lig=%.17g p_sct=%.17g c0=%.17g\n", b_term ? 'B' : 'A', hi.t, p_lig, p_sct, c.s[0]);
+        if (!is_black(c)) push_shadow(W, slot, ri, hi.t - LUMO_EPS, gathered * (c / pdf_light) / (double)ns);
     }
 }
 
