@@ -16,6 +16,8 @@ static thread_local std::string g_err;
 static int32_t fail(int32_t code, const std::string& msg) { g_err = msg; return code; }
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(e_ == cudaErrorMemoryAllocation ? LUMO_ERR_OOM : LUMO_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
 
+#define LUMO_ITER_BATCH 4   /* wave iterations enqueued per host synchronisation */
+
 struct lumo_ctx {
     int device = 0, sm_count = 0;
     cudaStream_t stream = nullptr, own_stream = nullptr;
@@ -27,7 +29,7 @@ struct lumo_ctx {
     Counters* d_visit = nullptr;   // traversal visit counters (CNT passes): [0] closest-hit kernels, [1] occlusion kernels
     int count_visits = 0;
     // per-kernel-class device time of the last render (CUDA events on the launching stream)
-    cudaEvent_t kev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t kev[5 * LUMO_ITER_BATCH] = {};
     double kernel_ms[4] = {0, 0, 0, 0}; unsigned long long kernel_launches[4] = {0, 0, 0, 0};
 };
 struct lumo_scene {
@@ -315,29 +317,38 @@ static int32_t run_wave(lumo_scene* sc, const Wave& W, WaveParams P, uint64_t& i
     CU(cudaMemsetAsync(W.flags, 0, (size_t)W.n_slots * 4, st));
     CU(cudaMemsetAsync(&W.run->next_work, 0, 8, st));
     P.cur = 0;
+    // Kernels read their queue sizes from device memory, so several iterations are enqueued back to back
+    // and the host looks at the live-path count only once per batch (an iteration over empty queues costs
+    // a few microseconds).
+    const int BATCH = LUMO_ITER_BATCH;
     for (;;) {
-        CU(cudaMemsetAsync(W.it, 0, sizeof(IterCounters), st));
-        CU(cudaEventRecord(ctx->kev[0], st));
-        k_regen<<<rgrid, 256, 0, st>>>(sc->S, W, P);
-        CU(cudaEventRecord(ctx->kev[1], st));
-        if (ctx->count_visits) k_wave_trace<true><<<tgrid, 128, 0, st>>>(sc->S, W, P.cur, ctx->d_visit); else k_wave_trace<false><<<tgrid, 128, 0, st>>>(sc->S, W, P.cur, nullptr);
-        CU(cudaEventRecord(ctx->kev[2], st));
-        k_terminal<<<sgrid, 128, 0, st>>>(sc->S, W, P);
-        ctx->launches += 3;
-        launch_shade_kind<LMAT_LAMBERTIAN>(sc, W, P, sgrid, ngrid, st, ctx->launches);
-        launch_shade_kind<LMAT_MFDIFFUSE>(sc, W, P, sgrid, ngrid, st, ctx->launches);
-        launch_shade_kind<LMAT_MFCONDUCTOR>(sc, W, P, sgrid, ngrid, st, ctx->launches);
-        launch_shade_kind<LMAT_MFDIELECTRIC>(sc, W, P, sgrid, ngrid, st, ctx->launches);
-        CU(cudaEventRecord(ctx->kev[3], st));
-        if (ctx->count_visits) k_wave_occlude<true><<<tgrid, 128, 0, st>>>(sc->S, W, ctx->d_visit + 1); else k_wave_occlude<false><<<tgrid, 128, 0, st>>>(sc->S, W, nullptr);
-        CU(cudaEventRecord(ctx->kev[4], st));
-        ctx->launches += 1; iterations++;
+        for (int b = 0; b < BATCH; b++) {
+            cudaEvent_t* ev = ctx->kev + 5 * b;
+            CU(cudaMemsetAsync(W.it, 0, sizeof(IterCounters), st));
+            CU(cudaEventRecord(ev[0], st));
+            k_regen<<<rgrid, 256, 0, st>>>(sc->S, W, P);
+            CU(cudaEventRecord(ev[1], st));
+            if (ctx->count_visits) k_wave_trace<true><<<tgrid, 128, 0, st>>>(sc->S, W, P.cur, ctx->d_visit); else k_wave_trace<false><<<tgrid, 128, 0, st>>>(sc->S, W, P.cur, nullptr);
+            CU(cudaEventRecord(ev[2], st));
+            k_terminal<<<sgrid, 128, 0, st>>>(sc->S, W, P);
+            ctx->launches += 3;
+            launch_shade_kind<LMAT_LAMBERTIAN>(sc, W, P, sgrid, ngrid, st, ctx->launches);
+            launch_shade_kind<LMAT_MFDIFFUSE>(sc, W, P, sgrid, ngrid, st, ctx->launches);
+            launch_shade_kind<LMAT_MFCONDUCTOR>(sc, W, P, sgrid, ngrid, st, ctx->launches);
+            launch_shade_kind<LMAT_MFDIELECTRIC>(sc, W, P, sgrid, ngrid, st, ctx->launches);
+            CU(cudaEventRecord(ev[3], st));
+            if (ctx->count_visits) k_wave_occlude<true><<<tgrid, 128, 0, st>>>(sc->S, W, ctx->d_visit + 1); else k_wave_occlude<false><<<tgrid, 128, 0, st>>>(sc->S, W, nullptr);
+            CU(cudaEventRecord(ev[4], st));
+            ctx->launches += 1; iterations++;
+            P.cur ^= 1u;
+        }
         CU(cudaMemcpyAsync(hc, W.it, sizeof(IterCounters), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         CU(cudaGetLastError());
-        if (P.mode == WM_MAIN) for (int k = 0; k < 4; k++) { float ms = 0; CU(cudaEventElapsedTime(&ms, ctx->kev[k], ctx->kev[k + 1])); ctx->kernel_ms[k] += ms; ctx->kernel_launches[k]++; }
+        if (P.mode == WM_MAIN) for (int b = 0; b < BATCH; b++) for (int k = 0; k < 4; k++) {
+            float ms = 0; CU(cudaEventElapsedTime(&ms, ctx->kev[5 * b + k], ctx->kev[5 * b + k + 1])); ctx->kernel_ms[k] += ms; ctx->kernel_launches[k]++;
+        }
         if (hc->it.n_active == 0) break;
-        P.cur ^= 1u;
     }
     // the last regen found nothing alive: every finished path has been retired into the film
     return LUMO_OK;

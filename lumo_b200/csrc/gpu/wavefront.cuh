@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(256) k_regen(const __grid_constant__ DevScene 
 
 // ---- trace: Scene::hit over the active queue, then binning by what the shading stage has to do --------
 template <bool CNT>
-__global__ void __launch_bounds__(128) k_wave_trace(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, uint32_t cur, Counters* gc) {
+__global__ void __launch_bounds__(128, 8) k_wave_trace(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, uint32_t cur, Counters* gc) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t n = W.it->n_active;
     Counters cnt = {0, 0, 0, 0, 0, 0};
@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(128) k_wave_trace(const __grid_constant__ DevS
 
 // ---- occlude: the occlusion half of Scene::hit_light over the shadow queue ------------------------
 template <bool CNT>
-__global__ void __launch_bounds__(128) k_wave_occlude(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, Counters* gc) {
+__global__ void __launch_bounds__(128, 8) k_wave_occlude(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, Counters* gc) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t n = min(W.it->n_shadow, W.shadow_cap);
     const uint32_t N = W.n_slots, C = W.shadow_cap;
