@@ -1,0 +1,433 @@
+// Bidirectional path tracing on the device: bd_path_trace.rs:23-290, bd_path_trace/{path_gen,vertex,mis,
+// measure}.rs and the camera importance functions camera.rs:167-388.
+//
+// First device version: one persistent thread per camera sample runs the whole estimator — light
+// subpath, camera subpath, every (s,t) connection with its MIS weight — with its two vertex arrays in
+// HBM (LUMO_BDPT_MAXV vertices each; the reference caps at 1024, paths that would exceed the device cap
+// are cut there and counted in the `overflow` counter).  Traversal calls (Scene::hit, hit_t, hit_light)
+// are the same faithful routines the wavefront kernels use; visible() needs the reference's first-found
+// distance, i.e. scene_hit_t, not an any-hit boolean.
+#pragma once
+#include "wavefront.cuh"
+
+namespace lumo_dev {
+
+#define LUMO_BDPT_MAXV 48
+#define LUMO_BDPT_MAX_DEPTH 1024u   /* bd_path_trace.rs:7 */
+
+struct Vtx { DevHit h; C4 gathered; double pdf_fwd, pdf_bck; D3 wo; int light; int pad; };   // vertex.rs:5-12
+
+__device__ const LumoMaterial g_blank_material = {LMAT_BLANK, 0u, 1.0, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, 0u, 0u, 0u, 0u, 0.0, 0.0};
+__device__ __forceinline__ const Mat& vmat(const DevScene& S, const Vtx& v) { return v.h.material < 0 ? g_blank_material : S.materials[v.h.material]; }
+__device__ __forceinline__ bool v_is_surface(const Vtx& v) { return v.h.material >= 0; }                    // vertex.rs:86-88 (Blank = camera)
+__device__ __forceinline__ bool v_is_light(const Vtx& v) { return v.light >= 0; }
+__device__ __forceinline__ bool v_is_delta(const DevScene& S, const Vtx& v, const Lam& l) { return v.h.material < 0 ? false : mat_is_delta(S, S.materials[v.h.material], l); }
+__device__ __forceinline__ double sa_to_area(double pdf, D3 xo, D3 xi, D3 wi, D3 ngi) { return pdf * fabs(dot(wi, ngi)) / dist2(xo, xi); }   // measure.rs:9-11
+__device__ __forceinline__ double v_shading_cosine(const DevScene& S, const Vtx& v, D3 wi) { return shading_cosine(vmat(S, v), wi, v.h.ns); }
+__device__ __forceinline__ double v_shading_correction(const DevScene& S, const Vtx& v, D3 wi) {           // vertex.rs:118-126
+    const Mat& m = vmat(S, v);
+    return shading_cosine(m, wi, v.h.ng) * shading_cosine(m, v.wo, v.h.ns) / (shading_cosine(m, v.wo, v.h.ng) * shading_cosine(m, wi, v.h.ns));
+}
+__device__ __noinline__ C4 v_bsdf_f(const DevScene& S, const Vtx& v, D3 wi, const Lam& l, int mode) {
+    const Mat& m = vmat(S, v);
+    if (!mat_is_standard(m)) return c4(0.0);
+    const Onb uvw = onb_new(v.h.ns);
+    return bsdf_f<-1>(S, m, uvw, v.wo, wi, l, mode, v.h);
+}
+__device__ __forceinline__ C4 v_f(const DevScene& S, const Vtx& v, const Vtx& next, const Lam& l, int mode) { return v_bsdf_f(S, v, normalize(next.h.p - v.h.p), l, mode); }   // vertex.rs:129-132
+__device__ __noinline__ double v_bsdf_pdf(const DevScene& S, const Vtx& v, D3 wi, const Lam& l, bool swap_dir) {
+    const Mat& m = vmat(S, v);
+    if (!mat_is_standard(m)) return 0.0;
+    const Onb uvw = onb_new(v.h.ns);
+    return bsdf_pdf<-1>(S, m, uvw, v.wo, wi, v.h, l, swap_dir);
+}
+__device__ __forceinline__ double v_pdf_prev(const DevScene& S, const Vtx& v, const Vtx& prev, D3 wi, const Lam& l) {   // vertex.rs:146-160
+    if (v_is_delta(S, v, l) || v_is_delta(S, prev, l)) return 0.0;
+    const double pdf_sa = v_bsdf_pdf(S, v, wi, l, true);
+    const D3 ngp = !v_is_surface(prev) ? -v.wo : prev.h.ng;
+    return sa_to_area(pdf_sa, v.h.p, prev.h.p, -v.wo, ngp);
+}
+__device__ __forceinline__ void v_camera(Vtx& v, D3 xo, double pdf_fwd, const C4& gathered) {               // vertex.rs:16-36
+    v.h.t = 0.0; v.h.material = -1; v.h.backface = false /* (-X).X > 0 */; v.h.p = xo; v.h.fp_error = d3(0, 0, 0);
+    v.h.ns = d3(1, 0, 0); v.h.ng = d3(1, 0, 0); v.h.u = 1.0; v.h.v = 0.0; wrap_uv(v.h.u, v.h.v);
+    v.gathered = gathered; v.pdf_fwd = pdf_fwd; v.pdf_bck = 0.0; v.wo = d3(0, 0, 0); v.light = -1; v.pad = 0;
+}
+
+// ---- camera importance (camera.rs:167-388) -----------------------------------------------------------
+__device__ __forceinline__ bool cam_bounds(const LumoCamera& C, double x, double y) { return x >= 0.0 && x < (double)C.res_x && y >= 0.0 && y < (double)C.res_y; }
+__device__ __forceinline__ void cam_to_raster(const LumoCamera& C, D3 xl, double& x, double& y) {
+    const D3 r = xf4_point(C.screen_to_raster_m, xf4_point(C.camera_to_screen_m, xl)); x = r.x; y = r.y;
+}
+__device__ __noinline__ bool cam_raster_xy(const LumoCamera& C, const Ray& ri, double& x, double& y) {
+    if (C.ortho) { cam_to_raster(C, xf4_point(C.world_to_camera_m, ri.o), x, y); return cam_bounds(C, x, y); }
+    const D3 wl = xf4_dir(C.world_to_camera_m, ri.d);
+    const double ct = wl.z;
+    if (ct <= 0.0) return false;
+    const double fl = C.lens_radius == 0.0 ? 1.0 / ct : C.focal_length / ct;
+    const D3 xl = xf4_point(C.world_to_camera_m, ri.o);
+    cam_to_raster(C, xl + wl * fl, x, y);
+    return cam_bounds(C, x, y);
+}
+__device__ __forceinline__ double cam_lens_area(const LumoCamera& C) { return C.lens_radius == 0.0 ? 1.0 : LUMO_PI * powi(C.lens_radius, 2); }
+__device__ __noinline__ bool cam_sample_towards(const LumoCamera& C, D3 xi, double r0, double r1, Ray& ri) {
+    double dx, dy; square_to_disk(r0, r1, dx, dy);
+    if (C.ortho) {
+        const D3 lens = C.lens_radius * d3(dx, dy, 0.0);
+        const D3 xil = xf4_point(C.world_to_camera_m, xi);
+        const D3 xol = xil * d3(1.0, 1.0, 0.0);
+        const D3 xo = xf4_point(C.world_to_camera_inv, xol + lens);
+        ri.o = xo; ri.d = normalize(normalize(xi - xo));
+    } else {
+        const D3 xol = C.lens_radius * d3(dx, dy, 0.0);
+        const D3 xil = xf4_point(C.world_to_camera_m, xi);
+        const D3 wil = normalize(xil - xol);
+        ri.o = xf4_point(C.world_to_camera_inv, xol); ri.d = normalize(xf4_dir(C.world_to_camera_inv, wil));
+    }
+    double x, y;
+    return cam_raster_xy(C, ri, x, y);
+}
+__device__ __forceinline__ double cam_pdf_xo(const LumoCamera& C, const Ray& ri) {
+    double x, y;
+    if (C.ortho) return cam_raster_xy(C, ri, x, y) ? 1.0 / C.image_plane_area : 0.0;
+    const D3 xl = xf4_point(C.world_to_camera_m, ri.o);
+    const double r2 = powi(C.lens_radius + LUMO_EPS, 2);
+    return dist2(xl, d3(0, 0, 0)) < r2 ? 1.0 / cam_lens_area(C) : 0.0;
+}
+__device__ __forceinline__ double cam_pdf_wi(const LumoCamera& C, const Ray& ri) {
+    double x, y;
+    const D3 wl = xf4_dir(C.world_to_camera_m, ri.d);
+    if (C.ortho) return (1.0 - wl.z < LUMO_EPS) ? 1.0 : 0.0;
+    if (!cam_raster_xy(C, ri, x, y)) return 0.0;
+    return 1.0 / (C.image_plane_area * powi(wl.z, 3));
+}
+__device__ __forceinline__ double cam_pdf_importance(const LumoCamera& C, const Ray& ri, D3 xi) {
+    double x, y;
+    if (!cam_raster_xy(C, ri, x, y)) return 0.0;
+    const double* m = C.world_to_camera_m;   // to_normal_inv = transpose(m 3x3); times (0,0,1)
+    const D3 ng = d3(m[0] * 0.0 + m[4] * 0.0 + m[8] * 1.0, m[1] * 0.0 + m[5] * 0.0 + m[9] * 1.0, m[2] * 0.0 + m[6] * 0.0 + m[10] * 1.0);
+    const double pdf = dist2(xi, ri.o) / (fabs(dot(ng, ri.d)) * cam_lens_area(C));
+    return fmax(pdf, 0.0);
+}
+__device__ __forceinline__ bool cam_sample_importance(const LumoCamera& C, const Ray& ri, C4& imp, double& x, double& y) {
+    if (!cam_raster_xy(C, ri, x, y)) return false;
+    if (C.ortho) { imp = (1.0 / C.image_plane_area) * c4(1.0); return true; }
+    const D3 wl = xf4_dir(C.world_to_camera_m, ri.d);
+    const double denom = C.image_plane_area * powi(wl.z, 4) * cam_lens_area(C);
+    imp = (1.0 / denom) * c4(1.0);
+    return true;
+}
+
+struct BdptCounters { unsigned long long closest, occlusion, overflow; };
+
+// ---- path generation (path_gen.rs) ---------------------------------------------------------------------
+// Returns the number of vertices written to vs[0..]; vs[0] = root must already be filled.
+__device__ __noinline__ int bdpt_walk(const DevScene& S, Ray ro, Rng& rng, Lam& lam, double delta, C4 gathered, double pdf_dir, int mode, Vtx* vs, BdptCounters& bc) {
+    uint32_t depth = 0;
+    int n = 1;
+    double pdf_fwd = pdf_dir;
+    for (;;) {
+        HitRec rec;
+        bc.closest++;
+        if (!scene_hit<false>(S, ro, LUMO_INF, rec, nullptr)) break;
+        if (n >= LUMO_BDPT_MAXV) { bc.overflow++; break; }
+        const DevHit ho = reconstruct_hit(S, ro, rec);
+        const Mat& m = S.materials[ho.material];
+        const uint32_t prev = depth;
+        const D3 wo = -ro.d;
+        Vtx& cv = vs[n];                                                                      // Vertex::surface, vertex.rs:51-84
+        cv.pdf_fwd = mat_is_delta(S, m, lam) ? 0.0 : sa_to_area(pdf_fwd, vs[prev].h.p, ho.p, -wo, ho.ng);
+        cv.h = ho; cv.gathered = gathered; cv.wo = wo; cv.pdf_bck = 0.0; cv.light = -1; cv.pad = 0;
+        n++;
+        depth += 1;
+        const uint32_t curr = depth;
+        const double ru = rng_float(rng), r0 = rng_float(rng), r1 = rng_float(rng);
+        D3 wi;
+        const Onb uvw = onb_new(ho.ns);
+        if (!bsdf_sample<-1>(S, m, uvw, wo, ho, lam, ru, r0, r1, wi)) {
+            if (mode == 1) n--;                                                               // path_gen.rs:97-99: a light path cannot end on a light
+            else {                                                                            // Scene::get_light_at (bvh.rs:97-102)
+                Ray rl; rl.o = hit_ray_origin(ho, true); rl.d = normalize(-ho.ng);
+                RayCtx w; make_ctx(rl, w);
+                const uint32_t li = S.P.n_lights ? tlas_hit<true, false>(S, S.P.lights_root, S.P.n_objects, w, 0.0, LUMO_INF, nullptr) : LUMO_NONE;
+                vs[curr].light = li == LUMO_NONE ? -1 : (int)li;
+            }
+            break;
+        }
+        const Ray ri = hit_generate_ray(ho, wi);
+        wi = ri.d;
+        pdf_fwd = bsdf_pdf<-1>(S, m, uvw, wo, wi, ho, lam, false);
+        if (pdf_fwd == 0.0) break;
+        const double corr = mode == 0 ? 1.0 : v_shading_correction(S, vs[curr], wi);
+        const C4 bsdf = bsdf_f<-1>(S, m, uvw, wo, wi, lam, mode, ho);
+        gathered = gathered * (bsdf * v_shading_cosine(S, vs[curr], wi) * corr / pdf_fwd);
+        vs[prev].pdf_bck = v_pdf_prev(S, vs[curr], vs[prev], wi, lam);
+        if (depth >= LUMO_RR_DEPTH) {
+            const double lum = luminance(S, gathered, lam);
+            const double rr = fmin(lum / delta, 1.0);
+            if (rng_float(rng) > rr) break;
+            if (depth >= LUMO_BDPT_MAX_DEPTH) break;
+            gathered = gathered / rr;
+        }
+        if (mat_is_delta(S, m, lam)) pdf_fwd = 0.0;
+        ro = ri;
+    }
+    return n;
+}
+
+// ---- MIS (mis.rs) ----------------------------------------------------------------------------------------
+__device__ __forceinline__ void light_leaving_pdf(const DevScene& S, int light, const Ray& r, D3 ng, double& pdf_origin, double& pdf_dir) {   // object.rs:120-127
+    pdf_origin = 1.0 / S.lights[light].area;
+    pdf_dir = dot(ng, r.d) / LUMO_PI;
+}
+__device__ __noinline__ double pdf_light_leaving(const DevScene& S, const Vtx& curr, const Vtx& next, const Lam& l) {      // mis.rs:4-33
+    if (v_is_delta(S, next, l)) return 0.0;
+    if (curr.light < 0) return 0.0;
+    const D3 xo = curr.h.p, xi = next.h.p;
+    Ray ri; ri.o = xo; ri.d = normalize(xi - xo);
+    const D3 wi = ri.d;
+    double po, pdf_dir; light_leaving_pdf(S, curr.light, ri, curr.h.ng, po, pdf_dir);
+    const D3 ngi = !v_is_surface(next) ? wi : next.h.ng;
+    return sa_to_area(pdf_dir, xo, xi, wi, ngi);
+}
+__device__ __noinline__ double pdf_camera_leaving(const DevScene& S, const Vtx& curr, const Vtx& next, const Lam& l) {     // mis.rs:36-54
+    if (v_is_delta(S, next, l)) return 0.0;
+    const D3 xo = curr.h.p, xi = next.h.p;
+    const D3 wi = normalize(xi - xo);
+    Ray r; r.o = xo; r.d = normalize(wi);
+    const double pdf_wi = cam_pdf_wi(S.P.camera, r);
+    const D3 ngi = !v_is_surface(next) ? wi : next.h.ng;
+    return sa_to_area(pdf_wi, xo, xi, wi, ngi);
+}
+__device__ __forceinline__ double pdf_light_origin(const DevScene& S, const Vtx& v) {                                       // mis.rs:57-64
+    if (v.light < 0) return 0.0;
+    return S.lights[v.light].pdf / S.lights[v.light].area;
+}
+__device__ __noinline__ double pdf_connection(const DevScene& S, const Vtx& curr, const Vtx& next, const Lam& l, const Vtx* prev) {   // mis.rs:69-96
+    if (v_is_delta(S, next, l)) return 0.0;
+    const D3 xo = curr.h.p, xi = next.h.p;
+    double pdf_sa; D3 wi;
+    if (prev) { const D3 wo = normalize(prev->h.p - xo); pdf_sa = v_bsdf_pdf(S, curr, wo, l, true); wi = curr.wo; }
+    else { wi = normalize(xi - xo); pdf_sa = v_bsdf_pdf(S, curr, wi, l, false); }
+    const D3 ngi = !v_is_surface(next) ? wi : next.h.ng;
+    return sa_to_area(pdf_sa, xo, xi, wi, ngi);
+}
+__device__ __forceinline__ double map0(double p) { return p == 0.0 ? 1.0 : p; }
+// mis.rs:103-239.  lp: light path (s vertices used), cp: camera path (t vertices used).  For s = 1 (NEE) and
+// t = 1 (light tracing) the freshly sampled end vertex is passed as `ls1_override` / `ct1_override`.
+__device__ __noinline__ double mis_weight(const DevScene& S, const Lam& l, const Vtx* lp, int s, const Vtx* cp, int t, const Vtx* ls1_override, const Vtx* ct1_override) {
+    if (s + t == 2) return 1.0;
+    const Vtx& ct1 = ct1_override ? *ct1_override : cp[t - 1];
+    const Vtx& ls1 = s == 0 ? cp[0] : (ls1_override ? *ls1_override : lp[s - 1]);
+    double pr[2 * LUMO_BDPT_MAXV + 4], pi[2 * LUMO_BDPT_MAXV + 4]; bool dl[2 * LUMO_BDPT_MAXV + 4];
+    int n = 0;
+    const int smax = s > 2 ? s : 2;
+    for (int i = 0; i + 2 < smax; i++) { pr[n] = lp[i].pdf_bck; pi[n] = lp[i].pdf_fwd; dl[n] = v_is_delta(S, lp[i], l); n++; }
+    if (s > 1) {
+        const Vtx& ls2 = lp[s - 2];
+        pr[n] = pdf_connection(S, ls1, ls2, l, &ct1); pi[n] = ls2.pdf_fwd; dl[n] = v_is_delta(S, ls2, l); n++;
+    }
+    if (s > 0) {
+        pr[n] = t == 1 ? pdf_camera_leaving(S, ct1, ls1, l) : pdf_connection(S, ct1, ls1, l, nullptr);
+        pi[n] = ls1.pdf_fwd; dl[n] = false; n++;
+    }
+    if (t > 0) {
+        const double pb = s == 0 ? pdf_light_origin(S, ct1) : (s == 1 ? pdf_light_leaving(S, ls1, ct1, l) : pdf_connection(S, ls1, ct1, l, nullptr));
+        pr[n] = ct1.pdf_fwd; pi[n] = pb; dl[n] = false; n++;
+    }
+    if (t > 1) {
+        const Vtx& ct2 = cp[t - 2];
+        const double pb = s == 0 ? pdf_light_leaving(S, ct1, ct2, l) : pdf_connection(S, ct1, ct2, l, &ls1);
+        pr[n] = ct2.pdf_fwd; pi[n] = pb; dl[n] = v_is_delta(S, ct2, l); n++;
+    }
+    const int tmax = t > 2 ? t : 2;
+    for (int i = tmax - 2; i-- > 0;) { pr[n] = cp[i].pdf_fwd; pi[n] = cp[i].pdf_bck; dl[n] = v_is_delta(S, cp[i], l); n++; }
+    double sum_ri = 0.0, ri = 1.0;
+    for (int i = s; i-- > 0;) {
+        ri *= map0(pr[i]) / map0(pi[i]);
+        if (!dl[i] && !(i > 0 && dl[i - 1])) sum_ri += ri * ri;
+    }
+    ri = 1.0; sum_ri += ri;
+    for (int i = s; i + 1 < s + t; i++) {
+        ri *= map0(pi[i]) / map0(pr[i]);
+        if (!dl[i] && !dl[i + 1]) sum_ri += ri * ri;
+    }
+    return 1.0 / sum_ri;
+}
+
+// ---- connections (bd_path_trace.rs:77-290) ---------------------------------------------------------------
+__device__ __noinline__ bool connect_light_path(const DevScene& S, Rng& rng, const Lam& lam, const Vtx* lp, int s, C4& color, double& rx, double& ry, BdptCounters& bc) {
+    const Vtx& ll = lp[s - 1];
+    if (v_is_delta(S, ll, lam)) return false;
+    const D3 xi = ll.h.p;
+    Ray ri;
+    const double r0 = rng_float(rng), r1 = rng_float(rng);
+    if (!cam_sample_towards(S.P.camera, xi, r0, r1, ri)) return false;
+    const D3 xo = ri.o, wi = ri.d;
+    const double p_sct = v_bsdf_pdf(S, ll, -wi, lam, false);
+    const double p_imp = cam_pdf_importance(S.P.camera, ri, xi);
+    if (p_sct == 0.0 || p_imp == 0.0) return false;
+    HitRec rec;
+    bc.closest++;
+    if (!scene_hit<false>(S, ri, LUMO_INF, rec, nullptr)) return false;
+    const DevHit hh = reconstruct_hit(S, ri, rec);
+    if (max_element(vabs(hh.p - xi)) > sqrt(LUMO_EPS)) return false;
+    if (!cam_sample_importance(S.P.camera, ri, color, rx, ry)) return false;
+    if (is_black(color)) return false;
+    color = color / p_imp;
+    Vtx cl; v_camera(cl, xo, cam_pdf_xo(S.P.camera, ri), color / p_imp);
+    color = color * (ll.gathered * c4(1.0) * v_shading_cosine(S, ll, -wi) * v_shading_correction(S, ll, -wi)
+                     * v_f(S, ll, cl, lam, 1) * mis_weight(S, lam, lp, s, nullptr, 1, nullptr, &cl));
+    return true;
+}
+__device__ __noinline__ C4 add_camera_path(const DevScene& S, const Lam& lam, const Vtx* cp, int t) {
+    const Vtx& ct = cp[t - 1];
+    if (!v_is_light(ct)) return c4(0.0);
+    const C4 rad = ct.gathered * mat_emit(S, vmat(S, ct), lam, ct.h.backface);
+    if (is_black(rad)) return c4(0.0);
+    return rad * mis_weight(S, lam, nullptr, 0, cp, t, nullptr, nullptr);
+}
+__device__ __noinline__ C4 connect_camera_path(const DevScene& S, Rng& rng, const Lam& lam, const Vtx* cp, int t, BdptCounters& bc) {
+    const Vtx& cl = cp[t - 1];
+    if (v_is_delta(S, cl, lam) || v_is_light(cl)) return c4(0.0);
+    const uint32_t li = sample_light(S, rng_float(rng));
+    const double pdf_light = S.lights[li].pdf;
+    const uint32_t lobj = S.P.n_objects + li;
+    const LumoObject lo = S.objects[lobj];
+    const DevHit& ho = cl.h;
+    const D3 xo = ho.p;
+    const double r0 = rng_float(rng), r1 = rng_float(rng);
+    D3 wi = light_sample_towards(S, lo, xo, r0, r1);
+    const double p_sct = v_bsdf_pdf(S, cl, wi, lam, false);
+    if (p_sct == 0.0) return c4(0.0);
+    const Ray ri = hit_generate_ray(ho, wi);
+    DevHit hi;
+    if (!light_hit(S, lobj, ri, hi)) return c4(0.0);
+    bc.occlusion++;
+    if (scene_occluded<false>(S, ri, hi.t - LUMO_EPS, nullptr)) return c4(0.0);
+    const D3 xi = hi.p;
+    const D3 ngi = !v_is_surface(cl) ? wi : hi.ng;
+    const double p_lig = light_sample_towards_pdf(S, lo, ri, xi, ngi) * pdf_light;
+    if (p_lig == 0.0) return c4(0.0);
+    wi = ri.d;
+    const double pdf_origin = sa_to_area(p_lig, xo, xi, wi, ngi);
+    const C4 emittance = mat_emit(S, S.materials[hi.material], lam, hi.backface);
+    Vtx ll; ll.h = hi; ll.gathered = emittance; ll.light = (int)li; ll.pdf_fwd = pdf_origin; ll.pdf_bck = 0.0; ll.wo = d3(0, 0, 0); ll.pad = 0;   // Vertex::light
+    const C4 bsdf = v_f(S, cl, ll, lam, 0);
+    const double cos_wi = v_shading_cosine(S, cl, wi);
+    const C4 radiance = cl.gathered * bsdf * emittance * c4(1.0) * cos_wi / p_lig;
+    return radiance * mis_weight(S, lam, nullptr, 1, cp, t, &ll, nullptr);
+}
+__device__ __noinline__ bool bdpt_visible(const DevScene& S, const DevHit& h1, const DevHit& h2, BdptCounters& bc) {          // :279-290
+    const D3 xo = h1.p, xi = h2.p;
+    const Ray ri = hit_generate_ray(h1, xi - xo);
+    const D3 wi = ri.d;
+    if (dot(wi, h1.ng) < LUMO_EPS) return false;
+    bc.occlusion++;
+    return fabs(sqrt(fmax(dist2(xo, xi), 0.0)) - scene_hit_t<false>(S, ri, nullptr)) < LUMO_EPS;
+}
+__device__ __noinline__ C4 connect_paths(const DevScene& S, const Lam& lam, const Vtx* lp, int s, const Vtx* cp, int t, BdptCounters& bc) {
+    const Vtx& ll = lp[s - 1]; const Vtx& cl = cp[t - 1];
+    if (v_is_delta(S, cl, lam) || v_is_light(cl) || v_is_delta(S, ll, lam) || !bdpt_visible(S, ll.h, cl.h, bc)) return c4(0.0);
+    const D3 xc = cl.h.p, xl = ll.h.p;
+    const D3 wi = normalize(xl - xc);
+    const double p_sct = v_bsdf_pdf(S, cl, wi, lam, false) * v_bsdf_pdf(S, ll, -wi, lam, false);
+    if (p_sct == 0.0) return c4(0.0);
+    const C4 lb = v_f(S, ll, cl, lam, 1), cb = v_f(S, cl, ll, lam, 0);
+    const C4 radiance = ll.gathered * lb * v_shading_cosine(S, ll, -wi) * cl.gathered * cb * v_shading_cosine(S, cl, wi) * c4(1.0) / dist2(xc, xl);
+    if (is_black(radiance)) return c4(0.0);
+    return radiance * mis_weight(S, lam, lp, s, cp, t, nullptr, nullptr);
+}
+
+// ---- the estimator: bd_path_trace::integrate (bd_path_trace.rs:23-75), one thread per camera sample --------
+__global__ void __launch_bounds__(64) k_bdpt(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P, Vtx* vbuf) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    Vtx* lp = vbuf + (size_t)tid * 2 * LUMO_BDPT_MAXV;
+    Vtx* cp = lp + LUMO_BDPT_MAXV;
+    BdptCounters bc = {0, 0, 0};
+    unsigned long long paths = 0, cost_sum = 0; uint32_t max_len = 0;
+    const uint32_t Wd = S.P.camera.res_x, Hd = S.P.camera.res_y;
+    for (;;) {
+        const unsigned long long w = agg_inc64(&W.run->next_work);
+        if (w >= P.total_work) break;
+        uint32_t px, py, sample;
+        if (P.mode == WM_PILOT) {
+            const uint32_t tile = (uint32_t)(w / LUMO_PILOT_N), k = (uint32_t)(w % LUMO_PILOT_N);
+            const uint32_t x0 = (tile % P.tiles_x) * 16u, y0 = (tile / P.tiles_x) * 16u;
+            px = min(x0 + 2u * (k % 8u), Wd - 1u); py = min(y0 + 2u * (k / 8u), Hd - 1u);
+            sample = 0xFFFFFF00u + P.pilot_round;
+        } else {
+            const unsigned long long per_s = (unsigned long long)P.tiles_x * P.tiles_y * 256ull;
+            const uint32_t si = (uint32_t)(w / per_s); const unsigned long long r = w % per_s;
+            const uint32_t tile = (uint32_t)(r / 256ull), q = (uint32_t)(r % 256ull);
+            const uint32_t blk = q / 32u, in = q % 32u;
+            px = (tile % P.tiles_x) * 16u + (blk % 2u) * 8u + (in % 8u);
+            py = (tile / P.tiles_x) * 16u + (blk / 2u) * 4u + (in / 8u);
+            sample = P.spp_begin + si;
+            if (px >= Wd || py >= Hd) continue;
+        }
+        const uint32_t pixel = px + py * Wd;
+        Rng rng = rng_make(P.seed, pixel, sample, 0u, 0u);
+        double jx, jy;
+        if (P.mode == WM_PILOT) { jx = rng_float(rng); jy = rng_float(rng); } else raster_jitter(P, pixel, sample, rng, jx, jy);
+        const double rx = (double)px + jx, ry = (double)py + jy;
+        const double l0 = rng_float(rng), l1 = rng_float(rng);
+        const Ray r = camera_generate_ray(S.P.camera, rx, ry, l0, l1);
+        Lam lam = lam_sample(rng_float(rng));
+        const double delta = W.tile_delta[tile_of(P, S, pixel)];
+        // light path (path_gen.rs:21-50)
+        int ns;
+        {
+            const uint32_t li = sample_light(S, rng_float(rng));
+            const double pdf_light = S.lights[li].pdf;
+            const LumoObject lo = S.objects[S.P.n_objects + li];
+            const double a0 = rng_float(rng), a1 = rng_float(rng), b0 = rng_float(rng), b1 = rng_float(rng);
+            const DevHit ho = light_sample_on(S, lo, a0, a1);                                  // Sampleable::sample_leaving, object.rs:107-117
+            const Onb uvw = onb_new(ho.ns);
+            const Ray ri = hit_generate_ray(ho, to_world(uvw, square_to_cos_hemisphere(b0, b1)));
+            double pdf_origin, pdf_dir; light_leaving_pdf(S, (int)li, ri, ho.ng, pdf_origin, pdf_dir);
+            const C4 emit = mat_emit(S, S.materials[ho.material], lam, ho.backface);
+            Vtx& root = lp[0];
+            root.h = ho; root.gathered = emit; root.light = (int)li; root.pdf_fwd = pdf_origin * pdf_light; root.pdf_bck = 0.0; root.wo = d3(0, 0, 0); root.pad = 0;
+            const C4 gathered = emit * fabs(dot(ri.d, ho.ns)) / (pdf_light * pdf_origin * pdf_dir);
+            ns = bdpt_walk(S, ri, rng, lam, delta, gathered, pdf_dir, 1, lp, bc);
+        }
+        // camera path (path_gen.rs:4-19)
+        int nt;
+        {
+            const double pdf_wi = cam_pdf_wi(S.P.camera, r), pdf_xo = cam_pdf_xo(S.P.camera, r);
+            v_camera(cp[0], r.o, pdf_xo, c4(1.0));
+            nt = bdpt_walk(S, r, rng, lam, delta, c4(1.0), pdf_wi, 0, cp, bc);
+        }
+        C4 radiance = c4(0.0);
+        unsigned long long cost = (unsigned long long)(ns + nt);
+        for (int s = 2; s <= ns; s++) {
+            if (!v_is_delta(S, lp[s - 1], lam)) cost += 1;
+            C4 col; double sx, sy;
+            if (connect_light_path(S, rng, lam, lp, s, col, sx, sy, bc) && P.mode == WM_MAIN)
+                film_add_sample(S, W.pixels, W.splats, tone_map(S, (int)P.tone_map, P.tone_map_arg, col, lam), lam, sx, sy, true);
+        }
+        radiance = radiance + add_camera_path(S, lam, cp, nt);
+        for (int t = 2; t <= nt; t++) {
+            if (!v_is_delta(S, cp[t - 1], lam) && v_is_light(cp[t - 1])) cost += 1;
+            radiance = radiance + connect_camera_path(S, rng, lam, cp, t, bc);
+        }
+        for (int t = 2; t <= nt; t++) for (int s = 2; s <= ns; s++) {
+            cost += 1;
+            radiance = radiance + connect_paths(S, lam, lp, s, cp, t, bc);
+        }
+        if (P.mode == WM_PILOT) { W.pilot_lum[w] = luminance(S, radiance, lam); W.pilot_cost[w] = (uint32_t)cost; }
+        else {
+            bool finite = true;
+            for (int k = 0; k < 4; k++) finite = finite && isfinite(radiance.s[k]);
+            if (!finite) atomicAdd(&W.run->nonfinite, 1ull);
+            film_add_sample(S, W.pixels, W.splats, tone_map(S, (int)P.tone_map, P.tone_map_arg, radiance, lam), lam, rx, ry, false);
+            paths++; cost_sum += cost; max_len = max(max_len, (uint32_t)(ns + nt));
+        }
+    }
+    if (paths) { atomicAdd(&W.run->camera_paths, paths); atomicAdd(&W.run->cost, cost_sum); atomicMax(&W.run->max_depth, max_len); }
+    if (bc.closest) atomicAdd(&W.run->closest, bc.closest);
+    if (bc.occlusion) atomicAdd(&W.run->occlusion, bc.occlusion);
+    if (bc.overflow) atomicAdd(&W.run->shadow_dropped, bc.overflow);
+}
+
+}  // namespace lumo_dev

@@ -2,7 +2,7 @@
 // Host side only orchestrates: scene upload, wave allocation, the iteration loop (regen -> trace ->
 // shade -> occlude) and the copies in and out.  No computation of the hot path happens on the CPU.
 #include "lumo_gpu.h"
-#include "wavefront.cuh"
+#include "bdpt.cuh"
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -354,11 +354,25 @@ static int32_t run_wave(lumo_scene* sc, const Wave& W, WaveParams P, uint64_t& i
     return LUMO_OK;
 }
 
+// BDPT: persistent threads, one camera sample each (bdpt.cuh)
+static int32_t run_bdpt(lumo_scene* sc, const Wave& W, const WaveParams& P, Vtx* vbuf, int grid, uint64_t& iterations) {
+    lumo_ctx* ctx = sc->ctx;
+    cudaStream_t st = ctx->stream;
+    CU(cudaMemsetAsync(&W.run->next_work, 0, 8, st));
+    CU(cudaEventRecord(ctx->kev[0], st));
+    k_bdpt<<<grid, 64, 0, st>>>(sc->S, W, P, vbuf);
+    CU(cudaEventRecord(ctx->kev[1], st));
+    ctx->launches++; iterations++;
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    if (P.mode == WM_MAIN) { float ms = 0; CU(cudaEventElapsedTime(&ms, ctx->kev[0], ctx->kev[1])); ctx->kernel_ms[2] += ms; ctx->kernel_launches[2]++; }
+    return LUMO_OK;
+}
+
 static int32_t render_impl(lumo_scene* sc, const lumo_render_params* rp, double* pixels_dev, double* splats_dev, uint64_t* counters, double* tile_deltas_host, double* device_ms) {
     lumo_ctx* ctx = sc->ctx;
     const LumoSceneParams& SP = sc->S.P;
     if (rp->integrator < 0 || rp->integrator > 2) return fail(LUMO_ERR_INVALID, "render: unknown integrator");
-    if (rp->integrator == LUMO_BD_PATH_TRACE) return fail(LUMO_ERR_UNSUPPORTED, "render: bidirectional path tracing is not implemented on the device yet");
     if (rp->sampler < 0 || rp->sampler > 2) return fail(LUMO_ERR_INVALID, "render: unknown sampler");
     if (rp->tone_map < 0 || rp->tone_map > 2) return fail(LUMO_ERR_INVALID, "render: unknown tone map");
     if (rp->spp_end < rp->spp_begin || rp->spp_end > rp->total_spp || rp->total_spp == 0) return fail(LUMO_ERR_INVALID, "render: bad sample range");
@@ -395,13 +409,16 @@ static int32_t render_impl(lumo_scene* sc, const lumo_render_params* rp, double*
     P.spp_begin = rp->spp_begin; P.spp_count = spp; P.total_spp = rp->total_spp; P.tiles_x = tiles_x; P.tiles_y = tiles_y;
     { const char* e = std::getenv("LUMO_DEBUG_PIXEL"); P.debug_pixel = e ? (uint32_t)std::atoll(e) : LUMO_NONE; }
     uint64_t iterations = 0;
+    const bool bdpt = rp->integrator == LUMO_BD_PATH_TRACE;
+    DevBuf vbuf; int bgrid = ctx->sm_count * 8;
+    if (bdpt) CU(vbuf.alloc((size_t)bgrid * 64 * 2 * LUMO_BDPT_MAXV * sizeof(Vtx)));
     if (rp->rr_delta <= 0.0 && rp->integrator != LUMO_DIRECT_LIGHT) {
         // Per-tile Russian-roulette threshold (the role of task.rs:42-53): two pilot rounds, the second
         // using the first round's estimate.  Pilot paths never touch the film or the reported counters.
         DevBuf nd; CU(nd.alloc((size_t)n_tiles * 8));
         for (uint32_t round = 0; round < 2; round++) {
             P.mode = WM_PILOT; P.pilot_round = round; P.total_work = (unsigned long long)n_tiles * LUMO_PILOT_N;
-            int32_t rc = run_wave(sc, W, P, iterations); if (rc != LUMO_OK) return rc;
+            int32_t rc = bdpt ? run_bdpt(sc, W, P, vbuf.as<Vtx>(), bgrid, iterations) : run_wave(sc, W, P, iterations); if (rc != LUMO_OK) return rc;
             k_pilot_reduce<<<(n_tiles + 127) / 128, 128, 0, st>>>(W, n_tiles, nd.as<double>());
             ctx->launches++;
             CU(cudaMemcpyAsync(W.tile_delta, nd.p, (size_t)n_tiles * 8, cudaMemcpyDeviceToDevice, st));
@@ -410,18 +427,18 @@ static int32_t render_impl(lumo_scene* sc, const lumo_render_params* rp, double*
         CU(cudaMemsetAsync(W.run, 0, sizeof(RunCounters), st));
     }
     P.mode = WM_MAIN; P.total_work = main_work;
-    if (spp > 0) { int32_t rc = run_wave(sc, W, P, iterations); if (rc != LUMO_OK) return rc; }
+    if (spp > 0) { int32_t rc = bdpt ? run_bdpt(sc, W, P, vbuf.as<Vtx>(), bgrid, iterations) : run_wave(sc, W, P, iterations); if (rc != LUMO_OK) return rc; }
     CU(cudaEventRecord(ctx->ev1, st));
     HostCounters* hc = (HostCounters*)ctx->host_pinned;
     CU(cudaMemcpyAsync(&hc->run, W.run, sizeof(RunCounters), cudaMemcpyDeviceToHost, st));
     if (tile_deltas_host) CU(cudaMemcpyAsync(tile_deltas_host, W.tile_delta, (size_t)n_tiles * 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    if (hc->run.shadow_dropped) return fail(LUMO_ERR_CUDA, "render: shadow queue overflow (internal sizing error)");
+    if (hc->run.shadow_dropped && !bdpt) return fail(LUMO_ERR_CUDA, "render: shadow queue overflow (internal sizing error)");
     float ms = 0; CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     if (device_ms) *device_ms = ms;
     if (counters) {
         counters[0] = hc->run.camera_paths; counters[1] = hc->run.closest; counters[2] = hc->run.occlusion; counters[3] = hc->run.cost;
-        counters[4] = ctx->launches - launches0; counters[5] = hc->run.max_depth; counters[6] = iterations; counters[7] = hc->run.nonfinite;
+        counters[4] = ctx->launches - launches0; counters[5] = hc->run.max_depth; counters[6] = iterations; counters[7] = hc->run.nonfinite + (bdpt ? (hc->run.shadow_dropped << 32) : 0ull);   // BDPT: subpaths cut at LUMO_BDPT_MAXV in the high half
     }
     return LUMO_OK;
 }

@@ -53,7 +53,37 @@ def test_per_sample_parity_same_streams(name, integrator, spp, gpu_ctx):
     G.close(); O.close()
 
 
-@pytest.mark.parametrize("name,integrator,spp", [("cornell", 0, 64), ("bunny", 0, 32), ("conference", 1, 32)])
+@pytest.mark.parametrize("name,spp", [("cornell", 2), ("caustics", 2), ("bunny", 1)])
+def test_bdpt_per_sample_parity_same_streams(name, spp, gpu_ctx):
+    """BDPathTrace (bd_path_trace.rs:23-75): main samples and light-tracing splats against the oracle with
+    shared Philox streams.  Splats land on other pixels, so they are compared as a film: pixels where both
+    agree to 1e-9, plus totals."""
+    from lumo_b200 import native
+    prog, blob, _ = small_scene(name, box_filter=True)
+    O = oracle_lib.OracleScene(prog)
+    G = native.GpuScene(gpu_ctx, blob)
+    epx, esp, ecnt, edel = O.render(integrator=2, spp=spp, seed=7, rng_mode=1)
+    gpx, gsp, gcnt, gdel, ms = G.render(integrator=2, spp=spp, seed=7)
+    assert gcnt["camera_paths"] == ecnt["camera_paths"] == spp * O.res_x * O.res_y
+    assert gcnt["nonfinite"] == 0                      # also: no subpath was cut at the device vertex cap (high half)
+    assert np.allclose(gpx[..., 3], epx[..., 3], rtol=1e-12, atol=0)
+    rel = np.abs(gdel / edel - 1)
+    assert np.median(rel) < 1e-5 and rel.max() < 0.5, (np.median(rel), rel.max())
+    assert abs(gcnt["closest"] - ecnt["closest"]) <= 0.01 * ecnt["closest"] + 8, (gcnt, ecnt)
+    assert abs(gcnt["occlusion"] - ecnt["occlusion"]) <= 0.01 * ecnt["occlusion"] + 8, (gcnt, ecnt)
+    assert abs(gcnt["cost"] - ecnt["cost"]) <= 0.01 * ecnt["cost"] + 8, (gcnt, ecnt)
+    e, g = _rgb(epx), _rgb(gpx)
+    bad = (np.abs(g - e) > 1e-6 * (np.abs(e) + 1e-6)).any(axis=-1)    # MIS sums carry libm-vs-CUDA ulp differences: 1e-6 here
+    # two subpaths per sample and, in `caustics`, mirror + dispersive glass meshes: measured 0 % (cornell) to 10.6 % (caustics) of pixels
+    assert bad.mean() <= 0.15, ("pixels whose main samples differ beyond rounding", float(bad.mean()))
+    assert abs(g.mean() - e.mean()) <= 0.02 * abs(e.mean()) + 1e-9, (g.mean(), e.mean())
+    sbad = (np.abs(gsp - esp) > 1e-6 * (np.abs(esp) + 1e-6)).any(axis=-1)
+    assert sbad.mean() <= 0.15, ("pixels whose splats differ beyond rounding", float(sbad.mean()))
+    assert abs(gsp.sum() - esp.sum()) <= 0.03 * abs(esp.sum()) + 1e-9, (gsp.sum(), esp.sum())
+    G.close(); O.close()
+
+
+@pytest.mark.parametrize("name,integrator,spp", [("cornell", 0, 64), ("bunny", 0, 32), ("conference", 1, 32), ("cornell", 2, 16)])
 def test_converged_image_relmse(name, integrator, spp, gpu_ctx):
     """relMSE = mean((a-b)^2 / (b^2 + 1e-3)) in linear RGB: the GPU image is as close to an
     oracle image as another oracle image with a different seed is (factor 1.5), and mean luminance agrees
@@ -62,14 +92,18 @@ def test_converged_image_relmse(name, integrator, spp, gpu_ctx):
     prog, blob, _ = small_scene(name)
     O = oracle_lib.OracleScene(prog)
     G = native.GpuScene(gpu_ctx, blob)
-    a = _rgb(O.render(integrator=integrator, spp=spp, seed=11, rng_mode=0)[0])
-    b = _rgb(O.render(integrator=integrator, spp=spp, seed=12, rng_mode=0)[0])
-    g = _rgb(G.render(integrator=integrator, spp=spp, seed=13)[0])
+    def full(px, sp):      # Film::rgb_image before the transfer function (film.rs:173-193): direct + splats / (spp * filter integral)
+        from lumo_b200 import PixelFilter
+        return _rgb(px) + sp / (spp * PixelFilter.default().integral())
+    ra = O.render(integrator=integrator, spp=spp, seed=11, rng_mode=0); rb = O.render(integrator=integrator, spp=spp, seed=12, rng_mode=0)
+    rg = G.render(integrator=integrator, spp=spp, seed=13)
+    a, b, g = full(ra[0], ra[1]), full(rb[0], rb[1]), full(rg[0], rg[1])
     ref = _relmse(a, b)
     assert _relmse(g, a) <= 1.5 * ref + 1e-6, (_relmse(g, a), ref)
     assert _relmse(g, b) <= 1.5 * ref + 1e-6, (_relmse(g, b), ref)
     m = 0.5 * (a.mean() + b.mean())
-    assert abs(g.mean() - m) <= 0.01 * m + 2 * abs(a.mean() - b.mean()), (g.mean(), a.mean(), b.mean())
+    tol = 0.08 if integrator == 2 else 0.01      # BDPT means are firefly-dominated at these sample counts: oracle seeds differ by +-5 %
+    assert abs(g.mean() - m) <= tol * m + 2 * abs(a.mean() - b.mean()), (g.mean(), a.mean(), b.mean())
     G.close(); O.close()
 
 
