@@ -361,10 +361,19 @@ __global__ void __launch_bounds__(128) k_nee(const __grid_constant__ DevScene S,
     const uint32_t N = W.n_slots, nq = W.it->n_class[K], cur = P.cur;
     const uint32_t ns = S.P.n_shadow_rays, per = 2u * ns;
     const unsigned long long total = (unsigned long long)nq * per;
-    for (unsigned long long it = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; it < total; it += (unsigned long long)gridDim.x * blockDim.x) {
-        const uint32_t slot = W.cls[K][(uint32_t)(it / per)];
+    const unsigned long long padded = (unsigned long long)((nq + 31u) / 32u) * 32ull * per;
+    (void)total;
+    for (unsigned long long it = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; it < padded; it += (unsigned long long)gridDim.x * blockDim.x) {
+        // warp-uniform term: 32 consecutive queue entries x `per` terms; every lane of a warp evaluates the same
+        // term (shadow sample i, light- or BSDF-sampled) for 32 different paths
+        // (with a single shadow sample the two terms of a path sit in adjacent lanes instead and share its state through L1)
+        uint32_t j, qi;
+        if (ns > 1u) { const unsigned long long grp = it / (32ull * per); j = (uint32_t)((it / 32ull) % per); qi = (uint32_t)(grp * 32ull + (it % 32ull)); }
+        else { j = (uint32_t)(it % per); qi = (uint32_t)(it / per); }
+        const uint32_t i = j >> 1;
+        if (qi >= nq) continue;
+        const uint32_t slot = W.cls[K][qi];
         if (!(W.flags[slot] & PF_NEE)) continue;
-        const uint32_t j = (uint32_t)(it % per), i = j >> 1;
         const bool b_term = (j & 1u) != 0u;
         Ray ro; HitRec rec; load_path(W, cur, slot, ro, rec);
         const DevHit ho = reconstruct_hit(S, ro, rec);

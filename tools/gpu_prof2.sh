@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python tools/prof_run.py bunny 2 > gpurun_out/prof_plain.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_bunny.csv python tools/prof_run.py bunny 2 > gpurun_out/ncu_launch.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"k_scatter|k_nee|k_wave_trace|k_regen" -s 12 -c 8 -o gpurun_out/prof_bunny2 python tools/prof_run.py bunny 2 > gpurun_out/ncu_full.log 2>&1
+cat gpurun_out/prof_plain.log; tail -2 gpurun_out/ncu_full.log
