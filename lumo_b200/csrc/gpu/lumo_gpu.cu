@@ -285,16 +285,17 @@ static void carve_wave(Wave& W, Carver& c, uint32_t N, uint32_t shadow_cap, uint
     W.rx = c.take<double>(N); W.ry = c.take<double>(N);
     W.pixel = c.take<uint32_t>(N); W.sample = c.take<uint32_t>(N); W.depth = c.take<uint32_t>(N); W.flags = c.take<uint32_t>(N); W.witem = c.take<uint32_t>(N);
     W.active = c.take<uint32_t>(N);
+    for (int b = 0; b < 2; b++) W.done[b] = c.take<uint32_t>(N);
     const size_t C = shadow_cap;
     W.sox = c.take<double>(C); W.soy = c.take<double>(C); W.soz = c.take<double>(C); W.sdx = c.take<double>(C); W.sdy = c.take<double>(C); W.sdz = c.take<double>(C);
     W.stmax = c.take<double>(C); W.sc = c.take<double>(4 * C); W.sslot = c.take<uint32_t>(C);
-    W.it = c.take<IterCounters>(1); W.run = c.take<RunCounters>(1);
+    W.it = c.take<IterCounters>(1); W.run = c.take<RunCounters>(1); W.qc = c.take<QueueCounters>(1);
     W.tile_delta = c.take<double>(n_tiles);
     W.pilot_lum = c.take<double>((size_t)n_tiles * LUMO_PILOT_N); W.pilot_cost = c.take<uint32_t>((size_t)n_tiles * LUMO_PILOT_N);
     (void)film_px;
 }
 
-struct HostCounters { IterCounters it; RunCounters run; };
+struct HostCounters { QueueCounters qc; RunCounters run; };
 
 // Runs waves until the work counter is exhausted and no path is alive.
 template <int K>
@@ -316,6 +317,11 @@ static int32_t run_wave(lumo_scene* sc, const Wave& W, WaveParams P, uint64_t& i
     const int ngrid = (int)std::min<uint64_t>(((uint64_t)W.n_slots * 2 * sc->S.P.n_shadow_rays + 127) / 128, (uint64_t)ctx->sm_count * 32);
     CU(cudaMemsetAsync(W.flags, 0, (size_t)W.n_slots * 4, st));
     CU(cudaMemsetAsync(&W.run->next_work, 0, 8, st));
+    // every slot starts out free: the first k_retire finds all of them in done[1] (no PF_DONE flag -> nothing to film)
+    const QueueCounters qc0 = {{0u, 0u}, {0u, W.n_slots}};
+    CU(cudaMemcpyAsync(W.qc, &qc0, sizeof qc0, cudaMemcpyHostToDevice, st));
+    k_iota<<<rgrid, 256, 0, st>>>(W.done[1], W.n_slots);
+    ctx->launches++;
     P.cur = 0;
     // Kernels read their queue sizes from device memory, so several iterations are enqueued back to back
     // and the host looks at the live-path count only once per batch (an iteration over empty queues costs
@@ -326,7 +332,8 @@ static int32_t run_wave(lumo_scene* sc, const Wave& W, WaveParams P, uint64_t& i
             cudaEvent_t* ev = ctx->kev + 5 * b;
             CU(cudaMemsetAsync(W.it, 0, sizeof(IterCounters), st));
             CU(cudaEventRecord(ev[0], st));
-            k_regen<<<rgrid, 256, 0, st>>>(sc->S, W, P);
+            k_retire<<<rgrid, 256, 0, st>>>(sc->S, W, P);
+            k_compact<<<rgrid, 256, 0, st>>>(W);
             CU(cudaEventRecord(ev[1], st));
             if (ctx->count_visits) k_wave_trace<true><<<tgrid, 128, 0, st>>>(sc->S, W, P.cur, ctx->d_visit); else k_wave_trace<false><<<tgrid, 128, 0, st>>>(sc->S, W, P.cur, nullptr);
             CU(cudaEventRecord(ev[2], st));
@@ -339,16 +346,17 @@ static int32_t run_wave(lumo_scene* sc, const Wave& W, WaveParams P, uint64_t& i
             CU(cudaEventRecord(ev[3], st));
             if (ctx->count_visits) k_wave_occlude<true><<<tgrid, 128, 0, st>>>(sc->S, W, ctx->d_visit + 1); else k_wave_occlude<false><<<tgrid, 128, 0, st>>>(sc->S, W, nullptr);
             CU(cudaEventRecord(ev[4], st));
-            ctx->launches += 1; iterations++;
+            k_queue_reset<<<1, 1, 0, st>>>(W.qc, P.cur);
+            ctx->launches += 3; iterations++;
             P.cur ^= 1u;
         }
-        CU(cudaMemcpyAsync(hc, W.it, sizeof(IterCounters), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(&hc->qc, W.qc, sizeof(QueueCounters), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         CU(cudaGetLastError());
         if (P.mode == WM_MAIN) for (int b = 0; b < BATCH; b++) for (int k = 0; k < 4; k++) {
             float ms = 0; CU(cudaEventElapsedTime(&ms, ctx->kev[5 * b + k], ctx->kev[5 * b + k + 1])); ctx->kernel_ms[k] += ms; ctx->kernel_launches[k]++;
         }
-        if (hc->it.n_active == 0) break;
+        if (hc->qc.n_active[P.cur] == 0 && hc->qc.n_done[P.cur ^ 1u] == 0) break;   // no survivors and nothing left to retire
     }
     // the last regen found nothing alive: every finished path has been retired into the film
     return LUMO_OK;

@@ -31,9 +31,15 @@ enum { WM_MAIN = 0, WM_PILOT = 1 };
 #define LUMO_N_CLASSES 5           /* shade queues: 0 = terminal (miss / light / blank), 1..4 = LumoMatKind of a Standard material */
 
 struct IterCounters {   // zeroed before every iteration
-    uint32_t n_active, n_shadow, trace_next, occl_next;
+    uint32_t n_shadow, trace_next, occl_next, n_active;
     uint32_t n_class[LUMO_N_CLASSES], pad[3];
 };
+// Counters that live across iterations (double-buffered by the parity of the iteration): done[p] = slots whose
+// path ended in an iteration of parity p, retired into the film (and refilled) at the start of the next one;
+// n_active[p] = how many paths survive into an iteration of parity p (termination test on the host).  The
+// active queue itself is rebuilt in slot order every iteration (k_compact) so that the structure-of-arrays
+// path state is read with coalesced accesses.
+struct QueueCounters { uint32_t n_active[2], n_done[2]; };
 struct RunCounters {    // zeroed once per render
     unsigned long long next_work, camera_paths, closest, occlusion, cost, shadow_queued, shadow_dropped, nonfinite;
     uint32_t max_depth, pad;
@@ -51,11 +57,11 @@ struct Wave {
     double *radiance, *lam;              // [k * n_slots + slot]
     double *rx, *ry;
     uint32_t *pixel, *sample, *depth, *flags, *witem;
-    uint32_t* active;
+    uint32_t* active; uint32_t* done[2];
     uint32_t* cls[LUMO_N_CLASSES];       // per-class shade queues (slot indices)
     // shadow queue (SoA)
     double *sox, *soy, *soz, *sdx, *sdy, *sdz, *stmax, *sc; uint32_t* sslot;
-    IterCounters* it; RunCounters* run;
+    IterCounters* it; RunCounters* run; QueueCounters* qc;
     // film + RR thresholds
     double *pixels, *splats, *tile_delta;
     double* pilot_lum; uint32_t* pilot_cost;
@@ -110,10 +116,15 @@ __device__ __forceinline__ void raster_jitter(const WaveParams& P, uint32_t pixe
     jx = o0x + o1x + s1x * a; jy = o0y + o1y + s1y * b;
 }
 
-// ---- regen: retire, refill, compact -------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_regen(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P) {
+// ---- retire: film + refill, densely over the slots whose path ended in the previous iteration ----------
+__global__ void k_iota(uint32_t* p, uint32_t n) { for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = i; }
+__global__ void k_queue_reset(QueueCounters* qc, uint32_t cur) { qc->n_active[cur] = 0u; qc->n_done[cur ^ 1u] = 0u; }
+
+__global__ void __launch_bounds__(256) k_retire(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P) {
     const uint32_t N = W.n_slots, c = P.cur;
-    for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < N; slot += gridDim.x * blockDim.x) {
+    const uint32_t n = W.qc->n_done[c ^ 1u];
+    for (uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x; qi < n; qi += gridDim.x * blockDim.x) {
+        const uint32_t slot = W.done[c ^ 1u][qi];
         uint32_t f = W.flags[slot];
         if (f & PF_DONE) {
             // RenderTaskExecutor::exec tail (task.rs:64-76)
@@ -133,51 +144,51 @@ __global__ void __launch_bounds__(256) k_regen(const __grid_constant__ DevScene 
                 atomicAdd(&W.run->camera_paths, 1ull);
                 atomicMax(&W.run->max_depth, depth);
             }
-            f = 0;
         }
-        if (!(f & PF_ALIVE)) {
-            bool want = W.run->next_work < P.total_work;   // cheap pre-check; the atomic decides
-            if (want) {
-                const unsigned long long w = agg_inc64(&W.run->next_work);
-                if (w < P.total_work) {
-                    const uint32_t Wd = S.P.camera.res_x, Hd = S.P.camera.res_y;
-                    uint32_t px, py, sample; bool ok = true;
-                    if (P.mode == WM_PILOT) {                       // two pilot rounds of 64 paths per tile estimate the RR threshold
-                        const uint32_t tile = (uint32_t)(w / LUMO_PILOT_N), k = (uint32_t)(w % LUMO_PILOT_N);
-                        const uint32_t x0 = (tile % P.tiles_x) * 16u, y0 = (tile / P.tiles_x) * 16u;
-                        px = min(x0 + 2u * (k % 8u), Wd - 1u); py = min(y0 + 2u * (k / 8u), Hd - 1u);
-                        sample = 0xFFFFFF00u + P.pilot_round;
-                    } else {                                          // sample-major, tile by tile, 8x4 pixel blocks per warp
-                        const unsigned long long per_s = (unsigned long long)P.tiles_x * P.tiles_y * 256ull;
-                        const uint32_t si = (uint32_t)(w / per_s); const unsigned long long r = w % per_s;
-                        const uint32_t tile = (uint32_t)(r / 256ull), q = (uint32_t)(r % 256ull);
-                        const uint32_t blk = q / 32u, in = q % 32u;   // 8 blocks of 8x4 in a 16x16 tile
-                        px = (tile % P.tiles_x) * 16u + (blk % 2u) * 8u + (in % 8u);
-                        py = (tile / P.tiles_x) * 16u + (blk / 2u) * 4u + (in / 8u);
-                        sample = P.spp_begin + si;
-                        ok = px < Wd && py < Hd;
-                    }
-                    if (ok) {
-                        const uint32_t pixel = px + py * Wd;
-                        Rng rng = rng_make(P.seed, pixel, sample, 0u, 0u);
-                        double jx, jy;
-                        if (P.mode == WM_PILOT) { jx = rng_float(rng); jy = rng_float(rng); } else raster_jitter(P, pixel, sample, rng, jx, jy);
-                        const double rx = (double)px + jx, ry = (double)py + jy;
-                        const double l0 = rng_float(rng), l1 = rng_float(rng);                 // integrator.rs:56-57
-                        const Ray r = camera_generate_ray(S.P.camera, rx, ry, l0, l1);
-                        const Lam lam = lam_sample(rng_float(rng));
-                        W.ox[c][slot] = r.o.x; W.oy[c][slot] = r.o.y; W.oz[c][slot] = r.o.z; W.dx[c][slot] = r.d.x; W.dy[c][slot] = r.d.y; W.dz[c][slot] = r.d.z;
-                        for (int k = 0; k < 4; k++) { W.lam[(size_t)k * N + slot] = lam.l[k]; W.gathered[c][(size_t)k * N + slot] = 1.0; W.radiance[(size_t)k * N + slot] = 0.0; }
-                        W.rx[slot] = rx; W.ry[slot] = ry;
-                        W.pixel[slot] = pixel; W.sample[slot] = sample; W.depth[slot] = 0u; W.draws[c][slot] = rng.draws; W.witem[slot] = (uint32_t)w;
-                        f = PF_ALIVE | PF_LAST_SPECULAR;
-                    }
-                }
+        f = 0;
+        const uint32_t Wd = S.P.camera.res_x, Hd = S.P.camera.res_y;
+        while (W.run->next_work < P.total_work) {       // cheap pre-check; the atomic decides.  Work items outside the image are skipped
+            const unsigned long long w = agg_inc64(&W.run->next_work);
+            if (w >= P.total_work) break;
+            uint32_t px, py, sample; bool ok = true;
+            if (P.mode == WM_PILOT) {                       // two pilot rounds of 64 paths per tile estimate the RR threshold
+                const uint32_t tile = (uint32_t)(w / LUMO_PILOT_N), k = (uint32_t)(w % LUMO_PILOT_N);
+                const uint32_t x0 = (tile % P.tiles_x) * 16u, y0 = (tile / P.tiles_x) * 16u;
+                px = min(x0 + 2u * (k % 8u), Wd - 1u); py = min(y0 + 2u * (k / 8u), Hd - 1u);
+                sample = 0xFFFFFF00u + P.pilot_round;
+            } else {                                          // sample-major, tile by tile, 8x4 pixel blocks per warp
+                const unsigned long long per_s = (unsigned long long)P.tiles_x * P.tiles_y * 256ull;
+                const uint32_t si = (uint32_t)(w / per_s); const unsigned long long r = w % per_s;
+                const uint32_t tile = (uint32_t)(r / 256ull), q = (uint32_t)(r % 256ull);
+                const uint32_t blk = q / 32u, in = q % 32u;   // 8 blocks of 8x4 in a 16x16 tile
+                px = (tile % P.tiles_x) * 16u + (blk % 2u) * 8u + (in % 8u);
+                py = (tile / P.tiles_x) * 16u + (blk / 2u) * 4u + (in / 8u);
+                sample = P.spp_begin + si;
+                ok = px < Wd && py < Hd;
             }
+            if (!ok) continue;
+            const uint32_t pixel = px + py * Wd;
+            Rng rng = rng_make(P.seed, pixel, sample, 0u, 0u);
+            double jx, jy;
+            if (P.mode == WM_PILOT) { jx = rng_float(rng); jy = rng_float(rng); } else raster_jitter(P, pixel, sample, rng, jx, jy);
+            const double rx = (double)px + jx, ry = (double)py + jy;
+            const double l0 = rng_float(rng), l1 = rng_float(rng);                 // integrator.rs:56-57
+            const Ray r = camera_generate_ray(S.P.camera, rx, ry, l0, l1);
+            const Lam lam = lam_sample(rng_float(rng));
+            W.ox[c][slot] = r.o.x; W.oy[c][slot] = r.o.y; W.oz[c][slot] = r.o.z; W.dx[c][slot] = r.d.x; W.dy[c][slot] = r.d.y; W.dz[c][slot] = r.d.z;
+            for (int k = 0; k < 4; k++) { W.lam[(size_t)k * N + slot] = lam.l[k]; W.gathered[c][(size_t)k * N + slot] = 1.0; W.radiance[(size_t)k * N + slot] = 0.0; }
+            W.rx[slot] = rx; W.ry[slot] = ry;
+            W.pixel[slot] = pixel; W.sample[slot] = sample; W.depth[slot] = 0u; W.draws[c][slot] = rng.draws; W.witem[slot] = (uint32_t)w;
+            f = PF_ALIVE | PF_LAST_SPECULAR;
+            break;
         }
         W.flags[slot] = f;
-        if (f & PF_ALIVE) W.active[agg_inc(&W.it->n_active)] = slot;
     }
+}
+// stream compaction of the live slots, in slot order within a warp
+__global__ void __launch_bounds__(256) k_compact(const __grid_constant__ Wave W) {
+    for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < W.n_slots; slot += gridDim.x * blockDim.x)
+        if (W.flags[slot] & PF_ALIVE) W.active[agg_inc(&W.it->n_active)] = slot;
 }
 
 // ---- trace: Scene::hit over the active queue, then binning by what the shading stage has to do --------
@@ -284,6 +295,7 @@ __global__ void __launch_bounds__(128) k_terminal(const __grid_constant__ DevSce
             if (!is_black(e)) { C4 rad = load_c4(W.radiance, N, slot); rad = rad + e; store_c4(W.radiance, N, slot, rad); }
         }
         W.flags[slot] = PF_DONE;
+        W.done[P.cur][agg_inc(&W.qc->n_done[P.cur])] = slot;
     }
 }
 
@@ -341,6 +353,8 @@ __global__ void __launch_bounds__(128) k_scatter(const __grid_constant__ DevScen
         }
         if (K == LMAT_MFDIELECTRIC) for (int k = 1; k < 4; k++) W.lam[(size_t)k * N + slot] = lam.l[k];
         W.flags[slot] = (done ? PF_DONE : f) | (nee ? PF_NEE : 0u);
+        if (done) W.done[cur][agg_inc(&W.qc->n_done[cur])] = slot;
+        else agg_inc(&W.qc->n_active[nxt]);
     }
 }
 
