@@ -140,6 +140,10 @@ __device__ __forceinline__ void box_intersect(const double* lo, const double* hi
 //            (kdtree.rs:165) — returns false if that fails.
 struct KdStackEntry { uint32_t node; double t_start, t_end; };
 
+// The loop is the reference's, re-phrased for SIMT ("while-while"): each lane first walks inner nodes /
+// pops its stack until it holds the next triangle to test, then all lanes of the warp that hold one run
+// the triangle test together.  Per lane the sequence of nodes, triangles and comparisons is exactly
+// kdtree.rs:117-160.
 template <bool GEO, bool CNT>
 __device__ __noinline__ bool kd_hit(const DevScene& S, const LumoKdTree* tree, const RayCtx& ctx, double t_min, double t_max,
                                     double& t_out, uint32_t& tri_out, D3& bary_out, Counters* c) {
@@ -155,43 +159,47 @@ __device__ __noinline__ bool kd_hit(const DevScene& S, const LumoKdTree* tree, c
     box_intersect(tree->lo, tree->hi, r.o, inv, t_start, t_end);
     t_start = fmax(t_start, t_min); t_end = fmin(t_end, t_max);
     const LumoTriVerts* tris = S.tri_verts + tree->tri_base;
-    while (true) {
-        if (t_hit < t_start) break;
-        LUMO_CNT(kd);
-        // 16-byte node: one vector load
-        const double2 raw = __ldg(reinterpret_cast<const double2*>(S.kd_nodes + curr));
-        const double point = raw.x;
-        const uint32_t na = (uint32_t)(__double_as_longlong(raw.y) & 0xFFFFFFFFll);
-        const uint32_t nb = (uint32_t)((unsigned long long)__double_as_longlong(raw.y) >> 32);
-        if (nb & 0x80000000u) {
-            const uint32_t count = nb & 0x7FFFFFFFu;
-            for (uint32_t k = 0; k < count; k++) {
-                const uint32_t i = __ldg(S.kd_leaf + na + k);
-                LUMO_CNT(leaf);
-                TriHit th;
-                const double t = tri_hit<false, CNT>(tris + i, r, q, t_min, t_end, th, c) ? th.t : LUMO_INF;
-                if (GEO) { if (t < t_end) { t_end = t; t_hit = t; idx = i; } }
-                else { if (t < t_end) { t_out = t; return true; } }
+    uint32_t leaf_pos = 0, leaf_end = 0;     // pending entries of the current leaf in LSEC_KD_LEAF
+    bool in_leaf = false;                    // the current node was a leaf: pop once its entries are done
+    for (;;) {
+        uint32_t tri = LUMO_NONE;
+        for (;;) {                           // advance to the next triangle of this lane
+            if (leaf_pos < leaf_end) { tri = __ldg(S.kd_leaf + leaf_pos); leaf_pos++; LUMO_CNT(leaf); break; }
+            if (in_leaf) {
+                if (sp == 0) break;
+                sp--;
+                curr = stack[sp].node; t_start = stack[sp].t_start; t_end = stack[sp].t_end;
+                in_leaf = false;
             }
-            if (sp == 0) break;
-            sp--;
-            curr = stack[sp].node; t_start = stack[sp].t_start; t_end = stack[sp].t_end;
-        } else {
-            const int axis = (int)nb;
-            const double o_a = axis == 0 ? r.o.x : (axis == 1 ? r.o.y : r.o.z);
-            const double i_a = axis == 0 ? inv.x : (axis == 1 ? inv.y : inv.z);
-            const double t_split = (point - o_a) * i_a;
-            const bool left_first = o_a < point || (o_a == point && i_a <= 0.0);
-            const uint32_t first = left_first ? curr + 1 : na;
-            const uint32_t second = left_first ? na : curr + 1;
-            if (t_split > t_end || t_split <= 0.0) curr = first;
-            else if (t_split < t_start) curr = second;
+            if (t_hit < t_start) break;
+            LUMO_CNT(kd);
+            const double2 raw = __ldg(reinterpret_cast<const double2*>(S.kd_nodes + curr));   // 16-byte node: one vector load
+            const double point = raw.x;
+            const uint32_t na = (uint32_t)(__double_as_longlong(raw.y) & 0xFFFFFFFFll);
+            const uint32_t nb = (uint32_t)((unsigned long long)__double_as_longlong(raw.y) >> 32);
+            if (nb & 0x80000000u) { leaf_pos = na; leaf_end = na + (nb & 0x7FFFFFFFu); in_leaf = true; }
             else {
-                curr = first;
-                if (sp < 64) { stack[sp].node = second; stack[sp].t_start = t_split; stack[sp].t_end = t_end; sp++; }
-                t_end = t_split;
+                const int axis = (int)nb;
+                const double o_a = axis == 0 ? r.o.x : (axis == 1 ? r.o.y : r.o.z);
+                const double i_a = axis == 0 ? inv.x : (axis == 1 ? inv.y : inv.z);
+                const double t_split = (point - o_a) * i_a;
+                const bool left_first = o_a < point || (o_a == point && i_a <= 0.0);
+                const uint32_t first = left_first ? curr + 1 : na;
+                const uint32_t second = left_first ? na : curr + 1;
+                if (t_split > t_end || t_split <= 0.0) curr = first;
+                else if (t_split < t_start) curr = second;
+                else {
+                    curr = first;
+                    if (sp < 64) { stack[sp].node = second; stack[sp].t_start = t_split; stack[sp].t_end = t_end; sp++; }
+                    t_end = t_split;
+                }
             }
         }
+        if (tri == LUMO_NONE) break;
+        TriHit th;
+        const double t = tri_hit<false, CNT>(tris + tri, r, q, t_min, t_end, th, c) ? th.t : LUMO_INF;
+        if (GEO) { if (t < t_end) { t_end = t; t_hit = t; idx = tri; } }
+        else { if (t < t_end) { t_out = t; return true; } }
     }
     if (!GEO) { t_out = LUMO_INF; return false; }
     if (idx == LUMO_NONE) return false;
@@ -348,37 +356,47 @@ __device__ __forceinline__ bool object_hit(const DevScene& S, const LumoObject& 
 // BVH::_hit<GEO> (bvh.rs:315-362) over one of the two object BVHs.  obj_base = first object
 // record of this BVH (0 for Scene.objects, n_objects for Scene.lights).
 template <bool GEO, bool CNT>
-__device__ __noinline__ uint32_t tlas_hit(const DevScene& S, uint32_t root, uint32_t obj_base, const RayCtx& w, double t_min, double t_max, Counters* c) {
+__device__ __noinline__ uint32_t tlas_hit(const DevScene& S, uint32_t root, uint32_t obj_base, const RayCtx& w, double t_min, double t_max, Counters* c, double* t_found = nullptr) {
     const Ray r = w.r;
     const D3 inv = w.inv;
     uint32_t stack[64];
     int sp = 0;
     uint32_t curr = 0, idx = LUMO_NONE;
     double tt = t_max;
-    while (true) {
-        const LumoTlasNode* node = S.tlas + root + curr;
-        LUMO_CNT(tlas);
-        double t_start, t_end;
-        box_intersect(node->lo, node->hi, r.o, inv, t_start, t_end);
-        t_start = fmax(t_start, t_min); t_end = fmin(t_end, tt);
-        if (t_start <= t_end) {
-            const uint32_t count = node->count;
-            if (count == 0) {
-                const uint32_t right = node->right;
-                curr += 1;
-                if (right != LUMO_NONE && sp < 64) stack[sp++] = right;
-                continue;
+    uint32_t leaf_pos = 0, leaf_end = 0;     // pending objects of the current leaf
+    bool need_pop = false;
+    // "while-while" form of bvh.rs:326-360: every lane walks nodes until it holds the next object to test, then
+    // the lanes of the warp run Object::hit_t together.  Per lane the order of nodes and objects is the reference's.
+    for (;;) {
+        uint32_t obj = LUMO_NONE;
+        for (;;) {
+            if (leaf_pos < leaf_end) { obj = S.tlas_leaf[leaf_pos]; leaf_pos++; break; }
+            if (need_pop) {
+                if (sp == 0) break;
+                curr = stack[--sp];
+                need_pop = false;
             }
-            const uint32_t first = node->first;
-            for (uint32_t k = 0; k < count; k++) {
-                const uint32_t i = S.tlas_leaf[first + k];
-                const double t = object_hit_t<CNT>(S, S.objects[obj_base + i], w, t_min, tt, c);
-                if (GEO) { if (t < tt) { tt = t; idx = i; } }
-                else { if (t < tt) return i; }
+            const LumoTlasNode* node = S.tlas + root + curr;
+            LUMO_CNT(tlas);
+            double t_start, t_end;
+            box_intersect(node->lo, node->hi, r.o, inv, t_start, t_end);
+            t_start = fmax(t_start, t_min); t_end = fmin(t_end, tt);
+            if (t_start <= t_end) {
+                const uint32_t count = node->count;
+                if (count == 0) {
+                    const uint32_t right = node->right;
+                    curr += 1;
+                    if (right != LUMO_NONE && sp < 64) stack[sp++] = right;
+                    continue;
+                }
+                leaf_pos = node->first; leaf_end = leaf_pos + count;
             }
+            need_pop = true;
         }
-        if (sp == 0) break;
-        curr = stack[--sp];
+        if (obj == LUMO_NONE) break;
+        const double t = object_hit_t<CNT>(S, S.objects[obj_base + obj], w, t_min, tt, c);
+        if (GEO) { if (t < tt) { tt = t; idx = obj; } }
+        else { if (t < tt) { if (t_found) *t_found = t; return obj; } }
     }
     return idx;
 }
@@ -392,11 +410,16 @@ __device__ __forceinline__ bool bvh_hit(const DevScene& S, uint32_t root, uint32
     h.obj = obj_base + idx;
     return true;
 }
+// BVH::hit_t (bvh.rs:371-374) finds the first object with a hit and then calls hit_t on it a second time with the
+// same arguments; that second call is a pure function of them, so its value is the one the traversal just
+// computed.  The counting instantiation still performs it, to report the reference's visit counts.
 template <bool CNT>
 __device__ __forceinline__ double bvh_hit_t(const DevScene& S, uint32_t root, uint32_t obj_base, const RayCtx& r, double t_min, double t_max, Counters* c) {
-    const uint32_t idx = tlas_hit<false, CNT>(S, root, obj_base, r, t_min, t_max, c);
+    double t = LUMO_INF;
+    const uint32_t idx = tlas_hit<false, CNT>(S, root, obj_base, r, t_min, t_max, c, &t);
     if (idx == LUMO_NONE) return LUMO_INF;
-    return object_hit_t<CNT>(S, S.objects[obj_base + idx], r, t_min, t_max, c);
+    if (CNT) return object_hit_t<CNT>(S, S.objects[obj_base + idx], r, t_min, t_max, c);
+    return t;
 }
 
 // Scene::hit (scene.rs:119-147): objects, then lights with t_max = h.t.  The reference always

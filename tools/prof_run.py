@@ -9,6 +9,8 @@ spp = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 prog, blob, integrator, _ = bench.build_workload(name)
 ctx = native.GpuContext(0)
 G = native.GpuScene(ctx, blob)
+if os.environ.get("PROF_WARM", "1") == "1":
+    G.render(integrator=integrator, spp=1, seed=2, rr_delta=0.05)      # module load + first-launch costs
 px, sp, cnt, _, ms = G.render(integrator=integrator, spp=spp, seed=1, rr_delta=0.05)
 print(json.dumps({"workload": name, "spp": spp, "ms": ms, "counters": cnt, "kernel_ms": ctx.kernel_times()}))
 G.close(); ctx.close()
