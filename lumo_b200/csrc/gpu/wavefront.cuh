@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(128) k_terminal(const __grid_constant__ DevSce
 }
 
 template <int K>
-__global__ void __launch_bounds__(128) k_scatter(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P) {
+__global__ void __launch_bounds__(128, 4) k_scatter(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P) {
     const uint32_t N = W.n_slots, n = W.it->n_class[K], cur = P.cur, nxt = P.cur ^ 1u;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t slot = W.cls[K][i];
@@ -371,7 +371,7 @@ __device__ __forceinline__ C4 mis_sample(const DevScene& S, const Mat& m, const 
 
 // One thread per MIS term of integrator.rs:89-137: item = (queue entry, shadow sample i, A = light sample | B = BSDF sample).
 template <int K>
-__global__ void __launch_bounds__(128) k_nee(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P) {
+__global__ void __launch_bounds__(128, 4) k_nee(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P) {
     const uint32_t N = W.n_slots, nq = W.it->n_class[K], cur = P.cur;
     const uint32_t ns = S.P.n_shadow_rays, per = 2u * ns;
     const unsigned long long total = (unsigned long long)nq * per;
