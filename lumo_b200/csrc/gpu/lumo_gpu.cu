@@ -28,6 +28,7 @@ struct lumo_ctx {
     unsigned long long launches = 0;
     Counters* d_visit = nullptr;   // traversal visit counters (CNT passes): [0] closest-hit kernels, [1] occlusion kernels
     int count_visits = 0;
+    int flat = 0;                  // LUMO_TRACE_FLAT=1 selects the lane-refilled traversal kernels (trace_flat.cuh): bit-exact too, but measured 2x slower
     // per-kernel-class device time of the last render (CUDA events on the launching stream)
     cudaEvent_t kev[5 * LUMO_ITER_BATCH] = {};
     double kernel_ms[4] = {0, 0, 0, 0}; unsigned long long kernel_launches[4] = {0, 0, 0, 0};
@@ -66,6 +67,7 @@ extern "C" int32_t lumo_gpu_ctx_create(int32_t device, lumo_ctx** out) {
     for (auto& e : ctx->kev) CU(cudaEventCreate(&e));
     // f64 traversal keeps two explicit stacks per thread
     cudaDeviceSetLimit(cudaLimitStackSize, 4096);
+    { const char* e = std::getenv("LUMO_TRACE_FLAT"); if (e) ctx->flat = std::atoi(e) != 0; }
     *out = ctx; return LUMO_OK;
 }
 extern "C" int32_t lumo_gpu_ctx_destroy(lumo_ctx* ctx) {
@@ -201,6 +203,7 @@ static int32_t launch_batch(lumo_scene* sc, const double* o_dev, const double* d
     lumo_ctx* ctx = sc->ctx;
     CU(cudaMemsetAsync(next_dev, 0, 8, ctx->stream));
     if (ctx->count_visits) k_trace_batch<MODE, true><<<trace_grid(ctx), 128, 0, ctx->stream>>>(sc->S, o_dev, d_dev, tmax_dev, n, next_dev, obj, tri, t, bary, occ, ctx->d_visit + (MODE == 0 ? 0 : 1));
+    else if (ctx->flat) k_trace_batch_flat<MODE><<<ctx->sm_count * 4, 128, 0, ctx->stream>>>(sc->S, o_dev, d_dev, tmax_dev, n, next_dev, obj, tri, t, bary, occ);
     else k_trace_batch<MODE, false><<<trace_grid(ctx), 128, 0, ctx->stream>>>(sc->S, o_dev, d_dev, tmax_dev, n, next_dev, obj, tri, t, bary, occ, nullptr);
     ctx->launches++;
     CU(cudaGetLastError());
@@ -335,7 +338,9 @@ static int32_t run_wave(lumo_scene* sc, const Wave& W, WaveParams P, uint64_t& i
             k_retire<<<rgrid, 256, 0, st>>>(sc->S, W, P);
             k_compact<<<rgrid, 256, 0, st>>>(W);
             CU(cudaEventRecord(ev[1], st));
-            if (ctx->count_visits) k_wave_trace<true><<<tgrid, 128, 0, st>>>(sc->S, W, P.cur, ctx->d_visit); else k_wave_trace<false><<<tgrid, 128, 0, st>>>(sc->S, W, P.cur, nullptr);
+            if (ctx->count_visits) k_wave_trace<true><<<tgrid, 128, 0, st>>>(sc->S, W, P.cur, ctx->d_visit);
+            else if (ctx->flat) { k_wave_trace_flat<<<ctx->sm_count * 4, 128, 0, st>>>(sc->S, W, P.cur); k_classify<<<rgrid, 256, 0, st>>>(W); ctx->launches++; }
+            else k_wave_trace<false><<<tgrid, 128, 0, st>>>(sc->S, W, P.cur, nullptr);
             CU(cudaEventRecord(ev[2], st));
             k_terminal<<<sgrid, 128, 0, st>>>(sc->S, W, P);
             ctx->launches += 3;
@@ -344,7 +349,9 @@ static int32_t run_wave(lumo_scene* sc, const Wave& W, WaveParams P, uint64_t& i
             launch_shade_kind<LMAT_MFCONDUCTOR>(sc, W, P, sgrid, ngrid, st, ctx->launches);
             launch_shade_kind<LMAT_MFDIELECTRIC>(sc, W, P, sgrid, ngrid, st, ctx->launches);
             CU(cudaEventRecord(ev[3], st));
-            if (ctx->count_visits) k_wave_occlude<true><<<tgrid, 128, 0, st>>>(sc->S, W, ctx->d_visit + 1); else k_wave_occlude<false><<<tgrid, 128, 0, st>>>(sc->S, W, nullptr);
+            if (ctx->count_visits) k_wave_occlude<true><<<tgrid, 128, 0, st>>>(sc->S, W, ctx->d_visit + 1);
+            else if (ctx->flat) k_wave_occlude_flat<<<ctx->sm_count * 4, 128, 0, st>>>(sc->S, W);
+            else k_wave_occlude<false><<<tgrid, 128, 0, st>>>(sc->S, W, nullptr);
             CU(cudaEventRecord(ev[4], st));
             k_queue_reset<<<1, 1, 0, st>>>(W.qc, P.cur);
             ctx->launches += 3; iterations++;

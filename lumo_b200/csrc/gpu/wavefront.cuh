@@ -17,6 +17,7 @@
 // count.
 #pragma once
 #include "shade.cuh"
+#include "trace_flat.cuh"
 #include <cooperative_groups.h>
 #include <cstdio>
 
@@ -254,6 +255,98 @@ __global__ void __launch_bounds__(128, 8) k_wave_occlude(const __grid_constant__
     }
     if (lane == 0 && threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(&W.run->occlusion, (unsigned long long)n);
     if (CNT) { atomicAdd(&gc->tlas, cnt.tlas); atomicAdd(&gc->inst, cnt.inst); atomicAdd(&gc->kd, cnt.kd); atomicAdd(&gc->leaf, cnt.leaf); atomicAdd(&gc->tri, cnt.tri); atomicAdd(&gc->sphere, cnt.sphere); }
+}
+
+// ---- lane-refilled traversal kernels (trace_flat.cuh) ------------------------------------------------
+struct WaveRaySource {
+    const Wave* W; uint32_t cur;
+    __device__ __forceinline__ void load(unsigned long long item, Ray& r, double& t_max) const {
+        const uint32_t slot = W->active[item];
+        r.o = d3(W->ox[cur][slot], W->oy[cur][slot], W->oz[cur][slot]); r.d = d3(W->dx[cur][slot], W->dy[cur][slot], W->dz[cur][slot]);
+        t_max = LUMO_INF;
+    }
+};
+#define PF_CLASS_SHIFT 8u   /* flags bits 8..10: shade class decided by the trace kernel (0 terminal, 1..4 material kind) */
+struct WaveHitSink {
+    const DevScene* S; const Wave* W;
+    __device__ __forceinline__ void store(unsigned long long item, const FlatResult& res) {
+        const uint32_t slot = W->active[item];
+        uint32_t klass = 0;
+        if (res.hit) {
+            W->ht[slot] = res.h.t; W->hb0[slot] = res.h.bary.x; W->hb1[slot] = res.h.bary.y; W->hb2[slot] = res.h.bary.z; W->hobj[slot] = res.h.obj; W->htri[slot] = res.h.tri;
+            const uint32_t kind = S->materials[S->objects[res.h.obj].material].kind;
+            if (kind >= LMAT_LAMBERTIAN && kind <= LMAT_MFDIELECTRIC) klass = kind;
+        } else W->hobj[slot] = LUMO_NONE;
+        W->flags[slot] = (W->flags[slot] & 0xFFu) | (klass << PF_CLASS_SHIFT);
+    }
+};
+__global__ void __launch_bounds__(128, 4) k_wave_trace_flat(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, uint32_t cur) {
+    const uint32_t n = W.it->n_active;
+    WaveRaySource src{&W, cur}; WaveHitSink sink{&S, &W};
+    flat_trace<FQ_CLOSEST>(S, n, nullptr, &W.it->trace_next, src, sink);
+    if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(&W.run->closest, (unsigned long long)n);
+}
+// shade queues in active-queue (slot) order, so that the shade kernels read path state coalesced
+__global__ void __launch_bounds__(256) k_classify(const __grid_constant__ Wave W) {
+    const uint32_t n = W.it->n_active, lane = threadIdx.x & 31u;
+    const uint32_t n_pad = (n + 31u) & ~31u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x) {
+        uint32_t slot = 0, klass = LUMO_N_CLASSES;
+        if (i < n) { slot = W.active[i]; klass = (W.flags[slot] >> PF_CLASS_SHIFT) & 7u; }
+#pragma unroll
+        for (uint32_t c = 0; c < LUMO_N_CLASSES; c++) {
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, klass == c);
+            if (m) {
+                uint32_t b = 0;
+                if (lane == (uint32_t)(__ffs(m) - 1)) b = atomicAdd(&W.it->n_class[c], (uint32_t)__popc(m));
+                b = __shfl_sync(0xFFFFFFFFu, b, __ffs(m) - 1);
+                if (klass == c) W.cls[c][b + __popc(m & ((1u << lane) - 1u))] = slot;
+            }
+        }
+    }
+}
+struct ShadowRaySource {
+    const Wave* W;
+    __device__ __forceinline__ void load(unsigned long long i, Ray& r, double& t_max) const {
+        r.o = d3(W->sox[i], W->soy[i], W->soz[i]); r.d = d3(W->sdx[i], W->sdy[i], W->sdz[i]); t_max = W->stmax[i];
+    }
+};
+struct ShadowSink {
+    const Wave* W;
+    __device__ __forceinline__ void store(unsigned long long i, const FlatResult& res) {
+        if (res.hit) return;
+        const uint32_t slot = W->sslot[i]; const uint32_t N = W->n_slots, C = W->shadow_cap;
+        for (int k = 0; k < 4; k++) { const double v = W->sc[(size_t)k * C + i]; if (v != 0.0) atomicAdd(&W->radiance[(size_t)k * N + slot], v); }
+    }
+};
+__global__ void __launch_bounds__(128, 4) k_wave_occlude_flat(const __grid_constant__ DevScene S, const __grid_constant__ Wave W) {
+    const uint32_t n = min(W.it->n_shadow, W.shadow_cap);
+    ShadowRaySource src{&W}; ShadowSink sink{&W};
+    flat_trace<FQ_OCCLUDED>(S, n, nullptr, &W.it->occl_next, src, sink);
+    if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(&W.run->occlusion, (unsigned long long)n);
+}
+// C-ABI ray batches through the same machine
+struct BatchSource {
+    const double *o, *d, *t_max;
+    __device__ __forceinline__ void load(unsigned long long i, Ray& r, double& tm) const {
+        r.o = d3(o[3 * i], o[3 * i + 1], o[3 * i + 2]); r.d = d3(d[3 * i], d[3 * i + 1], d[3 * i + 2]); tm = t_max ? t_max[i] : LUMO_INF;
+    }
+};
+template <int Q> struct BatchSink {
+    uint32_t *obj, *tri; double *t, *bary; uint8_t* occ;
+    __device__ __forceinline__ void store(unsigned long long i, const FlatResult& res) {
+        if (Q == FQ_CLOSEST) {
+            if (res.hit) { obj[i] = res.h.obj; tri[i] = res.h.tri; t[i] = res.h.t; bary[2 * i] = res.h.bary.x; bary[2 * i + 1] = res.h.bary.y; }
+            else { obj[i] = LUMO_NONE; tri[i] = LUMO_NONE; t[i] = LUMO_INF; bary[2 * i] = 0.0; bary[2 * i + 1] = 0.0; }
+        } else if (Q == FQ_OCCLUDED) occ[i] = res.hit ? 1 : 0;
+        else t[i] = res.t;
+    }
+};
+template <int Q>
+__global__ void __launch_bounds__(128, 4) k_trace_batch_flat(const __grid_constant__ DevScene S, const double* __restrict__ o, const double* __restrict__ d, const double* __restrict__ t_max,
+                                                             unsigned long long n, unsigned long long* next, uint32_t* obj, uint32_t* tri, double* t, double* bary, uint8_t* occ) {
+    BatchSource src{o, d, t_max}; BatchSink<Q> sink{obj, tri, t, bary, occ};
+    flat_trace<Q>(S, n, next, nullptr, src, sink);
 }
 
 // ---- shade ------------------------------------------------------------------------------------------

@@ -82,3 +82,26 @@ def test_edge_cases(gpu_ctx):
     assert go[-1] == 0xFFFFFFFF and np.isinf(gtt[-1])
     with pytest.raises(RuntimeError):
         native.GpuScene(gpu_ctx, blob[:-16])                        # malformed blob -> status code, not a crash
+
+
+def test_flat_traversal_is_bit_exact_too():
+    """The lane-refilled state-machine traversal (trace_flat.cuh, opt-in via LUMO_TRACE_FLAT=1) must produce the
+    same bits as the default nested one.  A context reads the switch when it is created."""
+    import os
+    from lumo_b200 import native
+    prog, blob, _ = small_scene("bistro")
+    O = oracle_lib.OracleScene(prog)
+    os.environ["LUMO_TRACE_FLAT"] = "1"
+    try:
+        ctx = native.GpuContext(0)
+    finally:
+        del os.environ["LUMO_TRACE_FLAT"]
+    G = native.GpuScene(ctx, blob)
+    for kind, (o, d) in ray_batches(O, 8000, seed=37).items():
+        eo, et, ett, eb = O.trace_closest(o, d)
+        go, gt, gtt, gb = G.trace_closest(o, d)
+        assert np.array_equal(eo, go) and np.array_equal(et, gt) and np.array_equal(_bits(ett), _bits(gtt)) and np.array_equal(_bits(eb), _bits(gb)), kind
+        tm = np.where(np.isfinite(ett), ett * 0.999, 5.0)
+        assert np.array_equal(O.trace_any(o, d, tm), G.trace_any(o, d, tm)), kind
+        assert np.array_equal(_bits(O.trace_first_found(o, d)), _bits(G.trace_first_found(o, d))), kind
+    G.close(); ctx.close(); O.close()
