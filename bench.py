@@ -28,17 +28,19 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {   # name -> (scene kwargs, integrator, default spp per step)
-    "bunny": (dict(), 0, 8),
-    "cornell": (dict(), 0, 16),
-    "dragon": (dict(), 0, 4),
-    "conference": (dict(), 0, 4),
-    "conference_dl": (dict(), 1, 8),
-    "bistro": (dict(), 0, 1),
+    "bunny": (dict(), 0, 32),
+    "cornell": (dict(), 0, 64),
+    "dragon": (dict(), 0, 8),
+    "caustics_bdpt": (dict(), 2, 2),
+    "conference": (dict(), 0, 16),
+    "conference_dl": (dict(), 1, 32),
+    "bistro": (dict(), 0, 2),
 }
 DESCR = {
     "bunny": "examples/bunny.rs PathTrace 1024x768, synthetic 69k-triangle stand-in mesh (assets are not available offline)",
     "cornell": "examples/cornell.rs PathTrace 512x512",
     "dragon": "examples/dragon.rs PathTrace 1024x768, synthetic 870k-triangle stand-in mesh",
+    "caustics_bdpt": "examples/caustics.rs BDPathTrace 1024x768, synthetic 15k-triangle stand-in mesh instanced twice (mirror + dispersive glass)",
     "conference": "examples/conference.rs PathTrace 1024x768, synthetic 332k-triangle room in 64 kd-trees",
     "conference_dl": "examples/conference.rs DirectLight 1024x768, synthetic 332k-triangle room in 64 kd-trees",
     "bistro": "examples/bistro.rs PathTrace 1920x1080, synthetic 1.05M-triangle street in 1024 kd-trees, 4097 lights",
@@ -141,7 +143,7 @@ def main():
     ap.add_argument("--workload", default="bunny", choices=list(WORKLOADS))
     ap.add_argument("--spp", type=int, default=0, help="samples per pixel per step and per GPU (0 = workload default)")
     ap.add_argument("--wave-paths", type=int, default=0)
-    ap.add_argument("--other-scenes", default="cornell,conference,bistro", help="comma list measured briefly after the main workload ('' = none)")
+    ap.add_argument("--other-scenes", default="cornell,dragon,caustics_bdpt,conference,conference_dl,bistro", help="comma list measured briefly after the main workload ('' = none)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -231,7 +233,7 @@ def main():
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "description": DESCR[args.workload], "integrator": ["PathTrace", "DirectLight", "BDPathTrace"][integrator],
                        "resolution": [W, H], "spp_per_step_per_gpu": spp, "parallelism": "scene replicated, samples sharded, 1 NCCL reduce" if world > 1 else "single GPU",
-                       "l2": "256 MiB buffer written between timed steps (L2 flush); wave state (>=230 MB) and film (44 MB) also exceed L2"},
+                       "l2": "256 MiB buffer written between timed steps (L2 flush); wave state (2^21 slots, ~0.7 GB) and film (44 MB) also exceed L2"},
             "msamples_per_s": paths / (ms_total * 1e-3) / 1e6,
             "rays": {"closest_hit": closest, "occlusion": occl, "camera_paths": paths, "reference_style_cost": tot["cost"]},
             "gpu_launches": int(launches), "clocks": clk}

@@ -120,6 +120,8 @@ int32_t lumo_gpu_ctx_visits(lumo_ctx* ctx, uint64_t* out12);   /* 6 for the clos
 /* Device time (ms, CUDA events on the launching stream) and launch count per kernel class of the last
  * lumo_gpu_render*: [0] regen (film + refill + compaction), [1] closest-hit trace, [2] shade, [3] occlusion trace. */
 int32_t lumo_gpu_ctx_kernel_times(lumo_ctx* ctx, double* ms4, uint64_t* launches4);
+/* Per wave iteration of the last render's main pass: out[2i] = closest-hit rays traced, out[2i+1] = shadow rays traced. */
+int32_t lumo_gpu_ctx_iter_log(lumo_ctx* ctx, uint32_t* out, uint32_t cap, uint32_t* n);
 
 /* Device-resident variants used by bench.py's kernel-only timing (inputs already in HBM). */
 int32_t lumo_gpu_trace_closest_dev(lumo_scene* scene, const double* origin_dev, const double* dir_dev, uint64_t n,

@@ -16,6 +16,7 @@ static thread_local std::string g_err;
 static int32_t fail(int32_t code, const std::string& msg) { g_err = msg; return code; }
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(e_ == cudaErrorMemoryAllocation ? LUMO_ERR_OOM : LUMO_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
 
+#define LUMO_ITER_LOG_CAP 16384
 #define LUMO_ITER_BATCH 4   /* wave iterations enqueued per host synchronisation */
 
 struct lumo_ctx {
@@ -28,6 +29,7 @@ struct lumo_ctx {
     unsigned long long launches = 0;
     Counters* d_visit = nullptr;   // traversal visit counters (CNT passes): [0] closest-hit kernels, [1] occlusion kernels
     int count_visits = 0;
+    uint32_t* d_iter_log = nullptr; uint32_t iter_log_n = 0;   // (closest-hit rays, shadow rays) per wave iteration of the last render's main pass
     int flat = 0;                  // LUMO_TRACE_FLAT=1 selects the lane-refilled traversal kernels (trace_flat.cuh): bit-exact too, but measured 2x slower
     // per-kernel-class device time of the last render (CUDA events on the launching stream)
     cudaEvent_t kev[5 * LUMO_ITER_BATCH] = {};
@@ -65,6 +67,7 @@ extern "C" int32_t lumo_gpu_ctx_create(int32_t device, lumo_ctx** out) {
     CU(cudaMalloc(&ctx->d_visit, 2 * sizeof(Counters)));
     CU(cudaMemset(ctx->d_visit, 0, 2 * sizeof(Counters)));
     for (auto& e : ctx->kev) CU(cudaEventCreate(&e));
+    CU(cudaMalloc(&ctx->d_iter_log, LUMO_ITER_LOG_CAP * 8));
     // f64 traversal keeps two explicit stacks per thread
     cudaDeviceSetLimit(cudaLimitStackSize, 4096);
     { const char* e = std::getenv("LUMO_TRACE_FLAT"); if (e) ctx->flat = std::atoi(e) != 0; }
@@ -75,6 +78,7 @@ extern "C" int32_t lumo_gpu_ctx_destroy(lumo_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->wave_mem) cudaFree(ctx->wave_mem);
     if (ctx->d_visit) cudaFree(ctx->d_visit);
+    if (ctx->d_iter_log) cudaFree(ctx->d_iter_log);
     if (ctx->host_pinned) cudaFreeHost(ctx->host_pinned);
     for (auto& e : ctx->kev) if (e) cudaEventDestroy(e);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -108,6 +112,16 @@ extern "C" int32_t lumo_gpu_ctx_visits(lumo_ctx* ctx, uint64_t* out12) {
     CU(cudaStreamSynchronize(ctx->stream));
     Counters c[2]; CU(cudaMemcpy(c, ctx->d_visit, sizeof c, cudaMemcpyDeviceToHost));
     for (int k = 0; k < 2; k++) { uint64_t* o = out12 + 6 * k; o[0] = c[k].tlas; o[1] = c[k].inst; o[2] = c[k].kd; o[3] = c[k].leaf; o[4] = c[k].tri; o[5] = c[k].sphere; }
+    return LUMO_OK;
+}
+// Queue sizes of the last render's main pass: out[2i] = rays traced by k_wave_trace in iteration i, out[2i+1] = shadow
+// rays traced by k_wave_occlude.  Returns the number of iterations in *n (at most cap are written).
+extern "C" int32_t lumo_gpu_ctx_iter_log(lumo_ctx* ctx, uint32_t* out, uint32_t cap, uint32_t* n) {
+    if (!ctx || !out || !n) return fail(LUMO_ERR_INVALID, "iter_log: null pointer");
+    CU(cudaSetDevice(ctx->device));
+    const uint32_t k = ctx->iter_log_n < cap ? ctx->iter_log_n : cap;
+    if (k) CU(cudaMemcpy(out, ctx->d_iter_log, (size_t)k * 8, cudaMemcpyDeviceToHost));
+    *n = ctx->iter_log_n;
     return LUMO_OK;
 }
 // Device time (ms) and launch count per kernel class of the last render: regen, trace, shade, occlude.
@@ -330,6 +344,7 @@ static int32_t run_wave(lumo_scene* sc, const Wave& W, WaveParams P, uint64_t& i
     // and the host looks at the live-path count only once per batch (an iteration over empty queues costs
     // a few microseconds).
     const int BATCH = LUMO_ITER_BATCH;
+    uint32_t main_iter = 0;
     for (;;) {
         for (int b = 0; b < BATCH; b++) {
             cudaEvent_t* ev = ctx->kev + 5 * b;
@@ -353,7 +368,8 @@ static int32_t run_wave(lumo_scene* sc, const Wave& W, WaveParams P, uint64_t& i
             else if (ctx->flat) k_wave_occlude_flat<<<ctx->sm_count * 4, 128, 0, st>>>(sc->S, W);
             else k_wave_occlude<false><<<tgrid, 128, 0, st>>>(sc->S, W, nullptr);
             CU(cudaEventRecord(ev[4], st));
-            k_queue_reset<<<1, 1, 0, st>>>(W.qc, P.cur);
+            k_queue_reset<<<1, 1, 0, st>>>(W.qc, P.cur, W.it, P.mode == WM_MAIN ? ctx->d_iter_log : nullptr, main_iter, LUMO_ITER_LOG_CAP);
+            if (P.mode == WM_MAIN) main_iter++;
             ctx->launches += 3; iterations++;
             P.cur ^= 1u;
         }
@@ -365,7 +381,7 @@ static int32_t run_wave(lumo_scene* sc, const Wave& W, WaveParams P, uint64_t& i
         }
         if (hc->qc.n_active[P.cur] == 0 && hc->qc.n_done[P.cur ^ 1u] == 0) break;   // no survivors and nothing left to retire
     }
-    // the last regen found nothing alive: every finished path has been retired into the film
+    if (P.mode == WM_MAIN) ctx->iter_log_n = main_iter < LUMO_ITER_LOG_CAP ? main_iter : LUMO_ITER_LOG_CAP;
     return LUMO_OK;
 }
 
@@ -397,7 +413,7 @@ static int32_t render_impl(lumo_scene* sc, const lumo_render_params* rp, double*
     const size_t film_px = (size_t)Wd * Hd;
     const uint32_t spp = rp->spp_end - rp->spp_begin;
     const unsigned long long main_work = (unsigned long long)n_tiles * 256ull * spp;
-    uint32_t N = rp->wave_paths ? rp->wave_paths : (1u << 20);
+    uint32_t N = rp->wave_paths ? rp->wave_paths : (1u << 21);   // measured on B200: 2^21 slots amortise the per-iteration launches and the tail; 2^22 gains nothing more
     N = (uint32_t)std::min<unsigned long long>(N, std::max<unsigned long long>(main_work, (unsigned long long)n_tiles * LUMO_PILOT_N));
     N = std::max(N, 1024u);
     const uint32_t per_path = 2u * SP.n_shadow_rays;

@@ -98,7 +98,7 @@ __device__ __noinline__ C4 lam_pdf(const Lam& l) {                              
     if (lam_terminated(l)) c.s[0] /= 4.0;
     return c;
 }
-__device__ __noinline__ double dense_one(const double* v, double lambda) {                                                   // dense_spectrum.rs:77-97
+__device__ __forceinline__ double dense_one(const double* v, double lambda) {                                                   // dense_spectrum.rs:77-97
     const double STEP = (830.0 - 360.0) / (95.0 - 1.0);
     const unsigned long long b1 = sat_u64(ceil((lambda - 360.0) / STEP));
     const double l1 = 360.0 + STEP * (double)b1;
@@ -109,14 +109,14 @@ __device__ __noinline__ double dense_one(const double* v, double lambda) {      
     const double x1 = (lambda - l0) / STEP, x0 = 1.0 - x1;
     return __ldg(v + b0) * x0 + __ldg(v + b1) * x1;
 }
-__device__ __forceinline__ C4 dense4(const double* v, const Lam& l) { C4 c; for (int i = 0; i < 4; i++) c.s[i] = dense_one(v, l.l[i]); return c; }
-__device__ __noinline__ double spec_one(const float* c, double lambda) {                                                     // spectrum.rs:108-118
+__device__ __forceinline__ C4 dense4(const double* v, const Lam& l) { C4 c; _Pragma("unroll") for (int i = 0; i < 4; i++) c.s[i] = dense_one(v, l.l[i]); return c; }
+__device__ __forceinline__ double spec_one(const float* c, double lambda) {                                                     // spectrum.rs:108-118
     const float l = (float)lambda;
     const float x = __fadd_rn(__fadd_rn(__fmul_rn(__fmul_rn(c[0], l), l), __fmul_rn(c[1], l)), c[2]);
     const float sg = __fadd_rn(0.5f, __fdiv_rn(x, __fmul_rn(2.0f, __fsqrt_rn(__fadd_rn(1.0f, __fmul_rn(x, x))))));
     return (double)__fmul_rn(c[3], sg);
 }
-__device__ __forceinline__ C4 spec4(const float* c, const Lam& l) { C4 r; for (int i = 0; i < 4; i++) r.s[i] = spec_one(c, l.l[i]); return r; }
+__device__ __forceinline__ C4 spec4(const float* c, const Lam& l) { C4 r; _Pragma("unroll") for (int i = 0; i < 4; i++) r.s[i] = spec_one(c, l.l[i]); return r; }
 #define LUMO_Y_INTEGRAL 106.856895
 __device__ __forceinline__ const double* table(const DevScene& S, uint32_t id) { return S.tables + 96ull * id; }
 __device__ __noinline__ double luminance(const DevScene& S, C4 c, const Lam& l) {                                            // color.rs:88-91
@@ -310,7 +310,7 @@ __device__ __forceinline__ Cx csqrt(Cx a) {                                     
     const double nr = sqrt(sqrt(a.re * a.re + a.im * a.im)), ar = atan2(a.im, a.re) / 2.0;
     return cx(nr * cos(ar), nr * sin(ar));
 }
-__device__ __noinline__ double fr_complex(D3 wo, D3 wh, double eta_, double k_) {                                             // microfacet.rs:226-241
+__device__ __forceinline__ double fr_complex(D3 wo, D3 wh, double eta_, double k_) {                                             // microfacet.rs:226-241
     const Cx eta = cx(eta_, k_);
     const double cos_o = clampd(dot(wo, wh), 0.0, 1.0);
     const double sin2_o = 1.0 - cos_o * cos_o;
@@ -322,7 +322,7 @@ __device__ __noinline__ double fr_complex(D3 wo, D3 wh, double eta_, double k_) 
     const Cx r_per = cdiv(cx(cos_o - eci.re, -eci.im), cx(cos_o + eci.re, eci.im));
     return ((r_par.re * r_par.re + r_par.im * r_par.im) + (r_per.re * r_per.re + r_per.im * r_per.im)) / 2.0;
 }
-__device__ __noinline__ double fr_real(D3 wo, D3 wh, double eta_) {                                                           // microfacet.rs:244-265
+__device__ __forceinline__ double fr_real(D3 wo, D3 wh, double eta_) {                                                           // microfacet.rs:244-265
     double cos_o = dot(wo, wh);
     const double eta = cos_o < 0.0 ? 1.0 / eta_ : eta_;
     cos_o = fabs(cos_o);
@@ -339,7 +339,8 @@ __device__ __forceinline__ double fresnel_at(const DevScene& S, const Mat& m, D3
     if (k == 0.0) return e == 0.0 ? 0.0 : fr_real(wo, wh, e);
     return fr_complex(wo, wh, e, k);
 }
-__device__ __forceinline__ C4 fresnel4(const DevScene& S, const Mat& m, D3 wo, D3 wh, const Lam& l) { C4 c; for (int i = 0; i < 4; i++) c.s[i] = fresnel_at(S, m, wo, wh, l.l[i]); return c; }
+// the four hero wavelengths are independent: unrolled so that their (long, dependent) f64 chains overlap
+__device__ __noinline__ C4 fresnel4(const DevScene& S, const Mat& m, D3 wo, D3 wh, const Lam& l) { C4 c; _Pragma("unroll") for (int i = 0; i < 4; i++) c.s[i] = fresnel_at(S, m, wo, wh, l.l[i]); return c; }
 __device__ __forceinline__ bool chi_pass(D3 wo, D3 wh) { return signum(wh.z) * dot(wo, wh) * wo.z > LUMO_EPS; }                 // microfacet.rs:268-274
 __device__ __noinline__ double ggx_lambda(const Mat& m, D3 w) {                                                              // microfacet.rs:296-311
     const double tan2 = tan2_theta(w);

@@ -119,7 +119,11 @@ __device__ __forceinline__ void raster_jitter(const WaveParams& P, uint32_t pixe
 
 // ---- retire: film + refill, densely over the slots whose path ended in the previous iteration ----------
 __global__ void k_iota(uint32_t* p, uint32_t n) { for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = i; }
-__global__ void k_queue_reset(QueueCounters* qc, uint32_t cur) { qc->n_active[cur] = 0u; qc->n_done[cur ^ 1u] = 0u; }
+// end of an iteration: recycle the queue counters and log the iteration's queue sizes (rays traced / shadow rays)
+__global__ void k_queue_reset(QueueCounters* qc, uint32_t cur, const IterCounters* it, uint32_t* log, uint32_t iter, uint32_t log_cap) {
+    qc->n_active[cur] = 0u; qc->n_done[cur ^ 1u] = 0u;
+    if (log && iter < log_cap) { log[2u * iter] = it->n_active; log[2u * iter + 1u] = it->n_shadow; }
+}
 
 __global__ void __launch_bounds__(256) k_retire(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P) {
     const uint32_t N = W.n_slots, c = P.cur;

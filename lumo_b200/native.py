@@ -129,6 +129,8 @@ def gpu_lib():
         L.lumo_gpu_ctx_set_stream.argtypes = [vp, vp]
         L.lumo_gpu_ctx_kernel_times.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
         L.lumo_gpu_ctx_kernel_times.restype = C.c_int32
+        L.lumo_gpu_ctx_iter_log.argtypes = [vp, C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(C.c_uint32)]
+        L.lumo_gpu_ctx_iter_log.restype = C.c_int32
         L.lumo_gpu_ctx_set_stream.restype = C.c_int32
         L.lumo_gpu_ctx_visits.argtypes = [vp, C.POINTER(C.c_uint64)]
         for f in ("lumo_gpu_render_dev", "lumo_gpu_trace_closest_dev", "lumo_gpu_ctx_count_visits", "lumo_gpu_ctx_visits","lumo_gpu_device_count", "lumo_gpu_ctx_create", "lumo_gpu_ctx_destroy", "lumo_gpu_scene_upload", "lumo_gpu_scene_destroy",
@@ -169,6 +171,13 @@ class GpuContext:
         _check(gpu_lib().lumo_gpu_ctx_visits(self.h, out), "lumo_gpu_ctx_visits")
         names = ("tlas_nodes", "inst", "kd_nodes", "leaf_idx", "tri_tests", "sphere_tests")
         return dict(zip(names, (int(v) for v in out[:6]))), dict(zip(names, (int(v) for v in out[6:])))
+
+    def iter_log(self):
+        cap = 16384
+        out = (C.c_uint32 * (2 * cap))(); n = C.c_uint32(0)
+        _check(gpu_lib().lumo_gpu_ctx_iter_log(self.h, out, cap, C.byref(n)), "lumo_gpu_ctx_iter_log")
+        k = min(int(n.value), cap)
+        return [(int(out[2 * i]), int(out[2 * i + 1])) for i in range(k)]
 
     def kernel_times(self):
         ms = (C.c_double * 4)(); n = (C.c_uint64 * 4)()
