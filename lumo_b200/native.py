@@ -191,11 +191,13 @@ class GpuContext:
 
 class GpuScene:
     """An uploaded scene blob; entry points mirror include/lumo_gpu.h one to one (host pointers)."""
-    def __init__(self, ctx, blob_bytes):
+    def __init__(self, ctx, blob_bytes, host_ptr=None):
+        """blob_bytes: the scene blob; host_ptr: optional address of a (e.g. pinned) host copy of the same bytes to upload from."""
         self.ctx = ctx
         self.blob = Blob(blob_bytes)
         self.h = C.c_void_p()
-        _check(gpu_lib().lumo_gpu_scene_upload(ctx.h, blob_bytes, len(blob_bytes), C.byref(self.h)), "lumo_gpu_scene_upload")
+        src = C.c_char_p(blob_bytes) if host_ptr is None else C.cast(C.c_void_p(host_ptr), C.c_char_p)
+        _check(gpu_lib().lumo_gpu_scene_upload(ctx.h, src, len(blob_bytes), C.byref(self.h)), "lumo_gpu_scene_upload")
         cam = self.blob.params["camera"]
         self.res_x, self.res_y = int(cam["res_x"]), int(cam["res_y"])
 
@@ -228,12 +230,16 @@ class GpuScene:
         return t
 
     def render(self, integrator=0, spp=1, seed=1, sampler=2, tone_map=0, tone_map_arg=0.0, rr_delta=0.0, spp_begin=0, spp_end=None,
-               total_spp=None, wave_paths=0, flags=0):
+               total_spp=None, wave_paths=0, flags=0, pixels=None, splats=None):
+        """pixels / splats: optional caller-owned host arrays [H,W,4] / [H,W,3] f64 (e.g. pinned, reused across frames); overwritten."""
         total = spp if total_spp is None else total_spp
         end = total if spp_end is None else spp_end
         P = RenderParams(integrator, sampler, tone_map, flags, tone_map_arg, rr_delta, seed, spp_begin, end, total, wave_paths)
         W, H = self.res_x, self.res_y
-        pixels = np.zeros((H, W, 4)); splats = np.zeros((H, W, 3))
+        if pixels is None: pixels = np.zeros((H, W, 4))
+        if splats is None: splats = np.zeros((H, W, 3))
+        assert pixels.shape == (H, W, 4) and splats.shape == (H, W, 3) and pixels.dtype == np.float64 and splats.dtype == np.float64
+        assert pixels.flags["C_CONTIGUOUS"] and splats.flags["C_CONTIGUOUS"]
         ntiles = ((W + 15) // 16) * ((H + 15) // 16)
         deltas = np.zeros(ntiles)
         out = FilmAccum(_dp(pixels), _dp(splats), (C.c_uint64 * 8)(), _dp(deltas), 0.0)
