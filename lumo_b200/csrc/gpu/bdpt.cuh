@@ -1,18 +1,19 @@
 // Bidirectional path tracing on the device: bd_path_trace.rs:23-290, bd_path_trace/{path_gen,vertex,mis,
 // measure}.rs and the camera importance functions camera.rs:167-388.
 //
-// First device version: one persistent thread per camera sample runs the whole estimator — light
-// subpath, camera subpath, every (s,t) connection with its MIS weight — with its two vertex arrays in
-// HBM (LUMO_BDPT_MAXV vertices each; the reference caps at 1024, paths that would exceed the device cap
-// are cut there and counted in the `overflow` counter).  Traversal calls (Scene::hit, hit_t, hit_light)
-// are the same faithful routines the wavefront kernels use; visible() needs the reference's first-found
-// distance, i.e. scene_hit_t, not an any-hit boolean.
+// Vertex-buffer design: a walk kernel writes the light and camera subpaths of a batch of camera samples to
+// vertex arrays in HBM (LUMO_BDPT_MAXV vertices each; the reference caps at 1024 — subpaths that would exceed
+// the device cap are cut there and counted), a connection kernel evaluates every (s,t) term of every sample
+// in parallel (one thread per term: visibility ray, BSDFs, MIS weight), a finish kernel retires the sample
+// into the film.  Traversal calls (Scene::hit, hit_t, hit_light) are the same faithful routines the wavefront
+// kernels use; visible() needs the reference's first-found distance, i.e. scene_hit_t, not an
+// any-hit boolean.
 #pragma once
 #include "wavefront.cuh"
 
 namespace lumo_dev {
 
-#define LUMO_BDPT_MAXV 48
+#define LUMO_BDPT_MAXV 64
 #define LUMO_BDPT_MAX_DEPTH 1024u   /* bd_path_trace.rs:7 */
 
 struct Vtx { DevHit h; C4 gathered; double pdf_fwd, pdf_bck; D3 wo; int light; int pad; };   // vertex.rs:5-12
@@ -338,18 +339,42 @@ __device__ __noinline__ C4 connect_paths(const DevScene& S, const Lam& lam, cons
     return radiance * mis_weight(S, lam, lp, s, cp, t, nullptr, nullptr);
 }
 
-// ---- the estimator: bd_path_trace::integrate (bd_path_trace.rs:23-75), one thread per camera sample --------
-__global__ void __launch_bounds__(64) k_bdpt(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P, Vtx* vbuf) {
-    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-    Vtx* lp = vbuf + (size_t)tid * 2 * LUMO_BDPT_MAXV;
-    Vtx* cp = lp + LUMO_BDPT_MAXV;
+// ---- the estimator: bd_path_trace::integrate (bd_path_trace.rs:23-75) as three kernels over a batch ------
+//   k_bdpt_walk     one thread per camera sample: camera ray, wavelengths, light subpath, camera subpath; the two
+//                   vertex arrays go to the batch's vertex buffer in HBM, together with the number of connection
+//                   terms the sample has;
+//   (exclusive scan of the term counts)
+//   k_bdpt_connect  one thread per term: light tracing (t = 1, a splat), emission (s = 0), NEE (s = 1) or a
+//                   subpath connection (s, t >= 2) with its visibility ray and MIS weight; contributions are
+//                   added to the sample's radiance with f64 atomics;
+//   k_bdpt_finish   one thread per sample: reference-style cost, tone map, film.
+// Random numbers: the terms that draw (light tracing: 2 per non-delta light vertex; NEE: 3 per camera vertex that is
+// neither delta nor a light) consume the sample's stream in the reference's order; a term finds its position by
+// counting the drawing terms before it.
+struct BdptBatch {
+    uint32_t cap;                    // samples per batch
+    Vtx* lp; Vtx* cp;                // [cap][LUMO_BDPT_MAXV]
+    int* ns; int* nt;                // subpath lengths
+    double* lam;                     // [4][cap]
+    double* rx; double* ry;
+    double* radiance;                // [4][cap]
+    uint32_t *pixel, *sample, *draws, *witem, *valid;
+    unsigned long long* n_terms;     // per sample (cap + 1 entries, the last one 0)
+    unsigned long long* term_off;    // exclusive scan of n_terms, cap + 1 entries
+};
+
+__device__ __forceinline__ uint32_t bdpt_term_count(int ns, int nt) {
+    const uint32_t L = ns >= 2 ? (uint32_t)(ns - 1) : 0u, C = nt >= 2 ? (uint32_t)(nt - 1) : 0u;
+    return L + 1u + C + L * C;
+}
+
+__global__ void __launch_bounds__(64) k_bdpt_walk(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P, const __grid_constant__ BdptBatch B,
+                                                   unsigned long long w0, uint32_t n) {
     BdptCounters bc = {0, 0, 0};
-    unsigned long long paths = 0, cost_sum = 0; uint32_t max_len = 0;
     const uint32_t Wd = S.P.camera.res_x, Hd = S.P.camera.res_y;
-    for (;;) {
-        const unsigned long long w = agg_inc64(&W.run->next_work);
-        if (w >= P.total_work) break;
-        uint32_t px, py, sample;
+    for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < n; b += gridDim.x * blockDim.x) {
+        const unsigned long long w = w0 + b;
+        uint32_t px, py, sample; bool ok = true;
         if (P.mode == WM_PILOT) {
             const uint32_t tile = (uint32_t)(w / LUMO_PILOT_N), k = (uint32_t)(w % LUMO_PILOT_N);
             const uint32_t x0 = (tile % P.tiles_x) * 16u, y0 = (tile / P.tiles_x) * 16u;
@@ -363,8 +388,11 @@ __global__ void __launch_bounds__(64) k_bdpt(const __grid_constant__ DevScene S,
             px = (tile % P.tiles_x) * 16u + (blk % 2u) * 8u + (in % 8u);
             py = (tile / P.tiles_x) * 16u + (blk / 2u) * 4u + (in / 8u);
             sample = P.spp_begin + si;
-            if (px >= Wd || py >= Hd) continue;
+            ok = px < Wd && py < Hd;
         }
+        B.valid[b] = ok ? 1u : 0u;
+        B.witem[b] = (uint32_t)w;
+        if (!ok) { B.n_terms[b] = 0ull; B.ns[b] = 0; B.nt[b] = 0; continue; }
         const uint32_t pixel = px + py * Wd;
         Rng rng = rng_make(P.seed, pixel, sample, 0u, 0u);
         double jx, jy;
@@ -374,9 +402,10 @@ __global__ void __launch_bounds__(64) k_bdpt(const __grid_constant__ DevScene S,
         const Ray r = camera_generate_ray(S.P.camera, rx, ry, l0, l1);
         Lam lam = lam_sample(rng_float(rng));
         const double delta = W.tile_delta[tile_of(P, S, pixel)];
-        // light path (path_gen.rs:21-50)
+        Vtx* lp = B.lp + (size_t)b * LUMO_BDPT_MAXV;
+        Vtx* cp = B.cp + (size_t)b * LUMO_BDPT_MAXV;
         int ns;
-        {
+        {   // light path (path_gen.rs:21-50)
             const uint32_t li = sample_light(S, rng_float(rng));
             const double pdf_light = S.lights[li].pdf;
             const LumoObject lo = S.objects[S.P.n_objects + li];
@@ -391,43 +420,87 @@ __global__ void __launch_bounds__(64) k_bdpt(const __grid_constant__ DevScene S,
             const C4 gathered = emit * fabs(dot(ri.d, ho.ns)) / (pdf_light * pdf_origin * pdf_dir);
             ns = bdpt_walk(S, ri, rng, lam, delta, gathered, pdf_dir, 1, lp, bc);
         }
-        // camera path (path_gen.rs:4-19)
         int nt;
-        {
+        {   // camera path (path_gen.rs:4-19)
             const double pdf_wi = cam_pdf_wi(S.P.camera, r), pdf_xo = cam_pdf_xo(S.P.camera, r);
             v_camera(cp[0], r.o, pdf_xo, c4(1.0));
             nt = bdpt_walk(S, r, rng, lam, delta, c4(1.0), pdf_wi, 0, cp, bc);
         }
-        C4 radiance = c4(0.0);
-        unsigned long long cost = (unsigned long long)(ns + nt);
-        for (int s = 2; s <= ns; s++) {
-            if (!v_is_delta(S, lp[s - 1], lam)) cost += 1;
+        B.ns[b] = ns; B.nt[b] = nt; B.n_terms[b] = (unsigned long long)bdpt_term_count(ns, nt);
+        for (int k = 0; k < 4; k++) { B.lam[(size_t)k * B.cap + b] = lam.l[k]; B.radiance[(size_t)k * B.cap + b] = 0.0; }
+        B.rx[b] = rx; B.ry[b] = ry; B.pixel[b] = pixel; B.sample[b] = sample; B.draws[b] = rng.draws;
+    }
+    if (bc.closest) atomicAdd(&W.run->closest, bc.closest);
+    if (bc.overflow) atomicAdd(&W.run->shadow_dropped, bc.overflow);
+}
+
+__global__ void __launch_bounds__(128) k_bdpt_connect(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P, const __grid_constant__ BdptBatch B, uint32_t n) {
+    BdptCounters bc = {0, 0, 0};
+    const unsigned long long total = B.term_off[n];
+    for (unsigned long long it = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; it < total; it += (unsigned long long)gridDim.x * blockDim.x) {
+        // sample that owns term `it`: last b with term_off[b] <= it
+        uint32_t lo_ = 0, hi_ = n;
+        while (hi_ - lo_ > 1u) { const uint32_t mid = (lo_ + hi_) >> 1; if (B.term_off[mid] <= it) lo_ = mid; else hi_ = mid; }
+        const uint32_t b = lo_;
+        uint32_t j = (uint32_t)(it - B.term_off[b]);
+        const int ns = B.ns[b], nt = B.nt[b];
+        const uint32_t L = ns >= 2 ? (uint32_t)(ns - 1) : 0u, C = nt >= 2 ? (uint32_t)(nt - 1) : 0u;
+        const Vtx* lp = B.lp + (size_t)b * LUMO_BDPT_MAXV;
+        const Vtx* cp = B.cp + (size_t)b * LUMO_BDPT_MAXV;
+        Lam lam; for (int k = 0; k < 4; k++) lam.l[k] = B.lam[(size_t)k * B.cap + b];
+        C4 contrib = c4(0.0);
+        if (j < L) {                                                   // light tracing, s = j + 2 (bd_path_trace.rs:34-43)
+            const int s = (int)j + 2;
+            uint32_t drawing = 0;
+            for (int q = 2; q < s; q++) if (!v_is_delta(S, lp[q - 1], lam)) drawing++;
             C4 col; double sx, sy;
-            if (connect_light_path(S, rng, lam, lp, s, col, sx, sy, bc) && P.mode == WM_MAIN)
+            const uint32_t sample = B.sample[b];
+            Rng rs = rng_make(P.seed, B.pixel[b], sample, 0u, B.draws[b] + 2u * drawing);
+            if (connect_light_path(S, rs, lam, lp, s, col, sx, sy, bc) && P.mode == WM_MAIN)
                 film_add_sample(S, W.pixels, W.splats, tone_map(S, (int)P.tone_map, P.tone_map_arg, col, lam), lam, sx, sy, true);
+            continue;
         }
-        radiance = radiance + add_camera_path(S, lam, cp, nt);
-        for (int t = 2; t <= nt; t++) {
-            if (!v_is_delta(S, cp[t - 1], lam) && v_is_light(cp[t - 1])) cost += 1;
-            radiance = radiance + connect_camera_path(S, rng, lam, cp, t, bc);
+        j -= L;
+        if (j == 0) contrib = add_camera_path(S, lam, cp, nt);          // s = 0
+        else if (j - 1u < C) {                                          // NEE, t = j + 1 (bd_path_trace.rs:47-55)
+            const int t = (int)(j - 1u) + 2;
+            uint32_t drawing_l = 0, drawing_c = 0;
+            for (int q = 2; q <= ns; q++) if (!v_is_delta(S, lp[q - 1], lam)) drawing_l++;
+            for (int q = 2; q < t; q++) if (!(v_is_delta(S, cp[q - 1], lam) || v_is_light(cp[q - 1]))) drawing_c++;
+            Rng rs = rng_make(P.seed, B.pixel[b], B.sample[b], 0u, B.draws[b] + 2u * drawing_l + 3u * drawing_c);
+            contrib = connect_camera_path(S, rs, lam, cp, t, bc);
+        } else {                                                        // (s, t >= 2) connection; order: t outer, s inner (bd_path_trace.rs:57-66)
+            const uint32_t k = j - 1u - C;
+            const int t = (int)(k / L) + 2, s = (int)(k % L) + 2;
+            contrib = connect_paths(S, lam, lp, s, cp, t, bc);
         }
-        for (int t = 2; t <= nt; t++) for (int s = 2; s <= ns; s++) {
-            cost += 1;
-            radiance = radiance + connect_paths(S, lam, lp, s, cp, t, bc);
-        }
-        if (P.mode == WM_PILOT) { W.pilot_lum[w] = luminance(S, radiance, lam); W.pilot_cost[w] = (uint32_t)cost; }
+        if (!is_black(contrib)) for (int k = 0; k < 4; k++) if (contrib.s[k] != 0.0) atomicAdd(&B.radiance[(size_t)k * B.cap + b], contrib.s[k]);
+    }
+    if (bc.closest) atomicAdd(&W.run->closest, bc.closest);
+    if (bc.occlusion) atomicAdd(&W.run->occlusion, bc.occlusion);
+}
+
+__global__ void __launch_bounds__(256) k_bdpt_finish(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P, const __grid_constant__ BdptBatch B, uint32_t n) {
+    for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < n; b += gridDim.x * blockDim.x) {
+        if (!B.valid[b]) continue;
+        const int ns = B.ns[b], nt = B.nt[b];
+        const Vtx* lp = B.lp + (size_t)b * LUMO_BDPT_MAXV;
+        const Vtx* cp = B.cp + (size_t)b * LUMO_BDPT_MAXV;
+        Lam lam; C4 radiance;
+        for (int k = 0; k < 4; k++) { lam.l[k] = B.lam[(size_t)k * B.cap + b]; radiance.s[k] = B.radiance[(size_t)k * B.cap + b]; }
+        unsigned long long cost = (unsigned long long)(ns + nt);                                 // bd_path_trace.rs:31-66
+        for (int s = 2; s <= ns; s++) if (!v_is_delta(S, lp[s - 1], lam)) cost += 1;
+        for (int t = 2; t <= nt; t++) if (!v_is_delta(S, cp[t - 1], lam) && v_is_light(cp[t - 1])) cost += 1;
+        if (nt >= 2 && ns >= 2) cost += (unsigned long long)(nt - 1) * (unsigned long long)(ns - 1);
+        if (P.mode == WM_PILOT) { const uint32_t w = B.witem[b]; W.pilot_lum[w] = luminance(S, radiance, lam); W.pilot_cost[w] = (uint32_t)cost; }
         else {
             bool finite = true;
             for (int k = 0; k < 4; k++) finite = finite && isfinite(radiance.s[k]);
             if (!finite) atomicAdd(&W.run->nonfinite, 1ull);
-            film_add_sample(S, W.pixels, W.splats, tone_map(S, (int)P.tone_map, P.tone_map_arg, radiance, lam), lam, rx, ry, false);
-            paths++; cost_sum += cost; max_len = max(max_len, (uint32_t)(ns + nt));
+            film_add_sample(S, W.pixels, W.splats, tone_map(S, (int)P.tone_map, P.tone_map_arg, radiance, lam), lam, B.rx[b], B.ry[b], false);
+            atomicAdd(&W.run->camera_paths, 1ull); atomicAdd(&W.run->cost, cost); atomicMax(&W.run->max_depth, (uint32_t)(ns + nt));
         }
     }
-    if (paths) { atomicAdd(&W.run->camera_paths, paths); atomicAdd(&W.run->cost, cost_sum); atomicMax(&W.run->max_depth, max_len); }
-    if (bc.closest) atomicAdd(&W.run->closest, bc.closest);
-    if (bc.occlusion) atomicAdd(&W.run->occlusion, bc.occlusion);
-    if (bc.overflow) atomicAdd(&W.run->shadow_dropped, bc.overflow);
 }
 
 }  // namespace lumo_dev

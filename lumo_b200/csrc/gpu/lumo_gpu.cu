@@ -3,6 +3,7 @@
 // shade -> occlude) and the copies in and out.  No computation of the hot path happens on the CPU.
 #include "lumo_gpu.h"
 #include "bdpt.cuh"
+#include <cub/device/device_scan.cuh>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -385,18 +386,53 @@ static int32_t run_wave(lumo_scene* sc, const Wave& W, WaveParams P, uint64_t& i
     return LUMO_OK;
 }
 
-// BDPT: persistent threads, one camera sample each (bdpt.cuh)
-static int32_t run_bdpt(lumo_scene* sc, const Wave& W, const WaveParams& P, Vtx* vbuf, int grid, uint64_t& iterations) {
+// BDPT: batches of camera samples through walk -> scan -> connect -> finish (bdpt.cuh)
+#define LUMO_BDPT_BATCH (1u << 17)
+struct BdptStorage { DevBuf mem, scan_tmp; BdptBatch B; size_t scan_bytes = 0; };
+static int32_t bdpt_alloc(BdptStorage& st) {
+    const uint32_t cap = LUMO_BDPT_BATCH;
+    Carver dry{nullptr};
+    auto carve = [&](Carver& c) {
+        BdptBatch& B = st.B; B.cap = cap;
+        B.lp = c.take<Vtx>((size_t)cap * LUMO_BDPT_MAXV); B.cp = c.take<Vtx>((size_t)cap * LUMO_BDPT_MAXV);
+        B.ns = c.take<int>(cap); B.nt = c.take<int>(cap);
+        B.lam = c.take<double>(4 * (size_t)cap); B.rx = c.take<double>(cap); B.ry = c.take<double>(cap); B.radiance = c.take<double>(4 * (size_t)cap);
+        B.pixel = c.take<uint32_t>(cap); B.sample = c.take<uint32_t>(cap); B.draws = c.take<uint32_t>(cap); B.witem = c.take<uint32_t>(cap); B.valid = c.take<uint32_t>(cap);
+        B.n_terms = c.take<unsigned long long>(cap + 1); B.term_off = c.take<unsigned long long>(cap + 1);
+    };
+    carve(dry);
+    CU(st.mem.alloc(dry.off));
+    Carver c{(uint8_t*)st.mem.p}; carve(c);
+    CU(cub::DeviceScan::ExclusiveSum(nullptr, st.scan_bytes, st.B.n_terms, st.B.term_off, (int)(cap + 1)));
+    CU(st.scan_tmp.alloc(st.scan_bytes));
+    return LUMO_OK;
+}
+static int32_t run_bdpt(lumo_scene* sc, const Wave& W, const WaveParams& P, BdptStorage& bs, uint64_t& iterations) {
     lumo_ctx* ctx = sc->ctx;
     cudaStream_t st = ctx->stream;
-    CU(cudaMemsetAsync(&W.run->next_work, 0, 8, st));
-    CU(cudaEventRecord(ctx->kev[0], st));
-    k_bdpt<<<grid, 64, 0, st>>>(sc->S, W, P, vbuf);
-    CU(cudaEventRecord(ctx->kev[1], st));
-    ctx->launches++; iterations++;
-    CU(cudaStreamSynchronize(st));
-    CU(cudaGetLastError());
-    if (P.mode == WM_MAIN) { float ms = 0; CU(cudaEventElapsedTime(&ms, ctx->kev[0], ctx->kev[1])); ctx->kernel_ms[2] += ms; ctx->kernel_launches[2]++; }
+    const BdptBatch& B = bs.B;
+    cudaEvent_t* ev = ctx->kev;
+    for (unsigned long long w0 = 0; w0 < P.total_work; w0 += B.cap) {
+        const uint32_t n = (uint32_t)std::min<unsigned long long>(B.cap, P.total_work - w0);
+        CU(cudaEventRecord(ev[0], st));
+        k_bdpt_walk<<<ctx->sm_count * 16, 64, 0, st>>>(sc->S, W, P, B, w0, n);
+        CU(cudaMemsetAsync(B.n_terms + n, 0, 8, st));
+        CU(cub::DeviceScan::ExclusiveSum(bs.scan_tmp.p, bs.scan_bytes, B.n_terms, B.term_off, (int)(n + 1), st));
+        CU(cudaEventRecord(ev[1], st));
+        k_bdpt_connect<<<ctx->sm_count * 16, 128, 0, st>>>(sc->S, W, P, B, n);
+        CU(cudaEventRecord(ev[2], st));
+        k_bdpt_finish<<<ctx->sm_count * 4, 256, 0, st>>>(sc->S, W, P, B, n);
+        CU(cudaEventRecord(ev[3], st));
+        ctx->launches += 4; iterations++;
+        CU(cudaStreamSynchronize(st));
+        CU(cudaGetLastError());
+        if (P.mode == WM_MAIN) {   // kernel classes for BDPT: [1] walks (incl. their traversal), [2] connections, [0] finish / film
+            float a = 0, b = 0, c = 0;
+            CU(cudaEventElapsedTime(&a, ev[0], ev[1])); CU(cudaEventElapsedTime(&b, ev[1], ev[2])); CU(cudaEventElapsedTime(&c, ev[2], ev[3]));
+            ctx->kernel_ms[1] += a; ctx->kernel_ms[2] += b; ctx->kernel_ms[0] += c;
+            ctx->kernel_launches[0]++; ctx->kernel_launches[1]++; ctx->kernel_launches[2]++;
+        }
+    }
     return LUMO_OK;
 }
 
@@ -441,15 +477,15 @@ static int32_t render_impl(lumo_scene* sc, const lumo_render_params* rp, double*
     { const char* e = std::getenv("LUMO_DEBUG_PIXEL"); P.debug_pixel = e ? (uint32_t)std::atoll(e) : LUMO_NONE; }
     uint64_t iterations = 0;
     const bool bdpt = rp->integrator == LUMO_BD_PATH_TRACE;
-    DevBuf vbuf; int bgrid = ctx->sm_count * 8;
-    if (bdpt) CU(vbuf.alloc((size_t)bgrid * 64 * 2 * LUMO_BDPT_MAXV * sizeof(Vtx)));
+    BdptStorage bs;
+    if (bdpt) { int32_t rc = bdpt_alloc(bs); if (rc != LUMO_OK) return rc; }
     if (rp->rr_delta <= 0.0 && rp->integrator != LUMO_DIRECT_LIGHT) {
         // Per-tile Russian-roulette threshold (the role of task.rs:42-53): two pilot rounds, the second
         // using the first round's estimate.  Pilot paths never touch the film or the reported counters.
         DevBuf nd; CU(nd.alloc((size_t)n_tiles * 8));
         for (uint32_t round = 0; round < 2; round++) {
             P.mode = WM_PILOT; P.pilot_round = round; P.total_work = (unsigned long long)n_tiles * LUMO_PILOT_N;
-            int32_t rc = bdpt ? run_bdpt(sc, W, P, vbuf.as<Vtx>(), bgrid, iterations) : run_wave(sc, W, P, iterations); if (rc != LUMO_OK) return rc;
+            int32_t rc = bdpt ? run_bdpt(sc, W, P, bs, iterations) : run_wave(sc, W, P, iterations); if (rc != LUMO_OK) return rc;
             k_pilot_reduce<<<(n_tiles + 127) / 128, 128, 0, st>>>(W, n_tiles, nd.as<double>());
             ctx->launches++;
             CU(cudaMemcpyAsync(W.tile_delta, nd.p, (size_t)n_tiles * 8, cudaMemcpyDeviceToDevice, st));
@@ -458,7 +494,7 @@ static int32_t render_impl(lumo_scene* sc, const lumo_render_params* rp, double*
         CU(cudaMemsetAsync(W.run, 0, sizeof(RunCounters), st));
     }
     P.mode = WM_MAIN; P.total_work = main_work;
-    if (spp > 0) { int32_t rc = bdpt ? run_bdpt(sc, W, P, vbuf.as<Vtx>(), bgrid, iterations) : run_wave(sc, W, P, iterations); if (rc != LUMO_OK) return rc; }
+    if (spp > 0) { int32_t rc = bdpt ? run_bdpt(sc, W, P, bs, iterations) : run_wave(sc, W, P, iterations); if (rc != LUMO_OK) return rc; }
     CU(cudaEventRecord(ctx->ev1, st));
     HostCounters* hc = (HostCounters*)ctx->host_pinned;
     CU(cudaMemcpyAsync(&hc->run, W.run, sizeof(RunCounters), cudaMemcpyDeviceToHost, st));
