@@ -145,7 +145,7 @@ struct KdStackEntry { uint32_t node; double t_start, t_end; };
 // the triangle test together.  Per lane the sequence of nodes, triangles and comparisons is exactly
 // kdtree.rs:117-160.
 template <bool GEO, bool CNT>
-__device__ __noinline__ bool kd_hit(const DevScene& S, const LumoKdTree* tree, const RayCtx& ctx, double t_min, double t_max,
+__device__ __forceinline__ bool kd_hit(const DevScene& S, const LumoKdTree* tree, const RayCtx& ctx, double t_min, double t_max,
                                     double& t_out, uint32_t& tri_out, D3& bary_out, Counters* c) {
     const Ray r = ctx.r;
     const RayTri q = ctx.q;
@@ -332,7 +332,7 @@ struct HitRec { double t; D3 bary; uint32_t obj, tri; };
 // Object::hit for one object record: distance + which triangle + barycentrics (the rest of `Hit`
 // is rebuilt from these by the shading kernels, shade.cuh reconstruct_hit).
 template <bool CNT>
-__device__ __forceinline__ bool object_hit(const DevScene& S, const LumoObject& o, const RayCtx& w, double t_min, double t_max, HitRec& h, Counters* c) {
+__device__ __noinline__ bool object_hit(const DevScene& S, const LumoObject& o, const RayCtx& w, double t_min, double t_max, HitRec& h, Counters* c) {
     LUMO_LOCAL_CTX(S, o, w, c);
     switch (o.kind) {
     case LOBJ_KD: case LOBJ_RECT:
