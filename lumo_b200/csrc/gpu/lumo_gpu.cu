@@ -320,7 +320,7 @@ template <int K>
 static void launch_shade_kind(lumo_scene* sc, const Wave& W, const WaveParams& P, int grid, int nee_grid, cudaStream_t st, unsigned long long& launches) {
     if (!(sc->kind_mask & (1u << K))) return;
     k_scatter<K><<<grid, 128, 0, st>>>(sc->S, W, P);
-    k_nee<K><<<nee_grid, 128, 0, st>>>(sc->S, W, P);
+    if (sc->S.P.n_shadow_rays > 1) k_nee<K, true><<<nee_grid, 128, 0, st>>>(sc->S, W, P); else k_nee<K, false><<<nee_grid, 128, 0, st>>>(sc->S, W, P);
     launches += 2;
 }
 

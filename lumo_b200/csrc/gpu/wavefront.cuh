@@ -466,26 +466,24 @@ __device__ __forceinline__ C4 mis_sample(const DevScene& S, const Mat& m, const 
     return bsdf * c4(1.0) * mat_emit(S, S.materials[hi.material], lam, hi.backface) * shading_cosine(m, wi, ho.ns) * weight / p_denom;
 }
 
-// One thread per MIS term of integrator.rs:89-137: item = (queue entry, shadow sample i, A = light sample | B = BSDF sample).
-template <int K>
+// integrator.rs:89-137.  A shadow sample has a light-sampled term (A) and a BSDF-sampled term (B), the latter almost
+// always ending at "the sampled direction misses the light".  Scenes with one shadow sample per bounce (<= 3 lights) run
+// one thread per path doing A then B (all lanes busy in A).  Scenes with several (n_shadow = log2 #lights) run one thread
+// per term, laid out so that every lane of a warp evaluates the same term index for 32 consecutive queue entries.
+template <int K, bool SPLIT>
 __global__ void __launch_bounds__(128, 4) k_nee(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P) {
     const uint32_t N = W.n_slots, nq = W.it->n_class[K], cur = P.cur;
-    const uint32_t ns = S.P.n_shadow_rays, per = 2u * ns;
-    const unsigned long long total = (unsigned long long)nq * per;
+    const uint32_t ns = S.P.n_shadow_rays;
+    const uint32_t per = SPLIT ? 2u * ns : ns;
     const unsigned long long padded = (unsigned long long)((nq + 31u) / 32u) * 32ull * per;
-    (void)total;
     for (unsigned long long it = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; it < padded; it += (unsigned long long)gridDim.x * blockDim.x) {
-        // warp-uniform term: 32 consecutive queue entries x `per` terms; every lane of a warp evaluates the same
-        // term (shadow sample i, light- or BSDF-sampled) for 32 different paths
-        // (with a single shadow sample the two terms of a path sit in adjacent lanes instead and share its state through L1)
-        uint32_t j, qi;
-        if (ns > 1u) { const unsigned long long grp = it / (32ull * per); j = (uint32_t)((it / 32ull) % per); qi = (uint32_t)(grp * 32ull + (it % 32ull)); }
-        else { j = (uint32_t)(it % per); qi = (uint32_t)(it / per); }
-        const uint32_t i = j >> 1;
+        const unsigned long long grp = it / (32ull * per);
+        const uint32_t j = (uint32_t)((it / 32ull) % per);
+        const uint32_t qi = (uint32_t)(grp * 32ull + (it % 32ull));
+        const uint32_t i = SPLIT ? j >> 1 : j;
         if (qi >= nq) continue;
         const uint32_t slot = W.cls[K][qi];
         if (!(W.flags[slot] & PF_NEE)) continue;
-        const bool b_term = (j & 1u) != 0u;
         Ray ro; HitRec rec; load_path(W, cur, slot, ro, rec);
         const DevHit ho = reconstruct_hit(S, ro, rec);
         const Mat& m = S.materials[ho.material];
@@ -496,29 +494,45 @@ __global__ void __launch_bounds__(128, 4) k_nee(const __grid_constant__ DevScene
         const D3 wo = -ro.d;
         const bool dbg = pixel == P.debug_pixel && P.mode == WM_MAIN;
         // draws of this bounce: 3 for the scatter sample, then 6 per shadow sample: light pick, light point (2), BSDF sample (3)
-        Rng rng = rng_make(P.seed, pixel, W.sample[slot], 0u, W.draws[cur][slot] + 3u + 6u * i);
+        const uint32_t d0 = W.draws[cur][slot] + 3u + 6u * i;
+        Rng rng = rng_make(P.seed, pixel, W.sample[slot], 0u, d0);
         const uint32_t li = sample_light(S, rng_float(rng));
         const double pdf_light = S.lights[li].pdf;
         const uint32_t lobj = S.P.n_objects + li;
         const LumoObject lo = S.objects[lobj];
-        D3 wi;
-        if (!b_term) {
-            const double r0 = rng_float(rng), r1 = rng_float(rng);
-            wi = light_sample_towards(S, lo, ho.p, r0, r1);
-        } else {
-            rng = rng_make(P.seed, pixel, W.sample[slot], 0u, W.draws[cur][slot] + 3u + 6u * i + 3u);
-            const double ru = rng_float(rng), r0 = rng_float(rng), r1 = rng_float(rng);
-            Lam l2 = lam;
-            if (!bsdf_sample<K>(S, m, uvw, wo, ho, l2, ru, r0, r1, wi)) continue;
+        auto do_term = [&](int term) {
+            D3 wi;
+            if (term == 0) {
+                const double r0 = rng_float(rng), r1 = rng_float(rng);
+                wi = light_sample_towards(S, lo, ho.p, r0, r1);
+            } else {
+                if (SPLIT) rng = rng_make(P.seed, pixel, W.sample[slot], 0u, d0 + 3u);
+                const double ru = rng_float(rng), r0 = rng_float(rng), r1 = rng_float(rng);
+                Lam l2 = lam;
+                if (!bsdf_sample<K>(S, m, uvw, wo, ho, l2, ru, r0, r1, wi)) return;
+            }
+            // mis_sample returns black when either pdf is zero (integrator.rs:150-152) whatever the light test says.  For the
+            // reflection-only BxDFs the pdf starts with two sign tests (bsdf.rs:88-90, bxdf.rs:136-139, scatter.rs:14-17):
+            // a light-sampled direction below the surface stops here, before any light or microfacet arithmetic.
+            // (measured: worth it for the one-thread-per-path form only; with one thread per term the early exits just thin the warps)
+            if (!SPLIT && K != LMAT_MFDIELECTRIC && term == 0) {
+                if (!is_reflection(wo, wi, ho.ng)) return;
+                if (!same_hemisphere(to_local(uvw, wo), to_local(uvw, wi))) return;
+            }
+            const Ray ri = hit_generate_ray(ho, wi);
+            DevHit hi;
+            if (!light_hit(S, lobj, ri, hi)) return;
+            const double p_lig = light_sample_towards_pdf(S, lo, ri, hi.p, hi.ng);
+            const double p_sct = bsdf_pdf<K>(S, m, uvw, wo, wi, ho, lam, false);
+            const C4 c = mis_sample<K>(S, m, uvw, wo, wi, ho, hi, lam, term == 0, p_lig, p_sct);
+            if (dbg) printf("  [gpu] %c vis t=%.17g p_lig=%.17g p_sct=%.17g c0=%.17g\n", term ? 'B' : 'A', hi.t, p_lig, p_sct, c.s[0]);
+            if (!is_black(c)) push_shadow(W, slot, ri, hi.t - LUMO_EPS, gathered * (c / pdf_light) / (double)ns);
+        };
+        if (SPLIT) do_term((int)(j & 1u));
+        else {
+#pragma unroll 1
+            for (int term = 0; term < 2; term++) do_term(term);
         }
-        const Ray ri = hit_generate_ray(ho, wi);
-        DevHit hi;
-        if (!light_hit(S, lobj, ri, hi)) continue;
-        const double p_lig = light_sample_towards_pdf(S, lo, ri, hi.p, hi.ng);
-        const double p_sct = bsdf_pdf<K>(S, m, uvw, wo, wi, ho, lam, false);
-        const C4 c = mis_sample<K>(S, m, uvw, wo, wi, ho, hi, lam, !b_term, p_lig, p_sct);
-        if (dbg) printf("  [gpu] %c vis t=%.17g p_lig=%.17g p_sct=%.17g c0=%.17g\n", b_term ? 'B' : 'A', hi.t, p_lig, p_sct, c.s[0]);
-        if (!is_black(c)) push_shadow(W, slot, ri, hi.t - LUMO_EPS, gathered * (c / pdf_light) / (double)ns);
     }
 }
 

@@ -7,7 +7,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 HOST_SO = os.path.join(HERE, "liblumo_host.so")
-GPU_SO = os.path.join(HERE, "liblumo_gpu.so")
+GPU_SO = os.environ.get("LUMO_GPU_SO", os.path.join(HERE, "liblumo_gpu.so"))   # override: A/B timing of two builds
 
 SECTIONS = ["tlas_nodes", "tlas_leaf", "objects", "instances", "kd_trees", "kd_nodes", "kd_leaf", "tri_verts", "tri_shade",
             "normals", "uvs", "rects", "spheres", "materials", "tables", "lights"]
