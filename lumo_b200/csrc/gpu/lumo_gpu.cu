@@ -158,6 +158,8 @@ static bool validate_blob(const uint8_t* b, uint64_t len, LumoBlobHeader& H, std
             (o.kind == LOBJ_RECT && o.rect >= H.sec[LSEC_RECTS].count)) { why = "object record " + std::to_string(i) + " out of range"; return false; }
     }
     const LumoKdTree* kds = (const LumoKdTree*)(b + H.sec[LSEC_KD_TREES].offset);
+    for (uint64_t i = P.n_objects; i < H.sec[LSEC_OBJECTS].count; i++)   // lights are intersected with a small kd stack (LUMO_LIGHT_KD_STACK)
+        if ((objs[i].kind == LOBJ_KD || objs[i].kind == LOBJ_RECT) && kds[objs[i].geom].n_tris > LUMO_LIGHT_KD_STACK) { why = "light kd-tree too large (lights are Rectangle / Triangle / Sphere objects)"; return false; }
     for (uint64_t i = 0; i < H.sec[LSEC_KD_TREES].count; i++)
         if (kds[i].root >= H.sec[LSEC_KD_NODES].count || (uint64_t)kds[i].tri_base + kds[i].n_tris > H.sec[LSEC_TRI_VERTS].count) { why = "kd tree record out of range"; return false; }
     const LumoKdNode* kn = (const LumoKdNode*)(b + H.sec[LSEC_KD_NODES].offset);

@@ -654,7 +654,7 @@ __device__ __noinline__ DevHit light_sample_on(const DevScene& S, const LumoObje
 __device__ __noinline__ bool light_hit(const DevScene& S, uint32_t obj_index, const Ray& r, DevHit& out) {
     HitRec rec;
     RayCtx w; make_ctx(r, w);
-    if (!object_hit<false>(S, S.objects[obj_index], w, 0.0, LUMO_INF, rec, nullptr)) return false;
+    if (!object_hit<false, LUMO_LIGHT_KD_STACK>(S, S.objects[obj_index], w, 0.0, LUMO_INF, rec, nullptr)) return false;
     rec.obj = obj_index;
     out = reconstruct_hit(S, r, rec);
     return true;

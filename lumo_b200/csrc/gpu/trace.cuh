@@ -144,13 +144,17 @@ struct KdStackEntry { uint32_t node; double t_start, t_end; };
 // pops its stack until it holds the next triangle to test, then all lanes of the warp that hold one run
 // the triangle test together.  Per lane the sequence of nodes, triangles and comparisons is exactly
 // kdtree.rs:117-160.
-template <bool GEO, bool CNT>
+// STACK: capacity of the (node, t_start, t_end) stack.  The reference's is 64 (kdtree.rs:110); the kd-trees of
+// Rectangle lights have two triangles, and the shading kernels that intersect one chosen light use a small one
+// so that their per-thread frame stays small (lumo_gpu_scene_upload checks that light kd-trees fit).
+#define LUMO_LIGHT_KD_STACK 8
+template <bool GEO, bool CNT, int STACK = 64>
 __device__ __forceinline__ bool kd_hit(const DevScene& S, const LumoKdTree* tree, const RayCtx& ctx, double t_min, double t_max,
                                     double& t_out, uint32_t& tri_out, D3& bary_out, Counters* c) {
     const Ray r = ctx.r;
     const RayTri q = ctx.q;
     const D3 inv = ctx.inv;
-    KdStackEntry stack[64];
+    KdStackEntry stack[STACK];
     int sp = 0;
     double t_hit = LUMO_INF;
     uint32_t curr = tree->root;
@@ -190,7 +194,7 @@ __device__ __forceinline__ bool kd_hit(const DevScene& S, const LumoKdTree* tree
                 else if (t_split < t_start) curr = second;
                 else {
                     curr = first;
-                    if (sp < 64) { stack[sp].node = second; stack[sp].t_start = t_split; stack[sp].t_end = t_end; sp++; }
+                    if (sp < STACK) { stack[sp].node = second; stack[sp].t_start = t_split; stack[sp].t_end = t_end; sp++; }
                     t_end = t_split;
                 }
             }
@@ -331,12 +335,12 @@ struct HitRec { double t; D3 bary; uint32_t obj, tri; };
 
 // Object::hit for one object record: distance + which triangle + barycentrics (the rest of `Hit`
 // is rebuilt from these by the shading kernels, shade.cuh reconstruct_hit).
-template <bool CNT>
+template <bool CNT, int STACK = 64>
 __device__ __noinline__ bool object_hit(const DevScene& S, const LumoObject& o, const RayCtx& w, double t_min, double t_max, HitRec& h, Counters* c) {
     LUMO_LOCAL_CTX(S, o, w, c);
     switch (o.kind) {
     case LOBJ_KD: case LOBJ_RECT:
-        return kd_hit<true, CNT>(S, S.kd_trees + o.geom, l, t_min, t_max, h.t, h.tri, h.bary, c);
+        return kd_hit<true, CNT, STACK>(S, S.kd_trees + o.geom, l, t_min, t_max, h.t, h.tri, h.bary, c);
     case LOBJ_SPHERE: {
         LUMO_CNT(sphere);
         double t = sphere_hit(S.spheres[o.geom].radius, l.r, t_min, t_max);
