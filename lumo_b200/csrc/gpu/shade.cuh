@@ -705,13 +705,19 @@ __device__ __forceinline__ double mitch(double x, double b, double c) {
     else if (x < 2.0) p = (-b - 6.0 * c) * powi(x, 3) + (6.0 * b + 30.0 * c) * powi(x, 2) + (-12.0 * b - 48.0 * c) * x + (8.0 * b + 24.0 * c);
     return p / 6.0;
 }
-__device__ __forceinline__ double filter_eval(const LumoFilm& F, double x, double y) {
+// PixelFilter::eval (filter.rs:82-102) is a product of the same 1-D profile in x and y for every filter kind; the
+// per-axis factors of a sample's footprint are evaluated once per row / column instead of once per pixel.
+__device__ __forceinline__ double filter_1d(const LumoFilm& F, double v, double gr) {
     switch (F.filter_kind) {
-    case 0: return (fabs(x) < F.filter_r && fabs(y) < F.filter_r) ? 1.0 : 0.0;
-    case 1: return fmax(F.filter_r - fabs(x), 0.0) * fmax(F.filter_r - fabs(y), 0.0);
-    case 2: { const double gr = gauss(F.filter_r, F.filter_p); return fmax(gauss(x, F.filter_p) - gr, 0.0) * fmax(gauss(y, F.filter_p) - gr, 0.0); }
-    default: { const double c = (1.0 - F.filter_p) / 2.0; return mitch(2.0 * x / F.filter_r, F.filter_p, c) * mitch(2.0 * y / F.filter_r, F.filter_p, c); }
+    case 0: return fabs(v) < F.filter_r ? 1.0 : 0.0;
+    case 1: return fmax(F.filter_r - fabs(v), 0.0);
+    case 2: return fmax(gauss(v, F.filter_p) - gr, 0.0);
+    default: return mitch(2.0 * v / F.filter_r, F.filter_p, (1.0 - F.filter_p) / 2.0);
     }
+}
+__device__ __forceinline__ double filter_eval(const LumoFilm& F, double x, double y) {
+    const double gr = F.filter_kind == 2 ? gauss(F.filter_r, F.filter_p) : 0.0;
+    return filter_1d(F, x, gr) * filter_1d(F, y, gr);
 }
 __device__ __forceinline__ C4 tone_map(const DevScene& S, int kind, double arg, C4 c, const Lam& l) {
     if (kind == 1) { C4 r; for (int i = 0; i < 4; i++) r.s[i] = clampd(c.s[i], 0.0, arg); return r; }
@@ -736,12 +742,19 @@ __device__ __noinline__ void film_add_sample(const DevScene& S, double* pixels, 
         mi_x = max(mi_x, tx0); mi_y = max(mi_y, ty0);
         mx_x = min(px + r, tx1 - 1); mx_y = min(py + r, ty1 - 1);
     }
-    for (unsigned long long fy = mi_y; fy <= mx_y; fy++) for (unsigned long long fx = mi_x; fx <= mx_x; fx++) {
-        const double w = filter_eval(F, rx - (0.5 + (double)fx), ry - (0.5 + (double)fy));
-        if (w != 0.0) {
-            const unsigned long long idx = fx + fy * W;
-            if (splat) { atomicAdd(splats + 3 * idx, rgb.x * w); atomicAdd(splats + 3 * idx + 1, rgb.y * w); atomicAdd(splats + 3 * idx + 2, rgb.z * w); }
-            else { atomicAdd(pixels + 4 * idx, rgb.x * w); atomicAdd(pixels + 4 * idx + 1, rgb.y * w); atomicAdd(pixels + 4 * idx + 2, rgb.z * w); atomicAdd(pixels + 4 * idx + 3, w); }
+    const double gr = F.filter_kind == 2 ? gauss(F.filter_r, F.filter_p) : 0.0;
+    double wx[8];                                                     // column factors of the footprint (r_disc <= 3 in practice)
+    const bool cached = mx_x - mi_x < 8ull;
+    if (cached) for (unsigned long long fx = mi_x; fx <= mx_x; fx++) wx[fx - mi_x] = filter_1d(F, rx - (0.5 + (double)fx), gr);
+    for (unsigned long long fy = mi_y; fy <= mx_y; fy++) {
+        const double wy = filter_1d(F, ry - (0.5 + (double)fy), gr);
+        for (unsigned long long fx = mi_x; fx <= mx_x; fx++) {
+            const double w = (cached ? wx[fx - mi_x] : filter_1d(F, rx - (0.5 + (double)fx), gr)) * wy;
+            if (w != 0.0) {
+                const unsigned long long idx = fx + fy * W;
+                if (splat) { atomicAdd(splats + 3 * idx, rgb.x * w); atomicAdd(splats + 3 * idx + 1, rgb.y * w); atomicAdd(splats + 3 * idx + 2, rgb.z * w); }
+                else { atomicAdd(pixels + 4 * idx, rgb.x * w); atomicAdd(pixels + 4 * idx + 1, rgb.y * w); atomicAdd(pixels + 4 * idx + 2, rgb.z * w); atomicAdd(pixels + 4 * idx + 3, w); }
+            }
         }
     }
 }
