@@ -97,6 +97,41 @@ def ray_bytes(v, n_rays, fixed):
     return fixed * n_rays + 64 * v["tlas_nodes"] + 96 * v["inst"] + 16 * v["kd_nodes"] + 4 * v["leaf_idx"] + 72 * v["tri_tests"] + 16 * v["sphere_tests"]
 
 
+def micro_trace(scene, dev, torch, np, n=1 << 22):
+    """lumo_gpu_trace_closest_dev on device-resident batches; kernel time from the library's CUDA events."""
+    P = scene.blob.params; cam = P["camera"]
+    W, H = int(cam["res_x"]), int(cam["res_y"])
+    g = torch.Generator(device=dev); g.manual_seed(23)
+    # primary rays: Camera::generate_ray for a pinhole camera (camera.rs:257-268), evaluated in f64 on the host side of the bench
+    rs = np.random.RandomState(23)
+    raster = np.stack([rs.rand(n) * W, rs.rand(n) * H, np.zeros(n), np.ones(n)], 0)
+    def xf(m16, v):
+        r = np.asarray(m16, np.float64).reshape(4, 4) @ v
+        w = np.where(r[3] == 0.0, 1.0, r[3]); r = r / w; r[3] = 1.0
+        return r
+    c = xf(cam["camera_to_screen_inv"], xf(cam["screen_to_raster_inv"], raster))
+    d_local = c[:3] / np.linalg.norm(c[:3], axis=0)
+    m = np.asarray(cam["world_to_camera_inv"], np.float64).reshape(4, 4)
+    o_w = np.repeat(m[:3, 3:4], n, axis=1)
+    d_w = m[:3, :3] @ d_local; d_w = d_w / np.linalg.norm(d_w, axis=0)
+    out = {}
+    lo = torch.tensor(np.array(P["bounds_lo"]), dtype=torch.float64, device=dev); hi = torch.tensor(np.array(P["bounds_hi"]), dtype=torch.float64, device=dev)
+    o2 = lo + torch.rand((n, 3), dtype=torch.float64, device=dev, generator=g) * (hi - lo)
+    z = 1 - 2 * torch.rand(n, dtype=torch.float64, device=dev, generator=g); ph = 2 * np.pi * torch.rand(n, dtype=torch.float64, device=dev, generator=g)
+    r = torch.sqrt(torch.clamp(1 - z * z, min=0))
+    d2 = torch.stack([r * torch.cos(ph), r * torch.sin(ph), z], -1).contiguous()
+    batches = {"primary": (torch.tensor(np.ascontiguousarray(o_w.T), device=dev), torch.tensor(np.ascontiguousarray(d_w.T), device=dev)), "incoherent": (o2.contiguous(), d2)}
+    obj = torch.empty(n, dtype=torch.int32, device=dev); tri = torch.empty(n, dtype=torch.int32, device=dev)
+    t = torch.empty(n, dtype=torch.float64, device=dev); bary = torch.empty((n, 2), dtype=torch.float64, device=dev)
+    for name, (o, d) in batches.items():
+        best = None
+        for k in range(4):
+            ms = scene.trace_closest_dev(o.data_ptr(), d.data_ptr(), n, obj.data_ptr(), tri.data_ptr(), t.data_ptr(), bary.data_ptr())
+            if k > 0: best = ms if best is None else min(best, ms)
+        out[name] = {"mrays_per_s": n / best / 1e3, "ms": best, "rays": n, "hit_fraction": float((obj != -1).double().mean().item())}
+    return out
+
+
 def cpu_baseline(prog, integrator, threads, spp=1, total_spp=None, seed=1):
     """The C++ restatement of lumo's CPU renderer (reference schedule: 16x16 tiles x 256-sample batches from a
     shared queue, per-tile xorshift; renderer.rs:174-204), -O3 -march=native, `threads` workers."""
@@ -277,10 +312,12 @@ def main():
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             sc2 = native.GpuScene(ctx, blob, host_ptr=pin_blob.data_ptr())
-            px, sp, cnt2, _, _ = sc2.render(integrator=integrator, spp=spp, seed=seeds[min(i, len(seeds) - 1)], wave_paths=args.wave_paths, pixels=pin_px.numpy(), splats=pin_sp.numpy())
+            t1 = time.perf_counter()
+            px, sp, cnt2, _, dev_ms = sc2.render(integrator=integrator, spp=spp, seed=seeds[min(i, len(seeds) - 1)], wave_paths=args.wave_paths, pixels=pin_px.numpy(), splats=pin_sp.numpy())
+            t2 = time.perf_counter()
             sc2.close()
             dt = time.perf_counter() - t0
-            print("e2e step %d: %.1f ms wall" % (i, 1e3 * dt), file=sys.stderr)
+            print("e2e step %d: %.1f ms wall (upload %.1f, render call %.1f of which device %.1f, iterations %d)" % (i, 1e3 * dt, 1e3 * (t1 - t0), 1e3 * (t2 - t1), dev_ms, cnt2["iterations"]), file=sys.stderr)
             if i > 0: e_rays += cnt2["closest"] + cnt2["occlusion"]; e_t += dt
         line["e2e"] = {"value": e_rays / e_t / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": len(blob) + 64, "d2h_bytes_per_step": W * H * 56 + 64,
                        "what": "lumo_gpu_scene_upload (pinned host blob) + lumo_gpu_render (pinned host film buffers) + lumo_gpu_scene_destroy per step, wall clock, mean of up to 5 steps after one discarded"}
@@ -288,6 +325,14 @@ def main():
     else:
         line["e2e"] = {"value": e2e_multi, "unit": "Mrays/s", "h2d_bytes_per_step": 128, "d2h_bytes_per_step": W * H * 56,
                        "what": "render_dev on every rank + NCCL reduce + film download on rank 0, wall clock (max over ranks); scene already resident"}
+
+    # micro: the closest-hit kernel alone on caller-supplied batches (SURVEY 8d "micro"): 2^22 primary rays of the config
+    # camera and 2^22 incoherent rays (origins uniform in the scene bounds, directions uniform on the sphere)
+    if world == 1:
+        try:
+            line["micro"] = micro_trace(scene, dev, torch, np)
+        except Exception as e:
+            line["micro"] = {"error": str(e)}
 
     if world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1

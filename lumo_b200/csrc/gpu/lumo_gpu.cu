@@ -26,6 +26,9 @@ struct lumo_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // wave storage, grown on demand and reused across renders
     void* wave_mem = nullptr; size_t wave_bytes = 0;
+    unsigned long long* d_cursor = nullptr;            // work cursor of the ray-batch kernels
+    uint8_t* blob_cache = nullptr; uint64_t blob_cache_bytes = 0;   // one recycled scene allocation (cudaFree / cudaMalloc stall unpredictably)
+    void* film_mem = nullptr; size_t film_bytes = 0;   // device film of lumo_gpu_render (host-buffer entry point), reused across calls
     void* host_pinned = nullptr;   // IterCounters + RunCounters read-back
     unsigned long long launches = 0;
     Counters* d_visit = nullptr;   // traversal visit counters (CNT passes): [0] closest-hit kernels, [1] occlusion kernels
@@ -38,7 +41,7 @@ struct lumo_ctx {
 };
 struct lumo_scene {
     lumo_ctx* ctx = nullptr;
-    uint8_t* d_blob = nullptr; uint64_t len = 0;
+    uint8_t* d_blob = nullptr; uint64_t len = 0, cap = 0;
     DevScene S;
     LumoBlobHeader H;
     uint32_t kind_mask = 0;   // bit k set: some Standard material of LumoMatKind k exists (which shade kernels to launch)
@@ -69,6 +72,7 @@ extern "C" int32_t lumo_gpu_ctx_create(int32_t device, lumo_ctx** out) {
     CU(cudaMemset(ctx->d_visit, 0, 2 * sizeof(Counters)));
     for (auto& e : ctx->kev) CU(cudaEventCreate(&e));
     CU(cudaMalloc(&ctx->d_iter_log, LUMO_ITER_LOG_CAP * 8));
+    CU(cudaMalloc(&ctx->d_cursor, 8));
     // f64 traversal keeps two explicit stacks per thread
     cudaDeviceSetLimit(cudaLimitStackSize, 4096);
     { const char* e = std::getenv("LUMO_TRACE_FLAT"); if (e) ctx->flat = std::atoi(e) != 0; }
@@ -78,6 +82,9 @@ extern "C" int32_t lumo_gpu_ctx_destroy(lumo_ctx* ctx) {
     if (!ctx) return LUMO_OK;
     cudaSetDevice(ctx->device);
     if (ctx->wave_mem) cudaFree(ctx->wave_mem);
+    if (ctx->film_mem) cudaFree(ctx->film_mem);
+    if (ctx->d_cursor) cudaFree(ctx->d_cursor);
+    if (ctx->blob_cache) cudaFree(ctx->blob_cache);
     if (ctx->d_visit) cudaFree(ctx->d_visit);
     if (ctx->d_iter_log) cudaFree(ctx->d_iter_log);
     if (ctx->host_pinned) cudaFreeHost(ctx->host_pinned);
@@ -185,7 +192,9 @@ extern "C" int32_t lumo_gpu_scene_upload(lumo_ctx* ctx, const void* blob, uint64
     lumo_scene* sc = new (std::nothrow) lumo_scene();
     if (!sc) return fail(LUMO_ERR_OOM, "scene_upload: out of host memory");
     sc->ctx = ctx; sc->len = len; sc->H = H;
-    cudaError_t e = cudaMalloc((void**)&sc->d_blob, len);
+    cudaError_t e = cudaSuccess;
+    if (ctx->blob_cache && ctx->blob_cache_bytes >= len) { sc->d_blob = ctx->blob_cache; sc->cap = ctx->blob_cache_bytes; ctx->blob_cache = nullptr; ctx->blob_cache_bytes = 0; }
+    else { e = cudaMalloc((void**)&sc->d_blob, len); sc->cap = len; }
     if (e != cudaSuccess) { delete sc; return fail(LUMO_ERR_OOM, std::string("scene_upload: cudaMalloc: ") + cudaGetErrorString(e)); }
     e = cudaMemcpyAsync(sc->d_blob, blob, len, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
@@ -206,8 +215,11 @@ extern "C" int32_t lumo_gpu_scene_upload(lumo_ctx* ctx, const void* blob, uint64
 }
 extern "C" int32_t lumo_gpu_scene_destroy(lumo_scene* sc) {
     if (!sc) return LUMO_OK;
-    cudaSetDevice(sc->ctx->device);
-    cudaFree(sc->d_blob);
+    lumo_ctx* ctx = sc->ctx;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (sc->cap > ctx->blob_cache_bytes) { if (ctx->blob_cache) cudaFree(ctx->blob_cache); ctx->blob_cache = sc->d_blob; ctx->blob_cache_bytes = sc->cap; }
+    else cudaFree(sc->d_blob);
     delete sc; return LUMO_OK;
 }
 
@@ -243,8 +255,8 @@ static int32_t trace_host(lumo_scene* sc, const double* o, const double* d, cons
     if (n == 0) return LUMO_OK;
     lumo_ctx* ctx = sc->ctx;
     CU(cudaSetDevice(ctx->device));
-    DevBuf bo, bd, bt, bobj, btri, btt, bbary, bocc, bnext;
-    CU(bo.alloc(n * 24)); CU(bd.alloc(n * 24)); CU(bnext.alloc(8));
+    DevBuf bo, bd, bt, bobj, btri, btt, bbary, bocc;
+    CU(bo.alloc(n * 24)); CU(bd.alloc(n * 24));
     if (t_max) CU(bt.alloc(n * 8));
     if (MODE == 0) { CU(bobj.alloc(n * 4)); CU(btri.alloc(n * 4)); CU(bbary.alloc(n * 16)); }
     if (MODE != 1) CU(btt.alloc(n * 8)); else CU(bocc.alloc(n));
@@ -252,7 +264,7 @@ static int32_t trace_host(lumo_scene* sc, const double* o, const double* d, cons
     CU(cudaMemcpyAsync(bo.p, o, n * 24, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(bd.p, d, n * 24, cudaMemcpyHostToDevice, st));
     if (t_max) CU(cudaMemcpyAsync(bt.p, t_max, n * 8, cudaMemcpyHostToDevice, st));
-    int32_t rc = launch_batch<MODE>(sc, bo.as<double>(), bd.as<double>(), t_max ? bt.as<double>() : nullptr, n, bnext.as<unsigned long long>(),
+    int32_t rc = launch_batch<MODE>(sc, bo.as<double>(), bd.as<double>(), t_max ? bt.as<double>() : nullptr, n, ctx->d_cursor,
                                     bobj.as<uint32_t>(), btri.as<uint32_t>(), btt.as<double>(), bbary.as<double>(), bocc.as<uint8_t>());
     if (rc != LUMO_OK) return rc;
     if (MODE == 0) {
@@ -278,9 +290,8 @@ extern "C" int32_t lumo_gpu_trace_closest_dev(lumo_scene* sc, const double* o_de
     if (!sc || !o_dev || !d_dev || !obj_dev || !tri_dev || !t_dev || !bary_dev) return fail(LUMO_ERR_INVALID, "trace_closest_dev: null pointer");
     lumo_ctx* ctx = sc->ctx;
     CU(cudaSetDevice(ctx->device));
-    DevBuf bnext; CU(bnext.alloc(8));
     CU(cudaEventRecord(ctx->ev0, ctx->stream));
-    int32_t rc = launch_batch<0>(sc, o_dev, d_dev, nullptr, n, bnext.as<unsigned long long>(), obj_dev, tri_dev, t_dev, bary_dev, nullptr);
+    int32_t rc = launch_batch<0>(sc, o_dev, d_dev, nullptr, n, ctx->d_cursor, obj_dev, tri_dev, t_dev, bary_dev, nullptr);
     if (rc != LUMO_OK) return rc;
     CU(cudaEventRecord(ctx->ev1, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -310,7 +321,7 @@ static void carve_wave(Wave& W, Carver& c, uint32_t N, uint32_t shadow_cap, uint
     W.sox = c.take<double>(C); W.soy = c.take<double>(C); W.soz = c.take<double>(C); W.sdx = c.take<double>(C); W.sdy = c.take<double>(C); W.sdz = c.take<double>(C);
     W.stmax = c.take<double>(C); W.sc = c.take<double>(4 * C); W.sslot = c.take<uint32_t>(C);
     W.it = c.take<IterCounters>(1); W.run = c.take<RunCounters>(1); W.qc = c.take<QueueCounters>(1);
-    W.tile_delta = c.take<double>(n_tiles);
+    W.tile_delta = c.take<double>(n_tiles); W.tile_delta_next = c.take<double>(n_tiles);
     W.pilot_lum = c.take<double>((size_t)n_tiles * LUMO_PILOT_N); W.pilot_cost = c.take<uint32_t>((size_t)n_tiles * LUMO_PILOT_N);
     (void)film_px;
 }
@@ -484,13 +495,12 @@ static int32_t render_impl(lumo_scene* sc, const lumo_render_params* rp, double*
     if (rp->rr_delta <= 0.0 && rp->integrator != LUMO_DIRECT_LIGHT) {
         // Per-tile Russian-roulette threshold (the role of task.rs:42-53): two pilot rounds, the second
         // using the first round's estimate.  Pilot paths never touch the film or the reported counters.
-        DevBuf nd; CU(nd.alloc((size_t)n_tiles * 8));
         for (uint32_t round = 0; round < 2; round++) {
             P.mode = WM_PILOT; P.pilot_round = round; P.total_work = (unsigned long long)n_tiles * LUMO_PILOT_N;
             int32_t rc = bdpt ? run_bdpt(sc, W, P, bs, iterations) : run_wave(sc, W, P, iterations); if (rc != LUMO_OK) return rc;
-            k_pilot_reduce<<<(n_tiles + 127) / 128, 128, 0, st>>>(W, n_tiles, nd.as<double>());
+            k_pilot_reduce<<<(n_tiles + 127) / 128, 128, 0, st>>>(W, n_tiles, W.tile_delta_next);
             ctx->launches++;
-            CU(cudaMemcpyAsync(W.tile_delta, nd.p, (size_t)n_tiles * 8, cudaMemcpyDeviceToDevice, st));
+            CU(cudaMemcpyAsync(W.tile_delta, W.tile_delta_next, (size_t)n_tiles * 8, cudaMemcpyDeviceToDevice, st));
         }
         CU(cudaStreamSynchronize(st));
         CU(cudaMemsetAsync(W.run, 0, sizeof(RunCounters), st));
@@ -517,11 +527,16 @@ extern "C" int32_t lumo_gpu_render(lumo_scene* sc, const lumo_render_params* rp,
     lumo_ctx* ctx = sc->ctx;
     CU(cudaSetDevice(ctx->device));
     const size_t film_px = (size_t)sc->S.P.camera.res_x * sc->S.P.camera.res_y;
-    DevBuf px, sp; CU(px.alloc(film_px * 32)); CU(sp.alloc(film_px * 24));
-    int32_t rc = render_impl(sc, rp, px.as<double>(), sp.as<double>(), out->counters, out->tile_deltas, &out->device_ms);
+    // no allocation on the steady-state path: cudaMalloc / cudaFree were measured to stall a call by up to 0.3 s now and then
+    if (film_px * 56 > ctx->film_bytes) {
+        if (ctx->film_mem) { cudaFree(ctx->film_mem); ctx->film_mem = nullptr; ctx->film_bytes = 0; }
+        CU(cudaMalloc(&ctx->film_mem, film_px * 56)); ctx->film_bytes = film_px * 56;
+    }
+    double* px = (double*)ctx->film_mem; double* sp = px + film_px * 4;
+    int32_t rc = render_impl(sc, rp, px, sp, out->counters, out->tile_deltas, &out->device_ms);
     if (rc != LUMO_OK) return rc;
-    CU(cudaMemcpyAsync(out->pixels, px.p, film_px * 32, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(out->splats, sp.p, film_px * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(out->pixels, px, film_px * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(out->splats, sp, film_px * 24, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return LUMO_OK;
 }

@@ -64,7 +64,7 @@ struct Wave {
     double *sox, *soy, *soz, *sdx, *sdy, *sdz, *stmax, *sc; uint32_t* sslot;
     IterCounters* it; RunCounters* run; QueueCounters* qc;
     // film + RR thresholds
-    double *pixels, *splats, *tile_delta;
+    double *pixels, *splats, *tile_delta, *tile_delta_next;
     double* pilot_lum; uint32_t* pilot_cost;
 };
 
