@@ -105,3 +105,55 @@ def test_flat_traversal_is_bit_exact_too():
         assert np.array_equal(O.trace_any(o, d, tm), G.trace_any(o, d, tm)), kind
         assert np.array_equal(_bits(O.trace_first_found(o, d)), _bits(G.trace_first_found(o, d))), kind
     G.close(); ctx.close(); O.close()
+
+
+def test_special_rays_bit_exact(gpu_ctx):
+    """Edge cases of the arithmetic: zero direction components (inf reciprocals, 0*inf = NaN dropped by
+    min/max), negative zero, origins exactly on box planes / kd split planes / triangle planes, finite t_max on both sides of
+    the hit, directions that are not normalised, NaN and infinite inputs.  GPU and oracle must agree bit for bit — including
+    on what they return for garbage."""
+    from lumo_b200 import native
+    for name in ("cornell", "bunny", "conference"):
+        prog, blob, _ = small_scene(name)
+        O = oracle_lib.OracleScene(prog); G = native.GpuScene(gpu_ctx, blob)
+        B = G.blob
+        rs = np.random.RandomState(3)
+        lo, hi = np.array(B.params["bounds_lo"]), np.array(B.params["bounds_hi"])
+        n = 4000
+        o = lo + rs.rand(n, 3) * (hi - lo)
+        d = rs.randn(n, 3); d /= np.linalg.norm(d, axis=1, keepdims=True)
+        # axis-parallel and plane-parallel directions, with both signs of zero
+        d[0:600, 0] = 0.0; d[200:800, 1] = -0.0; d[400:1000, 2] = 0.0
+        d[:1000] /= np.maximum(np.linalg.norm(d[:1000], axis=1, keepdims=True), 1e-300)
+        # origins on kd split planes and on triangle vertices of the first tree
+        T = B.kd_trees[0]
+        nodes = B.kd_nodes[int(T["root"]):int(T["root"]) + 64]
+        inner = nodes[(nodes["b"] & 0x80000000) == 0]
+        for k, nd in enumerate(inner[:200]):
+            o[1000 + k, int(nd["b"])] = float(nd["point"])
+        tv = B.tri_verts[int(T["tri_base"]):int(T["tri_base"]) + 200]
+        o[1200:1200 + len(tv)] = tv["a"]
+        # origins on the scene bounds
+        o[1500:1700, 0] = lo[0]; o[1700:1900, 1] = hi[1]
+        # un-normalised directions (instance-local rays are like this inside the traversal; the API takes them as given)
+        d[2000:2400] *= rs.rand(400, 1) * 10 + 0.1
+        # garbage
+        d[2400:2420] = 0.0; d[2420:2440, 0] = np.nan; o[2440:2460, 1] = np.inf; d[2460:2480] = np.inf; o[2480:2500] = 1e300
+        for oo, dd in ((o, d),):
+            with np.errstate(all="ignore"):
+                eo, et, ett, eb = O.trace_closest(oo, dd)
+                go, gt, gtt, gb = G.trace_closest(oo, dd)
+            assert np.array_equal(eo, go), (name, np.nonzero(eo != go)[0][:10])
+            assert np.array_equal(et, gt), name
+            assert np.array_equal(_bits(ett), _bits(gtt)) and np.array_equal(_bits(eb), _bits(gb)), name
+            ef = O.trace_first_found(oo, dd); gf = G.trace_first_found(oo, dd)
+            assert np.array_equal(_bits(ef), _bits(gf)), name
+            for scale in (0.25, 1.0, 1.0 + 1e-15, 4.0):
+                tm = np.where(np.isfinite(ett), ett * scale, 1.0)
+                assert np.array_equal(O.trace_any(oo, dd, tm), G.trace_any(oo, dd, tm)), (name, scale)
+        # finite t_max on the closest-hit entry point (the reference always passes +inf; the C ABI allows it)
+        tm = np.where(np.isfinite(ett), ett * rs.choice([0.5, 1.0, 2.0], size=n), 3.0)
+        go2, gt2, gtt2, _ = G.trace_closest(o, d, t_max=tm)
+        keep = np.isfinite(ett) & (tm >= ett * 1.5)
+        assert np.array_equal(go2[keep], go[keep]) and np.array_equal(_bits(gtt2[keep]), _bits(gtt[keep]))
+        G.close(); O.close()
