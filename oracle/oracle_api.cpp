@@ -584,6 +584,66 @@ void oracle_export_alias(void* h, double* prob, int64_t* alias, double* pdf) {
     for (size_t i = 0; i < L->scene.lights.alias_table.size(); i++) { prob[i] = L->scene.lights.alias_table[i].first; alias[i] = (int64_t)L->scene.lights.alias_table[i].second; pdf[i] = L->scene.lights.alias_pdf[i]; }
 }
 
+// ---- BDPT MIS property (mis_tests.rs:99-352): for complete paths built from a light subpath closed at the camera, the
+// MIS weights of all admissible (s,t) splits must sum to one.  out[i] = that sum for path i.
+static std::vector<Vertex> reverse_path(std::vector<Vertex> pth) {                                   // mis_tests.rs:318-352
+    std::reverse(pth.begin(), pth.end());
+    for (size_t i = pth.size(); i-- > 1;) pth[i].wo = -pth[i - 1].wo;
+    pth[0].wo = Vec3();
+    for (auto& v : pth) std::swap(v.pdf_fwd, v.pdf_bck);
+    return pth;
+}
+uint64_t oracle_mis_sums_from_light(void* h, uint64_t seed, uint64_t n_paths, double* out) {
+    auto* L = (Loaded*)h;
+    const Scene& sc = L->scene; const Camera& cam = L->camera;
+    Rng rng = Rng::xorshift(seed);
+    uint64_t done = 0, attempts = 0;
+    while (done < n_paths && attempts < 200 * n_paths + 1000) {
+        Lambda lam = Lambda::sample(rng.gen_float());
+        const Lambda l = lam;
+        Ray r = cam.generate_ray(Vec2(0, 0), rng.gen_vec2());                                      // mis_tests.rs:262-316
+        Vec3 xc = r.origin;
+        std::vector<Vertex> pth;
+        bool ok = false;
+        for (int tries = 0; tries < 200 && !ok; tries++, attempts++) {
+            pth = light_path(sc, rng, 0.0, lam);
+            if (pth.size() <= 2) continue;
+            const Vertex& ls = pth.back();
+            if (ls.is_delta(lam)) continue;
+            const Vertex& ls_m = pth[pth.size() - 2];
+            Vec3 xo = ls_m.h.p, wo = ls.wo, ngo = ls_m.h.ng, ngi = ls.h.ng, xi = ls.h.p;
+            Float t2 = xi.distance_squared(xc);
+            Vec3 wi = (xi - xc).normalize();
+            Ray ri = Ray::make(xc, wi);
+            Hit hh;
+            if (sc.hit(ri, hh) && hh.t * hh.t < t2 - EPSILON * EPSILON) continue;
+            pth.push_back(Vertex::camera(xc, 0.0, WHITE));
+            size_t len = pth.size();
+            pth[len - 1].wo = wi;
+            Float pdf_sa = cam.pdf_wi(ri);
+            Vec3 ngi2 = !pth[len - 2].is_surface() ? wi : ngi;
+            pth[len - 2].pdf_bck = sa_to_area(pdf_sa, xc, xi, wi, ngi2);
+            if (!pth[len - 3].is_delta(lam)) {
+                Float p2 = pth[len - 2].bsdf_pdf(-wi, lam, true);
+                Vec3 ngo2 = !pth[len - 3].is_surface() ? wo : ngo;
+                pth[len - 3].pdf_bck = sa_to_area(p2, xo, xi, wo, ngo2);
+            }
+            ok = true;
+        }
+        if (!ok) continue;
+        std::vector<Vertex> lp = pth, cp = reverse_path(pth);
+        Float sumw = 0.0;
+        for (size_t s = 0; s < lp.size(); s++) {                                                    // mis_tests.rs:119-152
+            size_t t = lp.size() - s;
+            if (t == 1 && s < 2) continue;
+            if (lp[s].is_delta(l) || (s > 0 && lp[s - 1].is_delta(l))) continue;
+            sumw += mis_weight(sc, cam, l, lp.data(), s, cp.data(), t);
+        }
+        out[done++] = sumw;
+    }
+    return done;
+}
+
 // ---- unit hooks used by the property tests ------------------------------------------------------
 double oracle_lambda_sample_one(double v) { return Lambda::sample_one(v); }
 void oracle_xorshift(uint64_t seed, uint64_t n, uint64_t* out) { Rng r = Rng::xorshift(seed); for (uint64_t i = 0; i < n; i++) out[i] = r.gen_u64(); }

@@ -143,3 +143,32 @@ def test_generators():
     # hero wavelengths (wavelength.rs:35-51): stratified, inside [360, 830]
     lams = [L.oracle_lambda_sample_one(C.c_double(u)) for u in np.linspace(0, 1, 101)]
     assert min(lams) >= 360.0 - 1e-6 and max(lams) <= 830.0 + 1e-6 and all(a <= b for a, b in zip(lams, lams[1:]))
+
+
+def _mis_sums(scene, cam, n=1500, seed=11):
+    O = oracle_lib.OracleScene(scene._program(cam))
+    out = np.zeros(n)
+    O.L.oracle_mis_sums_from_light.restype = C.c_uint64
+    k = int(O.L.oracle_mis_sums_from_light(O.h, C.c_uint64(seed), C.c_uint64(n), out.ctypes.data_as(C.POINTER(C.c_double))))
+    return out[:k]
+
+
+@pytest.mark.parametrize("case", ["diffuse", "specular_delta", "specular_rough", "big_scale"])
+def test_bdpt_mis_weights_sum_to_one(case):
+    """mis_tests.rs:22-157: light subpaths closed at the camera; the MIS weights (mis.rs:103-239) of all admissible (s,t)
+    splits sum to 1 +- 0.01 — in the diffuse box, with delta and rough spheres, and at Cornell scale."""
+    from lumo_b200 import Camera
+    rough = lambda: Spectrum(0.0, 0.0, 1e9, 1.0)
+    if case == "big_scale":
+        s = Scene.cornell_box(); cam = Camera.cornell_box()
+    else:
+        s = Scene.empty_box(rough(), Material.diffuse(Spectrum(0.0, 0.0, 0.0, 0.9)), Material.lambertian(Spectrum(0.0, 0.0, 0.0, 0.6)))
+        cam = CameraBuilder.new().build()
+        if case == "specular_delta":
+            s.add(Sphere(0.25, Material.mirror()).translate(-0.45, -0.5, -1.5)); s.add(Sphere(0.25, Material.glass()).translate(0.45, -0.5, -1.3))
+        if case == "specular_rough":
+            s.add(Sphere(0.25, Material.metal(rough(), 0.5, 1.5, 1.5)).translate(-0.45, -0.5, -1.5))
+            s.add(Sphere(0.25, Material.transparent(rough(), 0.5, 1.5)).translate(0.45, -0.5, -1.3))
+    sums = _mis_sums(s, cam)
+    assert len(sums) >= 500
+    assert np.abs(sums - 1.0).max() < 0.01, (np.abs(sums - 1.0).max(), int((np.abs(sums - 1.0) >= 0.01).sum()), len(sums))
