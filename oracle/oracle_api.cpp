@@ -644,6 +644,36 @@ uint64_t oracle_mis_sums_from_light(void* h, uint64_t seed, uint64_t n_paths, do
     return done;
 }
 
+// ---- chi^2 material for BxDF sampling vs pdf (bxdf/chi2_tests.rs:94-236): histogram of sampled directions and the pdf
+// integrated over the same (theta, phi) bins, both in the local shading frame of a z-up surface.
+void oracle_bsdf_chi2_tables(void* h, int mat, const double* wo3, double lambda_u, uint64_t seed, uint64_t n_samples,
+                             int theta_bins, int phi_bins, int sub, double* observed, double* expected) {
+    auto* L = (Loaded*)h;
+    const Material* m = L->scene.materials[mat].get();
+    Vec3 wo(wo3[0], wo3[1], wo3[2]);
+    Hit hh; hh.ng = Vec3(0, 0, 1); hh.ns = Vec3(0, 0, 1); hh.backface = false; hh.material = m;
+    Rng rng = Rng::xorshift(seed);
+    Lambda lam = Lambda::sample(lambda_u);
+    for (int i = 0; i < theta_bins * phi_bins; i++) { observed[i] = 0.0; expected[i] = 0.0; }
+    for (uint64_t i = 0; i < n_samples; i++) {                                                    // chi2_tests.rs:172-200
+        Vec3 wi;
+        Float ru = rng.gen_float(); Vec2 rs = rng.gen_vec2();
+        if (!m->bsdf_sample(wo, hh, lam, ru, rs, wi)) continue;
+        Float theta = std::acos(clampf(wi.z, -1.0, 1.0)), phi = std::atan2(wi.y, wi.x); if (phi < 0.0) phi += 2.0 * PI;
+        int tb = std::min((int)(theta / PI * theta_bins), theta_bins - 1), pb = std::min((int)(phi / (2.0 * PI) * phi_bins), phi_bins - 1);
+        observed[pb + tb * phi_bins] += 1.0;
+    }
+    for (int tb = 0; tb < theta_bins; tb++) for (int pb = 0; pb < phi_bins; pb++) {               // chi2_tests.rs:203-236 (midpoint rule instead of Simpson)
+        Float acc = 0.0;
+        for (int a = 0; a < sub; a++) for (int b = 0; b < sub; b++) {
+            Float theta = (tb + (a + 0.5) / sub) * PI / theta_bins, phi = (pb + (b + 0.5) / sub) * 2.0 * PI / phi_bins;
+            Vec3 wi(std::sin(theta) * std::cos(phi), std::sin(theta) * std::sin(phi), std::cos(theta));
+            acc += m->bsdf_pdf(wo, wi, hh, lam, false) * std::sin(theta);
+        }
+        expected[pb + tb * phi_bins] = acc * (PI / theta_bins / sub) * (2.0 * PI / phi_bins / sub) * (Float)n_samples;
+    }
+}
+
 // ---- unit hooks used by the property tests ------------------------------------------------------
 double oracle_lambda_sample_one(double v) { return Lambda::sample_one(v); }
 void oracle_xorshift(uint64_t seed, uint64_t n, uint64_t* out) { Rng r = Rng::xorshift(seed); for (uint64_t i = 0; i < n; i++) out[i] = r.gen_u64(); }

@@ -172,3 +172,41 @@ def test_bdpt_mis_weights_sum_to_one(case):
     sums = _mis_sums(s, cam)
     assert len(sums) >= 500
     assert np.abs(sums - 1.0).max() < 0.01, (np.abs(sums - 1.0).max(), int((np.abs(sums - 1.0) >= 0.01).sum()), len(sums))
+
+
+CHI2 = [("lambertian", lambda: Material.lambertian(WHITE))] + \
+       [("diffuse%02d" % int(r * 100), (lambda r=r: Material.microfacet(r, 1.5, 0.0, False, False, WHITE, WHITE, Spectrum()))) for r in (0.75, 0.5, 0.25, 0.1)] + \
+       [("conductor%02d" % int(r * 100), (lambda r=r: Material.metal(WHITE, r, 1.5, 0.0))) for r in (0.75, 0.5, 0.25, 0.1)] + \
+       [("dielectric%02d_eta%d" % (int(r * 100), int(e * 10)), (lambda r=r, e=e: Material.microfacet(r, e + 1e-9, 0.0, True, True, Spectrum(), WHITE, WHITE)))
+        for r in (0.75, 0.5, 0.25) for e in (1.5, 2.5)]
+
+
+@pytest.mark.parametrize("name,mk", CHI2)
+def test_bxdf_sampling_matches_pdf_chi2(name, mk):
+    """bxdf/chi2_tests.rs:9-170: chi^2 goodness of fit of BxDF::sample against the numerically integrated BxDF::pdf on a
+    10 x 20 (theta, phi) grid, 200 000 samples, bins with expectation < 5 pooled; significance 0.01 Sidak-corrected over
+    the runs (here 4 outgoing directions instead of 20)."""
+    from scipy.stats import chi2 as chi2_dist
+    s = Scene(); s.add(Rectangle((-1, 0, -1), (1, 0, -1), (1, 0, 1), mk()))
+    s.add_light(Rectangle((100, 100, 100), (100, 100, 101), (101, 100, 101), Material.light(WHITE)))
+    O = oracle_lib.OracleScene(s._program(CAM))
+    TB, PB, N, RUNS = 10, 20, 200000, 4
+    rs = np.random.RandomState(5)
+    obs = np.zeros(TB * PB); exp = np.zeros(TB * PB)
+    for run in range(RUNS):
+        z = 0.15 + 0.8 * rs.rand(); ph = 2 * np.pi * rs.rand(); r = math.sqrt(1 - z * z)
+        wo = (C.c_double * 3)(r * math.cos(ph), r * math.sin(ph), z)
+        O.L.oracle_bsdf_chi2_tables(O.h, C.c_int(0), wo, C.c_double(rs.rand()), C.c_uint64(100 + run), C.c_uint64(N), C.c_int(TB), C.c_int(PB), C.c_int(96),
+                                    obs.ctypes.data_as(C.POINTER(C.c_double)), exp.ctypes.data_as(C.POINTER(C.c_double)))
+        assert obs.sum() > 0.5 * N
+        e = exp * (obs.sum() / max(exp.sum(), 1e-300))          # failed samples (reflect below the horizon) are not in the histogram: compare shapes
+        assert abs(exp.sum() / N - obs.sum() / N) < 0.08, (exp.sum() / N, obs.sum() / N)     # the pdf integrates to the fraction of successful samples
+        # (midpoint quadrature returns 0 for bins that the refraction cone only clips; the reference's Simpson rule sees their edges)
+        assert obs[e == 0].sum() <= N * 1e-3
+        big = e >= 5.0
+        stat = float((((obs[big] - e[big]) ** 2) / e[big]).sum()); dof = int(big.sum())
+        if (~big).any() and e[~big].sum() > 0:
+            stat += (obs[~big].sum() - e[~big].sum()) ** 2 / e[~big].sum(); dof += 1
+        pval = 1.0 - chi2_dist.cdf(stat, dof - 1)
+        alpha = 1.0 - (1.0 - 0.01) ** (1.0 / RUNS)
+        assert pval > alpha, (name, run, stat, dof, pval)
