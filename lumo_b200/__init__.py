@@ -4,3 +4,4 @@ from .api import (Scene, Camera, CameraBuilder, CameraType, Material, Texture, R
                   Instance, LooseTriangles, Integrator, Renderer, SamplerType, ToneMap, PixelFilter, ColorSpace, illuminants)
 from .spectrum import Spectrum
 from .film import Film
+from . import parser

@@ -318,7 +318,11 @@ class Scene:                                         # src/tracer/scene.rs:18-11
         n = 0
         for l in self.lights:
             base = l.obj if isinstance(l, Instance) else l
-            n += len(base.mesh.faces) if isinstance(base, LooseTriangles) else 1
+            if isinstance(base, LooseTriangles):
+                fr = base.mesh.face_range
+                n += (fr[1] - fr[0]) if fr else len(base.mesh.faces)
+            else:
+                n += 1
         return n + (1 if self.environment_map else 0)
 
     # -- program emission --
@@ -338,8 +342,9 @@ class Scene:                                         # src/tracer/scene.rs:18-11
                 faces = src.faces
                 if len(faces) and isinstance(faces[0], Face):
                     has_n = any(f.nidx for f in faces); has_t = any(f.tidx for f in faces)
+                    pad = lambda idx, f: list(idx) if idx else [-1] * len(f.vidx)       # a face without normals / uvs: index -1 per corner
                     meshes[key] = w.mesh(src.vertices, [f.vidx for f in faces], src.normals if has_n else None, src.uvs if has_t else None,
-                                         [f.nidx for f in faces] if has_n else None, [f.tidx for f in faces] if has_t else None)
+                                         [pad(f.nidx, f) for f in faces] if has_n else None, [pad(f.tidx, f) for f in faces] if has_t else None)
                 else:
                     fn = getattr(src, "face_normals", None); ft = getattr(src, "face_uvs", None)
                     meshes[key] = w.mesh(src.vertices, faces, src.normals if fn is not None else None, src.uvs if ft is not None else None, fn, ft)

@@ -224,8 +224,9 @@ static void emit_triangles(Builder& B, const MeshIn& m, int64_t f0, int64_t f1, 
             V3 a = v3(tv.a[0], tv.a[1], tv.a[2]), bb = v3(tv.b[0], tv.b[1], tv.b[2]), cc = v3(tv.c[0], tv.c[1], tv.c[2]);
             if (length(cross(sub(bb, a), sub(cc, a))) == 0.0) continue;
             LumoTriShade ts; std::memset(&ts, 0, sizeof ts);
-            if (m.ni) { ts.flags |= 1; for (int k = 0; k < 3; k++) ts.n[k] = m.normal_base + (uint32_t)m.ni[c[k]]; }
-            if (m.ti) { ts.flags |= 2; for (int k = 0; k < 3; k++) ts.t[k] = m.uv_base + (uint32_t)m.ti[c[k]]; }
+            // a face may come without normals / uvs even if the mesh has some (Face::nidx / tidx empty, triangle_mesh.rs:4-23): index -1
+            if (m.ni && m.ni[c[0]] >= 0 && m.ni[c[1]] >= 0 && m.ni[c[2]] >= 0) { ts.flags |= 1; for (int k = 0; k < 3; k++) ts.n[k] = m.normal_base + (uint32_t)m.ni[c[k]]; }
+            if (m.ti && m.ti[c[0]] >= 0 && m.ti[c[1]] >= 0 && m.ti[c[2]] >= 0) { ts.flags |= 2; for (int k = 0; k < 3; k++) ts.t[k] = m.uv_base + (uint32_t)m.ti[c[k]]; }
             B.tri_verts.push_back(tv); B.tri_shade.push_back(ts);
         }
     }

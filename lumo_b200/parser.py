@@ -1,0 +1,175 @@
+"""`.obj` / `.mtl` ingest — host-side mirror of the reference's parser (src/parser.rs:125-265, parser/obj.rs:6-198,
+parser/mtl.rs:10-146, parser/mtl/task.rs:16-116).  Same grammar subset and the same scene structure: one shared
+`TriangleMesh`; every `g` / `o` / `usemtl` group becomes its own kd-tree (obj.rs:49-66,92-107); groups whose
+material emits become loose triangle lights, one light per triangle (obj.rs:97-104).
+
+Not mirrored (host I/O outside the hot path): downloading (no network), zip extraction, PNG / HDR decode.
+Texture maps (`map_Kd`, `map_Ks`, `map_Ke`, `map_Bump`) are not on the device yet: they are ignored with a warning and
+the material keeps its constant colours; an environment map is given as a constant `Spectrum`."""
+import io
+import math
+import warnings
+import numpy as np
+from .api import Scene, Material, TriangleMesh, Mesh, Face, LooseTriangles
+from .spectrum import Spectrum
+
+
+class ObjError(ValueError):
+    pass
+
+
+def _lines(src):
+    if isinstance(src, (bytes, bytearray)):
+        src = src.decode("utf-8", "replace")
+    if isinstance(src, str) and "\n" not in src and src.endswith((".obj", ".mtl")):
+        src = open(src).read()
+    for line in io.StringIO(src):
+        line = line.strip()
+        if not line or line.startswith("#"):
+            continue
+        yield line.split()
+
+
+def _floats(tokens, n):
+    try:
+        return [float(t) for t in tokens[1:1 + n]]
+    except ValueError:
+        raise ObjError("Could not parse double in file")
+    
+
+def _idx(tok, length):                                   # parser.rs:52-67: 1-based, negative = relative to the end
+    try:
+        i = int(tok)
+    except ValueError:
+        raise ObjError("Could not parse index in file")
+    return i - 1 if i > 0 else length + i
+
+
+def _parse_face(tokens, nv, nn, nt):                     # obj.rs:150-198: fan triangulation
+    v, n, t = [], [], []
+    for tok in tokens[1:]:
+        a = tok.split("/")
+        v.append(_idx(a[0], nv))
+        if len(a) > 1 and a[1] != "":
+            t.append(_idx(a[1], nt))
+        if len(a) > 2:
+            n.append(_idx(a[2], nn))
+    out = []
+    for i in range(1, len(v) - 1):
+        c = (0, i, i + 1)
+        out.append(Face([v[k] for k in c], [n[k] for k in c] if n else [], [t[k] for k in c] if t else []))
+    return out
+
+
+def _parse_common(tokens, V, N, T, F):                   # obj.rs:113-147
+    k = tokens[0]
+    if k == "v":
+        V.append(_floats(tokens, 3))
+    elif k == "vn":
+        x, y, z = _floats(tokens, 3)
+        l2 = x * x + y * y + z * z
+        if l2 == 0.0:
+            N.append([0.0, 0.0, 1.0])
+        else:
+            l = math.sqrt(max(l2, 0.0)); N.append([x / l, y / l, z / l])
+    elif k == "vt":
+        T.append(_floats(tokens, 2))
+    elif k == "f":
+        F.extend(_parse_face(tokens, len(V), len(N), len(T)))
+
+
+def mesh_from_obj(src, material):
+    """obj::load_file (obj.rs:6-24): the whole file as one mesh with one material."""
+    V, N, T, F = [], [], [], []
+    for tokens in _lines(src):
+        _parse_common(tokens, V, N, T, F)
+    return TriangleMesh.new(np.asarray(V, np.float64).reshape(-1, 3), F, np.asarray(N, np.float64).reshape(-1, 3), np.asarray(T, np.float64).reshape(-1, 2), material)
+
+
+def load_mtl(src, materials=None, indices=None):
+    """mtl::load_file + MtlTaskExecutor::exec + MtlConfig::build_material (mtl.rs:52-146, mtl/task.rs:16-116).
+    Returns (materials, name -> index); the first definition of a name wins (mtl.rs:134)."""
+    materials = [] if materials is None else materials
+    indices = {} if indices is None else indices
+    blocks, block = [], []
+    for tokens in _lines(src):
+        if tokens[0] == "newmtl" and block:
+            blocks.append(block); block = []
+        block.append(tokens)
+    if block:
+        blocks.append(block)
+    for block in blocks:
+        cfg = dict(Kd=Spectrum.BLACK(), Ks=Spectrum.BLACK(), Ke=Spectrum.BLACK(), Tf=Spectrum.BLACK(), eta=1.5, k=0.0, roughness=1.0, fresnel=False, transparent=False)
+        name = ""
+        for tokens in block:
+            k = tokens[0]
+            if k == "newmtl": name = tokens[1]
+            elif k in ("Kd", "Ks", "Ke", "Tf"): cfg[k] = Spectrum.from_rgb(*_floats(tokens, 3))
+            elif k == "Ni": cfg["eta"] = _floats(tokens, 1)[0]
+            elif k == "Ns": cfg["roughness"] = 1.0 - math.sqrt(min(_floats(tokens, 1)[0], 900.0)) / 30.0      # "blender uses this mapping"
+            elif k == "illum":
+                il = int(_floats(tokens, 1)[0])
+                if il == 5: cfg["fresnel"] = True
+                elif il == 6: cfg["transparent"] = True
+                elif il == 7: cfg["fresnel"] = cfg["transparent"] = True
+            elif k in ("map_Kd", "map_Ks", "map_Ke", "map_Bump"):
+                warnings.warn("%s of material %r ignored: image textures are not on the device yet" % (k, name))
+        if name in indices:
+            continue
+        if not cfg["Ke"].is_black():
+            m = Material.light(cfg["Ke"])
+        else:
+            m = Material.microfacet(cfg["roughness"], cfg["eta"], cfg["k"], cfg["transparent"], cfg["fresnel"], cfg["Kd"], cfg["Ks"], cfg["Tf"])
+        materials.append(m); indices[name] = len(materials) - 1
+    return materials, indices
+
+
+def scene_from_obj(obj_src, mtl_src=None, env_map=None, mtl_resolver=None):
+    """parser::scene_from_file + obj::load_scene (parser.rs:206-265, obj.rs:27-110).  `mtl_src`: the text of the material
+    library named by the caller (the `mtllib` argument of the reference); `mtl_resolver(name) -> text` serves `mtllib`
+    lines inside the .obj.  `env_map`: (Spectrum, scale) or None."""
+    obj_lines = list(_lines(obj_src))
+    materials, indices = [], {}
+    if mtl_src is not None:
+        load_mtl(mtl_src, materials, indices)
+    for tokens in obj_lines:
+        if tokens[0] == "mtllib":
+            if mtl_resolver is None:
+                raise ObjError("Could not find %s in the archive" % tokens[1])
+            load_mtl(mtl_resolver(tokens[1]), materials, indices)
+    V, N, T = [], [], []
+    faces, groups, midx = [], [], None
+    for tokens in obj_lines:
+        k = tokens[0]
+        if k in ("g", "o"):
+            if faces:
+                groups.append((faces, midx)); faces = []; midx = None
+        elif k == "usemtl":
+            if faces:
+                groups.append((faces, midx)); faces = []
+            if tokens[1] not in indices:
+                raise ObjError("Could not find material %s" % tokens[1])
+            midx = indices[tokens[1]]
+        else:
+            _parse_common(tokens, V, N, T, faces)
+    groups.append((faces, midx))
+    base = Mesh(np.asarray(V, np.float64).reshape(-1, 3), [f for g, _ in groups for f in g], np.asarray(N, np.float64).reshape(-1, 3),
+                np.asarray(T, np.float64).reshape(-1, 2), None)
+    scene = Scene()
+    f0 = 0
+    for g, mi in groups:
+        f1 = f0 + len(g)
+        if mi is None:
+            if g:
+                raise ObjError("faces without a material (no usemtl before them)")     # the reference indexes materials[usize::MAX] and panics
+            continue
+        if g:
+            chunk = Mesh(base.vertices, base.faces, base.normals, base.uvs, materials[mi], face_range=(f0, f1), shared=base)
+            if materials[mi].is_light():
+                scene.add_light(LooseTriangles(chunk, materials[mi]))
+            else:
+                scene.add(chunk)
+        f0 = f1
+    if env_map is not None:
+        scene.set_environment_map(env_map[0], env_map[1])
+    return scene

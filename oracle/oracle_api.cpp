@@ -59,8 +59,8 @@ static std::vector<Triangle> triangles_from_faces(const TriangleMesh* tm, const 
             Triangle t; t.mesh = tm; t.mat = mat;
             t.v[0] = (uint32_t)ms.vidx[ia]; t.v[1] = (uint32_t)ms.vidx[ib]; t.v[2] = (uint32_t)ms.vidx[ic];
             if (degenerate_triangle(t.a(), t.b(), t.c())) continue;
-            if (!ms.nidx.empty()) { t.has_n = true; t.n[0] = (uint32_t)ms.nidx[ia]; t.n[1] = (uint32_t)ms.nidx[ib]; t.n[2] = (uint32_t)ms.nidx[ic]; }
-            if (!ms.tidx.empty()) { t.has_t = true; t.tx[0] = (uint32_t)ms.tidx[ia]; t.tx[1] = (uint32_t)ms.tidx[ib]; t.tx[2] = (uint32_t)ms.tidx[ic]; }
+            if (!ms.nidx.empty() && ms.nidx[ia] >= 0 && ms.nidx[ib] >= 0 && ms.nidx[ic] >= 0) { t.has_n = true; t.n[0] = (uint32_t)ms.nidx[ia]; t.n[1] = (uint32_t)ms.nidx[ib]; t.n[2] = (uint32_t)ms.nidx[ic]; }
+            if (!ms.tidx.empty() && ms.tidx[ia] >= 0 && ms.tidx[ib] >= 0 && ms.tidx[ic] >= 0) { t.has_t = true; t.tx[0] = (uint32_t)ms.tidx[ia]; t.tx[1] = (uint32_t)ms.tidx[ib]; t.tx[2] = (uint32_t)ms.tidx[ic]; }
             tris.push_back(t);
         }
     }

@@ -1,0 +1,143 @@
+"""`.obj` / `.mtl` ingest (lumo_b200/parser.py) against the reference's parser semantics (src/parser/obj.rs, parser/mtl.rs,
+parser/mtl/task.rs): grouping into kd-trees, emissive groups as loose triangle lights, index conventions, material
+mapping.  The parsed scene goes through the same scene program as API-built scenes, so oracle and device see it alike."""
+import math
+import numpy as np
+import pytest
+import oracle_lib
+from lumo_b200 import parser, native, Material, Spectrum, CameraBuilder, program as P
+
+OBJ = """
+# a room: floor quad (fan-triangulated), a pyramid with normals and uvs, a lamp
+mtllib room.mtl
+v -2 0 -2
+v  2 0 -2
+v  2 0  2
+v -2 0  2
+v -0.5 0 -0.5
+v  0.5 0 -0.5
+v  0.5 0  0.5
+v -0.5 0  0.5
+v  0 1 0
+v -0.3 2.5 -0.3
+v  0.3 2.5 -0.3
+v  0.3 2.5  0.3
+v -0.3 2.5  0.3
+vn 0 1 0
+vn 0 0 0
+vt 0 0
+vt 1 0
+vt 1 1
+o floor
+usemtl grey
+f 1 2 3 4
+o pyramid
+usemtl gold
+f 5//1 6//1 9//1
+f 6/1/1 7/2/1 9/3/1
+usemtl glass
+f -7 -6 -5
+f 8 5 9
+g lamp
+usemtl lamp
+f 10 11 12 13
+"""
+MTL = """
+newmtl grey
+Kd 0.5 0.5 0.5
+Ns 0
+newmtl gold
+Kd 0 0 0
+Ks 1.0 0.8 0.3
+Ns 400
+Ni 0.4
+illum 5
+newmtl glass
+Tf 1 1 1
+Ks 1 1 1
+Ns 900
+Ni 1.45
+illum 7
+newmtl lamp
+Ke 10 10 10
+newmtl grey
+Kd 1 0 0
+"""
+
+
+def _scene():
+    return parser.scene_from_obj(OBJ, mtl_resolver=lambda name: MTL if name == "room.mtl" else None)
+
+
+def test_scene_structure():
+    s = _scene()
+    # groups: floor | gold (2 faces) | glass (2 faces) | lamp -> 3 kd-tree objects + one light group (obj.rs:49-66)
+    assert len(s.objects) == 3 and len(s.lights) == 1
+    assert s.num_lights() == 2                                    # the lamp quad is two triangles = two lights (obj.rs:97-104)
+    kinds = [o.material.kind for o in s.objects]
+    assert kinds == [P.M_MFDIFFUSE, P.M_MFCONDUCTOR, P.M_MFDIELECTRIC]
+    grey, gold, glass = (o.material.kw for o in s.objects)
+    assert grey["roughness"] == 1.0                               # Ns 0 -> 1 - sqrt(0)/30
+    assert abs(gold["roughness"] - (1.0 - math.sqrt(400.0) / 30.0)) < 1e-15 and gold["eta"] == 0.4
+    assert glass["roughness"] == 0.0 and glass["eta"] == 1.45     # Ns 900 -> 0; transparent + fresnel (illum 7)
+    assert np.allclose(grey["kd"], Spectrum.from_rgb(0.5, 0.5, 0.5).as_tuple())      # the first `newmtl grey` wins (mtl.rs:134)
+    base = s.objects[0].shared
+    assert len(base.vertices) == 13 and len(base.faces) == 2 + 2 + 2 + 2
+    assert np.allclose(base.normals[1], [0, 0, 1])                # degenerate normal -> +Z (obj.rs:127-133)
+    f = base.faces
+    assert f[2].vidx == [4, 5, 8] and f[2].nidx == [0, 0, 0] and f[2].tidx == []      # "5//1"
+    assert f[3].tidx == [0, 1, 2]
+    assert f[4].vidx == [6, 7, 8]                                 # negative indices count from the end (parser.rs:60-64)
+
+
+def test_blob_and_oracle_agree_on_parsed_scene():
+    s = _scene()
+    cam = CameraBuilder.new().origin(0.0, 1.5, 4.0).towards(0.0, 0.8, 0.0).resolution((32, 24)).build()
+    prog = s._program(cam)
+    B = native.Blob(native.build_blob(prog))
+    assert int(B.params["n_objects"]) == 3 and int(B.params["n_lights"]) == 2 and len(B.kd_trees) == 3
+    assert [int(t["n_tris"]) for t in B.kd_trees] == [2, 2, 2]
+    sh = B.tri_shade[int(B.kd_trees[1]["tri_base"]):int(B.kd_trees[1]["tri_base"]) + 2]
+    assert list(sh["flags"]) == [1, 3]                            # first gold face: normals only; second: normals + uvs
+    assert list(B.tri_shade[int(B.kd_trees[2]["tri_base"]):int(B.kd_trees[2]["tri_base"]) + 2]["flags"]) == [0, 0]
+    O = oracle_lib.OracleScene(prog)
+    assert (O.n_objects, O.n_lights) == (3, 2)
+    rs = np.random.RandomState(2)
+    o, d = O.camera_rays(rs.rand(2000, 2) * np.array([32, 24]))
+    obj, tri, t, _ = O.trace_closest(o, d)
+    seen = set(int(v) for v in np.unique(obj[obj != 0xFFFFFFFF]))
+    assert 0 in seen and (seen & {1, 2}) and (seen & {3, 4})     # floor, pyramid and lamp are seen
+    full = O.trace_closest_full(o, d)
+    hit_pyr = (obj == 1) & (tri == 1)
+    if hit_pyr.any():
+        assert np.all((full[hit_pyr, 10] >= 0) & (full[hit_pyr, 10] <= 1))        # interpolated uv of the textured face
+
+
+def test_mesh_from_obj_and_errors():
+    m = parser.mesh_from_obj("v 0 0 0\nv 1 0 0\nv 0 1 0\nv 1 1 0\nf 1 2 4 3\n", Material.lambertian(Spectrum.from_rgb(0.5, 0.5, 0.5)))
+    assert len(m.faces) == 2 and m.faces[1].vidx == [0, 3, 2]
+    with pytest.raises(parser.ObjError, match="Could not find material"):
+        parser.scene_from_obj("v 0 0 0\nusemtl nope\n", mtl_src="newmtl a\nKd 1 1 1\n")
+    with pytest.raises(parser.ObjError, match="Could not parse"):
+        parser.mesh_from_obj("v 0 zero 0\n", Material.Blank)
+    with pytest.raises(parser.ObjError):
+        parser.scene_from_obj("v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 3\n", mtl_src="newmtl a\nKd 1 1 1\n")      # faces before any usemtl
+
+
+@pytest.mark.gpu
+def test_parsed_scene_renders_like_the_oracle(gpu_ctx):
+    s = _scene()
+    cam = CameraBuilder.new().origin(0.0, 1.5, 4.0).towards(0.0, 0.8, 0.0).resolution((32, 24)).build()
+    prog = s._program(cam); blob = native.build_blob(prog)
+    O = oracle_lib.OracleScene(prog); G = native.GpuScene(gpu_ctx, blob)
+    rs = np.random.RandomState(4)
+    o, d = O.camera_rays(rs.rand(5000, 2) * np.array([32, 24]))
+    e = O.trace_closest(o, d); g = G.trace_closest(o, d)
+    assert np.array_equal(e[0], g[0]) and np.array_equal(e[1], g[1]) and np.array_equal(e[2].view(np.uint64), g[2].view(np.uint64))
+    epx, _, ec, _ = O.render(integrator=0, spp=4, seed=3, rng_mode=1)
+    gpx, _, gc, _, _ = G.render(integrator=0, spp=4, seed=3)
+    assert gc["camera_paths"] == ec["camera_paths"] and gc["nonfinite"] == 0
+    with np.errstate(invalid="ignore", divide="ignore"):
+        ei = np.nan_to_num(epx[..., :3] / epx[..., 3:4]); gi = np.nan_to_num(gpx[..., :3] / gpx[..., 3:4])
+    assert abs(gi.mean() - ei.mean()) <= 0.05 * abs(ei.mean()) + 1e-9
+    G.close(); O.close()
