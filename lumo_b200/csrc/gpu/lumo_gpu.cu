@@ -18,6 +18,7 @@ static int32_t fail(int32_t code, const std::string& msg) { g_err = msg; return 
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(e_ == cudaErrorMemoryAllocation ? LUMO_ERR_OOM : LUMO_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
 
 #define LUMO_ITER_LOG_CAP 16384
+#define LUMO_NM_MIN_RAYS 131072u
 #define LUMO_ITER_BATCH 4   /* wave iterations enqueued per host synchronisation */
 
 struct lumo_ctx {
@@ -33,6 +34,8 @@ struct lumo_ctx {
     unsigned long long launches = 0;
     Counters* d_visit = nullptr;   // traversal visit counters (CNT passes): [0] closest-hit kernels, [1] occlusion kernels
     int count_visits = 0;
+    void* nm_mem = nullptr; size_t nm_bytes = 0; NmRays nm_rays{}; uint32_t* d_n_batch = nullptr;   // node-major traversal state (trace_nm.cuh)
+    int nm = 0;                    // LUMO_TRACE_NM=1 selects the node-major traversal of small-BVH scenes (trace_nm.cuh): bit-exact, measured 10-25 % slower
     uint32_t* d_iter_log = nullptr; uint32_t iter_log_n = 0;   // (closest-hit rays, shadow rays) per wave iteration of the last render's main pass
     int flat = 0;                  // LUMO_TRACE_FLAT=1 selects the lane-refilled traversal kernels (trace_flat.cuh): bit-exact too, but measured 2x slower
     // per-kernel-class device time of the last render (CUDA events on the launching stream)
@@ -44,6 +47,9 @@ struct lumo_scene {
     uint8_t* d_blob = nullptr; uint64_t len = 0, cap = 0;
     DevScene S;
     LumoBlobHeader H;
+    struct NmSeg { uint32_t i0, i1; int heavy; };   // items [i0, i1]; heavy = local index of the heavy object that ends it, or -1
+    struct NmHostPlan { NmPlan P; std::vector<NmSeg> segs; std::vector<uint32_t> heavy; };
+    NmHostPlan nm_obj, nm_lig; bool nm_ok = false;   // node-major traversal plans (small object BVHs only)
     uint32_t kind_mask = 0;   // bit k set: some Standard material of LumoMatKind k exists (which shade kernels to launch)
 };
 
@@ -76,6 +82,8 @@ extern "C" int32_t lumo_gpu_ctx_create(int32_t device, lumo_ctx** out) {
     // f64 traversal keeps two explicit stacks per thread
     cudaDeviceSetLimit(cudaLimitStackSize, 4096);
     { const char* e = std::getenv("LUMO_TRACE_FLAT"); if (e) ctx->flat = std::atoi(e) != 0; }
+    { const char* e = std::getenv("LUMO_TRACE_NM"); if (e) ctx->nm = std::atoi(e) != 0; }
+    CU(cudaMalloc(&ctx->d_n_batch, 4));
     *out = ctx; return LUMO_OK;
 }
 extern "C" int32_t lumo_gpu_ctx_destroy(lumo_ctx* ctx) {
@@ -84,6 +92,8 @@ extern "C" int32_t lumo_gpu_ctx_destroy(lumo_ctx* ctx) {
     if (ctx->wave_mem) cudaFree(ctx->wave_mem);
     if (ctx->film_mem) cudaFree(ctx->film_mem);
     if (ctx->d_cursor) cudaFree(ctx->d_cursor);
+    if (ctx->nm_mem) cudaFree(ctx->nm_mem);
+    if (ctx->d_n_batch) cudaFree(ctx->d_n_batch);
     if (ctx->blob_cache) cudaFree(ctx->blob_cache);
     if (ctx->d_visit) cudaFree(ctx->d_visit);
     if (ctx->d_iter_log) cudaFree(ctx->d_iter_log);
@@ -209,6 +219,48 @@ extern "C" int32_t lumo_gpu_scene_upload(lumo_ctx* ctx, const void* blob, uint64
     S.rects = (const LumoRect*)at(LSEC_RECTS); S.spheres = (const LumoSphere*)at(LSEC_SPHERES);
     S.materials = (const LumoMaterial*)at(LSEC_MATERIALS); S.tables = (const double*)at(LSEC_TABLES); S.lights = (const LumoLight*)at(LSEC_LIGHTS);
     S.P = H.params;
+    {   // node-major plans: both BVHs in the reference's traversal order, if they are small enough
+        const uint8_t* hb = (const uint8_t*)blob;
+        const LumoTlasNode* tn = (const LumoTlasNode*)(hb + H.sec[LSEC_TLAS_NODES].offset);
+        const uint32_t* tl = (const uint32_t*)(hb + H.sec[LSEC_TLAS_LEAF].offset);
+        const LumoObject* ob = (const LumoObject*)(hb + H.sec[LSEC_OBJECTS].offset);
+        const LumoKdTree* kt = (const LumoKdTree*)(hb + H.sec[LSEC_KD_TREES].offset);
+        auto build = [&](lumo_scene::NmHostPlan& hp, uint32_t root, uint32_t n_nodes, uint32_t obj_base, uint32_t n_objects) -> bool {
+            if (n_nodes == 0 || n_nodes > LUMO_NM_MAX_NODES || n_objects > LUMO_NM_MAX_OBJECTS) return false;
+            NmPlan& P = hp.P; std::memset(&P, 0, sizeof P);
+            P.root = root; P.obj_base = obj_base; P.n_objects = n_objects;
+            for (uint32_t o = 0; o < n_objects; o++) {
+                const LumoObject& O = ob[obj_base + o];
+                if (O.kind == LOBJ_KD && kt[O.geom].n_tris > LUMO_NM_HEAVY_TRIS) { P.heavy_bits |= 1u << o; hp.heavy.push_back(o); }
+            }
+            std::vector<std::pair<uint32_t, int>> st; st.push_back({0u, -1});
+            uint32_t k = 0, n_items = 0, seg0 = 0;
+            while (!st.empty()) {
+                uint32_t node = st.back().first; int par = st.back().second; st.pop_back();
+                for (;;) {
+                    if (k >= LUMO_NM_MAX_NODES || node >= n_nodes) return false;
+                    P.node[k] = node; P.parent[k] = par;
+                    P.item[n_items++] = k;
+                    const LumoTlasNode& nd = tn[root + node];
+                    if (nd.count > 0) {                                  // leaf: its objects in list order
+                        for (uint32_t j = 0; j < nd.count; j++) {
+                            const uint32_t local = tl[nd.first + j];
+                            if (local >= n_objects || n_items >= LUMO_NM_MAX_ITEMS) return false;
+                            P.item[n_items++] = 0x80000000u | (k << 8) | local;
+                            if ((P.heavy_bits >> local) & 1u) { hp.segs.push_back({seg0, n_items - 1, (int)local}); seg0 = n_items; }
+                        }
+                        k++; break;
+                    }
+                    if (nd.right != LUMO_NONE) st.push_back({nd.right, (int)k});
+                    par = (int)k; node += 1; k++;
+                }
+            }
+            if (seg0 < n_items) hp.segs.push_back({seg0, n_items - 1, -1});
+            P.n_nodes = k; P.n_items = n_items;
+            return k == n_nodes && hp.segs.size() + 2 * hp.heavy.size() + 2 <= LUMO_NM_MAX_NODES;
+        };
+        sc->nm_ok = build(sc->nm_obj, 0, S.P.lights_root, 0, S.P.n_objects) && build(sc->nm_lig, S.P.lights_root, S.P.n_tlas_nodes - S.P.lights_root, S.P.n_objects, S.P.n_lights);
+    }
     { const LumoMaterial* mats = (const LumoMaterial*)((const uint8_t*)blob + H.sec[LSEC_MATERIALS].offset);
       for (uint64_t i = 0; i < H.sec[LSEC_MATERIALS].count; i++) if (mats[i].kind < 32) sc->kind_mask |= 1u << mats[i].kind; }
     *out = sc; return LUMO_OK;
@@ -226,11 +278,116 @@ extern "C" int32_t lumo_gpu_scene_destroy(lumo_scene* sc) {
 // ---- ray batches -----------------------------------------------------------------------------------
 static int trace_grid(const lumo_ctx* ctx) { return ctx->sm_count * 8; }
 
+struct Carver {   // carves 256-byte aligned arrays out of one allocation
+    uint8_t* base; size_t off = 0;
+    template <class T> T* take(size_t n) { T* p = base ? (T*)(base + off) : nullptr; off = (off + n * sizeof(T) + 255) & ~(size_t)255; return p; }
+};
+// ---- node-major traversal (trace_nm.cuh) ------------------------------------------------------------
+struct NmWaveSource {
+    Wave W; uint32_t cur;
+    __device__ __forceinline__ void load(unsigned long long item, Ray& r, double& t_max) const {
+        const uint32_t slot = W.active[item];
+        r.o = d3(W.ox[cur][slot], W.oy[cur][slot], W.oz[cur][slot]); r.d = d3(W.dx[cur][slot], W.dy[cur][slot], W.dz[cur][slot]);
+        t_max = LUMO_INF;
+    }
+};
+struct NmWaveHitSink {
+    Wave W; const LumoMaterial* materials; const LumoObject* objects;
+    __device__ __forceinline__ void store(unsigned long long item, const FlatResult& res) {
+        const uint32_t slot = W.active[item];
+        uint32_t klass = 0;
+        if (res.hit) {
+            W.ht[slot] = res.h.t; W.hb0[slot] = res.h.bary.x; W.hb1[slot] = res.h.bary.y; W.hb2[slot] = res.h.bary.z; W.hobj[slot] = res.h.obj; W.htri[slot] = res.h.tri;
+            const uint32_t kind = materials[objects[res.h.obj].material].kind;
+            if (kind >= LMAT_LAMBERTIAN && kind <= LMAT_MFDIELECTRIC) klass = kind;
+        } else W.hobj[slot] = LUMO_NONE;
+        W.flags[slot] = (W.flags[slot] & 0xFFu) | (klass << PF_CLASS_SHIFT);
+    }
+};
+struct NmShadowSource {
+    Wave W;
+    __device__ __forceinline__ void load(unsigned long long i, Ray& r, double& t_max) const {
+        r.o = d3(W.sox[i], W.soy[i], W.soz[i]); r.d = d3(W.sdx[i], W.sdy[i], W.sdz[i]); t_max = W.stmax[i];
+    }
+};
+struct NmShadowSink {
+    Wave W;
+    __device__ __forceinline__ void store(unsigned long long i, const FlatResult& res) {
+        if (res.hit) return;
+        const uint32_t slot = W.sslot[i]; const uint32_t N = W.n_slots, C = W.shadow_cap;
+        for (int k = 0; k < 4; k++) { const double v = W.sc[(size_t)k * C + i]; if (v != 0.0) atomicAdd(&W.radiance[(size_t)k * N + slot], v); }
+    }
+};
+static int32_t nm_reserve(lumo_ctx* ctx, uint32_t cap) {
+    auto carve = [&](Carver& c, NmRays& R) {
+        R.cap = cap;
+        R.ctx = c.take<double>(14 * (size_t)cap);
+        R.tt = c.take<double>(cap); R.bound = c.take<double>(cap); R.qtmax = c.take<double>(cap);
+        R.idx = c.take<uint32_t>(cap); R.done = c.take<uint32_t>(cap); R.have = c.take<uint32_t>(cap);
+        R.mask = c.take<unsigned long long>(cap);
+        R.ht = c.take<double>(cap); R.hb0 = c.take<double>(cap); R.hb1 = c.take<double>(cap); R.hb2 = c.take<double>(cap); R.hobj = c.take<uint32_t>(cap); R.htri = c.take<uint32_t>(cap);
+        R.queue = c.take<uint32_t>(cap); R.sorted = c.take<uint32_t>(cap);
+        R.counters = c.take<uint32_t>(NM_CNT_TOTAL);
+    };
+    if (ctx->nm_rays.cap >= cap && ctx->nm_mem) return LUMO_OK;
+    NmRays tmp{}; Carver dry{nullptr}; carve(dry, tmp);
+    if (ctx->nm_mem) { cudaFree(ctx->nm_mem); ctx->nm_mem = nullptr; ctx->nm_bytes = 0; ctx->nm_rays = NmRays{}; }
+    CU(cudaMalloc(&ctx->nm_mem, dry.off)); ctx->nm_bytes = dry.off;
+    Carver c{(uint8_t*)ctx->nm_mem}; carve(c, ctx->nm_rays);
+    return LUMO_OK;
+}
+template <bool CLOSEST>
+static void nm_bvh_pass(lumo_scene* sc, const lumo_scene::NmHostPlan& hp, const uint32_t* n_ptr, uint32_t n_cap, cudaStream_t st, unsigned long long& launches) {
+    lumo_ctx* ctx = sc->ctx; const NmRays& R = ctx->nm_rays;
+    const int g128 = (int)std::min<uint64_t>((n_cap + 127) / 128, (uint64_t)ctx->sm_count * 16);
+    const int gp = ctx->sm_count * 8;                                   // persistent, lane-refilled
+    uint32_t qslot = 0;                                                  // one queue counter + cursor per heavy launch (zeroed by setup / begin_lights)
+    for (const auto& sg : hp.segs) {
+        k_nm_segment<CLOSEST><<<g128, 128, 0, st>>>(sc->S, hp.P, R, n_ptr, n_cap, sg.i0, sg.i1, qslot);
+        launches++;
+        if (sg.heavy >= 0) {
+            k_nm_heavy<false, CLOSEST><<<gp, 128, 0, st>>>(sc->S, R, R.queue, qslot, hp.P.obj_base + (uint32_t)sg.heavy, (uint32_t)sg.heavy);
+            launches++; qslot++;
+        }
+    }
+    if (CLOSEST) {
+        if (hp.heavy.empty()) { k_nm_winners<<<g128, 128, 0, st>>>(sc->S, hp.P, R, n_ptr, n_cap, LUMO_NONE, qslot, 1u); launches++; }
+        for (size_t j = 0; j < hp.heavy.size(); j++) {
+            k_nm_winners<<<g128, 128, 0, st>>>(sc->S, hp.P, R, n_ptr, n_cap, hp.heavy[j], qslot, j == 0 ? 1u : 0u);
+            k_nm_heavy<true, true><<<gp, 128, 0, st>>>(sc->S, R, R.sorted, qslot, hp.P.obj_base + hp.heavy[j], hp.heavy[j]);
+            launches += 2; qslot++;
+        }
+    }
+}
+// Scene::hit (CLOSEST) or the occlusion half of Scene::hit_light for a batch described by Source / Sink
+template <bool CLOSEST, class Source, class Sink>
+static int32_t nm_trace(lumo_scene* sc, const uint32_t* n_ptr, uint32_t n_cap, const Source& src, const Sink& sink, unsigned long long* total, cudaStream_t st) {
+    lumo_ctx* ctx = sc->ctx;
+    int32_t rc = nm_reserve(ctx, n_cap); if (rc != LUMO_OK) return rc;
+    const NmRays& R = ctx->nm_rays;
+    const int g256 = (int)std::min<uint64_t>((n_cap + 255) / 256, (uint64_t)ctx->sm_count * 16);
+    k_nm_setup<Source><<<g256, 256, 0, st>>>(R, n_ptr, n_cap, src);
+    nm_bvh_pass<CLOSEST>(sc, sc->nm_obj, n_ptr, n_cap, st, ctx->launches);
+    k_nm_begin_lights<CLOSEST><<<g256, 256, 0, st>>>(R, n_ptr, n_cap);
+    nm_bvh_pass<CLOSEST>(sc, sc->nm_lig, n_ptr, n_cap, st, ctx->launches);
+    k_nm_finish<CLOSEST, Sink><<<g256, 256, 0, st>>>(R, n_ptr, n_cap, sink, total);
+    ctx->launches += 3;
+    CU(cudaGetLastError());
+    return LUMO_OK;
+}
+
 template <int MODE>
 static int32_t launch_batch(lumo_scene* sc, const double* o_dev, const double* d_dev, const double* tmax_dev, uint64_t n, unsigned long long* next_dev,
                             uint32_t* obj, uint32_t* tri, double* t, double* bary, uint8_t* occ) {
     lumo_ctx* ctx = sc->ctx;
     CU(cudaMemsetAsync(next_dev, 0, 8, ctx->stream));
+    if (!ctx->count_visits && !ctx->flat && ctx->nm && sc->nm_ok && MODE != 2 && n < 0x7FFFFFFFull) {
+        const uint32_t n32 = (uint32_t)n;
+        CU(cudaMemcpyAsync(ctx->d_n_batch, &n32, 4, cudaMemcpyHostToDevice, ctx->stream));
+        BatchSource src{o_dev, d_dev, tmax_dev};
+        if (MODE == 0) { BatchSink<FQ_CLOSEST> sink{obj, tri, t, bary, occ}; return nm_trace<true>(sc, ctx->d_n_batch, n32, src, sink, nullptr, ctx->stream); }
+        BatchSink<FQ_OCCLUDED> sink{obj, tri, t, bary, occ}; return nm_trace<false>(sc, ctx->d_n_batch, n32, src, sink, nullptr, ctx->stream);
+    }
     if (ctx->count_visits) k_trace_batch<MODE, true><<<trace_grid(ctx), 128, 0, ctx->stream>>>(sc->S, o_dev, d_dev, tmax_dev, n, next_dev, obj, tri, t, bary, occ, ctx->d_visit + (MODE == 0 ? 0 : 1));
     else if (ctx->flat) k_trace_batch_flat<MODE><<<ctx->sm_count * 4, 128, 0, ctx->stream>>>(sc->S, o_dev, d_dev, tmax_dev, n, next_dev, obj, tri, t, bary, occ);
     else k_trace_batch<MODE, false><<<trace_grid(ctx), 128, 0, ctx->stream>>>(sc->S, o_dev, d_dev, tmax_dev, n, next_dev, obj, tri, t, bary, occ, nullptr);
@@ -300,10 +457,6 @@ extern "C" int32_t lumo_gpu_trace_closest_dev(lumo_scene* sc, const double* o_de
 }
 
 // ---- render ----------------------------------------------------------------------------------------
-struct Carver {   // carves 256-byte aligned arrays out of one allocation
-    uint8_t* base; size_t off = 0;
-    template <class T> T* take(size_t n) { T* p = base ? (T*)(base + off) : nullptr; off = (off + n * sizeof(T) + 255) & ~(size_t)255; return p; }
-};
 static void carve_wave(Wave& W, Carver& c, uint32_t N, uint32_t shadow_cap, uint32_t n_tiles, size_t film_px) {
     W.n_slots = N; W.shadow_cap = shadow_cap;
     for (int b = 0; b < 2; b++) {
@@ -359,6 +512,8 @@ static int32_t run_wave(lumo_scene* sc, const Wave& W, WaveParams P, uint64_t& i
     // a few microseconds).
     const int BATCH = LUMO_ITER_BATCH;
     uint32_t main_iter = 0;
+    const bool use_nm = ctx->nm && sc->nm_ok && !ctx->count_visits && !ctx->flat;
+    uint32_t last_active = W.n_slots;          // live paths at the last host synchronisation (upper bound for the next batch)
     for (;;) {
         for (int b = 0; b < BATCH; b++) {
             cudaEvent_t* ev = ctx->kev + 5 * b;
@@ -367,7 +522,13 @@ static int32_t run_wave(lumo_scene* sc, const Wave& W, WaveParams P, uint64_t& i
             k_retire<<<rgrid, 256, 0, st>>>(sc->S, W, P);
             k_compact<<<rgrid, 256, 0, st>>>(W);
             CU(cudaEventRecord(ev[1], st));
+            const bool nm_now = use_nm && last_active >= LUMO_NM_MIN_RAYS;   // a few dozen small launches: only worth it for full queues
             if (ctx->count_visits) k_wave_trace<true><<<tgrid, 128, 0, st>>>(sc->S, W, P.cur, ctx->d_visit);
+            else if (nm_now) {
+                NmWaveSource src{W, P.cur}; NmWaveHitSink sink{W, sc->S.materials, sc->S.objects};
+                int32_t rc = nm_trace<true>(sc, &W.it->n_active, W.n_slots, src, sink, &W.run->closest, st); if (rc != LUMO_OK) return rc;
+                k_classify<<<rgrid, 256, 0, st>>>(W); ctx->launches++;
+            }
             else if (ctx->flat) { k_wave_trace_flat<<<ctx->sm_count * 4, 128, 0, st>>>(sc->S, W, P.cur); k_classify<<<rgrid, 256, 0, st>>>(W); ctx->launches++; }
             else k_wave_trace<false><<<tgrid, 128, 0, st>>>(sc->S, W, P.cur, nullptr);
             CU(cudaEventRecord(ev[2], st));
@@ -379,6 +540,10 @@ static int32_t run_wave(lumo_scene* sc, const Wave& W, WaveParams P, uint64_t& i
             launch_shade_kind<LMAT_MFDIELECTRIC>(sc, W, P, sgrid, ngrid, st, ctx->launches);
             CU(cudaEventRecord(ev[3], st));
             if (ctx->count_visits) k_wave_occlude<true><<<tgrid, 128, 0, st>>>(sc->S, W, ctx->d_visit + 1);
+            else if (nm_now) {
+                NmShadowSource src{W}; NmShadowSink sink{W};
+                int32_t rc = nm_trace<false>(sc, &W.it->n_shadow, W.shadow_cap, src, sink, &W.run->occlusion, st); if (rc != LUMO_OK) return rc;
+            }
             else if (ctx->flat) k_wave_occlude_flat<<<ctx->sm_count * 4, 128, 0, st>>>(sc->S, W);
             else k_wave_occlude<false><<<tgrid, 128, 0, st>>>(sc->S, W, nullptr);
             CU(cudaEventRecord(ev[4], st));
@@ -388,10 +553,15 @@ static int32_t run_wave(lumo_scene* sc, const Wave& W, WaveParams P, uint64_t& i
             P.cur ^= 1u;
         }
         CU(cudaMemcpyAsync(&hc->qc, W.qc, sizeof(QueueCounters), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(&hc->run, W.run, sizeof(RunCounters), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         CU(cudaGetLastError());
         if (P.mode == WM_MAIN) for (int b = 0; b < BATCH; b++) for (int k = 0; k < 4; k++) {
             float ms = 0; CU(cudaEventElapsedTime(&ms, ctx->kev[5 * b + k], ctx->kev[5 * b + k + 1])); ctx->kernel_ms[k] += ms; ctx->kernel_launches[k]++;
+        }
+        {   // survivors plus what the next k_retire can still refill
+            const unsigned long long remaining = hc->run.next_work < P.total_work ? P.total_work - hc->run.next_work : 0ull;
+            last_active = (uint32_t)std::min<unsigned long long>(W.n_slots, hc->qc.n_active[P.cur] + remaining);
         }
         if (hc->qc.n_active[P.cur] == 0 && hc->qc.n_done[P.cur ^ 1u] == 0) break;   // no survivors and nothing left to retire
     }

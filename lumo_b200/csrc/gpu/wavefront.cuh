@@ -18,6 +18,7 @@
 #pragma once
 #include "shade.cuh"
 #include "trace_flat.cuh"
+#include "trace_nm.cuh"
 #include <cooperative_groups.h>
 #include <cstdio>
 

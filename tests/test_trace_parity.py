@@ -107,6 +107,37 @@ def test_flat_traversal_is_bit_exact_too():
     G.close(); ctx.close(); O.close()
 
 
+def test_node_major_bit_exact():
+    """The node-major traversal of small object BVHs (trace_nm.cuh, opt-in via LUMO_TRACE_NM=1: per-BVH-segment kernels,
+    light objects in place, a lane-refilled kernel per big kd-tree) must produce the same bits as the nested default, for
+    the batch API and for a whole render."""
+    import os
+    from lumo_b200 import native
+    os.environ["LUMO_TRACE_NM"] = "1"
+    try:
+        ctx = native.GpuContext(0)
+    finally:
+        del os.environ["LUMO_TRACE_NM"]
+    ref = native.GpuContext(0)
+    for name in ("bunny", "cornell"):
+        prog, blob, ig = small_scene(name)
+        O = oracle_lib.OracleScene(prog)
+        G = native.GpuScene(ctx, blob)
+        for kind, (o, d) in ray_batches(O, 8000, seed=41).items():
+            eo, et, ett, eb = O.trace_closest(o, d)
+            go, gt, gtt, gb = G.trace_closest(o, d)
+            assert np.array_equal(eo, go) and np.array_equal(et, gt) and np.array_equal(_bits(ett), _bits(gtt)) and np.array_equal(_bits(eb), _bits(gb)), (name, kind)
+            tm = np.where(np.isfinite(ett), ett * 0.999, 5.0)
+            assert np.array_equal(O.trace_any(o, d, tm), G.trace_any(o, d, tm)), (name, kind)
+        # a render large enough for the wave to take the node-major path (>= 131072 live rays), against the default context
+        R = native.GpuScene(ref, blob)
+        a = G.render(integrator=ig, spp=64, seed=5)
+        b = R.render(integrator=ig, spp=64, seed=5)
+        assert np.array_equal(_bits(a[0]), _bits(b[0])) and a[2]["closest"] == b[2]["closest"] and a[2]["occlusion"] == b[2]["occlusion"], name
+        G.close(); R.close(); O.close()
+    ctx.close(); ref.close()
+
+
 def test_special_rays_bit_exact(gpu_ctx):
     """Edge cases of the arithmetic: zero direction components (inf reciprocals, 0*inf = NaN dropped by
     min/max), negative zero, origins exactly on box planes / kd split planes / triangle planes, finite t_max on both sides of
