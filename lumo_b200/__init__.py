@@ -4,4 +4,5 @@ from .api import (Scene, Camera, CameraBuilder, CameraType, Material, Texture, R
                   Instance, LooseTriangles, Integrator, Renderer, SamplerType, ToneMap, PixelFilter, ColorSpace, illuminants)
 from .spectrum import Spectrum
 from .film import Film
+from .image import Image
 from . import parser

@@ -81,21 +81,58 @@ class ColorSpace:                                    # src/tracer/color/space.rs
     sRGB, DCI_P3, Rec_2020 = 0, 1, 2
 
 
-class Texture:
-    """Only `Texture::Solid` is on the device so far (src/tracer/texture.rs:14-37); image / marble /
-    checkerboard textures are SURVEY §8f-2 follow-ups."""
-    def __init__(self, spec):
-        self.spec = spec
+class Texture:                                       # src/tracer/texture.rs:23-38
+    """Solid(Spectrum) | Checkerboard(Texture, Texture, scale) | Marble(Perlin seed, Spectrum) | Image(Image<Spectrum>) | Mandelbrot."""
+    def __init__(self, kind, spec=None, a=None, b=None, scale=1.0, seed=0, image=None):
+        self.kind, self.spec, self.a, self.b, self.scale, self.seed, self.image = kind, spec, a, b, scale, seed, image
 
     @staticmethod
-    def from_spectrum(spec): return Texture(spec)
+    def from_spectrum(spec): return Texture(P.TEX_SOLID, spec=spec)
+    @staticmethod
+    def Solid(spec): return Texture(P.TEX_SOLID, spec=spec)
+    @staticmethod
+    def Checkerboard(t1, t2, scale): return Texture(P.TEX_CHECKER, a=_as_tex(t1), b=_as_tex(t2), scale=float(scale))
+    @staticmethod
+    def Marble(seed, spec):
+        """`Texture::Marble(Perlin::new(seed), spec)`; the reference's `Perlin::default()` draws its seed from the clock."""
+        return Texture(P.TEX_MARBLE, spec=spec, seed=int(seed))
+    @staticmethod
+    def Image(image):
+        assert image.kind == "spectrum"
+        return Texture(P.TEX_IMAGE, spec=image.mean, image=image)
+    @staticmethod
+    def Mandelbrot(): return Texture(P.TEX_MANDELBROT)
+
+    def _emit(self, w, cache):
+        """texture id in the program (children first)"""
+        if id(self) in cache: return cache[id(self)]
+        sp = (self.spec if self.spec is not None else Spectrum.BLACK()).as_tuple()
+        if self.kind == P.TEX_CHECKER:
+            tid = w.texture(P.TEX_CHECKER, a=self.a._emit(w, cache), b=self.b._emit(w, cache), scale=self.scale)
+        elif self.kind == P.TEX_IMAGE:
+            tid = w.texture(P.TEX_IMAGE, spec=sp, width=self.image.width, height=self.image.height, data=self.image.data)
+        else:
+            tid = w.texture(self.kind, spec=sp, seed=self.seed)
+        cache[id(self)] = tid
+        return tid
+
+
+def _as_tex(t):
+    if isinstance(t, Texture): return t
+    if isinstance(t, Spectrum): return Texture.Solid(t)
+    if callable(t): return Texture.Solid(t())
+    raise TypeError("expected Texture or Spectrum")
 
 
 def _tex(t):
-    if isinstance(t, Texture): return t.spec
-    if isinstance(t, Spectrum): return t
-    if callable(t): return t()
-    raise TypeError("expected Texture or Spectrum")
+    """the Solid spectrum of a texture argument (Spectrum::BLACK placeholder for the other kinds: the device reads the texture)"""
+    t = _as_tex(t)
+    return t.spec if (t.kind == P.TEX_SOLID and t.spec is not None) else Spectrum.BLACK()
+
+
+def _tex_ref(t):
+    t = _as_tex(t)
+    return None if t.kind == P.TEX_SOLID else t
 
 
 class Material:                                      # src/tracer/material.rs:12-194
@@ -104,14 +141,16 @@ class Material:                                      # src/tracer/material.rs:12
         self.kw = kw
 
     @staticmethod
-    def microfacet(roughness, eta, k, is_transparent, fresnel_enabled, kd, ks, tf):
+    def microfacet(roughness, eta, k, is_transparent, fresnel_enabled, kd, ks, tf, bump_map=None):
         assert 0.0 <= roughness <= 1.0                # microfacet.rs:27
+        assert bump_map is None or bump_map.kind == "normal"
         eta_kind = P.ETA_CONST
         if is_transparent and eta == 1.5: eta_kind = P.ETA_GLASS        # material.rs:37-45
         if is_transparent and eta == 2.5: eta_kind = P.ETA_DIAMOND
         kind = P.M_MFDIELECTRIC if is_transparent else (P.M_MFCONDUCTOR if fresnel_enabled else P.M_MFDIFFUSE)
         return Material(kind, roughness=roughness, eta_kind=eta_kind, eta=eta, k_kind=P.ETA_CONST, k=k,
-                        kd=_tex(kd).as_tuple(), ks=_tex(ks).as_tuple(), tf=_tex(tf).as_tuple())
+                        kd=_tex(kd).as_tuple(), ks=_tex(ks).as_tuple(), tf=_tex(tf).as_tuple(),
+                        _textures=dict(kd_tex=_tex_ref(kd), ks_tex=_tex_ref(ks), tf_tex=_tex_ref(tf)), _bump=bump_map)
 
     @staticmethod
     def metal(ks, roughness, eta, k):
@@ -148,7 +187,8 @@ class Material:                                      # src/tracer/material.rs:12
 
     @staticmethod
     def Light(ke, illuminant, scale, two_sided):
-        return Material(P.M_LIGHT, ke=_tex(ke).as_tuple(), illuminant=ILLUMINANTS.index(illuminant), scale=scale, two_sided=int(two_sided))
+        return Material(P.M_LIGHT, ke=_tex(ke).as_tuple(), illuminant=ILLUMINANTS.index(illuminant), scale=scale, two_sided=int(two_sided),
+                        _textures=dict(ke_tex=_tex_ref(ke)))
 
     Blank = None
 
@@ -312,7 +352,7 @@ class Scene:                                         # src/tracer/scene.rs:18-11
     def add_light(self, light): self.lights.append(light)
 
     def set_environment_map(self, env_map, scale):
-        self.environment_map = (_tex(env_map), float(scale))
+        self.environment_map = (_as_tex(env_map), float(scale))
 
     def num_lights(self):
         n = 0
@@ -330,9 +370,19 @@ class Scene:                                         # src/tracer/scene.rs:18-11
         w = P.ProgramWriter()
         mats, meshes = {}, {}
 
+        texs = {}
+
         def mat_id(m):
             if m is None: return -1
-            if id(m) not in mats: mats[id(m)] = w.material(m.kind, **m.kw)
+            if id(m) not in mats:
+                kw = {k: v for k, v in m.kw.items() if not k.startswith("_")}
+                for slot, t in m.kw.get("_textures", {}).items():
+                    if t is not None: kw[slot] = t._emit(w, texs)
+                bump = m.kw.get("_bump")
+                if bump is not None:
+                    if id(bump) not in texs: texs[id(bump)] = w.texture(P.TEX_BUMP, width=bump.width, height=bump.height, data=bump.data)
+                    kw["bump_tex"] = texs[id(bump)]
+                mats[id(m)] = w.material(m.kind, **kw)
             return mats[id(m)]
 
         def mesh_id(m):
@@ -372,7 +422,8 @@ class Scene:                                         # src/tracer/scene.rs:18-11
         for o in self.objects: emit(o, False)
         for o in self.lights: emit(o, True)
         if self.environment_map:
-            w.envmap(self.environment_map[0].as_tuple(), self.environment_map[1])
+            env = _as_tex(self.environment_map[0])
+            w.envmap(_tex(env).as_tuple(), self.environment_map[1], -1 if env.kind == P.TEX_SOLID else env._emit(w, texs))
         c = camera
         w.camera(c._origin, c._towards, c._up, c._zoom, c._lens_radius, c._focal_length, c._vfov, c._resolution, c._camera_type,
                  c._pixel_filter.kind, c._pixel_filter.r, c._pixel_filter.p, c._color_space, ILLUMINANTS.index(c._illuminant))

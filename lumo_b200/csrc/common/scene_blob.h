@@ -10,7 +10,7 @@
 #include <stdint.h>
 
 #define LUMO_BLOB_MAGIC 0x31424F4C424D554CULL /* "LUMBLOB1" */
-#define LUMO_BLOB_VERSION 3u
+#define LUMO_BLOB_VERSION 4u
 #define LUMO_NONE 0xFFFFFFFFu
 
 enum LumoSection {
@@ -30,6 +30,10 @@ enum LumoSection {
     LSEC_MATERIALS,       // LumoMaterial[]
     LSEC_TABLES,          // f64[96] per table (95 samples, 5 nm, 360..830; +1 pad)
     LSEC_LIGHTS,          // LumoLight[]  alias table + pdf + area, one per Scene.lights entry
+    LSEC_TEXTURES,        // LumoTexture[]  (texture.rs:23-38); materials refer to them by index
+    LSEC_TEX_PIXELS,      // f32[4] per pixel: Image<Spectrum>.buffer as Spectrum {c0,c1,c2,scale}, row-major (image.rs:8-16)
+    LSEC_TEX_F64,         // f64 pool: Perlin tables (256 x 3 lattice normals, then 3 x 256 permutation entries as f64) and
+                          //           Image<Normal> buffers (3 f64 per pixel)
     LSEC_COUNT
 };
 
@@ -75,13 +79,27 @@ struct LumoTriShade {          // 32 B
 };
 struct LumoRect { double origin[3], b0[3], b1[3], pad; };  // 80 B (rectangle.rs:4-13)
 struct LumoSphere { double radius, pad; };
-struct LumoMaterial {          // 112 B
+enum LumoTexKind { LTEX_SOLID = 0, LTEX_CHECKER = 1, LTEX_MARBLE = 2, LTEX_IMAGE = 3, LTEX_MANDELBROT = 4, LTEX_BUMP = 5 };
+struct LumoTexture {           // 64 B  (texture.rs:23-38; LTEX_BUMP is the Image<Normal> of Material::Standard, material.rs:14)
+    uint32_t kind;
+    uint32_t a, b;             // Checkerboard: the two child textures
+    uint32_t width, height;    // Image / bump
+    uint32_t pad;
+    uint64_t data;             // Image: first pixel in LSEC_TEX_PIXELS; Marble / bump: first f64 in LSEC_TEX_F64
+    float spec[4];             // Solid / Marble colour; Image: the mean spectrum (Texture::power)
+    double scale;              // Checkerboard scale
+    double pad2;
+};
+struct LumoMaterial {          // 128 B
     uint32_t kind, flags;
     double roughness;          // clamped to >= 1e-5 (microfacet.rs:30-36), isotropic
-    float kd[4], ks[4], tf[4], ke[4];   // Spectrum {c0,c1,c2,scale} (spectrum.rs:14-19); Lambertian uses kd
-    uint32_t eta_table, k_table, illum_table, pad;
+    float kd[4], ks[4], tf[4], ke[4];   // Texture::Solid spectra {c0,c1,c2,scale} (spectrum.rs:14-19); Lambertian uses kd
+    uint32_t eta_table, k_table, illum_table;
+    uint32_t kd_tex;           // LUMO_NONE: the Solid spectrum above; else index into LSEC_TEXTURES (same for ks/tf/ke)
     double scale;              // Light scale
-    double pad2;
+    uint32_t ks_tex, tf_tex, ke_tex;
+    uint32_t bump_tex;         // LUMO_NONE or the LTEX_BUMP record of the normal map
+    uint64_t pad;
 };
 struct LumoLight {             // 32 B  (bvh.rs:24-25 alias_table / alias_pdf)
     double alias_prob, pdf, area;

@@ -18,7 +18,7 @@ namespace lumo_dev {
 
 struct Vtx { DevHit h; C4 gathered; double pdf_fwd, pdf_bck; D3 wo; int light; int pad; };   // vertex.rs:5-12
 
-__device__ const LumoMaterial g_blank_material = {LMAT_BLANK, 0u, 1.0, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, 0u, 0u, 0u, 0u, 0.0, 0.0};
+__device__ const LumoMaterial g_blank_material = {LMAT_BLANK, 0u, 1.0, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, 0u, 0u, 0u, LUMO_NONE, 0.0, LUMO_NONE, LUMO_NONE, LUMO_NONE, LUMO_NONE, 0ull};
 __device__ __forceinline__ const Mat& vmat(const DevScene& S, const Vtx& v) { return v.h.material < 0 ? g_blank_material : S.materials[v.h.material]; }
 __device__ __forceinline__ bool v_is_surface(const Vtx& v) { return v.h.material >= 0; }                    // vertex.rs:86-88 (Blank = camera)
 __device__ __forceinline__ bool v_is_light(const Vtx& v) { return v.light >= 0; }
@@ -32,14 +32,14 @@ __device__ __forceinline__ double v_shading_correction(const DevScene& S, const 
 __device__ __noinline__ C4 v_bsdf_f(const DevScene& S, const Vtx& v, D3 wi, const Lam& l, int mode) {
     const Mat& m = vmat(S, v);
     if (!mat_is_standard(m)) return c4(0.0);
-    const Onb uvw = onb_new(v.h.ns);
+    const Onb uvw = shading_onb(S, m, v.h);
     return bsdf_f<-1>(S, m, uvw, v.wo, wi, l, mode, v.h);
 }
 __device__ __forceinline__ C4 v_f(const DevScene& S, const Vtx& v, const Vtx& next, const Lam& l, int mode) { return v_bsdf_f(S, v, normalize(next.h.p - v.h.p), l, mode); }   // vertex.rs:129-132
 __device__ __noinline__ double v_bsdf_pdf(const DevScene& S, const Vtx& v, D3 wi, const Lam& l, bool swap_dir) {
     const Mat& m = vmat(S, v);
     if (!mat_is_standard(m)) return 0.0;
-    const Onb uvw = onb_new(v.h.ns);
+    const Onb uvw = shading_onb(S, m, v.h);
     return bsdf_pdf<-1>(S, m, uvw, v.wo, wi, v.h, l, swap_dir);
 }
 __device__ __forceinline__ double v_pdf_prev(const DevScene& S, const Vtx& v, const Vtx& prev, D3 wi, const Lam& l) {   // vertex.rs:146-160
@@ -143,7 +143,7 @@ __device__ __noinline__ int bdpt_walk(const DevScene& S, Ray ro, Rng& rng, Lam& 
         const uint32_t curr = depth;
         const double ru = rng_float(rng), r0 = rng_float(rng), r1 = rng_float(rng);
         D3 wi;
-        const Onb uvw = onb_new(ho.ns);
+        const Onb uvw = shading_onb(S, m, ho);
         if (!bsdf_sample<-1>(S, m, uvw, wo, ho, lam, ru, r0, r1, wi)) {
             if (mode == 1) n--;                                                               // path_gen.rs:97-99: a light path cannot end on a light
             else {                                                                            // Scene::get_light_at (bvh.rs:97-102)
@@ -283,7 +283,7 @@ __device__ __noinline__ bool connect_light_path(const DevScene& S, Rng& rng, con
 __device__ __noinline__ C4 add_camera_path(const DevScene& S, const Lam& lam, const Vtx* cp, int t) {
     const Vtx& ct = cp[t - 1];
     if (!v_is_light(ct)) return c4(0.0);
-    const C4 rad = ct.gathered * mat_emit(S, vmat(S, ct), lam, ct.h.backface);
+    const C4 rad = ct.gathered * mat_emit(S, vmat(S, ct), lam, ct.h);
     if (is_black(rad)) return c4(0.0);
     return rad * mis_weight(S, lam, nullptr, 0, cp, t, nullptr, nullptr);
 }
@@ -311,7 +311,7 @@ __device__ __noinline__ C4 connect_camera_path(const DevScene& S, Rng& rng, cons
     if (p_lig == 0.0) return c4(0.0);
     wi = ri.d;
     const double pdf_origin = sa_to_area(p_lig, xo, xi, wi, ngi);
-    const C4 emittance = mat_emit(S, S.materials[hi.material], lam, hi.backface);
+    const C4 emittance = mat_emit(S, S.materials[hi.material], lam, hi);
     Vtx ll; ll.h = hi; ll.gathered = emittance; ll.light = (int)li; ll.pdf_fwd = pdf_origin; ll.pdf_bck = 0.0; ll.wo = d3(0, 0, 0); ll.pad = 0;   // Vertex::light
     const C4 bsdf = v_f(S, cl, ll, lam, 0);
     const double cos_wi = v_shading_cosine(S, cl, wi);
@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(64) k_bdpt_walk(const __grid_constant__ DevSce
             const Onb uvw = onb_new(ho.ns);
             const Ray ri = hit_generate_ray(ho, to_world(uvw, square_to_cos_hemisphere(b0, b1)));
             double pdf_origin, pdf_dir; light_leaving_pdf(S, (int)li, ri, ho.ng, pdf_origin, pdf_dir);
-            const C4 emit = mat_emit(S, S.materials[ho.material], lam, ho.backface);
+            const C4 emit = mat_emit(S, S.materials[ho.material], lam, ho);
             Vtx& root = lp[0];
             root.h = ho; root.gathered = emit; root.light = (int)li; root.pdf_fwd = pdf_origin * pdf_light; root.pdf_bck = 0.0; root.wo = d3(0, 0, 0); root.pad = 0;
             const C4 gathered = emit * fabs(dot(ri.d, ho.ns)) / (pdf_light * pdf_origin * pdf_dir);

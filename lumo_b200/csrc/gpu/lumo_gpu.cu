@@ -157,7 +157,8 @@ static bool validate_blob(const uint8_t* b, uint64_t len, LumoBlobHeader& H, std
     if (H.version != LUMO_BLOB_VERSION) { why = "unsupported blob version"; return false; }
     if (H.n_sections != LSEC_COUNT || H.total_bytes != len) { why = "blob size / section count mismatch"; return false; }
     static const size_t elem[LSEC_COUNT] = {sizeof(LumoTlasNode), 4, sizeof(LumoObject), sizeof(LumoInstance), sizeof(LumoKdTree), sizeof(LumoKdNode), 4,
-                                            sizeof(LumoTriVerts), sizeof(LumoTriShade), 24, 16, sizeof(LumoRect), sizeof(LumoSphere), sizeof(LumoMaterial), 96 * 8, sizeof(LumoLight)};
+                                            sizeof(LumoTriVerts), sizeof(LumoTriShade), 24, 16, sizeof(LumoRect), sizeof(LumoSphere), sizeof(LumoMaterial), 96 * 8, sizeof(LumoLight),
+                                            sizeof(LumoTexture), 16, 8};
     for (int s = 0; s < LSEC_COUNT; s++) {
         const LumoSectionRef& r = H.sec[s];
         if (r.offset % 16 || r.offset > len || r.bytes > len - r.offset || r.bytes != r.count * elem[s]) { why = "blob section " + std::to_string(s) + " is malformed"; return false; }
@@ -191,6 +192,22 @@ static bool validate_blob(const uint8_t* b, uint64_t len, LumoBlobHeader& H, std
     const LumoMaterial* mats = (const LumoMaterial*)(b + H.sec[LSEC_MATERIALS].offset);
     for (uint64_t i = 0; i < H.sec[LSEC_MATERIALS].count; i++)
         if (mats[i].eta_table >= H.sec[LSEC_TABLES].count || mats[i].k_table >= H.sec[LSEC_TABLES].count || mats[i].illum_table >= H.sec[LSEC_TABLES].count) { why = "material table index out of range"; return false; }
+    const LumoTexture* tx = (const LumoTexture*)(b + H.sec[LSEC_TEXTURES].offset);
+    const uint64_t n_tex = H.sec[LSEC_TEXTURES].count;
+    for (uint64_t i = 0; i < n_tex; i++) {
+        const LumoTexture& T = tx[i];
+        bool ok = T.kind <= LTEX_BUMP;
+        if (T.kind == LTEX_CHECKER) ok = T.a < i && T.b < i && tx[T.a].kind != LTEX_BUMP && tx[T.b].kind != LTEX_BUMP;   // children precede: no cycles
+        if (T.kind == LTEX_MARBLE) ok = T.data + 1536 <= H.sec[LSEC_TEX_F64].count;
+        if (T.kind == LTEX_IMAGE) ok = T.width > 0 && T.height > 0 && T.data + (uint64_t)T.width * T.height <= H.sec[LSEC_TEX_PIXELS].count;
+        if (T.kind == LTEX_BUMP) ok = T.width > 0 && T.height > 0 && T.data + 3ull * T.width * T.height <= H.sec[LSEC_TEX_F64].count;
+        if (!ok) { why = "texture record " + std::to_string(i) + " out of range"; return false; }
+    }
+    for (uint64_t i = 0; i < H.sec[LSEC_MATERIALS].count; i++) {
+        const uint32_t col[4] = {mats[i].kd_tex, mats[i].ks_tex, mats[i].tf_tex, mats[i].ke_tex};
+        for (uint32_t t : col) if (t != LUMO_NONE && (t >= n_tex || tx[t].kind == LTEX_BUMP)) { why = "material texture index out of range"; return false; }
+        if (mats[i].bump_tex != LUMO_NONE && (mats[i].bump_tex >= n_tex || tx[mats[i].bump_tex].kind != LTEX_BUMP)) { why = "material bump map index out of range"; return false; }
+    }
     return true;
 }
 
@@ -218,6 +235,7 @@ extern "C" int32_t lumo_gpu_scene_upload(lumo_ctx* ctx, const void* blob, uint64
     S.normals = (const double*)at(LSEC_NORMALS); S.uvs = (const double*)at(LSEC_UVS);
     S.rects = (const LumoRect*)at(LSEC_RECTS); S.spheres = (const LumoSphere*)at(LSEC_SPHERES);
     S.materials = (const LumoMaterial*)at(LSEC_MATERIALS); S.tables = (const double*)at(LSEC_TABLES); S.lights = (const LumoLight*)at(LSEC_LIGHTS);
+    S.textures = (const LumoTexture*)at(LSEC_TEXTURES); S.tex_pixels = (const float*)at(LSEC_TEX_PIXELS); S.tex_f64 = (const double*)at(LSEC_TEX_F64);
     S.P = H.params;
     {   // node-major plans: both BVHs in the reference's traversal order, if they are small enough
         const uint8_t* hb = (const uint8_t*)blob;

@@ -117,6 +117,85 @@ __device__ __forceinline__ double spec_one(const float* c, double lambda) {     
     return (double)__fmul_rn(c[3], sg);
 }
 __device__ __forceinline__ C4 spec4(const float* c, const Lam& l) { C4 r; _Pragma("unroll") for (int i = 0; i < 4; i++) r.s[i] = spec_one(c, l.l[i]); return r; }
+
+// ---- Textures (texture.rs:23-113, perlin.rs:48-110, image.rs:99-193) -------------------------------
+// Materials whose kd / ks / tf / ke is a Texture::Solid keep the spectrum inline (m.kd ...) and never come here.
+__device__ __forceinline__ double perlin_noise(const double* tab, D3 p) {                                                       // perlin.rs:50-68
+    const D3 weight = d3(fractd(p.x), fractd(p.y), fractd(p.z));
+    const unsigned long long fx = sat_u64(floor(p.x)), fy = sat_u64(floor(p.y)), fz = sat_u64(floor(p.z));
+    const double* px = tab + 768; const double* py = px + 256; const double* pz = py + 256;
+    const D3 w = d3(((6.0 * weight.x - 15.0) * weight.x + 10.0) * weight.x * weight.x * weight.x,                                // perlin.rs:83-85
+                    ((6.0 * weight.y - 15.0) * weight.y + 10.0) * weight.y * weight.y * weight.y,
+                    ((6.0 * weight.z - 15.0) * weight.z + 10.0) * weight.z * weight.z * weight.z);
+    double acc = 0.0;
+#pragma unroll 1
+    for (int c = 0; c < 8; c++) {                                                                                                // (i, j, k), k fastest
+        const unsigned long long i = (unsigned long long)(c >> 2), j = (unsigned long long)((c >> 1) & 1), k = (unsigned long long)(c & 1);
+        const unsigned long long h = (unsigned long long)__ldg(px + ((fx + i) & 255ull)) ^ (unsigned long long)__ldg(py + ((fy + j) & 255ull)) ^ (unsigned long long)__ldg(pz + ((fz + k) & 255ull));
+        const D3 n = d3(__ldg(tab + 3 * h), __ldg(tab + 3 * h + 1), __ldg(tab + 3 * h + 2));
+        const D3 idx = d3((double)i, (double)j, (double)k);
+        const D3 widx = d3(2.0 * w.x * idx.x + 1.0 - w.x - idx.x, 2.0 * w.y * idx.y + 1.0 - w.y - idx.y, 2.0 * w.z * idx.z + 1.0 - w.z - idx.z);   // perlin.rs:92-109
+        acc = acc + widx.x * widx.y * widx.z * dot(n, w - idx);
+    }
+    return acc;
+}
+// Image::bilin_interp (image.rs:99-131): the four texel indices and the two weights
+struct Taps { uint32_t i00, i10, i01, i11; double wx, wy; };
+__device__ __forceinline__ uint32_t sat_u32(double v) { const unsigned long long u = sat_u64(v); return u > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)u; }
+__device__ __forceinline__ Taps image_taps(uint32_t width, uint32_t height, double u, double v) {
+    const double w = (double)width, h = (double)height;
+    const double x = u * w, y = (1.0 - v) * h;
+    const double xo_f = floor(x - 0.5), yo_f = floor(y - 0.5);
+    Taps t;
+    t.wx = 1.0 - (x - xo_f - 0.5); t.wy = 1.0 - (y - yo_f - 0.5);
+    const uint32_t xo = sat_u32(xo_f + w) % width, yo = sat_u32(yo_f + h) % height;
+    const uint32_t xi = (xo + 1u) % width, yi = (yo + 1u) % height;
+    t.i00 = xo + yo * width; t.i10 = xi + yo * width; t.i01 = xo + yi * width; t.i11 = xi + yi * width;
+    return t;
+}
+__device__ __noinline__ C4 texture_albedo(const DevScene& S, uint32_t tex, double u, double v, const Lam& l) {                  // texture.rs:53-92
+    const LumoTexture* T = S.textures + tex;
+    while (T->kind == LTEX_CHECKER) {                                                                                            // children see the same uv
+        const double su = u * T->scale, sv = v * T->scale;
+        T = S.textures + ((sat_u64(floor(su) + floor(sv)) % 2ull == 0ull) ? T->a : T->b);
+    }
+    switch (T->kind) {
+    case LTEX_MARBLE: {
+        const double* tab = S.tex_f64 + T->data;
+        D3 p = d3(4.0 * fabs(u), 4.0 * fabs(v), 4.0 * fabs(0.0));
+        double turb = 0.0;
+#pragma unroll 1
+        for (int depth = 0; depth < 6; depth++) {                                                                                // turbulence, texture.rs:105-112
+            turb = turb + powi(0.5, depth) * fabs(perlin_noise(tab, p));
+            p = 2.0 * p;
+        }
+        const double scaled = 1.0 - powi(0.5 + 0.5 * sin(60.0 * u + 20.0 * turb), 6);
+        return spec4(T->spec, l) * scaled;
+    }
+    case LTEX_IMAGE: {                                                                                                           // image.rs:184-193
+        const Taps t = image_taps(T->width, T->height, u, v);
+        const float* px = S.tex_pixels + 4 * T->data;
+        const C4 y0 = spec4(px + 4 * (size_t)t.i00, l) * t.wx + spec4(px + 4 * (size_t)t.i10, l) * (1.0 - t.wx);
+        const C4 y1 = spec4(px + 4 * (size_t)t.i01, l) * t.wx + spec4(px + 4 * (size_t)t.i11, l) * (1.0 - t.wx);
+        return y0 * t.wy + y1 * (1.0 - t.wy);
+    }
+    case LTEX_MANDELBROT: {
+        int depth = 0;
+        const double cre = 2.0 * (u - 0.75), cim = 2.0 * (v - 0.5);
+        double zre = 0.0, zim = 0.0;
+        while (depth < 256 && zre * zre + zim * zim < 64.0 * 64.0) {
+            const double nre = zre * zre - zim * zim, nim = zre * zim + zim * zre;
+            zre = nre + cre; zim = nim + cim;
+            depth++;
+        }
+        return depth == 256 ? c4(1.0) : c4(0.0);
+    }
+    default: return spec4(T->spec, l);
+    }
+}
+__device__ __forceinline__ C4 tex4(const DevScene& S, const float* solid, uint32_t tex, double u, double v, const Lam& l) {
+    return tex == LUMO_NONE ? spec4(solid, l) : texture_albedo(S, tex, u, v, l);
+}
 #define LUMO_Y_INTEGRAL 106.856895
 __device__ __forceinline__ const double* table(const DevScene& S, uint32_t id) { return S.tables + 96ull * id; }
 __device__ __noinline__ double luminance(const DevScene& S, C4 c, const Lam& l) {                                            // color.rs:88-91
@@ -230,6 +309,17 @@ __device__ __noinline__ Onb onb_new(D3 w) {
 }
 __device__ __forceinline__ D3 to_world(const Onb& o, D3 p) { return p.x * o.u + p.y * o.v + p.z * o.w; }
 __device__ __forceinline__ D3 to_local(const Onb& o, D3 p) { return d3(dot(p, o.u), dot(p, o.v), dot(p, o.w)); }
+// Image<Normal>::value_at (image.rs:134-151) + Material::map_normal (material.rs:324-331)
+__device__ __noinline__ D3 bump_normal(const DevScene& S, uint32_t tex, D3 ns, double u, double v) {
+    const LumoTexture* T = S.textures + tex;
+    const Taps t = image_taps(T->width, T->height, u, v);
+    const double* px = S.tex_f64 + T->data;
+    const D3 n00 = d3(px[3 * (size_t)t.i00], px[3 * (size_t)t.i00 + 1], px[3 * (size_t)t.i00 + 2]), n10 = d3(px[3 * (size_t)t.i10], px[3 * (size_t)t.i10 + 1], px[3 * (size_t)t.i10 + 2]);
+    const D3 n01 = d3(px[3 * (size_t)t.i01], px[3 * (size_t)t.i01 + 1], px[3 * (size_t)t.i01 + 2]), n11 = d3(px[3 * (size_t)t.i11], px[3 * (size_t)t.i11 + 1], px[3 * (size_t)t.i11 + 2]);
+    const D3 y0 = normalize(n00 * t.wx + n10 * (1.0 - t.wx)), y1 = normalize(n01 * t.wx + n11 * (1.0 - t.wx));
+    const D3 n = normalize(y0 * t.wy + y1 * (1.0 - t.wy));
+    return normalize(to_world(onb_new(ns), n));
+}
 
 // ---- rng/maps.rs -----------------------------------------------------------------------------------
 __device__ __forceinline__ void square_to_disk(double r0, double r1, double& dx, double& dy) {
@@ -277,10 +367,14 @@ __device__ __forceinline__ bool mat_is_delta(const DevScene& S, const Mat& m, co
     if (m.kind == LMAT_MFDIELECTRIC) return mf_is_delta(m) || eta_at(S, m, l.l[0]) == 1.0;
     return false;
 }
-__device__ __forceinline__ C4 mat_emit(const DevScene& S, const Mat& m, const Lam& l, bool backface) {                          // material.rs:220-231
+__device__ __forceinline__ C4 mat_emit(const DevScene& S, const Mat& m, const Lam& l, const DevHit& h) {                         // material.rs:220-231
     if (m.kind != LMAT_LIGHT) return c4(0.0);
-    if (!(m.flags & LMF_TWO_SIDED) && backface) return c4(0.0);
-    return m.scale * spec4(m.ke, l) * dense4(table(S, m.illum_table), l);
+    if (!(m.flags & LMF_TWO_SIDED) && h.backface) return c4(0.0);
+    return m.scale * tex4(S, m.ke, m.ke_tex, h.u, h.v, l) * dense4(table(S, m.illum_table), l);
+}
+// the shading frame of a hit: Onb::new(ns), with the normal map applied first for materials that have one (material.rs:258-310)
+__device__ __forceinline__ Onb shading_onb(const DevScene& S, const Mat& m, const DevHit& h) {
+    return onb_new(m.bump_tex == LUMO_NONE ? h.ns : bump_normal(S, m.bump_tex, h.ns, h.u, h.v));
 }
 __device__ __forceinline__ double shading_cosine(const Mat& m, D3 wi, D3 ns) { return mat_is_standard(m) ? fabs(dot(ns, wi)) : 1.0; }   // material.rs:315-321
 
@@ -402,7 +496,7 @@ __device__ __forceinline__ double refl_pdf_half(const Mat& m, D3 wo, D3 wh) {
 // K = material kind known at compile time (the per-kind shade kernels), or -1 for a runtime switch.
 #define LUMO_KIND(K, m) ((K) < 0 ? (m).kind : (uint32_t)(K))
 template <int K>
-__device__ __noinline__ C4 bx_f(const DevScene& S, const Mat& m, D3 wo, D3 wi, const Lam& l, bool reflection, bool backface, int mode) {
+__device__ __noinline__ C4 bx_f(const DevScene& S, const Mat& m, D3 wo, D3 wi, const Lam& l, bool reflection, bool backface, int mode, double u, double v) {
     const uint32_t kind = LUMO_KIND(K, m);
     if ((!reflection || backface) && kind != LMAT_MFDIELECTRIC) return c4(0.0);
     switch (kind) {
@@ -412,10 +506,10 @@ __device__ __noinline__ C4 bx_f(const DevScene& S, const Mat& m, D3 wo, D3 wi, c
         const double d = ggx_d(m, wh); const C4 f = fresnel4(S, m, wo, wh, l); const double g = ggx_g(m, wo, wi, wh);
         const C4 fr = d * f * g / (4.0 * fabs(wo.z) * fabs(wi.z));
         const double fd = disney_diffuse(m, wo.z, wi.z, wh.z);
-        return fr * spec4(m.ks, l) + spec4(m.kd, l) * (c4(1.0) - f) * fd / LUMO_PI;
+        return fr * tex4(S, m.ks, m.ks_tex, u, v, l) + tex4(S, m.kd, m.kd_tex, u, v, l) * (c4(1.0) - f) * fd / LUMO_PI;
     }
     case LMAT_MFCONDUCTOR: {                                                                                                    // bxdf/microfacet.rs:71-85
-        const C4 ks = spec4(m.ks, l);
+        const C4 ks = tex4(S, m.ks, m.ks_tex, u, v, l);
         if (mf_is_delta(m)) return ks * fresnel4(S, m, wo, d3(0, 0, 1), l) / fabs(wi.z);
         return ks * reflect_coeff(S, m, wo, wi, l);
     }
@@ -425,14 +519,14 @@ __device__ __noinline__ C4 bx_f(const DevScene& S, const Mat& m, D3 wo, D3 wi, c
         const bool flat = e == 1.0 || mf_is_delta(m);
         D3 wh = flat ? d3(0, 0, 1) : normalize(wi * ratio + wo);
         if (reflection) {
-            const C4 ks = spec4(m.ks, l);
+            const C4 ks = tex4(S, m.ks, m.ks_tex, u, v, l);
             if (flat) return ks * fresnel4(S, m, wo, wh, l) / fabs(wi.z);
             return ks * reflect_coeff(S, m, wo, wi, l);
         }
         const C4 f = fresnel4(S, m, wo, wh, l);
         if (wh.z < 0.0) wh = -wh;
         const double scale = mode == 0 ? ratio * ratio : 1.0;
-        const C4 tf = spec4(m.tf, l);
+        const C4 tf = tex4(S, m.tf, m.tf_tex, u, v, l);
         if (flat) return tf * (c4(1.0) - f) / (scale * fabs(wi.z));
         const double d = ggx_d(m, wh), g = ggx_g(m, wo, wi, wh);
         const double hwo = dot(wh, wo), hwi = dot(wh, wi);
@@ -514,7 +608,7 @@ __device__ __forceinline__ bool is_reflection(D3 wo, D3 wi, D3 ng) { return dot(
 template <int K>
 __device__ __forceinline__ C4 bsdf_f(const DevScene& S, const Mat& m, const Onb& uvw, D3 wo, D3 wi, const Lam& l, int mode, const DevHit& h) {
     if (K < 0 && !mat_is_standard(m)) return c4(0.0);
-    return bx_f<K>(S, m, to_local(uvw, wo), to_local(uvw, wi), l, is_reflection(wo, wi, h.ng), h.backface, mode);
+    return bx_f<K>(S, m, to_local(uvw, wo), to_local(uvw, wi), l, is_reflection(wo, wi, h.ng), h.backface, mode, h.u, h.v);
 }
 template <int K>
 __device__ __forceinline__ bool bsdf_sample(const DevScene& S, const Mat& m, const Onb& uvw, D3 wo, const DevHit& h, Lam& l, double ru, double r0, double r1, D3& wi) {

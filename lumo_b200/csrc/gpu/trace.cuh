@@ -25,6 +25,7 @@ struct DevScene {
     const double* normals; const double* uvs;
     const LumoRect* rects; const LumoSphere* spheres;
     const LumoMaterial* materials; const double* tables; const LumoLight* lights;
+    const LumoTexture* textures; const float* tex_pixels; const double* tex_f64;
     LumoSceneParams P;
 };
 

@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(128) k_terminal(const __grid_constant__ DevSce
             const DevHit ho = reconstruct_hit(S, ro, rec);
             const Mat& m = S.materials[ho.material];
             Lam lam; for (int k = 0; k < 4; k++) lam.l[k] = W.lam[(size_t)k * N + slot];
-            const C4 e = load_c4(W.gathered[P.cur], N, slot) * mat_emit(S, m, lam, ho.backface);
+            const C4 e = load_c4(W.gathered[P.cur], N, slot) * mat_emit(S, m, lam, ho);
             if (!is_black(e)) { C4 rad = load_c4(W.radiance, N, slot); rad = rad + e; store_c4(W.radiance, N, slot, rad); }
         }
         W.flags[slot] = PF_DONE;
@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(128, 4) k_scatter(const __grid_constant__ DevS
         Ray ro; HitRec rec; load_path(W, cur, slot, ro, rec);
         const DevHit ho = reconstruct_hit(S, ro, rec);
         const Mat& m = S.materials[ho.material];
-        const Onb uvw = onb_new(ho.ns);
+        const Onb uvw = shading_onb(S, m, ho);
         const uint32_t pixel = W.pixel[slot];
         Rng rng = rng_make(P.seed, pixel, W.sample[slot], 0u, W.draws[cur][slot]);
         Lam lam; for (int k = 0; k < 4; k++) lam.l[k] = W.lam[(size_t)k * N + slot];
@@ -464,7 +464,7 @@ __device__ __forceinline__ C4 mis_sample(const DevScene& S, const Mat& m, const 
     const double denom = p_lig * p_lig + p_sct * p_sct;
     const double weight = li ? (p_lig * p_lig) / denom : (p_sct * p_sct) / denom;
     const double p_denom = li ? p_lig : p_sct;
-    return bsdf * c4(1.0) * mat_emit(S, S.materials[hi.material], lam, hi.backface) * shading_cosine(m, wi, ho.ns) * weight / p_denom;
+    return bsdf * c4(1.0) * mat_emit(S, S.materials[hi.material], lam, hi) * shading_cosine(m, wi, ho.ns) * weight / p_denom;
 }
 
 // integrator.rs:89-137.  A shadow sample has a light-sampled term (A) and a BSDF-sampled term (B), the latter almost
@@ -488,7 +488,7 @@ __global__ void __launch_bounds__(128, 4) k_nee(const __grid_constant__ DevScene
         Ray ro; HitRec rec; load_path(W, cur, slot, ro, rec);
         const DevHit ho = reconstruct_hit(S, ro, rec);
         const Mat& m = S.materials[ho.material];
-        const Onb uvw = onb_new(ho.ns);
+        const Onb uvw = shading_onb(S, m, ho);
         const uint32_t pixel = W.pixel[slot];
         Lam lam; for (int k = 0; k < 4; k++) lam.l[k] = W.lam[(size_t)k * N + slot];   // already terminated by k_scatter if dispersive
         const C4 gathered = load_c4(W.gathered[cur], N, slot);

@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <deque>
 #include <map>
+#include <stdexcept>
 #include <string>
 #include <tuple>
 #include <vector>
@@ -25,7 +26,7 @@ namespace lumo_host {
 static thread_local std::string g_err;
 
 // ---- program reader -----------------------------------------------------------------------------
-enum { TAG_MATERIAL = 1, TAG_MESH = 2, TAG_OBJECT = 3, TAG_ENVMAP = 4, TAG_CAMERA = 5 };
+enum { TAG_MATERIAL = 1, TAG_MESH = 2, TAG_OBJECT = 3, TAG_ENVMAP = 4, TAG_CAMERA = 5, TAG_TEXTURE = 6 };
 enum { OBJ_KDMESH = 0, OBJ_RECT = 1, OBJ_SPHERE = 2, OBJ_LOOSE_TRIS = 3 };
 enum { OP_UNIT = 0, OP_ORIGIN, OP_SETX, OP_SETY, OP_SETZ, OP_TRANSLATE, OP_SCALE, OP_ROTX, OP_ROTY, OP_ROTZ };
 
@@ -90,13 +91,14 @@ struct Builder {
     std::vector<double> normals, uvs;
     std::vector<LumoRect> rects; std::vector<LumoSphere> spheres;
     std::vector<LumoMaterial> materials; std::vector<double> tables;
+    std::vector<LumoTexture> textures; std::vector<float> tex_pixels; std::vector<double> tex_f64;
     std::vector<LumoLight> lights;
     std::vector<double> light_area;
     std::vector<int32_t> light_power_mat;   // Instance::material() is the inner object's (instance.rs:146)
     std::vector<MeshIn> meshes;
     std::map<std::tuple<int64_t, int64_t, int64_t>, uint32_t> kd_cache;
     LumoSceneParams params;
-    bool have_env = false; float env_spec[4]; double env_scale = 0;
+    bool have_env = false; float env_spec[4]; double env_scale = 0; int64_t env_tex = -1;
 
     uint32_t add_table(const double* src) {
         // dedupe identical tables (constant eta/k are common)
@@ -445,6 +447,34 @@ static void fill_camera(LumoCamera& C, LumoFilm& F, Cursor& r) {
     F.r_disc = (uint32_t)sat_u64(std::ceil(fr - 0.5)); F.color_space = (uint32_t)cs; F.pad = 0;
 }
 
+// ---- Perlin::new (src/perlin.rs:31-46) ------------------------------------------------------------
+// 256 lattice normals = square_to_sphere of consecutive Xorshift pairs, then three Fisher-Yates permutations from the
+// same stream (src/rng.rs:39-116).  Appended to the f64 pool: 768 lattice values, then perm x, y, z as f64.
+struct Xorshift {
+    uint64_t hi, lo;
+    explicit Xorshift(uint64_t seed) { lo = seed > 1 ? seed : 1; hi = lo; step(); step(); step(); }               // rng.rs:40-48
+    uint64_t step() { uint64_t l = lo, h = hi; hi = l; h ^= h << 23; h ^= h >> 17; h ^= l; lo = h + l; return h; }  // rng.rs:50-59
+    double gen_float() { double v = (double)step() * std::ldexp(1.0, -64); const double lim = 1.0 - std::ldexp(1.0, -52); return v < lim ? v : lim; }   // rng.rs:71-75
+};
+static uint64_t add_perlin(std::vector<double>& pool, uint64_t seed) {
+    const uint64_t at = pool.size();
+    Xorshift rng(seed);
+    for (int i = 0; i < 256; i++) {
+        const double rx = rng.gen_float(), ry = rng.gen_float();
+        const double z = 1.0 - 2.0 * ry;                                                        // rng/maps.rs:49-55
+        const double rr = std::sqrt(std::fmax(1.0 - z * z, 0.0));
+        const double phi = 2.0 * kPi * rx;
+        pool.push_back(rr * std::cos(phi)); pool.push_back(rr * std::sin(phi)); pool.push_back(z);
+    }
+    for (int d = 0; d < 3; d++) {
+        uint64_t perm[256];
+        for (uint64_t i = 0; i < 256; i++) perm[i] = i;
+        for (uint64_t i = 0; i + 1 < 256; i++) { const uint64_t rnd = rng.step(); const uint64_t j = i + rnd % (256 - i); std::swap(perm[i], perm[j]); }   // rng.rs:104-116
+        for (uint64_t v : perm) pool.push_back((double)v);
+    }
+    return at;
+}
+
 // ---- driver -------------------------------------------------------------------------------------
 static bool run(const uint8_t* data, uint64_t len, std::vector<uint8_t>& out) {
     if (len < 16 || std::memcmp(data, "LUMOPRG1", 8) != 0) { g_err = "scene program: bad magic"; return false; }
@@ -457,8 +487,15 @@ static bool run(const uint8_t* data, uint64_t len, std::vector<uint8_t>& out) {
     struct LightArea { double area; };
     size_t off = 16;
     auto push_material = [&](int64_t kind, double rough, int64_t ek, double ec, int64_t kk, double kc, const float* kd, const float* ks, const float* tf,
-                             const float* ke, int64_t illum, double scale, int64_t two_sided) {
+                             const float* ke, int64_t illum, double scale, int64_t two_sided, const int64_t* tex /* kd ks tf ke bump, or null */) {
         LumoMaterial M; std::memset(&M, 0, sizeof M);
+        uint32_t* slots[5] = {&M.kd_tex, &M.ks_tex, &M.tf_tex, &M.ke_tex, &M.bump_tex};
+        for (int i = 0; i < 5; i++) {
+            const int64_t t = tex ? tex[i] : -1;
+            if (t >= (int64_t)B.textures.size()) throw std::runtime_error("material refers to an undefined texture");
+            if (t >= 0 && ((i == 4) != (B.textures[t].kind == LTEX_BUMP))) throw std::runtime_error("material texture slot / texture kind mismatch");
+            *slots[i] = t < 0 ? LUMO_NONE : (uint32_t)t;
+        }
         M.kind = (uint32_t)kind; M.roughness = std::fmax(rough, 1e-5);
         auto table_for = [&](int64_t k, double c) -> uint32_t {
             double tmp[95];
@@ -487,7 +524,30 @@ static bool run(const uint8_t* data, uint64_t len, std::vector<uint8_t>& out) {
             int64_t kind = r.i(); double rough = r.f(); int64_t ek = r.i(); double ec = r.f(); int64_t kk = r.i(); double kc = r.f();
             float sp[4][4]; for (auto& s : sp) for (float& v : s) v = (float)r.f();
             int64_t illum = r.i(); double scale = r.f(); int64_t ts = r.i();
-            push_material(kind, rough, ek, ec, kk, kc, sp[0], sp[1], sp[2], sp[3], illum, scale, ts);
+            int64_t tex[5] = {-1, -1, -1, -1, -1};
+            if (nbytes >= 30 * 8) for (int64_t& t : tex) t = r.i();
+            push_material(kind, rough, ek, ec, kk, kc, sp[0], sp[1], sp[2], sp[3], illum, scale, ts, tex);
+        } else if (tag == TAG_TEXTURE) {
+            LumoTexture T; std::memset(&T, 0, sizeof T);
+            T.kind = (uint32_t)r.i();
+            for (float& v : T.spec) v = (float)r.f();
+            const int64_t a = r.i(), b = r.i(); T.scale = r.f();
+            const int64_t seed = r.i(), w = r.i(), h = r.i();
+            T.a = T.b = LUMO_NONE;
+            if (T.kind == LTEX_CHECKER) {
+                if (a < 0 || b < 0 || a >= (int64_t)B.textures.size() || b >= (int64_t)B.textures.size()) throw std::runtime_error("checkerboard refers to an undefined texture");
+                if (B.textures[a].kind == LTEX_BUMP || B.textures[b].kind == LTEX_BUMP) throw std::runtime_error("checkerboard of a bump map");
+                T.a = (uint32_t)a; T.b = (uint32_t)b;
+            } else if (T.kind == LTEX_MARBLE) {
+                T.data = add_perlin(B.tex_f64, (uint64_t)seed);
+            } else if (T.kind == LTEX_IMAGE || T.kind == LTEX_BUMP) {
+                const int64_t per = T.kind == LTEX_IMAGE ? 4 : 3;
+                if (w <= 0 || h <= 0 || (uint64_t)(11 * 8 + w * h * per * 8) > nbytes) throw std::runtime_error("image texture: bad size");
+                T.width = (uint32_t)w; T.height = (uint32_t)h;
+                if (T.kind == LTEX_IMAGE) { T.data = B.tex_pixels.size() / 4; for (int64_t i = 0; i < w * h * 4; i++) B.tex_pixels.push_back((float)r.f()); }
+                else { T.data = B.tex_f64.size(); for (int64_t i = 0; i < w * h * 3; i++) B.tex_f64.push_back(r.f()); }
+            } else if (T.kind != LTEX_SOLID && T.kind != LTEX_MANDELBROT) throw std::runtime_error("unknown texture kind");
+            B.textures.push_back(T);
         } else if (tag == TAG_MESH) {
             MeshIn m;
             m.nv = r.i(); m.nn = r.i(); m.nt = r.i(); m.nf = r.i(); m.nc = r.i(); int64_t hn = r.i(), ht = r.i();
@@ -597,6 +657,7 @@ static bool run(const uint8_t* data, uint64_t len, std::vector<uint8_t>& out) {
         } else if (tag == TAG_ENVMAP) {
             for (float& v : B.env_spec) v = (float)r.f();
             B.env_scale = r.f(); B.have_env = true;
+            if (nbytes >= 6 * 8) B.env_tex = r.i();
         } else if (tag == TAG_CAMERA) {
             fill_camera(B.params.camera, B.params.film, r); have_camera = true;
         }
@@ -618,7 +679,8 @@ static bool run(const uint8_t* data, uint64_t len, std::vector<uint8_t>& out) {
         V3 c = center(bounds);
         double radius = length(sub(c, bounds.lo));   // Vec3::distance
         float z4[4] = {0, 0, 0, 0};
-        push_material(LMAT_LIGHT, 1.0, 0, 0.0, 0, 0.0, z4, z4, z4, B.env_spec, 2 /* D65 */, B.env_scale, 1);   // scene.rs:73-77
+        const int64_t env_tex[5] = {-1, -1, -1, B.env_tex, -1};
+        push_material(LMAT_LIGHT, 1.0, 0, 0.0, 0, 0.0, z4, z4, z4, B.env_spec, 2 /* D65 */, B.env_scale, 1, env_tex);   // scene.rs:73-77
         LumoSphere S = {radius, 0.0}; B.spheres.push_back(S);
         Xform t = compose(Xform::translation(c.x, c.y, c.z), Xform::identity());
         LumoObject o; std::memset(&o, 0, sizeof o); o.kind = LOBJ_SPHERE; o.geom = (uint32_t)B.spheres.size() - 1;
@@ -644,7 +706,13 @@ static bool run(const uint8_t* data, uint64_t len, std::vector<uint8_t>& out) {
             for (int k = 0; k < 4; k++) {
                 double phi = 0.0;
                 if (M.kind == LMAT_LIGHT) {                                                      // material.rs:234-242
-                    phi = M.scale * spectrum_sample(M.ke, lam[k]) * dense_sample(&B.tables[96 * M.illum_table], lam[k]);
+                    const float* ke = M.ke;
+                    if (M.ke_tex != LUMO_NONE) {                                                 // Texture::power (texture.rs:95-101)
+                        const LumoTexture& T = B.textures[M.ke_tex];
+                        if (T.kind != LTEX_SOLID && T.kind != LTEX_IMAGE) { g_err = "light texture has no power (only Solid and Image do, texture.rs:95-101)"; return false; }
+                        ke = T.spec;
+                    }
+                    phi = M.scale * spectrum_sample(ke, lam[k]) * dense_sample(&B.tables[96 * M.illum_table], lam[k]);
                     if (M.flags & LMF_TWO_SIDED) phi = 2.0 * phi;
                 }
                 double pw = B.light_area[i] * phi;
@@ -697,6 +765,9 @@ static bool run(const uint8_t* data, uint64_t len, std::vector<uint8_t>& out) {
         {B.materials.data(), B.materials.size() * sizeof(LumoMaterial), B.materials.size()},
         {B.tables.data(), B.tables.size() * 8, B.tables.size() / 96},
         {B.lights.data(), B.lights.size() * sizeof(LumoLight), B.lights.size()},
+        {B.textures.data(), B.textures.size() * sizeof(LumoTexture), B.textures.size()},
+        {B.tex_pixels.data(), B.tex_pixels.size() * 4, B.tex_pixels.size() / 4},
+        {B.tex_f64.data(), B.tex_f64.size() * 8, B.tex_f64.size()},
     };
     LumoBlobHeader H; std::memset(&H, 0, sizeof H);
     H.magic = LUMO_BLOB_MAGIC; H.version = LUMO_BLOB_VERSION; H.n_sections = LSEC_COUNT; H.params = P;

@@ -10,7 +10,7 @@ HOST_SO = os.path.join(HERE, "liblumo_host.so")
 GPU_SO = os.environ.get("LUMO_GPU_SO", os.path.join(HERE, "liblumo_gpu.so"))   # override: A/B timing of two builds
 
 SECTIONS = ["tlas_nodes", "tlas_leaf", "objects", "instances", "kd_trees", "kd_nodes", "kd_leaf", "tri_verts", "tri_shade",
-            "normals", "uvs", "rects", "spheres", "materials", "tables", "lights"]
+            "normals", "uvs", "rects", "spheres", "materials", "tables", "lights", "textures", "tex_pixels", "tex_f64"]
 
 TLAS_NODE = np.dtype([("lo", "<f8", 3), ("hi", "<f8", 3), ("right", "<u4"), ("first", "<u4"), ("count", "<u4"), ("pad", "<u4")])
 OBJECT = np.dtype([("kind", "<u4"), ("geom", "<u4"), ("inst", "<i4"), ("material", "<i4"), ("rect", "<u4"), ("pad", "<u4", 3)])
@@ -22,7 +22,10 @@ TRI_SHADE = np.dtype([("n", "<u4", 3), ("t", "<u4", 3), ("flags", "<u4"), ("pad"
 RECT = np.dtype([("origin", "<f8", 3), ("b0", "<f8", 3), ("b1", "<f8", 3), ("pad", "<f8")])
 SPHERE = np.dtype([("radius", "<f8"), ("pad", "<f8")])
 MATERIAL = np.dtype([("kind", "<u4"), ("flags", "<u4"), ("roughness", "<f8"), ("kd", "<f4", 4), ("ks", "<f4", 4), ("tf", "<f4", 4), ("ke", "<f4", 4),
-                     ("eta_table", "<u4"), ("k_table", "<u4"), ("illum_table", "<u4"), ("pad", "<u4"), ("scale", "<f8"), ("pad2", "<f8")])
+                     ("eta_table", "<u4"), ("k_table", "<u4"), ("illum_table", "<u4"), ("kd_tex", "<u4"), ("scale", "<f8"),
+                     ("ks_tex", "<u4"), ("tf_tex", "<u4"), ("ke_tex", "<u4"), ("bump_tex", "<u4"), ("pad", "<u8")])
+TEXTURE = np.dtype([("kind", "<u4"), ("a", "<u4"), ("b", "<u4"), ("width", "<u4"), ("height", "<u4"), ("pad", "<u4"), ("data", "<u8"),
+                    ("spec", "<f4", 4), ("scale", "<f8"), ("pad2", "<f8")])
 LIGHT = np.dtype([("alias_prob", "<f8"), ("pdf", "<f8"), ("area", "<f8"), ("alias", "<u4"), ("pad", "<u4")])
 CAMERA = np.dtype([("screen_to_raster_m", "<f8", 16), ("screen_to_raster_inv", "<f8", 16), ("camera_to_screen_m", "<f8", 16),
                    ("camera_to_screen_inv", "<f8", 16), ("world_to_camera_m", "<f8", 16), ("world_to_camera_inv", "<f8", 16),
@@ -38,7 +41,8 @@ HEADER = np.dtype([("magic", "<u8"), ("version", "<u4"), ("n_sections", "<u4"), 
                    ("params", PARAMS), ("sec", SECREF, len(SECTIONS))])
 _SEC_DTYPES = {"tlas_nodes": TLAS_NODE, "tlas_leaf": np.dtype("<u4"), "objects": OBJECT, "instances": INSTANCE, "kd_trees": KD_TREE,
                "kd_nodes": KD_NODE, "kd_leaf": np.dtype("<u4"), "tri_verts": TRI_VERTS, "tri_shade": TRI_SHADE, "normals": np.dtype(("<f8", 3)),
-               "uvs": np.dtype(("<f8", 2)), "rects": RECT, "spheres": SPHERE, "materials": MATERIAL, "tables": np.dtype(("<f8", 96)), "lights": LIGHT}
+               "uvs": np.dtype(("<f8", 2)), "rects": RECT, "spheres": SPHERE, "materials": MATERIAL, "tables": np.dtype(("<f8", 96)), "lights": LIGHT,
+               "textures": TEXTURE, "tex_pixels": np.dtype(("<f4", 4)), "tex_f64": np.dtype("<f8")}
 
 
 class Blob:
@@ -194,10 +198,10 @@ class GpuScene:
     def __init__(self, ctx, blob_bytes, host_ptr=None):
         """blob_bytes: the scene blob; host_ptr: optional address of a (e.g. pinned) host copy of the same bytes to upload from."""
         self.ctx = ctx
-        self.blob = Blob(blob_bytes)
         self.h = C.c_void_p()
         src = C.c_char_p(blob_bytes) if host_ptr is None else C.cast(C.c_void_p(host_ptr), C.c_char_p)
-        _check(gpu_lib().lumo_gpu_scene_upload(ctx.h, src, len(blob_bytes), C.byref(self.h)), "lumo_gpu_scene_upload")
+        _check(gpu_lib().lumo_gpu_scene_upload(ctx.h, src, len(blob_bytes), C.byref(self.h)), "lumo_gpu_scene_upload")   # validates the blob
+        self.blob = Blob(blob_bytes)
         cam = self.blob.params["camera"]
         self.res_x, self.res_y = int(cam["res_x"]), int(cam["res_y"])
 

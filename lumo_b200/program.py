@@ -8,12 +8,15 @@ BVHs with lumo's algorithms and flattens everything into the device scene blob.
 
 Layout: magic "LUMOPRG1", u32 version, u32 n_records, then records
   u32 tag, u32 0, u64 nbytes, payload (8-byte words: i64 or f64).
+Texture records (src/tracer/texture.rs:23-38) precede the materials that use them; a material / environment-map
+record may end with texture ids (-1 = the Solid spectrum given inline), older programs simply end earlier.
 """
 import struct
 import numpy as np
 
 MAGIC = b"LUMOPRG1"
-TAG_MATERIAL, TAG_MESH, TAG_OBJECT, TAG_ENVMAP, TAG_CAMERA = 1, 2, 3, 4, 5
+TAG_MATERIAL, TAG_MESH, TAG_OBJECT, TAG_ENVMAP, TAG_CAMERA, TAG_TEXTURE = 1, 2, 3, 4, 5, 6
+TEX_SOLID, TEX_CHECKER, TEX_MARBLE, TEX_IMAGE, TEX_MANDELBROT, TEX_BUMP = range(6)
 OBJ_KDMESH, OBJ_RECT, OBJ_SPHERE, OBJ_LOOSE_TRIS = 0, 1, 2, 3
 (OP_UNIT, OP_ORIGIN, OP_SETX, OP_SETY, OP_SETZ, OP_TRANSLATE, OP_SCALE, OP_ROTX, OP_ROTY, OP_ROTZ) = range(10)
 # material kinds
@@ -38,17 +41,20 @@ class ProgramWriter:
         self.records = []
         self.n_materials = 0
         self.n_meshes = 0
+        self.n_textures = 0
 
     def _rec(self, tag, payload):
         assert len(payload) % 8 == 0
         self.records.append(struct.pack("<IIQ", tag, 0, len(payload)) + payload)
 
     def material(self, kind, roughness=1.0, eta_kind=ETA_CONST, eta=1.5, k_kind=ETA_CONST, k=0.0,
-                 kd=(0, 0, 0, 0), ks=(0, 0, 0, 0), tf=(0, 0, 0, 0), ke=(0, 0, 0, 0), illuminant=2, scale=1.0, two_sided=0):
+                 kd=(0, 0, 0, 0), ks=(0, 0, 0, 0), tf=(0, 0, 0, 0), ke=(0, 0, 0, 0), illuminant=2, scale=1.0, two_sided=0,
+                 kd_tex=-1, ks_tex=-1, tf_tex=-1, ke_tex=-1, bump_tex=-1):
         p = _w(int(kind), float(roughness), int(eta_kind), float(eta), int(k_kind), float(k))
         for s in (kd, ks, tf, ke):
             p += _w(*[float(v) for v in s])
         p += _w(int(illuminant), float(scale), int(two_sided))
+        p += _w(int(kd_tex), int(ks_tex), int(tf_tex), int(ke_tex), int(bump_tex))
         self._rec(TAG_MATERIAL, p)
         self.n_materials += 1
         return self.n_materials - 1
@@ -91,8 +97,18 @@ class ProgramWriter:
             p += _w(int(o[0]), float(o[1]), float(o[2]), float(o[3]))
         self._rec(TAG_OBJECT, p)
 
-    def envmap(self, spec, scale):
-        self._rec(TAG_ENVMAP, _w(*[float(v) for v in spec], float(scale)))
+    def envmap(self, spec, scale, tex=-1):
+        self._rec(TAG_ENVMAP, _w(*[float(v) for v in spec], float(scale), int(tex)))
+
+    def texture(self, kind, spec=(0, 0, 0, 0), a=-1, b=-1, scale=1.0, seed=0, width=0, height=0, data=None):
+        """kind TEX_*; spec: Solid / Marble colour, Image mean; a, b, scale: Checkerboard; seed: Marble (Perlin::new);
+        data: Image -> float array [H, W, 4] of Spectrum coefficients, Bump -> float array [H, W, 3] of unit normals."""
+        p = _w(int(kind), *[float(v) for v in spec], int(a), int(b), float(scale), int(seed), int(width), int(height))
+        if data is not None:
+            p += np.ascontiguousarray(data, dtype=np.float64).tobytes()
+        self._rec(TAG_TEXTURE, p)
+        self.n_textures += 1
+        return self.n_textures - 1
 
     def camera(self, origin, towards, up, zoom, lens_radius, focal_length, vfov, resolution, camera_type,
                filter_kind, filter_r, filter_p, color_space, illuminant):

@@ -139,4 +139,42 @@ def bistro(n_chunks=1024, tris_per_chunk=1024, n_emissive=4096, resolution=(1920
     return s, cam, Integrator.PathTrace
 
 
-CONFIGS = {"cornell": cornell, "bunny": bunny, "dragon": dragon, "caustics": caustics, "conference": conference, "bistro": bistro}
+def textured(n_tris=2048, resolution=(256, 192)):
+    """Not a reference example: the empty box with every `Texture` kind (texture.rs:23-38) and a bump map
+    (material.rs:14) on its surfaces, a uv-mapped mesh, an image-textured light and an image environment map.
+    The parity tests and `bench.py --workload textured` use it to exercise the texture / bump path."""
+    from .image import Image
+    rs = np.random.RandomState(5)
+    palette = np.array([[230, 60, 50], [40, 170, 90], [60, 90, 220], [240, 220, 80], [250, 250, 250], [30, 30, 30]], np.uint8)
+    img = Image.from_rgb8(palette[rs.randint(0, len(palette), size=(12, 16))])
+    warm = Image.from_rgb8(np.array([[252, 201, 138], [255, 240, 220]], np.uint8)[rs.randint(0, 2, size=(4, 4))])
+    sky = Image.from_rgb8(np.array([[20, 24, 40], [60, 80, 140]], np.uint8)[(np.arange(8)[:, None] + np.arange(16)[None, :]) % 2])
+    yy, xx = np.mgrid[0:16, 0:16]
+    bump_rgb = np.stack([128 + 60 * np.sin(xx * 0.9), 128 + 60 * np.cos(yy * 0.7), np.full(xx.shape, 230.0)], -1).astype(np.uint8)
+    bump = Image.bump_from_rgb8(bump_rgb)
+    white = Spectrum.from_srgb(242, 242, 242)
+    checker = Texture.Checkerboard(Texture.Solid(white), Texture.Marble(7, Spectrum.RED()), 6.0)
+    nested = Texture.Checkerboard(Texture.Image(img), Texture.Checkerboard(Spectrum.CYAN(), Texture.Mandelbrot(), 3.0), 2.0)
+    LIGHT_EPS = 0.001
+    ground = -0.8; ceiling = -ground; right = 1.0; left = -right; front = -2.0; back = 0.0; l_dim = 0.25
+    s = Scene()
+    s.add_light(Rectangle((-l_dim, ceiling - LIGHT_EPS, 0.6 * front + l_dim), (-l_dim, ceiling - LIGHT_EPS, 0.6 * front - l_dim),
+                          (l_dim, ceiling - LIGHT_EPS, 0.6 * front - l_dim), Material.light_scale(Texture.Image(warm), 1.0)))
+    s.add(Rectangle((left, ground, back), (left, ground, front), (left, ceiling, front), Material.diffuse(Texture.Image(img))))
+    s.add(Rectangle((right, ground, front), (right, ground, back), (right, ceiling, back), Material.diffuse(Texture.Mandelbrot())))
+    s.add(Rectangle((left, ground, back), (right, ground, back), (right, ground, front), Material.diffuse(checker)))
+    s.add(Rectangle((left, ceiling, front), (right, ceiling, front), (right, ceiling, back), Material.diffuse(white)))
+    s.add(Rectangle((left, ground, front), (right, ground, front), (right, ceiling, front),
+                    Material.microfacet(0.6, 1.5, 0.0, False, False, nested, Spectrum.WHITE(), Spectrum.BLACK(), bump_map=bump)))
+    s.add(Sphere(0.3, Material.metal(Texture.Marble(11, Spectrum.YELLOW()), 0.15, 2.5, 3.0)).translate(-0.45, ground + 0.3, -1.3))
+    s.add(Sphere(0.25, Material.microfacet(0.05, 1.5, 0.0, True, True, Spectrum.BLACK(), Spectrum.WHITE(), Texture.Image(img), bump_map=bump)).translate(0.5, ground + 0.25, -1.0))
+    v, f = meshes.displaced_sphere(n_tris, seed=3, amplitude=0.2)
+    uv = np.stack([0.5 + np.arctan2(v[:, 2], v[:, 0]) / (2 * np.pi), 0.5 + np.arcsin(np.clip(v[:, 1] / np.linalg.norm(v, axis=1), -1, 1)) / np.pi], -1)
+    m = TriangleMesh.new(np.asarray(v, np.float64), np.asarray(f, np.int64), [], uv, Material.microfacet(0.4, 1.5, 0.0, False, False, checker, Texture.Image(img), Spectrum.BLACK(), bump_map=bump))
+    m.face_uvs = np.asarray(f, np.int64)
+    s.add(m.to_unit_size().to_origin().scale_uniform(0.5).translate(0.1, 0.1, -1.6))
+    s.set_environment_map(Texture.Image(sky), 0.5)
+    return s, _box(resolution), Integrator.PathTrace
+
+
+CONFIGS = {"cornell": cornell, "bunny": bunny, "dragon": dragon, "caustics": caustics, "conference": conference, "bistro": bistro, "textured": textured}

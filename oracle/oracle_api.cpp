@@ -24,7 +24,7 @@ struct Reader {
     int64_t i64() { int64_t v; std::memcpy(&v, p + off, 8); off += 8; return v; }
     double f64() { double v; std::memcpy(&v, p + off, 8); off += 8; return v; }
 };
-enum { TAG_MATERIAL = 1, TAG_MESH = 2, TAG_OBJECT = 3, TAG_ENVMAP = 4, TAG_CAMERA = 5 };
+enum { TAG_MATERIAL = 1, TAG_MESH = 2, TAG_OBJECT = 3, TAG_ENVMAP = 4, TAG_CAMERA = 5, TAG_TEXTURE = 6 };
 enum { OBJ_KDMESH = 0, OBJ_RECT = 1, OBJ_SPHERE = 2, OBJ_LOOSE_TRIS = 3 };
 enum { OP_UNIT = 0, OP_ORIGIN = 1, OP_SETX = 2, OP_SETY = 3, OP_SETZ = 4, OP_TRANSLATE = 5, OP_SCALE = 6, OP_ROTX = 7, OP_ROTY = 8, OP_ROTZ = 9 };
 
@@ -34,6 +34,7 @@ struct Loaded {
     Scene scene;
     Camera camera;
     std::vector<MeshSrc> mesh_src;
+    std::vector<std::unique_ptr<Texture>> textures;
     std::map<std::tuple<int64_t, int64_t, int64_t, int64_t>, std::shared_ptr<KdTree>> kd_cache;
     std::string err;
 };
@@ -92,7 +93,26 @@ static Loaded* load_program(const uint8_t* data, size_t len) {
             m->spec = m->kd;
             m->illum = illuminant_table((int)r.i64());
             m->scale = r.f64(); m->two_sided = r.i64() != 0;
+            if (nbytes >= 30 * 8) {
+                const Texture** slots[5] = {&m->kd_tex, &m->ks_tex, &m->tf_tex, &m->ke_tex, &m->bump_tex};
+                for (auto slot : slots) { int64_t t = r.i64(); *slot = t < 0 ? nullptr : L->textures.at((size_t)t).get(); }
+            }
             sc.materials.push_back(std::move(m));
+        } else if (tag == TAG_TEXTURE) {
+            auto t = std::make_unique<Texture>();
+            t->kind = (int)r.i64(); t->spec = read_spec(r);
+            int64_t a = r.i64(), b = r.i64(); t->scale = r.f64();
+            int64_t seed = r.i64(), w = r.i64(), h = r.i64();
+            if (t->kind == TEX_CHECKER) { t->t1 = L->textures.at((size_t)a).get(); t->t2 = L->textures.at((size_t)b).get(); }
+            else if (t->kind == TEX_MARBLE) t->pn = std::make_unique<Perlin>((uint64_t)seed);
+            else if (t->kind == TEX_IMAGE) {
+                t->img.width = (uint32_t)w; t->img.height = (uint32_t)h;
+                for (int64_t i = 0; i < w * h; i++) t->img.buffer.push_back(read_spec(r));
+            } else if (t->kind == TEX_BUMP) {
+                t->bump.width = (uint32_t)w; t->bump.height = (uint32_t)h;
+                for (int64_t i = 0; i < w * h; i++) { Float x = r.f64(), y = r.f64(), z = r.f64(); t->bump.buffer.push_back(Vec3(x, y, z)); }
+            }
+            L->textures.push_back(std::move(t));
         } else if (tag == TAG_MESH) {
             int64_t nv = r.i64(), nn = r.i64(), nt = r.i64(), nf = r.i64(), nc = r.i64(), has_n = r.i64(), has_t = r.i64();
             auto tm = std::make_unique<TriangleMesh>();
@@ -161,6 +181,7 @@ static Loaded* load_program(const uint8_t* data, size_t len) {
         } else if (tag == TAG_ENVMAP) {
             auto m = std::make_unique<Material>();
             m->kind = M_LIGHT; m->ke = read_spec(r); m->scale = r.f64(); m->illum = spectra::D65; m->two_sided = true;  // scene.rs:73-77
+            if (nbytes >= 6 * 8) { int64_t t = r.i64(); if (t >= 0) m->ke_tex = L->textures.at((size_t)t).get(); }
             sc.env = m.get();
             sc.materials.push_back(std::move(m));
         } else if (tag == TAG_CAMERA) {
@@ -675,6 +696,27 @@ void oracle_bsdf_chi2_tables(void* h, int mat, const double* wo3, double lambda_
 }
 
 // ---- unit hooks used by the property tests ------------------------------------------------------
+// ---- textures (texture.rs, perlin.rs, image.rs) evaluated directly, for the texture property tests
+uint64_t oracle_texture_count(void* h) { return ((Loaded*)h)->textures.size(); }
+int oracle_texture_kind(void* h, uint64_t tex) { return ((Loaded*)h)->textures.at(tex)->kind; }
+void oracle_texture_eval(void* h, uint64_t tex, const double* uv, uint64_t n, double lambda_u, double* out4) {
+    const Texture* t = ((Loaded*)h)->textures.at(tex).get();
+    Lambda lam = Lambda::sample(lambda_u);
+    for (uint64_t i = 0; i < n; i++) { Color c = t->albedo_at(lam, Vec2(uv[2 * i], uv[2 * i + 1])); for (int k = 0; k < 4; k++) out4[4 * i + k] = c.s[k]; }
+}
+void oracle_bump_eval(void* h, uint64_t tex, const double* uv, uint64_t n, double* out3) {
+    const Texture* t = ((Loaded*)h)->textures.at(tex).get();
+    for (uint64_t i = 0; i < n; i++) { Vec3 v = t->bump.value_at(Vec2(uv[2 * i], uv[2 * i + 1])); out3[3 * i] = v.x; out3[3 * i + 1] = v.y; out3[3 * i + 2] = v.z; }
+}
+void oracle_perlin_noise(uint64_t seed, const double* p3, uint64_t n, double* out) {
+    Perlin pn(seed);
+    for (uint64_t i = 0; i < n; i++) out[i] = pn.noise_at(Vec3(p3[3 * i], p3[3 * i + 1], p3[3 * i + 2]));
+}
+void oracle_perlin_tables(uint64_t seed, double* out1536) {   // lattice (768) then perm x, y, z: the layout of the device blob's f64 pool
+    Perlin pn(seed);
+    for (int i = 0; i < 256; i++) { out1536[3 * i] = pn.lattice[i].x; out1536[3 * i + 1] = pn.lattice[i].y; out1536[3 * i + 2] = pn.lattice[i].z; }
+    for (int i = 0; i < 256; i++) { out1536[768 + i] = (double)pn.px[i]; out1536[1024 + i] = (double)pn.py[i]; out1536[1280 + i] = (double)pn.pz[i]; }
+}
 double oracle_lambda_sample_one(double v) { return Lambda::sample_one(v); }
 void oracle_xorshift(uint64_t seed, uint64_t n, uint64_t* out) { Rng r = Rng::xorshift(seed); for (uint64_t i = 0; i < n; i++) out[i] = r.gen_u64(); }
 void oracle_philox(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t stream, uint64_t n, uint64_t* out) { Rng r = Rng::counter(seed, pixel, sample, stream); for (uint64_t i = 0; i < n; i++) out[i] = r.gen_u64(); }

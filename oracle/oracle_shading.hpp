@@ -113,6 +113,117 @@ struct Spectrum {
     Color sample(const Lambda& lam) const { Color c; for (int i = 0; i < 4; i++) c.s[i] = sample_one(lam.l[i]); return c; }
 };
 
+// ---- Textures (src/tracer/texture.rs, src/perlin.rs, src/image.rs) ------------------------------
+struct Perlin {                                                                                   // perlin.rs:14-46
+    std::vector<Vec3> lattice; std::vector<size_t> px, py, pz;
+    explicit Perlin(uint64_t seed) {
+        Rng rng = Rng::xorshift(seed);
+        for (int i = 0; i < 256; i++) lattice.push_back(square_to_sphere(rng.gen_vec2()));
+        px = gen_perm(rng); py = gen_perm(rng); pz = gen_perm(rng);
+    }
+    static std::vector<size_t> gen_perm(Rng& rng) {                                               // rng.rs:104-116
+        const size_t n = 256;
+        std::vector<size_t> perm(n);
+        for (size_t i = 0; i < n; i++) perm[i] = i;
+        for (size_t i = 0; i < n - 1; i++) { size_t rnd = (size_t)rng.gen_u64(); size_t j = i + (rnd % (n - i)); std::swap(perm[i], perm[j]); }
+        return perm;
+    }
+    size_t hash(size_t x, size_t y, size_t z) const { return px[x % 256] ^ py[y % 256] ^ pz[z % 256]; }   // perlin.rs:71-75
+    Float noise_at(Vec3 p) const {                                                                // perlin.rs:50-68
+        Vec3 weight(fract(p.x), fract(p.y), fract(p.z));
+        Vec3 fl = p.floor();
+        Vec3 normals[8];
+        int n = 0;
+        for (size_t i = 0; i < 2; i++) for (size_t j = 0; j < 2; j++) for (size_t k = 0; k < 2; k++)
+            normals[n++] = lattice[hash((size_t)sat_u64(fl.x) + i, (size_t)sat_u64(fl.y) + j, (size_t)sat_u64(fl.z) + k)];
+        auto ss = [](Float x) { return ((6.0 * x - 15.0) * x + 10.0) * x * x * x; };              // _smootherstep, perlin.rs:83-85
+        const Vec3 w(ss(weight.x), ss(weight.y), ss(weight.z));
+        Float acc = 0.0;                                                                          // interp, perlin.rs:92-109
+        n = 0;
+        for (int xi = 0; xi < 2; xi++) for (int yi = 0; yi < 2; yi++) for (int zi = 0; zi < 2; zi++) {
+            const Vec3 idx((Float)xi, (Float)yi, (Float)zi);
+            const Vec3 widx = 2.0 * w * idx + Vec3(1, 1, 1) - w - idx;
+            acc = acc + widx.x * widx.y * widx.z * normals[n++].dot(w - idx);
+        }
+        return acc;
+    }
+};
+struct ImageSpectrum {                                                                            // image.rs:8-16, 99-199
+    std::vector<Spectrum> buffer; uint32_t width = 0, height = 0;
+    static uint32_t sat_u32(Float v) { uint64_t u = sat_u64(v); return u > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)u; }
+    // bilin_interp (image.rs:99-131): texel indices and the two weights
+    void taps(Vec2 uv, uint32_t& xo, uint32_t& yo, uint32_t& xi, uint32_t& yi, Float& wx, Float& wy) const {
+        const Float w = (Float)width, h = (Float)height;
+        const Vec2 xy(uv.x * w, (1.0 - uv.y) * h);
+        const Vec2 xoyo(std::floor(xy.x - 0.5), std::floor(xy.y - 0.5));
+        const Vec2 x1y1(xy.x - xoyo.x - 0.5, xy.y - xoyo.y - 0.5);
+        wx = 1.0 - x1y1.x; wy = 1.0 - x1y1.y;
+        xo = sat_u32(xoyo.x + w) % width; yo = sat_u32(xoyo.y + h) % height;
+        xi = (xo + 1) % width; yi = (yo + 1) % height;
+    }
+    Color value_at(Vec2 uv, const Lambda& lam) const {                                            // image.rs:184-193
+        uint32_t xo, yo, xi, yi; Float wx, wy;
+        taps(uv, xo, yo, xi, yi, wx, wy);
+        auto lerp = [&](const Spectrum& s0, const Spectrum& s1, Float v) { return s0.sample(lam) * v + s1.sample(lam) * (1.0 - v); };
+        const Color y0 = lerp(buffer[xo + yo * width], buffer[xi + yo * width], wx);
+        const Color y1 = lerp(buffer[xo + yi * width], buffer[xi + yi * width], wx);
+        return y0 * wy + y1 * (1.0 - wy);
+    }
+};
+struct ImageNormal {                                                                              // image.rs:134-181
+    std::vector<Vec3> buffer; uint32_t width = 0, height = 0;
+    Vec3 value_at(Vec2 uv) const {
+        ImageSpectrum g; g.width = width; g.height = height;
+        uint32_t xo, yo, xi, yi; Float wx, wy;
+        g.taps(uv, xo, yo, xi, yi, wx, wy);
+        auto lerp = [](Vec3 n0, Vec3 n1, Float v) { return (n0 * v + n1 * (1.0 - v)).normalize(); };
+        const Vec3 y0 = lerp(buffer[xo + yo * width], buffer[xi + yo * width], wx);
+        const Vec3 y1 = lerp(buffer[xo + yi * width], buffer[xi + yi * width], wx);
+        return lerp(y0, y1, wy);
+    }
+};
+enum TexKind { TEX_SOLID = 0, TEX_CHECKER = 1, TEX_MARBLE = 2, TEX_IMAGE = 3, TEX_MANDELBROT = 4, TEX_BUMP = 5 };
+struct Texture {                                                                                  // texture.rs:23-38
+    int kind = TEX_SOLID;
+    Spectrum spec;                       // Solid / Marble colour; Image: mean
+    const Texture *t1 = nullptr, *t2 = nullptr; Float scale = 1.0;
+    std::unique_ptr<Perlin> pn;
+    ImageSpectrum img; ImageNormal bump;
+    static Float turbulence(const Perlin& pn, Float acc, Vec3 p, int depth) {                     // texture.rs:105-112
+        if (depth >= 6) return acc;
+        const Float w = powi(0.5, depth);
+        return turbulence(pn, acc + w * std::fabs(pn.noise_at(p)), 2.0 * p, depth + 1);
+    }
+    Color albedo_at(const Lambda& lam, Vec2 uv) const {                                           // texture.rs:53-92
+        switch (kind) {
+        case TEX_MARBLE: {
+            const Vec3 uvw(uv.x, uv.y, 0.0);
+            const Float turb = turbulence(*pn, 0.0, 4.0 * uvw.abs(), 0);
+            const Float scaled = 1.0 - powi(0.5 + 0.5 * std::sin(60.0 * uvw.x + 20.0 * turb), 6);
+            return spec.sample(lam) * scaled;
+        }
+        case TEX_CHECKER: {
+            const Vec2 uvs = uv * scale;
+            return (sat_u64(std::floor(uvs.x) + std::floor(uvs.y)) % 2 == 0) ? t1->albedo_at(lam, uv) : t2->albedo_at(lam, uv);
+        }
+        case TEX_IMAGE: return img.value_at(uv, lam);
+        case TEX_MANDELBROT: {
+            int depth = 0;
+            const Float cre = 2.0 * (uv.x - 0.75), cim = 2.0 * (uv.y - 0.5);
+            Float zre = 0.0, zim = 0.0;
+            while (depth < 256 && zre * zre + zim * zim < 64.0 * 64.0) {
+                const Float nre = zre * zre - zim * zim, nim = zre * zim + zim * zre;            // complex.rs Mul
+                zre = nre + cre; zim = nim + cim;
+                depth++;
+            }
+            return depth == 256 ? WHITE : BLACK;
+        }
+        default: return spec.sample(lam);
+        }
+    }
+    Color power(const Lambda& lam) const { return spec.sample(lam); }                             // texture.rs:95-101 (Solid; Image: mean)
+};
+
 // ---- Materials (src/tracer/material.rs, bsdf.rs, bxdf.rs, microfacet.rs, bxdf/*.rs) -----------
 enum MatKind { M_BLANK = 0, M_LAMBERTIAN = 1, M_MFDIFFUSE = 2, M_MFCONDUCTOR = 3, M_MFDIELECTRIC = 4, M_LIGHT = 5 };
 struct Material {
@@ -121,8 +232,17 @@ struct Material {
     Vec2 roughness;                // MicrofacetConfig (microfacet.rs:6-37); only Ggx is ever constructed (:51-60)
     DenseSpectrum eta, k;
     bool eta_const = true;
-    Spectrum kd, ks, tf;           // Texture::Solid only (Image textures: SURVEY §8f-2)
+    Spectrum kd, ks, tf;           // Texture::Solid spectra, unless the matching *_tex below is set
     Spectrum ke; const double* illum = nullptr; Float scale = 1.0; bool two_sided = false;   // Light
+    const Texture *kd_tex = nullptr, *ks_tex = nullptr, *tf_tex = nullptr, *ke_tex = nullptr, *bump_tex = nullptr;
+    Color kd_at(const Lambda& lam, Vec2 uv) const { return kd_tex ? kd_tex->albedo_at(lam, uv) : kd.sample(lam); }   // microfacet.rs:120-134
+    Color ks_at(const Lambda& lam, Vec2 uv) const { return ks_tex ? ks_tex->albedo_at(lam, uv) : ks.sample(lam); }
+    Color tf_at(const Lambda& lam, Vec2 uv) const { return tf_tex ? tf_tex->albedo_at(lam, uv) : tf.sample(lam); }
+    Vec3 map_normal(Vec3 ns, Vec2 uv) const {                                                 // material.rs:324-331
+        if (!bump_tex) return ns;
+        Onb onb(ns);
+        return onb.to_world(bump_tex->bump.value_at(uv)).normalize();
+    }
 
     bool mf_is_specular() const { return (roughness.x + roughness.y) / 2.0 < 0.01; }          // microfacet.rs:73-76
     bool mf_is_delta() const { return (roughness.x + roughness.y) / 2.0 < 1e-3; }             // microfacet.rs:80-83
@@ -146,11 +266,11 @@ struct Material {
     Color emit(const Lambda& lam, const Hit& h) const {                                       // material.rs:220-231
         if (kind != M_LIGHT) return BLACK;
         if (!two_sided && h.backface) return BLACK;
-        return scale * ke.sample(lam) * DenseSpectrum::sample_raw(illum, lam);
+        return scale * (ke_tex ? ke_tex->albedo_at(lam, h.uv) : ke.sample(lam)) * DenseSpectrum::sample_raw(illum, lam);
     }
     Color power(const Lambda& lam) const {                                                    // material.rs:234-242
         if (kind != M_LIGHT) return BLACK;
-        Color phi = scale * ke.sample(lam) * DenseSpectrum::sample_raw(illum, lam);
+        Color phi = scale * (ke_tex ? ke_tex->power(lam) : ke.sample(lam)) * DenseSpectrum::sample_raw(illum, lam);
         return two_sided ? 2.0 * phi : phi;
     }
     Float shading_cosine(Vec3 wi, Vec3 ns) const {                                            // material.rs:315-321
@@ -269,7 +389,7 @@ struct Material {
     }
 
     // ---- BxDF::f / sample / pdf in the local frame (bxdf.rs:69-151) ----
-    Color bx_f(Vec3 wo, Vec3 wi, const Lambda& lam, bool reflection, bool backface, int mode) const {
+    Color bx_f(Vec3 wo, Vec3 wi, const Lambda& lam, bool reflection, bool backface, int mode, Vec2 uv = Vec2()) const {
         if ((!reflection || backface) && bx_is_reflection()) return BLACK;
         switch (kind) {
         case M_LAMBERTIAN: return spec.sample(lam) / PI;                                      // scatter.rs:6-8
@@ -279,11 +399,11 @@ struct Material {
             Float dd = d(wh); Color f = f_col(wo, wh, lam); Float gg = g(wo, wi, wh);
             Color fr = dd * f * gg / (4.0 * std::fabs(cwo) * std::fabs(cwi));
             Float fd = disney_diffuse(cwo, cwi, cwh);
-            Color ksc = ks.sample(lam), kdc = kd.sample(lam);
+            Color ksc = ks_at(lam, uv), kdc = kd_at(lam, uv);
             return fr * ksc + kdc * (WHITE - f) * fd / PI;
         }
         case M_MFCONDUCTOR: {                                                                 // microfacet.rs:71-85
-            Color ksc = ks.sample(lam);
+            Color ksc = ks_at(lam, uv);
             if (mf_is_delta()) { Color f = f_col(wo, Vec3(0, 0, 1), lam); return ksc * f / std::fabs(sph::cos_theta(wi)); }
             return ksc * reflect_coeff(wo, wi, lam);
         }
@@ -295,14 +415,14 @@ struct Material {
             Float eta_ratio = reflection ? 1.0 : (wo_inside ? 1.0 / e : e);
             Vec3 wh = (e == 1.0 || mf_is_delta()) ? Vec3(0, 0, 1) : (wi * eta_ratio + wo).normalize();
             if (reflection) {
-                Color ksc = ks.sample(lam);
+                Color ksc = ks_at(lam, uv);
                 if (e == 1.0 || mf_is_delta()) { Color f = f_col(wo, wh, lam); return ksc * f / std::fabs(cwi); }
                 return ksc * reflect_coeff(wo, wi, lam);
             }
             Color f = f_col(wo, wh, lam);
             if (sph::cos_theta(wh) < 0.0) wh = -wh;
             Float scale_ = mode == RADIANCE ? eta_ratio * eta_ratio : 1.0;
-            Color tfc = tf.sample(lam);
+            Color tfc = tf_at(lam, uv);
             if (e == 1.0 || mf_is_delta()) return tfc * (WHITE - f) / (scale_ * std::fabs(cwi));
             Float dd = d(wh), gg = g(wo, wi, wh);
             Float wh_dot_wo = wh.dot(wo), wh_dot_wi = wh.dot(wi);
@@ -393,12 +513,12 @@ struct Material {
     Color bsdf_f(Vec3 wo, Vec3 wi, const Lambda& lam, int mode, const Hit& h) const {
         if (!is_standard()) return BLACK;
         bool refl = is_reflection(wo, wi, h.ng);
-        Onb uvw(h.ns);
-        return bx_f(uvw.to_local(wo), uvw.to_local(wi), lam, refl, h.backface, mode);
+        Onb uvw(map_normal(h.ns, h.uv));
+        return bx_f(uvw.to_local(wo), uvw.to_local(wi), lam, refl, h.backface, mode, h.uv);
     }
     bool bsdf_sample(Vec3 wo, const Hit& h, Lambda& lam, Float rand_u, Vec2 rs, Vec3& wi) const {
         if (!is_standard()) return false;
-        Onb uvw(h.ns);
+        Onb uvw(map_normal(h.ns, h.uv));
         Vec3 wl;
         if (!bx_sample(uvw.to_local(wo), h.backface, lam, rand_u, rs, wl)) return false;
         wi = uvw.to_world(wl);
@@ -408,7 +528,7 @@ struct Material {
         if (swap_dir) std::swap(wo, wi);
         if (!is_standard()) return 0.0;
         bool refl = is_reflection(wo, wi, h.ng);
-        Onb uvw(h.ns);
+        Onb uvw(map_normal(h.ns, h.uv));
         return bx_pdf(uvw.to_local(wo), uvw.to_local(wi), refl, lam);
     }
 };

@@ -20,6 +20,7 @@ SMALL = {
     "caustics": dict(n_tris=2000, resolution=(64, 48)),
     "conference": dict(n_chunks=8, tris_per_chunk=256, resolution=(64, 48)),
     "bistro": dict(n_chunks=16, tris_per_chunk=256, n_emissive=32, resolution=(64, 36)),
+    "textured": dict(n_tris=512, resolution=(64, 48)),
 }
 
 _cache = {}

@@ -102,6 +102,24 @@ class OracleScene:
         self.L.oracle_camera_rays(self.h, _p(r, C.c_double), _p(l, C.c_double), C.c_uint64(n), _p(o, C.c_double), _p(d, C.c_double))
         return o, d
 
+    def texture_count(self):
+        self.L.oracle_texture_count.restype = C.c_uint64
+        return int(self.L.oracle_texture_count(self.h))
+
+    def texture_kind(self, tex): return int(self.L.oracle_texture_kind(self.h, C.c_uint64(tex)))
+
+    def texture_eval(self, tex, uv, lambda_u=0.3):
+        uv = np.ascontiguousarray(uv, np.float64); n = uv.shape[0]
+        out = np.zeros((n, 4))
+        self.L.oracle_texture_eval(self.h, C.c_uint64(tex), _p(uv, C.c_double), C.c_uint64(n), C.c_double(lambda_u), _p(out, C.c_double))
+        return out
+
+    def bump_eval(self, tex, uv):
+        uv = np.ascontiguousarray(uv, np.float64); n = uv.shape[0]
+        out = np.zeros((n, 3))
+        self.L.oracle_bump_eval(self.h, C.c_uint64(tex), _p(uv, C.c_double), C.c_uint64(n), _p(out, C.c_double))
+        return out
+
     def counters(self, reset=False):
         c = np.zeros(8, np.uint64); self.L.oracle_counters(_p(c, C.c_uint64), C.c_int(int(reset)))
         return dict(zip(("tlas_nodes", "inst", "kd_nodes", "leaf_idx", "tri_tests", "sphere_tests", "closest", "occlusion"), (int(v) for v in c)))

@@ -25,7 +25,8 @@ def _relmse(a, b):
     return float(np.mean((a - b) ** 2 / (b ** 2 + 1e-3)))
 
 
-CASES = [("cornell", 0, 2), ("cornell", 1, 2), ("bunny", 0, 2), ("dragon", 0, 2), ("conference", 0, 2), ("conference", 1, 2), ("bistro", 0, 1), ("bistro", 1, 1), ("caustics", 0, 2)]
+CASES = [("cornell", 0, 2), ("cornell", 1, 2), ("bunny", 0, 2), ("dragon", 0, 2), ("conference", 0, 2), ("conference", 1, 2), ("bistro", 0, 1), ("bistro", 1, 1), ("caustics", 0, 2),
+         ("textured", 0, 2), ("textured", 1, 2)]      # every Texture kind, bump maps, image light + environment (scenes.textured)
 
 
 @pytest.mark.parametrize("name,integrator,spp", CASES)
@@ -53,7 +54,7 @@ def test_per_sample_parity_same_streams(name, integrator, spp, gpu_ctx):
     G.close(); O.close()
 
 
-@pytest.mark.parametrize("name,spp", [("cornell", 2), ("caustics", 2), ("bunny", 1)])
+@pytest.mark.parametrize("name,spp", [("cornell", 2), ("caustics", 2), ("bunny", 1), ("textured", 1)])
 def test_bdpt_per_sample_parity_same_streams(name, spp, gpu_ctx):
     """BDPathTrace (bd_path_trace.rs:23-75): main samples and light-tracing splats against the oracle with
     shared Philox streams.  Splats land on other pixels, so they are compared as a film: pixels where both
@@ -83,7 +84,7 @@ def test_bdpt_per_sample_parity_same_streams(name, spp, gpu_ctx):
     G.close(); O.close()
 
 
-@pytest.mark.parametrize("name,integrator,spp", [("cornell", 0, 64), ("cornell", 0, 512), ("bunny", 0, 32), ("conference", 1, 32), ("cornell", 2, 16)])
+@pytest.mark.parametrize("name,integrator,spp", [("cornell", 0, 64), ("cornell", 0, 512), ("bunny", 0, 32), ("conference", 1, 32), ("cornell", 2, 16), ("textured", 0, 32)])
 def test_converged_image_relmse(name, integrator, spp, gpu_ctx):
     """relMSE = mean((a-b)^2 / (b^2 + 1e-3)) in linear RGB: the GPU image is as close to an
     oracle image as another oracle image with a different seed is (factor 1.5), and mean luminance agrees
