@@ -35,6 +35,7 @@ WORKLOADS = {   # name -> (scene kwargs, integrator, default spp per step)
     "conference": (dict(), 0, 16),
     "conference_dl": (dict(), 1, 32),
     "bistro": (dict(), 0, 2),
+    "textured": (dict(n_tris=20000, resolution=(1024, 768)), 0, 16),
 }
 DESCR = {
     "bunny": "examples/bunny.rs PathTrace 1024x768, synthetic 69k-triangle stand-in mesh (assets are not available offline)",
@@ -44,6 +45,7 @@ DESCR = {
     "conference": "examples/conference.rs PathTrace 1024x768, synthetic 332k-triangle room in 64 kd-trees",
     "conference_dl": "examples/conference.rs DirectLight 1024x768, synthetic 332k-triangle room in 64 kd-trees",
     "bistro": "examples/bistro.rs PathTrace 1920x1080, synthetic 1.05M-triangle street in 1024 kd-trees, 4097 lights",
+    "textured": "not a reference example: empty box with every Texture kind, bump maps, image light + environment map (scenes.textured) PathTrace 1024x768",
 }
 
 
@@ -178,7 +180,7 @@ def main():
     ap.add_argument("--workload", default="bunny", choices=list(WORKLOADS))
     ap.add_argument("--spp", type=int, default=0, help="samples per pixel per step and per GPU (0 = workload default)")
     ap.add_argument("--wave-paths", type=int, default=0)
-    ap.add_argument("--other-scenes", default="cornell,dragon,caustics_bdpt,conference,conference_dl,bistro", help="comma list measured briefly after the main workload ('' = none)")
+    ap.add_argument("--other-scenes", default="cornell,dragon,caustics_bdpt,conference,conference_dl,bistro,textured", help="comma list measured briefly after the main workload ('' = none)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -3,14 +3,17 @@ parser/mtl.rs:10-146, parser/mtl/task.rs:16-116).  Same grammar subset and the s
 `TriangleMesh`; every `g` / `o` / `usemtl` group becomes its own kd-tree (obj.rs:49-66,92-107); groups whose
 material emits become loose triangle lights, one light per triangle (obj.rs:97-104).
 
-Not mirrored (host I/O outside the hot path): downloading (no network), zip extraction, PNG / HDR decode.
-Texture maps (`map_Kd`, `map_Ks`, `map_Ke`, `map_Bump`) are not on the device yet: they are ignored with a warning and
-the material keeps its constant colours; an environment map is given as a constant `Spectrum`."""
+Texture maps (`map_Kd`, `map_Ks`, `map_Ke`, `map_Bump`, mtl/task.rs:30-80) are read through an `image_resolver(name) ->
+PNG bytes` callback (the reference pulls them out of the scene's zip archive) and become `Texture::Image` / bump maps on
+the device; without a resolver they are ignored with a warning.  With `map_ks=False` a `map_Ks` image is the
+occlusion/roughness/metalness map of the reference: its mean green / blue channels become roughness and k
+(mtl/task.rs:60-68).  Not mirrored (host I/O outside the hot path): downloading (no network), zip extraction."""
 import io
 import math
 import warnings
 import numpy as np
-from .api import Scene, Material, TriangleMesh, Mesh, Face, LooseTriangles
+from .api import Scene, Material, Texture, TriangleMesh, Mesh, Face, LooseTriangles
+from .image import Image, decode_png
 from .spectrum import Spectrum
 
 
@@ -86,7 +89,7 @@ def mesh_from_obj(src, material):
     return TriangleMesh.new(np.asarray(V, np.float64).reshape(-1, 3), F, np.asarray(N, np.float64).reshape(-1, 3), np.asarray(T, np.float64).reshape(-1, 2), material)
 
 
-def load_mtl(src, materials=None, indices=None):
+def load_mtl(src, materials=None, indices=None, image_resolver=None, map_ks=True):
     """mtl::load_file + MtlTaskExecutor::exec + MtlConfig::build_material (mtl.rs:52-146, mtl/task.rs:16-116).
     Returns (materials, name -> index); the first definition of a name wins (mtl.rs:134)."""
     materials = [] if materials is None else materials
@@ -99,7 +102,8 @@ def load_mtl(src, materials=None, indices=None):
     if block:
         blocks.append(block)
     for block in blocks:
-        cfg = dict(Kd=Spectrum.BLACK(), Ks=Spectrum.BLACK(), Ke=Spectrum.BLACK(), Tf=Spectrum.BLACK(), eta=1.5, k=0.0, roughness=1.0, fresnel=False, transparent=False)
+        cfg = dict(Kd=Spectrum.BLACK(), Ks=Spectrum.BLACK(), Ke=Spectrum.BLACK(), Tf=Spectrum.BLACK(), eta=1.5, k=0.0, roughness=1.0, fresnel=False, transparent=False,
+                   map_Kd=None, map_Ks=None, map_Ke=None, map_Bump=None)
         name = ""
         for tokens in block:
             k = tokens[0]
@@ -112,31 +116,42 @@ def load_mtl(src, materials=None, indices=None):
                 if il == 5: cfg["fresnel"] = True
                 elif il == 6: cfg["transparent"] = True
                 elif il == 7: cfg["fresnel"] = cfg["transparent"] = True
-            elif k in ("map_Kd", "map_Ks", "map_Ke", "map_Bump"):
-                warnings.warn("%s of material %r ignored: image textures are not on the device yet" % (k, name))
+            elif k in ("map_Kd", "map_Ks", "map_Ke", "map_Bump"):                                       # mtl/task.rs:30-80
+                tex_name = " ".join(tokens[1:]).replace("\\", "/")
+                if image_resolver is None:
+                    warnings.warn("%s of material %r ignored: no image_resolver given" % (k, name)); continue
+                rgb = decode_png(image_resolver(tex_name))
+                if k == "map_Bump": cfg[k] = Image.bump_from_rgb8(rgb)
+                elif k == "map_Ks" and not map_ks:
+                    orm = Image.mean_vec3_from_rgb8(rgb)                                             # occlusion, roughness, metalness
+                    cfg["roughness"] = float(orm[1]); cfg["k"] = float(orm[2]); cfg["Ks"] = Spectrum.WHITE()
+                else: cfg[k] = Image.from_rgb8(rgb)
         if name in indices:
             continue
-        if not cfg["Ke"].is_black():
-            m = Material.light(cfg["Ke"])
+        if not cfg["Ke"].is_black() or cfg["map_Ke"] is not None:                                       # mtl.rs:59-91
+            m = Material.light(Texture.Image(cfg["map_Ke"]) if cfg["map_Ke"] is not None else cfg["Ke"])
         else:
-            m = Material.microfacet(cfg["roughness"], cfg["eta"], cfg["k"], cfg["transparent"], cfg["fresnel"], cfg["Kd"], cfg["Ks"], cfg["Tf"])
+            kd = Texture.Image(cfg["map_Kd"]) if cfg["map_Kd"] is not None else cfg["Kd"]
+            ks = Texture.Image(cfg["map_Ks"]) if cfg["map_Ks"] is not None else cfg["Ks"]
+            m = Material.microfacet(cfg["roughness"], cfg["eta"], cfg["k"], cfg["transparent"], cfg["fresnel"], kd, ks, cfg["Tf"], bump_map=cfg["map_Bump"])
         materials.append(m); indices[name] = len(materials) - 1
     return materials, indices
 
 
-def scene_from_obj(obj_src, mtl_src=None, env_map=None, mtl_resolver=None):
+def scene_from_obj(obj_src, mtl_src=None, env_map=None, mtl_resolver=None, image_resolver=None, map_ks=True):
     """parser::scene_from_file + obj::load_scene (parser.rs:206-265, obj.rs:27-110).  `mtl_src`: the text of the material
     library named by the caller (the `mtllib` argument of the reference); `mtl_resolver(name) -> text` serves `mtllib`
-    lines inside the .obj.  `env_map`: (Spectrum, scale) or None."""
+    lines inside the .obj.  `env_map`: (Spectrum or Texture, scale) or None;
+    `image_resolver(name) -> PNG bytes` serves the materials' texture maps."""
     obj_lines = list(_lines(obj_src))
     materials, indices = [], {}
     if mtl_src is not None:
-        load_mtl(mtl_src, materials, indices)
+        load_mtl(mtl_src, materials, indices, image_resolver, map_ks)
     for tokens in obj_lines:
         if tokens[0] == "mtllib":
             if mtl_resolver is None:
                 raise ObjError("Could not find %s in the archive" % tokens[1])
-            load_mtl(mtl_resolver(tokens[1]), materials, indices)
+            load_mtl(mtl_resolver(tokens[1]), materials, indices, image_resolver, map_ks)
     V, N, T = [], [], []
     faces, groups, midx = [], [], None
     for tokens in obj_lines:

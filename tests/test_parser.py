@@ -141,3 +141,34 @@ def test_parsed_scene_renders_like_the_oracle(gpu_ctx):
         ei = np.nan_to_num(epx[..., :3] / epx[..., 3:4]); gi = np.nan_to_num(gpx[..., :3] / gpx[..., 3:4])
     assert abs(gi.mean() - ei.mean()) <= 0.05 * abs(ei.mean()) + 1e-9
     G.close(); O.close()
+
+
+def test_texture_maps_become_image_textures():
+    """map_Kd / map_Ks / map_Ke / map_Bump (mtl/task.rs:30-80, mtl.rs:59-91): images served by name, decoded, and attached
+    as Texture::Image / bump map; with map_ks=False the map_Ks image is the occlusion-roughness-metalness map."""
+    from lumo_b200.image import encode_png
+    rs = np.random.RandomState(2)
+    pal = np.array([[200, 40, 40], [40, 200, 40], [250, 250, 250]], np.uint8)
+    files = {"tex/floor.png": encode_png(pal[rs.randint(0, 3, size=(4, 4))]), "orm.png": encode_png(np.full((2, 2, 3), [255, 64, 128], np.uint8)),
+             "nrm.png": encode_png(np.full((2, 2, 3), [128, 128, 255], np.uint8)), "lamp.png": encode_png(np.full((2, 2, 3), 255, np.uint8))}
+    mtl = MTL.replace("newmtl grey\nKd 0.5 0.5 0.5\nNs 0", "newmtl grey\nKd 0.5 0.5 0.5\nNs 0\nmap_Kd tex\\floor.png\nmap_Bump nrm.png\nmap_Ks orm.png") \
+             .replace("Ke 10 10 10", "Ke 0 0 0\nmap_Ke lamp.png")
+    asked = []
+    def images(name): asked.append(name); return files[name]
+    s = parser.scene_from_obj(OBJ, mtl_resolver=lambda name: mtl, image_resolver=images, map_ks=False)
+    assert asked[:3] == ["tex/floor.png", "nrm.png", "orm.png"]                     # backslashes normalised (task.rs:31)
+    grey = s.objects[0].material
+    assert grey.kw["_textures"]["kd_tex"] is not None and grey.kw["_textures"]["kd_tex"].kind == P.TEX_IMAGE and grey.kw["_bump"] is not None
+    assert grey.kw["_textures"]["ks_tex"] is None and abs(grey.kw["roughness"] - 64 / 256) < 1e-12 and abs(grey.kw["k"] - 128 / 256) < 1e-12
+    assert s.lights and s.lights[0].material.kw["_textures"]["ke_tex"].kind == P.TEX_IMAGE     # map_Ke alone makes a light (mtl.rs:60)
+    s2 = parser.scene_from_obj(OBJ, mtl_resolver=lambda name: mtl, image_resolver=images, map_ks=True)
+    assert s2.objects[0].material.kw["_textures"]["ks_tex"].kind == P.TEX_IMAGE
+    cam = CameraBuilder.new().origin(0, 2, 6).towards(0, 1, 0).resolution((32, 24)).build()
+    prog = s._program(cam)
+    B = native.Blob(native.build_blob(prog))
+    assert (B.textures["kind"] == P.TEX_IMAGE).sum() == 2 and (B.textures["kind"] == P.TEX_BUMP).sum() == 1
+    O = oracle_lib.OracleScene(prog)
+    assert O.texture_count() == 3
+    O.close()
+    with pytest.warns(UserWarning):
+        parser.scene_from_obj(OBJ, mtl_resolver=lambda name: mtl)                    # no resolver: maps ignored with a warning
