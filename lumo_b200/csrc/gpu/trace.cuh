@@ -149,12 +149,13 @@ struct KdStackEntry { uint32_t node; double t_start, t_end; };
 // Rectangle lights have two triangles, and the shading kernels that intersect one chosen light use a small one
 // so that their per-thread frame stays small (lumo_gpu_scene_upload checks that light kd-trees fit).
 #define LUMO_LIGHT_KD_STACK 8
-// Steps a lane may walk before the warp re-converges on the triangle test.  Unbounded ("while-while" proper) the warp
-// waits for its slowest walker every round; a short bound keeps the lanes that already hold a triangle from idling long,
-// at the price of running the triangle test with fewer of them.  Measured on B200 (trace + occlusion ms, bunny 4 spp /
-// bistro 1 spp): unbounded 36.3 / 184.9, 8: 35.9 / 174.6, 4: 32.9 / 166.8, 2: 32.1 / 166.2.
+// LUMO_KD_ROUND = 0 (default): "while-while" proper — every lane walks until it holds its next triangle, then the warp
+// runs the triangle test together.  LUMO_KD_ROUND = K > 0 bounds the walk to K steps per round, so lanes that already
+// hold a triangle idle less while the test runs with fewer lanes.  Measured on one B200, same box, K = 0 vs K = 2:
+// micro closest-hit 1135 / 718 vs 1030 / 656 Mrays/s (primary / incoherent); bunny 4 spp trace + occlusion 33.2 vs
+// 31.8 ms; bistro 1 spp 166.3 vs 165.3 ms.  A wash in the pipeline and a loss in the batch kernel: K stays 0.
 #ifndef LUMO_KD_ROUND
-#define LUMO_KD_ROUND 2
+#define LUMO_KD_ROUND 0
 #endif
 template <bool GEO, bool CNT, int STACK = 64>
 __device__ __forceinline__ bool kd_hit(const DevScene& S, const LumoKdTree* tree, const RayCtx& ctx, double t_min, double t_max,
@@ -173,19 +174,27 @@ __device__ __forceinline__ bool kd_hit(const DevScene& S, const LumoKdTree* tree
     const LumoTriVerts* tris = S.tri_verts + tree->tri_base;
     uint32_t leaf_pos = 0, leaf_end = 0;     // pending entries of the current leaf in LSEC_KD_LEAF
     bool in_leaf = false;                    // the current node was a leaf: pop once its entries are done
+#if LUMO_KD_ROUND > 0
     bool finished = false;
+#endif
     for (;;) {
         uint32_t tri = LUMO_NONE;
+#if LUMO_KD_ROUND > 0
 #pragma unroll 1
         for (int step = 0; step < LUMO_KD_ROUND; step++) {   // advance towards the next triangle of this lane
+#define LUMO_KD_DONE { finished = true; break; }
+#else
+        for (;;) {                                           // ... all the way to it ("while-while" proper)
+#define LUMO_KD_DONE break
+#endif
             if (leaf_pos < leaf_end) { tri = __ldg(S.kd_leaf + leaf_pos); leaf_pos++; LUMO_CNT(leaf); break; }
             if (in_leaf) {
-                if (sp == 0) { finished = true; break; }
+                if (sp == 0) LUMO_KD_DONE;
                 sp--;
                 curr = stack[sp].node; t_start = stack[sp].t_start; t_end = stack[sp].t_end;
                 in_leaf = false;
             }
-            if (t_hit < t_start) { finished = true; break; }
+            if (t_hit < t_start) LUMO_KD_DONE;
             LUMO_CNT(kd);
             const double2 raw = __ldg(reinterpret_cast<const double2*>(S.kd_nodes + curr));   // 16-byte node: one vector load
             const double point = raw.x;
@@ -209,7 +218,11 @@ __device__ __forceinline__ bool kd_hit(const DevScene& S, const LumoKdTree* tree
                 }
             }
         }
+#if LUMO_KD_ROUND > 0
         if (tri == LUMO_NONE) { if (finished) break; continue; }
+#else
+        if (tri == LUMO_NONE) break;
+#endif
         TriHit th;
         const double t = tri_hit<false, CNT>(tris + tri, r, q, t_min, t_end, th, c) ? th.t : LUMO_INF;
         if (GEO) { if (t < t_end) { t_end = t; t_hit = t; idx = tri; } }

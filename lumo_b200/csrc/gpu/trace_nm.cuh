@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(128, 8) k_nm_heavy(const __grid_constant__ Dev
         uint32_t tri = LUMO_NONE;
         bool finished = false;
 #pragma unroll 1
-        for (int step = 0; step < LUMO_KD_ROUND && has; step++) {                     // advance to this lane's next triangle (kdtree.rs:117-160)
+        for (int step = 0; step < 24 && has; step++) {                     // advance to this lane's next triangle (kdtree.rs:117-160)
             if (leaf_pos < leaf_end) { tri = __ldg(S.kd_leaf + leaf_pos); leaf_pos++; break; }
             if (in_leaf) {
                 if (sp == 0) { finished = true; break; }

@@ -397,8 +397,15 @@ __global__ void __launch_bounds__(128) k_terminal(const __grid_constant__ DevSce
     }
 }
 
+// resident CTAs per SM the shade kernels are compiled for (register budget = 65536 / (128 * blocks))
+#ifndef LUMO_SCATTER_BLOCKS
+#define LUMO_SCATTER_BLOCKS 4
+#endif
+#ifndef LUMO_NEE_BLOCKS
+#define LUMO_NEE_BLOCKS 4
+#endif
 template <int K>
-__global__ void __launch_bounds__(128, 4) k_scatter(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P) {
+__global__ void __launch_bounds__(128, LUMO_SCATTER_BLOCKS) k_scatter(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P) {
     const uint32_t N = W.n_slots, n = W.it->n_class[K], cur = P.cur, nxt = P.cur ^ 1u;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t slot = W.cls[K][i];
@@ -472,7 +479,7 @@ __device__ __forceinline__ C4 mis_sample(const DevScene& S, const Mat& m, const 
 // one thread per path doing A then B (all lanes busy in A).  Scenes with several (n_shadow = log2 #lights) run one thread
 // per term, laid out so that every lane of a warp evaluates the same term index for 32 consecutive queue entries.
 template <int K, bool SPLIT>
-__global__ void __launch_bounds__(128, 4) k_nee(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P) {
+__global__ void __launch_bounds__(128, LUMO_NEE_BLOCKS) k_nee(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P) {
     const uint32_t N = W.n_slots, nq = W.it->n_class[K], cur = P.cur;
     const uint32_t ns = S.P.n_shadow_rays;
     const uint32_t per = SPLIT ? 2u * ns : ns;

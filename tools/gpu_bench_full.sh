@@ -1,10 +1,9 @@
 #!/bin/bash
-# full measurement pass: bench (ours + reference arm), launch list, one full ncu capture of the dominant kernels
+# full measurement pass: bench (ours + reference arm), then the ncu launch list of the same profiling command
 mkdir -p gpurun_out
 python bench.py > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err
 tail -3 gpurun_out/bench_full.err
 python bench.py --impl reference > gpurun_out/bench_ref.json 2>> gpurun_out/bench_full.err
 python tools/prof_run.py bunny 4 > gpurun_out/prof_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/launches_bunny.csv python tools/prof_run.py bunny 4 > gpurun_out/ncu_launch.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"k_wave_trace|k_wave_occlude|k_nee|k_scatter|k_retire" -s 40 -c 9 -o gpurun_out/prof_final python tools/prof_run.py bunny 4 > gpurun_out/ncu_full.log 2>&1
-tail -2 gpurun_out/ncu_full.log
+tail -1 gpurun_out/ncu_launch.log | cut -c1-200
