@@ -49,6 +49,7 @@ struct lumo_scene {
     LumoBlobHeader H;
     struct NmSeg { uint32_t i0, i1; int heavy; };   // items [i0, i1]; heavy = local index of the heavy object that ends it, or -1
     struct NmHostPlan { NmPlan P; std::vector<NmSeg> segs; std::vector<uint32_t> heavy; };
+    bool has_textures = false;                       // any LumoTexture record (then materials may refer to textures / bump maps)
     NmHostPlan nm_obj, nm_lig; bool nm_ok = false;   // node-major traversal plans (small object BVHs only)
     uint32_t kind_mask = 0;   // bit k set: some Standard material of LumoMatKind k exists (which shade kernels to launch)
 };
@@ -235,6 +236,7 @@ extern "C" int32_t lumo_gpu_scene_upload(lumo_ctx* ctx, const void* blob, uint64
     S.normals = (const double*)at(LSEC_NORMALS); S.uvs = (const double*)at(LSEC_UVS);
     S.rects = (const LumoRect*)at(LSEC_RECTS); S.spheres = (const LumoSphere*)at(LSEC_SPHERES);
     S.materials = (const LumoMaterial*)at(LSEC_MATERIALS); S.tables = (const double*)at(LSEC_TABLES); S.lights = (const LumoLight*)at(LSEC_LIGHTS);
+    sc->has_textures = H.sec[LSEC_TEXTURES].count > 0;
     S.textures = (const LumoTexture*)at(LSEC_TEXTURES); S.tex_pixels = (const float*)at(LSEC_TEX_PIXELS); S.tex_f64 = (const double*)at(LSEC_TEX_F64);
     S.P = H.params;
     {   // node-major plans: both BVHs in the reference's traversal order, if they are small enough
@@ -503,8 +505,13 @@ struct HostCounters { QueueCounters qc; RunCounters run; };
 template <int K>
 static void launch_shade_kind(lumo_scene* sc, const Wave& W, const WaveParams& P, int grid, int nee_grid, cudaStream_t st, unsigned long long& launches) {
     if (!(sc->kind_mask & (1u << K))) return;
-    k_scatter<K><<<grid, 128, 0, st>>>(sc->S, W, P);
-    if (sc->S.P.n_shadow_rays > 1) k_nee<K, true><<<nee_grid, 128, 0, st>>>(sc->S, W, P); else k_nee<K, false><<<nee_grid, 128, 0, st>>>(sc->S, W, P);
+    if (sc->has_textures) {
+        k_scatter<K><<<grid, 128, 0, st>>>(sc->S, W, P);
+        if (sc->S.P.n_shadow_rays > 1) k_nee<K, true><<<nee_grid, 128, 0, st>>>(sc->S, W, P); else k_nee<K, false><<<nee_grid, 128, 0, st>>>(sc->S, W, P);
+    } else {                                         // no LumoTexture record in the scene: the texture-free instantiations (shade.cuh LUMO_K_SOLID)
+        k_scatter<K | LUMO_K_SOLID><<<grid, 128, 0, st>>>(sc->S, W, P);
+        if (sc->S.P.n_shadow_rays > 1) k_nee<K | LUMO_K_SOLID, true><<<nee_grid, 128, 0, st>>>(sc->S, W, P); else k_nee<K | LUMO_K_SOLID, false><<<nee_grid, 128, 0, st>>>(sc->S, W, P);
+    }
     launches += 2;
 }
 

@@ -376,7 +376,7 @@ __device__ __forceinline__ void load_path(const Wave& W, uint32_t cur, uint32_t 
 }
 // dispersion (bxdf/microfacet.rs:282-286): a dielectric with a non-constant eta keeps only the hero wavelength
 template <int K> __device__ __forceinline__ void maybe_terminate(const Mat& m, Lam& l) {
-    if (K == LMAT_MFDIELECTRIC && !(m.flags & LMF_ETA_CONST)) { l.l[1] = 0.0; l.l[2] = 0.0; l.l[3] = 0.0; }
+    if ((K & 7) == LMAT_MFDIELECTRIC && !(m.flags & LMF_ETA_CONST)) { l.l[1] = 0.0; l.l[2] = 0.0; l.l[3] = 0.0; }
 }
 
 __global__ void __launch_bounds__(128) k_terminal(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P) {
@@ -406,13 +406,13 @@ __global__ void __launch_bounds__(128) k_terminal(const __grid_constant__ DevSce
 #endif
 template <int K>
 __global__ void __launch_bounds__(128, LUMO_SCATTER_BLOCKS) k_scatter(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P) {
-    const uint32_t N = W.n_slots, n = W.it->n_class[K], cur = P.cur, nxt = P.cur ^ 1u;
+    const uint32_t N = W.n_slots, n = W.it->n_class[K & 7], cur = P.cur, nxt = P.cur ^ 1u;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t slot = W.cls[K][i];
+        const uint32_t slot = W.cls[K & 7][i];
         Ray ro; HitRec rec; load_path(W, cur, slot, ro, rec);
         const DevHit ho = reconstruct_hit(S, ro, rec);
         const Mat& m = S.materials[ho.material];
-        const Onb uvw = shading_onb(S, m, ho);
+        const Onb uvw = shading_onb<K>(S, m, ho);
         const uint32_t pixel = W.pixel[slot];
         Rng rng = rng_make(P.seed, pixel, W.sample[slot], 0u, W.draws[cur][slot]);
         Lam lam; for (int k = 0; k < 4; k++) lam.l[k] = W.lam[(size_t)k * N + slot];
@@ -456,7 +456,7 @@ __global__ void __launch_bounds__(128, LUMO_SCATTER_BLOCKS) k_scatter(const __gr
                 }
             }
         }
-        if (K == LMAT_MFDIELECTRIC) for (int k = 1; k < 4; k++) W.lam[(size_t)k * N + slot] = lam.l[k];
+        if ((K & 7) == LMAT_MFDIELECTRIC) for (int k = 1; k < 4; k++) W.lam[(size_t)k * N + slot] = lam.l[k];
         W.flags[slot] = (done ? PF_DONE : f) | (nee ? PF_NEE : 0u);
         if (done) W.done[cur][agg_inc(&W.qc->n_done[cur])] = slot;
         else agg_inc(&W.qc->n_active[nxt]);
@@ -471,7 +471,7 @@ __device__ __forceinline__ C4 mis_sample(const DevScene& S, const Mat& m, const 
     const double denom = p_lig * p_lig + p_sct * p_sct;
     const double weight = li ? (p_lig * p_lig) / denom : (p_sct * p_sct) / denom;
     const double p_denom = li ? p_lig : p_sct;
-    return bsdf * c4(1.0) * mat_emit(S, S.materials[hi.material], lam, hi) * shading_cosine(m, wi, ho.ns) * weight / p_denom;
+    return bsdf * c4(1.0) * mat_emit<K>(S, S.materials[hi.material], lam, hi) * shading_cosine(m, wi, ho.ns) * weight / p_denom;
 }
 
 // integrator.rs:89-137.  A shadow sample has a light-sampled term (A) and a BSDF-sampled term (B), the latter almost
@@ -480,7 +480,7 @@ __device__ __forceinline__ C4 mis_sample(const DevScene& S, const Mat& m, const 
 // per term, laid out so that every lane of a warp evaluates the same term index for 32 consecutive queue entries.
 template <int K, bool SPLIT>
 __global__ void __launch_bounds__(128, LUMO_NEE_BLOCKS) k_nee(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P) {
-    const uint32_t N = W.n_slots, nq = W.it->n_class[K], cur = P.cur;
+    const uint32_t N = W.n_slots, nq = W.it->n_class[K & 7], cur = P.cur;
     const uint32_t ns = S.P.n_shadow_rays;
     const uint32_t per = SPLIT ? 2u * ns : ns;
     const unsigned long long padded = (unsigned long long)((nq + 31u) / 32u) * 32ull * per;
@@ -490,12 +490,12 @@ __global__ void __launch_bounds__(128, LUMO_NEE_BLOCKS) k_nee(const __grid_const
         const uint32_t qi = (uint32_t)(grp * 32ull + (it % 32ull));
         const uint32_t i = SPLIT ? j >> 1 : j;
         if (qi >= nq) continue;
-        const uint32_t slot = W.cls[K][qi];
+        const uint32_t slot = W.cls[K & 7][qi];
         if (!(W.flags[slot] & PF_NEE)) continue;
         Ray ro; HitRec rec; load_path(W, cur, slot, ro, rec);
         const DevHit ho = reconstruct_hit(S, ro, rec);
         const Mat& m = S.materials[ho.material];
-        const Onb uvw = shading_onb(S, m, ho);
+        const Onb uvw = shading_onb<K>(S, m, ho);
         const uint32_t pixel = W.pixel[slot];
         Lam lam; for (int k = 0; k < 4; k++) lam.l[k] = W.lam[(size_t)k * N + slot];   // already terminated by k_scatter if dispersive
         const C4 gathered = load_c4(W.gathered[cur], N, slot);
@@ -523,7 +523,7 @@ __global__ void __launch_bounds__(128, LUMO_NEE_BLOCKS) k_nee(const __grid_const
             // reflection-only BxDFs the pdf starts with two sign tests (bsdf.rs:88-90, bxdf.rs:136-139, scatter.rs:14-17):
             // a light-sampled direction below the surface stops here, before any light or microfacet arithmetic.
             // (measured: worth it for the one-thread-per-path form only; with one thread per term the early exits just thin the warps)
-            if (!SPLIT && K != LMAT_MFDIELECTRIC && term == 0) {
+            if (!SPLIT && (K & 7) != LMAT_MFDIELECTRIC && term == 0) {
                 if (!is_reflection(wo, wi, ho.ng)) return;
                 if (!same_hemisphere(to_local(uvw, wo), to_local(uvw, wi))) return;
             }
