@@ -149,15 +149,19 @@ struct KdStackEntry { uint32_t node; double t_start, t_end; };
 // Rectangle lights have two triangles, and the shading kernels that intersect one chosen light use a small one
 // so that their per-thread frame stays small (lumo_gpu_scene_upload checks that light kd-trees fit).
 #define LUMO_LIGHT_KD_STACK 8
-// LUMO_KD_ROUND = 0 (default): "while-while" proper — every lane walks until it holds its next triangle, then the warp
-// runs the triangle test together.  LUMO_KD_ROUND = K > 0 bounds the walk to K steps per round, so lanes that already
-// hold a triangle idle less while the test runs with fewer lanes.  Measured on one B200, same box, K = 0 vs K = 2:
-// micro closest-hit 1135 / 718 vs 1030 / 656 Mrays/s (primary / incoherent); bunny 4 spp trace + occlusion 33.2 vs
-// 31.8 ms; bistro 1 spp 166.3 vs 165.3 ms.  A wash in the pipeline and a loss in the batch kernel: K stays 0.
+// ROUND = 0: "while-while" proper — every lane walks until it holds its next triangle, then the warp runs the triangle
+// test together.  ROUND = K > 0 bounds the walk to K steps per round, so lanes that already hold a triangle idle less
+// while the test runs with fewer lanes.  Measured on one B200, same box, 0 vs 2: the register-bounded wave kernels gain
+// (dragon 132 -> 146 Mrays/s, bunny +2 %, bistro and conference unchanged), the batch kernel loses (micro closest-hit
+// 1135 / 718 -> 1030 / 656 Mrays/s primary / incoherent).  So the wave kernels instantiate LUMO_WAVE_KD_ROUND and
+// everything else the default.
 #ifndef LUMO_KD_ROUND
 #define LUMO_KD_ROUND 0
 #endif
-template <bool GEO, bool CNT, int STACK = 64>
+#ifndef LUMO_WAVE_KD_ROUND
+#define LUMO_WAVE_KD_ROUND 2
+#endif
+template <bool GEO, bool CNT, int STACK = 64, int ROUND = LUMO_KD_ROUND>
 __device__ __forceinline__ bool kd_hit(const DevScene& S, const LumoKdTree* tree, const RayCtx& ctx, double t_min, double t_max,
                                     double& t_out, uint32_t& tri_out, D3& bary_out, Counters* c) {
     const Ray r = ctx.r;
@@ -174,27 +178,19 @@ __device__ __forceinline__ bool kd_hit(const DevScene& S, const LumoKdTree* tree
     const LumoTriVerts* tris = S.tri_verts + tree->tri_base;
     uint32_t leaf_pos = 0, leaf_end = 0;     // pending entries of the current leaf in LSEC_KD_LEAF
     bool in_leaf = false;                    // the current node was a leaf: pop once its entries are done
-#if LUMO_KD_ROUND > 0
     bool finished = false;
-#endif
     for (;;) {
         uint32_t tri = LUMO_NONE;
-#if LUMO_KD_ROUND > 0
 #pragma unroll 1
-        for (int step = 0; step < LUMO_KD_ROUND; step++) {   // advance towards the next triangle of this lane
-#define LUMO_KD_DONE { finished = true; break; }
-#else
-        for (;;) {                                           // ... all the way to it ("while-while" proper)
-#define LUMO_KD_DONE break
-#endif
+        for (int step = 0; ROUND == 0 || step < ROUND; step++) {   // advance towards the next triangle of this lane (ROUND = 0: all the way)
             if (leaf_pos < leaf_end) { tri = __ldg(S.kd_leaf + leaf_pos); leaf_pos++; LUMO_CNT(leaf); break; }
             if (in_leaf) {
-                if (sp == 0) LUMO_KD_DONE;
+                if (sp == 0) { finished = true; break; }
                 sp--;
                 curr = stack[sp].node; t_start = stack[sp].t_start; t_end = stack[sp].t_end;
                 in_leaf = false;
             }
-            if (t_hit < t_start) LUMO_KD_DONE;
+            if (t_hit < t_start) { finished = true; break; }
             LUMO_CNT(kd);
             const double2 raw = __ldg(reinterpret_cast<const double2*>(S.kd_nodes + curr));   // 16-byte node: one vector load
             const double point = raw.x;
@@ -218,11 +214,7 @@ __device__ __forceinline__ bool kd_hit(const DevScene& S, const LumoKdTree* tree
                 }
             }
         }
-#if LUMO_KD_ROUND > 0
-        if (tri == LUMO_NONE) { if (finished) break; continue; }
-#else
-        if (tri == LUMO_NONE) break;
-#endif
+        if (tri == LUMO_NONE) { if (ROUND == 0 || finished) break; continue; }
         TriHit th;
         const double t = tri_hit<false, CNT>(tris + tri, r, q, t_min, t_end, th, c) ? th.t : LUMO_INF;
         if (GEO) { if (t < t_end) { t_end = t; t_hit = t; idx = tri; } }
@@ -338,13 +330,13 @@ __device__ __noinline__ double sphere_hit(double radius, const Ray& r, double t_
 }
 
 // Object::hit_t for one object record (what the BVH leaf loop calls, bvh.rs:346)
-template <bool CNT>
+template <bool CNT, int ROUND = LUMO_KD_ROUND>
 __device__ __forceinline__ double object_hit_t(const DevScene& S, const LumoObject& o, const RayCtx& w, double t_min, double t_max, Counters* c) {
     LUMO_LOCAL_CTX(S, o, w, c);
     switch (o.kind) {
     case LOBJ_KD: case LOBJ_RECT: {
         double t; uint32_t tri; D3 bary;
-        return kd_hit<false, CNT>(S, S.kd_trees + o.geom, l, t_min, t_max, t, tri, bary, c) ? t : LUMO_INF;
+        return kd_hit<false, CNT, 64, ROUND>(S, S.kd_trees + o.geom, l, t_min, t_max, t, tri, bary, c) ? t : LUMO_INF;
     }
     case LOBJ_SPHERE: LUMO_CNT(sphere); return sphere_hit_t(S.spheres[o.geom].radius, l.r, t_min, t_max);
     default: {
@@ -358,12 +350,12 @@ struct HitRec { double t; D3 bary; uint32_t obj, tri; };
 
 // Object::hit for one object record: distance + which triangle + barycentrics (the rest of `Hit`
 // is rebuilt from these by the shading kernels, shade.cuh reconstruct_hit).
-template <bool CNT, int STACK = 64>
+template <bool CNT, int STACK = 64, int ROUND = LUMO_KD_ROUND>
 __device__ __noinline__ bool object_hit(const DevScene& S, const LumoObject& o, const RayCtx& w, double t_min, double t_max, HitRec& h, Counters* c) {
     LUMO_LOCAL_CTX(S, o, w, c);
     switch (o.kind) {
     case LOBJ_KD: case LOBJ_RECT:
-        return kd_hit<true, CNT, STACK>(S, S.kd_trees + o.geom, l, t_min, t_max, h.t, h.tri, h.bary, c);
+        return kd_hit<true, CNT, STACK, ROUND>(S, S.kd_trees + o.geom, l, t_min, t_max, h.t, h.tri, h.bary, c);
     case LOBJ_SPHERE: {
         LUMO_CNT(sphere);
         double t = sphere_hit(S.spheres[o.geom].radius, l.r, t_min, t_max);
@@ -382,7 +374,7 @@ __device__ __noinline__ bool object_hit(const DevScene& S, const LumoObject& o, 
 
 // BVH::_hit<GEO> (bvh.rs:315-362) over one of the two object BVHs.  obj_base = first object
 // record of this BVH (0 for Scene.objects, n_objects for Scene.lights).
-template <bool GEO, bool CNT>
+template <bool GEO, bool CNT, int ROUND = LUMO_KD_ROUND>
 __device__ __noinline__ uint32_t tlas_hit(const DevScene& S, uint32_t root, uint32_t obj_base, const RayCtx& w, double t_min, double t_max, Counters* c, double* t_found = nullptr) {
     const Ray r = w.r;
     const D3 inv = w.inv;
@@ -421,7 +413,7 @@ __device__ __noinline__ uint32_t tlas_hit(const DevScene& S, uint32_t root, uint
             need_pop = true;
         }
         if (obj == LUMO_NONE) break;
-        const double t = object_hit_t<CNT>(S, S.objects[obj_base + obj], w, t_min, tt, c);
+        const double t = object_hit_t<CNT, ROUND>(S, S.objects[obj_base + obj], w, t_min, tt, c);
         if (GEO) { if (t < tt) { tt = t; idx = obj; } }
         else { if (t < tt) { if (t_found) *t_found = t; return obj; } }
     }
@@ -429,36 +421,36 @@ __device__ __noinline__ uint32_t tlas_hit(const DevScene& S, uint32_t root, uint
 }
 
 // Object for BVH: hit / hit_t (bvh.rs:365-375)
-template <bool CNT>
+template <bool CNT, int ROUND = LUMO_KD_ROUND>
 __device__ __forceinline__ bool bvh_hit(const DevScene& S, uint32_t root, uint32_t obj_base, const RayCtx& r, double t_min, double t_max, HitRec& h, Counters* c) {
-    const uint32_t idx = tlas_hit<true, CNT>(S, root, obj_base, r, t_min, t_max, c);
+    const uint32_t idx = tlas_hit<true, CNT, ROUND>(S, root, obj_base, r, t_min, t_max, c);
     if (idx == LUMO_NONE) return false;
-    if (!object_hit<CNT>(S, S.objects[obj_base + idx], r, t_min, t_max, h, c)) return false;
+    if (!object_hit<CNT, 64, ROUND>(S, S.objects[obj_base + idx], r, t_min, t_max, h, c)) return false;
     h.obj = obj_base + idx;
     return true;
 }
 // BVH::hit_t (bvh.rs:371-374) finds the first object with a hit and then calls hit_t on it a second time with the
 // same arguments; that second call is a pure function of them, so its value is the one the traversal just
 // computed.  The counting instantiation still performs it, to report the reference's visit counts.
-template <bool CNT>
+template <bool CNT, int ROUND = LUMO_KD_ROUND>
 __device__ __forceinline__ double bvh_hit_t(const DevScene& S, uint32_t root, uint32_t obj_base, const RayCtx& r, double t_min, double t_max, Counters* c) {
     double t = LUMO_INF;
-    const uint32_t idx = tlas_hit<false, CNT>(S, root, obj_base, r, t_min, t_max, c, &t);
+    const uint32_t idx = tlas_hit<false, CNT, ROUND>(S, root, obj_base, r, t_min, t_max, c, &t);
     if (idx == LUMO_NONE) return LUMO_INF;
-    if (CNT) return object_hit_t<CNT>(S, S.objects[obj_base + idx], r, t_min, t_max, c);
+    if (CNT) return object_hit_t<CNT, ROUND>(S, S.objects[obj_base + idx], r, t_min, t_max, c);
     return t;
 }
 
 // Scene::hit (scene.rs:119-147): objects, then lights with t_max = h.t.  The reference always
 // starts from t_max = +inf; the C ABI lets the caller pass a finite one.
-template <bool CNT>
+template <bool CNT, int ROUND = LUMO_KD_ROUND>
 __device__ __forceinline__ bool scene_hit(const DevScene& S, const Ray& ray, double t_max, HitRec& h, Counters* c) {
     RayCtx r; make_ctx(ray, r);
-    bool have = bvh_hit<CNT>(S, 0, 0, r, 0.0, t_max, h, c);
+    bool have = bvh_hit<CNT, ROUND>(S, 0, 0, r, 0.0, t_max, h, c);
     if (have) t_max = h.t;
     if (S.P.n_lights) {
         HitRec hl;
-        if (bvh_hit<CNT>(S, S.P.lights_root, S.P.n_objects, r, 0.0, t_max, hl, c)) { h = hl; have = true; }
+        if (bvh_hit<CNT, ROUND>(S, S.P.lights_root, S.P.n_objects, r, 0.0, t_max, hl, c)) { h = hl; have = true; }
     }
     return have;
 }
@@ -472,11 +464,11 @@ __device__ __forceinline__ double scene_hit_t(const DevScene& S, const Ray& ray,
     return t;
 }
 // the two occlusion tests of Scene::hit_light (scene.rs:180-186)
-template <bool CNT>
+template <bool CNT, int ROUND = LUMO_KD_ROUND>
 __device__ __forceinline__ bool scene_occluded(const DevScene& S, const Ray& ray, double t_max, Counters* c) {
     RayCtx r; make_ctx(ray, r);
-    if (bvh_hit_t<CNT>(S, 0, 0, r, 0.0, t_max, c) < t_max) return true;
-    if (S.P.n_lights && bvh_hit_t<CNT>(S, S.P.lights_root, S.P.n_objects, r, 0.0, t_max, c) < t_max) return true;
+    if (bvh_hit_t<CNT, ROUND>(S, 0, 0, r, 0.0, t_max, c) < t_max) return true;
+    if (S.P.n_lights && bvh_hit_t<CNT, ROUND>(S, S.P.lights_root, S.P.n_objects, r, 0.0, t_max, c) < t_max) return true;
     return false;
 }
 

@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(128, 8) k_wave_trace(const __grid_constant__ D
             Ray r; r.o = d3(W.ox[cur][slot], W.oy[cur][slot], W.oz[cur][slot]); r.d = d3(W.dx[cur][slot], W.dy[cur][slot], W.dz[cur][slot]);
             HitRec h;
             klass = 0;
-            if (scene_hit<CNT>(S, r, LUMO_INF, h, &cnt)) {
+            if (scene_hit<CNT, LUMO_WAVE_KD_ROUND>(S, r, LUMO_INF, h, &cnt)) {
                 W.ht[slot] = h.t; W.hb0[slot] = h.bary.x; W.hb1[slot] = h.bary.y; W.hb2[slot] = h.bary.z; W.hobj[slot] = h.obj; W.htri[slot] = h.tri;
                 const uint32_t kind = S.materials[S.objects[h.obj].material].kind;
                 if (kind >= LMAT_LAMBERTIAN && kind <= LMAT_MFDIELECTRIC) klass = kind;
@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(128, 8) k_wave_occlude(const __grid_constant__
         const uint32_t i = base + lane;
         if (i < n) {
             Ray r; r.o = d3(W.sox[i], W.soy[i], W.soz[i]); r.d = d3(W.sdx[i], W.sdy[i], W.sdz[i]);
-            if (!scene_occluded<CNT>(S, r, W.stmax[i], &cnt)) {
+            if (!scene_occluded<CNT, LUMO_WAVE_KD_ROUND>(S, r, W.stmax[i], &cnt)) {
                 const uint32_t slot = W.sslot[i];
                 for (int k = 0; k < 4; k++) { const double v = W.sc[(size_t)k * C + i]; if (v != 0.0) atomicAdd(&W.radiance[(size_t)k * N + slot], v); }
             }
