@@ -16,13 +16,15 @@ namespace lumo_dev {
 #define LUMO_BDPT_MAXV 64
 #define LUMO_BDPT_MAX_DEPTH 1024u   /* bd_path_trace.rs:7 */
 
-struct Vtx { DevHit h; C4 gathered; double pdf_fwd, pdf_bck; D3 wo; int light; int pad; };   // vertex.rs:5-12
+// `delta`: Vertex::is_delta (vertex.rs:90-97) evaluated once when the vertex is made — it depends on the material and the hero
+// wavelength only, and the hero wavelength never changes along a sample (termination zeroes the secondary ones).
+struct Vtx { DevHit h; C4 gathered; double pdf_fwd, pdf_bck; D3 wo; int light; int delta; };   // vertex.rs:5-12
 
 __device__ const LumoMaterial g_blank_material = {LMAT_BLANK, 0u, 1.0, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, 0u, 0u, 0u, LUMO_NONE, 0.0, LUMO_NONE, LUMO_NONE, LUMO_NONE, LUMO_NONE, 0ull};
 __device__ __forceinline__ const Mat& vmat(const DevScene& S, const Vtx& v) { return v.h.material < 0 ? g_blank_material : S.materials[v.h.material]; }
 __device__ __forceinline__ bool v_is_surface(const Vtx& v) { return v.h.material >= 0; }                    // vertex.rs:86-88 (Blank = camera)
 __device__ __forceinline__ bool v_is_light(const Vtx& v) { return v.light >= 0; }
-__device__ __forceinline__ bool v_is_delta(const DevScene& S, const Vtx& v, const Lam& l) { return v.h.material < 0 ? false : mat_is_delta(S, S.materials[v.h.material], l); }
+__device__ __forceinline__ bool v_is_delta(const DevScene& S, const Vtx& v, const Lam& l) { return v.delta != 0; }
 __device__ __forceinline__ double sa_to_area(double pdf, D3 xo, D3 xi, D3 wi, D3 ngi) { return pdf * fabs(dot(wi, ngi)) / dist2(xo, xi); }   // measure.rs:9-11
 __device__ __forceinline__ double v_shading_cosine(const DevScene& S, const Vtx& v, D3 wi) { return shading_cosine(vmat(S, v), wi, v.h.ns); }
 __device__ __forceinline__ double v_shading_correction(const DevScene& S, const Vtx& v, D3 wi) {           // vertex.rs:118-126
@@ -51,7 +53,7 @@ __device__ __forceinline__ double v_pdf_prev(const DevScene& S, const Vtx& v, co
 __device__ __forceinline__ void v_camera(Vtx& v, D3 xo, double pdf_fwd, const C4& gathered) {               // vertex.rs:16-36
     v.h.t = 0.0; v.h.material = -1; v.h.backface = false /* (-X).X > 0 */; v.h.p = xo; v.h.fp_error = d3(0, 0, 0);
     v.h.ns = d3(1, 0, 0); v.h.ng = d3(1, 0, 0); v.h.u = 1.0; v.h.v = 0.0; wrap_uv(v.h.u, v.h.v);
-    v.gathered = gathered; v.pdf_fwd = pdf_fwd; v.pdf_bck = 0.0; v.wo = d3(0, 0, 0); v.light = -1; v.pad = 0;
+    v.gathered = gathered; v.pdf_fwd = pdf_fwd; v.pdf_bck = 0.0; v.wo = d3(0, 0, 0); v.light = -1; v.delta = 0;
 }
 
 // ---- camera importance (camera.rs:167-388) -----------------------------------------------------------
@@ -136,8 +138,9 @@ __device__ __noinline__ int bdpt_walk(const DevScene& S, Ray ro, Rng& rng, Lam& 
         const uint32_t prev = depth;
         const D3 wo = -ro.d;
         Vtx& cv = vs[n];                                                                      // Vertex::surface, vertex.rs:51-84
-        cv.pdf_fwd = mat_is_delta(S, m, lam) ? 0.0 : sa_to_area(pdf_fwd, vs[prev].h.p, ho.p, -wo, ho.ng);
-        cv.h = ho; cv.gathered = gathered; cv.wo = wo; cv.pdf_bck = 0.0; cv.light = -1; cv.pad = 0;
+        const bool is_delta = mat_is_delta(S, m, lam);
+        cv.pdf_fwd = is_delta ? 0.0 : sa_to_area(pdf_fwd, vs[prev].h.p, ho.p, -wo, ho.ng);
+        cv.h = ho; cv.gathered = gathered; cv.wo = wo; cv.pdf_bck = 0.0; cv.light = -1; cv.delta = is_delta ? 1 : 0;
         n++;
         depth += 1;
         const uint32_t curr = depth;
@@ -169,7 +172,7 @@ __device__ __noinline__ int bdpt_walk(const DevScene& S, Ray ro, Rng& rng, Lam& 
             if (depth >= LUMO_BDPT_MAX_DEPTH) break;
             gathered = gathered / rr;
         }
-        if (mat_is_delta(S, m, lam)) pdf_fwd = 0.0;
+        if (is_delta) pdf_fwd = 0.0;
         ro = ri;
     }
     return n;
@@ -312,7 +315,7 @@ __device__ __noinline__ C4 connect_camera_path(const DevScene& S, Rng& rng, cons
     wi = ri.d;
     const double pdf_origin = sa_to_area(p_lig, xo, xi, wi, ngi);
     const C4 emittance = mat_emit(S, S.materials[hi.material], lam, hi);
-    Vtx ll; ll.h = hi; ll.gathered = emittance; ll.light = (int)li; ll.pdf_fwd = pdf_origin; ll.pdf_bck = 0.0; ll.wo = d3(0, 0, 0); ll.pad = 0;   // Vertex::light
+    Vtx ll; ll.h = hi; ll.gathered = emittance; ll.light = (int)li; ll.pdf_fwd = pdf_origin; ll.pdf_bck = 0.0; ll.wo = d3(0, 0, 0); ll.delta = 0;   // Vertex::light
     const C4 bsdf = v_f(S, cl, ll, lam, 0);
     const double cos_wi = v_shading_cosine(S, cl, wi);
     const C4 radiance = cl.gathered * bsdf * emittance * c4(1.0) * cos_wi / p_lig;
@@ -344,9 +347,12 @@ __device__ __noinline__ C4 connect_paths(const DevScene& S, const Lam& lam, cons
 //                   vertex arrays go to the batch's vertex buffer in HBM, together with the number of connection
 //                   terms the sample has;
 //   (exclusive scan of the term counts)
-//   k_bdpt_connect  one thread per term: light tracing (t = 1, a splat), emission (s = 0), NEE (s = 1) or a
-//                   subpath connection (s, t >= 2) with its visibility ray and MIS weight; contributions are
-//                   added to the sample's radiance with f64 atomics;
+//   k_bdpt_connect<CLASS>  one thread per term of one class — light tracing (t = 1, a splat), emission (s = 0),
+//                   NEE (s = 1) or a subpath connection (s, t >= 2) with its visibility ray and MIS weight;
+//                   contributions are added to the sample's radiance with f64 atomics.  One launch per class with
+//                   its own dense term index: as ONE kernel over all terms (39 k SASS instructions, every lane of a
+//                   warp in another class) ncu showed 2.8 of 32 lanes active and 89 % of stall samples in
+//                   instruction fetch;
 //   k_bdpt_finish   one thread per sample: reference-style cost, tone map, film.
 // Random numbers: the terms that draw (light tracing: 2 per non-delta light vertex; NEE: 3 per camera vertex that is
 // neither delta nor a light) consume the sample's stream in the reference's order; a term finds its position by
@@ -359,14 +365,11 @@ struct BdptBatch {
     double* rx; double* ry;
     double* radiance;                // [4][cap]
     uint32_t *pixel, *sample, *draws, *witem, *valid;
-    unsigned long long* n_terms;     // per sample (cap + 1 entries, the last one 0)
-    unsigned long long* term_off;    // exclusive scan of n_terms, cap + 1 entries
+    unsigned long long* n_terms[3];  // per sample and class {light tracing, NEE, connection} (cap + 1 entries, the last one 0)
+    unsigned long long* term_off[3]; // their exclusive scans, cap + 1 entries (the emission class has one term per sample)
 };
+enum BdptClass { BC_LIGHT_TRACE = 0, BC_NEE = 1, BC_CONNECT = 2, BC_EMISSION = 3 };
 
-__device__ __forceinline__ uint32_t bdpt_term_count(int ns, int nt) {
-    const uint32_t L = ns >= 2 ? (uint32_t)(ns - 1) : 0u, C = nt >= 2 ? (uint32_t)(nt - 1) : 0u;
-    return L + 1u + C + L * C;
-}
 
 __global__ void __launch_bounds__(64) k_bdpt_walk(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P, const __grid_constant__ BdptBatch B,
                                                    unsigned long long w0, uint32_t n) {
@@ -392,7 +395,7 @@ __global__ void __launch_bounds__(64) k_bdpt_walk(const __grid_constant__ DevSce
         }
         B.valid[b] = ok ? 1u : 0u;
         B.witem[b] = (uint32_t)w;
-        if (!ok) { B.n_terms[b] = 0ull; B.ns[b] = 0; B.nt[b] = 0; continue; }
+        if (!ok) { B.n_terms[0][b] = 0ull; B.n_terms[1][b] = 0ull; B.n_terms[2][b] = 0ull; B.ns[b] = 0; B.nt[b] = 0; continue; }
         const uint32_t pixel = px + py * Wd;
         Rng rng = rng_make(P.seed, pixel, sample, 0u, 0u);
         double jx, jy;
@@ -416,7 +419,7 @@ __global__ void __launch_bounds__(64) k_bdpt_walk(const __grid_constant__ DevSce
             double pdf_origin, pdf_dir; light_leaving_pdf(S, (int)li, ri, ho.ng, pdf_origin, pdf_dir);
             const C4 emit = mat_emit(S, S.materials[ho.material], lam, ho);
             Vtx& root = lp[0];
-            root.h = ho; root.gathered = emit; root.light = (int)li; root.pdf_fwd = pdf_origin * pdf_light; root.pdf_bck = 0.0; root.wo = d3(0, 0, 0); root.pad = 0;
+            root.h = ho; root.gathered = emit; root.light = (int)li; root.pdf_fwd = pdf_origin * pdf_light; root.pdf_bck = 0.0; root.wo = d3(0, 0, 0); root.delta = 0;
             const C4 gathered = emit * fabs(dot(ri.d, ho.ns)) / (pdf_light * pdf_origin * pdf_dir);
             ns = bdpt_walk(S, ri, rng, lam, delta, gathered, pdf_dir, 1, lp, bc);
         }
@@ -426,7 +429,9 @@ __global__ void __launch_bounds__(64) k_bdpt_walk(const __grid_constant__ DevSce
             v_camera(cp[0], r.o, pdf_xo, c4(1.0));
             nt = bdpt_walk(S, r, rng, lam, delta, c4(1.0), pdf_wi, 0, cp, bc);
         }
-        B.ns[b] = ns; B.nt[b] = nt; B.n_terms[b] = (unsigned long long)bdpt_term_count(ns, nt);
+        B.ns[b] = ns; B.nt[b] = nt;
+        { const unsigned long long L = ns >= 2 ? (unsigned long long)(ns - 1) : 0ull, C = nt >= 2 ? (unsigned long long)(nt - 1) : 0ull;
+          B.n_terms[BC_LIGHT_TRACE][b] = L; B.n_terms[BC_NEE][b] = C; B.n_terms[BC_CONNECT][b] = L * C; }
         for (int k = 0; k < 4; k++) { B.lam[(size_t)k * B.cap + b] = lam.l[k]; B.radiance[(size_t)k * B.cap + b] = 0.0; }
         B.rx[b] = rx; B.ry[b] = ry; B.pixel[b] = pixel; B.sample[b] = sample; B.draws[b] = rng.draws;
     }
@@ -434,44 +439,45 @@ __global__ void __launch_bounds__(64) k_bdpt_walk(const __grid_constant__ DevSce
     if (bc.overflow) atomicAdd(&W.run->shadow_dropped, bc.overflow);
 }
 
+template <int CLS>
 __global__ void __launch_bounds__(128) k_bdpt_connect(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P, const __grid_constant__ BdptBatch B, uint32_t n) {
     BdptCounters bc = {0, 0, 0};
-    const unsigned long long total = B.term_off[n];
+    const unsigned long long* off = CLS == BC_EMISSION ? nullptr : B.term_off[CLS == BC_EMISSION ? 0 : CLS];
+    const unsigned long long total = CLS == BC_EMISSION ? (unsigned long long)n : off[n];
     for (unsigned long long it = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; it < total; it += (unsigned long long)gridDim.x * blockDim.x) {
-        // sample that owns term `it`: last b with term_off[b] <= it
-        uint32_t lo_ = 0, hi_ = n;
-        while (hi_ - lo_ > 1u) { const uint32_t mid = (lo_ + hi_) >> 1; if (B.term_off[mid] <= it) lo_ = mid; else hi_ = mid; }
-        const uint32_t b = lo_;
-        uint32_t j = (uint32_t)(it - B.term_off[b]);
+        uint32_t b, j = 0;
+        if (CLS == BC_EMISSION) b = (uint32_t)it;
+        else {                                                         // sample that owns term `it`: last b with off[b] <= it
+            uint32_t lo_ = 0, hi_ = n;
+            while (hi_ - lo_ > 1u) { const uint32_t mid = (lo_ + hi_) >> 1; if (off[mid] <= it) lo_ = mid; else hi_ = mid; }
+            b = lo_; j = (uint32_t)(it - off[b]);
+        }
         const int ns = B.ns[b], nt = B.nt[b];
-        const uint32_t L = ns >= 2 ? (uint32_t)(ns - 1) : 0u, C = nt >= 2 ? (uint32_t)(nt - 1) : 0u;
+        if (CLS == BC_EMISSION && nt == 0 && ns == 0) continue;        // an invalid sample has no terms at all
+        const uint32_t L = ns >= 2 ? (uint32_t)(ns - 1) : 0u;
         const Vtx* lp = B.lp + (size_t)b * LUMO_BDPT_MAXV;
         const Vtx* cp = B.cp + (size_t)b * LUMO_BDPT_MAXV;
         Lam lam; for (int k = 0; k < 4; k++) lam.l[k] = B.lam[(size_t)k * B.cap + b];
         C4 contrib = c4(0.0);
-        if (j < L) {                                                   // light tracing, s = j + 2 (bd_path_trace.rs:34-43)
+        if (CLS == BC_LIGHT_TRACE) {                                   // light tracing, s = j + 2 (bd_path_trace.rs:34-43)
             const int s = (int)j + 2;
             uint32_t drawing = 0;
             for (int q = 2; q < s; q++) if (!v_is_delta(S, lp[q - 1], lam)) drawing++;
             C4 col; double sx, sy;
-            const uint32_t sample = B.sample[b];
-            Rng rs = rng_make(P.seed, B.pixel[b], sample, 0u, B.draws[b] + 2u * drawing);
+            Rng rs = rng_make(P.seed, B.pixel[b], B.sample[b], 0u, B.draws[b] + 2u * drawing);
             if (connect_light_path(S, rs, lam, lp, s, col, sx, sy, bc) && P.mode == WM_MAIN)
                 film_add_sample(S, W.pixels, W.splats, tone_map(S, (int)P.tone_map, P.tone_map_arg, col, lam), lam, sx, sy, true);
             continue;
-        }
-        j -= L;
-        if (j == 0) contrib = add_camera_path(S, lam, cp, nt);          // s = 0
-        else if (j - 1u < C) {                                          // NEE, t = j + 1 (bd_path_trace.rs:47-55)
-            const int t = (int)(j - 1u) + 2;
+        } else if (CLS == BC_EMISSION) contrib = add_camera_path(S, lam, cp, nt);   // s = 0
+        else if (CLS == BC_NEE) {                                      // NEE, t = j + 2 (bd_path_trace.rs:47-55)
+            const int t = (int)j + 2;
             uint32_t drawing_l = 0, drawing_c = 0;
             for (int q = 2; q <= ns; q++) if (!v_is_delta(S, lp[q - 1], lam)) drawing_l++;
             for (int q = 2; q < t; q++) if (!(v_is_delta(S, cp[q - 1], lam) || v_is_light(cp[q - 1]))) drawing_c++;
             Rng rs = rng_make(P.seed, B.pixel[b], B.sample[b], 0u, B.draws[b] + 2u * drawing_l + 3u * drawing_c);
             contrib = connect_camera_path(S, rs, lam, cp, t, bc);
-        } else {                                                        // (s, t >= 2) connection; order: t outer, s inner (bd_path_trace.rs:57-66)
-            const uint32_t k = j - 1u - C;
-            const int t = (int)(k / L) + 2, s = (int)(k % L) + 2;
+        } else {                                                       // (s, t >= 2) connection; order: t outer, s inner (bd_path_trace.rs:57-66)
+            const int t = (int)(j / L) + 2, s = (int)(j % L) + 2;
             contrib = connect_paths(S, lam, lp, s, cp, t, bc);
         }
         if (!is_black(contrib)) for (int k = 0; k < 4; k++) if (contrib.s[k] != 0.0) atomicAdd(&B.radiance[(size_t)k * B.cap + b], contrib.s[k]);

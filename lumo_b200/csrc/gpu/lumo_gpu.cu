@@ -606,12 +606,12 @@ static int32_t bdpt_alloc(BdptStorage& st) {
         B.ns = c.take<int>(cap); B.nt = c.take<int>(cap);
         B.lam = c.take<double>(4 * (size_t)cap); B.rx = c.take<double>(cap); B.ry = c.take<double>(cap); B.radiance = c.take<double>(4 * (size_t)cap);
         B.pixel = c.take<uint32_t>(cap); B.sample = c.take<uint32_t>(cap); B.draws = c.take<uint32_t>(cap); B.witem = c.take<uint32_t>(cap); B.valid = c.take<uint32_t>(cap);
-        B.n_terms = c.take<unsigned long long>(cap + 1); B.term_off = c.take<unsigned long long>(cap + 1);
+        for (int k = 0; k < 3; k++) { B.n_terms[k] = c.take<unsigned long long>(cap + 1); B.term_off[k] = c.take<unsigned long long>(cap + 1); }
     };
     carve(dry);
     CU(st.mem.alloc(dry.off));
     Carver c{(uint8_t*)st.mem.p}; carve(c);
-    CU(cub::DeviceScan::ExclusiveSum(nullptr, st.scan_bytes, st.B.n_terms, st.B.term_off, (int)(cap + 1)));
+    CU(cub::DeviceScan::ExclusiveSum(nullptr, st.scan_bytes, st.B.n_terms[0], st.B.term_off[0], (int)(cap + 1)));
     CU(st.scan_tmp.alloc(st.scan_bytes));
     return LUMO_OK;
 }
@@ -624,14 +624,19 @@ static int32_t run_bdpt(lumo_scene* sc, const Wave& W, const WaveParams& P, Bdpt
         const uint32_t n = (uint32_t)std::min<unsigned long long>(B.cap, P.total_work - w0);
         CU(cudaEventRecord(ev[0], st));
         k_bdpt_walk<<<ctx->sm_count * 16, 64, 0, st>>>(sc->S, W, P, B, w0, n);
-        CU(cudaMemsetAsync(B.n_terms + n, 0, 8, st));
-        CU(cub::DeviceScan::ExclusiveSum(bs.scan_tmp.p, bs.scan_bytes, B.n_terms, B.term_off, (int)(n + 1), st));
+        for (int k = 0; k < 3; k++) {
+            CU(cudaMemsetAsync(B.n_terms[k] + n, 0, 8, st));
+            CU(cub::DeviceScan::ExclusiveSum(bs.scan_tmp.p, bs.scan_bytes, B.n_terms[k], B.term_off[k], (int)(n + 1), st));
+        }
         CU(cudaEventRecord(ev[1], st));
-        k_bdpt_connect<<<ctx->sm_count * 16, 128, 0, st>>>(sc->S, W, P, B, n);
+        k_bdpt_connect<BC_LIGHT_TRACE><<<ctx->sm_count * 16, 128, 0, st>>>(sc->S, W, P, B, n);
+        k_bdpt_connect<BC_EMISSION><<<ctx->sm_count * 16, 128, 0, st>>>(sc->S, W, P, B, n);
+        k_bdpt_connect<BC_NEE><<<ctx->sm_count * 16, 128, 0, st>>>(sc->S, W, P, B, n);
+        k_bdpt_connect<BC_CONNECT><<<ctx->sm_count * 16, 128, 0, st>>>(sc->S, W, P, B, n);
         CU(cudaEventRecord(ev[2], st));
         k_bdpt_finish<<<ctx->sm_count * 4, 256, 0, st>>>(sc->S, W, P, B, n);
         CU(cudaEventRecord(ev[3], st));
-        ctx->launches += 4; iterations++;
+        ctx->launches += 7; iterations++;
         CU(cudaStreamSynchronize(st));
         CU(cudaGetLastError());
         if (P.mode == WM_MAIN) {   // kernel classes for BDPT: [1] walks (incl. their traversal), [2] connections, [0] finish / film
