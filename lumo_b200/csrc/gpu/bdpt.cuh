@@ -122,62 +122,6 @@ __device__ __forceinline__ bool cam_sample_importance(const LumoCamera& C, const
 
 struct BdptCounters { unsigned long long closest, occlusion, overflow; };
 
-// ---- path generation (path_gen.rs) ---------------------------------------------------------------------
-// Returns the number of vertices written to vs[0..]; vs[0] = root must already be filled.
-__device__ __noinline__ int bdpt_walk(const DevScene& S, Ray ro, Rng& rng, Lam& lam, double delta, C4 gathered, double pdf_dir, int mode, Vtx* vs, BdptCounters& bc) {
-    uint32_t depth = 0;
-    int n = 1;
-    double pdf_fwd = pdf_dir;
-    for (;;) {
-        HitRec rec;
-        bc.closest++;
-        if (!scene_hit<false>(S, ro, LUMO_INF, rec, nullptr)) break;
-        if (n >= LUMO_BDPT_MAXV) { bc.overflow++; break; }
-        const DevHit ho = reconstruct_hit(S, ro, rec);
-        const Mat& m = S.materials[ho.material];
-        const uint32_t prev = depth;
-        const D3 wo = -ro.d;
-        Vtx& cv = vs[n];                                                                      // Vertex::surface, vertex.rs:51-84
-        const bool is_delta = mat_is_delta(S, m, lam);
-        cv.pdf_fwd = is_delta ? 0.0 : sa_to_area(pdf_fwd, vs[prev].h.p, ho.p, -wo, ho.ng);
-        cv.h = ho; cv.gathered = gathered; cv.wo = wo; cv.pdf_bck = 0.0; cv.light = -1; cv.delta = is_delta ? 1 : 0;
-        n++;
-        depth += 1;
-        const uint32_t curr = depth;
-        const double ru = rng_float(rng), r0 = rng_float(rng), r1 = rng_float(rng);
-        D3 wi;
-        const Onb uvw = shading_onb(S, m, ho);
-        if (!bsdf_sample<-1>(S, m, uvw, wo, ho, lam, ru, r0, r1, wi)) {
-            if (mode == 1) n--;                                                               // path_gen.rs:97-99: a light path cannot end on a light
-            else {                                                                            // Scene::get_light_at (bvh.rs:97-102)
-                Ray rl; rl.o = hit_ray_origin(ho, true); rl.d = normalize(-ho.ng);
-                RayCtx w; make_ctx(rl, w);
-                const uint32_t li = S.P.n_lights ? tlas_hit<true, false>(S, S.P.lights_root, S.P.n_objects, w, 0.0, LUMO_INF, nullptr) : LUMO_NONE;
-                vs[curr].light = li == LUMO_NONE ? -1 : (int)li;
-            }
-            break;
-        }
-        const Ray ri = hit_generate_ray(ho, wi);
-        wi = ri.d;
-        pdf_fwd = bsdf_pdf<-1>(S, m, uvw, wo, wi, ho, lam, false);
-        if (pdf_fwd == 0.0) break;
-        const double corr = mode == 0 ? 1.0 : v_shading_correction(S, vs[curr], wi);
-        const C4 bsdf = bsdf_f<-1>(S, m, uvw, wo, wi, lam, mode, ho);
-        gathered = gathered * (bsdf * v_shading_cosine(S, vs[curr], wi) * corr / pdf_fwd);
-        vs[prev].pdf_bck = v_pdf_prev(S, vs[curr], vs[prev], wi, lam);
-        if (depth >= LUMO_RR_DEPTH) {
-            const double lum = luminance(S, gathered, lam);
-            const double rr = fmin(lum / delta, 1.0);
-            if (rng_float(rng) > rr) break;
-            if (depth >= LUMO_BDPT_MAX_DEPTH) break;
-            gathered = gathered / rr;
-        }
-        if (is_delta) pdf_fwd = 0.0;
-        ro = ri;
-    }
-    return n;
-}
-
 // ---- MIS (mis.rs) ----------------------------------------------------------------------------------------
 __device__ __forceinline__ void light_leaving_pdf(const DevScene& S, int light, const Ray& r, D3 ng, double& pdf_origin, double& pdf_dir) {   // object.rs:120-127
     pdf_origin = 1.0 / S.lights[light].area;
@@ -343,9 +287,9 @@ __device__ __noinline__ C4 connect_paths(const DevScene& S, const Lam& lam, cons
 }
 
 // ---- the estimator: bd_path_trace::integrate (bd_path_trace.rs:23-75) as three kernels over a batch ------
-//   k_bdpt_walk     one thread per camera sample: camera ray, wavelengths, light subpath, camera subpath; the two
-//                   vertex arrays go to the batch's vertex buffer in HBM, together with the number of connection
-//                   terms the sample has;
+//   k_bw_setup / k_bw_trace / k_bw_step   the two random walks of every sample as a wavefront (below): camera ray,
+//                   wavelengths, light subpath, camera subpath; the two vertex arrays go to the batch's vertex
+//                   buffer in HBM, together with the number of connection terms the sample has per class;
 //   (exclusive scan of the term counts)
 //   k_bdpt_connect<CLASS>  one thread per term of one class — light tracing (t = 1, a splat), emission (s = 0),
 //                   NEE (s = 1) or a subpath connection (s, t >= 2) with its visibility ray and MIS weight;
@@ -365,78 +309,226 @@ struct BdptBatch {
     double* rx; double* ry;
     double* radiance;                // [4][cap]
     uint32_t *pixel, *sample, *draws, *witem, *valid;
+    // walk state of the sample's subpath in flight (k_bw_*): first the light subpath, then the camera subpath
+    double* w_ray;                   // [6][cap] current ray
+    double* w_cam;                   // [6][cap] the camera ray, drawn before the light walk (path_gen.rs draws in this order)
+    double* w_gathered;              // [4][cap]
+    double *w_pdf_fwd, *w_delta;     // solid-angle pdf of the last scatter; the tile's Russian-roulette threshold
+    uint32_t *w_phase, *w_n, *w_depth;   // 0 light walk, 1 camera walk; vertices written; scatter depth
+    double *w_ht, *w_hb0, *w_hb1, *w_hb2; uint32_t *w_hobj, *w_htri, *w_have;   // closest hit of the current ray (k_bw_trace)
+    uint32_t* act[2];                // active sample lists (double-buffered)
+    uint32_t* n_act;                 // [2]
     unsigned long long* n_terms[3];  // per sample and class {light tracing, NEE, connection} (cap + 1 entries, the last one 0)
     unsigned long long* term_off[3]; // their exclusive scans, cap + 1 entries (the emission class has one term per sample)
 };
 enum BdptClass { BC_LIGHT_TRACE = 0, BC_NEE = 1, BC_CONNECT = 2, BC_EMISSION = 3 };
 
 
-__global__ void __launch_bounds__(64) k_bdpt_walk(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P, const __grid_constant__ BdptBatch B,
-                                                   unsigned long long w0, uint32_t n) {
-    BdptCounters bc = {0, 0, 0};
+// ---- the two random walks of every sample as a wavefront ----------------------------------------------------
+// One subpath per sample is in flight: the light subpath first, then the camera subpath (they share the sample's
+// random stream and its wavelengths, which a dispersive scatter may terminate — path_gen.rs:21-50 then :4-19).
+// Per bounce: k_bw_trace (Scene::hit of every live subpath's ray, the same traversal as the wave kernels) and
+// k_bw_step (the body of path_gen::walk, path_gen.rs:53-157: vertex, BSDF sample, pdfs, throughput, roulette).
+// As ONE kernel per sample doing both walks with their traversals inline, ncu showed 3.6 of 32 lanes active.
+__device__ __forceinline__ void bw_append(const BdptBatch& B, uint32_t list, bool alive, uint32_t b) {
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, alive);
+    if (!m) return;
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t base = 0;
+    if (lane == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(&B.n_act[list], (uint32_t)__popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, __ffs(m) - 1);
+    if (alive) B.act[list][base + __popc(m & ((1u << lane) - 1u))] = b;
+}
+__device__ __forceinline__ void bw_store_ray(const BdptBatch& B, double* dst, uint32_t b, const Ray& r) {
+    const size_t c = B.cap;
+    dst[b] = r.o.x; dst[c + b] = r.o.y; dst[2 * c + b] = r.o.z; dst[3 * c + b] = r.d.x; dst[4 * c + b] = r.d.y; dst[5 * c + b] = r.d.z;
+}
+__device__ __forceinline__ Ray bw_load_ray(const BdptBatch& B, const double* src, uint32_t b) {
+    const size_t c = B.cap;
+    Ray r; r.o = d3(src[b], src[c + b], src[2 * c + b]); r.d = d3(src[3 * c + b], src[4 * c + b], src[5 * c + b]);
+    return r;
+}
+__device__ __forceinline__ void bw_finish_sample(const BdptBatch& B, uint32_t b, int ns, int nt) {
+    B.ns[b] = ns; B.nt[b] = nt;
+    const unsigned long long L = ns >= 2 ? (unsigned long long)(ns - 1) : 0ull, C = nt >= 2 ? (unsigned long long)(nt - 1) : 0ull;
+    B.n_terms[BC_LIGHT_TRACE][b] = L; B.n_terms[BC_NEE][b] = C; B.n_terms[BC_CONNECT][b] = L * C;
+}
+
+// per sample: pixel, camera ray, wavelengths, the light subpath's root and first ray (path_gen.rs:21-50)
+__global__ void __launch_bounds__(128) k_bw_setup(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P, const __grid_constant__ BdptBatch B,
+                                                  unsigned long long w0, uint32_t n) {
     const uint32_t Wd = S.P.camera.res_x, Hd = S.P.camera.res_y;
-    for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < n; b += gridDim.x * blockDim.x) {
-        const unsigned long long w = w0 + b;
-        uint32_t px, py, sample; bool ok = true;
-        if (P.mode == WM_PILOT) {
-            const uint32_t tile = (uint32_t)(w / LUMO_PILOT_N), k = (uint32_t)(w % LUMO_PILOT_N);
-            const uint32_t x0 = (tile % P.tiles_x) * 16u, y0 = (tile / P.tiles_x) * 16u;
-            px = min(x0 + 2u * (k % 8u), Wd - 1u); py = min(y0 + 2u * (k / 8u), Hd - 1u);
-            sample = 0xFFFFFF00u + P.pilot_round;
-        } else {
-            const unsigned long long per_s = (unsigned long long)P.tiles_x * P.tiles_y * 256ull;
-            const uint32_t si = (uint32_t)(w / per_s); const unsigned long long r = w % per_s;
-            const uint32_t tile = (uint32_t)(r / 256ull), q = (uint32_t)(r % 256ull);
-            const uint32_t blk = q / 32u, in = q % 32u;
-            px = (tile % P.tiles_x) * 16u + (blk % 2u) * 8u + (in % 8u);
-            py = (tile / P.tiles_x) * 16u + (blk / 2u) * 4u + (in / 8u);
-            sample = P.spp_begin + si;
-            ok = px < Wd && py < Hd;
+    const uint32_t n_pad = (n + 31u) & ~31u;
+    for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < n_pad; b += gridDim.x * blockDim.x) {
+        bool ok = b < n;
+        if (ok) {
+            const unsigned long long w = w0 + b;
+            uint32_t px, py, sample;
+            if (P.mode == WM_PILOT) {
+                const uint32_t tile = (uint32_t)(w / LUMO_PILOT_N), k = (uint32_t)(w % LUMO_PILOT_N);
+                const uint32_t x0 = (tile % P.tiles_x) * 16u, y0 = (tile / P.tiles_x) * 16u;
+                px = min(x0 + 2u * (k % 8u), Wd - 1u); py = min(y0 + 2u * (k / 8u), Hd - 1u);
+                sample = 0xFFFFFF00u + P.pilot_round;
+            } else {
+                const unsigned long long per_s = (unsigned long long)P.tiles_x * P.tiles_y * 256ull;
+                const uint32_t si = (uint32_t)(w / per_s); const unsigned long long r = w % per_s;
+                const uint32_t tile = (uint32_t)(r / 256ull), q = (uint32_t)(r % 256ull);
+                const uint32_t blk = q / 32u, in = q % 32u;
+                px = (tile % P.tiles_x) * 16u + (blk % 2u) * 8u + (in % 8u);
+                py = (tile / P.tiles_x) * 16u + (blk / 2u) * 4u + (in / 8u);
+                sample = P.spp_begin + si;
+                ok = px < Wd && py < Hd;
+            }
+            B.valid[b] = ok ? 1u : 0u;
+            B.witem[b] = (uint32_t)w;
+            if (!ok) bw_finish_sample(B, b, 0, 0);
+            else {
+                const uint32_t pixel = px + py * Wd;
+                Rng rng = rng_make(P.seed, pixel, sample, 0u, 0u);
+                double jx, jy;
+                if (P.mode == WM_PILOT) { jx = rng_float(rng); jy = rng_float(rng); } else raster_jitter(P, pixel, sample, rng, jx, jy);
+                const double rx = (double)px + jx, ry = (double)py + jy;
+                const double l0 = rng_float(rng), l1 = rng_float(rng);
+                const Ray r = camera_generate_ray(S.P.camera, rx, ry, l0, l1);
+                const Lam lam = lam_sample(rng_float(rng));
+                const uint32_t li = sample_light(S, rng_float(rng));
+                const double pdf_light = S.lights[li].pdf;
+                const LumoObject lo = S.objects[S.P.n_objects + li];
+                const double a0 = rng_float(rng), a1 = rng_float(rng), b0 = rng_float(rng), b1 = rng_float(rng);
+                const DevHit ho = light_sample_on(S, lo, a0, a1);                                  // Sampleable::sample_leaving, object.rs:107-117
+                const Onb uvw = onb_new(ho.ns);
+                const Ray ri = hit_generate_ray(ho, to_world(uvw, square_to_cos_hemisphere(b0, b1)));
+                double pdf_origin, pdf_dir; light_leaving_pdf(S, (int)li, ri, ho.ng, pdf_origin, pdf_dir);
+                const C4 emit = mat_emit(S, S.materials[ho.material], lam, ho);
+                Vtx& root = B.lp[(size_t)b * LUMO_BDPT_MAXV];
+                root.h = ho; root.gathered = emit; root.light = (int)li; root.pdf_fwd = pdf_origin * pdf_light; root.pdf_bck = 0.0; root.wo = d3(0, 0, 0); root.delta = 0;
+                const C4 gathered = emit * fabs(dot(ri.d, ho.ns)) / (pdf_light * pdf_origin * pdf_dir);
+                bw_store_ray(B, B.w_ray, b, ri); bw_store_ray(B, B.w_cam, b, r);
+                for (int k = 0; k < 4; k++) { B.w_gathered[(size_t)k * B.cap + b] = gathered.s[k]; B.lam[(size_t)k * B.cap + b] = lam.l[k]; B.radiance[(size_t)k * B.cap + b] = 0.0; }
+                B.w_pdf_fwd[b] = pdf_dir; B.w_delta[b] = W.tile_delta[tile_of(P, S, pixel)];
+                B.w_phase[b] = 0u; B.w_n[b] = 1u; B.w_depth[b] = 0u;
+                B.rx[b] = rx; B.ry[b] = ry; B.pixel[b] = pixel; B.sample[b] = sample; B.draws[b] = rng.draws;
+            }
         }
-        B.valid[b] = ok ? 1u : 0u;
-        B.witem[b] = (uint32_t)w;
-        if (!ok) { B.n_terms[0][b] = 0ull; B.n_terms[1][b] = 0ull; B.n_terms[2][b] = 0ull; B.ns[b] = 0; B.nt[b] = 0; continue; }
-        const uint32_t pixel = px + py * Wd;
-        Rng rng = rng_make(P.seed, pixel, sample, 0u, 0u);
-        double jx, jy;
-        if (P.mode == WM_PILOT) { jx = rng_float(rng); jy = rng_float(rng); } else raster_jitter(P, pixel, sample, rng, jx, jy);
-        const double rx = (double)px + jx, ry = (double)py + jy;
-        const double l0 = rng_float(rng), l1 = rng_float(rng);
-        const Ray r = camera_generate_ray(S.P.camera, rx, ry, l0, l1);
-        Lam lam = lam_sample(rng_float(rng));
-        const double delta = W.tile_delta[tile_of(P, S, pixel)];
-        Vtx* lp = B.lp + (size_t)b * LUMO_BDPT_MAXV;
-        Vtx* cp = B.cp + (size_t)b * LUMO_BDPT_MAXV;
-        int ns;
-        {   // light path (path_gen.rs:21-50)
-            const uint32_t li = sample_light(S, rng_float(rng));
-            const double pdf_light = S.lights[li].pdf;
-            const LumoObject lo = S.objects[S.P.n_objects + li];
-            const double a0 = rng_float(rng), a1 = rng_float(rng), b0 = rng_float(rng), b1 = rng_float(rng);
-            const DevHit ho = light_sample_on(S, lo, a0, a1);                                  // Sampleable::sample_leaving, object.rs:107-117
-            const Onb uvw = onb_new(ho.ns);
-            const Ray ri = hit_generate_ray(ho, to_world(uvw, square_to_cos_hemisphere(b0, b1)));
-            double pdf_origin, pdf_dir; light_leaving_pdf(S, (int)li, ri, ho.ng, pdf_origin, pdf_dir);
-            const C4 emit = mat_emit(S, S.materials[ho.material], lam, ho);
-            Vtx& root = lp[0];
-            root.h = ho; root.gathered = emit; root.light = (int)li; root.pdf_fwd = pdf_origin * pdf_light; root.pdf_bck = 0.0; root.wo = d3(0, 0, 0); root.delta = 0;
-            const C4 gathered = emit * fabs(dot(ri.d, ho.ns)) / (pdf_light * pdf_origin * pdf_dir);
-            ns = bdpt_walk(S, ri, rng, lam, delta, gathered, pdf_dir, 1, lp, bc);
-        }
-        int nt;
-        {   // camera path (path_gen.rs:4-19)
-            const double pdf_wi = cam_pdf_wi(S.P.camera, r), pdf_xo = cam_pdf_xo(S.P.camera, r);
-            v_camera(cp[0], r.o, pdf_xo, c4(1.0));
-            nt = bdpt_walk(S, r, rng, lam, delta, c4(1.0), pdf_wi, 0, cp, bc);
-        }
-        B.ns[b] = ns; B.nt[b] = nt;
-        { const unsigned long long L = ns >= 2 ? (unsigned long long)(ns - 1) : 0ull, C = nt >= 2 ? (unsigned long long)(nt - 1) : 0ull;
-          B.n_terms[BC_LIGHT_TRACE][b] = L; B.n_terms[BC_NEE][b] = C; B.n_terms[BC_CONNECT][b] = L * C; }
-        for (int k = 0; k < 4; k++) { B.lam[(size_t)k * B.cap + b] = lam.l[k]; B.radiance[(size_t)k * B.cap + b] = 0.0; }
-        B.rx[b] = rx; B.ry[b] = ry; B.pixel[b] = pixel; B.sample[b] = sample; B.draws[b] = rng.draws;
+        bw_append(B, 0u, ok, b);
     }
-    if (bc.closest) atomicAdd(&W.run->closest, bc.closest);
-    if (bc.overflow) atomicAdd(&W.run->shadow_dropped, bc.overflow);
+}
+
+// Scene::hit for the current ray of every live subpath.  Persistent warps pull 32 rays at a time from a cursor (n_act[2]):
+// ray costs differ by orders of magnitude (mirror / glass meshes), a static split leaves long tails.
+__global__ void __launch_bounds__(128, 8) k_bw_trace(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ BdptBatch B, uint32_t cur) {
+    const uint32_t n = B.n_act[cur];
+    if (blockIdx.x == 0 && threadIdx.x == 0) { B.n_act[cur ^ 1u] = 0u; if (n) atomicAdd(&W.run->closest, (unsigned long long)n); }
+    const uint32_t lane = threadIdx.x & 31u;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&B.n_act[2], 32u);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= n) break;
+        const uint32_t i = base + lane;
+        if (i < n) {
+            const uint32_t b = B.act[cur][i];
+            const Ray r = bw_load_ray(B, B.w_ray, b);
+            HitRec h;
+            if (scene_hit<false, LUMO_WAVE_KD_ROUND>(S, r, LUMO_INF, h, nullptr)) {
+                B.w_ht[b] = h.t; B.w_hb0[b] = h.bary.x; B.w_hb1[b] = h.bary.y; B.w_hb2[b] = h.bary.z; B.w_hobj[b] = h.obj; B.w_htri[b] = h.tri; B.w_have[b] = 1u;
+            } else B.w_have[b] = 0u;
+        }
+    }
+}
+
+// one iteration of path_gen::walk (path_gen.rs:53-157) for every live subpath; a light subpath that ends hands over to
+// the sample's camera subpath (path_gen.rs:4-19)
+__global__ void __launch_bounds__(128) k_bw_step(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P, const __grid_constant__ BdptBatch B, uint32_t cur) {
+    const uint32_t n_act = B.n_act[cur];
+    const uint32_t n_pad = (n_act + 31u) & ~31u;
+    if (blockIdx.x == 0 && threadIdx.x == 0) B.n_act[2] = 0u;             // the trace kernel's work cursor, for the next bounce
+    unsigned long long overflow = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x) {
+        bool alive = false; uint32_t b = 0;
+        if (i < n_act) {
+            b = B.act[cur][i];
+            const uint32_t phase = B.w_phase[b];
+            const int mode = phase == 0u ? 1 : 0;
+            Vtx* vs = (phase == 0u ? B.lp : B.cp) + (size_t)b * LUMO_BDPT_MAXV;
+            int n = (int)B.w_n[b];
+            uint32_t depth = B.w_depth[b];
+            bool end = false;
+            if (!B.w_have[b]) end = true;
+            else if (n >= LUMO_BDPT_MAXV) { overflow++; end = true; }
+            else {
+                const Ray ro = bw_load_ray(B, B.w_ray, b);
+                HitRec rec; rec.t = B.w_ht[b]; rec.bary = d3(B.w_hb0[b], B.w_hb1[b], B.w_hb2[b]); rec.obj = B.w_hobj[b]; rec.tri = B.w_htri[b];
+                Lam lam; C4 gathered;
+                for (int k = 0; k < 4; k++) { lam.l[k] = B.lam[(size_t)k * B.cap + b]; gathered.s[k] = B.w_gathered[(size_t)k * B.cap + b]; }
+                double pdf_fwd = B.w_pdf_fwd[b];
+                Rng rng = rng_make(P.seed, B.pixel[b], B.sample[b], 0u, B.draws[b]);
+                const DevHit ho = reconstruct_hit(S, ro, rec);
+                const Mat& m = S.materials[ho.material];
+                const uint32_t prev = depth;
+                const D3 wo = -ro.d;
+                Vtx& cv = vs[n];                                                                      // Vertex::surface, vertex.rs:51-84
+                const bool is_delta = mat_is_delta(S, m, lam);
+                cv.pdf_fwd = is_delta ? 0.0 : sa_to_area(pdf_fwd, vs[prev].h.p, ho.p, -wo, ho.ng);
+                cv.h = ho; cv.gathered = gathered; cv.wo = wo; cv.pdf_bck = 0.0; cv.light = -1; cv.delta = is_delta ? 1 : 0;
+                n++;
+                depth += 1;
+                const uint32_t curr = depth;
+                const double ru = rng_float(rng), r0 = rng_float(rng), r1 = rng_float(rng);
+                D3 wi;
+                const Onb uvw = shading_onb(S, m, ho);
+                if (!bsdf_sample<-1>(S, m, uvw, wo, ho, lam, ru, r0, r1, wi)) {
+                    if (mode == 1) n--;                                                               // path_gen.rs:97-99: a light path cannot end on a light
+                    else {                                                                            // Scene::get_light_at (bvh.rs:97-102)
+                        Ray rl; rl.o = hit_ray_origin(ho, true); rl.d = normalize(-ho.ng);
+                        RayCtx w; make_ctx(rl, w);
+                        const uint32_t li = S.P.n_lights ? tlas_hit<true, false>(S, S.P.lights_root, S.P.n_objects, w, 0.0, LUMO_INF, nullptr) : LUMO_NONE;
+                        vs[curr].light = li == LUMO_NONE ? -1 : (int)li;
+                    }
+                    end = true;
+                } else {
+                    const Ray ri = hit_generate_ray(ho, wi);
+                    wi = ri.d;
+                    pdf_fwd = bsdf_pdf<-1>(S, m, uvw, wo, wi, ho, lam, false);
+                    if (pdf_fwd == 0.0) end = true;
+                    else {
+                        const double corr = mode == 0 ? 1.0 : v_shading_correction(S, vs[curr], wi);
+                        const C4 bsdf = bsdf_f<-1>(S, m, uvw, wo, wi, lam, mode, ho);
+                        gathered = gathered * (bsdf * v_shading_cosine(S, vs[curr], wi) * corr / pdf_fwd);
+                        vs[prev].pdf_bck = v_pdf_prev(S, vs[curr], vs[prev], wi, lam);
+                        if (depth >= LUMO_RR_DEPTH) {
+                            const double lum = luminance(S, gathered, lam);
+                            const double rr = fmin(lum / B.w_delta[b], 1.0);
+                            if (rng_float(rng) > rr) end = true;
+                            else if (depth >= LUMO_BDPT_MAX_DEPTH) end = true;
+                            else gathered = gathered / rr;
+                        }
+                        if (!end) {
+                            if (is_delta) pdf_fwd = 0.0;
+                            bw_store_ray(B, B.w_ray, b, ri);
+                            for (int k = 0; k < 4; k++) B.w_gathered[(size_t)k * B.cap + b] = gathered.s[k];
+                            B.w_pdf_fwd[b] = pdf_fwd;
+                        }
+                    }
+                }
+                for (int k = 0; k < 4; k++) B.lam[(size_t)k * B.cap + b] = lam.l[k];      // a dispersive scatter may have terminated wavelengths
+                B.draws[b] = rng.draws;
+            }
+            if (!end) { B.w_n[b] = (uint32_t)n; B.w_depth[b] = depth; alive = true; }
+            else if (phase == 0u) {                                                               // light subpath done: start the camera subpath
+                B.ns[b] = n;
+                const Ray r = bw_load_ray(B, B.w_cam, b);
+                const double pdf_wi = cam_pdf_wi(S.P.camera, r), pdf_xo = cam_pdf_xo(S.P.camera, r);
+                v_camera(B.cp[(size_t)b * LUMO_BDPT_MAXV], r.o, pdf_xo, c4(1.0));
+                bw_store_ray(B, B.w_ray, b, r);
+                for (int k = 0; k < 4; k++) B.w_gathered[(size_t)k * B.cap + b] = 1.0;
+                B.w_pdf_fwd[b] = pdf_wi; B.w_phase[b] = 1u; B.w_n[b] = 1u; B.w_depth[b] = 0u;
+                alive = true;
+            } else bw_finish_sample(B, b, B.ns[b], n);
+        }
+        bw_append(B, cur ^ 1u, alive, b);
+    }
+    if (overflow) atomicAdd(&W.run->shadow_dropped, overflow);
 }
 
 template <int CLS>
@@ -444,7 +536,10 @@ __global__ void __launch_bounds__(128) k_bdpt_connect(const __grid_constant__ De
     BdptCounters bc = {0, 0, 0};
     const unsigned long long* off = CLS == BC_EMISSION ? nullptr : B.term_off[CLS == BC_EMISSION ? 0 : CLS];
     const unsigned long long total = CLS == BC_EMISSION ? (unsigned long long)n : off[n];
-    for (unsigned long long it = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; it < total; it += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long total_pad = (total + 31ull) & ~31ull;
+    for (unsigned long long it = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; it < total_pad; it += (unsigned long long)gridDim.x * blockDim.x) {
+        __syncwarp();                                                  // lanes whose term ended early must not run ahead into their next term:
+        if (it >= total) continue;                                     // without this, 20 terms per thread left 2.5 of 32 lanes converged
         uint32_t b, j = 0;
         if (CLS == BC_EMISSION) b = (uint32_t)it;
         else {                                                         // sample that owns term `it`: last b with off[b] <= it

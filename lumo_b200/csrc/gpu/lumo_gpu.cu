@@ -27,6 +27,7 @@ struct lumo_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // wave storage, grown on demand and reused across renders
     void* wave_mem = nullptr; size_t wave_bytes = 0;
+    void* bdpt_mem = nullptr; size_t bdpt_bytes = 0; void* bdpt_scan = nullptr; size_t bdpt_scan_bytes = 0;   // BDPT batch storage (vertex buffers), same policy
     unsigned long long* d_cursor = nullptr;            // work cursor of the ray-batch kernels
     uint8_t* blob_cache = nullptr; uint64_t blob_cache_bytes = 0;   // one recycled scene allocation (cudaFree / cudaMalloc stall unpredictably)
     void* film_mem = nullptr; size_t film_bytes = 0;   // device film of lumo_gpu_render (host-buffer entry point), reused across calls
@@ -91,6 +92,8 @@ extern "C" int32_t lumo_gpu_ctx_destroy(lumo_ctx* ctx) {
     if (!ctx) return LUMO_OK;
     cudaSetDevice(ctx->device);
     if (ctx->wave_mem) cudaFree(ctx->wave_mem);
+    if (ctx->bdpt_mem) cudaFree(ctx->bdpt_mem);
+    if (ctx->bdpt_scan) cudaFree(ctx->bdpt_scan);
     if (ctx->film_mem) cudaFree(ctx->film_mem);
     if (ctx->d_cursor) cudaFree(ctx->d_cursor);
     if (ctx->nm_mem) cudaFree(ctx->nm_mem);
@@ -595,24 +598,51 @@ static int32_t run_wave(lumo_scene* sc, const Wave& W, WaveParams P, uint64_t& i
 }
 
 // BDPT: batches of camera samples through walk -> scan -> connect -> finish (bdpt.cuh)
-#define LUMO_BDPT_BATCH (1u << 17)
-struct BdptStorage { DevBuf mem, scan_tmp; BdptBatch B; size_t scan_bytes = 0; };
-static int32_t bdpt_alloc(BdptStorage& st) {
-    const uint32_t cap = LUMO_BDPT_BATCH;
-    Carver dry{nullptr};
-    auto carve = [&](Carver& c) {
-        BdptBatch& B = st.B; B.cap = cap;
-        B.lp = c.take<Vtx>((size_t)cap * LUMO_BDPT_MAXV); B.cp = c.take<Vtx>((size_t)cap * LUMO_BDPT_MAXV);
-        B.ns = c.take<int>(cap); B.nt = c.take<int>(cap);
-        B.lam = c.take<double>(4 * (size_t)cap); B.rx = c.take<double>(cap); B.ry = c.take<double>(cap); B.radiance = c.take<double>(4 * (size_t)cap);
-        B.pixel = c.take<uint32_t>(cap); B.sample = c.take<uint32_t>(cap); B.draws = c.take<uint32_t>(cap); B.witem = c.take<uint32_t>(cap); B.valid = c.take<uint32_t>(cap);
-        for (int k = 0; k < 3; k++) { B.n_terms[k] = c.take<unsigned long long>(cap + 1); B.term_off[k] = c.take<unsigned long long>(cap + 1); }
-    };
-    carve(dry);
-    CU(st.mem.alloc(dry.off));
-    Carver c{(uint8_t*)st.mem.p}; carve(c);
-    CU(cub::DeviceScan::ExclusiveSum(nullptr, st.scan_bytes, st.B.n_terms[0], st.B.term_off[0], (int)(cap + 1)));
-    CU(st.scan_tmp.alloc(st.scan_bytes));
+// Samples per BDPT batch.  Every bounce of the walk wavefront costs at least one traversal's latency (~0.3 ms once a few
+// thousand subpaths are left), and long specular chains give 70+ bounces: large batches pay that tail once.  A sample
+// owns 2 x LUMO_BDPT_MAXV vertices (27 KB), so 2^20 samples are 28 GB of the 180 GB — sized down if memory is short.
+#define LUMO_BDPT_BATCH_MAX (1u << 20)
+struct BdptStorage { BdptBatch B; void* scan_tmp = nullptr; size_t scan_bytes = 0; };
+static void bdpt_carve(BdptBatch& B, Carver& c, uint32_t cap) {
+    B.cap = cap;
+    B.lp = c.take<Vtx>((size_t)cap * LUMO_BDPT_MAXV); B.cp = c.take<Vtx>((size_t)cap * LUMO_BDPT_MAXV);
+    B.ns = c.take<int>(cap); B.nt = c.take<int>(cap);
+    B.lam = c.take<double>(4 * (size_t)cap); B.rx = c.take<double>(cap); B.ry = c.take<double>(cap); B.radiance = c.take<double>(4 * (size_t)cap);
+    B.pixel = c.take<uint32_t>(cap); B.sample = c.take<uint32_t>(cap); B.draws = c.take<uint32_t>(cap); B.witem = c.take<uint32_t>(cap); B.valid = c.take<uint32_t>(cap);
+    for (int k = 0; k < 3; k++) { B.n_terms[k] = c.take<unsigned long long>(cap + 1); B.term_off[k] = c.take<unsigned long long>(cap + 1); }
+    B.w_ray = c.take<double>(6 * (size_t)cap); B.w_cam = c.take<double>(6 * (size_t)cap); B.w_gathered = c.take<double>(4 * (size_t)cap);
+    B.w_pdf_fwd = c.take<double>(cap); B.w_delta = c.take<double>(cap);
+    B.w_phase = c.take<uint32_t>(cap); B.w_n = c.take<uint32_t>(cap); B.w_depth = c.take<uint32_t>(cap);
+    B.w_ht = c.take<double>(cap); B.w_hb0 = c.take<double>(cap); B.w_hb1 = c.take<double>(cap); B.w_hb2 = c.take<double>(cap);
+    B.w_hobj = c.take<uint32_t>(cap); B.w_htri = c.take<uint32_t>(cap); B.w_have = c.take<uint32_t>(cap);
+    B.act[0] = c.take<uint32_t>(cap); B.act[1] = c.take<uint32_t>(cap); B.n_act = c.take<uint32_t>(4);
+}
+// batch storage for up to `want` samples, kept by the context and grown on demand
+static int32_t bdpt_alloc(lumo_ctx* ctx, BdptStorage& st, unsigned long long want) {
+    unsigned long long cap_max = LUMO_BDPT_BATCH_MAX;
+    if (const char* e = std::getenv("LUMO_BDPT_BATCH")) cap_max = std::max<unsigned long long>(1024ull, (unsigned long long)std::atoll(e));
+    uint32_t cap = (uint32_t)std::min<unsigned long long>(std::max<unsigned long long>((want + 1023ull) & ~1023ull, 1024ull), cap_max);
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    for (;;) {
+        Carver dry{nullptr}; BdptBatch tmp; bdpt_carve(tmp, dry, cap);
+        if (dry.off <= ctx->bdpt_bytes || dry.off <= (free_b + ctx->bdpt_bytes) / 2 || cap <= 16384u) {
+            if (dry.off > ctx->bdpt_bytes) {
+                if (ctx->bdpt_mem) { cudaFree(ctx->bdpt_mem); ctx->bdpt_mem = nullptr; ctx->bdpt_bytes = 0; }
+                CU(cudaMalloc(&ctx->bdpt_mem, dry.off)); ctx->bdpt_bytes = dry.off;
+            }
+            break;
+        }
+        cap /= 2;
+    }
+    Carver c{(uint8_t*)ctx->bdpt_mem}; bdpt_carve(st.B, c, cap);
+    size_t need = 0;
+    CU(cub::DeviceScan::ExclusiveSum(nullptr, need, st.B.n_terms[0], st.B.term_off[0], (int)(cap + 1)));
+    if (need > ctx->bdpt_scan_bytes) {
+        if (ctx->bdpt_scan) { cudaFree(ctx->bdpt_scan); ctx->bdpt_scan = nullptr; ctx->bdpt_scan_bytes = 0; }
+        CU(cudaMalloc(&ctx->bdpt_scan, need ? need : 16)); ctx->bdpt_scan_bytes = need;
+    }
+    st.scan_tmp = ctx->bdpt_scan; st.scan_bytes = ctx->bdpt_scan_bytes;
     return LUMO_OK;
 }
 static int32_t run_bdpt(lumo_scene* sc, const Wave& W, const WaveParams& P, BdptStorage& bs, uint64_t& iterations) {
@@ -620,13 +650,29 @@ static int32_t run_bdpt(lumo_scene* sc, const Wave& W, const WaveParams& P, Bdpt
     cudaStream_t st = ctx->stream;
     const BdptBatch& B = bs.B;
     cudaEvent_t* ev = ctx->kev;
+    static const bool bdpt_log = std::getenv("LUMO_BDPT_LOG") != nullptr;   // diagnostics: live subpaths and elapsed time every 8 bounces
     for (unsigned long long w0 = 0; w0 < P.total_work; w0 += B.cap) {
         const uint32_t n = (uint32_t)std::min<unsigned long long>(B.cap, P.total_work - w0);
         CU(cudaEventRecord(ev[0], st));
-        k_bdpt_walk<<<ctx->sm_count * 16, 64, 0, st>>>(sc->S, W, P, B, w0, n);
+        CU(cudaMemsetAsync(B.n_act, 0, 16, st));
+        k_bw_setup<<<ctx->sm_count * 8, 128, 0, st>>>(sc->S, W, P, B, w0, n);
+        ctx->launches += 1;
+        for (uint32_t it = 0;;) {                                        // one bounce of every live subpath per iteration; 8 iterations per host look
+            for (int k = 0; k < 8; k++, it++) {
+                k_bw_trace<<<ctx->sm_count * 8, 128, 0, st>>>(sc->S, W, B, it & 1u);
+                k_bw_step<<<ctx->sm_count * 8, 128, 0, st>>>(sc->S, W, P, B, it & 1u);
+            }
+            ctx->launches += 16;
+            uint32_t live = 0;
+            CU(cudaMemcpyAsync(&live, B.n_act + (it & 1u), 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            if (bdpt_log) { CU(cudaEventRecord(ev[4], st)); CU(cudaEventSynchronize(ev[4])); float ms = 0; CU(cudaEventElapsedTime(&ms, ev[0], ev[4]));
+                            std::fprintf(stderr, "[bdpt] batch %llu bounce %u live %u t %.3f ms\n", w0 / B.cap, it, live, ms); }
+            if (live == 0) break;
+        }
         for (int k = 0; k < 3; k++) {
             CU(cudaMemsetAsync(B.n_terms[k] + n, 0, 8, st));
-            CU(cub::DeviceScan::ExclusiveSum(bs.scan_tmp.p, bs.scan_bytes, B.n_terms[k], B.term_off[k], (int)(n + 1), st));
+            CU(cub::DeviceScan::ExclusiveSum(bs.scan_tmp, bs.scan_bytes, B.n_terms[k], B.term_off[k], (int)(n + 1), st));
         }
         CU(cudaEventRecord(ev[1], st));
         k_bdpt_connect<BC_LIGHT_TRACE><<<ctx->sm_count * 16, 128, 0, st>>>(sc->S, W, P, B, n);
@@ -636,7 +682,7 @@ static int32_t run_bdpt(lumo_scene* sc, const Wave& W, const WaveParams& P, Bdpt
         CU(cudaEventRecord(ev[2], st));
         k_bdpt_finish<<<ctx->sm_count * 4, 256, 0, st>>>(sc->S, W, P, B, n);
         CU(cudaEventRecord(ev[3], st));
-        ctx->launches += 7; iterations++;
+        ctx->launches += 6; iterations++;
         CU(cudaStreamSynchronize(st));
         CU(cudaGetLastError());
         if (P.mode == WM_MAIN) {   // kernel classes for BDPT: [1] walks (incl. their traversal), [2] connections, [0] finish / film
@@ -691,7 +737,7 @@ static int32_t render_impl(lumo_scene* sc, const lumo_render_params* rp, double*
     uint64_t iterations = 0;
     const bool bdpt = rp->integrator == LUMO_BD_PATH_TRACE;
     BdptStorage bs;
-    if (bdpt) { int32_t rc = bdpt_alloc(bs); if (rc != LUMO_OK) return rc; }
+    if (bdpt) { int32_t rc = bdpt_alloc(ctx, bs, std::max<unsigned long long>(main_work, (unsigned long long)n_tiles * LUMO_PILOT_N)); if (rc != LUMO_OK) return rc; }
     if (rp->rr_delta <= 0.0 && rp->integrator != LUMO_DIRECT_LIGHT) {
         // Per-tile Russian-roulette threshold (the role of task.rs:42-53): two pilot rounds, the second
         // using the first round's estimate.  Pilot paths never touch the film or the reported counters.

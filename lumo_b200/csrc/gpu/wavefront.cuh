@@ -407,7 +407,10 @@ __global__ void __launch_bounds__(128) k_terminal(const __grid_constant__ DevSce
 template <int K>
 __global__ void __launch_bounds__(128, LUMO_SCATTER_BLOCKS) k_scatter(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P) {
     const uint32_t N = W.n_slots, n = W.it->n_class[K & 7], cur = P.cur, nxt = P.cur ^ 1u;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t n_pad = (n + 31u) & ~31u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x) {
+        __syncwarp();                                 // keep the warp's lanes on the same item index (see k_nee)
+        if (i >= n) continue;
         const uint32_t slot = W.cls[K & 7][i];
         Ray ro; HitRec rec; load_path(W, cur, slot, ro, rec);
         const DevHit ho = reconstruct_hit(S, ro, rec);
@@ -485,6 +488,7 @@ __global__ void __launch_bounds__(128, LUMO_NEE_BLOCKS) k_nee(const __grid_const
     const uint32_t per = SPLIT ? 2u * ns : ns;
     const unsigned long long padded = (unsigned long long)((nq + 31u) / 32u) * 32ull * per;
     for (unsigned long long it = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; it < padded; it += (unsigned long long)gridDim.x * blockDim.x) {
+        __syncwarp();                                 // a lane whose item ended early waits here instead of running ahead into its next one
         const unsigned long long grp = it / (32ull * per);
         const uint32_t j = (uint32_t)((it / 32ull) % per);
         const uint32_t qi = (uint32_t)(grp * 32ull + (it % 32ull));
