@@ -148,6 +148,20 @@ def cpu_baseline(prog, integrator, threads, spp=1, total_spp=None, seed=1):
     return rays / dt / 1e6, cnt["camera_paths"] / dt / 1e6, dt, cnt
 
 
+_RESULT_OUT = None
+
+
+def _guard_stdout():
+    """stdout carries exactly ONE JSON line.  Libraries write there too (NCCL prints its version banner on communicator
+    creation, `make` may echo): keep the real stdout for the result and point fd 1 at stderr for everybody else."""
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+    return _RESULT_OUT
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -167,7 +181,7 @@ def run_reference(args):
             "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": threads, "kind": "port",
                              "sample": "1 spp of the full-resolution workload per step (lumo CPU path, C++ restatement; the Rust reference cannot be built offline)"},
             "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    print(json.dumps(line), file=_guard_stdout(), flush=True)
     return 0
 
 
@@ -183,6 +197,7 @@ def main():
     ap.add_argument("--other-scenes", default="cornell,dragon,caustics_bdpt,conference,conference_dl,bistro,textured", help="comma list measured briefly after the main workload ('' = none)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
+    _guard_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -360,7 +375,7 @@ def main():
                 others[name] = {"error": str(e)}
         line["other_scenes"] = others
 
-    print(json.dumps(line))
+    print(json.dumps(line), file=_guard_stdout(), flush=True)
     scene.close(); ctx.close()
     if dist is not None:
         dist.barrier(); dist.destroy_process_group()
