@@ -174,3 +174,24 @@ def test_camera_film_sampler_variants(variant, gpu_ctx):
     assert bad.mean() <= 0.25, (variant, float(bad.mean()))              # wide filters spread each flipped path over many pixels
     assert abs(gpx[..., :3].sum() - epx[..., :3].sum()) <= 0.02 * abs(epx[..., :3].sum()) + 1e-9
     G.close(); O.close()
+
+
+def test_bdpt_batching_is_invisible(gpu_ctx):
+    """BDPT runs in batches of samples (vertex buffers in HBM, up to 2^20 samples; LUMO_BDPT_BATCH overrides the cap).  The batch
+    size must not change anything but the order of the film's atomic adds: same counters, same image to rounding."""
+    import os
+    from lumo_b200 import native
+    prog, blob, _ = small_scene("caustics")
+    G = native.GpuScene(gpu_ctx, blob)
+    ref = G.render(integrator=2, spp=3, seed=9)
+    for cap in ("1024", "5000"):
+        os.environ["LUMO_BDPT_BATCH"] = cap
+        try:
+            got = G.render(integrator=2, spp=3, seed=9)
+        finally:
+            del os.environ["LUMO_BDPT_BATCH"]
+        for k in ("camera_paths", "closest", "occlusion", "cost", "max_depth", "nonfinite"):
+            assert got[2][k] == ref[2][k], (cap, k, got[2][k], ref[2][k])
+        assert got[2]["iterations"] > ref[2]["iterations"]                      # it really ran in more batches
+        assert np.allclose(got[0], ref[0], rtol=1e-9, atol=1e-12) and np.allclose(got[1], ref[1], rtol=1e-9, atol=1e-12), cap
+    G.close()
