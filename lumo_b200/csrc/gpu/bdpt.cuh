@@ -203,30 +203,6 @@ __device__ __noinline__ double mis_weight(const DevScene& S, const Lam& l, const
 }
 
 // ---- connections (bd_path_trace.rs:77-290) ---------------------------------------------------------------
-__device__ __noinline__ bool connect_light_path(const DevScene& S, Rng& rng, const Lam& lam, const Vtx* lp, int s, C4& color, double& rx, double& ry, BdptCounters& bc) {
-    const Vtx& ll = lp[s - 1];
-    if (v_is_delta(S, ll, lam)) return false;
-    const D3 xi = ll.h.p;
-    Ray ri;
-    const double r0 = rng_float(rng), r1 = rng_float(rng);
-    if (!cam_sample_towards(S.P.camera, xi, r0, r1, ri)) return false;
-    const D3 xo = ri.o, wi = ri.d;
-    const double p_sct = v_bsdf_pdf(S, ll, -wi, lam, false);
-    const double p_imp = cam_pdf_importance(S.P.camera, ri, xi);
-    if (p_sct == 0.0 || p_imp == 0.0) return false;
-    HitRec rec;
-    bc.closest++;
-    if (!scene_hit<false>(S, ri, LUMO_INF, rec, nullptr)) return false;
-    const DevHit hh = reconstruct_hit(S, ri, rec);
-    if (max_element(vabs(hh.p - xi)) > sqrt(LUMO_EPS)) return false;
-    if (!cam_sample_importance(S.P.camera, ri, color, rx, ry)) return false;
-    if (is_black(color)) return false;
-    color = color / p_imp;
-    Vtx cl; v_camera(cl, xo, cam_pdf_xo(S.P.camera, ri), color / p_imp);
-    color = color * (ll.gathered * c4(1.0) * v_shading_cosine(S, ll, -wi) * v_shading_correction(S, ll, -wi)
-                     * v_f(S, ll, cl, lam, 1) * mis_weight(S, lam, lp, s, nullptr, 1, nullptr, &cl));
-    return true;
-}
 __device__ __noinline__ C4 add_camera_path(const DevScene& S, const Lam& lam, const Vtx* cp, int t) {
     const Vtx& ct = cp[t - 1];
     if (!v_is_light(ct)) return c4(0.0);
@@ -265,38 +241,16 @@ __device__ __noinline__ C4 connect_camera_path(const DevScene& S, Rng& rng, cons
     const C4 radiance = cl.gathered * bsdf * emittance * c4(1.0) * cos_wi / p_lig;
     return radiance * mis_weight(S, lam, nullptr, 1, cp, t, &ll, nullptr);
 }
-__device__ __noinline__ bool bdpt_visible(const DevScene& S, const DevHit& h1, const DevHit& h2, BdptCounters& bc) {          // :279-290
-    const D3 xo = h1.p, xi = h2.p;
-    const Ray ri = hit_generate_ray(h1, xi - xo);
-    const D3 wi = ri.d;
-    if (dot(wi, h1.ng) < LUMO_EPS) return false;
-    bc.occlusion++;
-    return fabs(sqrt(fmax(dist2(xo, xi), 0.0)) - scene_hit_t<false>(S, ri, nullptr)) < LUMO_EPS;
-}
-__device__ __noinline__ C4 connect_paths(const DevScene& S, const Lam& lam, const Vtx* lp, int s, const Vtx* cp, int t, BdptCounters& bc) {
-    const Vtx& ll = lp[s - 1]; const Vtx& cl = cp[t - 1];
-    if (v_is_delta(S, cl, lam) || v_is_light(cl) || v_is_delta(S, ll, lam) || !bdpt_visible(S, ll.h, cl.h, bc)) return c4(0.0);
-    const D3 xc = cl.h.p, xl = ll.h.p;
-    const D3 wi = normalize(xl - xc);
-    const double p_sct = v_bsdf_pdf(S, cl, wi, lam, false) * v_bsdf_pdf(S, ll, -wi, lam, false);
-    if (p_sct == 0.0) return c4(0.0);
-    const C4 lb = v_f(S, ll, cl, lam, 1), cb = v_f(S, cl, ll, lam, 0);
-    const C4 radiance = ll.gathered * lb * v_shading_cosine(S, ll, -wi) * cl.gathered * cb * v_shading_cosine(S, cl, wi) * c4(1.0) / dist2(xc, xl);
-    if (is_black(radiance)) return c4(0.0);
-    return radiance * mis_weight(S, lam, lp, s, cp, t, nullptr, nullptr);
-}
-
 // ---- the estimator: bd_path_trace::integrate (bd_path_trace.rs:23-75) as three kernels over a batch ------
 //   k_bw_setup / k_bw_trace / k_bw_step   the two random walks of every sample as a wavefront (below): camera ray,
 //                   wavelengths, light subpath, camera subpath; the two vertex arrays go to the batch's vertex
 //                   buffer in HBM, together with the number of connection terms the sample has per class;
 //   (exclusive scan of the term counts)
-//   k_bdpt_connect<CLASS>  one thread per term of one class — light tracing (t = 1, a splat), emission (s = 0),
-//                   NEE (s = 1) or a subpath connection (s, t >= 2) with its visibility ray and MIS weight;
-//                   contributions are added to the sample's radiance with f64 atomics.  One launch per class with
-//                   its own dense term index: as ONE kernel over all terms (39 k SASS instructions, every lane of a
-//                   warp in another class) ncu showed 2.8 of 32 lanes active and 89 % of stall samples in
-//                   instruction fetch;
+//   per term class, each with its own dense term index — emission (s = 0) and NEE (s = 1): k_bdpt_connect<CLASS>, one
+//                   thread per term; light tracing (t = 1, a splat) and subpath connections (s, t >= 2): k_bq_prepare /
+//                   k_bq_trace / k_bq_finish through a visibility-ray queue; contributions are added to the sample's
+//                   radiance with f64 atomics.  As ONE kernel over all terms (39 k SASS instructions, every lane of a
+//                   warp in another class) ncu showed 2.8 of 32 lanes active and 89 % of stall samples in instruction fetch;
 //   k_bdpt_finish   one thread per sample: reference-style cost, tone map, film.
 // Random numbers: the terms that draw (light tracing: 2 per non-delta light vertex; NEE: 3 per camera vertex that is
 // neither delta nor a light) consume the sample's stream in the reference's order; a term finds its position by
@@ -318,6 +272,12 @@ struct BdptBatch {
     double *w_ht, *w_hb0, *w_hb1, *w_hb2; uint32_t *w_hobj, *w_htri, *w_have;   // closest hit of the current ray (k_bw_trace)
     uint32_t* act[2];                // active sample lists (double-buffered)
     uint32_t* n_act;                 // [2]
+    // visibility-ray queue of the light-tracing and connection classes (k_bq_*): a chunk of terms at a time
+    uint32_t qcap;
+    unsigned long long* q_term;      // b | s << 32 | t << 48
+    double* q_ray;                   // [6][qcap]
+    double *q_ht, *q_hb0, *q_hb1, *q_hb2; uint32_t *q_hobj, *q_htri, *q_have;   // closest hit (light tracing) / q_ht = first-found distance (connections)
+    uint32_t* q_n;                   // [0] entries, [1] trace cursor
     unsigned long long* n_terms[3];  // per sample and class {light tracing, NEE, connection} (cap + 1 entries, the last one 0)
     unsigned long long* term_off[3]; // their exclusive scans, cap + 1 entries (the emission class has one term per sample)
 };
@@ -531,10 +491,12 @@ __global__ void __launch_bounds__(128) k_bw_step(const __grid_constant__ DevScen
     if (overflow) atomicAdd(&W.run->shadow_dropped, overflow);
 }
 
+// emission (s = 0) and next-event estimation (s = 1) terms: one thread per term of the class
 template <int CLS>
 __global__ void __launch_bounds__(128) k_bdpt_connect(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P, const __grid_constant__ BdptBatch B, uint32_t n) {
+    static_assert(CLS == BC_EMISSION || CLS == BC_NEE, "light tracing and connections go through k_bq_*");
     BdptCounters bc = {0, 0, 0};
-    const unsigned long long* off = CLS == BC_EMISSION ? nullptr : B.term_off[CLS == BC_EMISSION ? 0 : CLS];
+    const unsigned long long* off = B.term_off[BC_NEE];
     const unsigned long long total = CLS == BC_EMISSION ? (unsigned long long)n : off[n];
     const unsigned long long total_pad = (total + 31ull) & ~31ull;
     for (unsigned long long it = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; it < total_pad; it += (unsigned long long)gridDim.x * blockDim.x) {
@@ -549,36 +511,160 @@ __global__ void __launch_bounds__(128) k_bdpt_connect(const __grid_constant__ De
         }
         const int ns = B.ns[b], nt = B.nt[b];
         if (CLS == BC_EMISSION && nt == 0 && ns == 0) continue;        // an invalid sample has no terms at all
-        const uint32_t L = ns >= 2 ? (uint32_t)(ns - 1) : 0u;
         const Vtx* lp = B.lp + (size_t)b * LUMO_BDPT_MAXV;
         const Vtx* cp = B.cp + (size_t)b * LUMO_BDPT_MAXV;
         Lam lam; for (int k = 0; k < 4; k++) lam.l[k] = B.lam[(size_t)k * B.cap + b];
         C4 contrib = c4(0.0);
-        if (CLS == BC_LIGHT_TRACE) {                                   // light tracing, s = j + 2 (bd_path_trace.rs:34-43)
-            const int s = (int)j + 2;
-            uint32_t drawing = 0;
-            for (int q = 2; q < s; q++) if (!v_is_delta(S, lp[q - 1], lam)) drawing++;
-            C4 col; double sx, sy;
-            Rng rs = rng_make(P.seed, B.pixel[b], B.sample[b], 0u, B.draws[b] + 2u * drawing);
-            if (connect_light_path(S, rs, lam, lp, s, col, sx, sy, bc) && P.mode == WM_MAIN)
-                film_add_sample(S, W.pixels, W.splats, tone_map(S, (int)P.tone_map, P.tone_map_arg, col, lam), lam, sx, sy, true);
-            continue;
-        } else if (CLS == BC_EMISSION) contrib = add_camera_path(S, lam, cp, nt);   // s = 0
-        else if (CLS == BC_NEE) {                                      // NEE, t = j + 2 (bd_path_trace.rs:47-55)
+        if (CLS == BC_EMISSION) contrib = add_camera_path(S, lam, cp, nt);          // s = 0
+        else {                                                         // NEE, t = j + 2 (bd_path_trace.rs:47-55)
             const int t = (int)j + 2;
-            uint32_t drawing_l = 0, drawing_c = 0;
-            for (int q = 2; q <= ns; q++) if (!v_is_delta(S, lp[q - 1], lam)) drawing_l++;
+            uint32_t drawing_l = 0, drawing_c = 0;                     // draws before this term, in the reference's order: 2 per non-delta light
+            for (int q = 2; q <= ns; q++) if (!v_is_delta(S, lp[q - 1], lam)) drawing_l++;      // vertex (light tracing), 3 per earlier NEE term
             for (int q = 2; q < t; q++) if (!(v_is_delta(S, cp[q - 1], lam) || v_is_light(cp[q - 1]))) drawing_c++;
             Rng rs = rng_make(P.seed, B.pixel[b], B.sample[b], 0u, B.draws[b] + 2u * drawing_l + 3u * drawing_c);
             contrib = connect_camera_path(S, rs, lam, cp, t, bc);
-        } else {                                                       // (s, t >= 2) connection; order: t outer, s inner (bd_path_trace.rs:57-66)
-            const int t = (int)(j / L) + 2, s = (int)(j % L) + 2;
-            contrib = connect_paths(S, lam, lp, s, cp, t, bc);
         }
         if (!is_black(contrib)) for (int k = 0; k < 4; k++) if (contrib.s[k] != 0.0) atomicAdd(&B.radiance[(size_t)k * B.cap + b], contrib.s[k]);
     }
     if (bc.closest) atomicAdd(&W.run->closest, bc.closest);
     if (bc.occlusion) atomicAdd(&W.run->occlusion, bc.occlusion);
+}
+
+// ---- light tracing (t = 1) and (s, t >= 2) connections through a visibility-ray queue ---------------------------
+// Both classes spend most of their time in one traversal per term, and most terms are rejected before or by it.  Run
+// inside the term's thread that traversal kept 4.5-5.8 of 32 lanes busy.  So, per chunk of terms:
+//   k_bq_prepare<CLASS>  the cheap rejections of connect_light_path / connect_paths + visible() up to the ray
+//                        (bd_path_trace.rs:77-113, 230-290); survivors are compacted into the queue with their ray;
+//   k_bq_trace<CLASS>    Scene::hit (light tracing) or Scene::hit_t (visible(), first-found semantics) for the queue;
+//   k_bq_finish<CLASS>   the rest of the term for the queue entries: BSDFs, importance, MIS weight, splat / radiance.
+__device__ __forceinline__ void bq_term_of(const BdptBatch& B, int cls, unsigned long long it, uint32_t n, uint32_t& b, int& s, int& t) {
+    const unsigned long long* off = B.term_off[cls];
+    uint32_t lo_ = 0, hi_ = n;
+    while (hi_ - lo_ > 1u) { const uint32_t mid = (lo_ + hi_) >> 1; if (off[mid] <= it) lo_ = mid; else hi_ = mid; }
+    b = lo_;
+    const uint32_t j = (uint32_t)(it - off[b]);
+    if (cls == BC_LIGHT_TRACE) { s = (int)j + 2; t = 1; }
+    else { const int ns = B.ns[b]; const uint32_t L = (uint32_t)(ns - 1); t = (int)(j / L) + 2; s = (int)(j % L) + 2; }   // t outer, s inner (bd_path_trace.rs:57-66)
+}
+__device__ __forceinline__ Rng bq_light_trace_rng(const DevScene& S, const WaveParams& P, const BdptBatch& B, uint32_t b, const Vtx* lp, int s, const Lam& lam) {
+    uint32_t drawing = 0;                                               // 2 draws per non-delta light vertex before this one, in the reference's order
+    for (int q = 2; q < s; q++) if (!v_is_delta(S, lp[q - 1], lam)) drawing++;
+    return rng_make(P.seed, B.pixel[b], B.sample[b], 0u, B.draws[b] + 2u * drawing);
+}
+template <int CLS>
+__global__ void __launch_bounds__(128) k_bq_prepare(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P, const __grid_constant__ BdptBatch B,
+                                                    uint32_t n, unsigned long long t0, uint32_t count) {
+    const uint32_t count_pad = (count + 31u) & ~31u, lane = threadIdx.x & 31u;
+    unsigned long long traced = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count_pad; i += gridDim.x * blockDim.x) {
+        bool keep = false; Ray ri; ri.o = d3(0, 0, 0); ri.d = d3(0, 0, 0); unsigned long long key = 0;
+        if (i < count) {
+            uint32_t b; int s, t;
+            bq_term_of(B, CLS, t0 + i, n, b, s, t);
+            const Vtx* lp = B.lp + (size_t)b * LUMO_BDPT_MAXV;
+            const Vtx* cp = B.cp + (size_t)b * LUMO_BDPT_MAXV;
+            Lam lam; for (int k = 0; k < 4; k++) lam.l[k] = B.lam[(size_t)k * B.cap + b];
+            key = (unsigned long long)b | ((unsigned long long)s << 32) | ((unsigned long long)t << 48);
+            const Vtx& ll = lp[s - 1];
+            if (CLS == BC_LIGHT_TRACE) {                                // connect_light_path up to its Scene::hit (bd_path_trace.rs:77-113)
+                if (!v_is_delta(S, ll, lam)) {
+                    Rng rs = bq_light_trace_rng(S, P, B, b, lp, s, lam);
+                    const double r0 = rng_float(rs), r1 = rng_float(rs);
+                    if (cam_sample_towards(S.P.camera, ll.h.p, r0, r1, ri)) {
+                        const double p_sct = v_bsdf_pdf(S, ll, -ri.d, lam, false);
+                        const double p_imp = cam_pdf_importance(S.P.camera, ri, ll.h.p);
+                        keep = !(p_sct == 0.0 || p_imp == 0.0);
+                    }
+                }
+            } else {                                                    // connect_paths up to visible()'s Scene::hit_t (:230-290)
+                const Vtx& cl = cp[t - 1];
+                if (!(v_is_delta(S, cl, lam) || v_is_light(cl) || v_is_delta(S, ll, lam))) {
+                    ri = hit_generate_ray(ll.h, cl.h.p - ll.h.p);
+                    keep = !(dot(ri.d, ll.h.ng) < LUMO_EPS);
+                }
+            }
+        }
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
+        if (m) {
+            uint32_t base = 0;
+            if (lane == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(&B.q_n[0], (uint32_t)__popc(m));
+            base = __shfl_sync(0xFFFFFFFFu, base, __ffs(m) - 1);
+            if (keep) {
+                const uint32_t q = base + __popc(m & ((1u << lane) - 1u));
+                B.q_term[q] = key;
+                const size_t c = B.qcap;
+                B.q_ray[q] = ri.o.x; B.q_ray[c + q] = ri.o.y; B.q_ray[2 * c + q] = ri.o.z; B.q_ray[3 * c + q] = ri.d.x; B.q_ray[4 * c + q] = ri.d.y; B.q_ray[5 * c + q] = ri.d.z;
+                traced++;
+            }
+        }
+    }
+    if (traced) atomicAdd(CLS == BC_LIGHT_TRACE ? &W.run->closest : &W.run->occlusion, traced);
+}
+template <int CLS>
+__global__ void __launch_bounds__(128, 8) k_bq_trace(const __grid_constant__ DevScene S, const __grid_constant__ BdptBatch B) {
+    const uint32_t n = B.q_n[0], lane = threadIdx.x & 31u;
+    const size_t c = B.qcap;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&B.q_n[1], 32u);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= n) break;
+        const uint32_t q = base + lane;
+        if (q < n) {
+            Ray r; r.o = d3(B.q_ray[q], B.q_ray[c + q], B.q_ray[2 * c + q]); r.d = d3(B.q_ray[3 * c + q], B.q_ray[4 * c + q], B.q_ray[5 * c + q]);
+            if (CLS == BC_LIGHT_TRACE) {
+                HitRec h;
+                if (scene_hit<false, LUMO_WAVE_KD_ROUND>(S, r, LUMO_INF, h, nullptr)) {
+                    B.q_ht[q] = h.t; B.q_hb0[q] = h.bary.x; B.q_hb1[q] = h.bary.y; B.q_hb2[q] = h.bary.z; B.q_hobj[q] = h.obj; B.q_htri[q] = h.tri; B.q_have[q] = 1u;
+                } else B.q_have[q] = 0u;
+            } else B.q_ht[q] = scene_hit_t<false>(S, r, nullptr);
+        }
+    }
+}
+template <int CLS>
+__global__ void __launch_bounds__(128) k_bq_finish(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P, const __grid_constant__ BdptBatch B) {
+    const uint32_t n = B.q_n[0];
+    const uint32_t n_pad = (n + 31u) & ~31u;
+    const size_t c = B.qcap;
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n_pad; q += gridDim.x * blockDim.x) {
+        __syncwarp();
+        if (q >= n) continue;
+        const unsigned long long key = B.q_term[q];
+        const uint32_t b = (uint32_t)key; const int s = (int)((key >> 32) & 0xFFFFu), t = (int)(key >> 48);
+        const Vtx* lp = B.lp + (size_t)b * LUMO_BDPT_MAXV;
+        const Vtx* cp = B.cp + (size_t)b * LUMO_BDPT_MAXV;
+        Lam lam; for (int k = 0; k < 4; k++) lam.l[k] = B.lam[(size_t)k * B.cap + b];
+        Ray ri; ri.o = d3(B.q_ray[q], B.q_ray[c + q], B.q_ray[2 * c + q]); ri.d = d3(B.q_ray[3 * c + q], B.q_ray[4 * c + q], B.q_ray[5 * c + q]);
+        const Vtx& ll = lp[s - 1];
+        if (CLS == BC_LIGHT_TRACE) {                                    // the rest of connect_light_path (bd_path_trace.rs:96-113)
+            if (!B.q_have[q]) continue;
+            HitRec rec; rec.t = B.q_ht[q]; rec.bary = d3(B.q_hb0[q], B.q_hb1[q], B.q_hb2[q]); rec.obj = B.q_hobj[q]; rec.tri = B.q_htri[q];
+            const D3 xi = ll.h.p, xo = ri.o, wi = ri.d;
+            const DevHit hh = reconstruct_hit(S, ri, rec);
+            if (max_element(vabs(hh.p - xi)) > sqrt(LUMO_EPS)) continue;
+            C4 color; double sx, sy;
+            if (!cam_sample_importance(S.P.camera, ri, color, sx, sy)) continue;
+            if (is_black(color)) continue;
+            const double p_imp = cam_pdf_importance(S.P.camera, ri, xi);
+            color = color / p_imp;
+            Vtx cl; v_camera(cl, xo, cam_pdf_xo(S.P.camera, ri), color / p_imp);
+            color = color * (ll.gathered * c4(1.0) * v_shading_cosine(S, ll, -wi) * v_shading_correction(S, ll, -wi)
+                             * v_f(S, ll, cl, lam, 1) * mis_weight(S, lam, lp, s, nullptr, 1, nullptr, &cl));
+            if (P.mode == WM_MAIN) film_add_sample(S, W.pixels, W.splats, tone_map(S, (int)P.tone_map, P.tone_map_arg, color, lam), lam, sx, sy, true);
+        } else {                                                        // visible()'s comparison and the rest of connect_paths (:243-255, :286-289)
+            const Vtx& cl = cp[t - 1];
+            const D3 xc = cl.h.p, xl = ll.h.p;
+            if (!(fabs(sqrt(fmax(dist2(xl, xc), 0.0)) - B.q_ht[q]) < LUMO_EPS)) continue;
+            const D3 wi = normalize(xl - xc);
+            const double p_sct = v_bsdf_pdf(S, cl, wi, lam, false) * v_bsdf_pdf(S, ll, -wi, lam, false);
+            if (p_sct == 0.0) continue;
+            const C4 lb = v_f(S, ll, cl, lam, 1), cb = v_f(S, cl, ll, lam, 0);
+            const C4 radiance = ll.gathered * lb * v_shading_cosine(S, ll, -wi) * cl.gathered * cb * v_shading_cosine(S, cl, wi) * c4(1.0) / dist2(xc, xl);
+            if (is_black(radiance)) continue;
+            const C4 contrib = radiance * mis_weight(S, lam, lp, s, cp, t, nullptr, nullptr);
+            if (!is_black(contrib)) for (int k = 0; k < 4; k++) if (contrib.s[k] != 0.0) atomicAdd(&B.radiance[(size_t)k * B.cap + b], contrib.s[k]);
+        }
+    }
 }
 
 __global__ void __launch_bounds__(256) k_bdpt_finish(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P, const __grid_constant__ BdptBatch B, uint32_t n) {

@@ -602,6 +602,7 @@ static int32_t run_wave(lumo_scene* sc, const Wave& W, WaveParams P, uint64_t& i
 // thousand subpaths are left), and long specular chains give 70+ bounces: large batches pay that tail once.  A sample
 // owns 2 x LUMO_BDPT_MAXV vertices (27 KB), so 2^20 samples are 28 GB of the 180 GB — sized down if memory is short.
 #define LUMO_BDPT_BATCH_MAX (1u << 20)
+#define LUMO_BDPT_QUEUE (1u << 22)   /* terms per chunk of the visibility-ray queue (100 B each) */
 struct BdptStorage { BdptBatch B; void* scan_tmp = nullptr; size_t scan_bytes = 0; };
 static void bdpt_carve(BdptBatch& B, Carver& c, uint32_t cap) {
     B.cap = cap;
@@ -616,6 +617,10 @@ static void bdpt_carve(BdptBatch& B, Carver& c, uint32_t cap) {
     B.w_ht = c.take<double>(cap); B.w_hb0 = c.take<double>(cap); B.w_hb1 = c.take<double>(cap); B.w_hb2 = c.take<double>(cap);
     B.w_hobj = c.take<uint32_t>(cap); B.w_htri = c.take<uint32_t>(cap); B.w_have = c.take<uint32_t>(cap);
     B.act[0] = c.take<uint32_t>(cap); B.act[1] = c.take<uint32_t>(cap); B.n_act = c.take<uint32_t>(4);
+    const uint32_t qcap = LUMO_BDPT_QUEUE; B.qcap = qcap;
+    B.q_term = c.take<unsigned long long>(qcap); B.q_ray = c.take<double>(6 * (size_t)qcap);
+    B.q_ht = c.take<double>(qcap); B.q_hb0 = c.take<double>(qcap); B.q_hb1 = c.take<double>(qcap); B.q_hb2 = c.take<double>(qcap);
+    B.q_hobj = c.take<uint32_t>(qcap); B.q_htri = c.take<uint32_t>(qcap); B.q_have = c.take<uint32_t>(qcap); B.q_n = c.take<uint32_t>(4);
 }
 // batch storage for up to `want` samples, kept by the context and grown on demand
 static int32_t bdpt_alloc(lumo_ctx* ctx, BdptStorage& st, unsigned long long want) {
@@ -675,14 +680,28 @@ static int32_t run_bdpt(lumo_scene* sc, const Wave& W, const WaveParams& P, Bdpt
             CU(cub::DeviceScan::ExclusiveSum(bs.scan_tmp, bs.scan_bytes, B.n_terms[k], B.term_off[k], (int)(n + 1), st));
         }
         CU(cudaEventRecord(ev[1], st));
-        k_bdpt_connect<BC_LIGHT_TRACE><<<ctx->sm_count * 16, 128, 0, st>>>(sc->S, W, P, B, n);
         k_bdpt_connect<BC_EMISSION><<<ctx->sm_count * 16, 128, 0, st>>>(sc->S, W, P, B, n);
         k_bdpt_connect<BC_NEE><<<ctx->sm_count * 16, 128, 0, st>>>(sc->S, W, P, B, n);
-        k_bdpt_connect<BC_CONNECT><<<ctx->sm_count * 16, 128, 0, st>>>(sc->S, W, P, B, n);
+        unsigned long long totals[3] = {0, 0, 0};                        // terms per class of this batch
+        for (int k = 0; k < 3; k++) CU(cudaMemcpyAsync(&totals[k], B.term_off[k] + n, 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        auto queued = [&](auto cls_tag) {                               // light tracing / connections: prepare -> trace -> finish per chunk of terms
+            constexpr int CLS = decltype(cls_tag)::value;
+            for (unsigned long long t0 = 0; t0 < totals[CLS]; t0 += B.qcap) {
+                const uint32_t count = (uint32_t)std::min<unsigned long long>(B.qcap, totals[CLS] - t0);
+                cudaMemsetAsync(B.q_n, 0, 16, st);
+                k_bq_prepare<CLS><<<ctx->sm_count * 16, 128, 0, st>>>(sc->S, W, P, B, n, t0, count);
+                k_bq_trace<CLS><<<ctx->sm_count * 8, 128, 0, st>>>(sc->S, B);
+                k_bq_finish<CLS><<<ctx->sm_count * 16, 128, 0, st>>>(sc->S, W, P, B);
+                ctx->launches += 3;
+            }
+        };
+        queued(std::integral_constant<int, BC_LIGHT_TRACE>());
+        queued(std::integral_constant<int, BC_CONNECT>());
         CU(cudaEventRecord(ev[2], st));
         k_bdpt_finish<<<ctx->sm_count * 4, 256, 0, st>>>(sc->S, W, P, B, n);
         CU(cudaEventRecord(ev[3], st));
-        ctx->launches += 6; iterations++;
+        ctx->launches += 4; iterations++;
         CU(cudaStreamSynchronize(st));
         CU(cudaGetLastError());
         if (P.mode == WM_MAIN) {   // kernel classes for BDPT: [1] walks (incl. their traversal), [2] connections, [0] finish / film
