@@ -313,8 +313,12 @@ def main():
                         "traffic": None,
                         "occlusion_kernel": {"achieved": bytes_occl / (occl_ms * 1e-3) / 1e9 if occl_ms > 0 else None, "bytes_per_ray": bytes_occl / max(cntc["occlusion"], 1)},
                         "note": "algorithmic bytes count every node/triangle visit; a scene that fits the 126 MB L2 is served from L2/L1, so this can exceed the HBM peak (see profiles/ for dram__bytes)"}
-    try:
-        line["roofline"]["traffic"] = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum of that kernel from the committed `ncu --set full` capture, per launch like `achieved`
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+        if tr:
+            rays_per_launch = cntc["closest"] / max(trace_n, 1)
+            line["roofline"]["traffic"] = tr["dram_bytes_per_ray"] * rays_per_launch
+            line["roofline"]["traffic_detail"] = dict(tr, rays_per_launch=rays_per_launch, note="measured DRAM bytes per ray x this run's rays per launch")
     except Exception:
         pass
 
