@@ -1,0 +1,9 @@
+#!/bin/bash
+# same-box A/B of library variants: tools/gpu_ab.sh a0 a1 ...  (micro + three pipelines, twice each)
+for rep in 1 2; do for V in "$@"; do
+  export LUMO_GPU_SO=$PWD/lumo_b200/liblumo_gpu_$V.so
+  echo -n "$V "; python tools/micro_run.py bunny 2>&1 | tail -1
+  for s in "bunny 4" "bistro 1" "dragon 2"; do
+    echo -n "$V "; timeout 300 python tools/prof_run.py $s 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['workload'], round(d['ms'],1), {k:round(v[0],1) for k,v in d['kernel_ms'].items()})"
+  done
+done; done
