@@ -523,7 +523,7 @@ static int32_t run_wave(lumo_scene* sc, const Wave& W, WaveParams P, uint64_t& i
     lumo_ctx* ctx = sc->ctx;
     cudaStream_t st = ctx->stream;
     HostCounters* hc = (HostCounters*)ctx->host_pinned;
-    const int tgrid = trace_grid(ctx);
+    const int tgrid = ctx->sm_count * LUMO_WAVE_TRACE_BLOCKS;   // persistent warps: one grid of resident CTAs
     const int rgrid = (int)std::min<uint64_t>((W.n_slots + 255) / 256, (uint64_t)ctx->sm_count * 16);
     const int sgrid = ctx->sm_count * 16;
     const int ngrid = (int)std::min<uint64_t>(((uint64_t)W.n_slots * 2 * sc->S.P.n_shadow_rays + 127) / 128, (uint64_t)ctx->sm_count * 32);

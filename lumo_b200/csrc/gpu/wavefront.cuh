@@ -198,8 +198,14 @@ __global__ void __launch_bounds__(256) k_compact(const __grid_constant__ Wave W)
 }
 
 // ---- trace: Scene::hit over the active queue, then binning by what the shading stage has to do --------
+#ifndef LUMO_WAVE_TRACE_BLOCKS
+// Resident CTAs per SM the wave traversal kernels are compiled for (and their persistent grid).  Same-box sweep on B200,
+// trace + occlusion ms for bunny 4 spp / dragon 2 spp: 4 CTAs (128 regs) 39.5 / 72.4, 6: 33.8 / 62.4, 8 (64 regs): 32.4 / 57.9,
+// 10 (48 regs): 34.0 / 60.8, 12: 37.3 / 66.4, 16 (32 regs): 51.9 / 92.7 — latency-bound, so occupancy wins until spills take over.
+#define LUMO_WAVE_TRACE_BLOCKS 8
+#endif
 template <bool CNT>
-__global__ void __launch_bounds__(128, 8) k_wave_trace(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, uint32_t cur, Counters* gc) {
+__global__ void __launch_bounds__(128, LUMO_WAVE_TRACE_BLOCKS) k_wave_trace(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, uint32_t cur, Counters* gc) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t n = W.it->n_active;
     Counters cnt = {0, 0, 0, 0, 0, 0};
@@ -239,7 +245,7 @@ __global__ void __launch_bounds__(128, 8) k_wave_trace(const __grid_constant__ D
 
 // ---- occlude: the occlusion half of Scene::hit_light over the shadow queue ------------------------
 template <bool CNT>
-__global__ void __launch_bounds__(128, 8) k_wave_occlude(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, Counters* gc) {
+__global__ void __launch_bounds__(128, LUMO_WAVE_TRACE_BLOCKS) k_wave_occlude(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, Counters* gc) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t n = min(W.it->n_shadow, W.shadow_cap);
     const uint32_t N = W.n_slots, C = W.shadow_cap;

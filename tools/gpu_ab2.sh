@@ -1,0 +1,7 @@
+#!/bin/bash
+for V in "$@"; do
+  export LUMO_GPU_SO=$PWD/lumo_b200/liblumo_gpu_$V.so
+  for s in "bunny 4" "bistro 1" "dragon 2" "conference 4"; do
+    echo -n "$V "; timeout 300 python tools/prof_run.py $s 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['workload'], round(d['ms'],1), {k:round(v[0],1) for k,v in d['kernel_ms'].items()})"
+  done
+done
