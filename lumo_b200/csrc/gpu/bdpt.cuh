@@ -1,13 +1,13 @@
 // Bidirectional path tracing on the device: bd_path_trace.rs:23-290, bd_path_trace/{path_gen,vertex,mis,
 // measure}.rs and the camera importance functions camera.rs:167-388.
 //
-// Vertex-buffer design: a walk kernel writes the light and camera subpaths of a batch of camera samples to
-// vertex arrays in HBM (LUMO_BDPT_MAXV vertices each; the reference caps at 1024 — subpaths that would exceed
-// the device cap are cut there and counted), a connection kernel evaluates every (s,t) term of every sample
-// in parallel (one thread per term: visibility ray, BSDFs, MIS weight), a finish kernel retires the sample
-// into the film.  Traversal calls (Scene::hit, hit_t, hit_light) are the same faithful routines the wavefront
-// kernels use; visible() needs the reference's first-found distance, i.e. scene_hit_t, not an
-// any-hit boolean.
+// Vertex-buffer design: the light and camera subpaths of a batch of camera samples are walked as a wavefront (one
+// bounce of every live subpath per iteration) into vertex arrays in HBM (LUMO_BDPT_MAXV vertices each; the reference
+// caps at 1024 — subpaths that would exceed the device cap are cut there and counted); the (s,t) terms of every sample
+// are then evaluated in parallel, one launch sequence per term class — emission and NEE one thread per term, light
+// tracing and connections through a visibility-ray queue — and a finish kernel retires the sample into the film.
+// Traversal calls (Scene::hit, hit_t, hit_light) are the same faithful routines the wavefront kernels use; visible()
+// needs the reference's first-found distance, i.e. scene_hit_t, not an any-hit boolean.
 #pragma once
 #include "wavefront.cuh"
 
