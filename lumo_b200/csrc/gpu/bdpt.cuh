@@ -668,6 +668,7 @@ __global__ void __launch_bounds__(128) k_bq_finish(const __grid_constant__ DevSc
 }
 
 __global__ void __launch_bounds__(256) k_bdpt_finish(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P, const __grid_constant__ BdptBatch B, uint32_t n) {
+    unsigned long long cost_sum = 0, paths = 0; uint32_t depth_max = 0;     // run counters: per thread here, one atomic per warp at the end
     for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < n; b += gridDim.x * blockDim.x) {
         if (!B.valid[b]) continue;
         const int ns = B.ns[b], nt = B.nt[b];
@@ -685,9 +686,15 @@ __global__ void __launch_bounds__(256) k_bdpt_finish(const __grid_constant__ Dev
             for (int k = 0; k < 4; k++) finite = finite && isfinite(radiance.s[k]);
             if (!finite) atomicAdd(&W.run->nonfinite, 1ull);
             film_add_sample(S, W.pixels, W.splats, tone_map(S, (int)P.tone_map, P.tone_map_arg, radiance, lam), lam, B.rx[b], B.ry[b], false);
-            atomicAdd(&W.run->camera_paths, 1ull); atomicAdd(&W.run->cost, cost); atomicMax(&W.run->max_depth, (uint32_t)(ns + nt));
+            paths += 1ull; cost_sum += cost; depth_max = max(depth_max, (uint32_t)(ns + nt));
         }
     }
+    __syncwarp();
+    for (int o = 16; o > 0; o >>= 1) {
+        cost_sum += __shfl_down_sync(0xFFFFFFFFu, cost_sum, o); paths += __shfl_down_sync(0xFFFFFFFFu, paths, o);
+        depth_max = max(depth_max, __shfl_down_sync(0xFFFFFFFFu, depth_max, o));
+    }
+    if ((threadIdx.x & 31u) == 0u && paths) { atomicAdd(&W.run->cost, cost_sum); atomicAdd(&W.run->camera_paths, paths); atomicMax(&W.run->max_depth, depth_max); }
 }
 
 }  // namespace lumo_dev

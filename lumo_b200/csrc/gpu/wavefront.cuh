@@ -129,6 +129,7 @@ __global__ void k_queue_reset(QueueCounters* qc, uint32_t cur, const IterCounter
 __global__ void __launch_bounds__(256) k_retire(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P) {
     const uint32_t N = W.n_slots, c = P.cur;
     const uint32_t n = W.qc->n_done[c ^ 1u];
+    unsigned long long cost_sum = 0, paths = 0; uint32_t depth_max = 0;     // run counters: per thread here, one atomic per warp at the end
     for (uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x; qi < n; qi += gridDim.x * blockDim.x) {
         const uint32_t slot = W.done[c ^ 1u][qi];
         uint32_t f = W.flags[slot];
@@ -146,9 +147,7 @@ __global__ void __launch_bounds__(256) k_retire(const __grid_constant__ DevScene
                 for (int k = 0; k < 4; k++) finite = finite && isfinite(rad.s[k]);
                 if (!finite) atomicAdd(&W.run->nonfinite, 1ull);
                 film_add_sample(S, W.pixels, W.splats, tone_map(S, (int)P.tone_map, P.tone_map_arg, rad, lam), lam, W.rx[slot], W.ry[slot], false);
-                atomicAdd(&W.run->cost, (unsigned long long)cost);
-                atomicAdd(&W.run->camera_paths, 1ull);
-                atomicMax(&W.run->max_depth, depth);
+                cost_sum += cost; paths += 1ull; depth_max = max(depth_max, depth);
             }
         }
         f = 0;
@@ -190,6 +189,12 @@ __global__ void __launch_bounds__(256) k_retire(const __grid_constant__ DevScene
         }
         W.flags[slot] = f;
     }
+    __syncwarp();
+    for (int o = 16; o > 0; o >>= 1) {
+        cost_sum += __shfl_down_sync(0xFFFFFFFFu, cost_sum, o); paths += __shfl_down_sync(0xFFFFFFFFu, paths, o);
+        depth_max = max(depth_max, __shfl_down_sync(0xFFFFFFFFu, depth_max, o));
+    }
+    if ((threadIdx.x & 31u) == 0u && paths) { atomicAdd(&W.run->cost, cost_sum); atomicAdd(&W.run->camera_paths, paths); atomicMax(&W.run->max_depth, depth_max); }
 }
 // stream compaction of the live slots, in slot order within a warp
 __global__ void __launch_bounds__(256) k_compact(const __grid_constant__ Wave W) {
