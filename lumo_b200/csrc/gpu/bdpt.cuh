@@ -397,8 +397,89 @@ __global__ void __launch_bounds__(128, 8) k_bw_trace(const __grid_constant__ Dev
     }
 }
 
-// one iteration of path_gen::walk (path_gen.rs:53-157) for every live subpath; a light subpath that ends hands over to
-// the sample's camera subpath (path_gen.rs:4-19)
+// one iteration of path_gen::walk (path_gen.rs:53-157) for the live subpath of sample b, given the closest hit of its
+// current ray; a light subpath that ends hands over to the sample's camera subpath (path_gen.rs:4-19).  Returns whether the
+// sample still has a subpath in flight.
+__device__ __forceinline__ bool bw_step_one(const DevScene& S, const WaveParams& P, const BdptBatch& B, uint32_t b, bool have, const HitRec& rec, unsigned long long& overflow) {
+    const uint32_t phase = B.w_phase[b];
+    const int mode = phase == 0u ? 1 : 0;
+    Vtx* vs = (phase == 0u ? B.lp : B.cp) + (size_t)b * LUMO_BDPT_MAXV;
+    int n = (int)B.w_n[b];
+    uint32_t depth = B.w_depth[b];
+    bool end = false;
+    if (!have) end = true;
+    else if (n >= LUMO_BDPT_MAXV) { overflow++; end = true; }
+    else {
+        const Ray ro = bw_load_ray(B, B.w_ray, b);
+        Lam lam; C4 gathered;
+        for (int k = 0; k < 4; k++) { lam.l[k] = B.lam[(size_t)k * B.cap + b]; gathered.s[k] = B.w_gathered[(size_t)k * B.cap + b]; }
+        double pdf_fwd = B.w_pdf_fwd[b];
+        Rng rng = rng_make(P.seed, B.pixel[b], B.sample[b], 0u, B.draws[b]);
+        const DevHit ho = reconstruct_hit(S, ro, rec);
+        const Mat& m = S.materials[ho.material];
+        const uint32_t prev = depth;
+        const D3 wo = -ro.d;
+        Vtx& cv = vs[n];                                                                      // Vertex::surface, vertex.rs:51-84
+        const bool is_delta = mat_is_delta(S, m, lam);
+        cv.pdf_fwd = is_delta ? 0.0 : sa_to_area(pdf_fwd, vs[prev].h.p, ho.p, -wo, ho.ng);
+        cv.h = ho; cv.gathered = gathered; cv.wo = wo; cv.pdf_bck = 0.0; cv.light = -1; cv.delta = is_delta ? 1 : 0;
+        n++;
+        depth += 1;
+        const uint32_t curr = depth;
+        const double ru = rng_float(rng), r0 = rng_float(rng), r1 = rng_float(rng);
+        D3 wi;
+        const Onb uvw = shading_onb(S, m, ho);
+        if (!bsdf_sample<-1>(S, m, uvw, wo, ho, lam, ru, r0, r1, wi)) {
+            if (mode == 1) n--;                                                               // path_gen.rs:97-99: a light path cannot end on a light
+            else {                                                                            // Scene::get_light_at (bvh.rs:97-102)
+                Ray rl; rl.o = hit_ray_origin(ho, true); rl.d = normalize(-ho.ng);
+                RayCtx w; make_ctx(rl, w);
+                const uint32_t li = S.P.n_lights ? tlas_hit<true, false>(S, S.P.lights_root, S.P.n_objects, w, 0.0, LUMO_INF, nullptr) : LUMO_NONE;
+                vs[curr].light = li == LUMO_NONE ? -1 : (int)li;
+            }
+            end = true;
+        } else {
+            const Ray ri = hit_generate_ray(ho, wi);
+            wi = ri.d;
+            pdf_fwd = bsdf_pdf<-1>(S, m, uvw, wo, wi, ho, lam, false);
+            if (pdf_fwd == 0.0) end = true;
+            else {
+                const double corr = mode == 0 ? 1.0 : v_shading_correction(S, vs[curr], wi);
+                const C4 bsdf = bsdf_f<-1>(S, m, uvw, wo, wi, lam, mode, ho);
+                gathered = gathered * (bsdf * v_shading_cosine(S, vs[curr], wi) * corr / pdf_fwd);
+                vs[prev].pdf_bck = v_pdf_prev(S, vs[curr], vs[prev], wi, lam);
+                if (depth >= LUMO_RR_DEPTH) {
+                    const double lum = luminance(S, gathered, lam);
+                    const double rr = fmin(lum / B.w_delta[b], 1.0);
+                    if (rng_float(rng) > rr) end = true;
+                    else if (depth >= LUMO_BDPT_MAX_DEPTH) end = true;
+                    else gathered = gathered / rr;
+                }
+                if (!end) {
+                    if (is_delta) pdf_fwd = 0.0;
+                    bw_store_ray(B, B.w_ray, b, ri);
+                    for (int k = 0; k < 4; k++) B.w_gathered[(size_t)k * B.cap + b] = gathered.s[k];
+                    B.w_pdf_fwd[b] = pdf_fwd;
+                }
+            }
+        }
+        for (int k = 0; k < 4; k++) B.lam[(size_t)k * B.cap + b] = lam.l[k];      // a dispersive scatter may have terminated wavelengths
+        B.draws[b] = rng.draws;
+    }
+    if (!end) { B.w_n[b] = (uint32_t)n; B.w_depth[b] = depth; return true; }
+    if (phase == 0u) {                                                                        // light subpath done: start the camera subpath
+        B.ns[b] = n;
+        const Ray r = bw_load_ray(B, B.w_cam, b);
+        const double pdf_wi = cam_pdf_wi(S.P.camera, r), pdf_xo = cam_pdf_xo(S.P.camera, r);
+        v_camera(B.cp[(size_t)b * LUMO_BDPT_MAXV], r.o, pdf_xo, c4(1.0));
+        bw_store_ray(B, B.w_ray, b, r);
+        for (int k = 0; k < 4; k++) B.w_gathered[(size_t)k * B.cap + b] = 1.0;
+        B.w_pdf_fwd[b] = pdf_wi; B.w_phase[b] = 1u; B.w_n[b] = 1u; B.w_depth[b] = 0u;
+        return true;
+    }
+    bw_finish_sample(B, b, B.ns[b], n);
+    return false;
+}
 __global__ void __launch_bounds__(128) k_bw_step(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P, const __grid_constant__ BdptBatch B, uint32_t cur) {
     const uint32_t n_act = B.n_act[cur];
     const uint32_t n_pad = (n_act + 31u) & ~31u;
@@ -408,86 +489,29 @@ __global__ void __launch_bounds__(128) k_bw_step(const __grid_constant__ DevScen
         bool alive = false; uint32_t b = 0;
         if (i < n_act) {
             b = B.act[cur][i];
-            const uint32_t phase = B.w_phase[b];
-            const int mode = phase == 0u ? 1 : 0;
-            Vtx* vs = (phase == 0u ? B.lp : B.cp) + (size_t)b * LUMO_BDPT_MAXV;
-            int n = (int)B.w_n[b];
-            uint32_t depth = B.w_depth[b];
-            bool end = false;
-            if (!B.w_have[b]) end = true;
-            else if (n >= LUMO_BDPT_MAXV) { overflow++; end = true; }
-            else {
-                const Ray ro = bw_load_ray(B, B.w_ray, b);
-                HitRec rec; rec.t = B.w_ht[b]; rec.bary = d3(B.w_hb0[b], B.w_hb1[b], B.w_hb2[b]); rec.obj = B.w_hobj[b]; rec.tri = B.w_htri[b];
-                Lam lam; C4 gathered;
-                for (int k = 0; k < 4; k++) { lam.l[k] = B.lam[(size_t)k * B.cap + b]; gathered.s[k] = B.w_gathered[(size_t)k * B.cap + b]; }
-                double pdf_fwd = B.w_pdf_fwd[b];
-                Rng rng = rng_make(P.seed, B.pixel[b], B.sample[b], 0u, B.draws[b]);
-                const DevHit ho = reconstruct_hit(S, ro, rec);
-                const Mat& m = S.materials[ho.material];
-                const uint32_t prev = depth;
-                const D3 wo = -ro.d;
-                Vtx& cv = vs[n];                                                                      // Vertex::surface, vertex.rs:51-84
-                const bool is_delta = mat_is_delta(S, m, lam);
-                cv.pdf_fwd = is_delta ? 0.0 : sa_to_area(pdf_fwd, vs[prev].h.p, ho.p, -wo, ho.ng);
-                cv.h = ho; cv.gathered = gathered; cv.wo = wo; cv.pdf_bck = 0.0; cv.light = -1; cv.delta = is_delta ? 1 : 0;
-                n++;
-                depth += 1;
-                const uint32_t curr = depth;
-                const double ru = rng_float(rng), r0 = rng_float(rng), r1 = rng_float(rng);
-                D3 wi;
-                const Onb uvw = shading_onb(S, m, ho);
-                if (!bsdf_sample<-1>(S, m, uvw, wo, ho, lam, ru, r0, r1, wi)) {
-                    if (mode == 1) n--;                                                               // path_gen.rs:97-99: a light path cannot end on a light
-                    else {                                                                            // Scene::get_light_at (bvh.rs:97-102)
-                        Ray rl; rl.o = hit_ray_origin(ho, true); rl.d = normalize(-ho.ng);
-                        RayCtx w; make_ctx(rl, w);
-                        const uint32_t li = S.P.n_lights ? tlas_hit<true, false>(S, S.P.lights_root, S.P.n_objects, w, 0.0, LUMO_INF, nullptr) : LUMO_NONE;
-                        vs[curr].light = li == LUMO_NONE ? -1 : (int)li;
-                    }
-                    end = true;
-                } else {
-                    const Ray ri = hit_generate_ray(ho, wi);
-                    wi = ri.d;
-                    pdf_fwd = bsdf_pdf<-1>(S, m, uvw, wo, wi, ho, lam, false);
-                    if (pdf_fwd == 0.0) end = true;
-                    else {
-                        const double corr = mode == 0 ? 1.0 : v_shading_correction(S, vs[curr], wi);
-                        const C4 bsdf = bsdf_f<-1>(S, m, uvw, wo, wi, lam, mode, ho);
-                        gathered = gathered * (bsdf * v_shading_cosine(S, vs[curr], wi) * corr / pdf_fwd);
-                        vs[prev].pdf_bck = v_pdf_prev(S, vs[curr], vs[prev], wi, lam);
-                        if (depth >= LUMO_RR_DEPTH) {
-                            const double lum = luminance(S, gathered, lam);
-                            const double rr = fmin(lum / B.w_delta[b], 1.0);
-                            if (rng_float(rng) > rr) end = true;
-                            else if (depth >= LUMO_BDPT_MAX_DEPTH) end = true;
-                            else gathered = gathered / rr;
-                        }
-                        if (!end) {
-                            if (is_delta) pdf_fwd = 0.0;
-                            bw_store_ray(B, B.w_ray, b, ri);
-                            for (int k = 0; k < 4; k++) B.w_gathered[(size_t)k * B.cap + b] = gathered.s[k];
-                            B.w_pdf_fwd[b] = pdf_fwd;
-                        }
-                    }
-                }
-                for (int k = 0; k < 4; k++) B.lam[(size_t)k * B.cap + b] = lam.l[k];      // a dispersive scatter may have terminated wavelengths
-                B.draws[b] = rng.draws;
-            }
-            if (!end) { B.w_n[b] = (uint32_t)n; B.w_depth[b] = depth; alive = true; }
-            else if (phase == 0u) {                                                               // light subpath done: start the camera subpath
-                B.ns[b] = n;
-                const Ray r = bw_load_ray(B, B.w_cam, b);
-                const double pdf_wi = cam_pdf_wi(S.P.camera, r), pdf_xo = cam_pdf_xo(S.P.camera, r);
-                v_camera(B.cp[(size_t)b * LUMO_BDPT_MAXV], r.o, pdf_xo, c4(1.0));
-                bw_store_ray(B, B.w_ray, b, r);
-                for (int k = 0; k < 4; k++) B.w_gathered[(size_t)k * B.cap + b] = 1.0;
-                B.w_pdf_fwd[b] = pdf_wi; B.w_phase[b] = 1u; B.w_n[b] = 1u; B.w_depth[b] = 0u;
-                alive = true;
-            } else bw_finish_sample(B, b, B.ns[b], n);
+            HitRec rec; rec.t = B.w_ht[b]; rec.bary = d3(B.w_hb0[b], B.w_hb1[b], B.w_hb2[b]); rec.obj = B.w_hobj[b]; rec.tri = B.w_htri[b];
+            alive = bw_step_one(S, P, B, b, B.w_have[b] != 0u, rec, overflow);
         }
         bw_append(B, cur ^ 1u, alive, b);
     }
+    if (overflow) atomicAdd(&W.run->shadow_dropped, overflow);
+}
+// The stragglers: once only a few thousand subpaths are left (long specular chains), every further bounce of the wavefront costs
+// a launch pair and one traversal's latency for next to no work.  One thread per remaining sample then runs its walks to the end.
+__global__ void __launch_bounds__(64) k_bw_tail(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P, const __grid_constant__ BdptBatch B, uint32_t cur) {
+    const uint32_t n_act = B.n_act[cur];
+    unsigned long long overflow = 0, closest = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_act; i += gridDim.x * blockDim.x) {
+        const uint32_t b = B.act[cur][i];
+        for (;;) {
+            const Ray r = bw_load_ray(B, B.w_ray, b);
+            HitRec rec; rec.t = 0.0; rec.bary = d3(0, 0, 0); rec.obj = LUMO_NONE; rec.tri = 0u;
+            closest++;
+            const bool have = scene_hit<false>(S, r, LUMO_INF, rec, nullptr);
+            if (!bw_step_one(S, P, B, b, have, rec, overflow)) break;
+        }
+    }
+    if (closest) atomicAdd(&W.run->closest, closest);
     if (overflow) atomicAdd(&W.run->shadow_dropped, overflow);
 }
 

@@ -602,6 +602,7 @@ static int32_t run_wave(lumo_scene* sc, const Wave& W, WaveParams P, uint64_t& i
 // thousand subpaths are left), and long specular chains give 70+ bounces: large batches pay that tail once.  A sample
 // owns 2 x LUMO_BDPT_MAXV vertices (27 KB), so 2^20 samples are 28 GB of the 180 GB — sized down if memory is short.
 #define LUMO_BDPT_BATCH_MAX (1u << 20)
+#define LUMO_BW_TAIL 32768u          /* live subpaths at or below which the walk wavefront hands over to k_bw_tail (walks, caustics 1 spp: 0: 133.9 ms, 2048: 130.4, 8192: 127.1, 32768: 123.2, 131072: 130.1) */
 #define LUMO_BDPT_QUEUE (1u << 22)   /* terms per chunk of the visibility-ray queue (100 B each) */
 struct BdptStorage { BdptBatch B; void* scan_tmp = nullptr; size_t scan_bytes = 0; };
 static void bdpt_carve(BdptBatch& B, Carver& c, uint32_t cap) {
@@ -655,6 +656,7 @@ static int32_t run_bdpt(lumo_scene* sc, const Wave& W, const WaveParams& P, Bdpt
     cudaStream_t st = ctx->stream;
     const BdptBatch& B = bs.B;
     cudaEvent_t* ev = ctx->kev;
+    static const uint32_t bw_tail = std::getenv("LUMO_BW_TAIL") ? (uint32_t)std::atoll(std::getenv("LUMO_BW_TAIL")) : LUMO_BW_TAIL;
     static const bool bdpt_log = std::getenv("LUMO_BDPT_LOG") != nullptr;   // diagnostics: live subpaths and elapsed time every 8 bounces
     for (unsigned long long w0 = 0; w0 < P.total_work; w0 += B.cap) {
         const uint32_t n = (uint32_t)std::min<unsigned long long>(B.cap, P.total_work - w0);
@@ -674,6 +676,11 @@ static int32_t run_bdpt(lumo_scene* sc, const Wave& W, const WaveParams& P, Bdpt
             if (bdpt_log) { CU(cudaEventRecord(ev[4], st)); CU(cudaEventSynchronize(ev[4])); float ms = 0; CU(cudaEventElapsedTime(&ms, ev[0], ev[4]));
                             std::fprintf(stderr, "[bdpt] batch %llu bounce %u live %u t %.3f ms\n", w0 / B.cap, it, live, ms); }
             if (live == 0) break;
+            if (live <= bw_tail) {                                  // the stragglers run their walks to the end in one launch
+                k_bw_tail<<<(live + 63u) / 64u, 64, 0, st>>>(sc->S, W, P, B, it & 1u);
+                ctx->launches += 1;
+                break;
+            }
         }
         for (int k = 0; k < 3; k++) {
             CU(cudaMemsetAsync(B.n_terms[k] + n, 0, 8, st));
