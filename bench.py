@@ -355,6 +355,22 @@ def main():
         except Exception as e:
             line["micro"] = {"error": str(e)}
 
+    # film finalisation kernel (Film::rgb_image on the device) on the accumulators the timed steps left in HBM:
+    # 56 B read + 3 B written per pixel, HBM bound; L2 flushed before each launch
+    if world == 1:
+        try:
+            fe = []
+            for k in range(5):
+                flush.zero_(); torch.cuda.synchronize()
+                rgb8, fms = ctx.film_encode_dev(px_ptr, sp_ptr, (H, W), 1.0 / max(spp, 1), 1.0, 0)
+                fe.append(fms)
+            fms = sorted(fe[1:])[len(fe[1:]) // 2]
+            line["film_encode"] = {"kernel": "k_film_encode", "ms": fms, "bytes": W * H * 59, "achieved": W * H * 59 / fms / 1e6, "unit": "GB/s",
+                                   "frac_of_hbm_peak": W * H * 59 / fms / 1e6 / peak, "d2h_bytes": W * H * 3,
+                                   "note": "one launch over a %d x %d film (%.1f MB): at this size launch latency, not bandwidth, decides the time" % (W, H, W * H * 59 / 1e6)}
+        except Exception as e:
+            line["film_encode"] = {"error": str(e)}
+
     if world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
         v, s, dt, ccnt = cpu_baseline(prog, integrator, threads, spp=1)

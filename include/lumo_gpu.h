@@ -112,6 +112,18 @@ int32_t lumo_gpu_render(lumo_scene* scene, const lumo_render_params* params, lum
 int32_t lumo_gpu_render_dev(lumo_scene* scene, const lumo_render_params* params, double* pixels_dev, double* splats_dev,
                             uint64_t* counters8, double* device_ms);
 
+/* Film finalisation on the device: Film::rgb_image (src/tracer/film.rs:173-193) = Pixel::value (film.rs:82-90)
+ * + splat_scale * splat / filter_integral, then TransferFunction::apply (src/tracer/color/space.rs:8-36;
+ * transfer 0 = the sRGB curve used by sRGB and DCI-P3, 1 = the rec. 2020 curve) with Rust's saturating
+ * `as u8`.  rgb8 = [n_pixels*3] HOST bytes, row-major like the accumulators.  The _dev variant reads the
+ * accumulators where lumo_gpu_render_dev (and the multi-GPU reduce) left them, so the host receives
+ * 3 B/pixel instead of 56 B/pixel; the other one takes host accumulators (e.g. after a host-side merge).
+ * kernel_ms (optional): CUDA-event time of the kernel on the context's stream. */
+int32_t lumo_gpu_film_encode_dev(lumo_ctx* ctx, const double* pixels_dev, const double* splats_dev, uint64_t n_pixels, double splat_scale,
+                                 double filter_integral, int32_t transfer, uint8_t* rgb8, float* kernel_ms);
+int32_t lumo_gpu_film_encode(lumo_ctx* ctx, const double* pixels, const double* splats, uint64_t n_pixels, double splat_scale,
+                             double filter_integral, int32_t transfer, uint8_t* rgb8);
+
 /* Traversal visit counters (N_tlas, N_inst, N_kd, N_idx, N_tri, N_sphere of DESIGN.md's byte
  * formula).  While enabled, the traversal kernels of this context run their counting instantiation;
  * never enabled inside a timed region. */

@@ -31,6 +31,7 @@ struct lumo_ctx {
     unsigned long long* d_cursor = nullptr;            // work cursor of the ray-batch kernels
     uint8_t* blob_cache = nullptr; uint64_t blob_cache_bytes = 0;   // one recycled scene allocation (cudaFree / cudaMalloc stall unpredictably)
     void* film_mem = nullptr; size_t film_bytes = 0;   // device film of lumo_gpu_render (host-buffer entry point), reused across calls
+    void* rgb_mem = nullptr; size_t rgb_bytes = 0;     // 8-bit image of lumo_gpu_film_encode*, reused across calls
     void* host_pinned = nullptr;   // IterCounters + RunCounters read-back
     unsigned long long launches = 0;
     Counters* d_visit = nullptr;   // traversal visit counters (CNT passes): [0] closest-hit kernels, [1] occlusion kernels
@@ -95,6 +96,7 @@ extern "C" int32_t lumo_gpu_ctx_destroy(lumo_ctx* ctx) {
     if (ctx->bdpt_mem) cudaFree(ctx->bdpt_mem);
     if (ctx->bdpt_scan) cudaFree(ctx->bdpt_scan);
     if (ctx->film_mem) cudaFree(ctx->film_mem);
+    if (ctx->rgb_mem) cudaFree(ctx->rgb_mem);
     if (ctx->d_cursor) cudaFree(ctx->d_cursor);
     if (ctx->nm_mem) cudaFree(ctx->nm_mem);
     if (ctx->d_n_batch) cudaFree(ctx->d_n_batch);
@@ -816,4 +818,91 @@ extern "C" int32_t lumo_gpu_render_dev(lumo_scene* sc, const lumo_render_params*
     if (!sc || !rp || !pixels_dev || !splats_dev) return fail(LUMO_ERR_INVALID, "render_dev: null pointer");
     CU(cudaSetDevice(sc->ctx->device));
     return render_impl(sc, rp, pixels_dev, splats_dev, counters8, nullptr, device_ms);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Film finalisation on the device: Film::rgb_image (src/tracer/film.rs:173-193) = Pixel::value
+// (film.rs:82-90) + splat_scale * splat / filter.integral(), then ColorSpace::encode ->
+// TransferFunction::apply (color/space.rs:8-36, 135-141) with Rust's saturating `as u8`.
+// A thread finishes four pixels (224 B read as 128-bit loads, 12 B written as three 32-bit words):
+// pure streaming, 59 B per pixel, HBM bound.  The host then reads 3 B/pixel instead of 56 B/pixel.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t trc_apply(double c, int transfer) {
+    double ec;
+    if (transfer == 1) {   // rec. 2020
+        const double beta = 0.018053968510807, alpha = 1.0 + 5.5 * beta;
+        ec = c <= beta ? 4.5 * c : alpha * pow(c, 0.45) - (alpha - 1.0);
+    } else {
+        ec = c <= 0.0031308 ? 12.92 * c : 1.055 * pow(c, 1.0 / 2.4) - 0.055;
+    }
+    const double v = ec * 255.0;
+    return !(v > 0.0) ? 0u : (v >= 255.0 ? 255u : (uint32_t)v);   // NaN and negatives -> 0, like `as u8`
+}
+__device__ __forceinline__ void film_pixel_rgb8(const double* __restrict__ px, const double* __restrict__ sp, size_t i, double splat_scale,
+                                                double filter_integral, int transfer, uint32_t out[3]) {
+    const double2 a = __ldg((const double2*)(px + 4 * i)), b = __ldg((const double2*)(px + 4 * i) + 1);
+    const double c[3] = {a.x, a.y, b.x}, w = b.y;
+    #pragma unroll
+    for (int k = 0; k < 3; k++) out[k] = trc_apply(c[k] / w + splat_scale * __ldg(sp + 3 * i + k) / filter_integral, transfer);
+}
+__global__ void __launch_bounds__(256) k_film_encode(const double* __restrict__ px, const double* __restrict__ sp, size_t n_pixels, double splat_scale,
+                                                     double filter_integral, int transfer, uint8_t* __restrict__ rgb) {
+    const size_t groups = (n_pixels + 3) / 4;
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (size_t)gridDim.x * blockDim.x) {
+        const size_t i0 = 4 * g;
+        if (i0 + 4 <= n_pixels) {
+            uint32_t v[12];
+            #pragma unroll
+            for (int j = 0; j < 4; j++) film_pixel_rgb8(px, sp, i0 + j, splat_scale, filter_integral, transfer, v + 3 * j);
+            uint32_t* o = (uint32_t*)(rgb + 3 * i0);   // 12 * g: 4-byte aligned
+            #pragma unroll
+            for (int q = 0; q < 3; q++) o[q] = v[4 * q] | (v[4 * q + 1] << 8) | (v[4 * q + 2] << 16) | (v[4 * q + 3] << 24);
+        } else {
+            for (size_t i = i0; i < n_pixels; i++) {
+                uint32_t v[3]; film_pixel_rgb8(px, sp, i, splat_scale, filter_integral, transfer, v);
+                rgb[3 * i] = (uint8_t)v[0]; rgb[3 * i + 1] = (uint8_t)v[1]; rgb[3 * i + 2] = (uint8_t)v[2];
+            }
+        }
+    }
+}
+static int32_t film_encode_impl(lumo_ctx* ctx, const double* px_dev, const double* sp_dev, uint64_t n_pixels, double splat_scale, double filter_integral,
+                                int32_t transfer, uint8_t* rgb8_host, float* kernel_ms) {
+    if (transfer != 0 && transfer != 1) return fail(LUMO_ERR_INVALID, "film_encode: transfer must be 0 (sRGB curve) or 1 (rec. 2020 curve)");
+    if (n_pixels == 0) return LUMO_OK;
+    const size_t out_bytes = (size_t)n_pixels * 3, out_cap = (out_bytes + 15) & ~(size_t)15;
+    if (out_cap > ctx->rgb_bytes) {
+        if (ctx->rgb_mem) { cudaFree(ctx->rgb_mem); ctx->rgb_mem = nullptr; ctx->rgb_bytes = 0; }
+        CU(cudaMalloc(&ctx->rgb_mem, out_cap)); ctx->rgb_bytes = out_cap;
+    }
+    const size_t groups = (n_pixels + 3) / 4;
+    const unsigned grid = (unsigned)std::min<size_t>((groups + 255) / 256, (size_t)ctx->sm_count * 8);
+    cudaStream_t st = ctx->stream;
+    CU(cudaEventRecord(ctx->ev0, st));
+    k_film_encode<<<grid, 256, 0, st>>>(px_dev, sp_dev, (size_t)n_pixels, splat_scale, filter_integral, transfer, (uint8_t*)ctx->rgb_mem);
+    CU(cudaGetLastError());
+    ctx->launches++;
+    CU(cudaEventRecord(ctx->ev1, st));
+    CU(cudaMemcpyAsync(rgb8_host, ctx->rgb_mem, out_bytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (kernel_ms) CU(cudaEventElapsedTime(kernel_ms, ctx->ev0, ctx->ev1));
+    return LUMO_OK;
+}
+extern "C" int32_t lumo_gpu_film_encode_dev(lumo_ctx* ctx, const double* pixels_dev, const double* splats_dev, uint64_t n_pixels, double splat_scale,
+                                            double filter_integral, int32_t transfer, uint8_t* rgb8, float* kernel_ms) {
+    if (!ctx || !pixels_dev || !splats_dev || !rgb8) return fail(LUMO_ERR_INVALID, "film_encode_dev: null pointer");
+    CU(cudaSetDevice(ctx->device));
+    return film_encode_impl(ctx, pixels_dev, splats_dev, n_pixels, splat_scale, filter_integral, transfer, rgb8, kernel_ms);
+}
+extern "C" int32_t lumo_gpu_film_encode(lumo_ctx* ctx, const double* pixels, const double* splats, uint64_t n_pixels, double splat_scale,
+                                        double filter_integral, int32_t transfer, uint8_t* rgb8) {
+    if (!ctx || !pixels || !splats || !rgb8) return fail(LUMO_ERR_INVALID, "film_encode: null pointer");
+    CU(cudaSetDevice(ctx->device));
+    if (n_pixels * 56 > ctx->film_bytes) {
+        if (ctx->film_mem) { cudaFree(ctx->film_mem); ctx->film_mem = nullptr; ctx->film_bytes = 0; }
+        CU(cudaMalloc(&ctx->film_mem, n_pixels * 56)); ctx->film_bytes = n_pixels * 56;
+    }
+    double* px = (double*)ctx->film_mem; double* sp = px + n_pixels * 4;
+    CU(cudaMemcpyAsync(px, pixels, n_pixels * 32, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(sp, splats, n_pixels * 24, cudaMemcpyHostToDevice, ctx->stream));
+    return film_encode_impl(ctx, px, sp, n_pixels, splat_scale, filter_integral, transfer, rgb8, nullptr);
 }

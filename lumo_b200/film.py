@@ -28,8 +28,19 @@ class Film:
     def rgb_image(self):
         return _color.encode(self.linear_rgb(), self.cs)
 
-    def save(self, fname):
-        img = self.rgb_image()
+    def rgb_image_device(self, ctx=None, device=0):
+        """The same image computed by the CUDA film kernel (lumo_gpu_film_encode; the transfer curve's pow is CUDA's,
+        so a value sitting on an integer boundary may differ by one code from `rgb_image`)."""
+        from . import native
+        own = ctx is None
+        if own: ctx = native.GpuContext(device)
+        try:
+            return ctx.film_encode(self.pixels, self.splats, self.splat_scale, self.filter.integral(), 1 if self.cs == 2 else 0)
+        finally:
+            if own: ctx.close()
+
+    def save(self, fname, device_encode=False):
+        img = self.rgb_image_device() if device_encode else self.rgb_image()
         h, w, _ = img.shape
         raw = b"".join(b"\x00" + img[y].tobytes() for y in range(h))
 

@@ -137,8 +137,10 @@ def gpu_lib():
         L.lumo_gpu_ctx_iter_log.restype = C.c_int32
         L.lumo_gpu_ctx_set_stream.restype = C.c_int32
         L.lumo_gpu_ctx_visits.argtypes = [vp, C.POINTER(C.c_uint64)]
+        L.lumo_gpu_film_encode_dev.argtypes = [vp, vp, vp, C.c_uint64, C.c_double, C.c_double, C.c_int32, u8p, C.POINTER(C.c_float)]
+        L.lumo_gpu_film_encode.argtypes = [vp, dp, dp, C.c_uint64, C.c_double, C.c_double, C.c_int32, u8p]
         for f in ("lumo_gpu_render_dev", "lumo_gpu_trace_closest_dev", "lumo_gpu_ctx_count_visits", "lumo_gpu_ctx_visits","lumo_gpu_device_count", "lumo_gpu_ctx_create", "lumo_gpu_ctx_destroy", "lumo_gpu_scene_upload", "lumo_gpu_scene_destroy",
-                  "lumo_gpu_trace_closest", "lumo_gpu_trace_any", "lumo_gpu_trace_first_found", "lumo_gpu_render"):
+                  "lumo_gpu_trace_closest", "lumo_gpu_trace_any", "lumo_gpu_trace_first_found", "lumo_gpu_render", "lumo_gpu_film_encode", "lumo_gpu_film_encode_dev"):
             getattr(L, f).restype = C.c_int32
         _gpu = L
     return _gpu
@@ -187,6 +189,22 @@ class GpuContext:
         ms = (C.c_double * 4)(); n = (C.c_uint64 * 4)()
         _check(gpu_lib().lumo_gpu_ctx_kernel_times(self.h, ms, n), "lumo_gpu_ctx_kernel_times")
         return {k: (ms[i], int(n[i])) for i, k in enumerate(("regen", "trace", "shade", "occlude"))}
+
+    def film_encode(self, pixels, splats, splat_scale, filter_integral, transfer=0):
+        """Film::rgb_image on the device from HOST accumulators [H,W,4] / [H,W,3] f64 -> uint8 [H,W,3]."""
+        pixels = np.ascontiguousarray(pixels, dtype=np.float64); splats = np.ascontiguousarray(splats, dtype=np.float64)
+        assert pixels.shape[-1] == 4 and splats.shape[-1] == 3 and pixels.shape[:-1] == splats.shape[:-1]
+        rgb = np.empty(splats.shape, dtype=np.uint8)
+        _check(gpu_lib().lumo_gpu_film_encode(self.h, _dp(pixels), _dp(splats), pixels.size // 4, float(splat_scale), float(filter_integral), int(transfer),
+                                              rgb.ctypes.data_as(C.POINTER(C.c_uint8))), "lumo_gpu_film_encode")
+        return rgb
+
+    def film_encode_dev(self, pixels_ptr, splats_ptr, shape, splat_scale, filter_integral, transfer=0):
+        """Same from DEVICE accumulators (raw pointers, as left by render_dev / the NCCL reduce); shape = (H, W).  Returns (uint8 [H,W,3], kernel ms)."""
+        rgb = np.empty((int(shape[0]), int(shape[1]), 3), dtype=np.uint8); ms = C.c_float(0.0)
+        _check(gpu_lib().lumo_gpu_film_encode_dev(self.h, C.c_void_p(pixels_ptr), C.c_void_p(splats_ptr), rgb.size // 3, float(splat_scale), float(filter_integral),
+                                                  int(transfer), rgb.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(ms)), "lumo_gpu_film_encode_dev")
+        return rgb, ms.value
 
     def __del__(self):
         try: self.close()

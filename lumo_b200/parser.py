@@ -7,9 +7,15 @@ Texture maps (`map_Kd`, `map_Ks`, `map_Ke`, `map_Bump`, mtl/task.rs:30-80) are r
 PNG bytes` callback (the reference pulls them out of the scene's zip archive) and become `Texture::Image` / bump maps on
 the device; without a resolver they are ignored with a warning.  With `map_ks=False` a `map_Ks` image is the
 occlusion/roughness/metalness map of the reference: its mean green / blue channels become roughness and k
-(mtl/task.rs:60-68).  Not mirrored (host I/O outside the hot path): downloading (no network), zip extraction."""
+(mtl/task.rs:60-68).
+
+The reference's own entry points exist under their names — `mesh_from_path`, `mesh_from_url`, `texture_from_url`,
+`scene_from_url`, `scene_from_file` (parser.rs:125-265) — over zip archives cached in `./scenes/` (`_check_cached`,
+`_extract_zip`); a missing archive is fetched with urllib where a network exists and is an `ObjError` otherwise."""
 import io
 import math
+import os
+import zipfile
 import warnings
 import numpy as np
 from .api import Scene, Material, Texture, TriangleMesh, Mesh, Face, LooseTriangles
@@ -187,4 +193,103 @@ def scene_from_obj(obj_src, mtl_src=None, env_map=None, mtl_resolver=None, image
         f0 = f1
     if env_map is not None:
         scene.set_environment_map(env_map[0], env_map[1])
+    return scene
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The reference's public entry points (parser.rs:125-265): files, cached URLs, zip archives.
+
+SCENE_DIR = "./scenes/"                                    # parser.rs:17
+
+
+def _extract_zip(data, end_match):
+    """parser.rs:82-113: the one archive member whose lower-cased name ends with `end_match`; several or none is an error."""
+    end_match = end_match.lower()
+    found = None
+    try:
+        with zipfile.ZipFile(io.BytesIO(data)) as z:
+            for info in z.infolist():
+                if info.filename.lower().endswith(end_match):
+                    if found is not None:
+                        raise ObjError("Found multiple %s in the archive" % end_match)
+                    found = z.read(info)
+    except zipfile.BadZipFile as e:
+        raise ObjError(str(e))
+    if not found:
+        raise ObjError("Could not find %s in the archive" % end_match)
+    return found
+
+
+def _check_cached(url):
+    """parser.rs:149-165: `SCENE_DIR` + last path component of the URL; downloaded once if absent."""
+    os.makedirs(SCENE_DIR, exist_ok=True)
+    path = SCENE_DIR + url.rsplit("/", 1)[-1]
+    if not os.path.exists(path):
+        print('"%s" not found, downloading from "%s"' % (path, url))
+        try:
+            import urllib.request
+            with urllib.request.urlopen(url, timeout=60) as r:
+                body = r.read()
+        except Exception as e:
+            raise ObjError("could not download %s: %s" % (url, e))
+        with open(path, "wb") as f:
+            f.write(body)
+    return path
+
+
+def _read(path):
+    with open(path, "rb") as f:
+        return f.read()
+
+
+def mesh_from_path(path, material):
+    """parser.rs:125-128"""
+    print('Loading .OBJ file "%s"' % path)
+    return mesh_from_obj(_read(path), material)
+
+
+def mesh_from_url(url, material):
+    """parser.rs:132-147: a plain .obj or the single .obj inside a .zip, cached under SCENE_DIR."""
+    path = _check_cached(url)
+    print('Loading .OBJ from "%s"' % path)
+    data = _read(path)
+    if url.endswith(".zip"):
+        data = _extract_zip(data, ".obj")
+    elif not url.endswith(".obj"):
+        raise ObjError("Bad URL, or at least does not end with .zip or .obj")
+    return mesh_from_obj(data, material)
+
+
+def texture_from_url(url, tex_name):
+    """parser.rs:168-180: `tex_name` (.png) out of the cached .zip as an Image<Spectrum>."""
+    if not tex_name.endswith(".png"):
+        raise ObjError("Can only load .png files")
+    if not url.endswith(".zip"):
+        raise ObjError("Can only extract textures from zip archives")
+    path = _check_cached(url)
+    print('Loading texture "%s" from "%s"' % (tex_name, path))
+    return Image.from_png(_extract_zip(_read(path), tex_name))
+
+
+def scene_from_url(url, obj_name, map_ks, mtllib=None, env_map=None):
+    """parser.rs:184-200"""
+    if not url.endswith(".zip"):
+        raise ObjError("Can only load scenes from .zip")
+    if not obj_name.endswith(".obj"):
+        raise ObjError("Can only parse .obj files")
+    return scene_from_file(_check_cached(url), obj_name, map_ks, mtllib, env_map)
+
+
+def scene_from_file(path, obj_name, map_ks, mtllib=None, env_map=None):
+    """parser.rs:204-265: scene `obj_name` from the zip at `path`; `mtllib` names a material library in the archive that is
+    read first, `mtllib` lines of the .obj follow; texture maps come from the same archive; `env_map` = (file, scale) is a
+    flat RGBE image in the archive."""
+    print('Loading scene "%s" from "%s"' % (obj_name, path))
+    archive = _read(path)
+    obj_bytes = _extract_zip(archive, obj_name)
+    mtl_src = _extract_zip(archive, mtllib) if mtllib is not None else None
+    scene = scene_from_obj(obj_bytes, mtl_src, None, mtl_resolver=lambda name: _extract_zip(archive, name),
+                           image_resolver=lambda name: _extract_zip(archive, name), map_ks=map_ks)
+    if env_map is not None:
+        scene.set_environment_map(Texture.Image(Image.from_hdri_bytes(_extract_zip(archive, env_map[0]))), env_map[1])
     return scene

@@ -1,0 +1,129 @@
+"""Film finalisation on the device (lumo_gpu_film_encode / _dev) against a CPU restatement of
+Film::rgb_image (src/tracer/film.rs:173-193), Pixel::value (film.rs:82-90) and TransferFunction::apply
+(src/tracer/color/space.rs:8-36).  Bytes must be equal except where the transfer curve's pow lands within
+a few ulp of an integer code boundary (CUDA pow vs glibc pow): there one code of difference is allowed,
+and the test bounds how often that may happen."""
+import math
+import numpy as np
+import pytest
+from conftest import small_scene
+
+
+def _apply_scalar(c, transfer):
+    """TransferFunction::apply with Rust's saturating float -> u8 cast (NaN -> 0)."""
+    if transfer == 1:
+        beta = 0.018053968510807; alpha = 1.0 + 5.5 * beta
+        ec = 4.5 * c if c <= beta else (alpha * math.pow(c, 0.45) - (alpha - 1.0) if not math.isnan(c) else c)
+    else:
+        ec = 12.92 * c if c <= 0.0031308 else (1.055 * math.pow(c, 1.0 / 2.4) - 0.055 if not math.isnan(c) else c)
+    v = ec * 255.0
+    if math.isnan(v) or v <= 0.0: return 0
+    return 255 if v >= 255.0 else int(v)
+
+
+def rgb_image_ref(pixels, splats, splat_scale, integral, transfer):
+    """Film::rgb_image, pixel by pixel (film.rs:176-189)."""
+    px = pixels.reshape(-1, 4); sp = splats.reshape(-1, 3)
+    out = np.zeros((len(px), 3), dtype=np.uint8)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        lin = px[:, :3] / px[:, 3:4] + splat_scale * sp / integral
+    for i in range(len(px)):
+        for k in range(3):
+            out[i, k] = _apply_scalar(float(lin[i, k]), transfer)
+    return out.reshape(splats.shape)
+
+
+def _accumulators(h, w, seed):
+    rs = np.random.RandomState(seed)
+    wsum = rs.rand(h, w, 1) * 40.0 + 0.5
+    val = np.exp(rs.randn(h, w, 3) * 2.0 - 2.0)             # linear values from ~1e-4 to ~10: both curve segments + saturation
+    px = np.concatenate([val * wsum, wsum], -1)
+    sp = np.where(rs.rand(h, w, 3) < 0.3, rs.rand(h, w, 3) * 5.0, 0.0)
+    flat = px.reshape(-1, 4)
+    flat[0] = 0.0                                           # pixel that never received a sample: 0/0 -> NaN -> 0
+    flat[1, :3] = -flat[1, :3]                              # negative radiance -> 0
+    flat[2, :3] = 1e300; flat[3, 0] = np.inf; flat[4, 1] = np.nan
+    flat[5] = (0.0031308 * 2.0, 0.0031307 * 2.0, 0.0, 2.0)  # either side of the sRGB knee
+    sp.reshape(-1, 3)[:6] = 0.0
+    return px, sp
+
+
+def _compare(got, want, max_off_fraction=2e-4):
+    assert got.shape == want.shape and got.dtype == np.uint8
+    d = np.abs(got.astype(np.int32) - want.astype(np.int32))
+    assert d.max() <= 1, "a byte differs by more than one code"
+    assert (d != 0).mean() <= max_off_fraction, "too many bytes off by one: %g" % (d != 0).mean()
+
+
+def test_reference_restatement_matches_host_film():
+    """CPU: the scalar restatement above and the vectorised host finalisation (lumo_b200/film.py) agree byte for byte."""
+    from lumo_b200 import color
+    px, sp = _accumulators(37, 53, 3)
+    for transfer, cs in ((0, 1), (1, 2)):
+        want = rgb_image_ref(px, sp, 1.0 / 16, 1.7, transfer)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            got = color.encode(px[..., :3] / px[..., 3:4] + (1.0 / 16) * sp / 1.7, cs)
+        assert np.array_equal(got, want)
+        assert tuple(want.reshape(-1, 3)[0]) == (0, 0, 0) and tuple(want.reshape(-1, 3)[1]) == (0, 0, 0)
+        assert tuple(want.reshape(-1, 3)[2]) == (255, 255, 255)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(1, 1), (1, 3), (5, 7), (37, 53), (96, 128)])
+@pytest.mark.parametrize("transfer", [0, 1])
+def test_film_encode_matches_restatement(shape, transfer, gpu_ctx):
+    px, sp = _accumulators(max(shape[0], 2), max(shape[1], 3), 11 + shape[0])
+    px, sp = np.ascontiguousarray(px[:shape[0], :shape[1]]), np.ascontiguousarray(sp[:shape[0], :shape[1]])
+    got = gpu_ctx.film_encode(px, sp, 1.0 / 64, 2.25, transfer)
+    _compare(got, rgb_image_ref(px, sp, 1.0 / 64, 2.25, transfer), max_off_fraction=1e-3 if px.size < 4000 else 2e-4)
+    # linear segment and the special values are exact
+    n = 6 if shape[0] >= 2 and shape[1] >= 3 else 1
+    assert np.array_equal(got.reshape(-1, 3)[:n], rgb_image_ref(px, sp, 1.0 / 64, 2.25, transfer).reshape(-1, 3)[:n])
+
+
+@pytest.mark.gpu
+def test_film_encode_full_hd_and_rendered_film(gpu_ctx):
+    """1920x1080 accumulators against the vectorised host finalisation; then a rendered cornell film through
+    Film.rgb_image_device vs Film.rgb_image."""
+    from lumo_b200 import color, native
+    from lumo_b200.film import Film
+    from lumo_b200 import PixelFilter
+    px, sp = _accumulators(1080, 1920, 5)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        want = color.encode(px[..., :3] / px[..., 3:4] + (1.0 / 1024) * sp / 1.3, 1)
+    _compare(gpu_ctx.film_encode(px, sp, 1.0 / 1024, 1.3, 0), want, max_off_fraction=1e-5)
+    prog, blob, ig = small_scene("cornell")
+    G = native.GpuScene(gpu_ctx, blob)
+    gpx, gsp, cnt, _, _ = G.render(integrator=2, spp=4, seed=3)        # BDPT: splats are populated
+    G.close()
+    film = Film(gpx, gsp, 4, PixelFilter.default(), 1)
+    dev = film.rgb_image_device(ctx=gpu_ctx)
+    _compare(dev, film.rgb_image(), max_off_fraction=1e-3)
+    assert dev.max() > 0
+
+
+@pytest.mark.gpu
+def test_film_encode_dev_reads_render_dev_buffers(gpu_ctx):
+    """render_dev leaves the accumulators in device memory; film_encode_dev finishes them there."""
+    torch = pytest.importorskip("torch")
+    from lumo_b200 import color, native
+    prog, blob, ig = small_scene("bunny")
+    G = native.GpuScene(gpu_ctx, blob)
+    W, H = G.res_x, G.res_y
+    dpx = torch.zeros(H, W, 4, dtype=torch.float64, device="cuda:0"); dsp = torch.zeros(H, W, 3, dtype=torch.float64, device="cuda:0")
+    torch.cuda.synchronize()
+    G.render_dev(dpx.data_ptr(), dsp.data_ptr(), integrator=0, spp=4, seed=9)
+    rgb, ms = gpu_ctx.film_encode_dev(dpx.data_ptr(), dsp.data_ptr(), (H, W), 0.25, 1.0, 0)
+    G.close()
+    px, sp = dpx.cpu().numpy(), dsp.cpu().numpy()
+    with np.errstate(invalid="ignore", divide="ignore"):
+        want = color.encode(px[..., :3] / px[..., 3:4] + 0.25 * sp / 1.0, 1)
+    _compare(rgb, want, max_off_fraction=1e-3)
+    assert ms > 0.0 and rgb.max() > 0
+
+
+@pytest.mark.gpu
+def test_film_encode_rejects_bad_arguments(gpu_ctx):
+    px, sp = _accumulators(4, 4, 1)
+    with pytest.raises(RuntimeError):
+        gpu_ctx.film_encode(px, sp, 1.0, 1.0, transfer=7)
