@@ -824,8 +824,8 @@ extern "C" int32_t lumo_gpu_render_dev(lumo_scene* sc, const lumo_render_params*
 // Film finalisation on the device: Film::rgb_image (src/tracer/film.rs:173-193) = Pixel::value
 // (film.rs:82-90) + splat_scale * splat / filter.integral(), then ColorSpace::encode ->
 // TransferFunction::apply (color/space.rs:8-36, 135-141) with Rust's saturating `as u8`.
-// A thread finishes four pixels (224 B read as 128-bit loads, 12 B written as three 32-bit words):
-// pure streaming, 59 B per pixel, HBM bound.  The host then reads 3 B/pixel instead of 56 B/pixel.
+// Pure streaming, 59 B per pixel (56 read as 128- and 64-bit loads, 3 written), HBM bound once the film is larger
+// than a launch's fixed cost.  The host then reads 3 B/pixel instead of 56 B/pixel.
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t trc_apply(double c, int transfer) {
     double ec;
@@ -845,24 +845,26 @@ __device__ __forceinline__ void film_pixel_rgb8(const double* __restrict__ px, c
     #pragma unroll
     for (int k = 0; k < 3; k++) out[k] = trc_apply(c[k] / w + splat_scale * __ldg(sp + 3 * i + k) / filter_integral, transfer);
 }
+// One pixel per thread (three independent pow chains in flight, enough warps to cover the DRAM latency); the block's
+// 768 bytes are staged in shared memory and leave as 192 aligned 32-bit words.  n_pixels is handled in tiles of 256.
 __global__ void __launch_bounds__(256) k_film_encode(const double* __restrict__ px, const double* __restrict__ sp, size_t n_pixels, double splat_scale,
                                                      double filter_integral, int transfer, uint8_t* __restrict__ rgb) {
-    const size_t groups = (n_pixels + 3) / 4;
-    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (size_t)gridDim.x * blockDim.x) {
-        const size_t i0 = 4 * g;
-        if (i0 + 4 <= n_pixels) {
-            uint32_t v[12];
-            #pragma unroll
-            for (int j = 0; j < 4; j++) film_pixel_rgb8(px, sp, i0 + j, splat_scale, filter_integral, transfer, v + 3 * j);
-            uint32_t* o = (uint32_t*)(rgb + 3 * i0);   // 12 * g: 4-byte aligned
-            #pragma unroll
-            for (int q = 0; q < 3; q++) o[q] = v[4 * q] | (v[4 * q + 1] << 8) | (v[4 * q + 2] << 16) | (v[4 * q + 3] << 24);
-        } else {
-            for (size_t i = i0; i < n_pixels; i++) {
-                uint32_t v[3]; film_pixel_rgb8(px, sp, i, splat_scale, filter_integral, transfer, v);
-                rgb[3 * i] = (uint8_t)v[0]; rgb[3 * i + 1] = (uint8_t)v[1]; rgb[3 * i + 2] = (uint8_t)v[2];
-            }
+    __shared__ __align__(16) uint8_t stage[768];
+    const size_t tiles = (n_pixels + 255) / 256;
+    for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const size_t base = tile * 256, i = base + threadIdx.x;
+        if (i < n_pixels) {
+            uint32_t v[3]; film_pixel_rgb8(px, sp, i, splat_scale, filter_integral, transfer, v);
+            stage[3 * threadIdx.x] = (uint8_t)v[0]; stage[3 * threadIdx.x + 1] = (uint8_t)v[1]; stage[3 * threadIdx.x + 2] = (uint8_t)v[2];
         }
+        __syncthreads();
+        const size_t n_here = n_pixels - base < 256 ? n_pixels - base : 256, bytes = 3 * n_here;   // 3 * base = 768 * tile: word aligned
+        if (threadIdx.x < 192) {
+            const size_t b = 4 * (size_t)threadIdx.x;
+            if (b + 4 <= bytes) ((uint32_t*)(rgb + 3 * base))[threadIdx.x] = ((const uint32_t*)stage)[threadIdx.x];
+            else for (size_t q = b; q < bytes; q++) rgb[3 * base + q] = stage[q];
+        }
+        __syncthreads();
     }
 }
 static int32_t film_encode_impl(lumo_ctx* ctx, const double* px_dev, const double* sp_dev, uint64_t n_pixels, double splat_scale, double filter_integral,
@@ -874,8 +876,7 @@ static int32_t film_encode_impl(lumo_ctx* ctx, const double* px_dev, const doubl
         if (ctx->rgb_mem) { cudaFree(ctx->rgb_mem); ctx->rgb_mem = nullptr; ctx->rgb_bytes = 0; }
         CU(cudaMalloc(&ctx->rgb_mem, out_cap)); ctx->rgb_bytes = out_cap;
     }
-    const size_t groups = (n_pixels + 3) / 4;
-    const unsigned grid = (unsigned)std::min<size_t>((groups + 255) / 256, (size_t)ctx->sm_count * 8);
+    const unsigned grid = (unsigned)std::min<size_t>((n_pixels + 255) / 256, (size_t)ctx->sm_count * 32);
     cudaStream_t st = ctx->stream;
     CU(cudaEventRecord(ctx->ev0, st));
     k_film_encode<<<grid, 256, 0, st>>>(px_dev, sp_dev, (size_t)n_pixels, splat_scale, filter_integral, transfer, (uint8_t*)ctx->rgb_mem);

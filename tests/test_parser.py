@@ -172,3 +172,51 @@ def test_texture_maps_become_image_textures():
     O.close()
     with pytest.warns(UserWarning):
         parser.scene_from_obj(OBJ, mtl_resolver=lambda name: mtl)                    # no resolver: maps ignored with a warning
+
+
+def _zip_bytes(files):
+    import io, zipfile
+    buf = io.BytesIO()
+    with zipfile.ZipFile(buf, "w", zipfile.ZIP_DEFLATED) as z:
+        for name, data in files.items():
+            z.writestr(name, data)
+    return buf.getvalue()
+
+
+def test_reference_entry_points_over_zip_archives(tmp_path, monkeypatch):
+    """parser::{mesh_from_path, mesh_from_url, texture_from_url, scene_from_url, scene_from_file} (parser.rs:125-265):
+    archives cached under ./scenes/, the member chosen by a case-insensitive suffix match, duplicates / misses as errors,
+    the `mtllib` argument read before the .obj's own `mtllib` lines, texture maps and the RGBE environment map from the
+    same archive."""
+    from lumo_b200.image import encode_png
+    monkeypatch.chdir(tmp_path)
+    png = encode_png(np.full((2, 2, 3), [250, 128, 10], np.uint8))
+    hdr = b"#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n-Y 2 +X 2\n" + bytes([128, 128, 128, 129] * 4)
+    mtl = MTL.replace("newmtl grey\nKd 0.5 0.5 0.5\nNs 0", "newmtl grey\nKd 0.5 0.5 0.5\nNs 0\nmap_Kd Tex\\Floor.PNG")
+    extra = "newmtl gold\nKd 1 1 1\n"                                 # given as the `mtllib` argument: read first, so this gold wins
+    (tmp_path / "scenes").mkdir()
+    (tmp_path / "scenes" / "room.zip").write_bytes(_zip_bytes({"Room/Room.OBJ": OBJ, "Room/room.mtl": mtl, "Room/extra.mtl": extra,
+                                                               "Room/tex/floor.png": png, "Room/sky.hdr": hdr}))
+    url = "https://example.invalid/assets/room.zip"
+    s = parser.scene_from_url(url, "room.obj", True, "extra.mtl", ("sky.hdr", 2.0))
+    assert len(s.objects) == 3 and s.num_lights() == 3 and s.environment_map is not None and s.environment_map[1] == 2.0   # two lamp triangles + the environment
+    assert s.objects[0].material.kw["_textures"]["kd_tex"].kind == P.TEX_IMAGE
+    assert s.objects[1].material.kind == P.M_MFDIFFUSE                # the argument's `gold` (diffuse) shadows room.mtl's conductor
+    s2 = parser.scene_from_file("./scenes/room.zip", "room.obj", True)
+    assert s2.objects[1].material.kind == P.M_MFCONDUCTOR and s2.environment_map is None and s2.num_lights() == 2
+    img = parser.texture_from_url(url, "floor.png")
+    assert img.data.shape[:2] == (2, 2)
+    m = parser.mesh_from_url(url, Material.Blank)
+    assert len(m.faces) == 8
+    (tmp_path / "quad.obj").write_text("v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nf 1 2 3 4\n")
+    assert len(parser.mesh_from_path(str(tmp_path / "quad.obj"), Material.Blank).faces) == 2
+    # errors of the reference, in its words
+    with pytest.raises(parser.ObjError, match="Can only load scenes from .zip"): parser.scene_from_url("http://x/room.obj", "room.obj", True)
+    with pytest.raises(parser.ObjError, match="Can only parse .obj files"): parser.scene_from_url(url, "room.mtl", True)
+    with pytest.raises(parser.ObjError, match="Can only load .png files"): parser.texture_from_url(url, "sky.hdr")
+    with pytest.raises(parser.ObjError, match="Can only extract textures from zip archives"): parser.texture_from_url("http://x/a.obj", "a.png")
+    with pytest.raises(parser.ObjError, match="Found multiple .mtl"): parser._extract_zip((tmp_path / "scenes" / "room.zip").read_bytes(), ".mtl")
+    with pytest.raises(parser.ObjError, match="Could not find nothing.obj"): parser.scene_from_file("./scenes/room.zip", "nothing.obj", True)
+    (tmp_path / "scenes" / "thing.bin").write_bytes(b"x")
+    with pytest.raises(parser.ObjError, match="Bad URL"): parser.mesh_from_url("http://x/thing.bin", Material.Blank)
+    with pytest.raises(parser.ObjError, match="could not download"): parser.mesh_from_url("http://127.0.0.1:9/none.obj", Material.Blank)   # nothing cached, nothing listening
