@@ -112,6 +112,15 @@ int32_t lumo_gpu_render(lumo_scene* scene, const lumo_render_params* params, lum
 int32_t lumo_gpu_render_dev(lumo_scene* scene, const lumo_render_params* params, double* pixels_dev, double* splats_dev,
                             uint64_t* counters8, double* device_ms);
 
+/* The same render on n GPUs of this host from ONE process: scenes[g] is the same blob uploaded through
+ * its own context (normally one context per GPU).  [spp_begin, spp_end) is cut into n contiguous ranges, one host
+ * thread per GPU drives its wave pipeline, and the film accumulators are summed on scenes[0]'s GPU by one kernel that
+ * reads the other GPUs' films over NVLink peer memory (staged by cudaMemcpyPeer where peer access is unavailable), in
+ * the fixed order 0..n-1.  `out` is filled as by lumo_gpu_render: counters are sums over GPUs ([5], [6]: maxima),
+ * device_ms = the slowest GPU's render + the reduce, tile_deltas are GPU 0's.  It replaces ThreadPool's fan-out /
+ * fan-in (src/renderer.rs:166-235) for the multi-GPU case; with one process per GPU use lumo_gpu_render_dev + ncclReduce. */
+int32_t lumo_gpu_render_multi(lumo_scene** scenes, int32_t n, const lumo_render_params* params, lumo_film_accum* out);
+
 /* Film finalisation on the device: Film::rgb_image (src/tracer/film.rs:173-193) = Pixel::value (film.rs:82-90)
  * + splat_scale * splat / filter_integral, then TransferFunction::apply (src/tracer/color/space.rs:8-36;
  * transfer 0 = the sRGB curve used by sRGB and DCI-P3, 1 = the rec. 2020 curve) with Rust's saturating

@@ -827,13 +827,31 @@ extern "C" int32_t lumo_gpu_render_dev(lumo_scene* sc, const lumo_render_params*
 // Pure streaming, 59 B per pixel (56 read as 128- and 64-bit loads, 3 written), HBM bound once the film is larger
 // than a launch's fixed cost.  The host then reads 3 B/pixel instead of 56 B/pixel.
 // ---------------------------------------------------------------------------------------------------
+// The curve's pow decides an 8-bit code, so an f32 estimate settles it unless 255*ec lands next to a code boundary:
+// powf is within 4 ulp, the estimate of 255*ec within 2e-4 absolute for ec <= 1, and the f64 pow (which made the
+// kernel FP64-pipe bound: 59 % pipe utilisation at 27 % of HBM bandwidth, profiles/) runs only within 1.5e-3 of a
+// boundary, for NaN, and below code 1.
 __device__ __forceinline__ uint32_t trc_apply(double c, int transfer) {
+    const double beta = 0.018053968510807, alpha = 1.0 + 5.5 * beta;
     double ec;
     if (transfer == 1) {   // rec. 2020
-        const double beta = 0.018053968510807, alpha = 1.0 + 5.5 * beta;
-        ec = c <= beta ? 4.5 * c : alpha * pow(c, 0.45) - (alpha - 1.0);
+        if (c <= beta) ec = 4.5 * c;
+        else {
+            const float vf = 255.0f * ((float)alpha * powf((float)c, 0.45f) - (float)(alpha - 1.0));
+            if (vf >= 255.5f) return 255u;
+            const float fr = vf - floorf(vf);
+            if (vf >= 1.0f && fr > 1.5e-3f && fr < 1.0f - 1.5e-3f) return (uint32_t)vf;
+            ec = alpha * pow(c, 0.45) - (alpha - 1.0);
+        }
     } else {
-        ec = c <= 0.0031308 ? 12.92 * c : 1.055 * pow(c, 1.0 / 2.4) - 0.055;
+        if (c <= 0.0031308) ec = 12.92 * c;
+        else {
+            const float vf = 255.0f * (1.055f * powf((float)c, 1.0f / 2.4f) - 0.055f);
+            if (vf >= 255.5f) return 255u;
+            const float fr = vf - floorf(vf);
+            if (vf >= 1.0f && fr > 1.5e-3f && fr < 1.0f - 1.5e-3f) return (uint32_t)vf;
+            ec = 1.055 * pow(c, 1.0 / 2.4) - 0.055;
+        }
     }
     const double v = ec * 255.0;
     return !(v > 0.0) ? 0u : (v >= 255.0 ? 255u : (uint32_t)v);   // NaN and negatives -> 0, like `as u8`
@@ -906,4 +924,112 @@ extern "C" int32_t lumo_gpu_film_encode(lumo_ctx* ctx, const double* pixels, con
     CU(cudaMemcpyAsync(px, pixels, n_pixels * 32, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(sp, splats, n_pixels * 24, cudaMemcpyHostToDevice, ctx->stream));
     return film_encode_impl(ctx, px, sp, n_pixels, splat_scale, filter_integral, transfer, rgb8, nullptr);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// lumo_gpu_render_multi: one host process, n GPUs.  The scene is replicated (one lumo_scene per
+// context), sample indices [spp_begin, spp_end) are cut into n contiguous ranges (sizes differ by at most one, like
+// lumo_b200/distributed.py: sample_range), one host thread per GPU runs the wave pipeline into that GPU's film, and the
+// films are summed on scenes[0]'s GPU by ONE kernel that loads the peers' accumulators straight over NVLink (peer
+// memory; no staging copies, no NCCL dependency in this library) in the fixed order 0..n-1.  GPUs without peer access
+// to scenes[0]'s are staged through cudaMemcpyPeerAsync first.
+// ---------------------------------------------------------------------------------------------------
+#define LUMO_MAX_MULTI 16
+struct FilmPeers { const double* p[LUMO_MAX_MULTI]; };
+__global__ void __launch_bounds__(256) k_film_reduce(FilmPeers src, int n, double* dst, size_t n_doubles) {
+    const size_t n2 = n_doubles / 2;   // 7 doubles per pixel: W*H*7 may be odd -> 128-bit body + scalar tail
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) {
+        double2 acc = ((const double2*)src.p[0])[i];
+        for (int g = 1; g < n; g++) { const double2 v = ((const double2*)src.p[g])[i]; acc.x += v.x; acc.y += v.y; }
+        ((double2*)dst)[i] = acc;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && (n_doubles & 1)) {
+        double acc = src.p[0][n_doubles - 1];
+        for (int g = 1; g < n; g++) acc += src.p[g][n_doubles - 1];
+        dst[n_doubles - 1] = acc;
+    }
+}
+#include <thread>
+extern "C" int32_t lumo_gpu_render_multi(lumo_scene** scenes, int32_t n, const lumo_render_params* rp, lumo_film_accum* out) {
+    if (!scenes || !rp || !out || !out->pixels || !out->splats) return fail(LUMO_ERR_INVALID, "render_multi: null pointer");
+    if (n < 1 || n > LUMO_MAX_MULTI) return fail(LUMO_ERR_INVALID, "render_multi: n must be in [1, 16]");
+    for (int g = 0; g < n; g++) {
+        if (!scenes[g]) return fail(LUMO_ERR_INVALID, "render_multi: null scene");
+        for (int h = 0; h < g; h++) if (scenes[h]->ctx == scenes[g]->ctx) return fail(LUMO_ERR_INVALID, "render_multi: every scene needs its own context");
+        if (scenes[g]->S.P.camera.res_x != scenes[0]->S.P.camera.res_x || scenes[g]->S.P.camera.res_y != scenes[0]->S.P.camera.res_y)
+            return fail(LUMO_ERR_INVALID, "render_multi: the scenes differ in film resolution");
+    }
+    if (rp->spp_end < rp->spp_begin) return fail(LUMO_ERR_INVALID, "render: bad sample range");
+    const size_t film_px = (size_t)scenes[0]->S.P.camera.res_x * scenes[0]->S.P.camera.res_y, film_doubles = film_px * 7;
+    const uint32_t total = rp->spp_end - rp->spp_begin, base = total / (uint32_t)n, extra = total % (uint32_t)n;
+    struct Part { int32_t rc = LUMO_OK; std::string err; uint64_t counters[8] = {}; double ms = 0.0; };
+    std::vector<Part> parts((size_t)n);
+    std::vector<std::thread> workers;
+    for (int g = 0; g < n; g++) {
+        workers.emplace_back([&, g]() {
+            Part& pt = parts[(size_t)g];
+            lumo_scene* sc = scenes[g]; lumo_ctx* ctx = sc->ctx;
+            pt.rc = [&]() -> int32_t {
+                CU(cudaSetDevice(ctx->device));
+                if (film_doubles * 8 > ctx->film_bytes) {
+                    if (ctx->film_mem) { cudaFree(ctx->film_mem); ctx->film_mem = nullptr; ctx->film_bytes = 0; }
+                    CU(cudaMalloc(&ctx->film_mem, film_doubles * 8)); ctx->film_bytes = film_doubles * 8;
+                }
+                lumo_render_params p = *rp;
+                p.spp_begin = rp->spp_begin + (uint32_t)g * base + std::min<uint32_t>((uint32_t)g, extra);
+                p.spp_end = p.spp_begin + base + ((uint32_t)g < extra ? 1u : 0u);
+                double* px = (double*)ctx->film_mem;
+                return render_impl(sc, &p, px, px + film_px * 4, pt.counters, g == 0 ? out->tile_deltas : nullptr, &pt.ms);
+            }();
+            if (pt.rc != LUMO_OK) pt.err = g_err;   // g_err is per thread: carry the message to the caller's thread
+        });
+    }
+    for (auto& w : workers) w.join();
+    for (int g = 0; g < n; g++) if (parts[(size_t)g].rc != LUMO_OK) return fail(parts[(size_t)g].rc, "render_multi, gpu " + std::to_string(g) + ": " + parts[(size_t)g].err);
+    // ---- the one exchange of the path: sum of the film accumulators on scenes[0]'s GPU -------------------
+    lumo_ctx* c0 = scenes[0]->ctx;
+    CU(cudaSetDevice(c0->device));
+    cudaStream_t st = c0->stream;
+    FilmPeers peers{};
+    std::vector<void*> staged;
+    peers.p[0] = (const double*)c0->film_mem;
+    for (int g = 1; g < n; g++) {
+        lumo_ctx* cg = scenes[g]->ctx;
+        bool direct = cg->device == c0->device;
+        if (!direct) {
+            int can = 0; CU(cudaDeviceCanAccessPeer(&can, c0->device, cg->device));
+            if (can) { cudaError_t e = cudaDeviceEnablePeerAccess(cg->device, 0); if (e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); direct = true; } else cudaGetLastError(); }
+        }
+        if (direct) peers.p[g] = (const double*)cg->film_mem;
+        else {
+            void* tmp = nullptr; CU(cudaMalloc(&tmp, film_doubles * 8)); staged.push_back(tmp);
+            CU(cudaMemcpyPeerAsync(tmp, c0->device, cg->film_mem, cg->device, film_doubles * 8, st));
+            peers.p[g] = (const double*)tmp;
+        }
+    }
+    if (n > 1) {
+        const unsigned grid = (unsigned)std::min<size_t>((film_doubles / 2 + 255) / 256, (size_t)c0->sm_count * 16);
+        CU(cudaEventRecord(c0->ev0, st));
+        k_film_reduce<<<std::max(grid, 1u), 256, 0, st>>>(peers, n, (double*)c0->film_mem, film_doubles);
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(c0->ev1, st));
+        c0->launches++;
+    }
+    const double* px = (const double*)c0->film_mem;
+    CU(cudaMemcpyAsync(out->pixels, px, film_px * 32, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(out->splats, px + film_px * 4, film_px * 24, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (void* t : staged) cudaFree(t);
+    float reduce_ms = 0.f; if (n > 1) CU(cudaEventElapsedTime(&reduce_ms, c0->ev0, c0->ev1));
+    // counters: sums, except [5] deepest path (max) and [6] wave iterations (max); device_ms: slowest GPU + the reduce
+    double ms = 0.0;
+    for (int k = 0; k < 8; k++) out->counters[k] = 0;
+    for (int g = 0; g < n; g++) {
+        const Part& pt = parts[(size_t)g];
+        for (int k = 0; k < 8; k++) out->counters[k] = (k == 5 || k == 6) ? std::max(out->counters[k], pt.counters[k]) : out->counters[k] + pt.counters[k];
+        ms = std::max(ms, pt.ms);
+    }
+    if (n > 1) out->counters[4] += 1;   // k_film_reduce
+    out->device_ms = ms + reduce_ms;
+    return LUMO_OK;
 }

@@ -139,8 +139,9 @@ def gpu_lib():
         L.lumo_gpu_ctx_visits.argtypes = [vp, C.POINTER(C.c_uint64)]
         L.lumo_gpu_film_encode_dev.argtypes = [vp, vp, vp, C.c_uint64, C.c_double, C.c_double, C.c_int32, u8p, C.POINTER(C.c_float)]
         L.lumo_gpu_film_encode.argtypes = [vp, dp, dp, C.c_uint64, C.c_double, C.c_double, C.c_int32, u8p]
+        L.lumo_gpu_render_multi.argtypes = [C.POINTER(vp), C.c_int32, C.POINTER(RenderParams), C.POINTER(FilmAccum)]
         for f in ("lumo_gpu_render_dev", "lumo_gpu_trace_closest_dev", "lumo_gpu_ctx_count_visits", "lumo_gpu_ctx_visits","lumo_gpu_device_count", "lumo_gpu_ctx_create", "lumo_gpu_ctx_destroy", "lumo_gpu_scene_upload", "lumo_gpu_scene_destroy",
-                  "lumo_gpu_trace_closest", "lumo_gpu_trace_any", "lumo_gpu_trace_first_found", "lumo_gpu_render", "lumo_gpu_film_encode", "lumo_gpu_film_encode_dev"):
+                  "lumo_gpu_trace_closest", "lumo_gpu_trace_any", "lumo_gpu_trace_first_found", "lumo_gpu_render", "lumo_gpu_film_encode", "lumo_gpu_film_encode_dev", "lumo_gpu_render_multi"):
             getattr(L, f).restype = C.c_int32
         _gpu = L
     return _gpu
@@ -283,3 +284,19 @@ class GpuScene:
         _check(gpu_lib().lumo_gpu_trace_closest_dev(self.h, C.c_void_p(o_ptr), C.c_void_p(d_ptr), n, C.c_void_p(obj_ptr), C.c_void_p(tri_ptr),
                                                     C.c_void_p(t_ptr), C.c_void_p(bary_ptr), C.byref(ms)), "lumo_gpu_trace_closest_dev")
         return ms.value
+
+
+def render_multi(scenes, integrator=0, spp=1, seed=1, sampler=2, tone_map=0, tone_map_arg=0.0, rr_delta=0.0, spp_begin=0, spp_end=None,
+                 total_spp=None, wave_paths=0):
+    """lumo_gpu_render_multi: `scenes` = the same blob uploaded as one GpuScene per context / GPU; the sample range is
+    split over them and the films are summed on scenes[0]'s GPU.  Returns what GpuScene.render returns."""
+    total = spp if total_spp is None else total_spp
+    end = total if spp_end is None else spp_end
+    P = RenderParams(integrator, sampler, tone_map, 0, tone_map_arg, rr_delta, seed, spp_begin, end, total, wave_paths)
+    W, H = scenes[0].res_x, scenes[0].res_y
+    pixels = np.zeros((H, W, 4)); splats = np.zeros((H, W, 3))
+    deltas = np.zeros(((W + 15) // 16) * ((H + 15) // 16))
+    out = FilmAccum(_dp(pixels), _dp(splats), (C.c_uint64 * 8)(), _dp(deltas), 0.0)
+    hs = (C.c_void_p * len(scenes))(*[s.h for s in scenes])
+    _check(gpu_lib().lumo_gpu_render_multi(hs, len(scenes), C.byref(P), C.byref(out)), "lumo_gpu_render_multi")
+    return pixels, splats, dict(zip(COUNTER_NAMES, (int(v) for v in out.counters))), deltas, out.device_ms

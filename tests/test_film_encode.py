@@ -127,3 +127,32 @@ def test_film_encode_rejects_bad_arguments(gpu_ctx):
     px, sp = _accumulators(4, 4, 1)
     with pytest.raises(RuntimeError):
         gpu_ctx.film_encode(px, sp, 1.0, 1.0, transfer=7)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("transfer", [0, 1])
+def test_film_encode_exact_next_to_code_boundaries(transfer, gpu_ctx):
+    """The kernel settles a code from an f32 estimate of the curve unless the value is next to a code boundary; this
+    walks every boundary k/255 at offsets from 1e-2 down to 1e-9 (both sides) and the saturation edge, where the bytes
+    must equal the f64 restatement exactly."""
+    ks = np.arange(1, 256, dtype=np.float64)
+    offs = np.array([0.0, 1e-2, 2e-3, 1.4e-3, 1e-3, 3e-4, 1e-4, 1e-5, 1e-6, 1e-7, 1e-9])
+    v = (ks[:, None, None] + np.stack([offs, -offs], -1)[None]).reshape(-1) / 255.0          # target ec
+    if transfer == 1:
+        beta = 0.018053968510807; alpha = 1.0 + 5.5 * beta
+        c = np.where(v <= 4.5 * beta, v / 4.5, ((v + (alpha - 1.0)) / alpha) ** (1.0 / 0.45))
+    else:
+        c = np.where(v <= 12.92 * 0.0031308, v / 12.92, ((v + 0.055) / 1.055) ** 2.4)
+    c = np.concatenate([c, [1.0, 1.0 + 1e-12, 1.0 - 1e-12, 1.01, 0.999, 3.0, 1e30]])
+    n = (len(c) + 2) // 3 * 3
+    c = np.concatenate([c, np.full(n - len(c), 0.5)])
+    px = np.concatenate([c.reshape(-1, 1, 3), np.ones((n // 3, 1, 1))], -1)                   # weight 1: value = c exactly
+    sp = np.zeros((n // 3, 1, 3))
+    got = gpu_ctx.film_encode(px, sp, 1.0, 1.0, transfer)
+    want = rgb_image_ref(px, sp, 1.0, 1.0, transfer)
+    d = np.abs(got.astype(np.int32) - want.astype(np.int32)).reshape(-1)
+    # offsets of 0 (and 1e-9 .. 1e-7 after the round trip through the inverse curve) sit within a few ulp of the boundary,
+    # where CUDA's and glibc's pow may round differently; everything else must be equal
+    far = np.ones(len(d), bool); idx = np.arange(len(ks) * len(offs) * 2).reshape(len(ks), len(offs), 2)
+    far[idx[:, [0], :].reshape(-1)] = False
+    assert d.max() <= 1 and d[far].max() == 0, np.nonzero(d[far])[0][:10]
