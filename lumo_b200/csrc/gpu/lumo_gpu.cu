@@ -827,52 +827,72 @@ extern "C" int32_t lumo_gpu_render_dev(lumo_scene* sc, const lumo_render_params*
 // Pure streaming, 59 B per pixel (56 read as 128- and 64-bit loads, 3 written), HBM bound once the film is larger
 // than a launch's fixed cost.  The host then reads 3 B/pixel instead of 56 B/pixel.
 // ---------------------------------------------------------------------------------------------------
-// The curve's pow decides an 8-bit code, so an f32 estimate settles it unless 255*ec lands next to a code boundary:
-// powf is within 4 ulp, the estimate of 255*ec within 2e-4 absolute for ec <= 1, and the f64 pow (which made the
-// kernel FP64-pipe bound: 59 % pipe utilisation at 27 % of HBM bandwidth, profiles/) runs only within 1.5e-3 of a
-// boundary, for NaN, and below code 1.
-__device__ __forceinline__ uint32_t trc_apply(double c, int transfer) {
-    const double beta = 0.018053968510807, alpha = 1.0 + 5.5 * beta;
+// TransferFunction::apply in f64, as the reference computes it.
+__device__ __noinline__ uint32_t trc_apply(double c, int transfer) {
     double ec;
     if (transfer == 1) {   // rec. 2020
-        if (c <= beta) ec = 4.5 * c;
-        else {
-            const float vf = 255.0f * ((float)alpha * powf((float)c, 0.45f) - (float)(alpha - 1.0));
-            if (vf >= 255.5f) return 255u;
-            const float fr = vf - floorf(vf);
-            if (vf >= 1.0f && fr > 1.5e-3f && fr < 1.0f - 1.5e-3f) return (uint32_t)vf;
-            ec = alpha * pow(c, 0.45) - (alpha - 1.0);
-        }
+        const double beta = 0.018053968510807, alpha = 1.0 + 5.5 * beta;
+        ec = c <= beta ? 4.5 * c : alpha * pow(c, 0.45) - (alpha - 1.0);
     } else {
-        if (c <= 0.0031308) ec = 12.92 * c;
-        else {
-            const float vf = 255.0f * (1.055f * powf((float)c, 1.0f / 2.4f) - 0.055f);
-            if (vf >= 255.5f) return 255u;
-            const float fr = vf - floorf(vf);
-            if (vf >= 1.0f && fr > 1.5e-3f && fr < 1.0f - 1.5e-3f) return (uint32_t)vf;
-            ec = 1.055 * pow(c, 1.0 / 2.4) - 0.055;
-        }
+        ec = c <= 0.0031308 ? 12.92 * c : 1.055 * pow(c, 1.0 / 2.4) - 0.055;
     }
     const double v = ec * 255.0;
     return !(v > 0.0) ? 0u : (v >= 255.0 ? 255u : (uint32_t)v);   // NaN and negatives -> 0, like `as u8`
 }
+// The f64 divisions and pow of a pixel only decide three 8-bit codes, and done for every pixel they make the kernel
+// FP64-pipe bound (ncu: pipe 59 % busy at 27 % of HBM bandwidth, profiles/r1_ncu_film_encode.txt).  So a pixel is first
+// evaluated in f32.  For non-negative terms and a weight in [1e-20, 1e20] the f32 linear value is within 3e-7
+// (relative) of the f64 one, and 255*ec computed from it is within
+//   tier 1: 3.4e-4 with __powf (ex2.approx(y * lg2.approx(x)): 1e-6 relative for x in [0.003, 1.1], y < 1),
+//   tier 2: 1.9e-4 with powf (4 ulp)
+// of the f64 result (both curves are continuous at their knee to 1e-7, so the side of the knee does not matter).
+// A code is taken from tier 1 when the value is at least 1.5e-3 away from the neighbouring codes, else from tier 2 at
+// 5e-4; what is left (0.1 % of the values, everything below code 1, NaN, negative terms, weights or splat factors
+// outside the f32-safe range) takes the reference's f64 path.  tests/test_film_encode.py compares the result with the
+// f64-only kernel (LUMO_FILM_F64=1) byte for byte and walks every code boundary.
+template <bool ACCURATE>
+__device__ __forceinline__ bool trc_estimate(float c, int transfer, uint32_t& code) {
+    float vf;
+    if (transfer == 1) {
+        const float beta = 0.018053968510807f, alpha = 1.0f + 5.5f * beta;
+        vf = 255.0f * (c <= beta ? 4.5f * c : alpha * (ACCURATE ? powf(c, 0.45f) : __powf(c, 0.45f)) - (alpha - 1.0f));
+    } else {
+        vf = 255.0f * (c <= 0.0031308f ? 12.92f * c : 1.055f * (ACCURATE ? powf(c, 1.0f / 2.4f) : __powf(c, 1.0f / 2.4f)) - 0.055f);
+    }
+    if (vf >= 255.5f) { code = 255u; return true; }
+    const float margin = ACCURATE ? 5e-4f : 1.5e-3f;
+    const float fl = floorf(vf), fr = vf - fl;
+    if (vf >= 1.0f && fr > margin && fr < 1.0f - margin) { code = (uint32_t)fl; return true; }
+    return false;   // also NaN
+}
 __device__ __forceinline__ void film_pixel_rgb8(const double* __restrict__ px, const double* __restrict__ sp, size_t i, double splat_scale,
-                                                double filter_integral, int transfer, uint32_t out[3]) {
+                                                double filter_integral, int transfer, float splat_f, uint32_t out[3]) {
     const double2 a = __ldg((const double2*)(px + 4 * i)), b = __ldg((const double2*)(px + 4 * i) + 1);
     const double c[3] = {a.x, a.y, b.x}, w = b.y;
+    const double s[3] = {__ldg(sp + 3 * i), __ldg(sp + 3 * i + 1), __ldg(sp + 3 * i + 2)};
+    const float wf = (float)w, rw = __frcp_rn(wf);
+    const bool w_ok = splat_f >= 0.0f && wf >= 1e-20f && wf <= 1e20f;     // splat_f < 0: the host found the splat factor unsafe for f32
     #pragma unroll
-    for (int k = 0; k < 3; k++) out[k] = trc_apply(c[k] / w + splat_scale * __ldg(sp + 3 * i + k) / filter_integral, transfer);
+    for (int k = 0; k < 3; k++) {
+        const float cf = (float)c[k], sf = (float)s[k];
+        if (w_ok && cf >= 0.0f && sf >= 0.0f) {
+            const float lin = cf * rw + splat_f * sf;
+            if (trc_estimate<false>(lin, transfer, out[k])) continue;
+            if (trc_estimate<true>(lin, transfer, out[k])) continue;
+        }
+        out[k] = trc_apply(c[k] / w + splat_scale * s[k] / filter_integral, transfer);
+    }
 }
 // One pixel per thread (three independent pow chains in flight, enough warps to cover the DRAM latency); the block's
 // 768 bytes are staged in shared memory and leave as 192 aligned 32-bit words.  n_pixels is handled in tiles of 256.
 __global__ void __launch_bounds__(256) k_film_encode(const double* __restrict__ px, const double* __restrict__ sp, size_t n_pixels, double splat_scale,
-                                                     double filter_integral, int transfer, uint8_t* __restrict__ rgb) {
+                                                     double filter_integral, int transfer, float splat_f, uint8_t* __restrict__ rgb) {
     __shared__ __align__(16) uint8_t stage[768];
     const size_t tiles = (n_pixels + 255) / 256;
     for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const size_t base = tile * 256, i = base + threadIdx.x;
         if (i < n_pixels) {
-            uint32_t v[3]; film_pixel_rgb8(px, sp, i, splat_scale, filter_integral, transfer, v);
+            uint32_t v[3]; film_pixel_rgb8(px, sp, i, splat_scale, filter_integral, transfer, splat_f, v);
             stage[3 * threadIdx.x] = (uint8_t)v[0]; stage[3 * threadIdx.x + 1] = (uint8_t)v[1]; stage[3 * threadIdx.x + 2] = (uint8_t)v[2];
         }
         __syncthreads();
@@ -897,7 +917,10 @@ static int32_t film_encode_impl(lumo_ctx* ctx, const double* px_dev, const doubl
     const unsigned grid = (unsigned)std::min<size_t>((n_pixels + 255) / 256, (size_t)ctx->sm_count * 32);
     cudaStream_t st = ctx->stream;
     CU(cudaEventRecord(ctx->ev0, st));
-    k_film_encode<<<grid, 256, 0, st>>>(px_dev, sp_dev, (size_t)n_pixels, splat_scale, filter_integral, transfer, (uint8_t*)ctx->rgb_mem);
+    // the f32 pre-pass needs a splat factor that f32 represents well; otherwise (splat_f = -1) every pixel takes the f64 path
+    const bool fast_ok = splat_scale >= 0.0 && splat_scale <= 1e10 && filter_integral >= 1e-10 && filter_integral <= 1e10 && !std::getenv("LUMO_FILM_F64");
+    const float splat_f = fast_ok ? (float)(splat_scale / filter_integral) : -1.0f;
+    k_film_encode<<<grid, 256, 0, st>>>(px_dev, sp_dev, (size_t)n_pixels, splat_scale, filter_integral, transfer, splat_f, (uint8_t*)ctx->rgb_mem);
     CU(cudaGetLastError());
     ctx->launches++;
     CU(cudaEventRecord(ctx->ev1, st));

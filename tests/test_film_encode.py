@@ -156,3 +156,24 @@ def test_film_encode_exact_next_to_code_boundaries(transfer, gpu_ctx):
     far = np.ones(len(d), bool); idx = np.arange(len(ks) * len(offs) * 2).reshape(len(ks), len(offs), 2)
     far[idx[:, [0], :].reshape(-1)] = False
     assert d.max() <= 1 and d[far].max() == 0, np.nonzero(d[far])[0][:10]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("transfer", [0, 1])
+def test_f32_prepass_never_changes_a_byte(transfer, gpu_ctx, monkeypatch):
+    """The kernel's f32 pre-pass against the same kernel with every pixel on the f64 path (LUMO_FILM_F64=1): identical
+    bytes over 2 M random pixels (with splats, zero weights, negatives, NaN, inf) and over weights / values at the edges
+    of the f32 range."""
+    px, sp = _accumulators(1080, 1920, 21 + transfer)
+    flat = px.reshape(-1, 4); rs = np.random.RandomState(4)
+    flat[100:200, 3] = 1e-30; flat[200:300, 3] = 1e25; flat[300:400, :3] *= 1e-40; flat[400:500, :3] *= 1e45      # denormal / huge in f32
+    flat[500:600] *= 1e-25; flat[600:700] *= 1e22
+    flat[700:800, :3] = -np.abs(flat[700:800, :3]) * 1e-3; sp.reshape(-1, 3)[700:800] = rs.rand(100, 3) * 60.0         # negative direct + positive splat
+    for scale, integral in ((1.0 / 64, 0.9977), (1.0, 1e-12), (1e12, 1.0)):
+        monkeypatch.delenv("LUMO_FILM_F64", raising=False)
+        fast = gpu_ctx.film_encode(px, sp, scale, integral, transfer)
+        monkeypatch.setenv("LUMO_FILM_F64", "1")
+        exact = gpu_ctx.film_encode(px, sp, scale, integral, transfer)
+        assert np.array_equal(fast, exact), (scale, integral, int((fast != exact).sum()))
+    monkeypatch.delenv("LUMO_FILM_F64", raising=False)
+    assert len(np.unique(fast)) > 200
