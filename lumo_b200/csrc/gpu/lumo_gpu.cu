@@ -883,26 +883,29 @@ __device__ __forceinline__ void film_pixel_rgb8(const double* __restrict__ px, c
         out[k] = trc_apply(c[k] / w + splat_scale * s[k] / filter_integral, transfer);
     }
 }
-// One pixel per thread (three independent pow chains in flight, enough warps to cover the DRAM latency); the block's
-// 768 bytes are staged in shared memory and leave as 192 aligned 32-bit words.  n_pixels is handled in tiles of 256.
-__global__ void __launch_bounds__(256) k_film_encode(const double* __restrict__ px, const double* __restrict__ sp, size_t n_pixels, double splat_scale,
-                                                     double filter_integral, int transfer, float splat_f, uint8_t* __restrict__ rgb) {
-    __shared__ __align__(16) uint8_t stage[768];
-    const size_t tiles = (n_pixels + 255) / 256;
-    for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const size_t base = tile * 256, i = base + threadIdx.x;
+// One pixel per thread; a warp's 96 bytes are staged in shared memory and leave as 24 aligned 32-bit words, so the only
+// synchronisation is within the warp (a block-wide barrier made seven warps wait for the one with an f64 pixel).
+// Warps stride over tiles of 32 pixels.
+__global__ void __launch_bounds__(256, 6) k_film_encode(const double* __restrict__ px, const double* __restrict__ sp, size_t n_pixels, double splat_scale,
+                                                        double filter_integral, int transfer, float splat_f, uint8_t* __restrict__ rgb) {
+    __shared__ __align__(16) uint8_t stage_all[8][96];
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint8_t* stage = stage_all[warp];
+    const size_t tiles = (n_pixels + 31) / 32, stride = (size_t)gridDim.x * 8;
+    for (size_t tile = (size_t)blockIdx.x * 8 + warp; tile < tiles; tile += stride) {
+        const size_t base = tile * 32, i = base + lane;
         if (i < n_pixels) {
             uint32_t v[3]; film_pixel_rgb8(px, sp, i, splat_scale, filter_integral, transfer, splat_f, v);
-            stage[3 * threadIdx.x] = (uint8_t)v[0]; stage[3 * threadIdx.x + 1] = (uint8_t)v[1]; stage[3 * threadIdx.x + 2] = (uint8_t)v[2];
+            stage[3 * lane] = (uint8_t)v[0]; stage[3 * lane + 1] = (uint8_t)v[1]; stage[3 * lane + 2] = (uint8_t)v[2];
         }
-        __syncthreads();
-        const size_t n_here = n_pixels - base < 256 ? n_pixels - base : 256, bytes = 3 * n_here;   // 3 * base = 768 * tile: word aligned
-        if (threadIdx.x < 192) {
-            const size_t b = 4 * (size_t)threadIdx.x;
-            if (b + 4 <= bytes) ((uint32_t*)(rgb + 3 * base))[threadIdx.x] = ((const uint32_t*)stage)[threadIdx.x];
+        __syncwarp();
+        const size_t n_here = n_pixels - base < 32 ? n_pixels - base : 32, bytes = 3 * n_here;   // 3 * base = 96 * tile: word aligned
+        if (lane < 24) {
+            const size_t b = 4 * (size_t)lane;
+            if (b + 4 <= bytes) ((uint32_t*)(rgb + 3 * base))[lane] = ((const uint32_t*)stage)[lane];
             else for (size_t q = b; q < bytes; q++) rgb[3 * base + q] = stage[q];
         }
-        __syncthreads();
+        __syncwarp();
     }
 }
 static int32_t film_encode_impl(lumo_ctx* ctx, const double* px_dev, const double* sp_dev, uint64_t n_pixels, double splat_scale, double filter_integral,
@@ -914,7 +917,7 @@ static int32_t film_encode_impl(lumo_ctx* ctx, const double* px_dev, const doubl
         if (ctx->rgb_mem) { cudaFree(ctx->rgb_mem); ctx->rgb_mem = nullptr; ctx->rgb_bytes = 0; }
         CU(cudaMalloc(&ctx->rgb_mem, out_cap)); ctx->rgb_bytes = out_cap;
     }
-    const unsigned grid = (unsigned)std::min<size_t>((n_pixels + 255) / 256, (size_t)ctx->sm_count * 32);
+    const unsigned grid = (unsigned)std::min<size_t>((n_pixels + 255) / 256, (size_t)ctx->sm_count * 24);   // 6 resident CTAs per SM, 4 rounds
     cudaStream_t st = ctx->stream;
     CU(cudaEventRecord(ctx->ev0, st));
     // the f32 pre-pass needs a splat factor that f32 represents well; otherwise (splat_f = -1) every pixel takes the f64 path
