@@ -120,6 +120,9 @@ int32_t lumo_gpu_render_dev(lumo_scene* scene, const lumo_render_params* params,
  * device_ms = the slowest GPU's render + the reduce, tile_deltas are GPU 0's.  It replaces ThreadPool's fan-out /
  * fan-in (src/renderer.rs:166-235) for the multi-GPU case; with one process per GPU use lumo_gpu_render_dev + ncclReduce. */
 int32_t lumo_gpu_render_multi(lumo_scene** scenes, int32_t n, const lumo_render_params* params, lumo_film_accum* out);
+/* The sample range lumo_gpu_render_multi gives GPU g of n out of [begin, end): contiguous, disjoint, covering, sizes differing
+ * by at most one.  Host arithmetic only (no device needed). */
+int32_t lumo_gpu_sample_range(int32_t g, int32_t n, uint32_t begin, uint32_t end, uint32_t* g_begin, uint32_t* g_end);
 
 /* Film finalisation on the device: Film::rgb_image (src/tracer/film.rs:173-193) = Pixel::value (film.rs:82-90)
  * + splat_scale * splat / filter_integral, then TransferFunction::apply (src/tracer/color/space.rs:8-36;

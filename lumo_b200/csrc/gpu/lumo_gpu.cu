@@ -976,6 +976,16 @@ __global__ void __launch_bounds__(256) k_film_reduce(FilmPeers src, int n, doubl
     }
 }
 #include <thread>
+// The sample range of GPU g of n: contiguous, disjoint, covering [begin, end), sizes differing by at most one
+// (the same rule as lumo_b200/distributed.py: sample_range).  Pure host arithmetic; exported so that it can be tested without a GPU.
+extern "C" int32_t lumo_gpu_sample_range(int32_t g, int32_t n, uint32_t begin, uint32_t end, uint32_t* g_begin, uint32_t* g_end) {
+    if (!g_begin || !g_end) return fail(LUMO_ERR_INVALID, "sample_range: null pointer");
+    if (n < 1 || g < 0 || g >= n || end < begin) return fail(LUMO_ERR_INVALID, "sample_range: bad arguments");
+    const uint32_t total = end - begin, base = total / (uint32_t)n, extra = total % (uint32_t)n;
+    *g_begin = begin + (uint32_t)g * base + std::min<uint32_t>((uint32_t)g, extra);
+    *g_end = *g_begin + base + ((uint32_t)g < extra ? 1u : 0u);
+    return LUMO_OK;
+}
 extern "C" int32_t lumo_gpu_render_multi(lumo_scene** scenes, int32_t n, const lumo_render_params* rp, lumo_film_accum* out) {
     if (!scenes || !rp || !out || !out->pixels || !out->splats) return fail(LUMO_ERR_INVALID, "render_multi: null pointer");
     if (n < 1 || n > LUMO_MAX_MULTI) return fail(LUMO_ERR_INVALID, "render_multi: n must be in [1, 16]");
@@ -987,7 +997,6 @@ extern "C" int32_t lumo_gpu_render_multi(lumo_scene** scenes, int32_t n, const l
     }
     if (rp->spp_end < rp->spp_begin) return fail(LUMO_ERR_INVALID, "render: bad sample range");
     const size_t film_px = (size_t)scenes[0]->S.P.camera.res_x * scenes[0]->S.P.camera.res_y, film_doubles = film_px * 7;
-    const uint32_t total = rp->spp_end - rp->spp_begin, base = total / (uint32_t)n, extra = total % (uint32_t)n;
     struct Part { int32_t rc = LUMO_OK; std::string err; uint64_t counters[8] = {}; double ms = 0.0; };
     std::vector<Part> parts((size_t)n);
     std::vector<std::thread> workers;
@@ -1002,8 +1011,7 @@ extern "C" int32_t lumo_gpu_render_multi(lumo_scene** scenes, int32_t n, const l
                     CU(cudaMalloc(&ctx->film_mem, film_doubles * 8)); ctx->film_bytes = film_doubles * 8;
                 }
                 lumo_render_params p = *rp;
-                p.spp_begin = rp->spp_begin + (uint32_t)g * base + std::min<uint32_t>((uint32_t)g, extra);
-                p.spp_end = p.spp_begin + base + ((uint32_t)g < extra ? 1u : 0u);
+                { const int32_t rc = lumo_gpu_sample_range(g, n, rp->spp_begin, rp->spp_end, &p.spp_begin, &p.spp_end); if (rc != LUMO_OK) return rc; }
                 double* px = (double*)ctx->film_mem;
                 return render_impl(sc, &p, px, px + film_px * 4, pt.counters, g == 0 ? out->tile_deltas : nullptr, &pt.ms);
             }();

@@ -140,8 +140,9 @@ def gpu_lib():
         L.lumo_gpu_film_encode_dev.argtypes = [vp, vp, vp, C.c_uint64, C.c_double, C.c_double, C.c_int32, u8p, C.POINTER(C.c_float)]
         L.lumo_gpu_film_encode.argtypes = [vp, dp, dp, C.c_uint64, C.c_double, C.c_double, C.c_int32, u8p]
         L.lumo_gpu_render_multi.argtypes = [C.POINTER(vp), C.c_int32, C.POINTER(RenderParams), C.POINTER(FilmAccum)]
+        L.lumo_gpu_sample_range.argtypes = [C.c_int32, C.c_int32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         for f in ("lumo_gpu_render_dev", "lumo_gpu_trace_closest_dev", "lumo_gpu_ctx_count_visits", "lumo_gpu_ctx_visits","lumo_gpu_device_count", "lumo_gpu_ctx_create", "lumo_gpu_ctx_destroy", "lumo_gpu_scene_upload", "lumo_gpu_scene_destroy",
-                  "lumo_gpu_trace_closest", "lumo_gpu_trace_any", "lumo_gpu_trace_first_found", "lumo_gpu_render", "lumo_gpu_film_encode", "lumo_gpu_film_encode_dev", "lumo_gpu_render_multi"):
+                  "lumo_gpu_trace_closest", "lumo_gpu_trace_any", "lumo_gpu_trace_first_found", "lumo_gpu_render", "lumo_gpu_film_encode", "lumo_gpu_film_encode_dev", "lumo_gpu_render_multi", "lumo_gpu_sample_range"):
             getattr(L, f).restype = C.c_int32
         _gpu = L
     return _gpu
@@ -300,3 +301,10 @@ def render_multi(scenes, integrator=0, spp=1, seed=1, sampler=2, tone_map=0, ton
     hs = (C.c_void_p * len(scenes))(*[s.h for s in scenes])
     _check(gpu_lib().lumo_gpu_render_multi(hs, len(scenes), C.byref(P), C.byref(out)), "lumo_gpu_render_multi")
     return pixels, splats, dict(zip(COUNTER_NAMES, (int(v) for v in out.counters))), deltas, out.device_ms
+
+
+def sample_range(g, n, begin, end):
+    """lumo_gpu_sample_range: [begin, end) of GPU g of n inside lumo_gpu_render_multi (host arithmetic, no device needed)."""
+    b = C.c_uint32(0); e = C.c_uint32(0)
+    _check(gpu_lib().lumo_gpu_sample_range(g, n, begin, end, C.byref(b), C.byref(e)), "lumo_gpu_sample_range")
+    return b.value, e.value

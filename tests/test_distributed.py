@@ -22,6 +22,21 @@ def test_sample_ranges_partition():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_c_abi_sample_range_equals_the_python_rule():
+    """lumo_gpu_render_multi splits the sample range with lumo_gpu_sample_range; it must be the rule the one-process-per-GPU
+    path uses (distributed.sample_range), also with an offset range, and must reject bad arguments."""
+    from lumo_b200 import native
+    for total in (0, 1, 7, 64, 1000):
+        for world in (1, 2, 3, 8, 16):
+            for off in (0, 5):
+                got = [native.sample_range(g, world, off, off + total) for g in range(world)]
+                want = [tuple(off + v for v in D.sample_range(g, world, total)) for g in range(world)]
+                assert got == want
+    for bad in ((2, 2, 0, 8), (-1, 2, 0, 8), (0, 0, 0, 8), (0, 2, 9, 8)):
+        with pytest.raises(RuntimeError, match="bad arguments"):
+            native.sample_range(*bad)
+
+
 def _fake_render(px, sp, begin, end, W, H):
     pix = torch.arange(W * H, dtype=torch.float64).view(H, W)
     for s in range(begin, end):
