@@ -295,6 +295,7 @@ def main():
     ctx.count_visits(True)
     cntc, _ = scene.render_dev(px_ptr, sp_ptr, integrator=integrator, seed=seeds[-1], spp_begin=s0, spp_end=s1, total_spp=total_spp, wave_paths=args.wave_paths)
     vis_closest, vis_occl = ctx.visits()
+    occl_stats = ctx.occlusion_stats()
     ctx.count_visits(False)
     # wave trace kernel per ray: 4 B slot index + 48 B ray read, 40 B hit record written
     bytes_trace = ray_bytes(vis_closest, cntc["closest"], 92)
@@ -310,7 +311,7 @@ def main():
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                         "algorithmic_bytes_per_launch": bytes_trace / max(trace_n, 1), "launches_per_step": trace_n, "avg_launch_ms": trace_ms / max(trace_n, 1),
                         "bytes_per_ray": bytes_trace / max(cntc["closest"], 1), "visits_per_ray": {k: v / max(cntc["closest"], 1) for k, v in vis_closest.items()},
-                        "traffic": None,
+                        "traffic": None, "occlusion_bvh_per_ray": {k: v / max(cntc["occlusion"], 1) for k, v in occl_stats.items()},
                         "occlusion_kernel": {"achieved": bytes_occl / (occl_ms * 1e-3) / 1e9 if occl_ms > 0 else None, "bytes_per_ray": bytes_occl / max(cntc["occlusion"], 1)},
                         "note": "algorithmic bytes count every node/triangle visit; a scene that fits the 126 MB L2 is served from L2/L1, so this can exceed the HBM peak (see profiles/ for dram__bytes)"}
     try:   # dram__bytes_read.sum + dram__bytes_write.sum of that kernel from the committed `ncu --set full` capture, per launch like `achieved`

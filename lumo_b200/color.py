@@ -50,12 +50,13 @@ def wb_matrix(illuminant_name):
 
 def encode(rgb, color_space):
     """TransferFunction::apply (space.rs:8-36): returns uint8, truncating and saturating."""
+    from .native import host_math      # the transfer curve's pow is csrc/common/lumo_math.h: the device kernel's, bit for bit
     c = np.asarray(rgb, dtype=np.float64)
     with np.errstate(invalid="ignore"):
         if color_space == 2:
             beta = 0.018053968510807; alpha = 1.0 + 5.5 * beta
-            ec = np.where(c <= beta, 4.5 * c, alpha * np.power(np.maximum(c, 0), 0.45) - (alpha - 1.0))
+            ec = np.where(c <= beta, 4.5 * c, alpha * host_math("pow", np.maximum(c, 0), 0.45) - (alpha - 1.0))
         else:
-            ec = np.where(c <= 0.0031308, 12.92 * c, 1.055 * np.power(np.maximum(c, 0), 1.0 / 2.4) - 0.055)
+            ec = np.where(c <= 0.0031308, 12.92 * c, 1.055 * host_math("pow", np.maximum(c, 0), 1.0 / 2.4) - 0.055)
     v = np.nan_to_num(ec * 255.0, nan=0.0, posinf=255.0, neginf=0.0)
     return np.clip(np.trunc(v), 0, 255).astype(np.uint8)

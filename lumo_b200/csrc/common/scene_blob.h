@@ -10,7 +10,7 @@
 #include <stdint.h>
 
 #define LUMO_BLOB_MAGIC 0x31424F4C424D554CULL /* "LUMBLOB1" */
-#define LUMO_BLOB_VERSION 4u
+#define LUMO_BLOB_VERSION 5u
 #define LUMO_NONE 0xFFFFFFFFu
 
 enum LumoSection {
@@ -34,6 +34,10 @@ enum LumoSection {
     LSEC_TEX_PIXELS,      // f32[4] per pixel: Image<Spectrum>.buffer as Spectrum {c0,c1,c2,scale}, row-major (image.rs:8-16)
     LSEC_TEX_F64,         // f64 pool: Perlin tables (256 x 3 lattice normals, then 3 x 256 permutation entries as f64) and
                           //           Image<Normal> buffers (3 f64 per pixel)
+    LSEC_AH_NODES,        // LumoAhNode[]  4-wide BVH over every primitive of the scene in world space (order-free occlusion queries)
+    LSEC_AH_PRIMS,        // LumoAhPrim[]  leaf primitive lists of that BVH
+    LSEC_OBJ_PATH_OFF,    // u32[n_objects + n_lights + 1]  CSR offsets into LSEC_OBJ_PATH
+    LSEC_OBJ_PATH,        // u32[]  per object: the object-BVH nodes from its root down to the leaf that lists it (absolute indices into LSEC_TLAS_NODES)
     LSEC_COUNT
 };
 
@@ -70,6 +74,23 @@ struct LumoKdNode {            // 16 B  (kdtree/node.rs:24-30 flattened)
     double point;              // split coordinate (inner)
     uint32_t a;                // inner: right child (absolute node index); leaf: first entry in LSEC_KD_LEAF
     uint32_t b;                // inner: axis 0..2; leaf: 0x80000000 | count
+};
+// Occlusion (`Scene::hit_light`, scene.rs:165-189) asks a boolean that does not depend on the visit order, so it is
+// answered from a second structure over the same primitives: a 4-wide BVH in world space with f32 boxes rounded outwards
+// (conservative culling only — every accepted primitive is confirmed by the reference's own f64 test and the reference's
+// own per-object traversal, csrc/gpu/occlude.cuh).  128 B = one cache line = eight 16-byte loads.
+#define LUMO_AH_LEAF 0x80000000u       /* child is a leaf: bits 0..26 first primitive, bits 27..30 count - 1 */
+#define LUMO_AH_SPHERE 0x80000000u     /* LumoAhPrim.tri: bit 31 set -> sphere, low bits = index into LSEC_SPHERES */
+#define LUMO_AH_INSTANCED 0x80000000u  /* LumoAhPrim.obj: bit 31 set -> the object has an instance transform */
+#define LUMO_AH_MAX_LEAF 4u
+struct LumoAhNode {            // 128 B
+    float lo_x[4], lo_y[4], lo_z[4], hi_x[4], hi_y[4], hi_z[4];   // child boxes, structure of arrays; empty child: lo = +inf, hi = -inf
+    uint32_t child[4];         // LUMO_NONE: empty; LUMO_AH_LEAF | ...: leaf; else index of the child node
+    uint32_t pad[4];
+};
+struct LumoAhPrim {            // 8 B
+    uint32_t tri;              // global triangle index (LSEC_TRI_VERTS), or LUMO_AH_SPHERE | sphere index
+    uint32_t obj;              // global object index (Scene.objects then Scene.lights) | LUMO_AH_INSTANCED: frame of the exact test, and the object the confirming traversal runs on
 };
 struct LumoTriVerts { double a[3], b[3], c[3], pad; };   // 80 B
 struct LumoTriShade {          // 32 B

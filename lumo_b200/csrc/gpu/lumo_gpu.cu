@@ -18,7 +18,6 @@ static int32_t fail(int32_t code, const std::string& msg) { g_err = msg; return 
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(e_ == cudaErrorMemoryAllocation ? LUMO_ERR_OOM : LUMO_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
 
 #define LUMO_ITER_LOG_CAP 16384
-#define LUMO_NM_MIN_RAYS 131072u
 #define LUMO_ITER_BATCH 4   /* wave iterations enqueued per host synchronisation */
 
 struct lumo_ctx {
@@ -36,10 +35,11 @@ struct lumo_ctx {
     unsigned long long launches = 0;
     Counters* d_visit = nullptr;   // traversal visit counters (CNT passes): [0] closest-hit kernels, [1] occlusion kernels
     int count_visits = 0;
-    void* nm_mem = nullptr; size_t nm_bytes = 0; NmRays nm_rays{}; uint32_t* d_n_batch = nullptr;   // node-major traversal state (trace_nm.cuh)
-    int nm = 0;                    // LUMO_TRACE_NM=1 selects the node-major traversal of small-BVH scenes (trace_nm.cuh): bit-exact, measured 10-25 % slower
+    AhCounters* d_ah = nullptr;    // occlusion-BVH counters (CNT passes and LUMO_OCCLUDE_CHECK)
+    void* occl_mem = nullptr; size_t occl_bytes = 0;   // queues of the batch occlusion entry point (lumo_gpu_trace_any)
+    int occl_faithful = 0;         // LUMO_OCCLUDE_FAITHFUL=1: shadow rays replay the reference's object BVH + kd-trees (k_wave_occlude) instead of the occlusion BVH
+    int occl_check = 0;            // LUMO_OCCLUDE_CHECK=1: run both on every shadow ray of a render and count disagreements (counters[7] high half)
     uint32_t* d_iter_log = nullptr; uint32_t iter_log_n = 0;   // (closest-hit rays, shadow rays) per wave iteration of the last render's main pass
-    int flat = 0;                  // LUMO_TRACE_FLAT=1 selects the lane-refilled traversal kernels (trace_flat.cuh): bit-exact too, but measured 2x slower
     // per-kernel-class device time of the last render (CUDA events on the launching stream)
     cudaEvent_t kev[5 * LUMO_ITER_BATCH] = {};
     double kernel_ms[4] = {0, 0, 0, 0}; unsigned long long kernel_launches[4] = {0, 0, 0, 0};
@@ -49,10 +49,7 @@ struct lumo_scene {
     uint8_t* d_blob = nullptr; uint64_t len = 0, cap = 0;
     DevScene S;
     LumoBlobHeader H;
-    struct NmSeg { uint32_t i0, i1; int heavy; };   // items [i0, i1]; heavy = local index of the heavy object that ends it, or -1
-    struct NmHostPlan { NmPlan P; std::vector<NmSeg> segs; std::vector<uint32_t> heavy; };
     bool has_textures = false;                       // any LumoTexture record (then materials may refer to textures / bump maps)
-    NmHostPlan nm_obj, nm_lig; bool nm_ok = false;   // node-major traversal plans (small object BVHs only)
     uint32_t kind_mask = 0;   // bit k set: some Standard material of LumoMatKind k exists (which shade kernels to launch)
 };
 
@@ -84,9 +81,10 @@ extern "C" int32_t lumo_gpu_ctx_create(int32_t device, lumo_ctx** out) {
     CU(cudaMalloc(&ctx->d_cursor, 8));
     // f64 traversal keeps two explicit stacks per thread
     cudaDeviceSetLimit(cudaLimitStackSize, 4096);
-    { const char* e = std::getenv("LUMO_TRACE_FLAT"); if (e) ctx->flat = std::atoi(e) != 0; }
-    { const char* e = std::getenv("LUMO_TRACE_NM"); if (e) ctx->nm = std::atoi(e) != 0; }
-    CU(cudaMalloc(&ctx->d_n_batch, 4));
+    { const char* e = std::getenv("LUMO_OCCLUDE_FAITHFUL"); if (e) ctx->occl_faithful = std::atoi(e) != 0; }
+    { const char* e = std::getenv("LUMO_OCCLUDE_CHECK"); if (e) ctx->occl_check = std::atoi(e) != 0; }
+    CU(cudaMalloc(&ctx->d_ah, sizeof(AhCounters)));
+    CU(cudaMemset(ctx->d_ah, 0, sizeof(AhCounters)));
     *out = ctx; return LUMO_OK;
 }
 extern "C" int32_t lumo_gpu_ctx_destroy(lumo_ctx* ctx) {
@@ -98,8 +96,8 @@ extern "C" int32_t lumo_gpu_ctx_destroy(lumo_ctx* ctx) {
     if (ctx->film_mem) cudaFree(ctx->film_mem);
     if (ctx->rgb_mem) cudaFree(ctx->rgb_mem);
     if (ctx->d_cursor) cudaFree(ctx->d_cursor);
-    if (ctx->nm_mem) cudaFree(ctx->nm_mem);
-    if (ctx->d_n_batch) cudaFree(ctx->d_n_batch);
+    if (ctx->d_ah) cudaFree(ctx->d_ah);
+    if (ctx->occl_mem) cudaFree(ctx->occl_mem);
     if (ctx->blob_cache) cudaFree(ctx->blob_cache);
     if (ctx->d_visit) cudaFree(ctx->d_visit);
     if (ctx->d_iter_log) cudaFree(ctx->d_iter_log);
@@ -127,6 +125,26 @@ extern "C" int32_t lumo_gpu_ctx_count_visits(lumo_ctx* ctx, int32_t enable) {
     CU(cudaSetDevice(ctx->device));
     ctx->count_visits = enable ? 1 : 0;
     CU(cudaMemset(ctx->d_visit, 0, 2 * sizeof(Counters)));
+    CU(cudaMemset(ctx->d_ah, 0, sizeof(AhCounters)));
+    return LUMO_OK;
+}
+// Counters of the occlusion-BVH kernels (occlude.cuh) since the last lumo_gpu_ctx_count_visits call: [0] BVH nodes visited,
+// [1] leaf primitives fetched, [2] f64 triangle tests, [3] sphere tests, [4] candidate blockers, [5] confirmed by the
+// reference's per-object traversal, [6] rays sent to the faithful kernel — all only while visit counting is on — and
+// [7] rays on which the occlusion BVH and the faithful kernel disagreed (LUMO_OCCLUDE_CHECK=1 renders; must stay 0).
+extern "C" int32_t lumo_gpu_ctx_occlusion_stats(lumo_ctx* ctx, uint64_t* out8) {
+    if (!ctx || !out8) return fail(LUMO_ERR_INVALID, "occlusion_stats: null pointer");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    AhCounters c; CU(cudaMemcpy(&c, ctx->d_ah, sizeof c, cudaMemcpyDeviceToHost));
+    out8[0] = c.nodes; out8[1] = c.prims; out8[2] = c.tris; out8[3] = c.spheres; out8[4] = c.candidates; out8[5] = c.confirmed; out8[6] = c.fallback; out8[7] = c.mismatches;
+    return LUMO_OK;
+}
+// Overrides the LUMO_OCCLUDE_FAITHFUL / LUMO_OCCLUDE_CHECK environment switches of this context: mode 0 = occlusion BVH
+// (default), 1 = the reference's traversal for shadow rays too, 2 = both on every shadow ray, disagreements counted.
+extern "C" int32_t lumo_gpu_ctx_occlusion_mode(lumo_ctx* ctx, int32_t mode) {
+    if (!ctx || mode < 0 || mode > 2) return fail(LUMO_ERR_INVALID, "occlusion_mode: bad arguments");
+    ctx->occl_faithful = mode == 1; ctx->occl_check = mode == 2;
     return LUMO_OK;
 }
 // out12: six counters of the closest-hit kernels, then six of the occlusion kernels
@@ -155,6 +173,39 @@ extern "C" int32_t lumo_gpu_ctx_kernel_times(lumo_ctx* ctx, double* ms4, uint64_
     return LUMO_OK;
 }
 
+// lumo_math.h as compiled for the device: fn 0 sin, 1 cos, 2 atan2(x, y), 3 acos, 4 atanh, 5 cosh, 6 exp, 7 log, 8 pow(x, y).
+// tests/test_lumo_math.py compares the bits with the same header compiled by g++ for the oracle and for the host library.
+__global__ void k_math_eval(int fn, const double* x, const double* y, uint64_t n, double* out) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const double a = x[i], b = y ? y[i] : 0.0;
+        double r;
+        switch (fn) {
+        case 0: r = lm_sin(a); break; case 1: r = lm_cos(a); break; case 2: r = lm_atan2(a, b); break; case 3: r = lm_acos(a); break;
+        case 4: r = lm_atanh(a); break; case 5: r = lm_cosh(a); break; case 6: r = lm_exp(a); break; case 7: r = lm_log(a); break;
+        default: r = lm_pow(a, b); break;
+        }
+        out[i] = r;
+    }
+}
+extern "C" int32_t lumo_gpu_math_eval(lumo_ctx* ctx, int32_t fn, const double* x, const double* y, uint64_t n, double* out) {
+    if (!ctx || !x || !out) return fail(LUMO_ERR_INVALID, "math_eval: null pointer");
+    if (fn < 0 || fn > 8) return fail(LUMO_ERR_INVALID, "math_eval: unknown function");
+    if (n == 0) return LUMO_OK;
+    CU(cudaSetDevice(ctx->device));
+    double *dx = nullptr, *dy = nullptr, *dout = nullptr;
+    cudaError_t e = cudaMalloc(&dx, n * 8);
+    if (e == cudaSuccess && y) e = cudaMalloc(&dy, n * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&dout, n * 8);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dx, x, n * 8, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && y) e = cudaMemcpyAsync(dy, y, n * 8, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) { k_math_eval<<<(unsigned)std::min<uint64_t>((n + 255) / 256, 4096), 256, 0, ctx->stream>>>(fn, dx, dy, n, dout); e = cudaGetLastError(); ctx->launches++; }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout, n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (dx) cudaFree(dx); if (dy) cudaFree(dy); if (dout) cudaFree(dout);
+    if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? LUMO_ERR_OOM : LUMO_ERR_CUDA, std::string("math_eval: ") + cudaGetErrorString(e));
+    return LUMO_OK;
+}
+
 // ---- scene -------------------------------------------------------------------------------------------
 static bool validate_blob(const uint8_t* b, uint64_t len, LumoBlobHeader& H, std::string& why) {
     if (len < sizeof(LumoBlobHeader)) { why = "blob shorter than its header"; return false; }
@@ -164,7 +215,7 @@ static bool validate_blob(const uint8_t* b, uint64_t len, LumoBlobHeader& H, std
     if (H.n_sections != LSEC_COUNT || H.total_bytes != len) { why = "blob size / section count mismatch"; return false; }
     static const size_t elem[LSEC_COUNT] = {sizeof(LumoTlasNode), 4, sizeof(LumoObject), sizeof(LumoInstance), sizeof(LumoKdTree), sizeof(LumoKdNode), 4,
                                             sizeof(LumoTriVerts), sizeof(LumoTriShade), 24, 16, sizeof(LumoRect), sizeof(LumoSphere), sizeof(LumoMaterial), 96 * 8, sizeof(LumoLight),
-                                            sizeof(LumoTexture), 16, 8};
+                                            sizeof(LumoTexture), 16, 8, sizeof(LumoAhNode), sizeof(LumoAhPrim), 4, 4};
     for (int s = 0; s < LSEC_COUNT; s++) {
         const LumoSectionRef& r = H.sec[s];
         if (r.offset % 16 || r.offset > len || r.bytes > len - r.offset || r.bytes != r.count * elem[s]) { why = "blob section " + std::to_string(s) + " is malformed"; return false; }
@@ -209,6 +260,28 @@ static bool validate_blob(const uint8_t* b, uint64_t len, LumoBlobHeader& H, std
         if (T.kind == LTEX_BUMP) ok = T.width > 0 && T.height > 0 && T.data + 3ull * T.width * T.height <= H.sec[LSEC_TEX_F64].count;
         if (!ok) { why = "texture record " + std::to_string(i) + " out of range"; return false; }
     }
+    {   // occlusion BVH: child links, leaf ranges, primitive records; per-object node chains
+        const LumoAhNode* an = (const LumoAhNode*)(b + H.sec[LSEC_AH_NODES].offset);
+        const LumoAhPrim* ap = (const LumoAhPrim*)(b + H.sec[LSEC_AH_PRIMS].offset);
+        const uint64_t n_an = H.sec[LSEC_AH_NODES].count, n_ap = H.sec[LSEC_AH_PRIMS].count, n_obj = H.sec[LSEC_OBJECTS].count;
+        if (n_an == 0 || n_ap == 0 || n_ap >= (1ull << 27)) { why = "occlusion BVH is empty or too large"; return false; }
+        for (uint64_t i = 0; i < n_an; i++) for (int k = 0; k < 4; k++) {
+            const uint32_t c = an[i].child[k];
+            if (c == LUMO_NONE) { if (!(an[i].lo_x[k] > an[i].hi_x[k])) { why = "occlusion BVH: empty child with a non-empty box"; return false; } continue; }
+            if (c & LUMO_AH_LEAF) { const uint64_t first = c & 0x07FFFFFFu, cnt = ((c >> 27) & 0xFu) + 1u; if (first + cnt > n_ap) { why = "occlusion BVH leaf range out of bounds"; return false; } }
+            else if (c >= n_an || c <= i) { why = "occlusion BVH child link out of range"; return false; }   // children follow their parent: no cycles
+        }
+        for (uint64_t i = 0; i < n_ap; i++) {
+            const uint32_t o = ap[i].obj & ~LUMO_AH_INSTANCED;
+            if (o >= n_obj || ((ap[i].obj & LUMO_AH_INSTANCED) != 0) != (objs[o].inst >= 0)) { why = "occlusion BVH primitive: bad object"; return false; }
+            if (ap[i].tri & LUMO_AH_SPHERE) { if ((ap[i].tri & ~LUMO_AH_SPHERE) >= H.sec[LSEC_SPHERES].count) { why = "occlusion BVH primitive: bad sphere"; return false; } }
+            else if (ap[i].tri >= H.sec[LSEC_TRI_VERTS].count) { why = "occlusion BVH primitive: bad triangle"; return false; }
+        }
+        const uint32_t* po = (const uint32_t*)(b + H.sec[LSEC_OBJ_PATH_OFF].offset); const uint32_t* pn = (const uint32_t*)(b + H.sec[LSEC_OBJ_PATH].offset);
+        if (H.sec[LSEC_OBJ_PATH_OFF].count != n_obj + 1) { why = "object path offsets: wrong count"; return false; }
+        for (uint64_t i = 0; i < n_obj; i++) if (po[i] > po[i + 1] || po[i + 1] > H.sec[LSEC_OBJ_PATH].count) { why = "object path offsets out of range"; return false; }
+        for (uint64_t i = 0; i < H.sec[LSEC_OBJ_PATH].count; i++) if (pn[i] >= H.sec[LSEC_TLAS_NODES].count) { why = "object path node out of range"; return false; }
+    }
     for (uint64_t i = 0; i < H.sec[LSEC_MATERIALS].count; i++) {
         const uint32_t col[4] = {mats[i].kd_tex, mats[i].ks_tex, mats[i].tf_tex, mats[i].ke_tex};
         for (uint32_t t : col) if (t != LUMO_NONE && (t >= n_tex || tx[t].kind == LTEX_BUMP)) { why = "material texture index out of range"; return false; }
@@ -243,49 +316,9 @@ extern "C" int32_t lumo_gpu_scene_upload(lumo_ctx* ctx, const void* blob, uint64
     S.materials = (const LumoMaterial*)at(LSEC_MATERIALS); S.tables = (const double*)at(LSEC_TABLES); S.lights = (const LumoLight*)at(LSEC_LIGHTS);
     sc->has_textures = H.sec[LSEC_TEXTURES].count > 0;
     S.textures = (const LumoTexture*)at(LSEC_TEXTURES); S.tex_pixels = (const float*)at(LSEC_TEX_PIXELS); S.tex_f64 = (const double*)at(LSEC_TEX_F64);
+    S.ah_nodes = (const LumoAhNode*)at(LSEC_AH_NODES); S.ah_prims = (const LumoAhPrim*)at(LSEC_AH_PRIMS);
+    S.obj_path_off = (const uint32_t*)at(LSEC_OBJ_PATH_OFF); S.obj_path = (const uint32_t*)at(LSEC_OBJ_PATH);
     S.P = H.params;
-    {   // node-major plans: both BVHs in the reference's traversal order, if they are small enough
-        const uint8_t* hb = (const uint8_t*)blob;
-        const LumoTlasNode* tn = (const LumoTlasNode*)(hb + H.sec[LSEC_TLAS_NODES].offset);
-        const uint32_t* tl = (const uint32_t*)(hb + H.sec[LSEC_TLAS_LEAF].offset);
-        const LumoObject* ob = (const LumoObject*)(hb + H.sec[LSEC_OBJECTS].offset);
-        const LumoKdTree* kt = (const LumoKdTree*)(hb + H.sec[LSEC_KD_TREES].offset);
-        auto build = [&](lumo_scene::NmHostPlan& hp, uint32_t root, uint32_t n_nodes, uint32_t obj_base, uint32_t n_objects) -> bool {
-            if (n_nodes == 0 || n_nodes > LUMO_NM_MAX_NODES || n_objects > LUMO_NM_MAX_OBJECTS) return false;
-            NmPlan& P = hp.P; std::memset(&P, 0, sizeof P);
-            P.root = root; P.obj_base = obj_base; P.n_objects = n_objects;
-            for (uint32_t o = 0; o < n_objects; o++) {
-                const LumoObject& O = ob[obj_base + o];
-                if (O.kind == LOBJ_KD && kt[O.geom].n_tris > LUMO_NM_HEAVY_TRIS) { P.heavy_bits |= 1u << o; hp.heavy.push_back(o); }
-            }
-            std::vector<std::pair<uint32_t, int>> st; st.push_back({0u, -1});
-            uint32_t k = 0, n_items = 0, seg0 = 0;
-            while (!st.empty()) {
-                uint32_t node = st.back().first; int par = st.back().second; st.pop_back();
-                for (;;) {
-                    if (k >= LUMO_NM_MAX_NODES || node >= n_nodes) return false;
-                    P.node[k] = node; P.parent[k] = par;
-                    P.item[n_items++] = k;
-                    const LumoTlasNode& nd = tn[root + node];
-                    if (nd.count > 0) {                                  // leaf: its objects in list order
-                        for (uint32_t j = 0; j < nd.count; j++) {
-                            const uint32_t local = tl[nd.first + j];
-                            if (local >= n_objects || n_items >= LUMO_NM_MAX_ITEMS) return false;
-                            P.item[n_items++] = 0x80000000u | (k << 8) | local;
-                            if ((P.heavy_bits >> local) & 1u) { hp.segs.push_back({seg0, n_items - 1, (int)local}); seg0 = n_items; }
-                        }
-                        k++; break;
-                    }
-                    if (nd.right != LUMO_NONE) st.push_back({nd.right, (int)k});
-                    par = (int)k; node += 1; k++;
-                }
-            }
-            if (seg0 < n_items) hp.segs.push_back({seg0, n_items - 1, -1});
-            P.n_nodes = k; P.n_items = n_items;
-            return k == n_nodes && hp.segs.size() + 2 * hp.heavy.size() + 2 <= LUMO_NM_MAX_NODES;
-        };
-        sc->nm_ok = build(sc->nm_obj, 0, S.P.lights_root, 0, S.P.n_objects) && build(sc->nm_lig, S.P.lights_root, S.P.n_tlas_nodes - S.P.lights_root, S.P.n_objects, S.P.n_lights);
-    }
     { const LumoMaterial* mats = (const LumoMaterial*)((const uint8_t*)blob + H.sec[LSEC_MATERIALS].offset);
       for (uint64_t i = 0; i < H.sec[LSEC_MATERIALS].count; i++) if (mats[i].kind < 32) sc->kind_mask |= 1u << mats[i].kind; }
     *out = sc; return LUMO_OK;
@@ -307,95 +340,21 @@ struct Carver {   // carves 256-byte aligned arrays out of one allocation
     uint8_t* base; size_t off = 0;
     template <class T> T* take(size_t n) { T* p = base ? (T*)(base + off) : nullptr; off = (off + n * sizeof(T) + 255) & ~(size_t)255; return p; }
 };
-// ---- node-major traversal (trace_nm.cuh) ------------------------------------------------------------
-struct NmWaveSource {
-    Wave W; uint32_t cur;
-    __device__ __forceinline__ void load(unsigned long long item, Ray& r, double& t_max) const {
-        const uint32_t slot = W.active[item];
-        r.o = d3(W.ox[cur][slot], W.oy[cur][slot], W.oz[cur][slot]); r.d = d3(W.dx[cur][slot], W.dy[cur][slot], W.dz[cur][slot]);
-        t_max = LUMO_INF;
-    }
-};
-struct NmWaveHitSink {
-    Wave W; const LumoMaterial* materials; const LumoObject* objects;
-    __device__ __forceinline__ void store(unsigned long long item, const FlatResult& res) {
-        const uint32_t slot = W.active[item];
-        uint32_t klass = 0;
-        if (res.hit) {
-            W.ht[slot] = res.h.t; W.hb0[slot] = res.h.bary.x; W.hb1[slot] = res.h.bary.y; W.hb2[slot] = res.h.bary.z; W.hobj[slot] = res.h.obj; W.htri[slot] = res.h.tri;
-            const uint32_t kind = materials[objects[res.h.obj].material].kind;
-            if (kind >= LMAT_LAMBERTIAN && kind <= LMAT_MFDIELECTRIC) klass = kind;
-        } else W.hobj[slot] = LUMO_NONE;
-        W.flags[slot] = (W.flags[slot] & 0xFFu) | (klass << PF_CLASS_SHIFT);
-    }
-};
-struct NmShadowSource {
-    Wave W;
-    __device__ __forceinline__ void load(unsigned long long i, Ray& r, double& t_max) const {
-        r.o = d3(W.sox[i], W.soy[i], W.soz[i]); r.d = d3(W.sdx[i], W.sdy[i], W.sdz[i]); t_max = W.stmax[i];
-    }
-};
-struct NmShadowSink {
-    Wave W;
-    __device__ __forceinline__ void store(unsigned long long i, const FlatResult& res) {
-        if (res.hit) return;
-        const uint32_t slot = W.sslot[i]; const uint32_t N = W.n_slots, C = W.shadow_cap;
-        for (int k = 0; k < 4; k++) { const double v = W.sc[(size_t)k * C + i]; if (v != 0.0) atomicAdd(&W.radiance[(size_t)k * N + slot], v); }
-    }
-};
-static int32_t nm_reserve(lumo_ctx* ctx, uint32_t cap) {
-    auto carve = [&](Carver& c, NmRays& R) {
-        R.cap = cap;
-        R.ctx = c.take<double>(14 * (size_t)cap);
-        R.tt = c.take<double>(cap); R.bound = c.take<double>(cap); R.qtmax = c.take<double>(cap);
-        R.idx = c.take<uint32_t>(cap); R.done = c.take<uint32_t>(cap); R.have = c.take<uint32_t>(cap);
-        R.mask = c.take<unsigned long long>(cap);
-        R.ht = c.take<double>(cap); R.hb0 = c.take<double>(cap); R.hb1 = c.take<double>(cap); R.hb2 = c.take<double>(cap); R.hobj = c.take<uint32_t>(cap); R.htri = c.take<uint32_t>(cap);
-        R.queue = c.take<uint32_t>(cap); R.sorted = c.take<uint32_t>(cap);
-        R.counters = c.take<uint32_t>(NM_CNT_TOTAL);
-    };
-    if (ctx->nm_rays.cap >= cap && ctx->nm_mem) return LUMO_OK;
-    NmRays tmp{}; Carver dry{nullptr}; carve(dry, tmp);
-    if (ctx->nm_mem) { cudaFree(ctx->nm_mem); ctx->nm_mem = nullptr; ctx->nm_bytes = 0; ctx->nm_rays = NmRays{}; }
-    CU(cudaMalloc(&ctx->nm_mem, dry.off)); ctx->nm_bytes = dry.off;
-    Carver c{(uint8_t*)ctx->nm_mem}; carve(c, ctx->nm_rays);
-    return LUMO_OK;
-}
-template <bool CLOSEST>
-static void nm_bvh_pass(lumo_scene* sc, const lumo_scene::NmHostPlan& hp, const uint32_t* n_ptr, uint32_t n_cap, cudaStream_t st, unsigned long long& launches) {
-    lumo_ctx* ctx = sc->ctx; const NmRays& R = ctx->nm_rays;
-    const int g128 = (int)std::min<uint64_t>((n_cap + 127) / 128, (uint64_t)ctx->sm_count * 16);
-    const int gp = ctx->sm_count * 8;                                   // persistent, lane-refilled
-    uint32_t qslot = 0;                                                  // one queue counter + cursor per heavy launch (zeroed by setup / begin_lights)
-    for (const auto& sg : hp.segs) {
-        k_nm_segment<CLOSEST><<<g128, 128, 0, st>>>(sc->S, hp.P, R, n_ptr, n_cap, sg.i0, sg.i1, qslot);
-        launches++;
-        if (sg.heavy >= 0) {
-            k_nm_heavy<false, CLOSEST><<<gp, 128, 0, st>>>(sc->S, R, R.queue, qslot, hp.P.obj_base + (uint32_t)sg.heavy, (uint32_t)sg.heavy);
-            launches++; qslot++;
-        }
-    }
-    if (CLOSEST) {
-        if (hp.heavy.empty()) { k_nm_winners<<<g128, 128, 0, st>>>(sc->S, hp.P, R, n_ptr, n_cap, LUMO_NONE, qslot, 1u); launches++; }
-        for (size_t j = 0; j < hp.heavy.size(); j++) {
-            k_nm_winners<<<g128, 128, 0, st>>>(sc->S, hp.P, R, n_ptr, n_cap, hp.heavy[j], qslot, j == 0 ? 1u : 0u);
-            k_nm_heavy<true, true><<<gp, 128, 0, st>>>(sc->S, R, R.sorted, qslot, hp.P.obj_base + hp.heavy[j], hp.heavy[j]);
-            launches += 2; qslot++;
-        }
-    }
-}
-// Scene::hit (CLOSEST) or the occlusion half of Scene::hit_light for a batch described by Source / Sink
-template <bool CLOSEST, class Source, class Sink>
-static int32_t nm_trace(lumo_scene* sc, const uint32_t* n_ptr, uint32_t n_cap, const Source& src, const Sink& sink, unsigned long long* total, cudaStream_t st) {
+// The occlusion half of Scene::hit_light through the occlusion BVH (occlude.cuh): BVH walk -> per-object confirmation by the
+// reference's own traversal -> faithful kernel for whatever is left.  Q.counters must be zero.
+template <class Source, class Sink>
+static int32_t launch_occlusion(lumo_scene* sc, const Source& src, const Sink& sink, const OcclQueues& Q, cudaStream_t st) {
     lumo_ctx* ctx = sc->ctx;
-    int32_t rc = nm_reserve(ctx, n_cap); if (rc != LUMO_OK) return rc;
-    const NmRays& R = ctx->nm_rays;
-    const int g256 = (int)std::min<uint64_t>((n_cap + 255) / 256, (uint64_t)ctx->sm_count * 16);
-    k_nm_setup<Source><<<g256, 256, 0, st>>>(R, n_ptr, n_cap, src);
-    nm_bvh_pass<CLOSEST>(sc, sc->nm_obj, n_ptr, n_cap, st, ctx->launches);
-    k_nm_begin_lights<CLOSEST><<<g256, 256, 0, st>>>(R, n_ptr, n_cap);
-    nm_bvh_pass<CLOSEST>(sc, sc->nm_lig, n_ptr, n_cap, st, ctx->launches);
-    k_nm_finish<CLOSEST, Sink><<<g256, 256, 0, st>>>(R, n_ptr, n_cap, sink, total);
+    const int g1 = ctx->sm_count * 4, g2 = ctx->sm_count * LUMO_WAVE_TRACE_BLOCKS;
+    if (ctx->count_visits) {
+        k_occl_bvh<true><<<g1, 128, 0, st>>>(sc->S, src, sink, Q, ctx->d_ah);
+        k_occl_confirm<true><<<g2, 128, 0, st>>>(sc->S, src, sink, Q, ctx->d_visit + 1, ctx->d_ah);
+        k_occl_fallback<true><<<g2, 128, 0, st>>>(sc->S, src, sink, Q, ctx->d_visit + 1);
+    } else {
+        k_occl_bvh<false><<<g1, 128, 0, st>>>(sc->S, src, sink, Q, nullptr);
+        k_occl_confirm<false><<<g2, 128, 0, st>>>(sc->S, src, sink, Q, nullptr, nullptr);
+        k_occl_fallback<false><<<g2, 128, 0, st>>>(sc->S, src, sink, Q, nullptr);
+    }
     ctx->launches += 3;
     CU(cudaGetLastError());
     return LUMO_OK;
@@ -405,16 +364,25 @@ template <int MODE>
 static int32_t launch_batch(lumo_scene* sc, const double* o_dev, const double* d_dev, const double* tmax_dev, uint64_t n, unsigned long long* next_dev,
                             uint32_t* obj, uint32_t* tri, double* t, double* bary, uint8_t* occ) {
     lumo_ctx* ctx = sc->ctx;
-    CU(cudaMemsetAsync(next_dev, 0, 8, ctx->stream));
-    if (!ctx->count_visits && !ctx->flat && ctx->nm && sc->nm_ok && MODE != 2 && n < 0x7FFFFFFFull) {
-        const uint32_t n32 = (uint32_t)n;
-        CU(cudaMemcpyAsync(ctx->d_n_batch, &n32, 4, cudaMemcpyHostToDevice, ctx->stream));
-        BatchSource src{o_dev, d_dev, tmax_dev};
-        if (MODE == 0) { BatchSink<FQ_CLOSEST> sink{obj, tri, t, bary, occ}; return nm_trace<true>(sc, ctx->d_n_batch, n32, src, sink, nullptr, ctx->stream); }
-        BatchSink<FQ_OCCLUDED> sink{obj, tri, t, bary, occ}; return nm_trace<false>(sc, ctx->d_n_batch, n32, src, sink, nullptr, ctx->stream);
+    if (MODE == 1 && !ctx->occl_faithful) {
+        // queues: confirm (index, object) + fallback (index) per ray of a chunk, 8 counters
+        const uint64_t CH = 1ull << 26;
+        const size_t need = (size_t)std::min<uint64_t>(n, CH) * 12 + 256;
+        if (need > ctx->occl_bytes) {
+            if (ctx->occl_mem) { cudaFree(ctx->occl_mem); ctx->occl_mem = nullptr; ctx->occl_bytes = 0; }
+            CU(cudaMalloc(&ctx->occl_mem, need)); ctx->occl_bytes = need;
+        }
+        for (uint64_t c0 = 0; c0 < n; c0 += CH) {
+            const uint32_t cnt = (uint32_t)std::min<uint64_t>(CH, n - c0);
+            OcclQueues Q; Q.counters = (uint32_t*)ctx->occl_mem; Q.confirm_i = Q.counters + 64; Q.confirm_obj = Q.confirm_i + cnt; Q.fallback_i = Q.confirm_obj + cnt;
+            CU(cudaMemsetAsync(Q.counters, 0, 32, ctx->stream));
+            BatchShadowSource src{o_dev + 3 * c0, d_dev + 3 * c0, tmax_dev + c0, cnt}; BatchShadowSink sink{occ + c0};
+            int32_t rc = launch_occlusion(sc, src, sink, Q, ctx->stream); if (rc != LUMO_OK) return rc;
+        }
+        return LUMO_OK;
     }
+    CU(cudaMemsetAsync(next_dev, 0, 8, ctx->stream));
     if (ctx->count_visits) k_trace_batch<MODE, true><<<trace_grid(ctx), 128, 0, ctx->stream>>>(sc->S, o_dev, d_dev, tmax_dev, n, next_dev, obj, tri, t, bary, occ, ctx->d_visit + (MODE == 0 ? 0 : 1));
-    else if (ctx->flat) k_trace_batch_flat<MODE><<<ctx->sm_count * 4, 128, 0, ctx->stream>>>(sc->S, o_dev, d_dev, tmax_dev, n, next_dev, obj, tri, t, bary, occ);
     else k_trace_batch<MODE, false><<<trace_grid(ctx), 128, 0, ctx->stream>>>(sc->S, o_dev, d_dev, tmax_dev, n, next_dev, obj, tri, t, bary, occ, nullptr);
     ctx->launches++;
     CU(cudaGetLastError());
@@ -498,6 +466,7 @@ static void carve_wave(Wave& W, Carver& c, uint32_t N, uint32_t shadow_cap, uint
     const size_t C = shadow_cap;
     W.sox = c.take<double>(C); W.soy = c.take<double>(C); W.soz = c.take<double>(C); W.sdx = c.take<double>(C); W.sdy = c.take<double>(C); W.sdz = c.take<double>(C);
     W.stmax = c.take<double>(C); W.sc = c.take<double>(4 * C); W.sslot = c.take<uint32_t>(C);
+    W.oq_i = c.take<uint32_t>(C); W.oq_obj = c.take<uint32_t>(C); W.oq_fb = c.take<uint32_t>(C); W.occ_record = c.take<uint8_t>(C);
     W.it = c.take<IterCounters>(1); W.run = c.take<RunCounters>(1); W.qc = c.take<QueueCounters>(1);
     W.tile_delta = c.take<double>(n_tiles); W.tile_delta_next = c.take<double>(n_tiles);
     W.pilot_lum = c.take<double>((size_t)n_tiles * LUMO_PILOT_N); W.pilot_cost = c.take<uint32_t>((size_t)n_tiles * LUMO_PILOT_N);
@@ -512,10 +481,10 @@ static void launch_shade_kind(lumo_scene* sc, const Wave& W, const WaveParams& P
     if (!(sc->kind_mask & (1u << K))) return;
     if (sc->has_textures) {
         k_scatter<K><<<grid, 128, 0, st>>>(sc->S, W, P);
-        if (sc->S.P.n_shadow_rays > 1) k_nee<K, true><<<nee_grid, 128, 0, st>>>(sc->S, W, P); else k_nee<K, false><<<nee_grid, 128, 0, st>>>(sc->S, W, P);
+        k_nee<K><<<nee_grid, 128, 0, st>>>(sc->S, W, P);
     } else {                                         // no LumoTexture record in the scene: the texture-free instantiations (shade.cuh LUMO_K_SOLID)
         k_scatter<K | LUMO_K_SOLID><<<grid, 128, 0, st>>>(sc->S, W, P);
-        if (sc->S.P.n_shadow_rays > 1) k_nee<K | LUMO_K_SOLID, true><<<nee_grid, 128, 0, st>>>(sc->S, W, P); else k_nee<K | LUMO_K_SOLID, false><<<nee_grid, 128, 0, st>>>(sc->S, W, P);
+        k_nee<K | LUMO_K_SOLID><<<nee_grid, 128, 0, st>>>(sc->S, W, P);
     }
     launches += 2;
 }
@@ -528,7 +497,7 @@ static int32_t run_wave(lumo_scene* sc, const Wave& W, WaveParams P, uint64_t& i
     const int tgrid = ctx->sm_count * LUMO_WAVE_TRACE_BLOCKS;   // persistent warps: one grid of resident CTAs
     const int rgrid = (int)std::min<uint64_t>((W.n_slots + 255) / 256, (uint64_t)ctx->sm_count * 16);
     const int sgrid = ctx->sm_count * 16;
-    const int ngrid = (int)std::min<uint64_t>(((uint64_t)W.n_slots * 2 * sc->S.P.n_shadow_rays + 127) / 128, (uint64_t)ctx->sm_count * 32);
+    const int ngrid = (int)std::min<uint64_t>(((uint64_t)W.n_slots + 127) / 128, (uint64_t)ctx->sm_count * 32);
     CU(cudaMemsetAsync(W.flags, 0, (size_t)W.n_slots * 4, st));
     CU(cudaMemsetAsync(&W.run->next_work, 0, 8, st));
     // every slot starts out free: the first k_retire finds all of them in done[1] (no PF_DONE flag -> nothing to film)
@@ -542,8 +511,6 @@ static int32_t run_wave(lumo_scene* sc, const Wave& W, WaveParams P, uint64_t& i
     // a few microseconds).
     const int BATCH = LUMO_ITER_BATCH;
     uint32_t main_iter = 0;
-    const bool use_nm = ctx->nm && sc->nm_ok && !ctx->count_visits && !ctx->flat;
-    uint32_t last_active = W.n_slots;          // live paths at the last host synchronisation (upper bound for the next batch)
     for (;;) {
         for (int b = 0; b < BATCH; b++) {
             cudaEvent_t* ev = ctx->kev + 5 * b;
@@ -552,14 +519,7 @@ static int32_t run_wave(lumo_scene* sc, const Wave& W, WaveParams P, uint64_t& i
             k_retire<<<rgrid, 256, 0, st>>>(sc->S, W, P);
             k_compact<<<rgrid, 256, 0, st>>>(W);
             CU(cudaEventRecord(ev[1], st));
-            const bool nm_now = use_nm && last_active >= LUMO_NM_MIN_RAYS;   // a few dozen small launches: only worth it for full queues
             if (ctx->count_visits) k_wave_trace<true><<<tgrid, 128, 0, st>>>(sc->S, W, P.cur, ctx->d_visit);
-            else if (nm_now) {
-                NmWaveSource src{W, P.cur}; NmWaveHitSink sink{W, sc->S.materials, sc->S.objects};
-                int32_t rc = nm_trace<true>(sc, &W.it->n_active, W.n_slots, src, sink, &W.run->closest, st); if (rc != LUMO_OK) return rc;
-                k_classify<<<rgrid, 256, 0, st>>>(W); ctx->launches++;
-            }
-            else if (ctx->flat) { k_wave_trace_flat<<<ctx->sm_count * 4, 128, 0, st>>>(sc->S, W, P.cur); k_classify<<<rgrid, 256, 0, st>>>(W); ctx->launches++; }
             else k_wave_trace<false><<<tgrid, 128, 0, st>>>(sc->S, W, P.cur, nullptr);
             CU(cudaEventRecord(ev[2], st));
             k_terminal<<<sgrid, 128, 0, st>>>(sc->S, W, P);
@@ -569,17 +529,20 @@ static int32_t run_wave(lumo_scene* sc, const Wave& W, WaveParams P, uint64_t& i
             launch_shade_kind<LMAT_MFCONDUCTOR>(sc, W, P, sgrid, ngrid, st, ctx->launches);
             launch_shade_kind<LMAT_MFDIELECTRIC>(sc, W, P, sgrid, ngrid, st, ctx->launches);
             CU(cudaEventRecord(ev[3], st));
-            if (ctx->count_visits) k_wave_occlude<true><<<tgrid, 128, 0, st>>>(sc->S, W, ctx->d_visit + 1);
-            else if (nm_now) {
-                NmShadowSource src{W}; NmShadowSink sink{W};
-                int32_t rc = nm_trace<false>(sc, &W.it->n_shadow, W.shadow_cap, src, sink, &W.run->occlusion, st); if (rc != LUMO_OK) return rc;
+            if (ctx->occl_faithful) {
+                if (ctx->count_visits) k_wave_occlude<true><<<tgrid, 128, 0, st>>>(sc->S, W, ctx->d_visit + 1, nullptr, nullptr);
+                else k_wave_occlude<false><<<tgrid, 128, 0, st>>>(sc->S, W, nullptr, nullptr, nullptr);
+                ctx->launches++;
+            } else {
+                WaveShadowSource src{W}; WaveShadowSink sink{W, ctx->occl_check ? W.occ_record : nullptr};
+                OcclQueues Q; Q.confirm_i = W.oq_i; Q.confirm_obj = W.oq_obj; Q.fallback_i = W.oq_fb; Q.counters = W.it->occl;
+                int32_t rc = launch_occlusion(sc, src, sink, Q, st); if (rc != LUMO_OK) return rc;
+                if (ctx->occl_check) { k_wave_occlude<false><<<tgrid, 128, 0, st>>>(sc->S, W, nullptr, W.occ_record, ctx->d_ah); ctx->launches++; }
             }
-            else if (ctx->flat) k_wave_occlude_flat<<<ctx->sm_count * 4, 128, 0, st>>>(sc->S, W);
-            else k_wave_occlude<false><<<tgrid, 128, 0, st>>>(sc->S, W, nullptr);
             CU(cudaEventRecord(ev[4], st));
             k_queue_reset<<<1, 1, 0, st>>>(W.qc, P.cur, W.it, P.mode == WM_MAIN ? ctx->d_iter_log : nullptr, main_iter, LUMO_ITER_LOG_CAP);
             if (P.mode == WM_MAIN) main_iter++;
-            ctx->launches += 3; iterations++;
+            ctx->launches += 2; iterations++;
             P.cur ^= 1u;
         }
         CU(cudaMemcpyAsync(&hc->qc, W.qc, sizeof(QueueCounters), cudaMemcpyDeviceToHost, st));
@@ -588,10 +551,6 @@ static int32_t run_wave(lumo_scene* sc, const Wave& W, WaveParams P, uint64_t& i
         CU(cudaGetLastError());
         if (P.mode == WM_MAIN) for (int b = 0; b < BATCH; b++) for (int k = 0; k < 4; k++) {
             float ms = 0; CU(cudaEventElapsedTime(&ms, ctx->kev[5 * b + k], ctx->kev[5 * b + k + 1])); ctx->kernel_ms[k] += ms; ctx->kernel_launches[k]++;
-        }
-        {   // survivors plus what the next k_retire can still refill
-            const unsigned long long remaining = hc->run.next_work < P.total_work ? P.total_work - hc->run.next_work : 0ull;
-            last_active = (uint32_t)std::min<unsigned long long>(W.n_slots, hc->qc.n_active[P.cur] + remaining);
         }
         if (hc->qc.n_active[P.cur] == 0 && hc->qc.n_done[P.cur ^ 1u] == 0) break;   // no survivors and nothing left to retire
     }
@@ -832,9 +791,9 @@ __device__ __noinline__ uint32_t trc_apply(double c, int transfer) {
     double ec;
     if (transfer == 1) {   // rec. 2020
         const double beta = 0.018053968510807, alpha = 1.0 + 5.5 * beta;
-        ec = c <= beta ? 4.5 * c : alpha * pow(c, 0.45) - (alpha - 1.0);
+        ec = c <= beta ? 4.5 * c : alpha * lm_pow(c, 0.45) - (alpha - 1.0);
     } else {
-        ec = c <= 0.0031308 ? 12.92 * c : 1.055 * pow(c, 1.0 / 2.4) - 0.055;
+        ec = c <= 0.0031308 ? 12.92 * c : 1.055 * lm_pow(c, 1.0 / 2.4) - 0.055;
     }
     const double v = ec * 255.0;
     return !(v > 0.0) ? 0u : (v >= 255.0 ? 255u : (uint32_t)v);   // NaN and negatives -> 0, like `as u8`

@@ -4,6 +4,7 @@
 // Every function cites the reference code it restates for the device.
 #pragma once
 #include "trace.cuh"
+#include "../common/lumo_math.h"
 
 namespace lumo_dev {
 
@@ -78,10 +79,10 @@ __device__ __forceinline__ bool is_black(C4 c) { return c.s[0] == 0.0 && c.s[1] 
 __device__ __forceinline__ double mean4(C4 c) { return (((0.0 + c.s[0]) + c.s[1]) + c.s[2] + c.s[3]) / 4.0; }
 
 struct Lam { double l[4]; };
-__device__ __forceinline__ double lam_sample_one(double v) { return 538.0 - 138.888889 * atanh(0.85691062 - 253.819 * v * 0.0072); }   // wavelength.rs:48-51
+__device__ __forceinline__ double lam_sample_one(double v) { return 538.0 - 138.888889 * lm_atanh(0.85691062 - 253.819 * v * 0.0072); }   // wavelength.rs:48-51
 __device__ __forceinline__ double lam_pdf_one(double l) {                                                                       // wavelength.rs:60-66
     if (l < 360.0 || l > 830.0) return 0.0;
-    const double c = cosh(0.0072 * (l - 538.05));
+    const double c = lm_cosh(0.0072 * (l - 538.05));
     return 1.0 / (253.819 * (c * c));
 }
 __device__ __noinline__ Lam lam_sample(double u) {                                                                           // wavelength.rs:35-44
@@ -169,7 +170,7 @@ __device__ __noinline__ C4 texture_albedo(const DevScene& S, uint32_t tex, doubl
             turb = turb + powi(0.5, depth) * fabs(perlin_noise(tab, p));
             p = 2.0 * p;
         }
-        const double scaled = 1.0 - powi(0.5 + 0.5 * sin(60.0 * u + 20.0 * turb), 6);
+        const double scaled = 1.0 - powi(0.5 + 0.5 * lm_sin(60.0 * u + 20.0 * turb), 6);
         return spec4(T->spec, l) * scaled;
     }
     case LTEX_IMAGE: {                                                                                                           // image.rs:184-193
@@ -250,6 +251,8 @@ __device__ __forceinline__ D3 propagate_fp_err(const LumoInstance* I, D3 xo, D3 
 // Rebuilds the reference's `Hit` from (object, triangle, t, barycentrics): the GEO tail of
 // Triangle::_hit (triangle.rs:155-186), Sphere::hit (sphere.rs:62-74), Rectangle::hit's uv override
 // (rectangle.rs:73-85) and Instance::hit's world transform (instance.rs:84-99).
+// UV = false (scenes without a single texture record): a sphere's (u, v) — an atan2 and an acos — is not computed, nothing reads it.
+template <bool UV = true>
 __device__ __noinline__ DevHit reconstruct_hit(const DevScene& S, const Ray& r, const HitRec& rec) {
     const LumoObject o = S.objects[rec.obj];
     const Ray l = to_local<false>(S, o, r, nullptr);
@@ -260,9 +263,11 @@ __device__ __noinline__ DevHit reconstruct_hit(const DevScene& S, const Ray& r, 
         xi = xi * radius / length(xi);
         h.fp_error = gamma_n(5) * vabs(xi);
         const D3 ni = xi / radius;
-        h.u = (atan2(-ni.z, ni.x) + LUMO_PI) / (2.0 * LUMO_PI);
-        h.v = acos(-ni.y) / LUMO_PI;
-        wrap_uv(h.u, h.v);
+        if (UV) {
+            h.u = (lm_atan2(-ni.z, ni.x) + LUMO_PI) / (2.0 * LUMO_PI);
+            h.v = lm_acos(-ni.y) / LUMO_PI;
+            wrap_uv(h.u, h.v);
+        } else { h.u = 0.0; h.v = 0.0; }
         h.p = xi; h.ns = ni; h.ng = ni;
         h.backface = dot(l.d, ni) > 0.0;
     } else {
@@ -335,7 +340,8 @@ __device__ __forceinline__ void square_to_disk(double r0, double r1, double& dx,
     if (ox == 0.0 && oy == 0.0) { dx = 0.0; dy = 0.0; return; }
     double rr, th;
     if (fabs(ox) > fabs(oy)) { rr = ox; th = LUMO_PI * (oy / ox) / 4.0; } else { rr = oy; th = LUMO_PI * (0.5 - (ox / oy) / 4.0); }
-    dx = rr * cos(th); dy = rr * sin(th);
+    double sn, cs; lm_sincos(th, &sn, &cs);
+    dx = rr * cs; dy = rr * sn;
 }
 __device__ __noinline__ D3 square_to_cos_hemisphere(double r0, double r1) {
     double dx, dy; square_to_disk(r0, r1, dx, dy);
@@ -345,7 +351,8 @@ __device__ __forceinline__ D3 square_to_sphere(double r0, double r1) {
     const double z = 1.0 - 2.0 * r1;
     const double rr = sqrt(fmax(1.0 - z * z, 0.0));
     const double phi = 2.0 * LUMO_PI * r0;
-    return d3(rr * cos(phi), rr * sin(phi), z);
+    double sn, cs; lm_sincos(phi, &sn, &cs);
+    return d3(rr * cs, rr * sn, z);
 }
 
 // ---- spherical utils (math/spherical_utils.rs) -----------------------------------------------------
@@ -412,8 +419,9 @@ __device__ __forceinline__ Cx cdivf(Cx a, double b) { if (b == 0.0) return cx(na
 __device__ __forceinline__ Cx cdiv(Cx a, Cx b) { if (b.re == 0.0 && b.im == 0.0) return cx(nan(""), nan("")); return cdivf(cmul(a, cx(b.re, -b.im)), b.re * b.re + b.im * b.im); }
 __device__ __forceinline__ Cx fdivc(double a, Cx b) { if (b.re == 0.0 && b.im == 0.0) return cx(nan(""), nan("")); return cdivf(cx(a * b.re, a * -b.im), b.re * b.re + b.im * b.im); }
 __device__ __forceinline__ Cx csqrt(Cx a) {                                                                                      // complex.rs:38-53
-    const double nr = sqrt(sqrt(a.re * a.re + a.im * a.im)), ar = atan2(a.im, a.re) / 2.0;
-    return cx(nr * cos(ar), nr * sin(ar));
+    const double nr = sqrt(sqrt(a.re * a.re + a.im * a.im)), ar = lm_atan2(a.im, a.re) / 2.0;
+    double sn, cs; lm_sincos(ar, &sn, &cs);
+    return cx(nr * cs, nr * sn);
 }
 __device__ __forceinline__ double fr_complex(D3 wo, D3 wh, double eta_, double k_) {                                             // microfacet.rs:226-241
     const Cx eta = cx(eta_, k_);
@@ -466,10 +474,11 @@ __device__ __noinline__ D3 sample_normal(const Mat& m, D3 wo, double r0, double 
     const D3 v = cross(u, ws);
     const double r = sqrt(r0);
     const double th = 2.0 * LUMO_PI * r1;
-    const double x = r * cos(th);
+    double sn, cs; lm_sincos(th, &sn, &cs);
+    const double x = r * cs;
     const double h = sqrt(fmax(1.0 - x * x, 0.0));
     const double lerp = (1.0 + ws.z) / 2.0;
-    const double y = (1.0 - lerp) * h + lerp * r * sin(th);
+    const double y = (1.0 - lerp) * h + lerp * r * sn;
     D3 wm = d3(x, y, sqrt(fmax(1.0 - x * x - y * y, 0.0)));
     wm = wm.x * u + wm.y * v + wm.z * ws;
     return normalize(d3(m.roughness * wm.x, m.roughness * wm.y, fmax(wm.z, LUMO_EPS)));
@@ -693,7 +702,8 @@ __device__ __forceinline__ D3 base_sample_towards(const DevScene& S, const LumoO
             const double ds = d * cos_t - sqrt(fmax(rr2 - d2 * sin_t * sin_t, 0.0));
             const double cos_a = (d2 + rr2 - ds * ds) / (2.0 * d * radius);
             const double sin_a = sqrt(fmax(1.0 - cos_a * cos_a, 0.0));
-            const D3 ngl = d3(cos(phi) * sin_a, sin(phi) * sin_a, cos_a);
+            double sn, cs; lm_sincos(phi, &sn, &cs);
+            const D3 ngl = d3(cs * sin_a, sn * sin_a, cos_a);
             xi = normalize(to_world(uvw, -ngl)) * radius;
         }
         return normalize(xi - xo);
@@ -755,12 +765,13 @@ __device__ __noinline__ DevHit light_sample_on(const DevScene& S, const LumoObje
     return h;
 }
 // light.hit(r, 0, INF) for one light object: Object::hit + Hit reconstruction
+template <bool UV = true>
 __device__ __noinline__ bool light_hit(const DevScene& S, uint32_t obj_index, const Ray& r, DevHit& out) {
     HitRec rec;
     RayCtx w; make_ctx(r, w);
     if (!object_hit<false, LUMO_LIGHT_KD_STACK>(S, S.objects[obj_index], w, 0.0, LUMO_INF, rec, nullptr)) return false;
     rec.obj = obj_index;
-    out = reconstruct_hit(S, r, rec);
+    out = reconstruct_hit<UV>(S, r, rec);
     return true;
 }
 // BVH::sample_light (bvh.rs:67-77): alias table
@@ -801,7 +812,7 @@ __device__ __noinline__ Ray camera_generate_ray(const LumoCamera& C, double rx, 
 }
 
 // ---- film (film/tile.rs:65-111, filter.rs:82-102, tone_mapping.rs:38-63) -----------------------------
-__device__ __forceinline__ double gauss(double x, double sigma) { return exp(-powi(x, 2) / (2.0 * sigma * sigma)) / sqrt(fmax(2.0 * LUMO_PI * sigma * sigma, 0.0)); }
+__device__ __forceinline__ double gauss(double x, double sigma) { return lm_exp(-powi(x, 2) / (2.0 * sigma * sigma)) / sqrt(fmax(2.0 * LUMO_PI * sigma * sigma, 0.0)); }
 __device__ __forceinline__ double mitch(double x, double b, double c) {
     x = fabs(x);
     double p = 0.0;

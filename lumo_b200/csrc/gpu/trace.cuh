@@ -26,6 +26,7 @@ struct DevScene {
     const LumoRect* rects; const LumoSphere* spheres;
     const LumoMaterial* materials; const double* tables; const LumoLight* lights;
     const LumoTexture* textures; const float* tex_pixels; const double* tex_f64;
+    const LumoAhNode* ah_nodes; const LumoAhPrim* ah_prims; const uint32_t* obj_path_off; const uint32_t* obj_path;   // occlude.cuh
     LumoSceneParams P;
 };
 
@@ -163,6 +164,12 @@ struct KdStackEntry { uint32_t node; double t_start, t_end; };
 #endif
 #ifndef LUMO_WAVE_KD_ROUND
 #define LUMO_WAVE_KD_ROUND 2
+#endif
+#ifndef LUMO_WAVE_TRACE_BLOCKS
+// Resident CTAs per SM the wave traversal kernels are compiled for (and their persistent grid).  Same-box sweep on B200,
+// trace + occlusion ms for bunny 4 spp / dragon 2 spp: 4 CTAs (128 regs) 39.5 / 72.4, 6: 33.8 / 62.4, 8 (64 regs): 32.4 / 57.9,
+// 10 (48 regs): 34.0 / 60.8, 12: 37.3 / 66.4, 16 (32 regs): 51.9 / 92.7 — latency-bound, so occupancy wins until spills take over.
+#define LUMO_WAVE_TRACE_BLOCKS 8
 #endif
 template <bool GEO, bool CNT, int STACK = 64, int ROUND = LUMO_KD_ROUND>
 __device__ __forceinline__ bool kd_hit(const DevScene& S, const LumoKdTree* tree, const RayCtx& ctx, double t_min, double t_max,

@@ -17,8 +17,7 @@
 // count.
 #pragma once
 #include "shade.cuh"
-#include "trace_flat.cuh"
-#include "trace_nm.cuh"
+#include "occlude.cuh"
 #include <cooperative_groups.h>
 #include <cstdio>
 
@@ -35,6 +34,7 @@ enum { WM_MAIN = 0, WM_PILOT = 1 };
 struct IterCounters {   // zeroed before every iteration
     uint32_t n_shadow, trace_next, occl_next, n_active;
     uint32_t n_class[LUMO_N_CLASSES], pad[3];
+    uint32_t occl[8];   // OcclQueues::counters of the occlusion-BVH kernels (occlude.cuh)
 };
 // Counters that live across iterations (double-buffered by the parity of the iteration): done[p] = slots whose
 // path ended in an iteration of parity p, retired into the film (and refilled) at the start of the next one;
@@ -63,6 +63,7 @@ struct Wave {
     uint32_t* cls[LUMO_N_CLASSES];       // per-class shade queues (slot indices)
     // shadow queue (SoA)
     double *sox, *soy, *soz, *sdx, *sdy, *sdz, *stmax, *sc; uint32_t* sslot;
+    uint32_t *oq_i, *oq_obj, *oq_fb; uint8_t* occ_record;   // occlusion-BVH pipeline: confirm queue, fallback queue; verdicts (LUMO_OCCLUDE_CHECK only)
     IterCounters* it; RunCounters* run; QueueCounters* qc;
     // film + RR thresholds
     double *pixels, *splats, *tile_delta, *tile_delta_next;
@@ -203,12 +204,6 @@ __global__ void __launch_bounds__(256) k_compact(const __grid_constant__ Wave W)
 }
 
 // ---- trace: Scene::hit over the active queue, then binning by what the shading stage has to do --------
-#ifndef LUMO_WAVE_TRACE_BLOCKS
-// Resident CTAs per SM the wave traversal kernels are compiled for (and their persistent grid).  Same-box sweep on B200,
-// trace + occlusion ms for bunny 4 spp / dragon 2 spp: 4 CTAs (128 regs) 39.5 / 72.4, 6: 33.8 / 62.4, 8 (64 regs): 32.4 / 57.9,
-// 10 (48 regs): 34.0 / 60.8, 12: 37.3 / 66.4, 16 (32 regs): 51.9 / 92.7 — latency-bound, so occupancy wins until spills take over.
-#define LUMO_WAVE_TRACE_BLOCKS 8
-#endif
 template <bool CNT>
 __global__ void __launch_bounds__(128, LUMO_WAVE_TRACE_BLOCKS) k_wave_trace(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, uint32_t cur, Counters* gc) {
     const uint32_t lane = threadIdx.x & 31u;
@@ -250,11 +245,13 @@ __global__ void __launch_bounds__(128, LUMO_WAVE_TRACE_BLOCKS) k_wave_trace(cons
 
 // ---- occlude: the occlusion half of Scene::hit_light over the shadow queue ------------------------
 template <bool CNT>
-__global__ void __launch_bounds__(128, LUMO_WAVE_TRACE_BLOCKS) k_wave_occlude(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, Counters* gc) {
+__global__ void __launch_bounds__(128, LUMO_WAVE_TRACE_BLOCKS) k_wave_occlude(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, Counters* gc,
+                                                                              const uint8_t* expect, AhCounters* ah) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t n = min(W.it->n_shadow, W.shadow_cap);
     const uint32_t N = W.n_slots, C = W.shadow_cap;
     Counters cnt = {0, 0, 0, 0, 0, 0};
+    unsigned long long mismatches = 0;
     for (;;) {
         uint32_t base = 0;
         if (lane == 0) base = atomicAdd(&W.it->occl_next, 32u);
@@ -263,7 +260,9 @@ __global__ void __launch_bounds__(128, LUMO_WAVE_TRACE_BLOCKS) k_wave_occlude(co
         const uint32_t i = base + lane;
         if (i < n) {
             Ray r; r.o = d3(W.sox[i], W.soy[i], W.soz[i]); r.d = d3(W.sdx[i], W.sdy[i], W.sdz[i]);
-            if (!scene_occluded<CNT, LUMO_WAVE_KD_ROUND>(S, r, W.stmax[i], &cnt)) {
+            const bool occluded = scene_occluded<CNT, LUMO_WAVE_KD_ROUND>(S, r, W.stmax[i], &cnt);
+            if (expect && (expect[i] != 0) != occluded) mismatches++;       // LUMO_OCCLUDE_CHECK: the occlusion BVH's verdict for the same ray
+            if (!occluded) {
                 const uint32_t slot = W.sslot[i];
                 for (int k = 0; k < 4; k++) { const double v = W.sc[(size_t)k * C + i]; if (v != 0.0) atomicAdd(&W.radiance[(size_t)k * N + slot], v); }
             }
@@ -271,99 +270,39 @@ __global__ void __launch_bounds__(128, LUMO_WAVE_TRACE_BLOCKS) k_wave_occlude(co
     }
     if (lane == 0 && threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(&W.run->occlusion, (unsigned long long)n);
     if (CNT) { atomicAdd(&gc->tlas, cnt.tlas); atomicAdd(&gc->inst, cnt.inst); atomicAdd(&gc->kd, cnt.kd); atomicAdd(&gc->leaf, cnt.leaf); atomicAdd(&gc->tri, cnt.tri); atomicAdd(&gc->sphere, cnt.sphere); }
+    if (expect && mismatches) atomicAdd(&ah->mismatches, mismatches);
 }
-
-// ---- lane-refilled traversal kernels (trace_flat.cuh) ------------------------------------------------
-struct WaveRaySource {
-    const Wave* W; uint32_t cur;
-    __device__ __forceinline__ void load(unsigned long long item, Ray& r, double& t_max) const {
-        const uint32_t slot = W->active[item];
-        r.o = d3(W->ox[cur][slot], W->oy[cur][slot], W->oz[cur][slot]); r.d = d3(W->dx[cur][slot], W->dy[cur][slot], W->dz[cur][slot]);
-        t_max = LUMO_INF;
+// the shadow queue as a ray source / verdict sink of the occlusion-BVH kernels (occlude.cuh)
+struct WaveShadowSource {
+    Wave W;
+    __device__ __forceinline__ uint32_t n() const { return min(W.it->n_shadow, W.shadow_cap); }
+    __device__ __forceinline__ void load(uint32_t i, Ray& r, double& t_max) const {
+        r.o = d3(W.sox[i], W.soy[i], W.soz[i]); r.d = d3(W.sdx[i], W.sdy[i], W.sdz[i]); t_max = W.stmax[i];
     }
 };
-#define PF_CLASS_SHIFT 8u   /* flags bits 8..10: shade class decided by the trace kernel (0 terminal, 1..4 material kind) */
-struct WaveHitSink {
-    const DevScene* S; const Wave* W;
-    __device__ __forceinline__ void store(unsigned long long item, const FlatResult& res) {
-        const uint32_t slot = W->active[item];
-        uint32_t klass = 0;
-        if (res.hit) {
-            W->ht[slot] = res.h.t; W->hb0[slot] = res.h.bary.x; W->hb1[slot] = res.h.bary.y; W->hb2[slot] = res.h.bary.z; W->hobj[slot] = res.h.obj; W->htri[slot] = res.h.tri;
-            const uint32_t kind = S->materials[S->objects[res.h.obj].material].kind;
-            if (kind >= LMAT_LAMBERTIAN && kind <= LMAT_MFDIELECTRIC) klass = kind;
-        } else W->hobj[slot] = LUMO_NONE;
-        W->flags[slot] = (W->flags[slot] & 0xFFu) | (klass << PF_CLASS_SHIFT);
+struct WaveShadowSink {
+    Wave W; uint8_t* record;     // record != nullptr (check mode): only note the verdict; the faithful kernel that follows adds the contributions
+    __device__ __forceinline__ void verdict(uint32_t i, bool occluded) const {
+        if (record) { record[i] = occluded ? 1 : 0; return; }
+        if (occluded) return;
+        const uint32_t slot = W.sslot[i]; const uint32_t N = W.n_slots, C = W.shadow_cap;
+        for (int k = 0; k < 4; k++) { const double v = W.sc[(size_t)k * C + i]; if (v != 0.0) atomicAdd(&W.radiance[(size_t)k * N + slot], v); }
+    }
+    __device__ __forceinline__ void done(uint32_t n) const { if (!record) atomicAdd(&W.run->occlusion, (unsigned long long)n); }
+};
+// caller-supplied ray batches (lumo_gpu_trace_any)
+struct BatchShadowSource {
+    const double *o, *d, *t_max; uint32_t count;
+    __device__ __forceinline__ uint32_t n() const { return count; }
+    __device__ __forceinline__ void load(uint32_t i, Ray& r, double& tm) const {
+        r.o = d3(o[3 * (size_t)i], o[3 * (size_t)i + 1], o[3 * (size_t)i + 2]); r.d = d3(d[3 * (size_t)i], d[3 * (size_t)i + 1], d[3 * (size_t)i + 2]); tm = t_max[i];
     }
 };
-__global__ void __launch_bounds__(128, 4) k_wave_trace_flat(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, uint32_t cur) {
-    const uint32_t n = W.it->n_active;
-    WaveRaySource src{&W, cur}; WaveHitSink sink{&S, &W};
-    flat_trace<FQ_CLOSEST>(S, n, nullptr, &W.it->trace_next, src, sink);
-    if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(&W.run->closest, (unsigned long long)n);
-}
-// shade queues in active-queue (slot) order, so that the shade kernels read path state coalesced
-__global__ void __launch_bounds__(256) k_classify(const __grid_constant__ Wave W) {
-    const uint32_t n = W.it->n_active, lane = threadIdx.x & 31u;
-    const uint32_t n_pad = (n + 31u) & ~31u;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x) {
-        uint32_t slot = 0, klass = LUMO_N_CLASSES;
-        if (i < n) { slot = W.active[i]; klass = (W.flags[slot] >> PF_CLASS_SHIFT) & 7u; }
-#pragma unroll
-        for (uint32_t c = 0; c < LUMO_N_CLASSES; c++) {
-            const uint32_t m = __ballot_sync(0xFFFFFFFFu, klass == c);
-            if (m) {
-                uint32_t b = 0;
-                if (lane == (uint32_t)(__ffs(m) - 1)) b = atomicAdd(&W.it->n_class[c], (uint32_t)__popc(m));
-                b = __shfl_sync(0xFFFFFFFFu, b, __ffs(m) - 1);
-                if (klass == c) W.cls[c][b + __popc(m & ((1u << lane) - 1u))] = slot;
-            }
-        }
-    }
-}
-struct ShadowRaySource {
-    const Wave* W;
-    __device__ __forceinline__ void load(unsigned long long i, Ray& r, double& t_max) const {
-        r.o = d3(W->sox[i], W->soy[i], W->soz[i]); r.d = d3(W->sdx[i], W->sdy[i], W->sdz[i]); t_max = W->stmax[i];
-    }
+struct BatchShadowSink {
+    uint8_t* occ;
+    __device__ __forceinline__ void verdict(uint32_t i, bool occluded) const { occ[i] = occluded ? 1 : 0; }
+    __device__ __forceinline__ void done(uint32_t) const {}
 };
-struct ShadowSink {
-    const Wave* W;
-    __device__ __forceinline__ void store(unsigned long long i, const FlatResult& res) {
-        if (res.hit) return;
-        const uint32_t slot = W->sslot[i]; const uint32_t N = W->n_slots, C = W->shadow_cap;
-        for (int k = 0; k < 4; k++) { const double v = W->sc[(size_t)k * C + i]; if (v != 0.0) atomicAdd(&W->radiance[(size_t)k * N + slot], v); }
-    }
-};
-__global__ void __launch_bounds__(128, 4) k_wave_occlude_flat(const __grid_constant__ DevScene S, const __grid_constant__ Wave W) {
-    const uint32_t n = min(W.it->n_shadow, W.shadow_cap);
-    ShadowRaySource src{&W}; ShadowSink sink{&W};
-    flat_trace<FQ_OCCLUDED>(S, n, nullptr, &W.it->occl_next, src, sink);
-    if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(&W.run->occlusion, (unsigned long long)n);
-}
-// C-ABI ray batches through the same machine
-struct BatchSource {
-    const double *o, *d, *t_max;
-    __device__ __forceinline__ void load(unsigned long long i, Ray& r, double& tm) const {
-        r.o = d3(o[3 * i], o[3 * i + 1], o[3 * i + 2]); r.d = d3(d[3 * i], d[3 * i + 1], d[3 * i + 2]); tm = t_max ? t_max[i] : LUMO_INF;
-    }
-};
-template <int Q> struct BatchSink {
-    uint32_t *obj, *tri; double *t, *bary; uint8_t* occ;
-    __device__ __forceinline__ void store(unsigned long long i, const FlatResult& res) {
-        if (Q == FQ_CLOSEST) {
-            if (res.hit) { obj[i] = res.h.obj; tri[i] = res.h.tri; t[i] = res.h.t; bary[2 * i] = res.h.bary.x; bary[2 * i + 1] = res.h.bary.y; }
-            else { obj[i] = LUMO_NONE; tri[i] = LUMO_NONE; t[i] = LUMO_INF; bary[2 * i] = 0.0; bary[2 * i + 1] = 0.0; }
-        } else if (Q == FQ_OCCLUDED) occ[i] = res.hit ? 1 : 0;
-        else t[i] = res.t;
-    }
-};
-template <int Q>
-__global__ void __launch_bounds__(128, 4) k_trace_batch_flat(const __grid_constant__ DevScene S, const double* __restrict__ o, const double* __restrict__ d, const double* __restrict__ t_max,
-                                                             unsigned long long n, unsigned long long* next, uint32_t* obj, uint32_t* tri, double* t, double* bary, uint8_t* occ) {
-    BatchSource src{o, d, t_max}; BatchSink<Q> sink{obj, tri, t, bary, occ};
-    flat_trace<Q>(S, n, next, nullptr, src, sink);
-}
 
 // ---- shade ------------------------------------------------------------------------------------------
 // The shading stage of one iteration is three kinds of kernels over the per-class queues:
@@ -489,72 +428,70 @@ __device__ __forceinline__ C4 mis_sample(const DevScene& S, const Mat& m, const 
 }
 
 // integrator.rs:89-137.  A shadow sample has a light-sampled term (A) and a BSDF-sampled term (B), the latter almost
-// always ending at "the sampled direction misses the light".  Scenes with one shadow sample per bounce (<= 3 lights) run
-// one thread per path doing A then B (all lanes busy in A).  Scenes with several (n_shadow = log2 #lights) run one thread
-// per term, laid out so that every lane of a warp evaluates the same term index for 32 consecutive queue entries.
-template <int K, bool SPLIT>
+// always ending at "the sampled direction misses the light".  One thread per path: the hit reconstruction, the shading
+// frame and the path state are set up once and the thread then runs the n_shadow_rays samples of this bounce (1 for up to
+// 3 lights, log2 #lights beyond: 12 for a street with 4097 lights) one after the other, A then B.  (Round 1 ran one thread
+// per MIS term for n_shadow_rays > 1, which repeated the set-up 24 times per bounce.)
+template <int K>
 __global__ void __launch_bounds__(128, LUMO_NEE_BLOCKS) k_nee(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P) {
     const uint32_t N = W.n_slots, nq = W.it->n_class[K & 7], cur = P.cur;
     const uint32_t ns = S.P.n_shadow_rays;
-    const uint32_t per = SPLIT ? 2u * ns : ns;
-    const unsigned long long padded = (unsigned long long)((nq + 31u) / 32u) * 32ull * per;
-    for (unsigned long long it = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; it < padded; it += (unsigned long long)gridDim.x * blockDim.x) {
+    const uint32_t n_pad = (nq + 31u) & ~31u;
+    for (uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x; qi < n_pad; qi += gridDim.x * blockDim.x) {
         __syncwarp();                                 // a lane whose item ended early waits here instead of running ahead into its next one
-        const unsigned long long grp = it / (32ull * per);
-        const uint32_t j = (uint32_t)((it / 32ull) % per);
-        const uint32_t qi = (uint32_t)(grp * 32ull + (it % 32ull));
-        const uint32_t i = SPLIT ? j >> 1 : j;
-        if (qi >= nq) continue;
-        const uint32_t slot = W.cls[K & 7][qi];
-        if (!(W.flags[slot] & PF_NEE)) continue;
-        Ray ro; HitRec rec; load_path(W, cur, slot, ro, rec);
-        const DevHit ho = reconstruct_hit(S, ro, rec);
-        const Mat& m = S.materials[ho.material];
-        const Onb uvw = shading_onb<K>(S, m, ho);
-        const uint32_t pixel = W.pixel[slot];
-        Lam lam; for (int k = 0; k < 4; k++) lam.l[k] = W.lam[(size_t)k * N + slot];   // already terminated by k_scatter if dispersive
-        const C4 gathered = load_c4(W.gathered[cur], N, slot);
-        const D3 wo = -ro.d;
-        const bool dbg = pixel == P.debug_pixel && P.mode == WM_MAIN;
-        // draws of this bounce: 3 for the scatter sample, then 6 per shadow sample: light pick, light point (2), BSDF sample (3)
-        const uint32_t d0 = W.draws[cur][slot] + 3u + 6u * i;
-        Rng rng = rng_make(P.seed, pixel, W.sample[slot], 0u, d0);
-        const uint32_t li = sample_light(S, rng_float(rng));
-        const double pdf_light = S.lights[li].pdf;
-        const uint32_t lobj = S.P.n_objects + li;
-        const LumoObject lo = S.objects[lobj];
-        auto do_term = [&](int term) {
-            D3 wi;
-            if (term == 0) {
-                const double r0 = rng_float(rng), r1 = rng_float(rng);
-                wi = light_sample_towards(S, lo, ho.p, r0, r1);
-            } else {
-                if (SPLIT) rng = rng_make(P.seed, pixel, W.sample[slot], 0u, d0 + 3u);
-                const double ru = rng_float(rng), r0 = rng_float(rng), r1 = rng_float(rng);
-                Lam l2 = lam;
-                if (!bsdf_sample<K>(S, m, uvw, wo, ho, l2, ru, r0, r1, wi)) return;
-            }
-            // mis_sample returns black when either pdf is zero (integrator.rs:150-152) whatever the light test says.  For the
-            // reflection-only BxDFs the pdf starts with two sign tests (bsdf.rs:88-90, bxdf.rs:136-139, scatter.rs:14-17):
-            // a light-sampled direction below the surface stops here, before any light or microfacet arithmetic.
-            // (measured: worth it for the one-thread-per-path form only; with one thread per term the early exits just thin the warps)
-            if (!SPLIT && (K & 7) != LMAT_MFDIELECTRIC && term == 0) {
-                if (!is_reflection(wo, wi, ho.ng)) return;
-                if (!same_hemisphere(to_local(uvw, wo), to_local(uvw, wi))) return;
-            }
-            const Ray ri = hit_generate_ray(ho, wi);
-            DevHit hi;
-            if (!light_hit(S, lobj, ri, hi)) return;
-            const double p_lig = light_sample_towards_pdf(S, lo, ri, hi.p, hi.ng);
-            const double p_sct = bsdf_pdf<K>(S, m, uvw, wo, wi, ho, lam, false);
-            const C4 c = mis_sample<K>(S, m, uvw, wo, wi, ho, hi, lam, term == 0, p_lig, p_sct);
-            if (dbg) printf("  [gpu] %c vis t=%.17g p_lig=%.17g p_sct=%.17g c0=%.17g\n", term ? 'B' : 'A', hi.t, p_lig, p_sct, c.s[0]);
-            if (!is_black(c)) push_shadow(W, slot, ri, hi.t - LUMO_EPS, gathered * (c / pdf_light) / (double)ns);
-        };
-        if (SPLIT) do_term((int)(j & 1u));
-        else {
+        uint32_t slot = 0;
+        bool on = qi < nq;
+        if (on) { slot = W.cls[K & 7][qi]; on = (W.flags[slot] & PF_NEE) != 0u; }
+        if (!__any_sync(0xFFFFFFFFu, on)) continue;
+        Ray ro; HitRec rec; DevHit ho; Onb uvw; Lam lam; C4 gathered; D3 wo; uint32_t pixel = 0, sample = 0, draws = 0;
+        if (on) {
+            load_path(W, cur, slot, ro, rec);
+            ho = reconstruct_hit<LUMO_TEX(K)>(S, ro, rec);
+            uvw = shading_onb<K>(S, S.materials[ho.material], ho);
+            pixel = W.pixel[slot]; sample = W.sample[slot]; draws = W.draws[cur][slot];
+            for (int k = 0; k < 4; k++) lam.l[k] = W.lam[(size_t)k * N + slot];   // already terminated by k_scatter if dispersive
+            gathered = load_c4(W.gathered[cur], N, slot);
+            wo = -ro.d;
+        }
+        const bool dbg = on && pixel == P.debug_pixel && P.mode == WM_MAIN;
 #pragma unroll 1
-            for (int term = 0; term < 2; term++) do_term(term);
+        for (uint32_t i = 0; i < ns; i++) {
+            __syncwarp();                             // the lanes of a warp start every shadow sample together
+            if (!on) continue;
+            const Mat& m = S.materials[ho.material];
+            // draws of this bounce: 3 for the scatter sample, then 6 per shadow sample: light pick, light point (2), BSDF sample (3)
+            Rng rng = rng_make(P.seed, pixel, sample, 0u, draws + 3u + 6u * i);
+            const uint32_t li = sample_light(S, rng_float(rng));
+            const double pdf_light = S.lights[li].pdf;
+            const uint32_t lobj = S.P.n_objects + li;
+            const LumoObject lo = S.objects[lobj];
+#pragma unroll 1
+            for (int term = 0; term < 2; term++) {
+                D3 wi;
+                if (term == 0) {
+                    const double r0 = rng_float(rng), r1 = rng_float(rng);
+                    wi = light_sample_towards(S, lo, ho.p, r0, r1);
+                    // mis_sample returns black when either pdf is zero (integrator.rs:150-152) whatever the light test says.  For the
+                    // reflection-only BxDFs the pdf starts with two sign tests (bsdf.rs:88-90, bxdf.rs:136-139, scatter.rs:14-17):
+                    // a light-sampled direction below the surface stops here, before any light or microfacet arithmetic.
+                    if ((K & 7) != LMAT_MFDIELECTRIC) {
+                        if (!is_reflection(wo, wi, ho.ng)) continue;
+                        if (!same_hemisphere(to_local(uvw, wo), to_local(uvw, wi))) continue;
+                    }
+                } else {
+                    const double ru = rng_float(rng), r0 = rng_float(rng), r1 = rng_float(rng);
+                    Lam l2 = lam;
+                    if (!bsdf_sample<K>(S, m, uvw, wo, ho, l2, ru, r0, r1, wi)) continue;
+                }
+                const Ray ri = hit_generate_ray(ho, wi);
+                DevHit hi;
+                if (!light_hit<LUMO_TEX(K)>(S, lobj, ri, hi)) continue;
+                const double p_lig = light_sample_towards_pdf(S, lo, ri, hi.p, hi.ng);
+                const double p_sct = bsdf_pdf<K>(S, m, uvw, wo, wi, ho, lam, false);
+                const C4 c = mis_sample<K>(S, m, uvw, wo, wi, ho, hi, lam, term == 0, p_lig, p_sct);
+                if (dbg) printf("  [gpu] %c vis t=%.17g p_lig=%.17g p_sct=%.17g c0=%.17g\n", term ? 'B' : 'A', hi.t, p_lig, p_sct, c.s[0]);
+                if (!is_black(c)) push_shadow(W, slot, ri, hi.t - LUMO_EPS, gathered * (c / pdf_light) / (double)ns);
+            }
         }
     }
 }

@@ -11,6 +11,8 @@
 #include "host_math.h"
 #include "spectra_data.h"
 #include "../common/scene_blob.h"
+#include "../common/lumo_math.h"
+#include "ah_bvh.h"
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -61,10 +63,10 @@ static double spectrum_sample(const float* c, double lambda) {                  
     float sg = 0.5f + x / (2.0f * std::sqrt(1.0f + x * x));
     return (double)(c[3] * sg);
 }
-static double lambda_sample_one(double u) { return 538.0 - 138.888889 * std::atanh(0.85691062 - 253.819 * u * 0.0072); }   // wavelength.rs:48-51
+static double lambda_sample_one(double u) { return 538.0 - 138.888889 * lm_atanh(0.85691062 - 253.819 * u * 0.0072); }   // wavelength.rs:48-51
 static double lambda_pdf_one(double l) {                                        // wavelength.rs:60-66
     if (l < 360.0 || l > 830.0) return 0.0;
-    double c = std::cosh(0.0072 * (l - 538.05));
+    double c = lm_cosh(0.0072 * (l - 538.05));
     return 1.0 / (253.819 * (c * c));
 }
 static const double* illuminant(int id) {
@@ -443,7 +445,7 @@ static void fill_camera(LumoCamera& C, LumoFilm& F, Cursor& r) {
     M3 wb = matmul3(matmul3(l2x, dg), x2l);
     std::memcpy(F.wb, wb.a, 72);
     F.filter_kind = (uint32_t)fk; F.filter_r = fr; F.filter_p = fp;
-    F.filter_gr = std::exp(-(fr * fr) / (2.0 * fp * fp)) / std::sqrt(std::fmax(2.0 * kPi * fp * fp, 0.0));   // filter.rs:118-123
+    F.filter_gr = lm_exp(-(fr * fr) / (2.0 * fp * fp)) / std::sqrt(std::fmax(2.0 * kPi * fp * fp, 0.0));   // filter.rs:118-123
     F.r_disc = (uint32_t)sat_u64(std::ceil(fr - 0.5)); F.color_space = (uint32_t)cs; F.pad = 0;
 }
 
@@ -464,7 +466,7 @@ static uint64_t add_perlin(std::vector<double>& pool, uint64_t seed) {
         const double z = 1.0 - 2.0 * ry;                                                        // rng/maps.rs:49-55
         const double rr = std::sqrt(std::fmax(1.0 - z * z, 0.0));
         const double phi = 2.0 * kPi * rx;
-        pool.push_back(rr * std::cos(phi)); pool.push_back(rr * std::sin(phi)); pool.push_back(z);
+        pool.push_back(rr * lm_cos(phi)); pool.push_back(rr * lm_sin(phi)); pool.push_back(z);
     }
     for (int d = 0; d < 3; d++) {
         uint64_t perm[256];
@@ -746,6 +748,60 @@ static bool run(const uint8_t* data, uint64_t len, std::vector<uint8_t>& out) {
     std::vector<LumoObject> all_objects = B.objects;
     all_objects.insert(all_objects.end(), B.light_objects.begin(), B.light_objects.end());
 
+    // ---- order-free occlusion structure (ah_bvh.h): every primitive of both object lists, in world space ------------
+    AhBuilder ah;
+    {
+        auto world_vertex = [&](const double* v, int32_t inst) {
+            if (inst < 0) return v3(v[0], v[1], v[2]);
+            const double* m = B.instances[(size_t)inst].m;
+            return v3(m[0] * v[0] + m[1] * v[1] + m[2] * v[2] + m[3], m[4] * v[0] + m[5] * v[1] + m[6] * v[2] + m[7], m[8] * v[0] + m[9] * v[1] + m[10] * v[2] + m[11]);
+        };
+        auto add_tri = [&](uint32_t ti, uint32_t g, int32_t inst) {
+            const LumoTriVerts& T = B.tri_verts[ti];
+            const V3 a = world_vertex(T.a, inst), b = world_vertex(T.b, inst), c = world_vertex(T.c, inst);
+            Box bb = {vmin(vmin(a, b), c), vmax(vmax(a, b), c)};
+            ah.add(bb, ti, g | (inst >= 0 ? LUMO_AH_INSTANCED : 0u));
+        };
+        for (size_t g = 0; g < all_objects.size(); g++) {
+            const LumoObject& o = all_objects[g];
+            if (o.kind == LOBJ_KD || o.kind == LOBJ_RECT) {
+                const LumoKdTree& T = B.kd_trees[o.geom];
+                for (uint32_t k = 0; k < T.n_tris; k++) add_tri(T.tri_base + k, (uint32_t)g, o.inst);
+            } else if (o.kind == LOBJ_TRI) add_tri(o.geom, (uint32_t)g, o.inst);
+            else {   // sphere: the object's own world box (instance.rs:107-128 / sphere.rs bounding box)
+                const Box& wb = g < B.objects.size() ? B.object_boxes[g] : B.light_boxes[g - B.objects.size()];
+                ah.add(wb, LUMO_AH_SPHERE | o.geom, (uint32_t)g | (o.inst >= 0 ? LUMO_AH_INSTANCED : 0u));
+            }
+        }
+        if (ah.prims.size() >= (1u << 27)) { g_err = "too many primitives for the occlusion BVH (2^27)"; return false; }
+        ah.build_binary(); ah.collapse();
+    }
+    // per object: its chain of object-BVH nodes, root first (the confirming traversal re-runs the reference's box tests on it)
+    std::vector<uint32_t> path_off(all_objects.size() + 1, 0), path_nodes;
+    {
+        std::vector<std::vector<uint32_t>> paths(all_objects.size());
+        auto walk = [&](uint32_t root, uint32_t n_nodes, uint32_t obj_base) {
+            if (n_nodes == 0) return;
+            struct Fr { uint32_t node; std::vector<uint32_t> chain; };
+            std::vector<Fr> st; st.push_back({0u, {}});
+            while (!st.empty()) {
+                Fr f = std::move(st.back()); st.pop_back();
+                for (;;) {
+                    f.chain.push_back(root + f.node);
+                    const LumoTlasNode& nd = B.tlas[root + f.node];
+                    if (nd.count > 0) { for (uint32_t k = 0; k < nd.count; k++) paths[obj_base + B.tlas_leaf[nd.first + k]] = f.chain; break; }
+                    if (nd.right != LUMO_NONE) st.push_back({nd.right, f.chain});
+                    f.node += 1;
+                    if (f.node >= n_nodes) break;
+                }
+            }
+        };
+        walk(0, light_root, 0);
+        walk(light_root, (uint32_t)B.tlas.size() - light_root, (uint32_t)B.objects.size());
+        for (size_t g = 0; g < all_objects.size(); g++) { path_off[g] = (uint32_t)path_nodes.size(); path_nodes.insert(path_nodes.end(), paths[g].begin(), paths[g].end()); }
+        path_off[all_objects.size()] = (uint32_t)path_nodes.size();
+    }
+
     // assemble
     struct Sec { const void* p; uint64_t bytes, count; };
     Sec secs[LSEC_COUNT] = {
@@ -768,6 +824,10 @@ static bool run(const uint8_t* data, uint64_t len, std::vector<uint8_t>& out) {
         {B.textures.data(), B.textures.size() * sizeof(LumoTexture), B.textures.size()},
         {B.tex_pixels.data(), B.tex_pixels.size() * 4, B.tex_pixels.size() / 4},
         {B.tex_f64.data(), B.tex_f64.size() * 8, B.tex_f64.size()},
+        {ah.nodes.data(), ah.nodes.size() * sizeof(LumoAhNode), ah.nodes.size()},
+        {ah.out_prims.data(), ah.out_prims.size() * sizeof(LumoAhPrim), ah.out_prims.size()},
+        {path_off.data(), path_off.size() * 4, path_off.size()},
+        {path_nodes.data(), path_nodes.size() * 4, path_nodes.size()},
     };
     LumoBlobHeader H; std::memset(&H, 0, sizeof H);
     H.magic = LUMO_BLOB_MAGIC; H.version = LUMO_BLOB_VERSION; H.n_sections = LSEC_COUNT; H.params = P;
@@ -798,5 +858,17 @@ int32_t lumo_host_build(const void* program, uint64_t len, void** blob, uint64_t
     catch (...) { lumo_host::g_err = "host build: unknown exception"; return -1; }
 }
 void lumo_host_free(void* p) { std::free(p); }
+// lumo_math.h on the host (fn as in lumo_gpu_math_eval): the host-side film finalisation (lumo_b200/color.py: encode) takes its
+// transfer-curve pow from here so that it is the device's, bit for bit.
+void lumo_host_math_eval(int32_t fn, const double* x, const double* y, uint64_t n, double* out) {
+    for (uint64_t i = 0; i < n; i++) {
+        const double a = x[i], b = y ? y[i] : 0.0;
+        switch (fn) {
+        case 0: out[i] = lm_sin(a); break; case 1: out[i] = lm_cos(a); break; case 2: out[i] = lm_atan2(a, b); break; case 3: out[i] = lm_acos(a); break;
+        case 4: out[i] = lm_atanh(a); break; case 5: out[i] = lm_cosh(a); break; case 6: out[i] = lm_exp(a); break; case 7: out[i] = lm_log(a); break;
+        default: out[i] = lm_pow(a, b); break;
+        }
+    }
+}
 const char* lumo_host_last_error(void) { return lumo_host::g_err.c_str(); }
 }

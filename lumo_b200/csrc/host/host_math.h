@@ -6,6 +6,7 @@
 #include <cstdint>
 #include <cstring>
 #include <limits>
+#include "../common/lumo_math.h"
 
 namespace lumo_host {
 
@@ -96,9 +97,9 @@ struct Xform {
         return t;
     }
     static Xform scale(double x, double y, double z) { M3 d = {{x, 0, 0, 0, y, 0, 0, 0, z}}; return from_m3(d); }
-    static Xform rot_x(double th) { double c = std::cos(th), s = std::sin(th); M3 r = {{1, 0, 0, 0, c, -s, 0, s, c}}; return from_m3(r); }
-    static Xform rot_y(double th) { double c = std::cos(th), s = std::sin(th); M3 r = {{c, 0, s, 0, 1, 0, -s, 0, c}}; return from_m3(r); }
-    static Xform rot_z(double th) { double c = std::cos(th), s = std::sin(th); M3 r = {{c, -s, 0, s, c, 0, 0, 0, 1}}; return from_m3(r); }
+    static Xform rot_x(double th) { double c = lm_cos(th), s = lm_sin(th); M3 r = {{1, 0, 0, 0, c, -s, 0, s, c}}; return from_m3(r); }
+    static Xform rot_y(double th) { double c = lm_cos(th), s = lm_sin(th); M3 r = {{c, 0, s, 0, 1, 0, -s, 0, c}}; return from_m3(r); }
+    static Xform rot_z(double th) { double c = lm_cos(th), s = lm_sin(th); M3 r = {{c, -s, 0, s, c, 0, 0, 0, 1}}; return from_m3(r); }
     static Xform perspective(double near, double far) {                                         // :113-131
         double a = far / (far - near), b = -far * near / (far - near);
         Xform t = identity();

@@ -10,7 +10,8 @@ HOST_SO = os.path.join(HERE, "liblumo_host.so")
 GPU_SO = os.environ.get("LUMO_GPU_SO", os.path.join(HERE, "liblumo_gpu.so"))   # override: A/B timing of two builds
 
 SECTIONS = ["tlas_nodes", "tlas_leaf", "objects", "instances", "kd_trees", "kd_nodes", "kd_leaf", "tri_verts", "tri_shade",
-            "normals", "uvs", "rects", "spheres", "materials", "tables", "lights", "textures", "tex_pixels", "tex_f64"]
+            "normals", "uvs", "rects", "spheres", "materials", "tables", "lights", "textures", "tex_pixels", "tex_f64",
+            "ah_nodes", "ah_prims", "obj_path_off", "obj_path"]
 
 TLAS_NODE = np.dtype([("lo", "<f8", 3), ("hi", "<f8", 3), ("right", "<u4"), ("first", "<u4"), ("count", "<u4"), ("pad", "<u4")])
 OBJECT = np.dtype([("kind", "<u4"), ("geom", "<u4"), ("inst", "<i4"), ("material", "<i4"), ("rect", "<u4"), ("pad", "<u4", 3)])
@@ -26,6 +27,9 @@ MATERIAL = np.dtype([("kind", "<u4"), ("flags", "<u4"), ("roughness", "<f8"), ("
                      ("ks_tex", "<u4"), ("tf_tex", "<u4"), ("ke_tex", "<u4"), ("bump_tex", "<u4"), ("pad", "<u8")])
 TEXTURE = np.dtype([("kind", "<u4"), ("a", "<u4"), ("b", "<u4"), ("width", "<u4"), ("height", "<u4"), ("pad", "<u4"), ("data", "<u8"),
                     ("spec", "<f4", 4), ("scale", "<f8"), ("pad2", "<f8")])
+AH_NODE = np.dtype([("lo_x", "<f4", 4), ("lo_y", "<f4", 4), ("lo_z", "<f4", 4), ("hi_x", "<f4", 4), ("hi_y", "<f4", 4), ("hi_z", "<f4", 4),
+                    ("child", "<u4", 4), ("pad", "<u4", 4)])
+AH_PRIM = np.dtype([("tri", "<u4"), ("obj", "<u4")])
 LIGHT = np.dtype([("alias_prob", "<f8"), ("pdf", "<f8"), ("area", "<f8"), ("alias", "<u4"), ("pad", "<u4")])
 CAMERA = np.dtype([("screen_to_raster_m", "<f8", 16), ("screen_to_raster_inv", "<f8", 16), ("camera_to_screen_m", "<f8", 16),
                    ("camera_to_screen_inv", "<f8", 16), ("world_to_camera_m", "<f8", 16), ("world_to_camera_inv", "<f8", 16),
@@ -42,7 +46,8 @@ HEADER = np.dtype([("magic", "<u8"), ("version", "<u4"), ("n_sections", "<u4"), 
 _SEC_DTYPES = {"tlas_nodes": TLAS_NODE, "tlas_leaf": np.dtype("<u4"), "objects": OBJECT, "instances": INSTANCE, "kd_trees": KD_TREE,
                "kd_nodes": KD_NODE, "kd_leaf": np.dtype("<u4"), "tri_verts": TRI_VERTS, "tri_shade": TRI_SHADE, "normals": np.dtype(("<f8", 3)),
                "uvs": np.dtype(("<f8", 2)), "rects": RECT, "spheres": SPHERE, "materials": MATERIAL, "tables": np.dtype(("<f8", 96)), "lights": LIGHT,
-               "textures": TEXTURE, "tex_pixels": np.dtype(("<f4", 4)), "tex_f64": np.dtype("<f8")}
+               "textures": TEXTURE, "tex_pixels": np.dtype(("<f4", 4)), "tex_f64": np.dtype("<f8"),
+               "ah_nodes": AH_NODE, "ah_prims": AH_PRIM, "obj_path_off": np.dtype("<u4"), "obj_path": np.dtype("<u4")}
 
 
 class Blob:
@@ -75,6 +80,8 @@ def host_lib():
         L.lumo_host_build.argtypes = [C.c_char_p, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
         L.lumo_host_free.argtypes = [C.c_void_p]
         L.lumo_host_last_error.restype = C.c_char_p
+        L.lumo_host_math_eval.argtypes = [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_uint64, C.POINTER(C.c_double)]
+        L.lumo_host_math_eval.restype = None
         _host = L
     return _host
 
@@ -90,6 +97,19 @@ def build_blob(program_bytes):
         return C.string_at(p, n.value)
     finally:
         L.lumo_host_free(p)
+
+
+MATH_FN = {"sin": 0, "cos": 1, "atan2": 2, "acos": 3, "atanh": 4, "cosh": 5, "exp": 6, "log": 7, "pow": 8}
+
+
+def host_math(fn, x, y=None):
+    """csrc/common/lumo_math.h evaluated by the host library (the same source the device kernels compile)."""
+    x = np.asarray(x, np.float64)
+    flat = np.ascontiguousarray(x).reshape(-1); out = np.empty_like(flat)
+    yy = None if y is None else np.ascontiguousarray(np.broadcast_to(np.asarray(y, np.float64), x.shape)).reshape(-1)
+    if flat.size:
+        host_lib().lumo_host_math_eval(MATH_FN[fn], _dp(flat), None if yy is None else _dp(yy), flat.size, _dp(out))
+    return out.reshape(x.shape)
 
 
 # ---- GPU library ---------------------------------------------------------------------------------
@@ -140,6 +160,10 @@ def gpu_lib():
         L.lumo_gpu_film_encode_dev.argtypes = [vp, vp, vp, C.c_uint64, C.c_double, C.c_double, C.c_int32, u8p, C.POINTER(C.c_float)]
         L.lumo_gpu_film_encode.argtypes = [vp, dp, dp, C.c_uint64, C.c_double, C.c_double, C.c_int32, u8p]
         L.lumo_gpu_render_multi.argtypes = [C.POINTER(vp), C.c_int32, C.POINTER(RenderParams), C.POINTER(FilmAccum)]
+        L.lumo_gpu_ctx_occlusion_mode.argtypes = [vp, C.c_int32]; L.lumo_gpu_ctx_occlusion_mode.restype = C.c_int32
+        L.lumo_gpu_ctx_occlusion_stats.argtypes = [vp, C.POINTER(C.c_uint64)]; L.lumo_gpu_ctx_occlusion_stats.restype = C.c_int32
+        L.lumo_gpu_math_eval.argtypes = [vp, C.c_int32, dp, dp, C.c_uint64, dp]
+        L.lumo_gpu_math_eval.restype = C.c_int32
         L.lumo_gpu_sample_range.argtypes = [C.c_int32, C.c_int32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         for f in ("lumo_gpu_render_dev", "lumo_gpu_trace_closest_dev", "lumo_gpu_ctx_count_visits", "lumo_gpu_ctx_visits","lumo_gpu_device_count", "lumo_gpu_ctx_create", "lumo_gpu_ctx_destroy", "lumo_gpu_scene_upload", "lumo_gpu_scene_destroy",
                   "lumo_gpu_trace_closest", "lumo_gpu_trace_any", "lumo_gpu_trace_first_found", "lumo_gpu_render", "lumo_gpu_film_encode", "lumo_gpu_film_encode_dev", "lumo_gpu_render_multi", "lumo_gpu_sample_range"):
@@ -180,6 +204,15 @@ class GpuContext:
         names = ("tlas_nodes", "inst", "kd_nodes", "leaf_idx", "tri_tests", "sphere_tests")
         return dict(zip(names, (int(v) for v in out[:6]))), dict(zip(names, (int(v) for v in out[6:])))
 
+    def occlusion_mode(self, mode):
+        """0: occlusion BVH + confirmation (default); 1: the reference's traversal for shadow rays; 2: both, disagreements counted."""
+        _check(gpu_lib().lumo_gpu_ctx_occlusion_mode(self.h, int(mode)), "lumo_gpu_ctx_occlusion_mode")
+
+    def occlusion_stats(self):
+        out = (C.c_uint64 * 8)()
+        _check(gpu_lib().lumo_gpu_ctx_occlusion_stats(self.h, out), "lumo_gpu_ctx_occlusion_stats")
+        return dict(zip(("nodes", "prims", "tri_tests", "sphere_tests", "candidates", "confirmed", "fallback", "mismatches"), (int(v) for v in out)))
+
     def iter_log(self):
         cap = 16384
         out = (C.c_uint32 * (2 * cap))(); n = C.c_uint32(0)
@@ -191,6 +224,13 @@ class GpuContext:
         ms = (C.c_double * 4)(); n = (C.c_uint64 * 4)()
         _check(gpu_lib().lumo_gpu_ctx_kernel_times(self.h, ms, n), "lumo_gpu_ctx_kernel_times")
         return {k: (ms[i], int(n[i])) for i, k in enumerate(("regen", "trace", "shade", "occlude"))}
+
+    def math_eval(self, fn, x, y=None):
+        """csrc/common/lumo_math.h evaluated on the device (parity hook)."""
+        x = np.ascontiguousarray(x, np.float64).ravel(); out = np.empty_like(x)
+        yy = None if y is None else np.ascontiguousarray(np.broadcast_to(np.asarray(y, np.float64), x.shape))
+        _check(gpu_lib().lumo_gpu_math_eval(self.h, MATH_FN[fn], _dp(x), None if yy is None else _dp(yy), x.size, _dp(out)), "lumo_gpu_math_eval")
+        return out
 
     def film_encode(self, pixels, splats, splat_scale, filter_integral, transfer=0):
         """Film::rgb_image on the device from HOST accumulators [H,W,4] / [H,W,3] f64 -> uint8 [H,W,3]."""

@@ -680,7 +680,7 @@ void oracle_bsdf_chi2_tables(void* h, int mat, const double* wo3, double lambda_
         Vec3 wi;
         Float ru = rng.gen_float(); Vec2 rs = rng.gen_vec2();
         if (!m->bsdf_sample(wo, hh, lam, ru, rs, wi)) continue;
-        Float theta = std::acos(clampf(wi.z, -1.0, 1.0)), phi = std::atan2(wi.y, wi.x); if (phi < 0.0) phi += 2.0 * PI;
+        Float theta = lm_acos(clampf(wi.z, -1.0, 1.0)), phi = lm_atan2(wi.y, wi.x); if (phi < 0.0) phi += 2.0 * PI;
         int tb = std::min((int)(theta / PI * theta_bins), theta_bins - 1), pb = std::min((int)(phi / (2.0 * PI) * phi_bins), phi_bins - 1);
         observed[pb + tb * phi_bins] += 1.0;
     }
@@ -688,8 +688,8 @@ void oracle_bsdf_chi2_tables(void* h, int mat, const double* wo3, double lambda_
         Float acc = 0.0;
         for (int a = 0; a < sub; a++) for (int b = 0; b < sub; b++) {
             Float theta = (tb + (a + 0.5) / sub) * PI / theta_bins, phi = (pb + (b + 0.5) / sub) * 2.0 * PI / phi_bins;
-            Vec3 wi(std::sin(theta) * std::cos(phi), std::sin(theta) * std::sin(phi), std::cos(theta));
-            acc += m->bsdf_pdf(wo, wi, hh, lam, false) * std::sin(theta);
+            Vec3 wi(lm_sin(theta) * lm_cos(phi), lm_sin(theta) * lm_sin(phi), lm_cos(theta));
+            acc += m->bsdf_pdf(wo, wi, hh, lam, false) * lm_sin(theta);
         }
         expected[pb + tb * phi_bins] = acc * (PI / theta_bins / sub) * (2.0 * PI / phi_bins / sub) * (Float)n_samples;
     }
@@ -718,6 +718,17 @@ void oracle_perlin_tables(uint64_t seed, double* out1536) {   // lattice (768) t
     for (int i = 0; i < 256; i++) { out1536[768 + i] = (double)pn.px[i]; out1536[1024 + i] = (double)pn.py[i]; out1536[1280 + i] = (double)pn.pz[i]; }
 }
 double oracle_lambda_sample_one(double v) { return Lambda::sample_one(v); }
+// lumo_math.h as compiled for the oracle: fn 0 sin, 1 cos, 2 atan2(x, y), 3 acos, 4 atanh, 5 cosh, 6 exp, 7 log, 8 pow(x, y)
+void oracle_math_eval(int fn, const double* x, const double* y, uint64_t n, double* out) {
+    for (uint64_t i = 0; i < n; i++) {
+        const double a = x[i], b = y ? y[i] : 0.0;
+        switch (fn) {
+        case 0: out[i] = lm_sin(a); break; case 1: out[i] = lm_cos(a); break; case 2: out[i] = lm_atan2(a, b); break; case 3: out[i] = lm_acos(a); break;
+        case 4: out[i] = lm_atanh(a); break; case 5: out[i] = lm_cosh(a); break; case 6: out[i] = lm_exp(a); break; case 7: out[i] = lm_log(a); break;
+        default: out[i] = lm_pow(a, b); break;
+        }
+    }
+}
 void oracle_xorshift(uint64_t seed, uint64_t n, uint64_t* out) { Rng r = Rng::xorshift(seed); for (uint64_t i = 0; i < n; i++) out[i] = r.gen_u64(); }
 void oracle_philox(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t stream, uint64_t n, uint64_t* out) { Rng r = Rng::counter(seed, pixel, sample, stream); for (uint64_t i = 0; i < n; i++) out[i] = r.gen_u64(); }
 double oracle_spectrum_sample(const float* c, double lambda) { Spectrum s; s.c0 = c[0]; s.c1 = c[1]; s.c2 = c[2]; s.scale = c[3]; return s.sample_one(lambda); }

@@ -482,8 +482,8 @@ struct Sphere : Object {
         xi = xi * radius / xi.length();
         Vec3 err = gamma_(5) * xi.abs();
         Vec3 ni = xi / radius;
-        Float u = (std::atan2(-ni.z, ni.x) + PI) / (2.0 * PI);
-        Float v = std::acos(-ni.y) / PI;
+        Float u = (lm_atan2(-ni.z, ni.x) + PI) / (2.0 * PI);
+        Float v = lm_acos(-ni.y) / PI;
         out = hit_new(t.value, mat, r.dir, xi, err, ni, ni, Vec2(u, v));
         out.tri = 0; out.bary = Vec3(0, 0, 0);   // the C ABI reports barycentrics for triangles only
         return true;
@@ -525,7 +525,7 @@ struct Sphere : Object {
             Float ds = d * cos_t - std::sqrt(fmax_(r2 - d2 * sin_t * sin_t, 0.0));
             Float cos_a = (d2 + r2 - ds * ds) / (2.0 * d * radius);
             Float sin_a = std::sqrt(fmax_(1.0 - cos_a * cos_a, 0.0));
-            Vec3 ng_local(std::cos(phi) * sin_a, std::sin(phi) * sin_a, cos_a);
+            Vec3 ng_local(lm_cos(phi) * sin_a, lm_sin(phi) * sin_a, cos_a);
             Vec3 ng = uvw.to_world(-ng_local).normalize();
             xi = ng * radius;
         }

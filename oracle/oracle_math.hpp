@@ -14,6 +14,10 @@
 #include <cstring>
 #include <limits>
 #include <algorithm>
+// sin / cos / atan2 / acos / atanh / cosh / exp: one FMA-free source shared with the device kernels and the host builder, so
+// that identical inputs give identical bits on every side (see the header of that file; the reference's own libm is not
+// pinned to the bit by anything it ships)
+#include "../lumo_b200/csrc/common/lumo_math.h"
 
 namespace oracle {
 
@@ -175,15 +179,15 @@ struct Transform {
     }
     static Transform scale(Float x, Float y, Float z) { return mat3(Mat3::diag(Vec3(x, y, z))); }
     static Transform rotate_x(Float th) {
-        Float c = std::cos(th), s = std::sin(th);
+        Float c = lm_cos(th), s = lm_sin(th);
         return mat3(Mat3(Vec3(1, 0, 0), Vec3(0, c, -s), Vec3(0, s, c)));
     }
     static Transform rotate_y(Float th) {
-        Float c = std::cos(th), s = std::sin(th);
+        Float c = lm_cos(th), s = lm_sin(th);
         return mat3(Mat3(Vec3(c, 0, s), Vec3(0, 1, 0), Vec3(-s, 0, c)));
     }
     static Transform rotate_z(Float th) {
-        Float c = std::cos(th), s = std::sin(th);
+        Float c = lm_cos(th), s = lm_sin(th);
         return mat3(Mat3(Vec3(c, -s, 0), Vec3(s, c, 0), Vec3(0, 0, 1)));
     }
     static Transform perspective(Float near, Float far) {                             // transform.rs:113-131
@@ -272,9 +276,9 @@ struct Complex {
     Float norm_sqr() const { return Re * Re + Im * Im; }
     Complex co() const { return Complex(Re, -Im); }
     Float norm() const { return std::sqrt(norm_sqr()); }
-    Float arg() const { return std::atan2(Im, Re); }   // libm::atan2 in the reference: ulp-level parity unpinned
+    Float arg() const { return lm_atan2(Im, Re); }   // libm::atan2 in the reference: ulp-level parity unpinned
     Complex sqrt() const {
-        return Complex(std::sqrt(norm()) * std::cos(arg() / 2.0), std::sqrt(norm()) * std::sin(arg() / 2.0));
+        return Complex(std::sqrt(norm()) * lm_cos(arg() / 2.0), std::sqrt(norm()) * lm_sin(arg() / 2.0));
     }
 };
 static inline Complex operator+(Complex a, Complex b) { return Complex(a.Re + b.Re, a.Im + b.Im); }
@@ -330,7 +334,7 @@ static inline Vec2 square_to_disk(Vec2 r) {
     Float rr, theta;
     if (std::fabs(offset.x) > std::fabs(offset.y)) { rr = offset.x; theta = PI * (offset.y / offset.x) / 4.0; }
     else { rr = offset.y; theta = PI * (0.5 - (offset.x / offset.y) / 4.0); }
-    return rr * Vec2(std::cos(theta), std::sin(theta));
+    return rr * Vec2(lm_cos(theta), lm_sin(theta));
 }
 static inline Vec3 square_to_cos_hemisphere(Vec2 r) {
     Vec2 d = square_to_disk(r);
@@ -341,7 +345,7 @@ static inline Vec3 square_to_sphere(Vec2 r) {
     Float z = 1.0 - 2.0 * r.y;
     Float rr = std::sqrt(fmax_(1.0 - z * z, 0.0));
     Float phi = 2.0 * PI * r.x;
-    return Vec3(rr * std::cos(phi), rr * std::sin(phi), z);
+    return Vec3(rr * lm_cos(phi), rr * lm_sin(phi), z);
 }
 
 // ---- random streams -------------------------------------------------------------------------

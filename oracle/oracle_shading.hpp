@@ -31,10 +31,10 @@ static const Color WHITE(1.0), BLACK(0.0);
 // ---- ColorWavelength (src/tracer/color/wavelength.rs) -----------------------------------------
 struct Lambda {
     Float l[4];
-    static Float sample_one(Float v) { return 538.0 - 138.888889 * std::atanh(0.85691062 - 253.819 * v * 0.0072); }  // :48-51
+    static Float sample_one(Float v) { return 538.0 - 138.888889 * lm_atanh(0.85691062 - 253.819 * v * 0.0072); }  // :48-51
     static Float pdf_one(Float lam) {                                                                                // :60-66
         if (lam < LAMBDA_MIN || lam > LAMBDA_MAX) return 0.0;
-        return 1.0 / (253.819 * powi(std::cosh(0.0072 * (lam - 538.05)), 2));
+        return 1.0 / (253.819 * powi(lm_cosh(0.0072 * (lam - 538.05)), 2));
     }
     static Lambda sample(Float u) {                                                                                  // :35-44
         Lambda r;
@@ -199,7 +199,7 @@ struct Texture {                                                                
         case TEX_MARBLE: {
             const Vec3 uvw(uv.x, uv.y, 0.0);
             const Float turb = turbulence(*pn, 0.0, 4.0 * uvw.abs(), 0);
-            const Float scaled = 1.0 - powi(0.5 + 0.5 * std::sin(60.0 * uvw.x + 20.0 * turb), 6);
+            const Float scaled = 1.0 - powi(0.5 + 0.5 * lm_sin(60.0 * uvw.x + 20.0 * turb), 6);
             return spec.sample(lam) * scaled;
         }
         case TEX_CHECKER: {
@@ -350,10 +350,10 @@ struct Material {
         Vec3 v = u.cross(ws);
         Float r = std::sqrt(rs.x);
         Float theta = 2.0 * PI * rs.y;
-        Float x = r * std::cos(theta);
+        Float x = r * lm_cos(theta);
         Float h = std::sqrt(fmax_(1.0 - x * x, 0.0));
         Float lerp = (1.0 + ws.z) / 2.0;
-        Float y = (1.0 - lerp) * h + lerp * r * std::sin(theta);
+        Float y = (1.0 - lerp) * h + lerp * r * lm_sin(theta);
         Vec3 wm(x, y, std::sqrt(fmax_(1.0 - x * x - y * y, 0.0)));
         wm = wm.x * u + wm.y * v + wm.z * ws;
         return Vec3(roughness.x * wm.x, roughness.y * wm.y, fmax_(wm.z, EPSILON)).normalize();
@@ -570,7 +570,7 @@ struct PixelFilter {
     int kind = 2; Float r = 1.5, p = 0.375;   // Gaussian(1.5, 1.5/4) default (:20-24)
     uint64_t r_disc() const { return sat_u64(std::ceil(r - 0.5)); }                            // :70-79
     static Float gauss(Float x, Float sigma) {                                                 // :118-123
-        return std::exp(-powi(x, 2) / (2.0 * sigma * sigma)) / std::sqrt(fmax_(2.0 * PI * sigma * sigma, 0.0));
+        return lm_exp(-powi(x, 2) / (2.0 * sigma * sigma)) / std::sqrt(fmax_(2.0 * PI * sigma * sigma, 0.0));
     }
     static Float mitch(Float x, Float b, Float c) {                                            // :132-150
         x = std::fabs(x);

@@ -84,59 +84,76 @@ def test_edge_cases(gpu_ctx):
         native.GpuScene(gpu_ctx, blob[:-16])                        # malformed blob -> status code, not a crash
 
 
-def test_flat_traversal_is_bit_exact_too():
-    """The lane-refilled state-machine traversal (trace_flat.cuh, opt-in via LUMO_TRACE_FLAT=1) must produce the
-    same bits as the default nested one.  A context reads the switch when it is created."""
-    import os
+def _shadow_rays(O, n, seed):
+    """Shadow-ray-like batches: from surface points of the scene towards random points of its bounding box, towards points
+    just in front of / just behind the first thing in that direction, and towards the surface point itself (grazing
+    configurations of hit_light's `t_light - 1e-10`)."""
+    rs = np.random.RandomState(seed)
+    batches = ray_batches(O, n, seed)
+    o1, d1 = batches["primary"]
+    _, _, t, _ = O.trace_closest(o1, d1)
+    ok = np.isfinite(t)
+    p = o1[ok] + d1[ok] * (t[ok] * (1 - 1e-9))[:, None]                 # points on surfaces
+    b = O.bounds(); lo, hi = b[:3], b[3:]
+    q = lo + rs.rand(len(p), 3) * (hi - lo)
+    v = q - p; dist = np.linalg.norm(v, axis=1); d = v / dist[:, None]
+    out = [(p, d, dist - 1e-10)]
+    _, _, t2, _ = O.trace_closest(p, d)
+    f = np.isfinite(t2)
+    for k in (1.0 - 1e-9, 1.0, 1.0 + 1e-9, 0.3):                          # t_max around the first blocker
+        out.append((p[f], d[f], t2[f] * k - 1e-10))
+    o3, d3 = batches["incoherent"]
+    out.append((o3, d3, rs.rand(len(o3)) * np.linalg.norm(hi - lo)))
+    return out
+
+
+@pytest.mark.parametrize("name", list(SMALL))
+def test_occlusion_bvh_equals_reference_traversal_and_oracle(name, gpu_ctx):
+    """G2: the order-free occlusion BVH (+ confirmation by the reference's per-object traversal, occlude.cuh) returns the
+    oracle's booleans, and the same booleans as the device's own replay of the reference traversal (occlusion mode 1)."""
     from lumo_b200 import native
-    prog, blob, _ = small_scene("bistro")
+    prog, blob, _ = small_scene(name)
     O = oracle_lib.OracleScene(prog)
-    os.environ["LUMO_TRACE_FLAT"] = "1"
+    G = native.GpuScene(gpu_ctx, blob)
+    n_rays = 0
     try:
-        ctx = native.GpuContext(0)
+        for o, d, tm in _shadow_rays(O, N, seed=43):
+            want = O.trace_any(o, d, tm)
+            gpu_ctx.occlusion_mode(0); fast = G.trace_any(o, d, tm)
+            gpu_ctx.occlusion_mode(1); slow = G.trace_any(o, d, tm)
+            assert np.array_equal(slow, want), (name, "reference traversal on the device vs oracle", int((slow != want).sum()))
+            assert np.array_equal(fast, want), (name, "occlusion BVH vs oracle", int((fast != want).sum()))
+            n_rays += len(want)
     finally:
-        del os.environ["LUMO_TRACE_FLAT"]
-    G = native.GpuScene(ctx, blob)
-    for kind, (o, d) in ray_batches(O, 8000, seed=37).items():
-        eo, et, ett, eb = O.trace_closest(o, d)
-        go, gt, gtt, gb = G.trace_closest(o, d)
-        assert np.array_equal(eo, go) and np.array_equal(et, gt) and np.array_equal(_bits(ett), _bits(gtt)) and np.array_equal(_bits(eb), _bits(gb)), kind
-        tm = np.where(np.isfinite(ett), ett * 0.999, 5.0)
-        assert np.array_equal(O.trace_any(o, d, tm), G.trace_any(o, d, tm)), kind
-        assert np.array_equal(_bits(O.trace_first_found(o, d)), _bits(G.trace_first_found(o, d))), kind
-    G.close(); ctx.close(); O.close()
+        gpu_ctx.occlusion_mode(0)
+    assert n_rays > 2 * N
+    G.close(); O.close()
 
 
-def test_node_major_bit_exact():
-    """The node-major traversal of small object BVHs (trace_nm.cuh, opt-in via LUMO_TRACE_NM=1: per-BVH-segment kernels,
-    light objects in place, a lane-refilled kernel per big kd-tree) must produce the same bits as the nested default, for
-    the batch API and for a whole render."""
-    import os
+def test_occlusion_bvh_counters_and_render_cross_check(gpu_ctx):
+    """Mode 2 runs both kernels on every shadow ray of a render: zero disagreements, and the film equals the default mode's
+    up to the order of the atomic adds.  The counting instantiation reports the BVH work (bench.py's roofline input)."""
     from lumo_b200 import native
-    os.environ["LUMO_TRACE_NM"] = "1"
-    try:
-        ctx = native.GpuContext(0)
-    finally:
-        del os.environ["LUMO_TRACE_NM"]
-    ref = native.GpuContext(0)
-    for name in ("bunny", "cornell"):
+    for name in ("bunny", "bistro", "conference", "caustics"):
         prog, blob, ig = small_scene(name)
-        O = oracle_lib.OracleScene(prog)
-        G = native.GpuScene(ctx, blob)
-        for kind, (o, d) in ray_batches(O, 8000, seed=41).items():
-            eo, et, ett, eb = O.trace_closest(o, d)
-            go, gt, gtt, gb = G.trace_closest(o, d)
-            assert np.array_equal(eo, go) and np.array_equal(et, gt) and np.array_equal(_bits(ett), _bits(gtt)) and np.array_equal(_bits(eb), _bits(gb)), (name, kind)
-            tm = np.where(np.isfinite(ett), ett * 0.999, 5.0)
-            assert np.array_equal(O.trace_any(o, d, tm), G.trace_any(o, d, tm)), (name, kind)
-        # a render large enough for the wave to take the node-major path (>= 131072 live rays), against the default context
-        R = native.GpuScene(ref, blob)
-        a = G.render(integrator=ig, spp=64, seed=5)
-        b = R.render(integrator=ig, spp=64, seed=5)
-        # same paths, same ray counts; the film sums differ only by the order of the atomic adds
-        assert np.allclose(a[0], b[0], rtol=1e-11, atol=1e-13) and a[2]["closest"] == b[2]["closest"] and a[2]["occlusion"] == b[2]["occlusion"], name
-        G.close(); R.close(); O.close()
-    ctx.close(); ref.close()
+        G = native.GpuScene(gpu_ctx, blob)
+        try:
+            gpu_ctx.count_visits(False)
+            gpu_ctx.occlusion_mode(0); a = G.render(integrator=0, spp=16, seed=9)
+            gpu_ctx.occlusion_mode(2); b = G.render(integrator=0, spp=16, seed=9)
+            st = gpu_ctx.occlusion_stats()
+            gpu_ctx.occlusion_mode(1); c = G.render(integrator=0, spp=16, seed=9)
+        finally:
+            gpu_ctx.occlusion_mode(0)
+        assert st["mismatches"] == 0, (name, st)
+        assert a[2]["occlusion"] == b[2]["occlusion"] == c[2]["occlusion"] > 0 and a[2]["closest"] == c[2]["closest"]
+        assert np.allclose(a[0], c[0], rtol=1e-11, atol=1e-13) and np.allclose(a[0], b[0], rtol=1e-11, atol=1e-13), name
+        gpu_ctx.count_visits(True)
+        G.render(integrator=0, spp=2, seed=9)
+        st = gpu_ctx.occlusion_stats(); gpu_ctx.count_visits(False)
+        assert st["nodes"] > 0 and st["tri_tests"] + st["sphere_tests"] > 0 and st["candidates"] == st["confirmed"] + st["fallback"], (name, st)
+        assert st["fallback"] <= 1e-3 * max(st["candidates"], 1) + 2, (name, st)
+        G.close()
 
 
 def test_special_rays_bit_exact(gpu_ctx):
