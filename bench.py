@@ -1,21 +1,24 @@
 #!/usr/bin/env python
 """bench.py — Mrays/s and Msamples/s of the lumo hot path on B200 (BASELINE.json metric).
 
-A "step" is one pass of the hot path over the workload: `--spp` samples per pixel of the whole
-image through the wavefront pipeline (camera rays -> closest-hit traversal -> shading/NEE ->
-occlusion traversal -> film).  rays = closest-hit queries + occlusion queries, counted on the
-device.  With N GPUs (torchrun) every rank renders its own sample range of a N*spp render with the
-scene replicated (weak scaling) and the film accumulators are combined with ONE NCCL reduce
-inside the timed region.
+Workload at N = 1: `bistro` — examples/bistro.rs, PathTrace, 1920x1080, the configuration BASELINE.json's target is
+quoted on (synthetic 1.05 M-triangle street in 1024 kd-trees, 4097 lights: the assets do not exist offline).  A "step"
+is one pass of the hot path over one batch: `--spp` samples per pixel (default 32) of the whole image through the
+wavefront pipeline (camera rays -> closest-hit traversal -> shading / NEE -> occlusion traversal -> film).
+rays = closest-hit queries + occlusion queries, counted on the device.  With N GPUs (torchrun) every rank renders its
+own sample range of an N*spp render with the scene replicated (weak scaling) and the film accumulators are combined with
+ONE NCCL reduce inside the timed region.
 
-  value     whole-job Mrays/s, scene resident in HBM, film left on the device
-  e2e       the same metric through the public C-ABI calls with HOST buffers: scene blob upload
-            (H2D) + render + film download (D2H) inside the timed region
-  roofline  the closest-hit trace kernel: algorithmic bytes (DESIGN.md byte formula x visit
-            counters from an untimed counting pass of the same workload) / its CUDA-event time
-  cpu_baseline  the C++ restatement of lumo's CPU renderer (oracle/, reference schedule, all host
-            cores) on a bounded sample of the same workload
-`--impl reference` runs only that CPU restatement (the reference is Rust and cannot be built here)."""
+  value         whole-job Mrays/s, scene resident in HBM, film left on the device (CUDA events, max over ranks)
+  e2e           the same metric through the public calls with HOST buffers, every step: scene blob upload from pinned host
+                memory (H2D) + render (+ NCCL reduce at N > 1) + film download into pinned host memory (D2H, 56 B/pixel)
+  roofline      the kernel class that takes the most time of the step; `roofline_by_kernel` has all three (closest-hit
+                trace, shading, occlusion) — algorithmic bytes (DESIGN.md byte formulas x device visit counters from an
+                untimed counting pass of the same step) / CUDA-event time of the class
+  cpu_baseline  the C++ restatement of lumo's CPU renderer (oracle/, reference schedule, all host cores) at the SAME spp on
+                every k-th 16x16 tile of the same image (k chosen for ~10-20 s of CPU work)
+  other_workloads  the four other BASELINE configs, each measured the same way with fewer steps
+`--impl reference` runs only that CPU restatement (the reference is Rust and cannot be built here), same config."""
 import argparse
 import json
 import os
@@ -28,13 +31,13 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {   # name -> (scene kwargs, integrator, default spp per step)
+    "bistro": (dict(), 0, 32),
     "bunny": (dict(), 0, 32),
     "cornell": (dict(), 0, 64),
-    "dragon": (dict(), 0, 8),
-    "caustics_bdpt": (dict(), 2, 2),
-    "conference": (dict(), 0, 16),
+    "dragon": (dict(), 0, 16),
+    "caustics_bdpt": (dict(), 2, 4),
+    "conference": (dict(), 0, 32),
     "conference_dl": (dict(), 1, 32),
-    "bistro": (dict(), 0, 2),
     "textured": (dict(n_tris=20000, resolution=(1024, 768)), 0, 16),
 }
 DESCR = {
@@ -47,6 +50,8 @@ DESCR = {
     "bistro": "examples/bistro.rs PathTrace 1920x1080, synthetic 1.05M-triangle street in 1024 kd-trees, 4097 lights",
     "textured": "not a reference example: empty box with every Texture kind, bump maps, image light + environment map (scenes.textured) PathTrace 1024x768",
 }
+INTEGRATORS = ["PathTrace", "DirectLight", "BDPathTrace"]
+TARGET_MRAYS = 1000.0   # BASELINE.json north_star: >= 1 Gray/s per B200 on Bistro path tracing
 
 
 def build_workload(name):
@@ -56,6 +61,13 @@ def build_workload(name):
     prog = s._program(cam)
     blob = native.build_blob(prog)
     return prog, blob, integrator, spp
+
+
+def config_of(name, integrator, spp, world, res):
+    """The `config` object — identical in the repo arm and the reference arm."""
+    return {"workload": name, "description": DESCR[name], "integrator": INTEGRATORS[integrator], "resolution": list(res), "spp_per_step_per_gpu": spp,
+            "parallelism": "scene replicated, samples sharded, 1 NCCL reduce" if world > 1 else "single GPU",
+            "l2": "256 MiB buffer written between timed steps (L2 flush); wave state and film also exceed the 126 MB L2"}
 
 
 class ClockSampler:
@@ -95,8 +107,14 @@ class ClockSampler:
 
 
 def ray_bytes(v, n_rays, fixed):
-    """DESIGN.md byte formula: per-ray queue traffic + nodes / instances / leaf entries / triangles visited."""
+    """DESIGN.md byte formula of the reference-order traversal: per-ray queue traffic + nodes / instances / leaf entries / triangles visited."""
     return fixed * n_rays + 64 * v["tlas_nodes"] + 96 * v["inst"] + 16 * v["kd_nodes"] + 4 * v["leaf_idx"] + 72 * v["tri_tests"] + 16 * v["sphere_tests"]
+
+
+def occl_bytes(st, vis, n_rays):
+    """Occlusion pipeline: 60 B shadow-queue entry per ray, 128 B per BVH node, 8 B per leaf primitive, 72 B per triangle test,
+    16 B per sphere test, 8 B per confirm-queue entry, plus the confirming traversal's own visits (reference-order formula)."""
+    return 60 * n_rays + 128 * st["nodes"] + 8 * st["prims"] + 72 * st["tri_tests"] + 16 * st["sphere_tests"] + 8 * st["candidates"] + ray_bytes(vis, 0, 0) + 60 * st["candidates"]
 
 
 def micro_trace(scene, dev, torch, np, n=1 << 22):
@@ -104,7 +122,6 @@ def micro_trace(scene, dev, torch, np, n=1 << 22):
     P = scene.blob.params; cam = P["camera"]
     W, H = int(cam["res_x"]), int(cam["res_y"])
     g = torch.Generator(device=dev); g.manual_seed(23)
-    # primary rays: Camera::generate_ray for a pinhole camera (camera.rs:257-268), evaluated in f64 on the host side of the bench
     rs = np.random.RandomState(23)
     raster = np.stack([rs.rand(n) * W, rs.rand(n) * H, np.zeros(n), np.ones(n)], 0)
     def xf(m16, v):
@@ -134,18 +151,52 @@ def micro_trace(scene, dev, torch, np, n=1 << 22):
     return out
 
 
-def cpu_baseline(prog, integrator, threads, spp=1, total_spp=None, seed=1):
-    """The C++ restatement of lumo's CPU renderer (reference schedule: 16x16 tiles x 256-sample batches from a
-    shared queue, per-tile xorshift; renderer.rs:174-204), -O3 -march=native, `threads` workers."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import oracle_lib
-    O = oracle_lib.OracleScene(prog, native=True)
-    t0 = time.time()
-    _, _, cnt, _ = O.render(integrator=integrator, spp=spp, seed=seed, rng_mode=0, threads=threads)
-    dt = time.time() - t0
-    O.close()
-    rays = cnt["closest"] + cnt["occlusion"]
-    return rays / dt / 1e6, cnt["camera_paths"] / dt / 1e6, dt, cnt
+# ---- CPU arm: the C++ restatement of lumo's CPU renderer ------------------------------------------------------------------
+class CpuArm:
+    """lumo's CPU path (C++ restatement, reference schedule: 16x16 tiles x 256-sample batches from a shared queue, per-tile
+    xorshift and ring-buffer RR threshold; renderer.rs:174-204, task.rs:25-81), -O3 -march=native, all host cores, at the
+    workload's own spp on every `tile_step`-th tile of the full-resolution image."""
+    def __init__(self, prog, integrator, spp, target_seconds):
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib
+        self.O = oracle_lib.OracleScene(prog, native=True)
+        self.integrator, self.spp = integrator, spp
+        self.threads = os.cpu_count() or 1
+        n_tiles = ((self.O.res_x + 15) // 16) * ((self.O.res_y + 15) // 16)
+        # calibrate on ~2 tiles per thread, then choose the stride for about target_seconds per step
+        cal = max(1, n_tiles // (2 * self.threads))
+        t0 = time.time(); _, _, cnt, _ = self.O.render(integrator=integrator, spp=spp, seed=99, rng_mode=0, threads=self.threads, tile_step=cal); dt = max(time.time() - t0, 1e-3)
+        tiles_cal = -(-n_tiles // cal)
+        per_tile = dt / tiles_cal * min(self.threads, tiles_cal) / self.threads       # wall seconds per tile at full occupancy of the cores
+        want_tiles = max(self.threads * 2, int(target_seconds / max(per_tile, 1e-9)))
+        self.tile_step = max(1, n_tiles // min(n_tiles, want_tiles))
+        self.n_tiles, self.tiles = n_tiles, -(-n_tiles // self.tile_step)
+
+    def step(self, seed):
+        t0 = time.time()
+        _, _, cnt, _ = self.O.render(integrator=self.integrator, spp=self.spp, seed=seed, rng_mode=0, threads=self.threads, tile_step=self.tile_step)
+        dt = time.time() - t0
+        return cnt, dt
+
+    def sample_text(self):
+        return ("%d spp (the workload's own) on every %d-th 16x16 tile of the full-resolution image: %d of %d tiles per step (lumo CPU path, C++ restatement with the "
+                "reference tile/batch schedule and RR recurrence; the Rust reference cannot be built offline)" % (self.spp, self.tile_step, self.tiles, self.n_tiles))
+
+    def close(self):
+        self.O.close()
+
+
+def cpu_measure(prog, integrator, spp, target_seconds, steps=1, warmup=0, seed0=1):
+    arm = CpuArm(prog, integrator, spp, target_seconds)
+    rays = paths = secs = 0.0
+    for i in range(warmup + steps):
+        cnt, dt = arm.step(seed0 + i)
+        if i >= warmup:
+            rays += cnt["closest"] + cnt["occlusion"]; paths += cnt["camera_paths"]; secs += dt
+    out = {"value": rays / secs / 1e6, "unit": "Mrays/s", "cores": arm.threads, "kind": "port", "msamples_per_s": paths / secs / 1e6,
+           "rays_per_sample": rays / max(paths, 1), "seconds_per_step": secs / steps, "sample": arm.sample_text()}
+    arm.close()
+    return out
 
 
 _RESULT_OUT = None
@@ -166,70 +217,42 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    prog, blob, integrator, spp_default = build_workload(args.workload)
-    threads = os.cpu_count() or 1
-    vals, samps, dts = [], [], []
-    for i in range(args.warmup + args.steps):
-        v, s, dt, cnt = cpu_baseline(prog, integrator, threads, spp=1, seed=1 + i)
-        if i >= args.warmup:
-            vals.append(v); samps.append(s); dts.append(dt)
-    val = sum(vals) / len(vals)
-    line = {"impl": "reference", "metric": "Mrays/s", "value": val, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * sum(dts) / len(dts), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "description": DESCR[args.workload], "integrator": ["PathTrace", "DirectLight", "BDPathTrace"][integrator]},
-            "msamples_per_s": sum(samps) / len(samps),
-            "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": threads, "kind": "port",
-                             "sample": "1 spp of the full-resolution workload per step (lumo CPU path, C++ restatement; the Rust reference cannot be built offline)"},
-            "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    prog, blob, integrator, spp = build_workload(args.workload)
+    if args.spp: spp = args.spp
+    from lumo_b200 import native
+    B = native.Blob(blob); res = (int(B.params["camera"]["res_x"]), int(B.params["camera"]["res_y"]))
+    # each step a bounded sample: sized so that warmup + steps end within a few minutes
+    per_step = max(2.0, min(15.0, 240.0 / max(args.steps + args.warmup, 1)))
+    r = cpu_measure(prog, integrator, spp, per_step, steps=args.steps, warmup=args.warmup)
+    line = {"impl": "reference", "metric": "Mrays/s", "value": r["value"], "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * r["seconds_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_of(args.workload, integrator, spp, int(os.environ.get("WORLD_SIZE", "1")), res),
+            "msamples_per_s": r["msamples_per_s"], "rays_per_sample": r["rays_per_sample"],
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), file=_guard_stdout(), flush=True)
     return 0
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="bunny", choices=list(WORKLOADS))
-    ap.add_argument("--spp", type=int, default=0, help="samples per pixel per step and per GPU (0 = workload default)")
-    ap.add_argument("--wave-paths", type=int, default=0)
-    ap.add_argument("--other-scenes", default="cornell,dragon,caustics_bdpt,conference,conference_dl,bistro,textured", help="comma list measured briefly after the main workload ('' = none)")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    args = ap.parse_args()
-    _guard_stdout()
-    if args.impl == "reference":
-        return run_reference(args)
-
-    import numpy as np
-    import torch
-    from lumo_b200 import native
-    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: lumo_b200 has no CPU path")
-    torch.cuda.set_device(local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    dev = torch.device("cuda", local)
-
-    prog, blob, integrator, spp = build_workload(args.workload)
-    if args.spp: spp = args.spp
+# ---- GPU arm ----------------------------------------------------------------------------------------------------------------
+def measure(name, args, env, steps, warmup, full):
+    """One workload on this rank's GPU (and, at world > 1, together with the other ranks).  Returns the JSON line's content on
+    rank 0, None elsewhere.  full: also micro batches / film kernel / strong-scaling extras (main workload only)."""
+    torch, np, native, dist = env["torch"], env["np"], env["native"], env["dist"]
+    world, rank, dev, ctx, stream, flush = env["world"], env["rank"], env["dev"], env["ctx"], env["stream"], env["flush"]
+    prog, blob, integrator, spp = build_workload(name)
+    if args.spp and name == args.workload: spp = args.spp
     total_spp = spp * world
     s0, s1 = rank * spp, (rank + 1) * spp
-    ctx = native.GpuContext(local)
-    stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
     scene = native.GpuScene(ctx, blob)
     W, H = scene.res_x, scene.res_y
     film = torch.zeros(W * H * 7, dtype=torch.float64, device=dev)      # pixels[W*H*4] then splats[W*H*3]
     px_ptr, sp_ptr = film.data_ptr(), film.data_ptr() + W * H * 4 * 8
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
 
-    def step(seed):
-        cnt, ms = scene.render_dev(px_ptr, sp_ptr, integrator=integrator, seed=seed, spp_begin=s0, spp_end=s1, total_spp=total_spp, wave_paths=args.wave_paths)
-        if dist is not None:
+    def step(seed, a=s0, b=s1, total=total_spp, reduce=True):
+        cnt, ms = scene.render_dev(px_ptr, sp_ptr, integrator=integrator, seed=seed, spp_begin=a, spp_end=b, total_spp=total, wave_paths=args.wave_paths)
+        if dist is not None and reduce:
             dist.reduce(film, dst=0)       # the one collective of the path: film accumulators over NVLink
         return cnt
 
@@ -237,16 +260,16 @@ def main():
         if dist is not None: dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(args.warmup):
+    for i in range(warmup):
         step(100 + i)
     barrier()
-    clocks = ClockSampler(local) if rank == 0 else None
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    clocks = ClockSampler(env["local"]) if rank == 0 else None
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     tot = {"closest": 0, "occlusion": 0, "camera_paths": 0, "cost": 0, "gpu_launches": 0, "iterations": 0}
     ktimes = {"regen": [0.0, 0], "trace": [0.0, 0], "shade": [0.0, 0], "occlude": [0.0, 0]}
-    seeds = [1 + i for i in range(args.steps)]
+    seeds = [1 + i for i in range(steps)]
     barrier()
-    for i in range(args.steps):
+    for i in range(steps):
         flush.zero_()                      # L2 flush between timed iterations (outside the events)
         ev[i][0].record(stream)
         cnt = step(seeds[i])
@@ -264,102 +287,126 @@ def main():
     rays = closest + occl
     value = rays / (ms_total * 1e-3) / 1e6
 
-    e2e_multi = None
-    if dist is not None:
-        # multi-GPU e2e (all ranks take part in the reduce): render + NCCL reduce + film download on rank 0, wall clock
+    # ---- e2e: host buffers on both sides of every step, the same definition at every N ---------------------------------------
+    # upload of the scene blob from pinned host memory, render, NCCL reduce (N > 1), download of the 56 B/pixel film accumulators
+    # into pinned host memory on rank 0; wall clock, max over ranks, one discarded step then up to 5 timed ones
+    pin_blob = torch.frombuffer(bytearray(blob), dtype=torch.uint8).pin_memory()
+    pin_film = torch.empty(W * H * 7, dtype=torch.float64).pin_memory() if rank == 0 else None
+    n_e2e = max(1, min(steps, 5 if full else 2))
+    e_rays, e_t = 0.0, 0.0
+    for i in range(1 + n_e2e):
         barrier(); t0 = time.perf_counter()
-        cnt2 = step(seeds[-1])
-        if rank == 0: host_film = film.cpu()
+        sc2 = native.GpuScene(ctx, blob, host_ptr=pin_blob.data_ptr())
+        cnt2, _ = sc2.render_dev(px_ptr, sp_ptr, integrator=integrator, seed=seeds[min(i, len(seeds) - 1)], spp_begin=s0, spp_end=s1, total_spp=total_spp, wave_paths=args.wave_paths)
+        if dist is not None: dist.reduce(film, dst=0)
+        if rank == 0: pin_film.copy_(film, non_blocking=True)
         torch.cuda.synchronize()
+        sc2.close()
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         r2 = torch.tensor([cnt2["closest"] + cnt2["occlusion"]], dtype=torch.float64, device=dev)
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX); dist.all_reduce(r2, op=dist.ReduceOp.SUM)
-        e2e_multi = float(r2.item()) / float(dt.item()) / 1e6
-    if rank != 0:
         if dist is not None:
-            dist.barrier(); dist.destroy_process_group()
-        return 0
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX); dist.all_reduce(r2, op=dist.ReduceOp.SUM)
+        if i > 0: e_rays += float(r2.item()); e_t += float(dt.item())
+    e2e = {"value": e_rays / e_t / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": world * (len(blob) + 64), "d2h_bytes_per_step": W * H * 56 + 64 * world, "steps": n_e2e,
+           "what": "per step and per rank: lumo_gpu_scene_upload from a pinned host blob + lumo_gpu_render_dev" + (" + ONE NCCL reduce of the film" if world > 1 else "") +
+                   " + download of the 56 B/pixel film accumulators into pinned host memory on rank 0 + lumo_gpu_scene_destroy; wall clock, max over ranks, after one discarded step"}
 
-    # ---- rank 0 only from here: counting pass, e2e, cpu baseline (N=1), other scenes ------------
-    line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "description": DESCR[args.workload], "integrator": ["PathTrace", "DirectLight", "BDPathTrace"][integrator],
-                       "resolution": [W, H], "spp_per_step_per_gpu": spp, "parallelism": "scene replicated, samples sharded, 1 NCCL reduce" if world > 1 else "single GPU",
-                       "l2": "256 MiB buffer written between timed steps (L2 flush); wave state (2^21 slots, ~0.7 GB) and film (44 MB) also exceed L2"},
-            "msamples_per_s": paths / (ms_total * 1e-3) / 1e6,
+    # ---- G6 inside the run (N > 1): the reduced film of N ranks equals rank 0's own render of the whole range ---------------
+    film_check = None
+    if dist is not None and full:
+        k = 2                                                     # 2 spp per rank keeps the single-GPU side short
+        scene.render_dev(px_ptr, sp_ptr, integrator=integrator, seed=77, spp_begin=rank * k, spp_end=(rank + 1) * k, total_spp=k * world)
+        dist.reduce(film, dst=0)
+        if rank == 0:
+            multi = film.clone()
+            scene.render_dev(px_ptr, sp_ptr, integrator=integrator, seed=77, spp_begin=0, spp_end=k * world, total_spp=k * world)
+            den = float(multi.abs().max().item())
+            diff = float((multi - film).abs().max().item())
+            film_check = {"spp_per_rank": k, "max_abs_diff": diff, "max_abs_value": den, "max_rel_diff": diff / max(den, 1e-300), "bound": 1e-12,
+                          "ok": diff <= 1e-12 * max(den, 1e-300), "checksum": float(multi.sum().item()),
+                          "what": "film accumulators of the N-rank render after the NCCL reduce vs rank 0's own render of the same %d samples per pixel (same seed)" % (k * world)}
+            del multi
+        dist.barrier()
+    if rank != 0:
+        scene.close(); del film
+        return None
+
+    # ---- rank 0 only from here: counting pass, rooflines, cpu baseline ------------------------------------------------------------
+    line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_of(name, integrator, spp, world, (W, H)),
+            "msamples_per_s": paths / (ms_total * 1e-3) / 1e6, "rays_per_sample": rays / max(paths, 1),
             "rays": {"closest_hit": closest, "occlusion": occl, "camera_paths": paths, "reference_style_cost": tot["cost"]},
-            "gpu_launches": int(launches), "clocks": clk}
-    line["kernel_ms_per_step"] = {k: v[0] / args.steps for k, v in ktimes.items()}
+            "gpu_launches": int(launches), "clocks": clk, "e2e": e2e}
+    if name == "bistro":
+        line["target"] = {"what": "BASELINE.json north_star: >= 1 Gray/s per B200 on Bistro path tracing", "mrays_per_s_per_gpu": TARGET_MRAYS, "achieved_fraction": value / world / TARGET_MRAYS}
+    if film_check is not None: line["film_check"] = film_check
+    kms = {k: v[0] / steps for k, v in ktimes.items()}
+    step_ms = ms_total / steps
+    line["kernel_ms_per_step"] = dict(kms, outside_kernel_classes=max(step_ms - sum(kms.values()), 0.0), covered_fraction=sum(kms.values()) / step_ms,
+                                      note="device time between CUDA events around each kernel class of the main pass on this rank; `outside` = the two pilot rounds of the RR threshold, memsets, queue bookkeeping, host synchronisation every 4 wave iterations")
 
-    # roofline of the dominant kernel (closest-hit trace): one untimed counting pass of the last timed step
+    # one untimed counting pass of the last timed step (visit-counting instantiations of the traversal kernels)
     ctx.count_visits(True)
     cntc, _ = scene.render_dev(px_ptr, sp_ptr, integrator=integrator, seed=seeds[-1], spp_begin=s0, spp_end=s1, total_spp=total_spp, wave_paths=args.wave_paths)
     vis_closest, vis_occl = ctx.visits()
-    occl_stats = ctx.occlusion_stats()
+    ost = ctx.occlusion_stats()
     ctx.count_visits(False)
-    # wave trace kernel per ray: 4 B slot index + 48 B ray read, 40 B hit record written
-    bytes_trace = ray_bytes(vis_closest, cntc["closest"], 92)
-    bytes_occl = ray_bytes(vis_occl, cntc["occlusion"], 60)
-    trace_ms, trace_n = ktimes["trace"][0] / args.steps, ktimes["trace"][1] / args.steps
-    occl_ms = ktimes["occlude"][0] / args.steps
     peaks = {}
     try: peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception: pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = bytes_trace / (trace_ms * 1e-3) / 1e9
-    line["roofline"] = {"bound": "hbm", "kernel": "k_wave_trace (closest-hit)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                        "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                        "algorithmic_bytes_per_launch": bytes_trace / max(trace_n, 1), "launches_per_step": trace_n, "avg_launch_ms": trace_ms / max(trace_n, 1),
-                        "bytes_per_ray": bytes_trace / max(cntc["closest"], 1), "visits_per_ray": {k: v / max(cntc["closest"], 1) for k, v in vis_closest.items()},
-                        "traffic": None, "occlusion_bvh_per_ray": {k: v / max(cntc["occlusion"], 1) for k, v in occl_stats.items()},
-                        "occlusion_kernel": {"achieved": bytes_occl / (occl_ms * 1e-3) / 1e9 if occl_ms > 0 else None, "bytes_per_ray": bytes_occl / max(cntc["occlusion"], 1)},
-                        "note": "algorithmic bytes count every node/triangle visit; a scene that fits the 126 MB L2 is served from L2/L1, so this can exceed the HBM peak (see profiles/ for dram__bytes)"}
-    try:   # dram__bytes_read.sum + dram__bytes_write.sum of that kernel from the committed `ncu --set full` capture, per launch like `achieved`
-        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
-        if tr:
-            rays_per_launch = cntc["closest"] / max(trace_n, 1)
-            line["roofline"]["traffic"] = tr["dram_bytes_per_ray"] * rays_per_launch
-            line["roofline"]["traffic_detail"] = dict(tr, rays_per_launch=rays_per_launch, note="measured DRAM bytes per ray x this run's rays per launch")
-    except Exception:
-        pass
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"
+    traffic_db = {}
+    try: traffic_db = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(name, {})
+    except Exception: pass
+    bounces = max(cntc["closest"], 1)
+    n_shadow_per_bounce = cntc["occlusion"] / bounces
+    by = {}
 
-    # e2e: public C-ABI calls with host buffers — upload the blob, render, download the film
-    if world == 1:
-        ctx.set_stream(None)
-        # host side of the call: the blob and the film buffers live in pinned host memory, as a caller that renders many frames keeps them
-        pin_blob = torch.frombuffer(bytearray(blob), dtype=torch.uint8).pin_memory()
-        pin_px = torch.empty((H, W, 4), dtype=torch.float64).pin_memory(); pin_sp = torch.empty((H, W, 3), dtype=torch.float64).pin_memory()
-        e_rays, e_t = 0.0, 0.0
-        for i in range(1 + min(args.steps, 5)):
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            sc2 = native.GpuScene(ctx, blob, host_ptr=pin_blob.data_ptr())
-            t1 = time.perf_counter()
-            px, sp, cnt2, _, dev_ms = sc2.render(integrator=integrator, spp=spp, seed=seeds[min(i, len(seeds) - 1)], wave_paths=args.wave_paths, pixels=pin_px.numpy(), splats=pin_sp.numpy())
-            t2 = time.perf_counter()
-            sc2.close()
-            dt = time.perf_counter() - t0
-            print("e2e step %d: %.1f ms wall (upload %.1f, render call %.1f of which device %.1f, iterations %d)" % (i, 1e3 * dt, 1e3 * (t1 - t0), 1e3 * (t2 - t1), dev_ms, cnt2["iterations"]), file=sys.stderr)
-            if i > 0: e_rays += cnt2["closest"] + cnt2["occlusion"]; e_t += dt
-        line["e2e"] = {"value": e_rays / e_t / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": len(blob) + 64, "d2h_bytes_per_step": W * H * 56 + 64,
-                       "what": "lumo_gpu_scene_upload (pinned host blob) + lumo_gpu_render (pinned host film buffers) + lumo_gpu_scene_destroy per step, wall clock, mean of up to 5 steps after one discarded"}
-        ctx.set_stream(stream.cuda_stream)
-    else:
-        line["e2e"] = {"value": e2e_multi, "unit": "Mrays/s", "h2d_bytes_per_step": 128, "d2h_bytes_per_step": W * H * 56,
-                       "what": "render_dev on every rank + NCCL reduce + film download on rank 0, wall clock (max over ranks); scene already resident"}
+    def entry(kernel, cls, bytes_total, units, unit_name, note):
+        ms, n = kms[cls], ktimes[cls][1] / steps
+        if ms <= 0: return None
+        ach = bytes_total / (ms * 1e-3) / 1e9
+        e = {"bound": "hbm", "kernel": kernel, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
+             "algorithmic_bytes_per_launch": bytes_total / max(n, 1), "launches_per_step": n, "avg_launch_ms": ms / max(n, 1), "ms_per_step": ms,
+             "bytes_per_" + unit_name: bytes_total / max(units, 1), "traffic": None, "note": note}
+        tr = traffic_db.get(cls)
+        if tr:   # dram__bytes_read.sum + dram__bytes_write.sum per unit from the committed `ncu --set full` capture of this workload, x this run's units per launch
+            e["traffic"] = tr["dram_bytes_per_unit"] * units / max(n, 1)
+            e["traffic_detail"] = dict(tr, units_per_launch=units / max(n, 1))
+        return e
 
-    # micro: the closest-hit kernel alone on caller-supplied batches (SURVEY 8d "micro"): 2^22 primary rays of the config
-    # camera and 2^22 incoherent rays (origins uniform in the scene bounds, directions uniform on the sphere)
-    if world == 1:
+    by["trace"] = entry("k_wave_trace (closest-hit, reference-order traversal)", "trace", ray_bytes(vis_closest, cntc["closest"], 92), cntc["closest"], "ray",
+                        "92 B ray in / hit out + 64 B per object-BVH node + 96 B per instance transform + 16 B per kd node + 4 B per leaf entry + 72 B per triangle test; counts every visit, so a scene that fits the 126 MB L2 can exceed the HBM peak")
+    if by["trace"]: by["trace"]["visits_per_ray"] = {k: v / max(cntc["closest"], 1) for k, v in vis_closest.items()}
+    by["occlude"] = entry("k_occl_bvh + k_occl_confirm + k_occl_fallback (order-free occlusion BVH, confirmed by the reference's per-object traversal)", "occlude",
+                          occl_bytes(ost, vis_occl, cntc["occlusion"]), cntc["occlusion"], "ray",
+                          "60 B shadow-queue entry + 128 B per BVH node + 8 B per leaf primitive + 72 B per triangle test + 68 B per candidate + the confirming traversal's visits")
+    if by["occlude"]: by["occlude"]["per_ray"] = {k: v / max(cntc["occlusion"], 1) for k, v in ost.items()}
+    by["shade"] = entry("k_terminal + k_scatter<K> + k_nee<K> (one bounce of the integrator)", "shade", bounces * (192 * 2 + 32 + 64) + 128.0 * cntc["occlusion"], bounces, "bounce",
+                        "SURVEY 8d: B_bounce = 2 x 192 B path state + 32 B hit record + 64 B material + 128 B per queued shadow ray (%.2f per bounce here)" % n_shadow_per_bounce)
+    by = {k: v for k, v in by.items() if v}
+    dominant = max(by, key=lambda k: by[k]["ms_per_step"]) if by else None
+    if dominant:
+        line["roofline"] = dict(by[dominant], dominant_class=dominant)
+        line["roofline_by_kernel"] = by
+    fp = env.get("fp64")
+    if fp and "roofline" in line: line["roofline"]["fp64_peak"] = fp
+
+    if not args.no_cpu:
         try:
-            line["micro"] = micro_trace(scene, dev, torch, np)
+            line["cpu_baseline"] = cpu_measure(prog, integrator, spp, args.cpu_seconds if full else min(args.cpu_seconds, 6.0))
+            line["vs_cpu"] = {"mrays_ratio_e2e": e2e["value"] / line["cpu_baseline"]["value"], "msamples_ratio": line["msamples_per_s"] / line["cpu_baseline"]["msamples_per_s"],
+                              "rays_per_sample_gpu": line["rays_per_sample"], "rays_per_sample_cpu": line["cpu_baseline"]["rays_per_sample"],
+                              "note": "same scene, same spp; rays per sample differ through the Russian-roulette threshold (per-tile pilot estimate on the GPU, per-tile running recurrence on the CPU, SURVEY A.16)"}
         except Exception as e:
-            line["micro"] = {"error": str(e)}
+            line["cpu_baseline"] = {"error": str(e)}
 
-    # film finalisation kernel (Film::rgb_image on the device): 56 B read + 3 B written per pixel, HBM bound; L2 flushed
-    # before each launch.  (i) the accumulators the timed steps left in HBM, (ii) a 3840x2160 film of the same values
-    # tiled (464 MB in, larger than L2): at (i)'s size the launch's fixed cost decides the time, (ii) shows the bandwidth
-    if world == 1:
+    if full:
+        try: line["micro"] = micro_trace(scene, dev, torch, np)
+        except Exception as e: line["micro"] = {"error": str(e)}
+        # film finalisation kernel (Film::rgb_image on the device): 56 B read + 3 B written per pixel, HBM bound; L2 flushed before each launch
         try:
             def film_ms(pp, sp_, h, w):
                 fe = []
@@ -381,33 +428,58 @@ def main():
                                    "d2h_bytes_per_pixel": 3}
         except Exception as e:
             line["film_encode"] = {"error": str(e)}
+    scene.close(); del film
+    return line
 
-    if world == 1 and not args.no_cpu:
-        threads = os.cpu_count() or 1
-        v, s, dt, ccnt = cpu_baseline(prog, integrator, threads, spp=1)
-        line["cpu_baseline"] = {"value": v, "unit": "Mrays/s", "cores": threads, "kind": "port", "msamples_per_s": s, "seconds": dt,
-                                "sample": "1 spp of the same full-resolution workload (lumo CPU path, C++ restatement with the reference tile/batch schedule; the Rust reference cannot be built offline)"}
 
-    if world == 1 and args.other_scenes:
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="bistro", choices=list(WORKLOADS))
+    ap.add_argument("--spp", type=int, default=0, help="samples per pixel per step and per GPU (0 = workload default)")
+    ap.add_argument("--wave-paths", type=int, default=0)
+    ap.add_argument("--other-workloads", default="cornell,bunny,dragon,caustics_bdpt,conference", help="comma list measured after the main workload with fewer steps ('' = none); N = 1 only")
+    ap.add_argument("--other-steps", type=int, default=2)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU work per cpu_baseline sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
+    args = ap.parse_args()
+    _guard_stdout()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    from lumo_b200 import native
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: lumo_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    ctx = native.GpuContext(local)
+    env = {"torch": torch, "np": np, "native": native, "dist": dist, "world": world, "rank": rank, "local": local, "dev": dev, "ctx": ctx,
+           "stream": torch.cuda.current_stream(), "flush": torch.empty(256 << 20, dtype=torch.uint8, device=dev)}
+    if rank == 0:
+        try: env["fp64"] = ctx.fp64_peak()
+        except Exception as e: env["fp64"] = {"error": str(e)}
+    line = measure(args.workload, args, env, args.steps, max(args.warmup, 3) if args.warmup >= 3 else args.warmup, full=True)
+    if rank == 0 and world == 1 and args.other_workloads:
         others = {}
-        for name in [n for n in args.other_scenes.split(",") if n and n != args.workload]:
+        for name in [n for n in args.other_workloads.split(",") if n and n != args.workload]:
             try:
-                p2, b2, ig2, spp2 = build_workload(name)
-                sc2 = native.GpuScene(ctx, b2)
-                f2 = torch.zeros(sc2.res_x * sc2.res_y * 7, dtype=torch.float64, device=dev)
-                for k in range(2):
-                    flush.zero_()
-                    cnt2, ms2 = sc2.render_dev(f2.data_ptr(), f2.data_ptr() + sc2.res_x * sc2.res_y * 32, integrator=ig2, seed=5 + k, spp=spp2)
-                kt = ctx.kernel_times()
-                others[name] = {"mrays_per_s": (cnt2["closest"] + cnt2["occlusion"]) / ms2 / 1e3, "msamples_per_s": cnt2["camera_paths"] / ms2 / 1e3, "ms": ms2, "spp": spp2,
-                                "resolution": [sc2.res_x, sc2.res_y], "kernel_ms": {k: v[0] for k, v in kt.items()}, "description": DESCR[name]}
-                sc2.close(); del f2
+                others[name] = measure(name, args, env, max(1, args.other_steps), 3, full=False)
             except Exception as e:   # a failed side measurement must not lose the main line
                 others[name] = {"error": str(e)}
-        line["other_scenes"] = others
-
-    print(json.dumps(line), file=_guard_stdout(), flush=True)
-    scene.close(); ctx.close()
+        line["other_workloads"] = others
+    if rank == 0:
+        print(json.dumps(line), file=_guard_stdout(), flush=True)
+    ctx.close()
     if dist is not None:
         dist.barrier(); dist.destroy_process_group()
     return 0

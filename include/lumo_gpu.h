@@ -144,10 +144,11 @@ int32_t lumo_gpu_ctx_visits(lumo_ctx* ctx, uint64_t* out12);   /* 6 for the clos
 /* Shadow rays are answered from an order-free occlusion BVH and confirmed by the reference's own per-object traversal
  * (csrc/gpu/occlude.cuh).  mode 0: that (default); 1: the reference's object BVH + kd-tree traversal for shadow rays too;
  * 2: both on every shadow ray of a render, disagreements counted in stats[7].  stats: [0] BVH nodes, [1] leaf primitives,
- * [2] triangle tests, [3] sphere tests, [4] candidates, [5] confirmed, [6] sent to the faithful kernel (0..6 only while
- * visit counting is on), [7] disagreements.  Reset by lumo_gpu_ctx_count_visits. */
+ * [2] triangle tests, [3] sphere tests, [4] candidates sent to the confirmation pass, [5] confirmed, [6] sent to the faithful
+ * kernel, [8] blockers accepted as robust without confirmation (all only while visit counting is on), [7] disagreements.
+ * stats has NINE entries.  Reset by lumo_gpu_ctx_count_visits. */
 int32_t lumo_gpu_ctx_occlusion_mode(lumo_ctx* ctx, int32_t mode);
-int32_t lumo_gpu_ctx_occlusion_stats(lumo_ctx* ctx, uint64_t* stats8);
+int32_t lumo_gpu_ctx_occlusion_stats(lumo_ctx* ctx, uint64_t* stats9);
 /* Device time (ms, CUDA events on the launching stream) and launch count per kernel class of the last
  * lumo_gpu_render*: [0] regen (film + refill + compaction), [1] closest-hit trace, [2] shade, [3] occlusion trace. */
 int32_t lumo_gpu_ctx_kernel_times(lumo_ctx* ctx, double* ms4, uint64_t* launches4);
@@ -157,6 +158,10 @@ int32_t lumo_gpu_ctx_iter_log(lumo_ctx* ctx, uint32_t* out, uint32_t cap, uint32
 /* Device-resident variants used by bench.py's kernel-only timing (inputs already in HBM). */
 int32_t lumo_gpu_trace_closest_dev(lumo_scene* scene, const double* origin_dev, const double* dir_dev, uint64_t n,
                                    uint32_t* obj_dev, uint32_t* tri_dev, double* t_dev, double* bary_dev, float* kernel_ms);
+
+/* The FP64 issue ceiling of the context's GPU, measured: eight independent DFMA chains per thread over a full grid; TFLOP/s
+ * (2 flops per DFMA), best of three launches, and that launch's time.  bench.py reports it as roofline.fp64_peak. */
+int32_t lumo_gpu_fp64_peak(lumo_ctx* ctx, double* tflops, double* ms);
 
 /* Parity hook: evaluates csrc/common/lumo_math.h (the FMA-free sin / cos / atan2 / acos / atanh / cosh / exp / log / pow every side
  * of the path shares) on the device.  fn: 0 sin, 1 cos, 2 atan2(x, y), 3 acos, 4 atanh, 5 cosh, 6 exp, 7 log, 8 pow(x, y); y may be

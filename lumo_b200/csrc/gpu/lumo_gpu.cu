@@ -129,15 +129,16 @@ extern "C" int32_t lumo_gpu_ctx_count_visits(lumo_ctx* ctx, int32_t enable) {
     return LUMO_OK;
 }
 // Counters of the occlusion-BVH kernels (occlude.cuh) since the last lumo_gpu_ctx_count_visits call: [0] BVH nodes visited,
-// [1] leaf primitives fetched, [2] f64 triangle tests, [3] sphere tests, [4] candidate blockers, [5] confirmed by the
-// reference's per-object traversal, [6] rays sent to the faithful kernel — all only while visit counting is on — and
-// [7] rays on which the occlusion BVH and the faithful kernel disagreed (LUMO_OCCLUDE_CHECK=1 renders; must stay 0).
-extern "C" int32_t lumo_gpu_ctx_occlusion_stats(lumo_ctx* ctx, uint64_t* out8) {
+// [1] leaf primitives fetched, [2] f64 triangle tests, [3] sphere tests, [4] candidate blockers sent to the confirmation
+// pass, [5] confirmed by the reference's per-object traversal, [6] rays sent to the faithful kernel, [8] blockers accepted
+// as robust without confirmation — all only while visit counting is on — and [7] rays on which the occlusion BVH and the
+// faithful kernel disagreed (LUMO_OCCLUDE_CHECK=1 renders; must stay 0).
+extern "C" int32_t lumo_gpu_ctx_occlusion_stats(lumo_ctx* ctx, uint64_t* out8) {   // nine values
     if (!ctx || !out8) return fail(LUMO_ERR_INVALID, "occlusion_stats: null pointer");
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
     AhCounters c; CU(cudaMemcpy(&c, ctx->d_ah, sizeof c, cudaMemcpyDeviceToHost));
-    out8[0] = c.nodes; out8[1] = c.prims; out8[2] = c.tris; out8[3] = c.spheres; out8[4] = c.candidates; out8[5] = c.confirmed; out8[6] = c.fallback; out8[7] = c.mismatches;
+    out8[0] = c.nodes; out8[1] = c.prims; out8[2] = c.tris; out8[3] = c.spheres; out8[4] = c.candidates; out8[5] = c.confirmed; out8[6] = c.fallback; out8[7] = c.mismatches; out8[8] = c.robust;
     return LUMO_OK;
 }
 // Overrides the LUMO_OCCLUDE_FAITHFUL / LUMO_OCCLUDE_CHECK environment switches of this context: mode 0 = occlusion BVH
@@ -203,6 +204,39 @@ extern "C" int32_t lumo_gpu_math_eval(lumo_ctx* ctx, int32_t fn, const double* x
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (dx) cudaFree(dx); if (dy) cudaFree(dy); if (dout) cudaFree(dout);
     if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? LUMO_ERR_OOM : LUMO_ERR_CUDA, std::string("math_eval: ") + cudaGetErrorString(e));
+    return LUMO_OK;
+}
+
+// FP64 issue ceiling of this GPU (SURVEY 8d asks for it next to the bandwidth roofline: every kernel of the path computes
+// in f64): eight independent DFMA chains per thread, 2048 resident threads per SM.  Returns TFLOP/s (2 flops per DFMA).
+__global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters) {
+    double a0 = 1e-9 * threadIdx.x, a1 = a0 + 1.0, a2 = a0 + 2.0, a3 = a0 + 3.0, a4 = a0 + 4.0, a5 = a0 + 5.0, a6 = a0 + 6.0, a7 = a0 + 7.0;
+    const double b = 0.99999999, c = 1e-9;
+#pragma unroll 4
+    for (int i = 0; i < iters; i++) {
+        a0 = __fma_rn(a0, b, c); a1 = __fma_rn(a1, b, c); a2 = __fma_rn(a2, b, c); a3 = __fma_rn(a3, b, c);
+        a4 = __fma_rn(a4, b, c); a5 = __fma_rn(a5, b, c); a6 = __fma_rn(a6, b, c); a7 = __fma_rn(a7, b, c);
+    }
+    const double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (s == -1.0) out[0] = s;   // never true; keeps the chains alive
+}
+extern "C" int32_t lumo_gpu_fp64_peak(lumo_ctx* ctx, double* tflops, double* ms_out) {
+    if (!ctx || !tflops) return fail(LUMO_ERR_INVALID, "fp64_peak: null pointer");
+    CU(cudaSetDevice(ctx->device));
+    const int iters = 8192, grid = ctx->sm_count * 8;
+    double best = 0.0, best_ms = 0.0;
+    for (int rep = 0; rep < 4; rep++) {
+        CU(cudaEventRecord(ctx->ev0, ctx->stream));
+        k_fp64_peak<<<grid, 256, 0, ctx->stream>>>((double*)ctx->d_cursor, iters);
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(ctx->ev1, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        float ms = 0; CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        const double tf = 2.0 * 8.0 * (double)iters * (double)grid * 256.0 / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) { best = tf; best_ms = ms; }
+        ctx->launches++;
+    }
+    *tflops = best; if (ms_out) *ms_out = best_ms;
     return LUMO_OK;
 }
 
@@ -467,6 +501,10 @@ static void carve_wave(Wave& W, Carver& c, uint32_t N, uint32_t shadow_cap, uint
     W.sox = c.take<double>(C); W.soy = c.take<double>(C); W.soz = c.take<double>(C); W.sdx = c.take<double>(C); W.sdy = c.take<double>(C); W.sdz = c.take<double>(C);
     W.stmax = c.take<double>(C); W.sc = c.take<double>(4 * C); W.sslot = c.take<uint32_t>(C);
     W.oq_i = c.take<uint32_t>(C); W.oq_obj = c.take<uint32_t>(C); W.oq_fb = c.take<uint32_t>(C); W.occ_record = c.take<uint8_t>(C);
+    W.nee_ctx = c.take<double>((size_t)LUMO_NEE_CTX_DOUBLES * N); W.nee_meta = c.take<uint32_t>(N);
+    { NeeTermQueue& T = W.tq; T.ox = c.take<double>(C); T.oy = c.take<double>(C); T.oz = c.take<double>(C); T.dx = c.take<double>(C); T.dy = c.take<double>(C); T.dz = c.take<double>(C);
+      T.wx = c.take<double>(C); T.wy = c.take<double>(C); T.wz = c.take<double>(C); T.tmax = c.take<double>(C); T.p_lig = c.take<double>(C); T.pdf_light = c.take<double>(C);
+      T.le = c.take<double>(4 * C); T.slot = c.take<uint32_t>(C); }
     W.it = c.take<IterCounters>(1); W.run = c.take<RunCounters>(1); W.qc = c.take<QueueCounters>(1);
     W.tile_delta = c.take<double>(n_tiles); W.tile_delta_next = c.take<double>(n_tiles);
     W.pilot_lum = c.take<double>((size_t)n_tiles * LUMO_PILOT_N); W.pilot_cost = c.take<uint32_t>((size_t)n_tiles * LUMO_PILOT_N);
@@ -479,14 +517,20 @@ struct HostCounters { QueueCounters qc; RunCounters run; };
 template <int K>
 static void launch_shade_kind(lumo_scene* sc, const Wave& W, const WaveParams& P, int grid, int nee_grid, cudaStream_t st, unsigned long long& launches) {
     if (!(sc->kind_mask & (1u << K))) return;
+    // no LumoTexture record in the scene: the texture-free instantiations (shade.cuh LUMO_K_SOLID)
     if (sc->has_textures) {
         k_scatter<K><<<grid, 128, 0, st>>>(sc->S, W, P);
-        k_nee<K><<<nee_grid, 128, 0, st>>>(sc->S, W, P);
-    } else {                                         // no LumoTexture record in the scene: the texture-free instantiations (shade.cuh LUMO_K_SOLID)
+        k_nee_a<true><<<nee_grid, 128, 0, st>>>(sc->S, W, P, (uint32_t)K);
+        k_nee_b<K><<<nee_grid, 128, 0, st>>>(sc->S, W, P);
+        k_nee_eval<K><<<nee_grid, 128, 0, st>>>(sc->S, W, P);
+    } else {
         k_scatter<K | LUMO_K_SOLID><<<grid, 128, 0, st>>>(sc->S, W, P);
-        k_nee<K | LUMO_K_SOLID><<<nee_grid, 128, 0, st>>>(sc->S, W, P);
+        k_nee_a<false><<<nee_grid, 128, 0, st>>>(sc->S, W, P, (uint32_t)K);
+        k_nee_b<K | LUMO_K_SOLID><<<nee_grid, 128, 0, st>>>(sc->S, W, P);
+        k_nee_eval<K | LUMO_K_SOLID><<<nee_grid, 128, 0, st>>>(sc->S, W, P);
     }
-    launches += 2;
+    k_terms_reset<<<1, 1, 0, st>>>(W.it);
+    launches += 5;
 }
 
 // Runs waves until the work counter is exhausted and no path is alive.
@@ -497,7 +541,7 @@ static int32_t run_wave(lumo_scene* sc, const Wave& W, WaveParams P, uint64_t& i
     const int tgrid = ctx->sm_count * LUMO_WAVE_TRACE_BLOCKS;   // persistent warps: one grid of resident CTAs
     const int rgrid = (int)std::min<uint64_t>((W.n_slots + 255) / 256, (uint64_t)ctx->sm_count * 16);
     const int sgrid = ctx->sm_count * 16;
-    const int ngrid = (int)std::min<uint64_t>(((uint64_t)W.n_slots + 127) / 128, (uint64_t)ctx->sm_count * 32);
+    const int ngrid = (int)std::min<uint64_t>(((uint64_t)W.n_slots * sc->S.P.n_shadow_rays + 127) / 128, (uint64_t)ctx->sm_count * 32);
     CU(cudaMemsetAsync(W.flags, 0, (size_t)W.n_slots * 4, st));
     CU(cudaMemsetAsync(&W.run->next_work, 0, 8, st));
     // every slot starts out free: the first k_retire finds all of them in done[1] (no PF_DONE flag -> nothing to film)

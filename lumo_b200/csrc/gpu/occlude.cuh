@@ -9,7 +9,9 @@
 //      rounding-error bounds), so no primitive the ray can hit is skipped;
 //   2. a primitive that survives is tested with the reference's own f64 routine in its object's frame
 //      (Triangle::hit_t = tri_hit<false>, Sphere::hit_t) — that only nominates a candidate object;
-//   3. k_occl_confirm then runs what the reference would have run for that object: the box tests of the object-BVH nodes
+//   3. a candidate whose hit point lies well inside its triangle's bounding box is a blocker for the reference as well
+//      (ah_hit_is_robust gives the argument); for every other candidate k_occl_confirm runs what the reference would have run
+//      for that object: the box tests of the object-BVH nodes
 //      above it (bvh.rs:333-335, with tt = t_max as in the any-hit pass) and Object::hit_t through the object's own
 //      kd-tree (kdtree.rs:101-169, cell clipping included).  Occluded is reported only if that says so;
 //   4. a ray whose candidate is not confirmed (the cell clipping or a box test disagreed by an ulp), or whose traversal
@@ -23,7 +25,7 @@ namespace lumo_dev {
 
 #define LUMO_AH_STACK 48
 
-struct AhCounters { unsigned long long nodes, prims, tris, spheres, candidates, confirmed, fallback, mismatches; };
+struct AhCounters { unsigned long long nodes, prims, tris, spheres, candidates, confirmed, fallback, mismatches, robust; };
 
 // f32 side of a ray for the slab tests.  t = fma(plane, inv, -(o * inv)) with absolute slack s = |o * inv| * 2^-22 folded
 // into the two constants (near planes: t - s, far planes: t + s) and a relative slack of 2^-20 at the comparison:
@@ -75,89 +77,103 @@ __device__ __forceinline__ void ah_local_load(const AhLocal& L, Ray& r, RayTri& 
 }
 #define LUMO_AH_LOCAL_DOUBLES 11
 
-// Walks the occlusion BVH.  Returns 0: nothing the ray could hit, 1: candidate blocker (cand = global object index),
-// 2: traversal stack overflow (the caller sends the ray to the faithful kernel).
+// One step through an inner node: the four slab tests; the hit child that starts first is walked next, the others go on
+// the stack.  Returns false when nothing is left to walk (no hit child and an empty stack).  over: the stack was full.
 template <bool CNT>
-__device__ __forceinline__ int ah_any_hit(const DevScene& S, const Ray& ray, const RayTri& q, double t_max, AhLocal& L, uint32_t& cand, AhCounters* c) {
-    const AhRay a = ah_make_ray(ray, t_max);
-    uint32_t stack[LUMO_AH_STACK];
-    int sp = 0;
-    uint32_t node = 0;                       // the root is always an inner node (ah_bvh.h: collapse)
-    for (;;) {
-        // ---- inner nodes: test the four child boxes, continue into one hit child, push the others ----
-        while (!(node & LUMO_AH_LEAF)) {
-            if (CNT) c->nodes++;
-            const float4* n4 = reinterpret_cast<const float4*>(S.ah_nodes + node);
-            const float4 ax = __ldg(n4 + a.ox), bx = __ldg(n4 + 3 - a.ox);
-            const float4 ay = __ldg(n4 + 1 + a.oy), by = __ldg(n4 + 4 - a.oy);
-            const float4 az = __ldg(n4 + 2 + a.oz), bz = __ldg(n4 + 5 - a.oz);
-            const uint4 ch = __ldg(reinterpret_cast<const uint4*>(n4 + 6));
-            // entry distances (biased early) and exit distances (biased late) of the four children
-            const float n0 = fmaxf(fmaxf(__fmaf_rn(ax.x, a.ix, a.nx), __fmaf_rn(ay.x, a.iy, a.ny)), fmaxf(__fmaf_rn(az.x, a.iz, a.nz), 0.0f));
-            const float n1 = fmaxf(fmaxf(__fmaf_rn(ax.y, a.ix, a.nx), __fmaf_rn(ay.y, a.iy, a.ny)), fmaxf(__fmaf_rn(az.y, a.iz, a.nz), 0.0f));
-            const float n2 = fmaxf(fmaxf(__fmaf_rn(ax.z, a.ix, a.nx), __fmaf_rn(ay.z, a.iy, a.ny)), fmaxf(__fmaf_rn(az.z, a.iz, a.nz), 0.0f));
-            const float n3 = fmaxf(fmaxf(__fmaf_rn(ax.w, a.ix, a.nx), __fmaf_rn(ay.w, a.iy, a.ny)), fmaxf(__fmaf_rn(az.w, a.iz, a.nz), 0.0f));
-            const float f0 = fminf(fminf(__fmaf_rn(bx.x, a.ix, a.fx), __fmaf_rn(by.x, a.iy, a.fy)), fminf(__fmaf_rn(bz.x, a.iz, a.fz), a.tmax));
-            const float f1 = fminf(fminf(__fmaf_rn(bx.y, a.ix, a.fx), __fmaf_rn(by.y, a.iy, a.fy)), fminf(__fmaf_rn(bz.y, a.iz, a.fz), a.tmax));
-            const float f2 = fminf(fminf(__fmaf_rn(bx.z, a.ix, a.fx), __fmaf_rn(by.z, a.iy, a.fy)), fminf(__fmaf_rn(bz.z, a.iz, a.fz), a.tmax));
-            const float f3 = fminf(fminf(__fmaf_rn(bx.w, a.ix, a.fx), __fmaf_rn(by.w, a.iy, a.fy)), fminf(__fmaf_rn(bz.w, a.iz, a.fz), a.tmax));
-            const float rel = 1.00000095367431640625f;   // 1 + 2^-20
-            const bool h0 = n0 <= f0 * rel, h1 = n1 <= f1 * rel, h2 = n2 <= f2 * rel, h3 = n3 <= f3 * rel;
-            // the hit child that starts first is walked next (a blocker is most likely found near the origin), the others wait on the stack
-            uint32_t next = LUMO_NONE; float best = 0.0f;
-            bool over = false;
-#define LUMO_AH_TAKE(h, n, c)                                                                                       \
-            if (h) {                                                                                                \
-                if (next == LUMO_NONE) { next = c; best = n; }                                                      \
-                else if (sp >= LUMO_AH_STACK) over = true;                                                          \
-                else if (n < best) { stack[sp++] = next; next = c; best = n; }                                      \
-                else stack[sp++] = c;                                                                               \
-            }
-            LUMO_AH_TAKE(h0, n0, ch.x) LUMO_AH_TAKE(h1, n1, ch.y) LUMO_AH_TAKE(h2, n2, ch.z) LUMO_AH_TAKE(h3, n3, ch.w)
-#undef LUMO_AH_TAKE
-            if (over) return 2;
-            if (next == LUMO_NONE) { if (sp == 0) return 0; next = stack[--sp]; }
-            node = next;
-        }
-        // ---- leaf: the reference's own tests, in the primitive's object frame ----
-        const uint32_t first = node & 0x07FFFFFFu, count = ((node >> 27) & 0xFu) + 1u;
-        for (uint32_t k = 0; k < count; k++) {
-            const uint2 pr = __ldg(reinterpret_cast<const uint2*>(S.ah_prims + first + k));
-            if (CNT) c->prims++;
-            const uint32_t obj = pr.y & ~LUMO_AH_INSTANCED;
-            double t;
-            if (pr.x & LUMO_AH_SPHERE) {
-                // Sphere::hit_t needs the ray in the sphere's frame but none of the triangle constants.  An enclosing sphere (the
-                // environment light) is met by every ray: when origin and end point of the segment are both inside the ball by a
-                // wide margin, the exit distance t1 is beyond t_max and the quadratic of sphere.rs:77-96 returns "no hit" — decided
-                // here without the square root and the two divisions.
-                if (CNT) c->spheres++;
-                const double radius = S.spheres[pr.x & ~LUMO_AH_SPHERE].radius;
-                const Ray lr = (pr.y & LUMO_AH_INSTANCED) ? to_local<false>(S, S.objects[obj], ray, nullptr) : ray;
-                const double qa = dot(lr.d, lr.d), qb = 2.0 * dot(lr.d, lr.o), qo = dot(lr.o, lr.o), r2 = radius * radius;
-                const double f_end = (qa * t_max) * t_max + qb * t_max + (qo - r2);
-                const double scale = fabs(qa * t_max * t_max) + fabs(qb * t_max) + qo + r2;
-                if (qo - r2 < -1e-9 * (qo + r2) && f_end < -1e-9 * scale) t = LUMO_INF;
-                else t = sphere_hit_t(radius, lr, 0.0, t_max);
-            } else {
-                if (CNT) c->tris++;
-                Ray lr = ray; RayTri lq = q;
-                if (pr.y & LUMO_AH_INSTANCED) {
-                    const int inst = S.objects[obj].inst;
-                    if (inst != L.cur) {
-                        RayCtx lc; make_ctx(to_local<false>(S, S.objects[obj], ray, nullptr), lc);
-                        ah_local_store(L, lc); L.cur = inst;
-                    }
-                    ah_local_load(L, lr, lq);
-                }
-                TriHit th;
-                t = tri_hit<false, false>(S.tri_verts + pr.x, lr, lq, 0.0, t_max, th, nullptr) ? th.t : LUMO_INF;
-            }
-            if (t < t_max) { cand = obj; return 1; }
-        }
-        if (sp == 0) return 0;
-        node = stack[--sp];
+__device__ __forceinline__ bool ah_node_step(const DevScene& S, const AhRay& a, uint32_t& node, uint32_t* stack, int& sp, bool& over, AhCounters* c) {
+    if (CNT) c->nodes++;
+    const float4* n4 = reinterpret_cast<const float4*>(S.ah_nodes + node);
+    const float4 ax = __ldg(n4 + a.ox), bx = __ldg(n4 + 3 - a.ox);
+    const float4 ay = __ldg(n4 + 1 + a.oy), by = __ldg(n4 + 4 - a.oy);
+    const float4 az = __ldg(n4 + 2 + a.oz), bz = __ldg(n4 + 5 - a.oz);
+    const uint4 ch = __ldg(reinterpret_cast<const uint4*>(n4 + 6));
+    // entry distances (biased early) and exit distances (biased late) of the four children
+    const float n0 = fmaxf(fmaxf(__fmaf_rn(ax.x, a.ix, a.nx), __fmaf_rn(ay.x, a.iy, a.ny)), fmaxf(__fmaf_rn(az.x, a.iz, a.nz), 0.0f));
+    const float n1 = fmaxf(fmaxf(__fmaf_rn(ax.y, a.ix, a.nx), __fmaf_rn(ay.y, a.iy, a.ny)), fmaxf(__fmaf_rn(az.y, a.iz, a.nz), 0.0f));
+    const float n2 = fmaxf(fmaxf(__fmaf_rn(ax.z, a.ix, a.nx), __fmaf_rn(ay.z, a.iy, a.ny)), fmaxf(__fmaf_rn(az.z, a.iz, a.nz), 0.0f));
+    const float n3 = fmaxf(fmaxf(__fmaf_rn(ax.w, a.ix, a.nx), __fmaf_rn(ay.w, a.iy, a.ny)), fmaxf(__fmaf_rn(az.w, a.iz, a.nz), 0.0f));
+    const float f0 = fminf(fminf(__fmaf_rn(bx.x, a.ix, a.fx), __fmaf_rn(by.x, a.iy, a.fy)), fminf(__fmaf_rn(bz.x, a.iz, a.fz), a.tmax));
+    const float f1 = fminf(fminf(__fmaf_rn(bx.y, a.ix, a.fx), __fmaf_rn(by.y, a.iy, a.fy)), fminf(__fmaf_rn(bz.y, a.iz, a.fz), a.tmax));
+    const float f2 = fminf(fminf(__fmaf_rn(bx.z, a.ix, a.fx), __fmaf_rn(by.z, a.iy, a.fy)), fminf(__fmaf_rn(bz.z, a.iz, a.fz), a.tmax));
+    const float f3 = fminf(fminf(__fmaf_rn(bx.w, a.ix, a.fx), __fmaf_rn(by.w, a.iy, a.fy)), fminf(__fmaf_rn(bz.w, a.iz, a.fz), a.tmax));
+    const float rel = 1.00000095367431640625f;   // 1 + 2^-20
+    // (an empty child has an inverted infinite box, which fails the test by itself — except for garbage rays whose 1/d is 0 or NaN)
+    const bool h0 = n0 <= f0 * rel && ch.x != LUMO_NONE, h1 = n1 <= f1 * rel && ch.y != LUMO_NONE, h2 = n2 <= f2 * rel && ch.z != LUMO_NONE, h3 = n3 <= f3 * rel && ch.w != LUMO_NONE;
+    uint32_t next = LUMO_NONE; float best = 0.0f;
+#define LUMO_AH_TAKE(h, n, c)                                                                           \
+    if (h) {                                                                                            \
+        if (next == LUMO_NONE) { next = c; best = n; }                                                  \
+        else if (sp >= LUMO_AH_STACK) over = true;                                                      \
+        else if (n < best) { stack[sp++] = next; next = c; best = n; }                                  \
+        else stack[sp++] = c;                                                                           \
     }
+    LUMO_AH_TAKE(h0, n0, ch.x) LUMO_AH_TAKE(h1, n1, ch.y) LUMO_AH_TAKE(h2, n2, ch.z) LUMO_AH_TAKE(h3, n3, ch.w)
+#undef LUMO_AH_TAKE
+    if (next == LUMO_NONE) { if (sp == 0) return false; next = stack[--sp]; }
+    node = next;
+    return true;
+}
+
+// A hit found through the occlusion BVH is *robust* when the hit point lies inside the triangle's own bounding box with a
+// margin of 1e-9 (relative) on every axis.  Then the reference's traversal of this object is certain to report a blocker too,
+// and the confirmation pass is skipped:
+//   * every box above the triangle (its kd-tree's root box, the object-BVH nodes over the object) contains the triangle's
+//     box, so the ray is inside each of them around t by the same margin — their slab tests (aabb.rs:33-44, rounding
+//     errors of a few 1e-16) pass, and t lies inside the kd root interval;
+//   * lumo's kd build lists a triangle in every leaf whose cell its box overlaps (kdtree/node.rs:198-230; checked on the
+//     blob by tests/test_host_build.py).  Any split plane the walk's rounding could put on the wrong side of the hit is
+//     within ~1e-15 of the hit point, hence cuts the triangle's box, hence both cells list the triangle: the front-to-back
+//     walk (kdtree.rs:117-160) meets it in a cell whose exit is beyond t — unless it returns earlier with another hit,
+//     which is a blocker just the same.  The distance itself is the same arithmetic (Triangle::hit_t) in both places.
+// Axis-aligned triangles (zero-thickness boxes: walls, rectangles) and hits within the margin of a box face are not
+// robust; they take the confirmation pass, which replays the reference's traversal of the object.
+__device__ __forceinline__ bool ah_hit_is_robust(const LumoTriVerts* tv, const Ray& lr, double t) {
+    D3 A, B, C; load_tri(tv, A, B, C);
+    const D3 p = lr.o + t * lr.d;
+    const D3 lo = d3(fmin(A.x, fmin(B.x, C.x)), fmin(A.y, fmin(B.y, C.y)), fmin(A.z, fmin(B.z, C.z)));
+    const D3 hi = d3(fmax(A.x, fmax(B.x, C.x)), fmax(A.y, fmax(B.y, C.y)), fmax(A.z, fmax(B.z, C.z)));
+    const double k = 1e-9;
+    const double mx = k * (fmax(fabs(lo.x), fabs(hi.x)) + fabs(lr.o.x)) + 1e-300, my = k * (fmax(fabs(lo.y), fabs(hi.y)) + fabs(lr.o.y)) + 1e-300,
+                 mz = k * (fmax(fabs(lo.z), fabs(hi.z)) + fabs(lr.o.z)) + 1e-300;
+    return p.x > lo.x + mx && p.x < hi.x - mx && p.y > lo.y + my && p.y < hi.y - my && p.z > lo.z + mz && p.z < hi.z - mz && t > k * fabs(t) + 1e-300;
+}
+
+// One leaf primitive: the reference's own f64 test in the primitive's object frame.  Returns the hit distance or +inf;
+// robust: see ah_hit_is_robust (spheres never are).
+template <bool CNT>
+__device__ __forceinline__ double ah_prim_test(const DevScene& S, uint32_t prim, const Ray& ray, const RayTri& q, double t_max, AhLocal& L, uint32_t& obj, bool& robust, AhCounters* c) {
+    const uint2 pr = __ldg(reinterpret_cast<const uint2*>(S.ah_prims + prim));
+    if (CNT) c->prims++;
+    robust = false;
+    obj = pr.y & ~LUMO_AH_INSTANCED;
+    if (pr.x & LUMO_AH_SPHERE) {
+        // Sphere::hit_t needs the ray in the sphere's frame but none of the triangle constants.  An enclosing sphere (the
+        // environment light) is met by every ray: when origin and end point of the segment are both inside the ball by a
+        // wide margin, the exit distance t1 is beyond t_max and the quadratic of sphere.rs:77-96 returns "no hit" — decided
+        // here without the square root and the two divisions.
+        if (CNT) c->spheres++;
+        const double radius = S.spheres[pr.x & ~LUMO_AH_SPHERE].radius;
+        const Ray lr = (pr.y & LUMO_AH_INSTANCED) ? to_local<false>(S, S.objects[obj], ray, nullptr) : ray;
+        const double qa = dot(lr.d, lr.d), qb = 2.0 * dot(lr.d, lr.o), qo = dot(lr.o, lr.o), r2 = radius * radius;
+        const double f_end = (qa * t_max) * t_max + qb * t_max + (qo - r2);
+        const double scale = fabs(qa * t_max * t_max) + fabs(qb * t_max) + qo + r2;
+        if (qo - r2 < -1e-9 * (qo + r2) && f_end < -1e-9 * scale) return LUMO_INF;
+        return sphere_hit_t(radius, lr, 0.0, t_max);
+    }
+    if (CNT) c->tris++;
+    Ray lr = ray; RayTri lq = q;
+    if (pr.y & LUMO_AH_INSTANCED) {
+        const int inst = S.objects[obj].inst;
+        if (inst != L.cur) {
+            RayCtx lc; make_ctx(to_local<false>(S, S.objects[obj], ray, nullptr), lc);
+            ah_local_store(L, lc); L.cur = inst;
+        }
+        ah_local_load(L, lr, lq);
+    }
+    TriHit th;
+    if (!tri_hit<false, false>(S.tri_verts + pr.x, lr, lq, 0.0, t_max, th, nullptr)) return LUMO_INF;
+    if (th.t < t_max) robust = ah_hit_is_robust(S.tri_verts + pr.x, lr, th.t);
+    return th.t;
 }
 
 // The reference's verdict on ONE object for an any-hit query: every object-BVH node above it must pass the box test of
@@ -184,34 +200,78 @@ struct OcclQueues {
     uint32_t* counters;   // [0] work cursor of k_occl_bvh, [1] confirm queue size, [2] fallback queue size, [3] confirm cursor, [4] fallback cursor
 };
 
+// The walk itself.  Rays differ a lot in how far they get (a blocked ray stops at its first hit, a free one walks on to the
+// light), so a warp that took 32 rays and waited for the slowest ran at ~6 of 32 lanes (ncu, profiles/).  Here a lane
+// whose ray is finished takes the next ray of the queue while the others continue (lanes are refilled once LUMO_AH_REFILL
+// of them are free), and the lanes of a warp alternate between the two kinds of work together: up to LUMO_AH_NODE_ROUND
+// inner-node steps, then one leaf primitive for every lane that holds one.
+#ifndef LUMO_AH_REFILL
+#define LUMO_AH_REFILL 8
+#endif
+#ifndef LUMO_AH_NODE_ROUND
+#define LUMO_AH_NODE_ROUND 3
+#endif
 template <bool CNT, class Source, class Sink>
 __global__ void __launch_bounds__(128, 4) k_occl_bvh(const __grid_constant__ DevScene S, const Source src, const Sink sink, const OcclQueues Q, AhCounters* gc) {
     __shared__ double local_ctx[LUMO_AH_LOCAL_DOUBLES * 128];
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t n = src.n();
-    AhCounters cnt = {0, 0, 0, 0, 0, 0, 0, 0};
-    AhLocal L; L.slot = local_ctx + threadIdx.x; L.stride = 128;
+    AhCounters cnt = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    AhLocal L; L.slot = local_ctx + threadIdx.x; L.stride = 128; L.cur = -1;
+    uint32_t stack[LUMO_AH_STACK];
+    // per-lane state of the ray in flight
+    bool active = false, exhausted = false;
+    uint32_t i = 0, node = 0, leaf_pos = 0, leaf_end = 0;
+    int sp = 0;
+    Ray r; RayTri q; double t_max = 0.0; AhRay a;
+    r.o = d3(0, 0, 0); r.d = d3(0, 0, 1); q = ray_tri_setup(r); a = ah_make_ray(r, 0.0);
     for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&Q.counters[0], 32u);
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (base >= n) break;
-        const uint32_t i = base + lane;
-        int verdict = -1; uint32_t cand = 0;
-        if (i < n) {
-            Ray r; double t_max; src.load(i, r, t_max);
-            const RayTri q = ray_tri_setup(r);
-            L.cur = -1;
-            verdict = ah_any_hit<CNT>(S, r, q, t_max, L, cand, &cnt);
-            if (verdict == 0) sink.verdict(i, false);
+        // ---- refill: free lanes take the next rays of the queue (one atomic per warp) ----
+        const uint32_t free_m = __ballot_sync(0xFFFFFFFFu, !active && !exhausted);
+        const uint32_t busy_m = __ballot_sync(0xFFFFFFFFu, active);
+        if (free_m && ((uint32_t)__popc(free_m) >= LUMO_AH_REFILL || busy_m == 0u)) {
+            uint32_t base = 0;
+            if (lane == (uint32_t)(__ffs(free_m) - 1)) base = atomicAdd(&Q.counters[0], (uint32_t)__popc(free_m));
+            base = __shfl_sync(0xFFFFFFFFu, base, __ffs(free_m) - 1);
+            if (!active && !exhausted) {
+                i = base + __popc(free_m & ((1u << lane) - 1u));
+                if (i < n) {
+                    src.load(i, r, t_max);
+                    q = ray_tri_setup(r); a = ah_make_ray(r, t_max);
+                    L.cur = -1; node = 0; sp = 0; leaf_pos = leaf_end = 0; active = true;      // node 0: the root is always an inner node
+                } else exhausted = true;
+            }
+        } else if (busy_m == 0u) break;            // nothing in flight and nothing left to take
+        // ---- inner nodes ----
+        int verdict = -1;                            // 0: free of blockers, 1: candidate blocker (to be confirmed), 2: stack overflow, 3: robust blocker
+        uint32_t cand = 0;
+#pragma unroll 1
+        for (int step = 0; step < LUMO_AH_NODE_ROUND; step++) {
+            if (active && verdict < 0 && leaf_pos == leaf_end && !(node & LUMO_AH_LEAF)) {
+                bool over = false;
+                if (!ah_node_step<CNT>(S, a, node, stack, sp, over, &cnt)) verdict = 0;
+                if (over) verdict = 2;
+            }
         }
-        // candidates and overflows are compacted into dense queues for the next two kernels
+        // ---- one leaf primitive ----
+        if (active && verdict < 0 && leaf_pos == leaf_end && (node & LUMO_AH_LEAF)) { leaf_pos = node & 0x07FFFFFFu; leaf_end = leaf_pos + ((node >> 27) & 0xFu) + 1u; }
+        if (active && verdict < 0 && leaf_pos < leaf_end) {
+            uint32_t obj; bool robust;
+            const double t = ah_prim_test<CNT>(S, leaf_pos, r, q, t_max, L, obj, robust, &cnt);
+            leaf_pos++;
+            if (t < t_max) { verdict = robust ? 3 : 1; cand = obj; }
+            else if (leaf_pos == leaf_end) { if (sp == 0) verdict = 0; else node = stack[--sp]; }
+        }
+        // ---- finished rays: verdict, or a place in the queues of the next two kernels ----
+        if (verdict == 0) sink.verdict(i, false);
+        if (verdict == 3) { sink.verdict(i, true); if (CNT) cnt.robust++; }
         const uint32_t m1 = __ballot_sync(0xFFFFFFFFu, verdict == 1), m2 = __ballot_sync(0xFFFFFFFFu, verdict == 2);
         if (m1) {
             uint32_t b = 0;
             if (lane == (uint32_t)(__ffs(m1) - 1)) b = atomicAdd(&Q.counters[1], (uint32_t)__popc(m1));
             b = __shfl_sync(0xFFFFFFFFu, b, __ffs(m1) - 1);
             if (verdict == 1) { const uint32_t j = b + __popc(m1 & ((1u << lane) - 1u)); Q.confirm_i[j] = i; Q.confirm_obj[j] = cand; }
+            if (CNT) cnt.candidates += __popc(m1) * (lane == 0);
         }
         if (m2) {
             uint32_t b = 0;
@@ -219,10 +279,10 @@ __global__ void __launch_bounds__(128, 4) k_occl_bvh(const __grid_constant__ Dev
             b = __shfl_sync(0xFFFFFFFFu, b, __ffs(m2) - 1);
             if (verdict == 2) Q.fallback_i[b + __popc(m2 & ((1u << lane) - 1u))] = i;
         }
-        if (CNT) { cnt.candidates += __popc(m1) * (lane == 0); }
+        if (verdict >= 0) active = false;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) sink.done(n);
-    if (CNT) { atomicAdd(&gc->nodes, cnt.nodes); atomicAdd(&gc->prims, cnt.prims); atomicAdd(&gc->tris, cnt.tris); atomicAdd(&gc->spheres, cnt.spheres); atomicAdd(&gc->candidates, cnt.candidates); }
+    if (CNT) { atomicAdd(&gc->nodes, cnt.nodes); atomicAdd(&gc->prims, cnt.prims); atomicAdd(&gc->tris, cnt.tris); atomicAdd(&gc->spheres, cnt.spheres); atomicAdd(&gc->candidates, cnt.candidates); atomicAdd(&gc->robust, cnt.robust); }
 }
 
 template <bool CNT, class Source, class Sink>

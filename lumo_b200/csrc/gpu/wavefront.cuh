@@ -35,6 +35,7 @@ struct IterCounters {   // zeroed before every iteration
     uint32_t n_shadow, trace_next, occl_next, n_active;
     uint32_t n_class[LUMO_N_CLASSES], pad[3];
     uint32_t occl[8];   // OcclQueues::counters of the occlusion-BVH kernels (occlude.cuh)
+    uint32_t n_terms, pad2[3];   // NEE term queue
 };
 // Counters that live across iterations (double-buffered by the parity of the iteration): done[p] = slots whose
 // path ended in an iteration of parity p, retired into the film (and refilled) at the start of the next one;
@@ -50,6 +51,12 @@ struct RunCounters {    // zeroed once per render
 // Path state, structure of arrays.  Ray, throughput and RNG position are double-buffered: the scatter
 // kernel writes the NEXT bounce's values into buffer cur^1 while the NEE kernel of the same iteration
 // still reads this bounce's values from buffer cur.
+struct NeeTermQueue;
+struct Wave;
+struct NeeTermQueue {   // NEE stage 1 -> stage 2 (see k_nee_a): structure of arrays, capacity = shadow_cap; reused by one material family after the other
+    double *ox, *oy, *oz, *dx, *dy, *dz, *wx, *wy, *wz, *tmax, *p_lig, *pdf_light, *le;   // le[k * cap + i]
+    uint32_t* slot;     // bit 31: the BSDF-sampled term (B)
+};
 struct Wave {
     uint32_t n_slots, shadow_cap;
     double *ox[2], *oy[2], *oz[2], *dx[2], *dy[2], *dz[2];
@@ -63,6 +70,7 @@ struct Wave {
     uint32_t* cls[LUMO_N_CLASSES];       // per-class shade queues (slot indices)
     // shadow queue (SoA)
     double *sox, *soy, *soz, *sdx, *sdy, *sdz, *stmax, *sc; uint32_t* sslot;
+    double* nee_ctx; uint32_t* nee_meta; NeeTermQueue tq;   // NEE: per-slot shading context [k * n_slots + slot] (17 doubles), term queue
     uint32_t *oq_i, *oq_obj, *oq_fb; uint8_t* occ_record;   // occlusion-BVH pipeline: confirm queue, fallback queue; verdicts (LUMO_OCCLUDE_CHECK only)
     IterCounters* it; RunCounters* run; QueueCounters* qc;
     // film + RR thresholds
@@ -310,8 +318,8 @@ struct BatchShadowSink {
 //                emission if the previous bounce was specular (path_trace.rs:24-29), path ends;
 //   k_scatter<K> class K: the BSDF sample of this bounce, throughput update, Russian roulette, next ray
 //                (path_trace.rs:23,42-78; direct_light.rs:23-68) — decides whether NEE runs;
-//   k_nee<K>     class K x shadow sample x {light sample, BSDF sample}: integrator.rs:74-184, one thread
-//                per MIS term; the occlusion half of hit_light goes to the shadow queue.
+//   k_nee_a / k_nee_b<K> / k_nee_eval<K>   next-event estimation, integrator.rs:74-184 (see below); the occlusion half of
+//                hit_light goes to the shadow queue.
 // One material family per kernel keeps warps on one code path and the instruction footprint small.
 __device__ __forceinline__ void push_shadow(const Wave& W, uint32_t slot, const Ray& r, double t_max, const C4& c) {
     const uint32_t i = agg_inc(&W.it->n_shadow);
@@ -354,6 +362,7 @@ __global__ void __launch_bounds__(128) k_terminal(const __grid_constant__ DevSce
 #ifndef LUMO_NEE_BLOCKS
 #define LUMO_NEE_BLOCKS 4
 #endif
+__device__ __forceinline__ void nee_ctx_store(const Wave& W, uint32_t slot, const DevHit& h, D3 nb);
 template <int K>
 __global__ void __launch_bounds__(128, LUMO_SCATTER_BLOCKS) k_scatter(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P) {
     const uint32_t N = W.n_slots, n = W.it->n_class[K & 7], cur = P.cur, nxt = P.cur ^ 1u;
@@ -383,7 +392,7 @@ __global__ void __launch_bounds__(128, LUMO_SCATTER_BLOCKS) k_scatter(const __gr
             if (!mat_is_specular(m)) { nee = true; done = true; }
             else if (depth >= LUMO_DL_MAX_RECURSION) done = true;
         } else nee = !mat_is_delta(S, m, lam);
-        if (nee) rng.draws += 6u * S.P.n_shadow_rays;      // the draws k_nee consumes (integrator.rs:96-118)
+        if (nee) { rng.draws += 6u * S.P.n_shadow_rays; nee_ctx_store(W, slot, ho, uvw.w); }   // the draws the NEE stages consume (integrator.rs:96-118); their view of this hit
         if (!done) {
             const Ray ri = hit_generate_ray(ho, wi);
             wi = ri.d;
@@ -416,85 +425,156 @@ __global__ void __launch_bounds__(128, LUMO_SCATTER_BLOCKS) k_scatter(const __gr
     }
 }
 
-// integrator.rs:139-184
-template <int K>
-__device__ __forceinline__ C4 mis_sample(const DevScene& S, const Mat& m, const Onb& uvw, D3 wo, D3 wi, const DevHit& ho, const DevHit& hi, const Lam& lam, bool li, double p_lig, double p_sct) {
-    if (p_lig == 0.0 || p_sct == 0.0) return c4(0.0);
-    const C4 bsdf = bsdf_f<K>(S, m, uvw, wo, wi, lam, 0, ho);
-    const double denom = p_lig * p_lig + p_sct * p_sct;
-    const double weight = li ? (p_lig * p_lig) / denom : (p_sct * p_sct) / denom;
-    const double p_denom = li ? p_lig : p_sct;
-    return bsdf * c4(1.0) * mat_emit<K>(S, S.materials[hi.material], lam, hi) * shading_cosine(m, wi, ho.ns) * weight / p_denom;
+// ---- next-event estimation (integrator.rs:74-184) in three dense stages ---------------------------------------------------
+// A bounce that runs NEE evaluates n_shadow_rays shadow samples (1 for up to 3 lights, log2 #lights beyond: 12 for a street
+// with 4097 lights), each with a light-sampled term (A) and a BSDF-sampled term (B).  As one kernel this was the largest
+// and the worst-running piece of the pipeline: 16 k SASS instructions (37 % of the stall samples waiting for instruction
+// fetch), 128 registers, and terms that end early (A below the horizon, B missing the light) thinning the warps.  Now:
+//   k_scatter<K>   (already there) also leaves the bounce's shading context — reconstructed Hit, shading normals — in HBM
+//   k_nee_a        one thread per (path, sample): light pick, point on the light, the two sign tests, the light's own
+//                  intersection test, its pdf and emission                  -> term queue      (no material code at all)
+//   k_nee_b<K>     one thread per (path, sample): BSDF sample of material family K, the chosen light's intersection
+//                  test, its pdf and emission                               -> term queue      (only BxDF::sample of K)
+//   k_nee_eval<K>  one thread per surviving term: BSDF pdf and value, MIS weight, contribution -> shadow queue
+// Every function is called with the arguments the single kernel passed, so the arithmetic — and the film — is unchanged.
+#define LUMO_NEE_CTX_DOUBLES 17   /* p, fp_error, ng, ns, shading normal after the normal map, u, v */
+__device__ __forceinline__ void nee_ctx_store(const Wave& W, uint32_t slot, const DevHit& h, D3 nb) {
+    const size_t N = W.n_slots; double* c = W.nee_ctx + slot;
+    c[0] = h.p.x; c[N] = h.p.y; c[2 * N] = h.p.z; c[3 * N] = h.fp_error.x; c[4 * N] = h.fp_error.y; c[5 * N] = h.fp_error.z;
+    c[6 * N] = h.ng.x; c[7 * N] = h.ng.y; c[8 * N] = h.ng.z; c[9 * N] = h.ns.x; c[10 * N] = h.ns.y; c[11 * N] = h.ns.z;
+    c[12 * N] = nb.x; c[13 * N] = nb.y; c[14 * N] = nb.z; c[15 * N] = h.u; c[16 * N] = h.v;
+    W.nee_meta[slot] = (uint32_t)h.material | (h.backface ? 0x80000000u : 0u);
 }
-
-// integrator.rs:89-137.  A shadow sample has a light-sampled term (A) and a BSDF-sampled term (B), the latter almost
-// always ending at "the sampled direction misses the light".  One thread per path: the hit reconstruction, the shading
-// frame and the path state are set up once and the thread then runs the n_shadow_rays samples of this bounce (1 for up to
-// 3 lights, log2 #lights beyond: 12 for a street with 4097 lights) one after the other, A then B.  (Round 1 ran one thread
-// per MIS term for n_shadow_rays > 1, which repeated the set-up 24 times per bounce.)
-template <int K>
-__global__ void __launch_bounds__(128, LUMO_NEE_BLOCKS) k_nee(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P) {
-    const uint32_t N = W.n_slots, nq = W.it->n_class[K & 7], cur = P.cur;
-    const uint32_t ns = S.P.n_shadow_rays;
-    const uint32_t n_pad = (nq + 31u) & ~31u;
-    for (uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x; qi < n_pad; qi += gridDim.x * blockDim.x) {
+__device__ __forceinline__ void nee_ctx_load(const Wave& W, uint32_t slot, DevHit& h, D3& nb) {
+    const size_t N = W.n_slots; const double* c = W.nee_ctx + slot;
+    h.t = 0.0;
+    h.p = d3(c[0], c[N], c[2 * N]); h.fp_error = d3(c[3 * N], c[4 * N], c[5 * N]);
+    h.ng = d3(c[6 * N], c[7 * N], c[8 * N]); h.ns = d3(c[9 * N], c[10 * N], c[11 * N]);
+    nb = d3(c[12 * N], c[13 * N], c[14 * N]); h.u = c[15 * N]; h.v = c[16 * N];
+    const uint32_t m = W.nee_meta[slot];
+    h.material = (int)(m & 0x7FFFFFFFu); h.backface = (m & 0x80000000u) != 0u;
+}
+__device__ __forceinline__ void push_term(const Wave& W, uint32_t slot, bool term_b, const Ray& r, D3 wi, double t_max, double p_lig, double pdf_light, const C4& le) {
+    const uint32_t i = agg_inc(&W.it->n_terms);
+    if (i >= W.shadow_cap) { atomicAdd(&W.run->shadow_dropped, 1ull); return; }
+    const NeeTermQueue& T = W.tq;
+    T.ox[i] = r.o.x; T.oy[i] = r.o.y; T.oz[i] = r.o.z; T.dx[i] = r.d.x; T.dy[i] = r.d.y; T.dz[i] = r.d.z; T.wx[i] = wi.x; T.wy[i] = wi.y; T.wz[i] = wi.z;
+    T.tmax[i] = t_max; T.p_lig[i] = p_lig; T.pdf_light[i] = pdf_light; T.slot[i] = slot | (term_b ? 0x80000000u : 0u);
+    for (int k = 0; k < 4; k++) T.le[(size_t)k * W.shadow_cap + i] = le.s[k];
+}
+// (path, shadow sample) of a thread: 32 consecutive queue entries of class `klass` share a warp and a sample index
+__device__ __forceinline__ bool nee_item(const Wave& W, uint32_t klass, unsigned long long it, uint32_t ns, uint32_t nq, uint32_t& slot, uint32_t& i) {
+    const unsigned long long grp = it / (32ull * ns);
+    i = (uint32_t)((it / 32ull) % ns);
+    const uint32_t qi = (uint32_t)(grp * 32ull + (it % 32ull));
+    if (qi >= nq) return false;
+    slot = W.cls[klass][qi];
+    return (W.flags[slot] & PF_NEE) != 0u;
+}
+#ifndef LUMO_NEE_A_BLOCKS
+#define LUMO_NEE_A_BLOCKS 5
+#endif
+// the light-sampled term, up to the point where the material comes in (integrator.rs:96-110)
+template <bool TEX>
+__global__ void __launch_bounds__(128, LUMO_NEE_A_BLOCKS) k_nee_a(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P, uint32_t klass) {
+    const uint32_t N = W.n_slots, nq = W.it->n_class[klass], cur = P.cur, ns = S.P.n_shadow_rays;
+    const unsigned long long padded = (unsigned long long)((nq + 31u) / 32u) * 32ull * ns;
+    for (unsigned long long it = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; it < padded; it += (unsigned long long)gridDim.x * blockDim.x) {
         __syncwarp();                                 // a lane whose item ended early waits here instead of running ahead into its next one
-        uint32_t slot = 0;
-        bool on = qi < nq;
-        if (on) { slot = W.cls[K & 7][qi]; on = (W.flags[slot] & PF_NEE) != 0u; }
-        if (!__any_sync(0xFFFFFFFFu, on)) continue;
-        Ray ro; HitRec rec; DevHit ho; Onb uvw; Lam lam; C4 gathered; D3 wo; uint32_t pixel = 0, sample = 0, draws = 0;
-        if (on) {
-            load_path(W, cur, slot, ro, rec);
-            ho = reconstruct_hit<LUMO_TEX(K)>(S, ro, rec);
-            uvw = shading_onb<K>(S, S.materials[ho.material], ho);
-            pixel = W.pixel[slot]; sample = W.sample[slot]; draws = W.draws[cur][slot];
-            for (int k = 0; k < 4; k++) lam.l[k] = W.lam[(size_t)k * N + slot];   // already terminated by k_scatter if dispersive
-            gathered = load_c4(W.gathered[cur], N, slot);
-            wo = -ro.d;
+        uint32_t slot, i;
+        if (!nee_item(W, klass, it, ns, nq, slot, i)) continue;
+        DevHit ho; D3 nb; nee_ctx_load(W, slot, ho, nb);
+        // draws of this bounce: 3 for the scatter sample, then 6 per shadow sample: light pick, light point (2), BSDF sample (3)
+        Rng rng = rng_make(P.seed, W.pixel[slot], W.sample[slot], 0u, W.draws[cur][slot] + 3u + 6u * i);
+        const uint32_t li = sample_light(S, rng_float(rng));
+        const uint32_t lobj = S.P.n_objects + li;
+        const LumoObject lo = S.objects[lobj];
+        const double r0 = rng_float(rng), r1 = rng_float(rng);
+        const D3 wi = light_sample_towards(S, lo, ho.p, r0, r1);
+        // mis_sample returns black when either pdf is zero (integrator.rs:150-152) whatever the light test says.  For the
+        // reflection-only BxDFs the pdf starts with two sign tests (bsdf.rs:88-90, bxdf.rs:136-139, scatter.rs:14-17):
+        // a light-sampled direction below the surface stops here, before any light or microfacet arithmetic.
+        if (klass != LMAT_MFDIELECTRIC) {
+            const D3 wo = d3(-W.dx[cur][slot], -W.dy[cur][slot], -W.dz[cur][slot]);
+            if (!is_reflection(wo, wi, ho.ng)) continue;
+            const Onb uvw = onb_new(nb);
+            if (!same_hemisphere(to_local(uvw, wo), to_local(uvw, wi))) continue;
         }
-        const bool dbg = on && pixel == P.debug_pixel && P.mode == WM_MAIN;
-#pragma unroll 1
-        for (uint32_t i = 0; i < ns; i++) {
-            __syncwarp();                             // the lanes of a warp start every shadow sample together
-            if (!on) continue;
-            const Mat& m = S.materials[ho.material];
-            // draws of this bounce: 3 for the scatter sample, then 6 per shadow sample: light pick, light point (2), BSDF sample (3)
-            Rng rng = rng_make(P.seed, pixel, sample, 0u, draws + 3u + 6u * i);
-            const uint32_t li = sample_light(S, rng_float(rng));
-            const double pdf_light = S.lights[li].pdf;
-            const uint32_t lobj = S.P.n_objects + li;
-            const LumoObject lo = S.objects[lobj];
-#pragma unroll 1
-            for (int term = 0; term < 2; term++) {
-                D3 wi;
-                if (term == 0) {
-                    const double r0 = rng_float(rng), r1 = rng_float(rng);
-                    wi = light_sample_towards(S, lo, ho.p, r0, r1);
-                    // mis_sample returns black when either pdf is zero (integrator.rs:150-152) whatever the light test says.  For the
-                    // reflection-only BxDFs the pdf starts with two sign tests (bsdf.rs:88-90, bxdf.rs:136-139, scatter.rs:14-17):
-                    // a light-sampled direction below the surface stops here, before any light or microfacet arithmetic.
-                    if ((K & 7) != LMAT_MFDIELECTRIC) {
-                        if (!is_reflection(wo, wi, ho.ng)) continue;
-                        if (!same_hemisphere(to_local(uvw, wo), to_local(uvw, wi))) continue;
-                    }
-                } else {
-                    const double ru = rng_float(rng), r0 = rng_float(rng), r1 = rng_float(rng);
-                    Lam l2 = lam;
-                    if (!bsdf_sample<K>(S, m, uvw, wo, ho, l2, ru, r0, r1, wi)) continue;
-                }
-                const Ray ri = hit_generate_ray(ho, wi);
-                DevHit hi;
-                if (!light_hit<LUMO_TEX(K)>(S, lobj, ri, hi)) continue;
-                const double p_lig = light_sample_towards_pdf(S, lo, ri, hi.p, hi.ng);
-                const double p_sct = bsdf_pdf<K>(S, m, uvw, wo, wi, ho, lam, false);
-                const C4 c = mis_sample<K>(S, m, uvw, wo, wi, ho, hi, lam, term == 0, p_lig, p_sct);
-                if (dbg) printf("  [gpu] %c vis t=%.17g p_lig=%.17g p_sct=%.17g c0=%.17g\n", term ? 'B' : 'A', hi.t, p_lig, p_sct, c.s[0]);
-                if (!is_black(c)) push_shadow(W, slot, ri, hi.t - LUMO_EPS, gathered * (c / pdf_light) / (double)ns);
-            }
-        }
+        const Ray ri = hit_generate_ray(ho, wi);
+        DevHit hi;
+        if (!light_hit<TEX>(S, lobj, ri, hi)) continue;
+        const double p_lig = light_sample_towards_pdf(S, lo, ri, hi.p, hi.ng);
+        Lam lam; for (int k = 0; k < 4; k++) lam.l[k] = W.lam[(size_t)k * N + slot];   // already terminated by k_scatter if dispersive
+        const C4 le = mat_emit<TEX ? -1 : LUMO_K_SOLID>(S, S.materials[hi.material], lam, hi);
+        push_term(W, slot, false, ri, wi, hi.t - LUMO_EPS, p_lig, S.lights[li].pdf, le);
     }
 }
+// the BSDF-sampled term up to the same point (integrator.rs:112-134)
+template <int K>
+__global__ void __launch_bounds__(128, LUMO_NEE_A_BLOCKS) k_nee_b(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P) {
+    const uint32_t N = W.n_slots, nq = W.it->n_class[K & 7], cur = P.cur, ns = S.P.n_shadow_rays;
+    const unsigned long long padded = (unsigned long long)((nq + 31u) / 32u) * 32ull * ns;
+    for (unsigned long long it = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; it < padded; it += (unsigned long long)gridDim.x * blockDim.x) {
+        __syncwarp();
+        uint32_t slot, i;
+        if (!nee_item(W, K & 7, it, ns, nq, slot, i)) continue;
+        DevHit ho; D3 nb; nee_ctx_load(W, slot, ho, nb);
+        const Mat& m = S.materials[ho.material];
+        const uint32_t pixel = W.pixel[slot], sample = W.sample[slot], d0 = W.draws[cur][slot] + 3u + 6u * i;
+        Rng rng = rng_make(P.seed, pixel, sample, 0u, d0);
+        const uint32_t li = sample_light(S, rng_float(rng));
+        const uint32_t lobj = S.P.n_objects + li;
+        rng = rng_make(P.seed, pixel, sample, 0u, d0 + 3u);
+        const double ru = rng_float(rng), r0 = rng_float(rng), r1 = rng_float(rng);
+        Lam lam; for (int k = 0; k < 4; k++) lam.l[k] = W.lam[(size_t)k * N + slot];
+        const Onb uvw = onb_new(nb);
+        const D3 wo = d3(-W.dx[cur][slot], -W.dy[cur][slot], -W.dz[cur][slot]);
+        D3 wi;
+        Lam l2 = lam;
+        if (!bsdf_sample<K>(S, m, uvw, wo, ho, l2, ru, r0, r1, wi)) continue;
+        const Ray ri = hit_generate_ray(ho, wi);
+        DevHit hi;
+        if (!light_hit<LUMO_TEX(K)>(S, lobj, ri, hi)) continue;
+        const double p_lig = light_sample_towards_pdf(S, S.objects[lobj], ri, hi.p, hi.ng);
+        const C4 le = mat_emit<K>(S, S.materials[hi.material], lam, hi);
+        push_term(W, slot, true, ri, wi, hi.t - LUMO_EPS, p_lig, S.lights[li].pdf, le);
+    }
+}
+// BSDF pdf and value, MIS weight (integrator.rs:139-184), contribution -> shadow queue.  Dense over the term queue.
+template <int K>
+__global__ void __launch_bounds__(128, LUMO_NEE_BLOCKS) k_nee_eval(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P) {
+    const uint32_t N = W.n_slots, cur = P.cur, C = W.shadow_cap;
+    const uint32_t n = min(W.it->n_terms, C);
+    const uint32_t n_pad = (n + 31u) & ~31u;
+    const double ns = (double)S.P.n_shadow_rays;
+    const NeeTermQueue& T = W.tq;
+    for (uint32_t ti = blockIdx.x * blockDim.x + threadIdx.x; ti < n_pad; ti += gridDim.x * blockDim.x) {
+        __syncwarp();
+        if (ti >= n) continue;
+        const uint32_t sl = T.slot[ti], slot = sl & 0x7FFFFFFFu;
+        const bool light_sampled = (sl & 0x80000000u) == 0u;
+        const double p_lig = T.p_lig[ti];
+        DevHit ho; D3 nb; nee_ctx_load(W, slot, ho, nb);
+        const Mat& m = S.materials[ho.material];
+        const Onb uvw = onb_new(nb);
+        const D3 wo = d3(-W.dx[cur][slot], -W.dy[cur][slot], -W.dz[cur][slot]);
+        const D3 wi = d3(T.wx[ti], T.wy[ti], T.wz[ti]);
+        Lam lam; for (int k = 0; k < 4; k++) lam.l[k] = W.lam[(size_t)k * N + slot];
+        const double p_sct = bsdf_pdf<K>(S, m, uvw, wo, wi, ho, lam, false);
+        if (p_lig == 0.0 || p_sct == 0.0) continue;                                   // integrator.rs:150-152
+        const C4 bsdf = bsdf_f<K>(S, m, uvw, wo, wi, lam, 0, ho);
+        const double denom = p_lig * p_lig + p_sct * p_sct;
+        const double weight = light_sampled ? (p_lig * p_lig) / denom : (p_sct * p_sct) / denom;
+        const double p_denom = light_sampled ? p_lig : p_sct;
+        C4 le; for (int k = 0; k < 4; k++) le.s[k] = T.le[(size_t)k * C + ti];
+        const C4 c = bsdf * c4(1.0) * le * shading_cosine(m, wi, ho.ns) * weight / p_denom;
+        if (W.pixel[slot] == P.debug_pixel && P.mode == WM_MAIN) printf("  [gpu] %c vis t=%.17g p_lig=%.17g p_sct=%.17g c0=%.17g\n", light_sampled ? 'A' : 'B', T.tmax[ti] + LUMO_EPS, p_lig, p_sct, c.s[0]);
+        if (is_black(c)) continue;
+        Ray ri; ri.o = d3(T.ox[ti], T.oy[ti], T.oz[ti]); ri.d = d3(T.dx[ti], T.dy[ti], T.dz[ti]);
+        push_shadow(W, slot, ri, T.tmax[ti], load_c4(W.gathered[cur], N, slot) * (c / T.pdf_light[ti]) / ns);
+    }
+}
+__global__ void k_terms_reset(IterCounters* it) { it->n_terms = 0u; }
 
 // RR threshold of a tile from its 64 pilot paths, summed in index order (task.rs:42-53 applied to
 // the pilot set): var = sum f^2 - (sum f)^2 / n; delta = var <= 0 ? 1e-5 : sqrt(var / sum cost)

@@ -162,6 +162,7 @@ def gpu_lib():
         L.lumo_gpu_render_multi.argtypes = [C.POINTER(vp), C.c_int32, C.POINTER(RenderParams), C.POINTER(FilmAccum)]
         L.lumo_gpu_ctx_occlusion_mode.argtypes = [vp, C.c_int32]; L.lumo_gpu_ctx_occlusion_mode.restype = C.c_int32
         L.lumo_gpu_ctx_occlusion_stats.argtypes = [vp, C.POINTER(C.c_uint64)]; L.lumo_gpu_ctx_occlusion_stats.restype = C.c_int32
+        L.lumo_gpu_fp64_peak.argtypes = [vp, dp, dp]; L.lumo_gpu_fp64_peak.restype = C.c_int32
         L.lumo_gpu_math_eval.argtypes = [vp, C.c_int32, dp, dp, C.c_uint64, dp]
         L.lumo_gpu_math_eval.restype = C.c_int32
         L.lumo_gpu_sample_range.argtypes = [C.c_int32, C.c_int32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
@@ -209,9 +210,9 @@ class GpuContext:
         _check(gpu_lib().lumo_gpu_ctx_occlusion_mode(self.h, int(mode)), "lumo_gpu_ctx_occlusion_mode")
 
     def occlusion_stats(self):
-        out = (C.c_uint64 * 8)()
+        out = (C.c_uint64 * 9)()
         _check(gpu_lib().lumo_gpu_ctx_occlusion_stats(self.h, out), "lumo_gpu_ctx_occlusion_stats")
-        return dict(zip(("nodes", "prims", "tri_tests", "sphere_tests", "candidates", "confirmed", "fallback", "mismatches"), (int(v) for v in out)))
+        return dict(zip(("nodes", "prims", "tri_tests", "sphere_tests", "candidates", "confirmed", "fallback", "mismatches", "robust"), (int(v) for v in out)))
 
     def iter_log(self):
         cap = 16384
@@ -224,6 +225,12 @@ class GpuContext:
         ms = (C.c_double * 4)(); n = (C.c_uint64 * 4)()
         _check(gpu_lib().lumo_gpu_ctx_kernel_times(self.h, ms, n), "lumo_gpu_ctx_kernel_times")
         return {k: (ms[i], int(n[i])) for i, k in enumerate(("regen", "trace", "shade", "occlude"))}
+
+    def fp64_peak(self):
+        """Measured DFMA throughput of this GPU (TFLOP/s) — the FP64 issue ceiling next to the bandwidth roofline."""
+        tf = C.c_double(0.0); ms = C.c_double(0.0)
+        _check(gpu_lib().lumo_gpu_fp64_peak(self.h, C.byref(tf), C.byref(ms)), "lumo_gpu_fp64_peak")
+        return {"tflops": tf.value, "ms": ms.value, "what": "8 independent DFMA chains per thread, 2048 threads per SM, 2 flops per DFMA; best of 3 launches"}
 
     def math_eval(self, fn, x, y=None):
         """csrc/common/lumo_math.h evaluated on the device (parity hook)."""

@@ -260,6 +260,7 @@ struct RenderParams {       // mirrors include/lumo_gpu.h lumo_render_params + t
     uint64_t seed;
     uint32_t spp_begin, spp_end, total_spp;
     int32_t threads;
+    int32_t tile_step, pad;  // reference schedule only: render every tile_step-th 16x16 tile (0 / 1 = all) — bench.py's bounded CPU sample of a full-size workload at the workload's own spp
 };
 
 static std::vector<FilmSample> integrate(const Loaded& L, int integrator, Rng& rng, Float delta, Vec2 raster_xy) {  // integrator.rs:45-69
@@ -297,7 +298,9 @@ static void render_reference(const Loaded& L, const RenderParams& P, FilmAccum& 
         taken = std::min(taken + SAMPLES_INCREMENT, total);
         for (uint64_t y = 0; y < tiles_y; y++) for (uint64_t x = 0; x < tiles_x; x++) {
             uint64_t x0 = x * TILE_SIZE, y0 = y * TILE_SIZE;
-            tasks.push_back({x0, y0, std::min(x0 + TILE_SIZE, cam.res_x), std::min(y0 + TILE_SIZE, cam.res_y), batch, taken - prev, master.gen_u64()});
+            const uint64_t seed = master.gen_u64();                 // every tile draws its seed, rendered or not
+            if (P.tile_step > 1 && (x + y * tiles_x) % (uint64_t)P.tile_step != 0) continue;
+            tasks.push_back({x0, y0, std::min(x0 + TILE_SIZE, cam.res_x), std::min(y0 + TILE_SIZE, cam.res_y), batch, taken - prev, seed});
         }
     }
     std::vector<std::unique_ptr<FilmTile>> done(tasks.size());
@@ -343,8 +346,8 @@ static void render_reference(const Loaded& L, const RenderParams& P, FilmAccum& 
     std::vector<std::thread> th;
     for (int i = 0; i < nt; i++) th.emplace_back(worker);
     for (auto& t : th) t.join();
-    for (size_t i = 0; i < tasks.size(); i++) { add_tile(film, *done[i]); film.cost += costs[i]; done[i].reset(); }
-    film.cam = total * cam.res_x * cam.res_y;
+    film.cam = 0;
+    for (size_t i = 0; i < tasks.size(); i++) { add_tile(film, *done[i]); film.cost += costs[i]; done[i].reset(); film.cam += tasks[i].samples * (tasks[i].x1 - tasks[i].x0) * (tasks[i].y1 - tasks[i].y0); }
 }
 
 // GPU schedule (what lumo_gpu_render does): every (pixel, sample) owns a Philox

@@ -17,7 +17,8 @@ def build(native=False):
 class RenderParams(C.Structure):
     _fields_ = [("integrator", C.c_int32), ("sampler", C.c_int32), ("tone_map", C.c_int32), ("rng_mode", C.c_int32),
                 ("tone_map_arg", C.c_double), ("rr_delta", C.c_double), ("seed", C.c_uint64),
-                ("spp_begin", C.c_uint32), ("spp_end", C.c_uint32), ("total_spp", C.c_uint32), ("threads", C.c_int32)]
+                ("spp_begin", C.c_uint32), ("spp_end", C.c_uint32), ("total_spp", C.c_uint32), ("threads", C.c_int32),
+                ("tile_step", C.c_int32), ("pad", C.c_int32)]
 
 
 _libs = {}
@@ -125,10 +126,11 @@ class OracleScene:
         return dict(zip(("tlas_nodes", "inst", "kd_nodes", "leaf_idx", "tri_tests", "sphere_tests", "closest", "occlusion"), (int(v) for v in c)))
 
     def render(self, integrator=0, spp=1, seed=1, sampler=2, tone_map=0, tone_map_arg=0.0, rng_mode=0, rr_delta=0.0,
-               threads=8, spp_begin=0, spp_end=None, total_spp=None):
+               threads=8, spp_begin=0, spp_end=None, total_spp=None, tile_step=1):
+        """tile_step > 1 (reference schedule only, rng_mode 0): render every tile_step-th 16x16 tile."""
         total = spp if total_spp is None else total_spp
         end = total if spp_end is None else spp_end
-        P = RenderParams(integrator, sampler, tone_map, rng_mode, tone_map_arg, rr_delta, seed, spp_begin, end, total, threads)
+        P = RenderParams(integrator, sampler, tone_map, rng_mode, tone_map_arg, rr_delta, seed, spp_begin, end, total, threads, tile_step, 0)
         W, H = self.res_x, self.res_y
         pixels = np.zeros((H, W, 4)); splats = np.zeros((H, W, 3)); cnt = np.zeros(4, np.uint64)
         ntiles = ((W + 15) // 16) * ((H + 15) // 16)
