@@ -350,7 +350,7 @@ def measure(name, args, env, steps, warmup, full):
     ctx.count_visits(True)
     cntc, _ = scene.render_dev(px_ptr, sp_ptr, integrator=integrator, seed=seeds[-1], spp_begin=s0, spp_end=s1, total_spp=total_spp, wave_paths=args.wave_paths)
     vis_closest, vis_occl = ctx.visits()
-    ost = ctx.occlusion_stats()
+    ost = ctx.occlusion_stats(); cst = ctx.closest_stats()
     ctx.count_visits(False)
     peaks = {}
     try: peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -377,9 +377,14 @@ def measure(name, args, env, steps, warmup, full):
             e["traffic_detail"] = dict(tr, units_per_launch=units / max(n, 1))
         return e
 
-    by["trace"] = entry("k_wave_trace (closest-hit, reference-order traversal)", "trace", ray_bytes(vis_closest, cntc["closest"], 92), cntc["closest"], "ray",
-                        "92 B ray in / hit out + 64 B per object-BVH node + 96 B per instance transform + 16 B per kd node + 4 B per leaf entry + 72 B per triangle test; counts every visit, so a scene that fits the 126 MB L2 can exceed the HBM peak")
-    if by["trace"]: by["trace"]["visits_per_ray"] = {k: v / max(cntc["closest"], 1) for k, v in vis_closest.items()}
+    trace_bytes = ray_bytes(vis_closest, cntc["closest"], 92) + 128 * cst["nodes"] + 8 * cst["prims"] + 72 * cst["tri_tests"] + 16 * cst["sphere_tests"] + (28 + 28 + 52) * cntc["closest"]
+    by["trace"] = entry("k_closest_bvh + k_closest_finish + k_closest_fallback + k_wave_classify (Scene::hit: world-space BVH, the reference traversal on the winning object, full reference traversal where needed)",
+                        "trace", trace_bytes, cntc["closest"], "ray",
+                        "92 B ray in / hit out + 128 B per BVH node + 8 B per leaf primitive + 72 B per triangle test + 108 B of per-ray scratch and second ray read, plus the reference-order visits of the finish / fallback kernels "
+                        "(64 B per object-BVH node, 96 B per instance transform, 16 B per kd node, 4 B per leaf entry, 72 B per triangle test); counts every visit, so a scene that fits the 126 MB L2 can exceed the HBM peak")
+    if by["trace"]:
+        by["trace"]["bvh_per_ray"] = {k: v / max(cntc["closest"], 1) for k, v in cst.items() if k != "rays"}
+        by["trace"]["reference_order_visits_per_ray"] = {k: v / max(cntc["closest"], 1) for k, v in vis_closest.items()}
     by["occlude"] = entry("k_occl_bvh + k_occl_confirm + k_occl_fallback (order-free occlusion BVH, confirmed by the reference's per-object traversal)", "occlude",
                           occl_bytes(ost, vis_occl, cntc["occlusion"]), cntc["occlusion"], "ray",
                           "60 B shadow-queue entry + 128 B per BVH node + 8 B per leaf primitive + 72 B per triangle test + 68 B per candidate + the confirming traversal's visits")

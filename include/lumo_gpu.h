@@ -38,8 +38,8 @@ enum lumo_status {
 
 /* Integrator::{PathTrace, DirectLight, BDPathTrace}  (src/tracer/integrator.rs:17-27) */
 enum lumo_integrator { LUMO_PATH_TRACE = 0, LUMO_DIRECT_LIGHT = 1, LUMO_BD_PATH_TRACE = 2 };
-/* SamplerType (src/samplers.rs:8-21); Sobol is not provided */
-enum lumo_sampler { LUMO_SAMPLER_UNIFORM = 0, LUMO_SAMPLER_JITTERED = 1, LUMO_SAMPLER_MULTI_JITTERED = 2 };
+/* SamplerType (src/samplers.rs:8-21); Sobol has 1023 points (samplers/sobol_seq.rs:3): total_spp <= 1023 */
+enum lumo_sampler { LUMO_SAMPLER_UNIFORM = 0, LUMO_SAMPLER_JITTERED = 1, LUMO_SAMPLER_MULTI_JITTERED = 2, LUMO_SAMPLER_SOBOL = 3 };
 /* ToneMap (src/tone_mapping.rs:13-20) */
 enum lumo_tone_map { LUMO_TONE_NONE = 0, LUMO_TONE_CLAMP = 1, LUMO_TONE_REINHARD = 2 };
 
@@ -141,6 +141,12 @@ int32_t lumo_gpu_film_encode(lumo_ctx* ctx, const double* pixels, const double* 
  * never enabled inside a timed region. */
 int32_t lumo_gpu_ctx_count_visits(lumo_ctx* ctx, int32_t enable);
 int32_t lumo_gpu_ctx_visits(lumo_ctx* ctx, uint64_t* out12);   /* 6 for the closest-hit kernels, then 6 for the occlusion kernels */
+/* Closest hits (Scene::hit) go through a world-space BVH with the reference traversal run on the winning object only, and
+ * through the full reference traversal wherever that is not provably the same (csrc/gpu/closest.cuh).  mode 0: that (default);
+ * 1: the reference traversal for every ray.  stats (only while visit counting is on; reset by lumo_gpu_ctx_count_visits):
+ * [0] BVH nodes, [1] leaf primitives, [2] triangle tests, [3] sphere tests, [4] rays sent to the reference traversal, [5] rays. */
+int32_t lumo_gpu_ctx_closest_mode(lumo_ctx* ctx, int32_t mode);
+int32_t lumo_gpu_ctx_closest_stats(lumo_ctx* ctx, uint64_t* stats6);
 /* Shadow rays are answered from an order-free occlusion BVH and confirmed by the reference's own per-object traversal
  * (csrc/gpu/occlude.cuh).  mode 0: that (default); 1: the reference's object BVH + kd-tree traversal for shadow rays too;
  * 2: both on every shadow ray of a render, disagreements counted in stats[7].  stats: [0] BVH nodes, [1] leaf primitives,

@@ -25,8 +25,8 @@ class Integrator:                                    # src/tracer/integrator.rs:
     NAMES = {0: "path tracing", 1: "direct light integration", 2: "bidirectional path tracing"}
 
 
-class SamplerType:                                   # src/samplers.rs:8-21 (Sobol: not supported, needs its tables)
-    Uniform, Jittered, MultiJittered = 0, 1, 2
+class SamplerType:                                   # src/samplers.rs:8-21
+    Uniform, Jittered, MultiJittered, Sobol = 0, 1, 2, 3
 
 
 class ToneMap:                                       # src/tone_mapping.rs:13-35

@@ -1,0 +1,282 @@
+// Closest hits (`Scene::hit`, src/tracer/scene.rs:119-147) through the world-space BVH of occlude.cuh, with the reference's
+// own traversal run only on the object that wins — and, for every ray where that is not provably the reference's result,
+// the reference traversal of trace.cuh as before.
+//
+// What `Scene::hit` computes: for Scene.objects, then for Scene.lights with t_max = the objects' hit,
+// BVH::_hit walks the object BVH in build order and keeps the object whose ANY-hit distance `hit_t(r, t_min, tt)` is
+// below the running bound tt (bvh.rs:343-352); the winner is then intersected in full (`hit`, bvh.rs:368).  For a kd-tree
+// the any-hit distance is the first triangle the front-to-back walk accepts, not necessarily the nearest one, so in
+// general the winner depends on the visit order.  It does not when
+//   (1) the nearest hit t1 of the whole group belongs to object G and no other object of the group has a hit at a
+//       distance <= t1 (no tie), and
+//   (2) G's any-hit distance A — the first triangle its own kd walk accepts — equals t1.
+// Then every object visited before G reports a distance above t1 (or nothing), G reports A = t1 whatever bound it is handed
+// (a bound above A does not change the first accepted triangle), and nothing visited after G can get below it: G wins, and
+// the result is G's full intersection.  All distances involved are Triangle::hit_t / Sphere::hit_t values computed with the
+// reference's arithmetic in the object's frame, so (1) and (2) are exact comparisons, not estimates.
+//
+//   k_closest_bvh     lane-refilled, near-child-first walk of the world-space BVH (f32 boxes only cull, conservatively):
+//                     per group the nearest hit (t1, G) and the nearest hit of any other object (conservatively), with
+//                     the reference's f64 primitive tests; lights are only of interest below the objects' t1.
+//   k_closest_finish  for G: the box tests of the object-BVH nodes above it with the tightest bound the reference could
+//                     hold there (bvh.rs:333-335), then `Object::hit` = the reference's kd walk, which also yields A;
+//                     checks (1), (2) and that the full hit's distance is t1; the same for the nearest light below it.
+//                     Any check that fails (a tie, A != t1, a rejected full hit, a traversal stack overflow) sends the ray to
+//   k_closest_fallback  `scene_hit` of trace.cuh — the reference traversal, unchanged.
+// tests/test_trace_parity.py compares ids, t and barycentrics bit for bit with the oracle through this pipeline.
+#pragma once
+#include "occlude.cuh"
+
+namespace lumo_dev {
+
+struct ClosestScratch {    // per ray of a launch
+    double *t1, *tl;       // nearest hit among Scene.objects / among Scene.lights (below t1)
+    uint32_t *o1, *ol;     // their objects (global index), LUMO_NONE if none
+    uint32_t* flags;       // bit 0: another object hit at <= t1, bit 1: another light hit at <= tl, bit 2: traversal stack overflow
+    uint32_t* fallback_i;  // rays for k_closest_fallback
+    uint32_t* counters;    // [0] work cursor of k_closest_bvh, [1] cursor of k_closest_finish, [2] fallback queue size, [3] fallback cursor
+};
+struct ClosestCounters { unsigned long long nodes, prims, tris, spheres, fallback, rays; };
+
+#define LUMO_CH_STACK 48
+#ifndef LUMO_CH_REFILL
+#define LUMO_CH_REFILL 8
+#endif
+#ifndef LUMO_CH_NODE_ROUND
+#define LUMO_CH_NODE_ROUND 3
+#endif
+
+// One inner-node step of the ordered walk: hit children are pushed with their entry distances, the nearest is walked next.
+template <bool CNT>
+__device__ __forceinline__ bool ch_node_step(const DevScene& S, const AhRay& a, uint32_t& node, uint32_t* stack, float* stack_t, int& sp, bool& over, ClosestCounters* c) {
+    if (CNT) c->nodes++;
+    const float4* n4 = reinterpret_cast<const float4*>(S.ah_nodes + node);
+    const float4 ax = __ldg(n4 + a.ox), bx = __ldg(n4 + 3 - a.ox);
+    const float4 ay = __ldg(n4 + 1 + a.oy), by = __ldg(n4 + 4 - a.oy);
+    const float4 az = __ldg(n4 + 2 + a.oz), bz = __ldg(n4 + 5 - a.oz);
+    const uint4 ch = __ldg(reinterpret_cast<const uint4*>(n4 + 6));
+    const float n0 = fmaxf(fmaxf(__fmaf_rn(ax.x, a.ix, a.nx), __fmaf_rn(ay.x, a.iy, a.ny)), fmaxf(__fmaf_rn(az.x, a.iz, a.nz), 0.0f));
+    const float n1 = fmaxf(fmaxf(__fmaf_rn(ax.y, a.ix, a.nx), __fmaf_rn(ay.y, a.iy, a.ny)), fmaxf(__fmaf_rn(az.y, a.iz, a.nz), 0.0f));
+    const float n2 = fmaxf(fmaxf(__fmaf_rn(ax.z, a.ix, a.nx), __fmaf_rn(ay.z, a.iy, a.ny)), fmaxf(__fmaf_rn(az.z, a.iz, a.nz), 0.0f));
+    const float n3 = fmaxf(fmaxf(__fmaf_rn(ax.w, a.ix, a.nx), __fmaf_rn(ay.w, a.iy, a.ny)), fmaxf(__fmaf_rn(az.w, a.iz, a.nz), 0.0f));
+    const float f0 = fminf(fminf(__fmaf_rn(bx.x, a.ix, a.fx), __fmaf_rn(by.x, a.iy, a.fy)), fminf(__fmaf_rn(bz.x, a.iz, a.fz), a.tmax));
+    const float f1 = fminf(fminf(__fmaf_rn(bx.y, a.ix, a.fx), __fmaf_rn(by.y, a.iy, a.fy)), fminf(__fmaf_rn(bz.y, a.iz, a.fz), a.tmax));
+    const float f2 = fminf(fminf(__fmaf_rn(bx.z, a.ix, a.fx), __fmaf_rn(by.z, a.iy, a.fy)), fminf(__fmaf_rn(bz.z, a.iz, a.fz), a.tmax));
+    const float f3 = fminf(fminf(__fmaf_rn(bx.w, a.ix, a.fx), __fmaf_rn(by.w, a.iy, a.fy)), fminf(__fmaf_rn(bz.w, a.iz, a.fz), a.tmax));
+    const float rel = 1.00000095367431640625f;   // 1 + 2^-20
+    const bool h0 = n0 <= f0 * rel && ch.x != LUMO_NONE, h1 = n1 <= f1 * rel && ch.y != LUMO_NONE, h2 = n2 <= f2 * rel && ch.z != LUMO_NONE, h3 = n3 <= f3 * rel && ch.w != LUMO_NONE;
+    uint32_t next = LUMO_NONE; float best = 0.0f;
+#define LUMO_CH_TAKE(h, n, c)                                                                                                  \
+    if (h) {                                                                                                                   \
+        if (next == LUMO_NONE) { next = c; best = n; }                                                                         \
+        else if (sp >= LUMO_CH_STACK) over = true;                                                                             \
+        else if (n < best) { stack[sp] = next; stack_t[sp] = best; sp++; next = c; best = n; }                                 \
+        else { stack[sp] = c; stack_t[sp] = n; sp++; }                                                                         \
+    }
+    LUMO_CH_TAKE(h0, n0, ch.x) LUMO_CH_TAKE(h1, n1, ch.y) LUMO_CH_TAKE(h2, n2, ch.z) LUMO_CH_TAKE(h3, n3, ch.w)
+#undef LUMO_CH_TAKE
+    if (next == LUMO_NONE) return false;
+    node = next;
+    return true;
+}
+// pops the next node that can still hold something at or below the current bound; false: the walk is over
+__device__ __forceinline__ bool ch_pop(const AhRay& a, uint32_t& node, const uint32_t* stack, const float* stack_t, int& sp) {
+    while (sp > 0) {
+        --sp;
+        if (stack_t[sp] <= a.tmax * 1.00000095367431640625f) { node = stack[sp]; return true; }
+    }
+    return false;
+}
+// one leaf primitive: the reference's own f64 test in the primitive's object frame, distances up to `bound` accepted
+template <bool CNT>
+__device__ __forceinline__ double ch_prim_test(const DevScene& S, const uint2 pr, const Ray& ray, const RayTri& q, double bound, AhLocal& L, ClosestCounters* c) {
+    const uint32_t obj = pr.y & ~LUMO_AH_INSTANCED;
+    if (pr.x & LUMO_AH_SPHERE) {
+        if (CNT) c->spheres++;
+        const Ray lr = (pr.y & LUMO_AH_INSTANCED) ? to_local<false>(S, S.objects[obj], ray, nullptr) : ray;
+        return sphere_hit_t(S.spheres[pr.x & ~LUMO_AH_SPHERE].radius, lr, 0.0, bound);
+    }
+    if (CNT) c->tris++;
+    Ray lr = ray; RayTri lq = q;
+    if (pr.y & LUMO_AH_INSTANCED) {
+        const int inst = S.objects[obj].inst;
+        if (inst != L.cur) {
+            RayCtx lc; make_ctx(to_local<false>(S, S.objects[obj], ray, nullptr), lc);
+            ah_local_store(L, lc); L.cur = inst;
+        }
+        ah_local_load(L, lr, lq);
+    }
+    TriHit th;
+    return tri_hit<false, false>(S.tri_verts + pr.x, lr, lq, 0.0, bound, th, nullptr) ? th.t : LUMO_INF;
+}
+
+// Source: n(), load(i, Ray&, t_max&).
+template <bool CNT, class Source>
+__global__ void __launch_bounds__(128, 4) k_closest_bvh(const __grid_constant__ DevScene S, const Source src, const ClosestScratch Q, ClosestCounters* gc) {
+    __shared__ double local_ctx[LUMO_AH_LOCAL_DOUBLES * 128];
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n = src.n();
+    const uint32_t n_objects = S.P.n_objects;
+    ClosestCounters cnt = {0, 0, 0, 0, 0, 0};
+    AhLocal L; L.slot = local_ctx + threadIdx.x; L.stride = 128; L.cur = -1;
+    uint32_t stack[LUMO_CH_STACK]; float stack_t[LUMO_CH_STACK];
+    bool active = false, exhausted = false;
+    uint32_t i = 0, node = 0, leaf_pos = 0, leaf_end = 0, o1 = LUMO_NONE, ol = LUMO_NONE, flags = 0;
+    int sp = 0;
+    Ray r; RayTri q; AhRay a;
+    double t1 = 0.0, tl = 0.0, s1 = 0.0, sl = 0.0;     // nearest per group; nearest of any other object per group (conservative)
+    r.o = d3(0, 0, 0); r.d = d3(0, 0, 1); q = ray_tri_setup(r); a = ah_make_ray(r, 0.0);
+    for (;;) {
+        const uint32_t free_m = __ballot_sync(0xFFFFFFFFu, !active && !exhausted);
+        const uint32_t busy_m = __ballot_sync(0xFFFFFFFFu, active);
+        if (free_m && ((uint32_t)__popc(free_m) >= LUMO_CH_REFILL || busy_m == 0u)) {
+            uint32_t base = 0;
+            if (lane == (uint32_t)(__ffs(free_m) - 1)) base = atomicAdd(&Q.counters[0], (uint32_t)__popc(free_m));
+            base = __shfl_sync(0xFFFFFFFFu, base, __ffs(free_m) - 1);
+            if (!active && !exhausted) {
+                i = base + __popc(free_m & ((1u << lane) - 1u));
+                if (i < n) {
+                    double t_max; src.load(i, r, t_max);
+                    q = ray_tri_setup(r); a = ah_make_ray(r, t_max);
+                    t1 = t_max; tl = t_max; s1 = LUMO_INF; sl = LUMO_INF; o1 = LUMO_NONE; ol = LUMO_NONE; flags = 0;
+                    L.cur = -1; node = 0; sp = 0; leaf_pos = leaf_end = 0; active = true;
+                } else exhausted = true;
+            }
+        } else if (busy_m == 0u) break;
+        bool done = false;
+#pragma unroll 1
+        for (int step = 0; step < LUMO_CH_NODE_ROUND; step++) {
+            if (active && !done && leaf_pos == leaf_end && !(node & LUMO_AH_LEAF)) {
+                bool over = false;
+                if (!ch_node_step<CNT>(S, a, node, stack, stack_t, sp, over, &cnt)) { if (!ch_pop(a, node, stack, stack_t, sp)) done = true; }
+                if (over) { flags |= 4u; done = true; }
+            }
+        }
+        if (active && !done && leaf_pos == leaf_end && (node & LUMO_AH_LEAF)) { leaf_pos = node & 0x07FFFFFFu; leaf_end = leaf_pos + ((node >> 27) & 0xFu) + 1u; }
+        if (active && !done && leaf_pos < leaf_end) {
+            const uint2 pr = __ldg(reinterpret_cast<const uint2*>(S.ah_prims + leaf_pos));
+            if (CNT) cnt.prims++;
+            const uint32_t obj = pr.y & ~LUMO_AH_INSTANCED;
+            leaf_pos++;
+            if (obj < n_objects) {
+                const double t = ch_prim_test<CNT>(S, pr, r, q, t1, L, &cnt);
+                if (t <= t1) {                                   // distances equal to the bound matter: a tie sends the ray to the reference traversal
+                    if (obj == o1) { if (t < t1) t1 = t; }
+                    else if (t < t1 || o1 == LUMO_NONE) { if (o1 != LUMO_NONE) s1 = fmin(s1, t1); t1 = t; o1 = obj; }
+                    else s1 = fmin(s1, t);
+                    float tm = (float)t1; if ((double)tm < t1) tm = nextafterf(tm, INFINITY);
+                    a.tmax = tm;                                 // nothing beyond the nearest object hit is of interest (lights: only below it)
+                }
+            } else {
+                const double bound = fmin(t1, tl);
+                const double t = ch_prim_test<CNT>(S, pr, r, q, bound, L, &cnt);
+                if (t <= bound) {
+                    if (obj == ol) { if (t < tl) tl = t; }
+                    else if (t < tl || ol == LUMO_NONE) { if (ol != LUMO_NONE) sl = fmin(sl, tl); tl = t; ol = obj; }
+                    else sl = fmin(sl, t);
+                }
+            }
+            if (leaf_pos == leaf_end) { if (!ch_pop(a, node, stack, stack_t, sp)) done = true; }
+        }
+        if (done) {
+            if (o1 != LUMO_NONE && s1 <= t1) flags |= 1u;
+            if (ol != LUMO_NONE && sl <= tl) flags |= 2u;
+            Q.t1[i] = t1; Q.tl[i] = tl; Q.o1[i] = o1; Q.ol[i] = ol; Q.flags[i] = flags;
+            active = false;
+        }
+    }
+    if (CNT) { atomicAdd(&gc->nodes, cnt.nodes); atomicAdd(&gc->prims, cnt.prims); atomicAdd(&gc->tris, cnt.tris); atomicAdd(&gc->spheres, cnt.spheres); }
+}
+
+// the box tests of the object-BVH nodes above `obj` (bvh.rs:333-335).  When the reference reaches them its bound tt is
+// above t_hit (every other object's hits are), so passing with tt = t_hit implies passing with the reference's tt.
+template <bool CNT>
+__device__ __forceinline__ bool ch_path_ok(const DevScene& S, uint32_t obj, const RayCtx& w, double t_hit, Counters* c) {
+    const uint32_t p0 = S.obj_path_off[obj], p1 = S.obj_path_off[obj + 1];
+    for (uint32_t p = p0; p < p1; p++) {
+        const LumoTlasNode* node = S.tlas + S.obj_path[p];
+        LUMO_CNT(tlas);
+        double t_start, t_end;
+        box_intersect(node->lo, node->hi, w.r.o, w.inv, t_start, t_end);
+        t_start = fmax(t_start, 0.0); t_end = fmin(t_end, t_hit);
+        if (!(t_start <= t_end)) return false;
+    }
+    return true;
+}
+__device__ __forceinline__ bool same_bits(double a, double b) { return __double_as_longlong(a) == __double_as_longlong(b); }
+
+// Sink: store(i, have, HitRec) — the final hit record of ray i.
+template <bool CNT, class Source, class Sink>
+__global__ void __launch_bounds__(128, LUMO_WAVE_TRACE_BLOCKS) k_closest_finish(const __grid_constant__ DevScene S, const Source src, const Sink sink, const ClosestScratch Q, Counters* vc) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n = src.n();
+    Counters cnt = {0, 0, 0, 0, 0, 0};
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&Q.counters[1], 32u);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= n) break;
+        const uint32_t i = base + lane;
+        bool again = false;
+        if (i < n) {
+            Ray ray; double t_max; src.load(i, ray, t_max);
+            const uint32_t o1 = Q.o1[i], ol = Q.ol[i], flags = Q.flags[i];
+            const double t1 = Q.t1[i], tl = Q.tl[i];
+            HitRec h; bool have = false;
+            double t_h = t_max;
+            if (flags & 4u) again = true;
+            RayCtx w;
+            if (!again && (o1 != LUMO_NONE || ol != LUMO_NONE)) make_ctx(ray, w);
+            if (!again && o1 != LUMO_NONE) {
+                double any_t;
+                if ((flags & 1u) || !ch_path_ok<CNT>(S, o1, w, t1, &cnt)) again = true;
+                else if (!object_hit<CNT, 64, LUMO_WAVE_KD_ROUND>(S, S.objects[o1], w, 0.0, t_max, h, &cnt, &any_t)) again = true;     // a rejected full hit empties the whole group
+                else if (!same_bits(any_t, t1) || !same_bits(h.t, t1)) again = true;
+                else { h.obj = o1; have = true; t_h = h.t; }
+            }
+            if (!again && ol != LUMO_NONE && tl < t_h) {       // Scene::hit: lights with t_max = the objects' hit; a light has to be strictly nearer
+                HitRec hl; double any_t;
+                if ((flags & 2u) || !ch_path_ok<CNT>(S, ol, w, tl, &cnt)) again = true;
+                else if (!object_hit<CNT, 64, LUMO_WAVE_KD_ROUND>(S, S.objects[ol], w, 0.0, t_h, hl, &cnt, &any_t)) again = true;
+                else if (!same_bits(any_t, tl)) again = true;
+                else { hl.obj = ol; h = hl; have = true; }
+            }
+            if (!again) sink.store(i, have, h);
+        }
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, again);
+        if (m) {
+            uint32_t b = 0;
+            if (lane == (uint32_t)(__ffs(m) - 1)) b = atomicAdd(&Q.counters[2], (uint32_t)__popc(m));
+            b = __shfl_sync(0xFFFFFFFFu, b, __ffs(m) - 1);
+            if (again) Q.fallback_i[b + __popc(m & ((1u << lane) - 1u))] = i;
+        }
+    }
+    if (CNT) { atomicAdd(&vc->tlas, cnt.tlas); atomicAdd(&vc->inst, cnt.inst); atomicAdd(&vc->kd, cnt.kd); atomicAdd(&vc->leaf, cnt.leaf); atomicAdd(&vc->tri, cnt.tri); atomicAdd(&vc->sphere, cnt.sphere); }
+}
+
+template <bool CNT, class Source, class Sink>
+__global__ void __launch_bounds__(128, LUMO_WAVE_TRACE_BLOCKS) k_closest_fallback(const __grid_constant__ DevScene S, const Source src, const Sink sink, const ClosestScratch Q, Counters* vc, ClosestCounters* gc) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n = Q.counters[2];
+    Counters cnt = {0, 0, 0, 0, 0, 0};
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&Q.counters[3], 32u);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= n) break;
+        const uint32_t j = base + lane;
+        if (j < n) {
+            const uint32_t i = Q.fallback_i[j];
+            Ray ray; double t_max; src.load(i, ray, t_max);
+            HitRec h;
+            const bool have = scene_hit<CNT, LUMO_WAVE_KD_ROUND>(S, ray, t_max, h, &cnt);
+            sink.store(i, have, h);
+        }
+    }
+    if (CNT) {
+        atomicAdd(&vc->tlas, cnt.tlas); atomicAdd(&vc->inst, cnt.inst); atomicAdd(&vc->kd, cnt.kd); atomicAdd(&vc->leaf, cnt.leaf); atomicAdd(&vc->tri, cnt.tri); atomicAdd(&vc->sphere, cnt.sphere);
+        if (blockIdx.x == 0 && threadIdx.x == 0) { atomicAdd(&gc->fallback, (unsigned long long)n); atomicAdd(&gc->rays, (unsigned long long)src.n()); }
+    }
+}
+
+}  // namespace lumo_dev

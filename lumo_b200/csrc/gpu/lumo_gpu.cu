@@ -36,6 +36,8 @@ struct lumo_ctx {
     Counters* d_visit = nullptr;   // traversal visit counters (CNT passes): [0] closest-hit kernels, [1] occlusion kernels
     int count_visits = 0;
     AhCounters* d_ah = nullptr;    // occlusion-BVH counters (CNT passes and LUMO_OCCLUDE_CHECK)
+    ClosestCounters* d_ch = nullptr;   // closest-hit pipeline counters (CNT passes)
+    int closest_faithful = 0;      // LUMO_CLOSEST_FAITHFUL=1: Scene::hit replays the reference traversal for every ray (k_wave_trace) instead of closest.cuh
     void* occl_mem = nullptr; size_t occl_bytes = 0;   // queues of the batch occlusion entry point (lumo_gpu_trace_any)
     int occl_faithful = 0;         // LUMO_OCCLUDE_FAITHFUL=1: shadow rays replay the reference's object BVH + kd-trees (k_wave_occlude) instead of the occlusion BVH
     int occl_check = 0;            // LUMO_OCCLUDE_CHECK=1: run both on every shadow ray of a render and count disagreements (counters[7] high half)
@@ -85,6 +87,9 @@ extern "C" int32_t lumo_gpu_ctx_create(int32_t device, lumo_ctx** out) {
     { const char* e = std::getenv("LUMO_OCCLUDE_CHECK"); if (e) ctx->occl_check = std::atoi(e) != 0; }
     CU(cudaMalloc(&ctx->d_ah, sizeof(AhCounters)));
     CU(cudaMemset(ctx->d_ah, 0, sizeof(AhCounters)));
+    { const char* e = std::getenv("LUMO_CLOSEST_FAITHFUL"); if (e) ctx->closest_faithful = std::atoi(e) != 0; }
+    CU(cudaMalloc(&ctx->d_ch, sizeof(ClosestCounters)));
+    CU(cudaMemset(ctx->d_ch, 0, sizeof(ClosestCounters)));
     *out = ctx; return LUMO_OK;
 }
 extern "C" int32_t lumo_gpu_ctx_destroy(lumo_ctx* ctx) {
@@ -97,6 +102,7 @@ extern "C" int32_t lumo_gpu_ctx_destroy(lumo_ctx* ctx) {
     if (ctx->rgb_mem) cudaFree(ctx->rgb_mem);
     if (ctx->d_cursor) cudaFree(ctx->d_cursor);
     if (ctx->d_ah) cudaFree(ctx->d_ah);
+    if (ctx->d_ch) cudaFree(ctx->d_ch);
     if (ctx->occl_mem) cudaFree(ctx->occl_mem);
     if (ctx->blob_cache) cudaFree(ctx->blob_cache);
     if (ctx->d_visit) cudaFree(ctx->d_visit);
@@ -126,6 +132,24 @@ extern "C" int32_t lumo_gpu_ctx_count_visits(lumo_ctx* ctx, int32_t enable) {
     ctx->count_visits = enable ? 1 : 0;
     CU(cudaMemset(ctx->d_visit, 0, 2 * sizeof(Counters)));
     CU(cudaMemset(ctx->d_ah, 0, sizeof(AhCounters)));
+    CU(cudaMemset(ctx->d_ch, 0, sizeof(ClosestCounters)));
+    return LUMO_OK;
+}
+// Closest hits (Scene::hit) go through the world-space BVH with the reference traversal run on the winning object only, and
+// through the full reference traversal wherever that is not provably the same (csrc/gpu/closest.cuh).  mode 0: that (default);
+// 1: the reference traversal for every ray.  stats (only while visit counting is on): [0] BVH nodes, [1] leaf primitives,
+// [2] triangle tests, [3] sphere tests, [4] rays sent to the reference traversal, [5] rays.
+extern "C" int32_t lumo_gpu_ctx_closest_mode(lumo_ctx* ctx, int32_t mode) {
+    if (!ctx || mode < 0 || mode > 1) return fail(LUMO_ERR_INVALID, "closest_mode: bad arguments");
+    ctx->closest_faithful = mode == 1;
+    return LUMO_OK;
+}
+extern "C" int32_t lumo_gpu_ctx_closest_stats(lumo_ctx* ctx, uint64_t* out6) {
+    if (!ctx || !out6) return fail(LUMO_ERR_INVALID, "closest_stats: null pointer");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ClosestCounters c; CU(cudaMemcpy(&c, ctx->d_ch, sizeof c, cudaMemcpyDeviceToHost));
+    out6[0] = c.nodes; out6[1] = c.prims; out6[2] = c.tris; out6[3] = c.spheres; out6[4] = c.fallback; out6[5] = c.rays;
     return LUMO_OK;
 }
 // Counters of the occlusion-BVH kernels (occlude.cuh) since the last lumo_gpu_ctx_count_visits call: [0] BVH nodes visited,
@@ -394,6 +418,25 @@ static int32_t launch_occlusion(lumo_scene* sc, const Source& src, const Sink& s
     return LUMO_OK;
 }
 
+// Scene::hit through closest.cuh: BVH walk -> finish on the winning object -> reference traversal for the rest.  Q.counters must be zero.
+template <class Source, class Sink>
+static int32_t launch_closest(lumo_scene* sc, const Source& src, const Sink& sink, const ClosestScratch& Q, cudaStream_t st) {
+    lumo_ctx* ctx = sc->ctx;
+    const int g1 = ctx->sm_count * 4, g2 = ctx->sm_count * LUMO_WAVE_TRACE_BLOCKS;
+    if (ctx->count_visits) {
+        k_closest_bvh<true><<<g1, 128, 0, st>>>(sc->S, src, Q, ctx->d_ch);
+        k_closest_finish<true><<<g2, 128, 0, st>>>(sc->S, src, sink, Q, ctx->d_visit);
+        k_closest_fallback<true><<<g2, 128, 0, st>>>(sc->S, src, sink, Q, ctx->d_visit, ctx->d_ch);
+    } else {
+        k_closest_bvh<false><<<g1, 128, 0, st>>>(sc->S, src, Q, nullptr);
+        k_closest_finish<false><<<g2, 128, 0, st>>>(sc->S, src, sink, Q, nullptr);
+        k_closest_fallback<false><<<g2, 128, 0, st>>>(sc->S, src, sink, Q, nullptr, nullptr);
+    }
+    ctx->launches += 3;
+    CU(cudaGetLastError());
+    return LUMO_OK;
+}
+
 template <int MODE>
 static int32_t launch_batch(lumo_scene* sc, const double* o_dev, const double* d_dev, const double* tmax_dev, uint64_t n, unsigned long long* next_dev,
                             uint32_t* obj, uint32_t* tri, double* t, double* bary, uint8_t* occ) {
@@ -412,6 +455,25 @@ static int32_t launch_batch(lumo_scene* sc, const double* o_dev, const double* d
             CU(cudaMemsetAsync(Q.counters, 0, 32, ctx->stream));
             BatchShadowSource src{o_dev + 3 * c0, d_dev + 3 * c0, tmax_dev + c0, cnt}; BatchShadowSink sink{occ + c0};
             int32_t rc = launch_occlusion(sc, src, sink, Q, ctx->stream); if (rc != LUMO_OK) return rc;
+        }
+        return LUMO_OK;
+    }
+    if (MODE == 0 && !ctx->closest_faithful) {
+        // per ray of a chunk: t1, tl (8 B each), o1, ol, flags, fallback index (4 B each); 4 counters
+        const uint64_t CH = 1ull << 26;
+        const size_t need = (size_t)std::min<uint64_t>(n, CH) * 32 + 256;
+        if (need > ctx->occl_bytes) {
+            if (ctx->occl_mem) { cudaFree(ctx->occl_mem); ctx->occl_mem = nullptr; ctx->occl_bytes = 0; }
+            CU(cudaMalloc(&ctx->occl_mem, need)); ctx->occl_bytes = need;
+        }
+        for (uint64_t c0 = 0; c0 < n; c0 += CH) {
+            const uint32_t cnt = (uint32_t)std::min<uint64_t>(CH, n - c0);
+            ClosestScratch Q; Q.counters = (uint32_t*)ctx->occl_mem; Q.t1 = (double*)((uint8_t*)ctx->occl_mem + 256); Q.tl = Q.t1 + cnt;
+            Q.o1 = (uint32_t*)(Q.tl + cnt); Q.ol = Q.o1 + cnt; Q.flags = Q.ol + cnt; Q.fallback_i = Q.flags + cnt;
+            CU(cudaMemsetAsync(Q.counters, 0, 16, ctx->stream));
+            BatchRaySource src{o_dev + 3 * c0, d_dev + 3 * c0, tmax_dev ? tmax_dev + c0 : nullptr, cnt};
+            BatchHitSink sink{obj + c0, tri + c0, t + c0, bary + 2 * c0};
+            int32_t rc = launch_closest(sc, src, sink, Q, ctx->stream); if (rc != LUMO_OK) return rc;
         }
         return LUMO_OK;
     }
@@ -501,6 +563,7 @@ static void carve_wave(Wave& W, Carver& c, uint32_t N, uint32_t shadow_cap, uint
     W.sox = c.take<double>(C); W.soy = c.take<double>(C); W.soz = c.take<double>(C); W.sdx = c.take<double>(C); W.sdy = c.take<double>(C); W.sdz = c.take<double>(C);
     W.stmax = c.take<double>(C); W.sc = c.take<double>(4 * C); W.sslot = c.take<uint32_t>(C);
     W.oq_i = c.take<uint32_t>(C); W.oq_obj = c.take<uint32_t>(C); W.oq_fb = c.take<uint32_t>(C); W.occ_record = c.take<uint8_t>(C);
+    W.ch_t1 = c.take<double>(N); W.ch_tl = c.take<double>(N); W.ch_o1 = c.take<uint32_t>(N); W.ch_ol = c.take<uint32_t>(N); W.ch_flags = c.take<uint32_t>(N); W.ch_fb = c.take<uint32_t>(N);
     W.nee_ctx = c.take<double>((size_t)LUMO_NEE_CTX_DOUBLES * N); W.nee_meta = c.take<uint32_t>(N);
     { NeeTermQueue& T = W.tq; T.ox = c.take<double>(C); T.oy = c.take<double>(C); T.oz = c.take<double>(C); T.dx = c.take<double>(C); T.dy = c.take<double>(C); T.dz = c.take<double>(C);
       T.wx = c.take<double>(C); T.wy = c.take<double>(C); T.wz = c.take<double>(C); T.tmax = c.take<double>(C); T.p_lig = c.take<double>(C); T.pdf_light = c.take<double>(C);
@@ -563,8 +626,15 @@ static int32_t run_wave(lumo_scene* sc, const Wave& W, WaveParams P, uint64_t& i
             k_retire<<<rgrid, 256, 0, st>>>(sc->S, W, P);
             k_compact<<<rgrid, 256, 0, st>>>(W);
             CU(cudaEventRecord(ev[1], st));
-            if (ctx->count_visits) k_wave_trace<true><<<tgrid, 128, 0, st>>>(sc->S, W, P.cur, ctx->d_visit);
-            else k_wave_trace<false><<<tgrid, 128, 0, st>>>(sc->S, W, P.cur, nullptr);
+            if (ctx->closest_faithful) {
+                if (ctx->count_visits) k_wave_trace<true><<<tgrid, 128, 0, st>>>(sc->S, W, P.cur, ctx->d_visit);
+                else k_wave_trace<false><<<tgrid, 128, 0, st>>>(sc->S, W, P.cur, nullptr);
+            } else {
+                WaveRaySource src{W, P.cur}; WaveHitSink sink{W};
+                ClosestScratch Q; Q.t1 = W.ch_t1; Q.tl = W.ch_tl; Q.o1 = W.ch_o1; Q.ol = W.ch_ol; Q.flags = W.ch_flags; Q.fallback_i = W.ch_fb; Q.counters = W.it->closest;
+                int32_t rc = launch_closest(sc, src, sink, Q, st); if (rc != LUMO_OK) return rc;
+                k_wave_classify<<<rgrid, 256, 0, st>>>(sc->S, W);
+            }
             CU(cudaEventRecord(ev[2], st));
             k_terminal<<<sgrid, 128, 0, st>>>(sc->S, W, P);
             ctx->launches += 3;
@@ -730,7 +800,8 @@ static int32_t render_impl(lumo_scene* sc, const lumo_render_params* rp, double*
     lumo_ctx* ctx = sc->ctx;
     const LumoSceneParams& SP = sc->S.P;
     if (rp->integrator < 0 || rp->integrator > 2) return fail(LUMO_ERR_INVALID, "render: unknown integrator");
-    if (rp->sampler < 0 || rp->sampler > 2) return fail(LUMO_ERR_INVALID, "render: unknown sampler");
+    if (rp->sampler < 0 || rp->sampler > 3) return fail(LUMO_ERR_INVALID, "render: unknown sampler");
+    if (rp->sampler == LUMO_SAMPLER_SOBOL && rp->total_spp > 1023u) return fail(LUMO_ERR_INVALID, "render: the Sobol sampler has 1023 points (samplers/sobol_seq.rs:3)");
     if (rp->tone_map < 0 || rp->tone_map > 2) return fail(LUMO_ERR_INVALID, "render: unknown tone map");
     if (rp->spp_end < rp->spp_begin || rp->spp_end > rp->total_spp || rp->total_spp == 0) return fail(LUMO_ERR_INVALID, "render: bad sample range");
     if (!(rp->rr_delta >= 0.0)) return fail(LUMO_ERR_INVALID, "render: rr_delta must be >= 0");

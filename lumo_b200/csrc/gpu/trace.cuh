@@ -173,7 +173,7 @@ struct KdStackEntry { uint32_t node; double t_start, t_end; };
 #endif
 template <bool GEO, bool CNT, int STACK = 64, int ROUND = LUMO_KD_ROUND>
 __device__ __forceinline__ bool kd_hit(const DevScene& S, const LumoKdTree* tree, const RayCtx& ctx, double t_min, double t_max,
-                                    double& t_out, uint32_t& tri_out, D3& bary_out, Counters* c) {
+                                    double& t_out, uint32_t& tri_out, D3& bary_out, Counters* c, double* t_first = nullptr) {
     const Ray r = ctx.r;
     const RayTri q = ctx.q;
     const D3 inv = ctx.inv;
@@ -234,7 +234,8 @@ __device__ __forceinline__ bool kd_hit(const DevScene& S, const LumoKdTree* tree
         if (tri == LUMO_NONE) { if (ROUND == 0 || finished) break; continue; }
         TriHit th;
         const double t = tri_hit<false, CNT>(tris + tri, r, q, t_min, t_end, th, c) ? th.t : LUMO_INF;
-        if (GEO) { if (t < t_end) { t_end = t; t_hit = t; idx = tri; } }
+        // t_first: the distance the any-hit form of this walk (GEO = false) would have returned — both forms are the same walk up to the first accepted triangle
+        if (GEO) { if (t < t_end) { if (t_first && idx == LUMO_NONE) *t_first = t; t_end = t; t_hit = t; idx = tri; } }
         else { if (t < t_end) { t_out = t; return true; } }
     }
     if (!GEO) { t_out = LUMO_INF; return false; }
@@ -367,14 +368,18 @@ struct HitRec { double t; D3 bary; uint32_t obj, tri; };
 
 // Object::hit for one object record: distance + which triangle + barycentrics (the rest of `Hit`
 // is rebuilt from these by the shading kernels, shade.cuh reconstruct_hit).
+// any_t (optional): Object::hit_t of the same object and arguments, i.e. the distance the selection pass of BVH::_hit compares
+// (bvh.rs:346) — for a kd-tree the first triangle the walk accepts, for a sphere Sphere::hit_t, for a triangle its hit_t.
 template <bool CNT, int STACK = 64, int ROUND = LUMO_KD_ROUND>
-__device__ __noinline__ bool object_hit(const DevScene& S, const LumoObject& o, const RayCtx& w, double t_min, double t_max, HitRec& h, Counters* c) {
+__device__ __noinline__ bool object_hit(const DevScene& S, const LumoObject& o, const RayCtx& w, double t_min, double t_max, HitRec& h, Counters* c, double* any_t = nullptr) {
     LUMO_LOCAL_CTX(S, o, w, c);
+    if (any_t) *any_t = LUMO_INF;
     switch (o.kind) {
     case LOBJ_KD: case LOBJ_RECT:
-        return kd_hit<true, CNT, STACK, ROUND>(S, S.kd_trees + o.geom, l, t_min, t_max, h.t, h.tri, h.bary, c);
+        return kd_hit<true, CNT, STACK, ROUND>(S, S.kd_trees + o.geom, l, t_min, t_max, h.t, h.tri, h.bary, c, any_t);
     case LOBJ_SPHERE: {
         LUMO_CNT(sphere);
+        if (any_t) *any_t = sphere_hit_t(S.spheres[o.geom].radius, l.r, t_min, t_max);
         double t = sphere_hit(S.spheres[o.geom].radius, l.r, t_min, t_max);
         if (!(t < LUMO_INF)) return false;
         h.t = t; h.tri = 0; h.bary = d3(0, 0, 0);
@@ -382,6 +387,7 @@ __device__ __noinline__ bool object_hit(const DevScene& S, const LumoObject& o, 
     }
     default: {
         TriHit th;
+        if (any_t) { TriHit ta; *any_t = tri_hit<false, false>(S.tri_verts + o.geom, l.r, l.q, t_min, t_max, ta, nullptr) ? ta.t : LUMO_INF; }
         if (!tri_hit<true, CNT>(S.tri_verts + o.geom, l.r, l.q, t_min, t_max, th, c)) return false;
         h.t = th.t; h.tri = 0; h.bary = th.bary;
         return true;

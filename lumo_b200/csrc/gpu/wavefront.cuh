@@ -18,6 +18,7 @@
 #pragma once
 #include "shade.cuh"
 #include "occlude.cuh"
+#include "closest.cuh"
 #include <cooperative_groups.h>
 #include <cstdio>
 
@@ -36,6 +37,7 @@ struct IterCounters {   // zeroed before every iteration
     uint32_t n_class[LUMO_N_CLASSES], pad[3];
     uint32_t occl[8];   // OcclQueues::counters of the occlusion-BVH kernels (occlude.cuh)
     uint32_t n_terms, pad2[3];   // NEE term queue
+    uint32_t closest[4];         // ClosestScratch::counters of the closest-hit pipeline (closest.cuh)
 };
 // Counters that live across iterations (double-buffered by the parity of the iteration): done[p] = slots whose
 // path ended in an iteration of parity p, retired into the film (and refilled) at the start of the next one;
@@ -70,6 +72,7 @@ struct Wave {
     uint32_t* cls[LUMO_N_CLASSES];       // per-class shade queues (slot indices)
     // shadow queue (SoA)
     double *sox, *soy, *soz, *sdx, *sdy, *sdz, *stmax, *sc; uint32_t* sslot;
+    double *ch_t1, *ch_tl; uint32_t *ch_o1, *ch_ol, *ch_flags, *ch_fb;   // closest-hit pipeline: per-ray scratch of k_closest_bvh, fallback queue (capacity n_slots)
     double* nee_ctx; uint32_t* nee_meta; NeeTermQueue tq;   // NEE: per-slot shading context [k * n_slots + slot] (17 doubles), term queue
     uint32_t *oq_i, *oq_obj, *oq_fb; uint8_t* occ_record;   // occlusion-BVH pipeline: confirm queue, fallback queue; verdicts (LUMO_OCCLUDE_CHECK only)
     IterCounters* it; RunCounters* run; QueueCounters* qc;
@@ -111,6 +114,21 @@ __device__ __forceinline__ void store_c4(double* a, uint32_t n, uint32_t slot, c
 // produced independently.
 __device__ __forceinline__ void raster_jitter(const WaveParams& P, uint32_t pixel, uint32_t s, Rng& rng, double& jx, double& jy) {
     if (P.sampler == 0) { jx = rng_float(rng); jy = rng_float(rng); return; }
+    if (P.sampler == 3) {
+        // SobolSampler (samplers.rs:193-247, samplers/sobol_seq.rs): point s + 1 of two Gray-code Sobol dimensions of degree 10
+        // (direction numbers m << (64 - i - 1)), XOR-scrambled with the pixel's sampler seed.  The reference steps
+        // prev ^= V[ctz(n)]; unrolled that is the XOR of V[i] over the set bits of gray(n) = n ^ (n >> 1), so any sample
+        // index is produced independently.  The seed is the pixel's Philox key where the reference draws it from the tile stream.
+        const unsigned long long m1[10] = {1, 1, 7, 15, 5, 19, 69, 51, 121, 695}, m2[10] = {1, 1, 7, 7, 7, 53, 57, 229, 473, 533};
+        Rng keyr = rng_make(P.seed, pixel, 0xFFFFFFFFu, 1u, 0u);
+        const unsigned long long k = rng_u64(keyr);
+        const unsigned long long n = (unsigned long long)s + 1ull, g = n ^ (n >> 1);
+        unsigned long long a = 0ull, b = 0ull;
+#pragma unroll
+        for (int i = 0; i < 10; i++) if ((g >> i) & 1ull) { a ^= m1[i] << (64 - i - 1); b ^= m2[i] << (64 - i - 1); }
+        jx = __ull2double_rn(a ^ k) * 5.421010862427522170037e-20; jy = __ull2double_rn(b ^ k) * 5.421010862427522170037e-20;
+        return;
+    }
     const unsigned long long total = P.total_spp;
     const unsigned long long dim = sat_u64(ceil(sqrt((double)total)));
     const double s0x = 1.0 / (double)dim, s0y = (double)dim / (double)total;
@@ -250,6 +268,64 @@ __global__ void __launch_bounds__(128, LUMO_WAVE_TRACE_BLOCKS) k_wave_trace(cons
     if (lane == 0 && threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(&W.run->closest, (unsigned long long)n);
     if (CNT) { atomicAdd(&gc->tlas, cnt.tlas); atomicAdd(&gc->inst, cnt.inst); atomicAdd(&gc->kd, cnt.kd); atomicAdd(&gc->leaf, cnt.leaf); atomicAdd(&gc->tri, cnt.tri); atomicAdd(&gc->sphere, cnt.sphere); }
 }
+
+// ---- the same through the closest-hit pipeline of closest.cuh: ray source, hit sink, class binning --------------------------------
+struct WaveRaySource {
+    Wave W; uint32_t cur;
+    __device__ __forceinline__ uint32_t n() const { return W.it->n_active; }
+    __device__ __forceinline__ void load(uint32_t i, Ray& r, double& t_max) const {
+        const uint32_t slot = W.active[i];
+        r.o = d3(W.ox[cur][slot], W.oy[cur][slot], W.oz[cur][slot]); r.d = d3(W.dx[cur][slot], W.dy[cur][slot], W.dz[cur][slot]);
+        t_max = LUMO_INF;
+    }
+};
+struct WaveHitSink {
+    Wave W;
+    __device__ __forceinline__ void store(uint32_t i, bool have, const HitRec& h) const {
+        const uint32_t slot = W.active[i];
+        if (have) { W.ht[slot] = h.t; W.hb0[slot] = h.bary.x; W.hb1[slot] = h.bary.y; W.hb2[slot] = h.bary.z; W.hobj[slot] = h.obj; W.htri[slot] = h.tri; }
+        else W.hobj[slot] = LUMO_NONE;
+    }
+};
+// stream compaction of the traced slots into the per-class shade queues, in active-queue order (what k_wave_trace does at its end)
+__global__ void __launch_bounds__(256) k_wave_classify(const __grid_constant__ DevScene S, const __grid_constant__ Wave W) {
+    const uint32_t n = W.it->n_active, lane = threadIdx.x & 31u;
+    const uint32_t n_pad = (n + 31u) & ~31u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x) {
+        uint32_t slot = 0, klass = LUMO_N_CLASSES;
+        if (i < n) {
+            slot = W.active[i]; klass = 0;
+            const uint32_t obj = W.hobj[slot];
+            if (obj != LUMO_NONE) { const uint32_t kind = S.materials[S.objects[obj].material].kind; if (kind >= LMAT_LAMBERTIAN && kind <= LMAT_MFDIELECTRIC) klass = kind; }
+        }
+#pragma unroll
+        for (uint32_t c = 0; c < LUMO_N_CLASSES; c++) {
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, klass == c);
+            if (m) {
+                uint32_t b = 0;
+                if (lane == (uint32_t)(__ffs(m) - 1)) b = atomicAdd(&W.it->n_class[c], (uint32_t)__popc(m));
+                b = __shfl_sync(0xFFFFFFFFu, b, __ffs(m) - 1);
+                if (klass == c) W.cls[c][b + __popc(m & ((1u << lane) - 1u))] = slot;
+            }
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&W.run->closest, (unsigned long long)n);
+}
+// caller-supplied ray batches (lumo_gpu_trace_closest)
+struct BatchRaySource {
+    const double *o, *d, *t_max; uint32_t count;
+    __device__ __forceinline__ uint32_t n() const { return count; }
+    __device__ __forceinline__ void load(uint32_t i, Ray& r, double& tm) const {
+        r.o = d3(o[3 * (size_t)i], o[3 * (size_t)i + 1], o[3 * (size_t)i + 2]); r.d = d3(d[3 * (size_t)i], d[3 * (size_t)i + 1], d[3 * (size_t)i + 2]); tm = t_max ? t_max[i] : LUMO_INF;
+    }
+};
+struct BatchHitSink {
+    uint32_t *obj, *tri; double *t, *bary;
+    __device__ __forceinline__ void store(uint32_t i, bool have, const HitRec& h) const {
+        if (have) { obj[i] = h.obj; tri[i] = h.tri; t[i] = h.t; bary[2 * (size_t)i] = h.bary.x; bary[2 * (size_t)i + 1] = h.bary.y; }
+        else { obj[i] = LUMO_NONE; tri[i] = LUMO_NONE; t[i] = LUMO_INF; bary[2 * (size_t)i] = 0.0; bary[2 * (size_t)i + 1] = 0.0; }
+    }
+};
 
 // ---- occlude: the occlusion half of Scene::hit_light over the shadow queue ------------------------
 template <bool CNT>

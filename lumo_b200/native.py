@@ -160,6 +160,8 @@ def gpu_lib():
         L.lumo_gpu_film_encode_dev.argtypes = [vp, vp, vp, C.c_uint64, C.c_double, C.c_double, C.c_int32, u8p, C.POINTER(C.c_float)]
         L.lumo_gpu_film_encode.argtypes = [vp, dp, dp, C.c_uint64, C.c_double, C.c_double, C.c_int32, u8p]
         L.lumo_gpu_render_multi.argtypes = [C.POINTER(vp), C.c_int32, C.POINTER(RenderParams), C.POINTER(FilmAccum)]
+        L.lumo_gpu_ctx_closest_mode.argtypes = [vp, C.c_int32]; L.lumo_gpu_ctx_closest_mode.restype = C.c_int32
+        L.lumo_gpu_ctx_closest_stats.argtypes = [vp, C.POINTER(C.c_uint64)]; L.lumo_gpu_ctx_closest_stats.restype = C.c_int32
         L.lumo_gpu_ctx_occlusion_mode.argtypes = [vp, C.c_int32]; L.lumo_gpu_ctx_occlusion_mode.restype = C.c_int32
         L.lumo_gpu_ctx_occlusion_stats.argtypes = [vp, C.POINTER(C.c_uint64)]; L.lumo_gpu_ctx_occlusion_stats.restype = C.c_int32
         L.lumo_gpu_fp64_peak.argtypes = [vp, dp, dp]; L.lumo_gpu_fp64_peak.restype = C.c_int32
@@ -204,6 +206,15 @@ class GpuContext:
         _check(gpu_lib().lumo_gpu_ctx_visits(self.h, out), "lumo_gpu_ctx_visits")
         names = ("tlas_nodes", "inst", "kd_nodes", "leaf_idx", "tri_tests", "sphere_tests")
         return dict(zip(names, (int(v) for v in out[:6]))), dict(zip(names, (int(v) for v in out[6:])))
+
+    def closest_mode(self, mode):
+        """0: world-space BVH + the reference traversal on the winning object, reference traversal where not provably equal (default); 1: reference traversal for every ray."""
+        _check(gpu_lib().lumo_gpu_ctx_closest_mode(self.h, int(mode)), "lumo_gpu_ctx_closest_mode")
+
+    def closest_stats(self):
+        out = (C.c_uint64 * 6)()
+        _check(gpu_lib().lumo_gpu_ctx_closest_stats(self.h, out), "lumo_gpu_ctx_closest_stats")
+        return dict(zip(("nodes", "prims", "tri_tests", "sphere_tests", "fallback", "rays"), (int(v) for v in out)))
 
     def occlusion_mode(self, mode):
         """0: occlusion BVH + confirmation (default); 1: the reference's traversal for shadow rays; 2: both, disagreements counted."""

@@ -215,11 +215,22 @@ static std::vector<size_t> gen_perm(Rng& rng, size_t n) {                       
     }
     return perm;
 }
-struct Sampler {   // Uniform / Jittered / MultiJittered (samplers.rs:54-192); Sobol not restated (needs its direction tables)
+// SobolSampler (samplers.rs:193-247, samplers/sobol_seq.rs:1-39): two Gray-code Sobol dimensions of degree 10, direction
+// numbers m << (64 - i - 1); a batch starts from the state after `batch * 256` steps; the pixel's sampler seed is XORed in.
+static const uint64_t SOBOL_M1[10] = {1, 1, 7, 15, 5, 19, 69, 51, 121, 695};     // dim 119 (sobol_seq.rs:7)
+static const uint64_t SOBOL_M2[10] = {1, 1, 7, 7, 7, 53, 57, 229, 473, 533};     // dim 103 (sobol_seq.rs:9)
+static inline uint64_t sobol_v(const uint64_t* m, int i) { return m[i] << (64 - i - 1); }
+struct Sampler {   // Uniform / Jittered / MultiJittered / Sobol (samplers.rs:54-247)
     int kind; uint64_t state, end, dim; Vec2 scale0, scale1; std::vector<size_t> px, py; Rng rng;
+    uint64_t sob_seed = 0, sob0 = 0, sob1 = 0;
     Sampler(int kind_, uint64_t batch, uint64_t samples, uint64_t seed) : kind(kind_), rng(Rng::xorshift(seed)) {
         uint64_t s0 = batch * SAMPLES_INCREMENT, s1 = std::min((batch + 1) * SAMPLES_INCREMENT, samples);
         state = s0; end = s1;
+        if (kind == 3) {                                   // BATCH_STATES[batch]: the sequence advanced s0 times (sobol_seq.rs:13-31)
+            sob_seed = seed;
+            for (uint64_t k = 1; k <= s0; k++) { const int tz = __builtin_ctzll(k); sob0 ^= sobol_v(SOBOL_M1, tz); sob1 ^= sobol_v(SOBOL_M2, tz); }
+            return;
+        }
         if (kind == 0) { state = 0; end = s1 - s0; return; }
         dim = sat_u64(std::ceil(std::sqrt((Float)samples)));
         scale0 = Vec2(1.0 / (Float)dim, (Float)dim / (Float)samples);
@@ -227,6 +238,13 @@ struct Sampler {   // Uniform / Jittered / MultiJittered (samplers.rs:54-192); S
     }
     bool next(Vec2& out) {
         if (state == end) return false;
+        if (kind == 3) {                                   // samplers.rs:218-247
+            state++;
+            const int tz = __builtin_ctzll(state);
+            sob0 ^= sobol_v(SOBOL_M1, tz); sob1 ^= sobol_v(SOBOL_M2, tz);
+            out = Vec2((Float)(sob0 ^ sob_seed) * 5.421010862427522170037e-20, (Float)(sob1 ^ sob_seed) * 5.421010862427522170037e-20);
+            return true;
+        }
         if (kind == 0) { state++; out = rng.gen_vec2(); return true; }
         uint64_t x0 = state % dim, y0 = state / dim;
         Vec2 off0 = scale0 * Vec2((Float)x0, (Float)y0);
@@ -355,6 +373,14 @@ static void render_reference(const Loaded& L, const RenderParams& P, FilmAccum& 
 // traversal code is the same restated reference code as above.
 static Vec2 counter_jitter(const RenderParams& P, uint32_t pixel, uint32_t s, Rng& rng) {
     if (P.sampler == 0) return rng.gen_vec2();
+    if (P.sampler == 3) {   // Sobol point s + 1 in closed form: the Gray-code recurrence unrolled, XOR of the direction numbers of the set bits of gray(n)
+        Rng keyr = Rng::counter(P.seed, pixel, 0xFFFFFFFFu, 1);
+        const uint64_t k = keyr.gen_u64();
+        const uint64_t n = (uint64_t)s + 1, g = n ^ (n >> 1);
+        uint64_t a = 0, b = 0;
+        for (int i = 0; i < 10; i++) if ((g >> i) & 1) { a ^= sobol_v(SOBOL_M1, i); b ^= sobol_v(SOBOL_M2, i); }
+        return Vec2((Float)(a ^ k) * 5.421010862427522170037e-20, (Float)(b ^ k) * 5.421010862427522170037e-20);
+    }
     uint64_t total = P.total_spp;
     uint64_t dim = sat_u64(std::ceil(std::sqrt((Float)total)));
     Vec2 scale0(1.0 / (Float)dim, (Float)dim / (Float)total);
@@ -731,6 +757,12 @@ void oracle_math_eval(int fn, const double* x, const double* y, uint64_t n, doub
         default: out[i] = lm_pow(a, b); break;
         }
     }
+}
+// samples of one pixel from the reference samplers (kind 0..3): out[2i], out[2i+1]; returns how many
+uint64_t oracle_sampler_points(int kind, uint64_t batch, uint64_t samples, uint64_t seed, uint64_t cap, double* out) {
+    Sampler sm(kind, batch, samples, seed); Vec2 v; uint64_t n = 0;
+    while (n < cap && sm.next(v)) { out[2 * n] = v.x; out[2 * n + 1] = v.y; n++; }
+    return n;
 }
 void oracle_xorshift(uint64_t seed, uint64_t n, uint64_t* out) { Rng r = Rng::xorshift(seed); for (uint64_t i = 0; i < n; i++) out[i] = r.gen_u64(); }
 void oracle_philox(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t stream, uint64_t n, uint64_t* out) { Rng r = Rng::counter(seed, pixel, sample, stream); for (uint64_t i = 0; i < n; i++) out[i] = r.gen_u64(); }

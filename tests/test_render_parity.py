@@ -1,13 +1,12 @@
 """G4: the wavefront integrators against the oracle run with the SAME counter-based random streams
-(oracle rng_mode=1).  Same draws + same operation order make a GPU path the same path as the
-oracle's until a libm-vs-CUDA last-bit difference in a sampled direction (sin/cos/atanh are not
-bit-reproducible) flips a geometric tie — e.g. the Cornell light is coplanar with the
-ceiling, and a spawned ray may or may not re-hit its own triangle.  Measured on B200: 0.3 % (flat
-Cornell walls) to 1.8 % (rough-metal and glass meshes, where curvature amplifies the last bit) of
-paths.  So: (1) per-sample comparison with a box filter — at least 94 % of pixels (2 samples each) bit-close;
-(2) unbiasedness — mean film value and ray counts within tolerances far below what a systematic
-error (a missed quirk of SURVEY Appendix A) would produce; (3) relMSE against the oracle no larger
-than the oracle's own seed-to-seed relMSE."""
+(oracle rng_mode=1).  Same draws + same operation order + the same transcendental functions
+(csrc/common/lumo_math.h is compiled into the device kernels, the host builder and the oracle alike) make
+every GPU path the oracle's path, decision for decision.  Round 1 — CUDA's libm on one side, glibc's on the
+other — lost 0.3-10 % of the pixels to last-bit differences in sampled directions flipping geometric ties;
+with the shared functions NO pixel differs (profiles/r2_parity_same_streams.txt: 21 scene x integrator
+combinations, 0 pixels beyond 1e-12).  So: (1) per-sample comparison — every pixel equal to the rounding of
+the film's atomic adds, closest-hit and cost counters equal exactly, RR thresholds equal to rounding;
+(2) relMSE against the oracle's reference schedule no larger than the oracle's own seed-to-seed relMSE."""
 import numpy as np
 import pytest
 import oracle_lib
@@ -43,14 +42,13 @@ def test_per_sample_parity_same_streams(name, integrator, spp, gpu_ctx):
     assert np.allclose(gpx[..., 3], epx[..., 3], rtol=1e-12, atol=0)
     # per-tile RR thresholds from the pilot passes: a tile whose 128 pilot paths all agree matches to rounding
     rel = np.abs(gdel / edel - 1)
-    assert np.median(rel) < 1e-9 and rel.max() < 0.5, (np.median(rel), rel.max())
-    # ray counts: equal unless a path flipped
-    assert abs(gcnt["closest"] - ecnt["closest"]) <= 0.01 * ecnt["closest"] + 8, (gcnt, ecnt)
-    assert abs(gcnt["cost"] - ecnt["cost"]) <= 0.01 * ecnt["cost"] + 8, (gcnt, ecnt)
+    assert rel.max() < 1e-12, (np.median(rel), rel.max())                      # the pilot paths are the same paths: sums differ by rounding only
+    # the same paths: the same number of closest-hit queries and the same reference-style cost, exactly
+    assert gcnt["closest"] == ecnt["closest"] and gcnt["cost"] == ecnt["cost"], (gcnt, ecnt)
+    assert gcnt["occlusion"] <= ecnt["occlusion"]                              # shadow rays whose MIS contribution is exactly zero are not queued on the device
     e, g = _rgb(epx), _rgb(gpx)
-    bad = (np.abs(g - e) > 1e-9 * (np.abs(e) + 1e-6)).any(axis=-1)
-    assert bad.mean() <= 0.06, ("pixels whose samples differ beyond rounding", float(bad.mean()))
-    assert abs(g.mean() - e.mean()) <= 0.02 * abs(e.mean()) + 1e-9, (g.mean(), e.mean())
+    bad = (np.abs(g - e) > 1e-11 * (np.abs(e) + 1e-6)).any(axis=-1)
+    assert not bad.any(), ("pixels whose samples differ beyond the rounding of the film's atomic adds", int(bad.sum()), float(np.abs(g - e).max()))
     G.close(); O.close()
 
 
@@ -69,18 +67,13 @@ def test_bdpt_per_sample_parity_same_streams(name, spp, gpu_ctx):
     assert gcnt["nonfinite"] == 0                      # also: no subpath was cut at the device vertex cap (high half)
     assert np.allclose(gpx[..., 3], epx[..., 3], rtol=1e-12, atol=0)
     rel = np.abs(gdel / edel - 1)
-    assert np.median(rel) < 1e-5 and rel.max() < 0.5, (np.median(rel), rel.max())
-    assert abs(gcnt["closest"] - ecnt["closest"]) <= 0.01 * ecnt["closest"] + 8, (gcnt, ecnt)
-    assert abs(gcnt["occlusion"] - ecnt["occlusion"]) <= 0.01 * ecnt["occlusion"] + 8, (gcnt, ecnt)
-    assert abs(gcnt["cost"] - ecnt["cost"]) <= 0.01 * ecnt["cost"] + 8, (gcnt, ecnt)
+    assert rel.max() < 1e-12, (np.median(rel), rel.max())
+    assert gcnt["closest"] == ecnt["closest"] and gcnt["occlusion"] == ecnt["occlusion"] and gcnt["cost"] == ecnt["cost"], (gcnt, ecnt)
     e, g = _rgb(epx), _rgb(gpx)
-    bad = (np.abs(g - e) > 1e-6 * (np.abs(e) + 1e-6)).any(axis=-1)    # MIS sums carry libm-vs-CUDA ulp differences: 1e-6 here
-    # two subpaths per sample and, in `caustics`, mirror + dispersive glass meshes: measured 0 % (cornell) to 10.6 % (caustics) of pixels
-    assert bad.mean() <= 0.15, ("pixels whose main samples differ beyond rounding", float(bad.mean()))
-    assert abs(g.mean() - e.mean()) <= 0.02 * abs(e.mean()) + 1e-9, (g.mean(), e.mean())
-    sbad = (np.abs(gsp - esp) > 1e-6 * (np.abs(esp) + 1e-6)).any(axis=-1)
-    assert sbad.mean() <= 0.15, ("pixels whose splats differ beyond rounding", float(sbad.mean()))
-    assert abs(gsp.sum() - esp.sum()) <= 0.03 * abs(esp.sum()) + 1e-9, (gsp.sum(), esp.sum())
+    bad = (np.abs(g - e) > 1e-9 * (np.abs(e) + 1e-6)).any(axis=-1)    # a sample's radiance is a sum over its (s, t) terms, added with atomics in any order
+    assert not bad.any(), ("pixels whose main samples differ beyond rounding", int(bad.sum()))
+    sbad = (np.abs(gsp - esp) > 1e-9 * (np.abs(esp) + 1e-6)).any(axis=-1)
+    assert not sbad.any(), ("pixels whose splats differ beyond rounding", int(sbad.sum()))
     G.close(); O.close()
 
 
@@ -146,6 +139,7 @@ VARIANTS = {
     "clamp": dict(render=dict(tone_map=1, tone_map_arg=0.5)),
     "uniform_sampler": dict(render=dict(sampler=0)),
     "jittered_sampler": dict(render=dict(sampler=1)),
+    "sobol_sampler": dict(render=dict(sampler=3)),          # SamplerType::Sobol (samplers.rs:193-247)
 }
 
 
@@ -169,10 +163,10 @@ def test_camera_film_sampler_variants(variant, gpu_ctx):
     gpx, gsp, gcnt, _, _ = G.render(**kw)
     assert gcnt["camera_paths"] == ecnt["camera_paths"] and gcnt["nonfinite"] == 0
     assert np.allclose(gpx[..., 3], epx[..., 3], rtol=1e-11, atol=1e-14), variant          # filter weights: same sample positions, same filter
-    assert abs(gcnt["closest"] - ecnt["closest"]) <= 0.01 * ecnt["closest"] + 8
-    bad = (np.abs(gpx[..., :3] - epx[..., :3]) > 1e-8 * (np.abs(epx[..., :3]) + 1e-6)).any(axis=-1)
-    assert bad.mean() <= 0.25, (variant, float(bad.mean()))              # wide filters spread each flipped path over many pixels
-    assert abs(gpx[..., :3].sum() - epx[..., :3].sum()) <= 0.02 * abs(epx[..., :3].sum()) + 1e-9
+    assert gcnt["closest"] == ecnt["closest"] and gcnt["cost"] == ecnt["cost"], (variant, gcnt, ecnt)
+    scale = np.abs(epx[..., :3]).max()
+    bad = (np.abs(gpx[..., :3] - epx[..., :3]) > 1e-11 * (np.abs(epx[..., :3]) + 1e-3 * scale)).any(axis=-1)   # filtered sums of both signs (negative filter lobes, XYZ -> RGB)
+    assert not bad.any(), (variant, int(bad.sum()))
     G.close(); O.close()
 
 

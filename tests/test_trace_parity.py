@@ -57,10 +57,14 @@ def test_visit_counters_equal_oracle(gpu_ctx):
     O.counters(reset=True)
     O.trace_closest(o, d, threads=1)
     oc = O.counters(reset=True)
-    gpu_ctx.count_visits(True)
-    G.trace_closest(o, d)
-    gc, _ = gpu_ctx.visits()
-    gpu_ctx.count_visits(False)
+    gpu_ctx.closest_mode(1)                      # the device's replay of the reference traversal (the default pipeline only runs it where it has to)
+    try:
+        gpu_ctx.count_visits(True)
+        G.trace_closest(o, d)
+        gc, _ = gpu_ctx.visits()
+        gpu_ctx.count_visits(False)
+    finally:
+        gpu_ctx.closest_mode(0)
     for k in ("tlas_nodes", "inst", "kd_nodes", "leaf_idx", "tri_tests", "sphere_tests"):
         assert oc[k] == gc[k], (k, oc[k], gc[k])
 
@@ -82,6 +86,28 @@ def test_edge_cases(gpu_ctx):
     assert go[-1] == 0xFFFFFFFF and np.isinf(gtt[-1])
     with pytest.raises(RuntimeError):
         native.GpuScene(gpu_ctx, blob[:-16])                        # malformed blob -> status code, not a crash
+
+
+@pytest.mark.parametrize("name", list(SMALL))
+def test_closest_pipeline_equals_reference_traversal(name, gpu_ctx):
+    """closest.cuh (world-space BVH + the reference traversal on the winning object, full reference traversal where the
+    winner is not provably the reference's) against the device's own replay of the reference traversal for every ray
+    (closest mode 1): the same bits, ray for ray; and only a minority of the rays needs the full replay."""
+    from lumo_b200 import native
+    prog, blob, _ = small_scene(name)
+    O = oracle_lib.OracleScene(prog)
+    G = native.GpuScene(gpu_ctx, blob)
+    try:
+        for kind, (o, d) in ray_batches(O, N, seed=47).items():
+            gpu_ctx.closest_mode(1); so, st, stt, sb = G.trace_closest(o, d)
+            gpu_ctx.closest_mode(0)
+            gpu_ctx.count_visits(True); fo, ft, ftt, fb = G.trace_closest(o, d); cs = gpu_ctx.closest_stats(); gpu_ctx.count_visits(False)
+            assert np.array_equal(so, fo) and np.array_equal(st, ft) and np.array_equal(_bits(stt), _bits(ftt)) and np.array_equal(_bits(sb), _bits(fb)), (name, kind)
+            assert cs["rays"] == len(o) and cs["nodes"] > 0
+            assert cs["fallback"] <= 0.5 * len(o), (name, kind, cs)
+    finally:
+        gpu_ctx.closest_mode(0); gpu_ctx.count_visits(False)
+    G.close(); O.close()
 
 
 def _shadow_rays(O, n, seed):
