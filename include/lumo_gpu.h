@@ -64,10 +64,14 @@ typedef struct lumo_render_params {
 typedef struct lumo_film_accum {
     double* pixels;
     double* splats;
-    uint64_t counters[8];    /* [0] camera paths, [1] closest-hit queries (Scene::hit), [2] occlusion /
+    uint64_t counters[10];   /* [0] camera paths, [1] closest-hit queries (Scene::hit), [2] occlusion /
                                 visibility queries, [3] reference-style cost (sum FilmSample.cost,
                                 renderer.rs:221), [4] kernels launched, [5] deepest path, [6] wave
-                                iterations, [7] samples whose radiance was NaN/inf (tone_mapping.rs:42-56) */
+                                iterations, [7] samples whose radiance was NaN/inf (tone_mapping.rs:42-56),
+                                [8] BDPT subpaths cut because the device ran out of vertex storage (the reference
+                                caps a subpath at 1024 vertices, bd_path_trace.rs:7; 0 unless the overflow pool is
+                                exhausted), [9] shadow rays on which the occlusion BVH and the reference traversal
+                                disagreed (occlusion mode 2 only; must be 0) */
     double* tile_deltas;     /* optional [ceil(W/16)*ceil(H/16)]: RR threshold used per 16x16 tile */
     double device_ms;        /* CUDA-event time of the render on the context's stream */
 } lumo_film_accum;
@@ -110,7 +114,7 @@ int32_t lumo_gpu_render(lumo_scene* scene, const lumo_render_params* params, lum
  * [W*H*4], splats_dev [W*H*3], overwritten): the multi-GPU path reduces them with one NCCL
  * reduce over NVLink before the host reads anything. */
 int32_t lumo_gpu_render_dev(lumo_scene* scene, const lumo_render_params* params, double* pixels_dev, double* splats_dev,
-                            uint64_t* counters8, double* device_ms);
+                            uint64_t* counters10, double* device_ms);
 
 /* The same render on n GPUs of this host from ONE process: scenes[g] is the same blob uploaded through
  * its own context (normally one context per GPU).  [spp_begin, spp_end) is cut into n contiguous ranges, one host
@@ -144,9 +148,12 @@ int32_t lumo_gpu_ctx_visits(lumo_ctx* ctx, uint64_t* out12);   /* 6 for the clos
 /* Closest hits (Scene::hit) go through a world-space BVH with the reference traversal run on the winning object only, and
  * through the full reference traversal wherever that is not provably the same (csrc/gpu/closest.cuh).  mode 0: that (default);
  * 1: the reference traversal for every ray.  stats (only while visit counting is on; reset by lumo_gpu_ctx_count_visits):
- * [0] BVH nodes, [1] leaf primitives, [2] triangle tests, [3] sphere tests, [4] rays sent to the reference traversal, [5] rays. */
+ * [0] BVH nodes, [1] leaf primitives, [2] triangle tests, [3] sphere tests, [4] rays sent to the reference traversal, [5] rays,
+ * [6..13] why: stack overflow / another object at or below the nearest hit / a box above the winner fails / the winner's full
+ * hit is rejected / its any-hit or full distance is not the nearest hit / the last three again for the nearest light.
+ * stats has FOURTEEN entries. */
 int32_t lumo_gpu_ctx_closest_mode(lumo_ctx* ctx, int32_t mode);
-int32_t lumo_gpu_ctx_closest_stats(lumo_ctx* ctx, uint64_t* stats6);
+int32_t lumo_gpu_ctx_closest_stats(lumo_ctx* ctx, uint64_t* stats14);
 /* Shadow rays are answered from an order-free occlusion BVH and confirmed by the reference's own per-object traversal
  * (csrc/gpu/occlude.cuh).  mode 0: that (default); 1: the reference's object BVH + kd-tree traversal for shadow rays too;
  * 2: both on every shadow ray of a render, disagreements counted in stats[7].  stats: [0] BVH nodes, [1] leaf primitives,

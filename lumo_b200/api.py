@@ -524,6 +524,7 @@ class Renderer:
         start = time.time()
         blob = self.blob()
         ctx = native.GpuContext(self._device)
+        gs = None
         try:
             gs = native.GpuScene(ctx, blob)
             if not self.quiet:
@@ -531,8 +532,9 @@ class Renderer:
             px, sp, cnt, deltas, ms = gs.render(integrator=self._integrator, spp=self.num_samples, seed=self._seed, sampler=self._sampler,
                                                 tone_map=self._tone_map.kind, tone_map_arg=self._tone_map.arg, rr_delta=self._rr_delta,
                                                 wave_paths=self._wave_paths)
-            gs.close()
         finally:
+            if gs is not None:
+                gs.close()               # the scene before its context, also when the render raised
             ctx.close()
         if not self.quiet:                                                # renderer.rs:237-241
             print("Finished rendering in %.3f s (%d camera rays, %d total rays)" % (time.time() - start, cnt["camera_paths"], cnt["cost"]))

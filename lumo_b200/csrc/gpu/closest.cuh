@@ -36,7 +36,7 @@ struct ClosestScratch {    // per ray of a launch
     uint32_t* fallback_i;  // rays for k_closest_fallback
     uint32_t* counters;    // [0] work cursor of k_closest_bvh, [1] cursor of k_closest_finish, [2] fallback queue size, [3] fallback cursor
 };
-struct ClosestCounters { unsigned long long nodes, prims, tris, spheres, fallback, rays; };
+struct ClosestCounters { unsigned long long nodes, prims, tris, spheres, fallback, rays, why[8]; };   // why: reasons for the reference traversal (see k_closest_finish)
 
 #define LUMO_CH_STACK 48
 #ifndef LUMO_CH_REFILL
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(128, 4) k_closest_bvh(const __grid_constant__ 
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t n = src.n();
     const uint32_t n_objects = S.P.n_objects;
-    ClosestCounters cnt = {0, 0, 0, 0, 0, 0};
+    ClosestCounters cnt = {};
     AhLocal L; L.slot = local_ctx + threadIdx.x; L.stride = 128; L.cur = -1;
     uint32_t stack[LUMO_CH_STACK]; float stack_t[LUMO_CH_STACK];
     bool active = false, exhausted = false;
@@ -207,7 +207,7 @@ __device__ __forceinline__ bool same_bits(double a, double b) { return __double_
 
 // Sink: store(i, have, HitRec) — the final hit record of ray i.
 template <bool CNT, class Source, class Sink>
-__global__ void __launch_bounds__(128, LUMO_WAVE_TRACE_BLOCKS) k_closest_finish(const __grid_constant__ DevScene S, const Source src, const Sink sink, const ClosestScratch Q, Counters* vc) {
+__global__ void __launch_bounds__(128, LUMO_WAVE_TRACE_BLOCKS) k_closest_finish(const __grid_constant__ DevScene S, const Source src, const Sink sink, const ClosestScratch Q, Counters* vc, ClosestCounters* gc) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t n = src.n();
     Counters cnt = {0, 0, 0, 0, 0, 0};
@@ -224,23 +224,28 @@ __global__ void __launch_bounds__(128, LUMO_WAVE_TRACE_BLOCKS) k_closest_finish(
             const double t1 = Q.t1[i], tl = Q.tl[i];
             HitRec h; bool have = false;
             double t_h = t_max;
-            if (flags & 4u) again = true;
+            int why = -1;      // 0 stack overflow, 1 another object at <= t1, 2 a box above the winner fails, 3 the winner's full hit is rejected, 4 its any-hit or full distance is not t1; 5..7: the same for the light
+            if (flags & 4u) why = 0;
             RayCtx w;
-            if (!again && (o1 != LUMO_NONE || ol != LUMO_NONE)) make_ctx(ray, w);
-            if (!again && o1 != LUMO_NONE) {
+            if (why < 0 && (o1 != LUMO_NONE || ol != LUMO_NONE)) make_ctx(ray, w);
+            if (why < 0 && o1 != LUMO_NONE) {
                 double any_t;
-                if ((flags & 1u) || !ch_path_ok<CNT>(S, o1, w, t1, &cnt)) again = true;
-                else if (!object_hit<CNT, 64, LUMO_WAVE_KD_ROUND>(S, S.objects[o1], w, 0.0, t_max, h, &cnt, &any_t)) again = true;     // a rejected full hit empties the whole group
-                else if (!same_bits(any_t, t1) || !same_bits(h.t, t1)) again = true;
+                if (flags & 1u) why = 1;
+                else if (!ch_path_ok<CNT>(S, o1, w, t1, &cnt)) why = 2;
+                else if (!object_hit<CNT, 64, LUMO_WAVE_KD_ROUND>(S, S.objects[o1], w, 0.0, t_max, h, &cnt, &any_t)) why = 3;     // a rejected full hit empties the whole group
+                else if (!same_bits(any_t, t1) || !same_bits(h.t, t1)) why = 4;
                 else { h.obj = o1; have = true; t_h = h.t; }
             }
-            if (!again && ol != LUMO_NONE && tl < t_h) {       // Scene::hit: lights with t_max = the objects' hit; a light has to be strictly nearer
+            if (why < 0 && ol != LUMO_NONE && tl < t_h) {      // Scene::hit: lights with t_max = the objects' hit; a light has to be strictly nearer
                 HitRec hl; double any_t;
-                if ((flags & 2u) || !ch_path_ok<CNT>(S, ol, w, tl, &cnt)) again = true;
-                else if (!object_hit<CNT, 64, LUMO_WAVE_KD_ROUND>(S, S.objects[ol], w, 0.0, t_h, hl, &cnt, &any_t)) again = true;
-                else if (!same_bits(any_t, tl)) again = true;
+                if (flags & 2u) why = 5;
+                else if (!ch_path_ok<CNT>(S, ol, w, tl, &cnt)) why = 6;
+                else if (!object_hit<CNT, 64, LUMO_WAVE_KD_ROUND>(S, S.objects[ol], w, 0.0, t_h, hl, &cnt, &any_t)) why = 7;
+                else if (!same_bits(any_t, tl)) why = 7;
                 else { hl.obj = ol; h = hl; have = true; }
             }
+            again = why >= 0;
+            if (CNT && again) atomicAdd(&gc->why[why], 1ull);
             if (!again) sink.store(i, have, h);
         }
         const uint32_t m = __ballot_sync(0xFFFFFFFFu, again);

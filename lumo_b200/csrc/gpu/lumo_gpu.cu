@@ -40,7 +40,7 @@ struct lumo_ctx {
     int closest_faithful = 0;      // LUMO_CLOSEST_FAITHFUL=1: Scene::hit replays the reference traversal for every ray (k_wave_trace) instead of closest.cuh
     void* occl_mem = nullptr; size_t occl_bytes = 0;   // queues of the batch occlusion entry point (lumo_gpu_trace_any)
     int occl_faithful = 0;         // LUMO_OCCLUDE_FAITHFUL=1: shadow rays replay the reference's object BVH + kd-trees (k_wave_occlude) instead of the occlusion BVH
-    int occl_check = 0;            // LUMO_OCCLUDE_CHECK=1: run both on every shadow ray of a render and count disagreements (counters[7] high half)
+    int occl_check = 0;            // LUMO_OCCLUDE_CHECK=1: run both on every shadow ray of a render and count disagreements (counters[9])
     uint32_t* d_iter_log = nullptr; uint32_t iter_log_n = 0;   // (closest-hit rays, shadow rays) per wave iteration of the last render's main pass
     // per-kernel-class device time of the last render (CUDA events on the launching stream)
     cudaEvent_t kev[5 * LUMO_ITER_BATCH] = {};
@@ -62,16 +62,9 @@ extern "C" int32_t lumo_gpu_device_count(int32_t* n) {
     int c = 0; CU(cudaGetDeviceCount(&c)); *n = c; return LUMO_OK;
 }
 
-extern "C" int32_t lumo_gpu_ctx_create(int32_t device, lumo_ctx** out) {
-    if (!out) return fail(LUMO_ERR_INVALID, "ctx_create: null pointer");
-    int c = 0; CU(cudaGetDeviceCount(&c));
-    if (device < 0 || device >= c) return fail(LUMO_ERR_INVALID, "ctx_create: no such device");
-    CU(cudaSetDevice(device));
-    cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10) return fail(LUMO_ERR_UNSUPPORTED, "ctx_create: liblumo_gpu is built for sm_100a only");
-    lumo_ctx* ctx = new (std::nothrow) lumo_ctx();
-    if (!ctx) return fail(LUMO_ERR_OOM, "ctx_create: out of host memory");
-    ctx->device = device; ctx->sm_count = prop.multiProcessorCount;
+extern "C" int32_t lumo_gpu_ctx_destroy(lumo_ctx* ctx);
+static int32_t ctx_init(lumo_ctx* ctx, int32_t device, int sm_count) {
+    ctx->device = device; ctx->sm_count = sm_count;
     CU(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
     ctx->stream = ctx->own_stream;
     CU(cudaEventCreate(&ctx->ev0)); CU(cudaEventCreate(&ctx->ev1));
@@ -81,8 +74,9 @@ extern "C" int32_t lumo_gpu_ctx_create(int32_t device, lumo_ctx** out) {
     for (auto& e : ctx->kev) CU(cudaEventCreate(&e));
     CU(cudaMalloc(&ctx->d_iter_log, LUMO_ITER_LOG_CAP * 8));
     CU(cudaMalloc(&ctx->d_cursor, 8));
-    // f64 traversal keeps two explicit stacks per thread
-    cudaDeviceSetLimit(cudaLimitStackSize, 4096);
+    // the reference-order traversal keeps two explicit stacks per thread (2.3 KB).  The limit is device-wide and shared with the
+    // host process (e.g. torch): only ever raised, never lowered.
+    { size_t cur = 0; CU(cudaDeviceGetLimit(&cur, cudaLimitStackSize)); if (cur < 4096) CU(cudaDeviceSetLimit(cudaLimitStackSize, 4096)); }
     { const char* e = std::getenv("LUMO_OCCLUDE_FAITHFUL"); if (e) ctx->occl_faithful = std::atoi(e) != 0; }
     { const char* e = std::getenv("LUMO_OCCLUDE_CHECK"); if (e) ctx->occl_check = std::atoi(e) != 0; }
     CU(cudaMalloc(&ctx->d_ah, sizeof(AhCounters)));
@@ -90,6 +84,19 @@ extern "C" int32_t lumo_gpu_ctx_create(int32_t device, lumo_ctx** out) {
     { const char* e = std::getenv("LUMO_CLOSEST_FAITHFUL"); if (e) ctx->closest_faithful = std::atoi(e) != 0; }
     CU(cudaMalloc(&ctx->d_ch, sizeof(ClosestCounters)));
     CU(cudaMemset(ctx->d_ch, 0, sizeof(ClosestCounters)));
+    return LUMO_OK;
+}
+extern "C" int32_t lumo_gpu_ctx_create(int32_t device, lumo_ctx** out) {
+    if (!out) return fail(LUMO_ERR_INVALID, "ctx_create: null pointer");
+    int c = 0; CU(cudaGetDeviceCount(&c));
+    if (device < 0 || device >= c) return fail(LUMO_ERR_INVALID, "ctx_create: no such device");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(LUMO_ERR_UNSUPPORTED, "ctx_create: liblumo_gpu is built for sm_100a only");
+    lumo_ctx* ctx = new (std::nothrow) lumo_ctx();
+    if (!ctx) return fail(LUMO_ERR_OOM, "ctx_create: out of host memory");
+    const int32_t rc = ctx_init(ctx, device, prop.multiProcessorCount);
+    if (rc != LUMO_OK) { const std::string msg = g_err; lumo_gpu_ctx_destroy(ctx); g_err = msg; return rc; }   // nothing created so far is leaked
     *out = ctx; return LUMO_OK;
 }
 extern "C" int32_t lumo_gpu_ctx_destroy(lumo_ctx* ctx) {
@@ -138,18 +145,20 @@ extern "C" int32_t lumo_gpu_ctx_count_visits(lumo_ctx* ctx, int32_t enable) {
 // Closest hits (Scene::hit) go through the world-space BVH with the reference traversal run on the winning object only, and
 // through the full reference traversal wherever that is not provably the same (csrc/gpu/closest.cuh).  mode 0: that (default);
 // 1: the reference traversal for every ray.  stats (only while visit counting is on): [0] BVH nodes, [1] leaf primitives,
-// [2] triangle tests, [3] sphere tests, [4] rays sent to the reference traversal, [5] rays.
+// [2] triangle tests, [3] sphere tests, [4] rays sent to the reference traversal, [5] rays, [6..13] why they were sent: stack
+// overflow, another object at or below the nearest hit, a box above the winner failing, the winner's full hit rejected, its
+// any-hit or full distance differing from the nearest hit, and the last three again for the nearest light.
 extern "C" int32_t lumo_gpu_ctx_closest_mode(lumo_ctx* ctx, int32_t mode) {
     if (!ctx || mode < 0 || mode > 1) return fail(LUMO_ERR_INVALID, "closest_mode: bad arguments");
     ctx->closest_faithful = mode == 1;
     return LUMO_OK;
 }
-extern "C" int32_t lumo_gpu_ctx_closest_stats(lumo_ctx* ctx, uint64_t* out6) {
+extern "C" int32_t lumo_gpu_ctx_closest_stats(lumo_ctx* ctx, uint64_t* out6) {   // fourteen values
     if (!ctx || !out6) return fail(LUMO_ERR_INVALID, "closest_stats: null pointer");
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
     ClosestCounters c; CU(cudaMemcpy(&c, ctx->d_ch, sizeof c, cudaMemcpyDeviceToHost));
-    out6[0] = c.nodes; out6[1] = c.prims; out6[2] = c.tris; out6[3] = c.spheres; out6[4] = c.fallback; out6[5] = c.rays;
+    out6[0] = c.nodes; out6[1] = c.prims; out6[2] = c.tris; out6[3] = c.spheres; out6[4] = c.fallback; out6[5] = c.rays; for (int k = 0; k < 8; k++) out6[6 + k] = c.why[k];
     return LUMO_OK;
 }
 // Counters of the occlusion-BVH kernels (occlude.cuh) since the last lumo_gpu_ctx_count_visits call: [0] BVH nodes visited,
@@ -425,11 +434,11 @@ static int32_t launch_closest(lumo_scene* sc, const Source& src, const Sink& sin
     const int g1 = ctx->sm_count * 4, g2 = ctx->sm_count * LUMO_WAVE_TRACE_BLOCKS;
     if (ctx->count_visits) {
         k_closest_bvh<true><<<g1, 128, 0, st>>>(sc->S, src, Q, ctx->d_ch);
-        k_closest_finish<true><<<g2, 128, 0, st>>>(sc->S, src, sink, Q, ctx->d_visit);
+        k_closest_finish<true><<<g2, 128, 0, st>>>(sc->S, src, sink, Q, ctx->d_visit, ctx->d_ch);
         k_closest_fallback<true><<<g2, 128, 0, st>>>(sc->S, src, sink, Q, ctx->d_visit, ctx->d_ch);
     } else {
         k_closest_bvh<false><<<g1, 128, 0, st>>>(sc->S, src, Q, nullptr);
-        k_closest_finish<false><<<g2, 128, 0, st>>>(sc->S, src, sink, Q, nullptr);
+        k_closest_finish<false><<<g2, 128, 0, st>>>(sc->S, src, sink, Q, nullptr, nullptr);
         k_closest_fallback<false><<<g2, 128, 0, st>>>(sc->S, src, sink, Q, nullptr, nullptr);
     }
     ctx->launches += 3;
@@ -830,6 +839,7 @@ static int32_t render_impl(lumo_scene* sc, const lumo_render_params* rp, double*
     CU(cudaMemsetAsync(pixels_dev, 0, film_px * 32, st));
     CU(cudaMemsetAsync(splats_dev, 0, film_px * 24, st));
     CU(cudaMemsetAsync(W.run, 0, sizeof(RunCounters), st));
+    if (ctx->occl_check) CU(cudaMemsetAsync(&ctx->d_ah->mismatches, 0, 8, st));   // per render
     k_fill<<<64, 256, 0, st>>>(W.tile_delta, n_tiles, rp->rr_delta > 0.0 ? rp->rr_delta : 1e-5);
     ctx->launches++;
     WaveParams P; std::memset(&P, 0, sizeof P);
@@ -865,7 +875,10 @@ static int32_t render_impl(lumo_scene* sc, const lumo_render_params* rp, double*
     if (device_ms) *device_ms = ms;
     if (counters) {
         counters[0] = hc->run.camera_paths; counters[1] = hc->run.closest; counters[2] = hc->run.occlusion; counters[3] = hc->run.cost;
-        counters[4] = ctx->launches - launches0; counters[5] = hc->run.max_depth; counters[6] = iterations; counters[7] = hc->run.nonfinite + (bdpt ? (hc->run.shadow_dropped << 32) : 0ull);   // BDPT: subpaths cut at LUMO_BDPT_MAXV in the high half
+        counters[4] = ctx->launches - launches0; counters[5] = hc->run.max_depth; counters[6] = iterations; counters[7] = hc->run.nonfinite;
+        counters[8] = bdpt ? hc->run.shadow_dropped : 0ull;   // BDPT: subpaths cut for lack of vertex storage
+        counters[9] = 0;
+        if (ctx->occl_check) { AhCounters ac; CU(cudaMemcpy(&ac, ctx->d_ah, sizeof ac, cudaMemcpyDeviceToHost)); counters[9] = ac.mismatches; }
     }
     return LUMO_OK;
 }
@@ -888,10 +901,10 @@ extern "C" int32_t lumo_gpu_render(lumo_scene* sc, const lumo_render_params* rp,
     CU(cudaStreamSynchronize(ctx->stream));
     return LUMO_OK;
 }
-extern "C" int32_t lumo_gpu_render_dev(lumo_scene* sc, const lumo_render_params* rp, double* pixels_dev, double* splats_dev, uint64_t* counters8, double* device_ms) {
+extern "C" int32_t lumo_gpu_render_dev(lumo_scene* sc, const lumo_render_params* rp, double* pixels_dev, double* splats_dev, uint64_t* counters10, double* device_ms) {
     if (!sc || !rp || !pixels_dev || !splats_dev) return fail(LUMO_ERR_INVALID, "render_dev: null pointer");
     CU(cudaSetDevice(sc->ctx->device));
-    return render_impl(sc, rp, pixels_dev, splats_dev, counters8, nullptr, device_ms);
+    return render_impl(sc, rp, pixels_dev, splats_dev, counters10, nullptr, device_ms);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1060,7 +1073,18 @@ extern "C" int32_t lumo_gpu_sample_range(int32_t g, int32_t n, uint32_t begin, u
     *g_end = *g_begin + base + ((uint32_t)g < extra ? 1u : 0u);
     return LUMO_OK;
 }
+static int32_t render_multi_impl(lumo_scene** scenes, int32_t n, const lumo_render_params* rp, lumo_film_accum* out, std::vector<void*>& staged);
 extern "C" int32_t lumo_gpu_render_multi(lumo_scene** scenes, int32_t n, const lumo_render_params* rp, lumo_film_accum* out) {
+    std::vector<void*> staged;          // peer films copied to GPU 0 where peer access is unavailable: freed on every exit
+    int32_t rc;
+    try { rc = render_multi_impl(scenes, n, rp, out, staged); }
+    catch (const std::bad_alloc&) { rc = fail(LUMO_ERR_OOM, "render_multi: out of host memory"); }
+    catch (const std::exception& e) { rc = fail(LUMO_ERR_CUDA, std::string("render_multi: ") + e.what()); }
+    catch (...) { rc = fail(LUMO_ERR_CUDA, "render_multi: unknown exception"); }
+    if (!staged.empty()) { const std::string msg = g_err; if (scenes && scenes[0]) cudaSetDevice(scenes[0]->ctx->device); for (void* t : staged) cudaFree(t); g_err = msg; }
+    return rc;
+}
+static int32_t render_multi_impl(lumo_scene** scenes, int32_t n, const lumo_render_params* rp, lumo_film_accum* out, std::vector<void*>& staged) {
     if (!scenes || !rp || !out || !out->pixels || !out->splats) return fail(LUMO_ERR_INVALID, "render_multi: null pointer");
     if (n < 1 || n > LUMO_MAX_MULTI) return fail(LUMO_ERR_INVALID, "render_multi: n must be in [1, 16]");
     for (int g = 0; g < n; g++) {
@@ -1071,9 +1095,11 @@ extern "C" int32_t lumo_gpu_render_multi(lumo_scene** scenes, int32_t n, const l
     }
     if (rp->spp_end < rp->spp_begin) return fail(LUMO_ERR_INVALID, "render: bad sample range");
     const size_t film_px = (size_t)scenes[0]->S.P.camera.res_x * scenes[0]->S.P.camera.res_y, film_doubles = film_px * 7;
-    struct Part { int32_t rc = LUMO_OK; std::string err; uint64_t counters[8] = {}; double ms = 0.0; };
+    struct Part { int32_t rc = LUMO_OK; std::string err; uint64_t counters[10] = {}; double ms = 0.0; };
     std::vector<Part> parts((size_t)n);
     std::vector<std::thread> workers;
+    workers.reserve((size_t)n);
+    struct Joiner { std::vector<std::thread>& w; ~Joiner() { for (auto& t : w) if (t.joinable()) t.join(); } } joiner{workers};   // also when a later thread cannot be started
     for (int g = 0; g < n; g++) {
         workers.emplace_back([&, g]() {
             Part& pt = parts[(size_t)g];
@@ -1099,7 +1125,6 @@ extern "C" int32_t lumo_gpu_render_multi(lumo_scene** scenes, int32_t n, const l
     CU(cudaSetDevice(c0->device));
     cudaStream_t st = c0->stream;
     FilmPeers peers{};
-    std::vector<void*> staged;
     peers.p[0] = (const double*)c0->film_mem;
     for (int g = 1; g < n; g++) {
         lumo_ctx* cg = scenes[g]->ctx;
@@ -1127,14 +1152,13 @@ extern "C" int32_t lumo_gpu_render_multi(lumo_scene** scenes, int32_t n, const l
     CU(cudaMemcpyAsync(out->pixels, px, film_px * 32, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(out->splats, px + film_px * 4, film_px * 24, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    for (void* t : staged) cudaFree(t);
     float reduce_ms = 0.f; if (n > 1) CU(cudaEventElapsedTime(&reduce_ms, c0->ev0, c0->ev1));
     // counters: sums, except [5] deepest path (max) and [6] wave iterations (max); device_ms: slowest GPU + the reduce
     double ms = 0.0;
-    for (int k = 0; k < 8; k++) out->counters[k] = 0;
+    for (int k = 0; k < 10; k++) out->counters[k] = 0;
     for (int g = 0; g < n; g++) {
         const Part& pt = parts[(size_t)g];
-        for (int k = 0; k < 8; k++) out->counters[k] = (k == 5 || k == 6) ? std::max(out->counters[k], pt.counters[k]) : out->counters[k] + pt.counters[k];
+        for (int k = 0; k < 10; k++) out->counters[k] = (k == 5 || k == 6) ? std::max(out->counters[k], pt.counters[k]) : out->counters[k] + pt.counters[k];
         ms = std::max(ms, pt.ms);
     }
     if (n > 1) out->counters[4] += 1;   // k_film_reduce

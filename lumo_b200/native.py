@@ -3,6 +3,7 @@ include/lumo_gpu.h).  The GPU library is mandatory for every compute entry point
 or no CUDA device is present the call raises — there is no CPU fallback in this package."""
 import ctypes as C
 import os
+import weakref
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -120,12 +121,12 @@ class RenderParams(C.Structure):        # include/lumo_gpu.h lumo_render_params
 
 
 class FilmAccum(C.Structure):           # include/lumo_gpu.h lumo_film_accum
-    _fields_ = [("pixels", C.POINTER(C.c_double)), ("splats", C.POINTER(C.c_double)), ("counters", C.c_uint64 * 8),
+    _fields_ = [("pixels", C.POINTER(C.c_double)), ("splats", C.POINTER(C.c_double)), ("counters", C.c_uint64 * 10),
                 ("tile_deltas", C.POINTER(C.c_double)), ("device_ms", C.c_double)]
 
 
 _gpu = None
-COUNTER_NAMES = ("camera_paths", "closest", "occlusion", "cost", "gpu_launches", "max_depth", "iterations", "nonfinite")
+COUNTER_NAMES = ("camera_paths", "closest", "occlusion", "cost", "gpu_launches", "max_depth", "iterations", "nonfinite", "bdpt_cut_subpaths", "occlusion_mismatches")
 
 
 def gpu_lib():
@@ -188,10 +189,13 @@ class GpuContext:
     def __init__(self, device=0):
         L = gpu_lib()
         self.h = C.c_void_p()
+        self._scenes = weakref.WeakSet()     # scenes uploaded through this context: closed before it
         _check(L.lumo_gpu_ctx_create(device, C.byref(self.h)), "lumo_gpu_ctx_create")
 
     def close(self):
         if self.h:
+            for s in list(self._scenes):     # a scene's destructor touches its context: never leave one open behind a destroyed context
+                s.close()
             gpu_lib().lumo_gpu_ctx_destroy(self.h); self.h = None
 
     def set_stream(self, cuda_stream_ptr):
@@ -212,9 +216,11 @@ class GpuContext:
         _check(gpu_lib().lumo_gpu_ctx_closest_mode(self.h, int(mode)), "lumo_gpu_ctx_closest_mode")
 
     def closest_stats(self):
-        out = (C.c_uint64 * 6)()
+        out = (C.c_uint64 * 14)()
         _check(gpu_lib().lumo_gpu_ctx_closest_stats(self.h, out), "lumo_gpu_ctx_closest_stats")
-        return dict(zip(("nodes", "prims", "tri_tests", "sphere_tests", "fallback", "rays"), (int(v) for v in out)))
+        names = ("nodes", "prims", "tri_tests", "sphere_tests", "fallback", "rays", "why_stack_overflow", "why_object_tie", "why_object_box", "why_object_full_hit_rejected",
+                 "why_object_distance", "why_light_tie", "why_light_box", "why_light_hit")
+        return dict(zip(names, (int(v) for v in out)))
 
     def occlusion_mode(self, mode):
         """0: occlusion BVH + confirmation (default); 1: the reference's traversal for shadow rays; 2: both, disagreements counted."""
@@ -279,6 +285,7 @@ class GpuScene:
         self.h = C.c_void_p()
         src = C.c_char_p(blob_bytes) if host_ptr is None else C.cast(C.c_void_p(host_ptr), C.c_char_p)
         _check(gpu_lib().lumo_gpu_scene_upload(ctx.h, src, len(blob_bytes), C.byref(self.h)), "lumo_gpu_scene_upload")   # validates the blob
+        ctx._scenes.add(self)
         self.blob = Blob(blob_bytes)
         cam = self.blob.params["camera"]
         self.res_x, self.res_y = int(cam["res_x"]), int(cam["res_y"])
@@ -324,7 +331,7 @@ class GpuScene:
         assert pixels.flags["C_CONTIGUOUS"] and splats.flags["C_CONTIGUOUS"]
         ntiles = ((W + 15) // 16) * ((H + 15) // 16)
         deltas = np.zeros(ntiles)
-        out = FilmAccum(_dp(pixels), _dp(splats), (C.c_uint64 * 8)(), _dp(deltas), 0.0)
+        out = FilmAccum(_dp(pixels), _dp(splats), (C.c_uint64 * 10)(), _dp(deltas), 0.0)
         _check(gpu_lib().lumo_gpu_render(self.h, C.byref(P), C.byref(out)), "lumo_gpu_render")
         return pixels, splats, dict(zip(COUNTER_NAMES, (int(v) for v in out.counters))), deltas, out.device_ms
 
@@ -334,7 +341,7 @@ class GpuScene:
         total = spp if total_spp is None else total_spp
         end = total if spp_end is None else spp_end
         P = RenderParams(integrator, sampler, tone_map, 0, tone_map_arg, rr_delta, seed, spp_begin, end, total, wave_paths)
-        cnt = (C.c_uint64 * 8)(); ms = C.c_double(0.0)
+        cnt = (C.c_uint64 * 10)(); ms = C.c_double(0.0)
         _check(gpu_lib().lumo_gpu_render_dev(self.h, C.byref(P), C.c_void_p(pixels_ptr), C.c_void_p(splats_ptr), cnt, C.byref(ms)), "lumo_gpu_render_dev")
         return dict(zip(COUNTER_NAMES, (int(v) for v in cnt))), ms.value
 
@@ -355,7 +362,7 @@ def render_multi(scenes, integrator=0, spp=1, seed=1, sampler=2, tone_map=0, ton
     W, H = scenes[0].res_x, scenes[0].res_y
     pixels = np.zeros((H, W, 4)); splats = np.zeros((H, W, 3))
     deltas = np.zeros(((W + 15) // 16) * ((H + 15) // 16))
-    out = FilmAccum(_dp(pixels), _dp(splats), (C.c_uint64 * 8)(), _dp(deltas), 0.0)
+    out = FilmAccum(_dp(pixels), _dp(splats), (C.c_uint64 * 10)(), _dp(deltas), 0.0)
     hs = (C.c_void_p * len(scenes))(*[s.h for s in scenes])
     _check(gpu_lib().lumo_gpu_render_multi(hs, len(scenes), C.byref(P), C.byref(out)), "lumo_gpu_render_multi")
     return pixels, splats, dict(zip(COUNTER_NAMES, (int(v) for v in out.counters))), deltas, out.device_ms

@@ -22,6 +22,8 @@ def test_sample_ranges_partition():
             assert max(sizes) - min(sizes) <= 1
 
 
+@pytest.mark.skipif(not os.path.exists(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lumo_b200", "liblumo_gpu.so")),
+                    reason="liblumo_gpu.so not built (needs nvcc)")
 def test_c_abi_sample_range_equals_the_python_rule():
     """lumo_gpu_render_multi splits the sample range with lumo_gpu_sample_range; it must be the rule the one-process-per-GPU
     path uses (distributed.sample_range), also with an offset range, and must reject bad arguments."""
@@ -71,4 +73,4 @@ def test_sharded_film_equals_single_process(world, tmp_path):
     _fake_render(px, sp, 0, total, W, H)
     got = np.load(out)
     assert np.allclose(got, buf.numpy(), rtol=1e-13, atol=0)
-    assert np.array_equal(got[3::4][: W * H][:8], np.full(8, float(total))) or True
+    assert np.array_equal(got[3:4 * W * H:4], np.full(W * H, float(total)))      # weight channel of pixels[H,W,4]: one per sample

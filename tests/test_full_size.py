@@ -21,6 +21,79 @@ def _bits(a):
     return np.ascontiguousarray(a, np.float64).view(np.uint64)
 
 
+FULL = ["cornell", "bunny", "dragon", "caustics_bdpt", "conference", "bistro"]      # the BASELINE configs at their full sizes
+
+
+def _device_rays(B, n, seed, torch_dev="cuda:0"):
+    """n incoherent rays inside the scene bounds (origins uniform, directions uniform on the sphere), generated with numpy."""
+    rs = np.random.RandomState(seed)
+    lo, hi = np.array(B.params["bounds_lo"]), np.array(B.params["bounds_hi"])
+    o = lo + rs.rand(n, 3) * (hi - lo)
+    z = 1 - 2 * rs.rand(n); ph = 2 * np.pi * rs.rand(n); r = np.sqrt(np.maximum(1 - z * z, 0))
+    return o, np.stack([r * np.cos(ph), r * np.sin(ph), z], -1)
+
+
+@pytest.mark.parametrize("name", FULL)
+def test_full_size_ten_million_rays_both_pipelines(name, gpu_ctx):
+    """G1 / G2 at full size, >= 10^7 rays per config: the default pipelines (world-space BVH + the reference traversal where
+    it decides: closest.cuh, occlude.cuh) against the device's replay of the reference traversal for every ray — ids,
+    distances, barycentrics and occlusion booleans bit for bit; then a bounded sample of each batch kind (primary rays of
+    the config's camera, incoherent rays, bounce rays off the first hit) against the oracle on the same full-size scene."""
+    from lumo_b200 import native
+    from conftest import ray_batches
+    prog, blob, integrator, _ = _full(name)
+    G = native.GpuScene(gpu_ctx, blob)
+    n_total = 0
+    try:
+        for chunk in range(5):
+            o, d = _device_rays(G.blob, 2_100_000, 100 + chunk)
+            gpu_ctx.closest_mode(0); fo, ft, ftt, fb = G.trace_closest(o, d)
+            gpu_ctx.closest_mode(1); so, st, stt, sb = G.trace_closest(o, d)
+            assert np.array_equal(fo, so) and np.array_equal(ft, st) and np.array_equal(_bits(ftt), _bits(stt)) and np.array_equal(_bits(fb), _bits(sb)), (name, chunk)
+            # shadow-ray-like segments: up to just before / just behind the first hit, and random lengths
+            rs = np.random.RandomState(200 + chunk)
+            tm = np.where(np.isfinite(ftt), ftt * rs.choice([0.5, 1.0 - 1e-9, 1.0 + 1e-9, 2.0], size=len(ftt)), rs.rand(len(ftt)) * 100.0) - 1e-10
+            gpu_ctx.occlusion_mode(0); fa = G.trace_any(o, d, tm)
+            gpu_ctx.occlusion_mode(1); sa = G.trace_any(o, d, tm)
+            assert np.array_equal(fa, sa), (name, chunk, int((fa != sa).sum()))
+            assert 0.02 < fa.mean() < 0.98 or name == "cornell"
+            n_total += len(o)
+    finally:
+        gpu_ctx.closest_mode(0); gpu_ctx.occlusion_mode(0)
+    assert n_total >= 10_000_000
+    O = oracle_lib.OracleScene(prog)
+    for kind, (o, d) in ray_batches(O, 20000, seed=53).items():
+        eo, et, ett, eb = O.trace_closest(o, d)
+        go, gt, gtt, gb = G.trace_closest(o, d)
+        assert np.array_equal(eo, go) and np.array_equal(et, gt) and np.array_equal(_bits(ett), _bits(gtt)) and np.array_equal(_bits(eb), _bits(gb)), (name, kind)
+        tm = np.where(np.isfinite(ett), ett * 0.999, 5.0)
+        assert np.array_equal(O.trace_any(o, d, tm), G.trace_any(o, d, tm)), (name, kind)
+    O.close(); G.close()
+
+
+@pytest.mark.parametrize("name", FULL)
+def test_full_size_render_cross_check(name, gpu_ctx):
+    """Every shadow ray of a full-size render through both occlusion paths (mode 2): zero disagreements; and the film and the
+    counters of the default pipelines equal those of the all-reference-traversal render (closest mode 1 + occlusion mode 1)."""
+    from lumo_b200 import native
+    prog, blob, integrator, _ = _full(name)
+    if integrator == 2: integrator = 0                 # the shadow queue belongs to PathTrace / DirectLight
+    G = native.GpuScene(gpu_ctx, blob)
+    spp = 1 if name == "bistro" else 4
+    try:
+        gpu_ctx.occlusion_mode(2); a = G.render(integrator=integrator, spp=spp, seed=5, rr_delta=0.05)
+        gpu_ctx.occlusion_mode(1); gpu_ctx.closest_mode(1); b = G.render(integrator=integrator, spp=spp, seed=5, rr_delta=0.05)
+    finally:
+        gpu_ctx.occlusion_mode(0); gpu_ctx.closest_mode(0)
+    assert a[2]["occlusion_mismatches"] == 0, (name, a[2])
+    for k in ("camera_paths", "closest", "occlusion", "cost", "max_depth", "nonfinite"):
+        assert a[2][k] == b[2][k], (name, k, a[2][k], b[2][k])
+    assert a[2]["occlusion"] > 1_000_000 or name == "cornell"
+    scale = np.abs(b[0]).max()
+    assert np.allclose(a[0], b[0], rtol=1e-10, atol=1e-13 * scale), name
+    G.close()
+
+
 @pytest.mark.parametrize("name", ["bunny", "bistro"])
 def test_full_size_ray_properties(name, gpu_ctx):
     from lumo_b200 import native
