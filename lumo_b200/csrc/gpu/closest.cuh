@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(128, 4) k_closest_bvh(const __grid_constant__ 
             leaf_pos++;
             if (obj < n_objects) {
                 const double t = ch_prim_test<CNT>(S, pr, r, q, t1, L, &cnt);
-                if (t <= t1) {                                   // distances equal to the bound matter: a tie sends the ray to the reference traversal
+                if (t <= t1 && t < LUMO_INF) {                   // (a miss is +inf.)  Distances equal to the bound matter: a tie sends the ray to the reference traversal
                     if (obj == o1) { if (t < t1) t1 = t; }
                     else if (t < t1 || o1 == LUMO_NONE) { if (o1 != LUMO_NONE) s1 = fmin(s1, t1); t1 = t; o1 = obj; }
                     else s1 = fmin(s1, t);
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(128, 4) k_closest_bvh(const __grid_constant__ 
             } else {
                 const double bound = fmin(t1, tl);
                 const double t = ch_prim_test<CNT>(S, pr, r, q, bound, L, &cnt);
-                if (t <= bound) {
+                if (t <= bound && t < LUMO_INF) {
                     if (obj == ol) { if (t < tl) tl = t; }
                     else if (t < tl || ol == LUMO_NONE) { if (ol != LUMO_NONE) sl = fmin(sl, tl); tl = t; ol = obj; }
                     else sl = fmin(sl, t);

@@ -13,6 +13,7 @@
 #include "../common/scene_blob.h"
 #include "../common/lumo_math.h"
 #include "ah_bvh.h"
+#include "srgb_table.h"
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -858,6 +859,12 @@ int32_t lumo_host_build(const void* program, uint64_t len, void** blob, uint64_t
     catch (...) { lumo_host::g_err = "host build: unknown exception"; return -1; }
 }
 void lumo_host_free(void* p) { std::free(p); }
+// Regenerates the payload of the reference's `srgb.coeff` (spectrum/tables.rs:6-84): scale[64] then data[3 * 64^3 * 3], f32.
+// illum_div <= 0: normalise D65 so that white has Y = 1 under the optimiser's own quadrature.  Takes some 10 s per core-minute.
+int32_t lumo_host_srgb_table(float* scale64, float* data, int32_t threads, double illum_div, double clamp_max) {
+    try { lumo_host::srgb_table::generate(scale64, data, threads, illum_div, clamp_max); return 0; }
+    catch (...) { lumo_host::g_err = "srgb table: exception"; return -1; }
+}
 // lumo_math.h on the host (fn as in lumo_gpu_math_eval): the host-side film finalisation (lumo_b200/color.py: encode) takes its
 // transfer-curve pow from here so that it is the device's, bit for bit.
 void lumo_host_math_eval(int32_t fn, const double* x, const double* y, uint64_t n, double* out) {

@@ -1,11 +1,10 @@
-"""Host-side RGB -> spectrum coefficients (not on the device path: the scene blob carries
-(c0,c1,c2,scale) and oracle and GPU read the same numbers).  The reference looks coefficients up in a
-precomputed 64^3 table that is missing from the offline mount; lumo_b200.spectrum runs the Jakob-Hanika
-fit directly.  Checked against the reference's only known-answer vectors (tests/golden/
-spectrum_rgb_coeffs.json, from spectrum_tests.rs:37-111).  The coefficients of the sigmoid polynomial are
-strongly correlated, so a direct fit and a table lookup agree in c0/c1 to ~3 digits (stated below) but not
-to the reference's 4.6e-4 absolute bound; what must hold exactly is the defining property — the
-spectrum integrates back to the requested colour."""
+"""Host-side RGB -> spectrum coefficients (not on the device path: the scene blob carries (c0, c1, c2, scale)
+and oracle and GPU read the same numbers).  The reference looks the coefficients up in a precomputed 64^3 table that is
+missing from the offline mount; lumo_b200 regenerates the table with the published optimiser's procedure
+(csrc/host/srgb_table.h) and does the reference's f32 trilinear lookup on it (spectrum/tables.rs:31-83).  These are the
+reference's only known-answer vectors for anything on or next to the hot path (tests/golden/spectrum_rgb_coeffs.json,
+from spectrum_tests.rs:37-111), and they are met at the reference's OWN tolerance: |difference| < EPSILON^(1/3) = 4.64e-4
+on all three coefficients (spectrum_tests.rs:6-17)."""
 import json
 import os
 import numpy as np
@@ -16,13 +15,31 @@ from lumo_b200 import color
 G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "spectrum_rgb_coeffs.json")))
 
 
-def test_coefficients_close_to_reference_vectors():
-    for v in G["vectors"][:32]:
+REF_TOL = (1e-10) ** (1.0 / 3.0)          # crate::EPSILON.powf(1.0 / 3.0), spectrum_tests.rs:13
+
+
+def test_coefficients_meet_the_references_own_tolerance():
+    assert len(G["vectors"]) == 33           # 32 random colours (`probably_correct`) + white (`white_correct`)
+    worst = [0.0, 0.0, 0.0]
+    for v in G["vectors"]:
         s = Spectrum.from_rgb(*v["rgb"])
-        c0, c1, c2 = v["coeffs"]
-        assert abs(s.c0 - c0) <= 1.5e-6                      # the vectors print c0 to 6 decimals
-        assert abs(s.c1 - c1) <= 5e-4 + 2e-3 * abs(c1)
-        assert abs(s.c2 - c2) <= 0.1 + 4e-3 * abs(c2)
+        for k, (got, want) in enumerate(zip((s.c0, s.c1, s.c2), v["coeffs"])):
+            d = abs(float(np.float32(got)) - float(np.float32(want)))
+            worst[k] = max(worst[k], d)
+            assert d < REF_TOL, (v["rgb"], k, got, want)
+    assert worst[2] > 0.0                    # a lookup in a regenerated table, not a copy of the answers
+
+
+def test_table_has_the_references_file_format():
+    """srgb.coeff as spectrum/tables.rs:6-29 reads it: 9 437 448 bytes, "SPEC", u32 resolution 64, 64 scale knots, coefficients."""
+    import os
+    from lumo_b200 import spectrum
+    scale, data = spectrum.srgb_coeff_table()
+    assert os.path.getsize(spectrum._COEFF_PATH) == 9437448
+    raw = open(spectrum._COEFF_PATH, "rb").read(8)
+    assert raw[:4] == b"SPEC" and int.from_bytes(raw[4:8], "little") == 64
+    assert len(scale) == 64 and len(data) == 3 * 64 ** 3 * 3 and scale[0] == 0.0 and scale[-1] == 1.0 and (np.diff(scale) >= 0).all()
+    assert np.isfinite(data).all()
 
 
 def test_spectrum_integrates_back_to_rgb():
