@@ -8,7 +8,7 @@
 // the any-hit distance is the first triangle the front-to-back walk accepts, not necessarily the nearest one, so in
 // general the winner depends on the visit order.  It does not when
 //   (1) the nearest hit t1 of the whole group belongs to object G and no other object of the group has a hit at a
-//       distance <= t1 (no tie), and
+//       distance <= t1 (no tie; the kernels even ask for a hair of 1e-9 t1 of clearance), and
 //   (2) G's any-hit distance A — the first triangle its own kd walk accepts — equals t1.
 // Then every object visited before G reports a distance above t1 (or nothing), G reports A = t1 whatever bound it is handed
 // (a bound above A does not change the first accepted triangle), and nothing visited after G can get below it: G wins, and
@@ -110,9 +110,12 @@ __device__ __forceinline__ double ch_prim_test(const DevScene& S, const uint2 pr
     return tri_hit<false, false>(S.tri_verts + pr.x, lr, lq, 0.0, bound, th, nullptr) ? th.t : LUMO_INF;
 }
 
+// a hair behind t (see k_closest_bvh)
+__device__ __forceinline__ double ch_ext(double t) { return t + fabs(t) * 1e-9 + 1e-300; }
+
 // Source: n(), load(i, Ray&, t_max&).
 template <bool CNT, class Source>
-__global__ void __launch_bounds__(128, 4) k_closest_bvh(const __grid_constant__ DevScene S, const Source src, const ClosestScratch Q, ClosestCounters* gc) {
+__global__ void __launch_bounds__(128, LUMO_BVH_BLOCKS) k_closest_bvh(const __grid_constant__ DevScene S, const Source src, const ClosestScratch Q, ClosestCounters* gc) {
     __shared__ double local_ctx[LUMO_AH_LOCAL_DOUBLES * 128];
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t n = src.n();
@@ -158,19 +161,25 @@ __global__ void __launch_bounds__(128, 4) k_closest_bvh(const __grid_constant__ 
             if (CNT) cnt.prims++;
             const uint32_t obj = pr.y & ~LUMO_AH_INSTANCED;
             leaf_pos++;
+            // Distances up to a hair (1e-9, relative) behind the nearest hit are looked at too: an object that close behind the
+            // winner sends the ray to the reference traversal, and in return k_closest_finish may assume that the bound the
+            // reference holds when it reaches the winner's boxes is at least that hair above t1 (flat boxes — walls — have
+            // their own entry distance within an ulp of the hit).
             if (obj < n_objects) {
-                const double t = ch_prim_test<CNT>(S, pr, r, q, t1, L, &cnt);
-                if (t <= t1 && t < LUMO_INF) {                   // (a miss is +inf.)  Distances equal to the bound matter: a tie sends the ray to the reference traversal
+                const double lim = ch_ext(t1);
+                const double t = ch_prim_test<CNT>(S, pr, r, q, lim, L, &cnt);
+                if (t <= lim && t < LUMO_INF) {                  // (a miss is +inf)
                     if (obj == o1) { if (t < t1) t1 = t; }
                     else if (t < t1 || o1 == LUMO_NONE) { if (o1 != LUMO_NONE) s1 = fmin(s1, t1); t1 = t; o1 = obj; }
                     else s1 = fmin(s1, t);
-                    float tm = (float)t1; if ((double)tm < t1) tm = nextafterf(tm, INFINITY);
+                    const double e = ch_ext(t1);
+                    float tm = (float)e; if ((double)tm < e) tm = nextafterf(tm, INFINITY);
                     a.tmax = tm;                                 // nothing beyond the nearest object hit is of interest (lights: only below it)
                 }
             } else {
-                const double bound = fmin(t1, tl);
-                const double t = ch_prim_test<CNT>(S, pr, r, q, bound, L, &cnt);
-                if (t <= bound && t < LUMO_INF) {
+                const double lim = fmin(t1, ch_ext(tl));
+                const double t = ch_prim_test<CNT>(S, pr, r, q, lim, L, &cnt);
+                if (t <= lim && t < LUMO_INF) {
                     if (obj == ol) { if (t < tl) tl = t; }
                     else if (t < tl || ol == LUMO_NONE) { if (ol != LUMO_NONE) sl = fmin(sl, tl); tl = t; ol = obj; }
                     else sl = fmin(sl, t);
@@ -179,8 +188,8 @@ __global__ void __launch_bounds__(128, 4) k_closest_bvh(const __grid_constant__ 
             if (leaf_pos == leaf_end) { if (!ch_pop(a, node, stack, stack_t, sp)) done = true; }
         }
         if (done) {
-            if (o1 != LUMO_NONE && s1 <= t1) flags |= 1u;
-            if (ol != LUMO_NONE && sl <= tl) flags |= 2u;
+            if (o1 != LUMO_NONE && s1 <= ch_ext(t1)) flags |= 1u;
+            if (ol != LUMO_NONE && sl <= ch_ext(tl)) flags |= 2u;
             Q.t1[i] = t1; Q.tl[i] = tl; Q.o1[i] = o1; Q.ol[i] = ol; Q.flags[i] = flags;
             active = false;
         }
@@ -189,16 +198,16 @@ __global__ void __launch_bounds__(128, 4) k_closest_bvh(const __grid_constant__ 
 }
 
 // the box tests of the object-BVH nodes above `obj` (bvh.rs:333-335).  When the reference reaches them its bound tt is
-// above t_hit (every other object's hits are), so passing with tt = t_hit implies passing with the reference's tt.
+// at least `tt_low` (every other object's hits are beyond it), so passing with tt = tt_low implies passing with the reference's tt.
 template <bool CNT>
-__device__ __forceinline__ bool ch_path_ok(const DevScene& S, uint32_t obj, const RayCtx& w, double t_hit, Counters* c) {
+__device__ __forceinline__ bool ch_path_ok(const DevScene& S, uint32_t obj, const RayCtx& w, double tt_low, Counters* c) {
     const uint32_t p0 = S.obj_path_off[obj], p1 = S.obj_path_off[obj + 1];
     for (uint32_t p = p0; p < p1; p++) {
         const LumoTlasNode* node = S.tlas + S.obj_path[p];
         LUMO_CNT(tlas);
         double t_start, t_end;
         box_intersect(node->lo, node->hi, w.r.o, w.inv, t_start, t_end);
-        t_start = fmax(t_start, 0.0); t_end = fmin(t_end, t_hit);
+        t_start = fmax(t_start, 0.0); t_end = fmin(t_end, tt_low);
         if (!(t_start <= t_end)) return false;
     }
     return true;
@@ -231,7 +240,7 @@ __global__ void __launch_bounds__(128, LUMO_WAVE_TRACE_BLOCKS) k_closest_finish(
             if (why < 0 && o1 != LUMO_NONE) {
                 double any_t;
                 if (flags & 1u) why = 1;
-                else if (!ch_path_ok<CNT>(S, o1, w, t1, &cnt)) why = 2;
+                else if (!ch_path_ok<CNT>(S, o1, w, fmin(t_max, ch_ext(t1)), &cnt)) why = 2;
                 else if (!object_hit<CNT, 64, LUMO_WAVE_KD_ROUND>(S, S.objects[o1], w, 0.0, t_max, h, &cnt, &any_t)) why = 3;     // a rejected full hit empties the whole group
                 else if (!same_bits(any_t, t1) || !same_bits(h.t, t1)) why = 4;
                 else { h.obj = o1; have = true; t_h = h.t; }
@@ -239,7 +248,7 @@ __global__ void __launch_bounds__(128, LUMO_WAVE_TRACE_BLOCKS) k_closest_finish(
             if (why < 0 && ol != LUMO_NONE && tl < t_h) {      // Scene::hit: lights with t_max = the objects' hit; a light has to be strictly nearer
                 HitRec hl; double any_t;
                 if (flags & 2u) why = 5;
-                else if (!ch_path_ok<CNT>(S, ol, w, tl, &cnt)) why = 6;
+                else if (!ch_path_ok<CNT>(S, ol, w, fmin(t_h, ch_ext(tl)), &cnt)) why = 6;
                 else if (!object_hit<CNT, 64, LUMO_WAVE_KD_ROUND>(S, S.objects[ol], w, 0.0, t_h, hl, &cnt, &any_t)) why = 7;
                 else if (!same_bits(any_t, tl)) why = 7;
                 else { hl.obj = ol; h = hl; have = true; }

@@ -412,7 +412,7 @@ struct Carver {   // carves 256-byte aligned arrays out of one allocation
 template <class Source, class Sink>
 static int32_t launch_occlusion(lumo_scene* sc, const Source& src, const Sink& sink, const OcclQueues& Q, cudaStream_t st) {
     lumo_ctx* ctx = sc->ctx;
-    const int g1 = ctx->sm_count * 4, g2 = ctx->sm_count * LUMO_WAVE_TRACE_BLOCKS;
+    const int g1 = ctx->sm_count * LUMO_BVH_BLOCKS, g2 = ctx->sm_count * LUMO_WAVE_TRACE_BLOCKS;
     if (ctx->count_visits) {
         k_occl_bvh<true><<<g1, 128, 0, st>>>(sc->S, src, sink, Q, ctx->d_ah);
         k_occl_confirm<true><<<g2, 128, 0, st>>>(sc->S, src, sink, Q, ctx->d_visit + 1, ctx->d_ah);
@@ -431,7 +431,7 @@ static int32_t launch_occlusion(lumo_scene* sc, const Source& src, const Sink& s
 template <class Source, class Sink>
 static int32_t launch_closest(lumo_scene* sc, const Source& src, const Sink& sink, const ClosestScratch& Q, cudaStream_t st) {
     lumo_ctx* ctx = sc->ctx;
-    const int g1 = ctx->sm_count * 4, g2 = ctx->sm_count * LUMO_WAVE_TRACE_BLOCKS;
+    const int g1 = ctx->sm_count * LUMO_BVH_BLOCKS, g2 = ctx->sm_count * LUMO_WAVE_TRACE_BLOCKS;
     if (ctx->count_visits) {
         k_closest_bvh<true><<<g1, 128, 0, st>>>(sc->S, src, Q, ctx->d_ch);
         k_closest_finish<true><<<g2, 128, 0, st>>>(sc->S, src, sink, Q, ctx->d_visit, ctx->d_ch);

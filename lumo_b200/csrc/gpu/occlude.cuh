@@ -205,6 +205,10 @@ struct OcclQueues {
 // whose ray is finished takes the next ray of the queue while the others continue (lanes are refilled once LUMO_AH_REFILL
 // of them are free), and the lanes of a warp alternate between the two kinds of work together: up to LUMO_AH_NODE_ROUND
 // inner-node steps, then one leaf primitive for every lane that holds one.
+// resident CTAs per SM the two BVH walks are compiled for (register budget 65536 / (128 * blocks)) and launched with
+#ifndef LUMO_BVH_BLOCKS
+#define LUMO_BVH_BLOCKS 4
+#endif
 #ifndef LUMO_AH_REFILL
 #define LUMO_AH_REFILL 8
 #endif
@@ -212,7 +216,7 @@ struct OcclQueues {
 #define LUMO_AH_NODE_ROUND 3
 #endif
 template <bool CNT, class Source, class Sink>
-__global__ void __launch_bounds__(128, 4) k_occl_bvh(const __grid_constant__ DevScene S, const Source src, const Sink sink, const OcclQueues Q, AhCounters* gc) {
+__global__ void __launch_bounds__(128, LUMO_BVH_BLOCKS) k_occl_bvh(const __grid_constant__ DevScene S, const Source src, const Sink sink, const OcclQueues Q, AhCounters* gc) {
     __shared__ double local_ctx[LUMO_AH_LOCAL_DOUBLES * 128];
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t n = src.n();

@@ -29,8 +29,8 @@ class Film:
         return _color.encode(self.linear_rgb(), self.cs)
 
     def rgb_image_device(self, ctx=None, device=0):
-        """The same image computed by the CUDA film kernel (lumo_gpu_film_encode; the transfer curve's pow is CUDA's,
-        so a value sitting on an integer boundary may differ by one code from `rgb_image`)."""
+        """The same image computed by the CUDA film kernel (lumo_gpu_film_encode): byte for byte `rgb_image` — the transfer
+        curve's pow is csrc/common/lumo_math.h on both sides."""
         from . import native
         own = ctx is None
         if own: ctx = native.GpuContext(device)
