@@ -2,8 +2,10 @@
 // measure}.rs and the camera importance functions camera.rs:167-388.
 //
 // Vertex-buffer design: the light and camera subpaths of a batch of camera samples are walked as a wavefront (one
-// bounce of every live subpath per iteration) into vertex arrays in HBM (LUMO_BDPT_MAXV vertices each; the reference
-// caps at 1024 — subpaths that would exceed the device cap are cut there and counted); the (s,t) terms of every sample
+// bounce of every live subpath per iteration) into vertex arrays in HBM: LUMO_BDPT_MAXV vertices per subpath in place, and
+// for the rare longer ones (specular chains) further blocks of LUMO_BDPT_MAXV from an overflow pool, up to the reference's
+// own cap of 1024 (bd_path_trace.rs:7); a subpath is only cut — and counted, counters[8] — if the pool runs dry; the (s,t)
+// terms of every sample
 // are then evaluated in parallel, one launch sequence per term class — emission and NEE one thread per term, light
 // tracing and connections through a visibility-ray queue — and a finish kernel retires the sample into the film.
 // Traversal calls (Scene::hit, hit_t, hit_light) are the same faithful routines the wavefront kernels use; visible()
@@ -15,10 +17,20 @@ namespace lumo_dev {
 
 #define LUMO_BDPT_MAXV 64
 #define LUMO_BDPT_MAX_DEPTH 1024u   /* bd_path_trace.rs:7 */
+#define LUMO_BDPT_OVF_BLOCKS (LUMO_BDPT_MAX_DEPTH / LUMO_BDPT_MAXV)   /* overflow blocks a subpath can own (vertices 64 .. 1087) */
 
 // `delta`: Vertex::is_delta (vertex.rs:90-97) evaluated once when the vertex is made — it depends on the material and the hero
 // wavelength only, and the hero wavelength never changes along a sample (termination zeroes the secondary ones).
 struct Vtx { DevHit h; C4 gathered; double pdf_fwd, pdf_bck; D3 wo; int light; int delta; };   // vertex.rs:5-12
+// The vertices of one subpath: the first LUMO_BDPT_MAXV in the batch's vertex buffer, the rest in blocks of the overflow pool.
+struct VtxArr {
+    Vtx* base; const uint32_t* tab; Vtx* pool;
+    __device__ __forceinline__ Vtx& operator[](int k) const {
+        if (k < LUMO_BDPT_MAXV) return base[k];
+        return pool[(size_t)tab[k / LUMO_BDPT_MAXV - 1] * LUMO_BDPT_MAXV + (size_t)(k % LUMO_BDPT_MAXV)];
+    }
+};
+__device__ __forceinline__ VtxArr vtx_none() { VtxArr a; a.base = nullptr; a.tab = nullptr; a.pool = nullptr; return a; }
 
 __device__ const LumoMaterial g_blank_material = {LMAT_BLANK, 0u, 1.0, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, 0u, 0u, 0u, LUMO_NONE, 0.0, LUMO_NONE, LUMO_NONE, LUMO_NONE, LUMO_NONE, 0ull};
 __device__ __forceinline__ const Mat& vmat(const DevScene& S, const Vtx& v) { return v.h.material < 0 ? g_blank_material : S.materials[v.h.material]; }
@@ -162,55 +174,73 @@ __device__ __noinline__ double pdf_connection(const DevScene& S, const Vtx& curr
 __device__ __forceinline__ double map0(double p) { return p == 0.0 ? 1.0 : p; }
 // mis.rs:103-239.  lp: light path (s vertices used), cp: camera path (t vertices used).  For s = 1 (NEE) and
 // t = 1 (light tracing) the freshly sampled end vertex is passed as `ls1_override` / `ct1_override`.
-__device__ __noinline__ double mis_weight(const DevScene& S, const Lam& l, const Vtx* lp, int s, const Vtx* cp, int t, const Vtx* ls1_override, const Vtx* ct1_override) {
+__device__ __noinline__ double mis_weight(const DevScene& S, const Lam& l, const VtxArr& lp, int s, const VtxArr& cp, int t, const Vtx* ls1_override, const Vtx* ct1_override) {
     if (s + t == 2) return 1.0;
     const Vtx& ct1 = ct1_override ? *ct1_override : cp[t - 1];
     const Vtx& ls1 = s == 0 ? cp[0] : (ls1_override ? *ls1_override : lp[s - 1]);
-    double pr[2 * LUMO_BDPT_MAXV + 4], pi[2 * LUMO_BDPT_MAXV + 4]; bool dl[2 * LUMO_BDPT_MAXV + 4];
-    int n = 0;
-    const int smax = s > 2 ? s : 2;
-    for (int i = 0; i + 2 < smax; i++) { pr[n] = lp[i].pdf_bck; pi[n] = lp[i].pdf_fwd; dl[n] = v_is_delta(S, lp[i], l); n++; }
+    // The reference fills three arrays of s + t entries (pdf towards the light, pdf towards the camera, is-delta; mis.rs:139-141)
+    // and sums over them twice.  Entry i is a pure function of i: vertex i of the light subpath below the connection, four
+    // entries around it, vertex s + t - 1 - i of the camera subpath above — so the sums run over entry(i) directly, in the
+    // reference's order, and no array bounds the path length.
+    double pr_a = 0.0, pi_a = 0.0, pr_b = 0.0, pi_b = 0.0, pr_c = 0.0, pi_c = 0.0, pr_d = 0.0, pi_d = 0.0; bool dl_a = false, dl_d = false;
     if (s > 1) {
         const Vtx& ls2 = lp[s - 2];
-        pr[n] = pdf_connection(S, ls1, ls2, l, &ct1); pi[n] = ls2.pdf_fwd; dl[n] = v_is_delta(S, ls2, l); n++;
+        pr_a = pdf_connection(S, ls1, ls2, l, &ct1); pi_a = ls2.pdf_fwd; dl_a = v_is_delta(S, ls2, l);
     }
-    if (s > 0) {
-        pr[n] = t == 1 ? pdf_camera_leaving(S, ct1, ls1, l) : pdf_connection(S, ct1, ls1, l, nullptr);
-        pi[n] = ls1.pdf_fwd; dl[n] = false; n++;
-    }
+    if (s > 0) { pr_b = t == 1 ? pdf_camera_leaving(S, ct1, ls1, l) : pdf_connection(S, ct1, ls1, l, nullptr); pi_b = ls1.pdf_fwd; }
     if (t > 0) {
         const double pb = s == 0 ? pdf_light_origin(S, ct1) : (s == 1 ? pdf_light_leaving(S, ls1, ct1, l) : pdf_connection(S, ls1, ct1, l, nullptr));
-        pr[n] = ct1.pdf_fwd; pi[n] = pb; dl[n] = false; n++;
+        pr_c = ct1.pdf_fwd; pi_c = pb;
     }
     if (t > 1) {
         const Vtx& ct2 = cp[t - 2];
         const double pb = s == 0 ? pdf_light_leaving(S, ct1, ct2, l) : pdf_connection(S, ct1, ct2, l, &ls1);
-        pr[n] = ct2.pdf_fwd; pi[n] = pb; dl[n] = v_is_delta(S, ct2, l); n++;
+        pr_d = ct2.pdf_fwd; pi_d = pb; dl_d = v_is_delta(S, ct2, l);
     }
-    const int tmax = t > 2 ? t : 2;
-    for (int i = tmax - 2; i-- > 0;) { pr[n] = cp[i].pdf_fwd; pi[n] = cp[i].pdf_bck; dl[n] = v_is_delta(S, cp[i], l); n++; }
+    auto entry = [&](int i, double& pr, double& pi, bool& dl) {
+        if (i < s - 2) { const Vtx& v = lp[i]; pr = v.pdf_bck; pi = v.pdf_fwd; dl = v_is_delta(S, v, l); }
+        else if (i == s - 2) { pr = pr_a; pi = pi_a; dl = dl_a; }
+        else if (i == s - 1) { pr = pr_b; pi = pi_b; dl = false; }
+        else if (i == s) { pr = pr_c; pi = pi_c; dl = false; }
+        else if (i == s + 1) { pr = pr_d; pi = pi_d; dl = dl_d; }
+        else { const Vtx& v = cp[s + t - 1 - i]; pr = v.pdf_fwd; pi = v.pdf_bck; dl = v_is_delta(S, v, l); }
+    };
     double sum_ri = 0.0, ri = 1.0;
-    for (int i = s; i-- > 0;) {
-        ri *= map0(pr[i]) / map0(pi[i]);
-        if (!dl[i] && !(i > 0 && dl[i - 1])) sum_ri += ri * ri;
+    {   // towards the light: i = s - 1 .. 0, each needing the delta flag of entry i - 1 as well
+        double pr = 0.0, pi = 0.0; bool dl = false;
+        if (s > 0) entry(s - 1, pr, pi, dl);
+        for (int i = s; i-- > 0;) {
+            double prn = 0.0, pin = 0.0; bool dln = false;
+            if (i > 0) entry(i - 1, prn, pin, dln);
+            ri *= map0(pr) / map0(pi);
+            if (!dl && !(i > 0 && dln)) sum_ri += ri * ri;
+            pr = prn; pi = pin; dl = dln;
+        }
     }
     ri = 1.0; sum_ri += ri;
-    for (int i = s; i + 1 < s + t; i++) {
-        ri *= map0(pi[i]) / map0(pr[i]);
-        if (!dl[i] && !dl[i + 1]) sum_ri += ri * ri;
+    {   // towards the camera: i = s .. s + t - 2, each needing the delta flag of entry i + 1
+        double pr = 0.0, pi = 0.0; bool dl = false;
+        if (s + 1 < s + t) entry(s, pr, pi, dl);
+        for (int i = s; i + 1 < s + t; i++) {
+            double prn, pin; bool dln;
+            entry(i + 1, prn, pin, dln);
+            ri *= map0(pi) / map0(pr);
+            if (!dl && !dln) sum_ri += ri * ri;
+            pr = prn; pi = pin; dl = dln;
+        }
     }
     return 1.0 / sum_ri;
 }
 
 // ---- connections (bd_path_trace.rs:77-290) ---------------------------------------------------------------
-__device__ __noinline__ C4 add_camera_path(const DevScene& S, const Lam& lam, const Vtx* cp, int t) {
+__device__ __noinline__ C4 add_camera_path(const DevScene& S, const Lam& lam, const VtxArr& cp, int t) {
     const Vtx& ct = cp[t - 1];
     if (!v_is_light(ct)) return c4(0.0);
     const C4 rad = ct.gathered * mat_emit(S, vmat(S, ct), lam, ct.h);
     if (is_black(rad)) return c4(0.0);
-    return rad * mis_weight(S, lam, nullptr, 0, cp, t, nullptr, nullptr);
+    return rad * mis_weight(S, lam, vtx_none(), 0, cp, t, nullptr, nullptr);
 }
-__device__ __noinline__ C4 connect_camera_path(const DevScene& S, Rng& rng, const Lam& lam, const Vtx* cp, int t, BdptCounters& bc) {
+__device__ __noinline__ C4 connect_camera_path(const DevScene& S, Rng& rng, const Lam& lam, const VtxArr& cp, int t, BdptCounters& bc) {
     const Vtx& cl = cp[t - 1];
     if (v_is_delta(S, cl, lam) || v_is_light(cl)) return c4(0.0);
     const uint32_t li = sample_light(S, rng_float(rng));
@@ -239,7 +269,7 @@ __device__ __noinline__ C4 connect_camera_path(const DevScene& S, Rng& rng, cons
     const C4 bsdf = v_f(S, cl, ll, lam, 0);
     const double cos_wi = v_shading_cosine(S, cl, wi);
     const C4 radiance = cl.gathered * bsdf * emittance * c4(1.0) * cos_wi / p_lig;
-    return radiance * mis_weight(S, lam, nullptr, 1, cp, t, &ll, nullptr);
+    return radiance * mis_weight(S, lam, vtx_none(), 1, cp, t, &ll, nullptr);
 }
 // ---- the estimator: bd_path_trace::integrate (bd_path_trace.rs:23-75) as three kernels over a batch ------
 //   k_bw_setup / k_bw_trace / k_bw_step   the two random walks of every sample as a wavefront (below): camera ray,
@@ -257,7 +287,9 @@ __device__ __noinline__ C4 connect_camera_path(const DevScene& S, Rng& rng, cons
 // counting the drawing terms before it.
 struct BdptBatch {
     uint32_t cap;                    // samples per batch
-    Vtx* lp; Vtx* cp;                // [cap][LUMO_BDPT_MAXV]
+    Vtx* lp; Vtx* cp;                // [cap][LUMO_BDPT_MAXV]: the first LUMO_BDPT_MAXV vertices of every subpath
+    Vtx* pool; uint32_t pool_blocks; uint32_t* pool_next;   // overflow blocks of LUMO_BDPT_MAXV vertices, handed out by an atomic counter
+    uint32_t* ovf_l; uint32_t* ovf_c;   // [cap][LUMO_BDPT_OVF_BLOCKS]: the blocks a subpath owns
     int* ns; int* nt;                // subpath lengths
     double* lam;                     // [4][cap]
     double* rx; double* ry;
@@ -282,6 +314,8 @@ struct BdptBatch {
     unsigned long long* term_off[3]; // their exclusive scans, cap + 1 entries (the emission class has one term per sample)
 };
 enum BdptClass { BC_LIGHT_TRACE = 0, BC_NEE = 1, BC_CONNECT = 2, BC_EMISSION = 3 };
+__device__ __forceinline__ VtxArr bdpt_lp(const BdptBatch& B, uint32_t b) { VtxArr a; a.base = B.lp + (size_t)b * LUMO_BDPT_MAXV; a.tab = B.ovf_l + (size_t)b * LUMO_BDPT_OVF_BLOCKS; a.pool = B.pool; return a; }
+__device__ __forceinline__ VtxArr bdpt_cp(const BdptBatch& B, uint32_t b) { VtxArr a; a.base = B.cp + (size_t)b * LUMO_BDPT_MAXV; a.tab = B.ovf_c + (size_t)b * LUMO_BDPT_OVF_BLOCKS; a.pool = B.pool; return a; }
 
 
 // ---- the two random walks of every sample as a wavefront ----------------------------------------------------
@@ -400,15 +434,24 @@ __global__ void __launch_bounds__(128, 8) k_bw_trace(const __grid_constant__ Dev
 // one iteration of path_gen::walk (path_gen.rs:53-157) for the live subpath of sample b, given the closest hit of its
 // current ray; a light subpath that ends hands over to the sample's camera subpath (path_gen.rs:4-19).  Returns whether the
 // sample still has a subpath in flight.
+// the vertex about to be written (index n, a multiple of LUMO_BDPT_MAXV) needs a new overflow block
+__device__ __forceinline__ bool bw_grow(const BdptBatch& B, uint32_t phase, uint32_t b, int n) {
+    const int slot = n / LUMO_BDPT_MAXV - 1;
+    if (slot >= (int)LUMO_BDPT_OVF_BLOCKS) return false;
+    const uint32_t blk = atomicAdd(B.pool_next, 1u);
+    if (blk >= B.pool_blocks) return false;
+    (phase == 0u ? B.ovf_l : B.ovf_c)[(size_t)b * LUMO_BDPT_OVF_BLOCKS + slot] = blk;
+    return true;
+}
 __device__ __forceinline__ bool bw_step_one(const DevScene& S, const WaveParams& P, const BdptBatch& B, uint32_t b, bool have, const HitRec& rec, unsigned long long& overflow) {
     const uint32_t phase = B.w_phase[b];
     const int mode = phase == 0u ? 1 : 0;
-    Vtx* vs = (phase == 0u ? B.lp : B.cp) + (size_t)b * LUMO_BDPT_MAXV;
+    const VtxArr vs = phase == 0u ? bdpt_lp(B, b) : bdpt_cp(B, b);
     int n = (int)B.w_n[b];
     uint32_t depth = B.w_depth[b];
     bool end = false;
     if (!have) end = true;
-    else if (n >= LUMO_BDPT_MAXV) { overflow++; end = true; }
+    else if (n >= LUMO_BDPT_MAXV && n % LUMO_BDPT_MAXV == 0 && !bw_grow(B, phase, b, n)) { overflow++; end = true; }   // the next vertex opens a new block and none is left
     else {
         const Ray ro = bw_load_ray(B, B.w_ray, b);
         Lam lam; C4 gathered;
@@ -535,8 +578,7 @@ __global__ void __launch_bounds__(128) k_bdpt_connect(const __grid_constant__ De
         }
         const int ns = B.ns[b], nt = B.nt[b];
         if (CLS == BC_EMISSION && nt == 0 && ns == 0) continue;        // an invalid sample has no terms at all
-        const Vtx* lp = B.lp + (size_t)b * LUMO_BDPT_MAXV;
-        const Vtx* cp = B.cp + (size_t)b * LUMO_BDPT_MAXV;
+        const VtxArr lp = bdpt_lp(B, b), cp = bdpt_cp(B, b);
         Lam lam; for (int k = 0; k < 4; k++) lam.l[k] = B.lam[(size_t)k * B.cap + b];
         C4 contrib = c4(0.0);
         if (CLS == BC_EMISSION) contrib = add_camera_path(S, lam, cp, nt);          // s = 0
@@ -570,7 +612,7 @@ __device__ __forceinline__ void bq_term_of(const BdptBatch& B, int cls, unsigned
     if (cls == BC_LIGHT_TRACE) { s = (int)j + 2; t = 1; }
     else { const int ns = B.ns[b]; const uint32_t L = (uint32_t)(ns - 1); t = (int)(j / L) + 2; s = (int)(j % L) + 2; }   // t outer, s inner (bd_path_trace.rs:57-66)
 }
-__device__ __forceinline__ Rng bq_light_trace_rng(const DevScene& S, const WaveParams& P, const BdptBatch& B, uint32_t b, const Vtx* lp, int s, const Lam& lam) {
+__device__ __forceinline__ Rng bq_light_trace_rng(const DevScene& S, const WaveParams& P, const BdptBatch& B, uint32_t b, const VtxArr& lp, int s, const Lam& lam) {
     uint32_t drawing = 0;                                               // 2 draws per non-delta light vertex before this one, in the reference's order
     for (int q = 2; q < s; q++) if (!v_is_delta(S, lp[q - 1], lam)) drawing++;
     return rng_make(P.seed, B.pixel[b], B.sample[b], 0u, B.draws[b] + 2u * drawing);
@@ -585,8 +627,7 @@ __global__ void __launch_bounds__(128) k_bq_prepare(const __grid_constant__ DevS
         if (i < count) {
             uint32_t b; int s, t;
             bq_term_of(B, CLS, t0 + i, n, b, s, t);
-            const Vtx* lp = B.lp + (size_t)b * LUMO_BDPT_MAXV;
-            const Vtx* cp = B.cp + (size_t)b * LUMO_BDPT_MAXV;
+            const VtxArr lp = bdpt_lp(B, b), cp = bdpt_cp(B, b);
             Lam lam; for (int k = 0; k < 4; k++) lam.l[k] = B.lam[(size_t)k * B.cap + b];
             key = (unsigned long long)b | ((unsigned long long)s << 32) | ((unsigned long long)t << 48);
             const Vtx& ll = lp[s - 1];
@@ -655,8 +696,7 @@ __global__ void __launch_bounds__(128) k_bq_finish(const __grid_constant__ DevSc
         if (q >= n) continue;
         const unsigned long long key = B.q_term[q];
         const uint32_t b = (uint32_t)key; const int s = (int)((key >> 32) & 0xFFFFu), t = (int)(key >> 48);
-        const Vtx* lp = B.lp + (size_t)b * LUMO_BDPT_MAXV;
-        const Vtx* cp = B.cp + (size_t)b * LUMO_BDPT_MAXV;
+        const VtxArr lp = bdpt_lp(B, b), cp = bdpt_cp(B, b);
         Lam lam; for (int k = 0; k < 4; k++) lam.l[k] = B.lam[(size_t)k * B.cap + b];
         Ray ri; ri.o = d3(B.q_ray[q], B.q_ray[c + q], B.q_ray[2 * c + q]); ri.d = d3(B.q_ray[3 * c + q], B.q_ray[4 * c + q], B.q_ray[5 * c + q]);
         const Vtx& ll = lp[s - 1];
@@ -673,7 +713,7 @@ __global__ void __launch_bounds__(128) k_bq_finish(const __grid_constant__ DevSc
             color = color / p_imp;
             Vtx cl; v_camera(cl, xo, cam_pdf_xo(S.P.camera, ri), color / p_imp);
             color = color * (ll.gathered * c4(1.0) * v_shading_cosine(S, ll, -wi) * v_shading_correction(S, ll, -wi)
-                             * v_f(S, ll, cl, lam, 1) * mis_weight(S, lam, lp, s, nullptr, 1, nullptr, &cl));
+                             * v_f(S, ll, cl, lam, 1) * mis_weight(S, lam, lp, s, vtx_none(), 1, nullptr, &cl));
             if (P.mode == WM_MAIN) film_add_sample(S, W.pixels, W.splats, tone_map(S, (int)P.tone_map, P.tone_map_arg, color, lam), lam, sx, sy, true);
         } else {                                                        // visible()'s comparison and the rest of connect_paths (:243-255, :286-289)
             const Vtx& cl = cp[t - 1];
@@ -696,8 +736,7 @@ __global__ void __launch_bounds__(256) k_bdpt_finish(const __grid_constant__ Dev
     for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < n; b += gridDim.x * blockDim.x) {
         if (!B.valid[b]) continue;
         const int ns = B.ns[b], nt = B.nt[b];
-        const Vtx* lp = B.lp + (size_t)b * LUMO_BDPT_MAXV;
-        const Vtx* cp = B.cp + (size_t)b * LUMO_BDPT_MAXV;
+        const VtxArr lp = bdpt_lp(B, b), cp = bdpt_cp(B, b);
         Lam lam; C4 radiance;
         for (int k = 0; k < 4; k++) { lam.l[k] = B.lam[(size_t)k * B.cap + b]; radiance.s[k] = B.radiance[(size_t)k * B.cap + b]; }
         unsigned long long cost = (unsigned long long)(ns + nt);                                 // bd_path_trace.rs:31-66

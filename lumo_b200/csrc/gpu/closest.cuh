@@ -43,7 +43,7 @@ struct ClosestCounters { unsigned long long nodes, prims, tris, spheres, fallbac
 #define LUMO_CH_REFILL 8
 #endif
 #ifndef LUMO_CH_NODE_ROUND
-#define LUMO_CH_NODE_ROUND 3
+#define LUMO_CH_NODE_ROUND 4
 #endif
 
 // One inner-node step of the ordered walk: hit children are pushed with their entry distances, the nearest is walked next.

@@ -684,7 +684,8 @@ static int32_t run_wave(lumo_scene* sc, const Wave& W, WaveParams P, uint64_t& i
 // BDPT: batches of camera samples through walk -> scan -> connect -> finish (bdpt.cuh)
 // Samples per BDPT batch.  Every bounce of the walk wavefront costs at least one traversal's latency (~0.3 ms once a few
 // thousand subpaths are left), and long specular chains give 70+ bounces: large batches pay that tail once.  A sample
-// owns 2 x LUMO_BDPT_MAXV vertices (27 KB), so 2^20 samples are 28 GB of the 180 GB — sized down if memory is short.
+// owns 2 x LUMO_BDPT_MAXV vertices in place (27 KB; longer subpaths take blocks from an overflow pool, up to the reference's
+// 1024), so 2^20 samples are 28 GB of the 180 GB — sized down if memory is short.
 #define LUMO_BDPT_BATCH_MAX (1u << 20)
 #define LUMO_BW_TAIL 32768u          /* live subpaths at or below which the walk wavefront hands over to k_bw_tail (walks, caustics 1 spp: 0: 133.9 ms, 2048: 130.4, 8192: 127.1, 32768: 123.2, 131072: 130.1) */
 #define LUMO_BDPT_QUEUE (1u << 22)   /* terms per chunk of the visibility-ray queue (100 B each) */
@@ -692,6 +693,11 @@ struct BdptStorage { BdptBatch B; void* scan_tmp = nullptr; size_t scan_bytes = 
 static void bdpt_carve(BdptBatch& B, Carver& c, uint32_t cap) {
     B.cap = cap;
     B.lp = c.take<Vtx>((size_t)cap * LUMO_BDPT_MAXV); B.cp = c.take<Vtx>((size_t)cap * LUMO_BDPT_MAXV);
+    // overflow blocks for subpaths longer than LUMO_BDPT_MAXV vertices (specular chains): one block per 16 samples is ~60x what the
+    // caustics scene uses; a subpath is cut (and counted) only when the pool is exhausted
+    B.pool_blocks = std::max(1024u, cap / 16u);
+    B.pool = c.take<Vtx>((size_t)B.pool_blocks * LUMO_BDPT_MAXV); B.pool_next = c.take<uint32_t>(4);
+    B.ovf_l = c.take<uint32_t>((size_t)cap * LUMO_BDPT_OVF_BLOCKS); B.ovf_c = c.take<uint32_t>((size_t)cap * LUMO_BDPT_OVF_BLOCKS);
     B.ns = c.take<int>(cap); B.nt = c.take<int>(cap);
     B.lam = c.take<double>(4 * (size_t)cap); B.rx = c.take<double>(cap); B.ry = c.take<double>(cap); B.radiance = c.take<double>(4 * (size_t)cap);
     B.pixel = c.take<uint32_t>(cap); B.sample = c.take<uint32_t>(cap); B.draws = c.take<uint32_t>(cap); B.witem = c.take<uint32_t>(cap); B.valid = c.take<uint32_t>(cap);
@@ -746,6 +752,7 @@ static int32_t run_bdpt(lumo_scene* sc, const Wave& W, const WaveParams& P, Bdpt
         const uint32_t n = (uint32_t)std::min<unsigned long long>(B.cap, P.total_work - w0);
         CU(cudaEventRecord(ev[0], st));
         CU(cudaMemsetAsync(B.n_act, 0, 16, st));
+        CU(cudaMemsetAsync(B.pool_next, 0, 16, st));
         k_bw_setup<<<ctx->sm_count * 8, 128, 0, st>>>(sc->S, W, P, B, w0, n);
         ctx->launches += 1;
         for (uint32_t it = 0;;) {                                        // one bounce of every live subpath per iteration; 8 iterations per host look

@@ -205,15 +205,17 @@ struct OcclQueues {
 // whose ray is finished takes the next ray of the queue while the others continue (lanes are refilled once LUMO_AH_REFILL
 // of them are free), and the lanes of a warp alternate between the two kinds of work together: up to LUMO_AH_NODE_ROUND
 // inner-node steps, then one leaf primitive for every lane that holds one.
-// resident CTAs per SM the two BVH walks are compiled for (register budget 65536 / (128 * blocks)) and launched with
+// resident CTAs per SM the two BVH walks are compiled for (register budget 65536 / (128 * blocks)) and launched with.
+// Same-box A/B on B200, bistro 4 spp, occlusion class ms: 4 CTAs (114 registers) 176.2, 5 (102) 155.3, 6 (85, spills) 161.4.
 #ifndef LUMO_BVH_BLOCKS
-#define LUMO_BVH_BLOCKS 4
+#define LUMO_BVH_BLOCKS 5
 #endif
 #ifndef LUMO_AH_REFILL
 #define LUMO_AH_REFILL 8
 #endif
+// (same A/B: refill at 4 free lanes 181.8 / at 8: 176.2; node steps per round 2: 185.2, 3: 176.2, 4: 173.1)
 #ifndef LUMO_AH_NODE_ROUND
-#define LUMO_AH_NODE_ROUND 3
+#define LUMO_AH_NODE_ROUND 4
 #endif
 template <bool CNT, class Source, class Sink>
 __global__ void __launch_bounds__(128, LUMO_BVH_BLOCKS) k_occl_bvh(const __grid_constant__ DevScene S, const Source src, const Sink sink, const OcclQueues Q, AhCounters* gc) {

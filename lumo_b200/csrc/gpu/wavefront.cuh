@@ -547,8 +547,9 @@ __device__ __forceinline__ bool nee_item(const Wave& W, uint32_t klass, unsigned
     slot = W.cls[klass][qi];
     return (W.flags[slot] & PF_NEE) != 0u;
 }
+// (same-box A/B, bistro 4 spp, shade class ms: 4 CTAs per SM 245.6, 5: 250.6, 6: 265.9)
 #ifndef LUMO_NEE_A_BLOCKS
-#define LUMO_NEE_A_BLOCKS 5
+#define LUMO_NEE_A_BLOCKS 4
 #endif
 // the light-sampled term, up to the point where the material comes in (integrator.rs:96-110)
 template <bool TEX>
