@@ -19,6 +19,7 @@ static int32_t fail(int32_t code, const std::string& msg) { g_err = msg; return 
 
 #define LUMO_ITER_LOG_CAP 16384
 #define LUMO_ITER_BATCH 4   /* wave iterations enqueued per host synchronisation */
+#define LUMO_TINY_SCENE_PRIMS 256u   /* at or below: closest hits and occlusion replay the reference traversal directly (measured on the 32-triangle Cornell box: 875 vs 714 Mrays/s) */
 
 struct lumo_ctx {
     int device = 0, sm_count = 0;
@@ -53,6 +54,7 @@ struct lumo_scene {
     LumoBlobHeader H;
     bool has_textures = false;                       // any LumoTexture record (then materials may refer to textures / bump maps)
     uint32_t kind_mask = 0;   // bit k set: some Standard material of LumoMatKind k exists (which shade kernels to launch)
+    bool tiny = false;        // a handful of primitives (Cornell box: 32): the reference traversal itself is a few steps, the BVH pipelines' extra passes cost more than they save
 };
 
 extern "C" const char* lumo_gpu_last_error(void) { return g_err.c_str(); }
@@ -289,6 +291,7 @@ static bool validate_blob(const uint8_t* b, uint64_t len, LumoBlobHeader& H, std
     }
     const LumoSceneParams& P = H.params;
     if (P.n_objects == 0 || P.n_lights == 0) { why = "scene needs at least one object and one light"; return false; }
+    if (P.n_lights >= (1u << 24) || P.n_shadow_rays == 0 || P.n_shadow_rays > 64) { why = "more than 2^24 lights, or a shadow-ray count outside [1, 64]"; return false; }   // the NEE pick queue packs light | sample << 24
     if (H.sec[LSEC_OBJECTS].count != (uint64_t)P.n_objects + P.n_lights || H.sec[LSEC_LIGHTS].count != P.n_lights) { why = "object / light counts disagree with sections"; return false; }
     if (P.camera.res_x == 0 || P.camera.res_y == 0) { why = "camera resolution is zero"; return false; }
     // index ranges (a malformed blob must not make a kernel read out of bounds)
@@ -382,6 +385,7 @@ extern "C" int32_t lumo_gpu_scene_upload(lumo_ctx* ctx, const void* blob, uint64
     S.rects = (const LumoRect*)at(LSEC_RECTS); S.spheres = (const LumoSphere*)at(LSEC_SPHERES);
     S.materials = (const LumoMaterial*)at(LSEC_MATERIALS); S.tables = (const double*)at(LSEC_TABLES); S.lights = (const LumoLight*)at(LSEC_LIGHTS);
     sc->has_textures = H.sec[LSEC_TEXTURES].count > 0;
+    sc->tiny = H.sec[LSEC_AH_PRIMS].count <= LUMO_TINY_SCENE_PRIMS;
     S.textures = (const LumoTexture*)at(LSEC_TEXTURES); S.tex_pixels = (const float*)at(LSEC_TEX_PIXELS); S.tex_f64 = (const double*)at(LSEC_TEX_F64);
     S.ah_nodes = (const LumoAhNode*)at(LSEC_AH_NODES); S.ah_prims = (const LumoAhPrim*)at(LSEC_AH_PRIMS);
     S.obj_path_off = (const uint32_t*)at(LSEC_OBJ_PATH_OFF); S.obj_path = (const uint32_t*)at(LSEC_OBJ_PATH);
@@ -577,6 +581,7 @@ static void carve_wave(Wave& W, Carver& c, uint32_t N, uint32_t shadow_cap, uint
     { NeeTermQueue& T = W.tq; T.ox = c.take<double>(C); T.oy = c.take<double>(C); T.oz = c.take<double>(C); T.dx = c.take<double>(C); T.dy = c.take<double>(C); T.dz = c.take<double>(C);
       T.wx = c.take<double>(C); T.wy = c.take<double>(C); T.wz = c.take<double>(C); T.tmax = c.take<double>(C); T.p_lig = c.take<double>(C); T.pdf_light = c.take<double>(C);
       T.le = c.take<double>(4 * C); T.slot = c.take<uint32_t>(C); }
+    for (int b = 0; b < 2; b++) { W.pk_slot[b] = c.take<uint32_t>(C / 2 + 32); W.pk_li[b] = c.take<uint32_t>(C / 2 + 32); }
     W.it = c.take<IterCounters>(1); W.run = c.take<RunCounters>(1); W.qc = c.take<QueueCounters>(1);
     W.tile_delta = c.take<double>(n_tiles); W.tile_delta_next = c.take<double>(n_tiles);
     W.pilot_lum = c.take<double>((size_t)n_tiles * LUMO_PILOT_N); W.pilot_cost = c.take<uint32_t>((size_t)n_tiles * LUMO_PILOT_N);
@@ -590,19 +595,20 @@ template <int K>
 static void launch_shade_kind(lumo_scene* sc, const Wave& W, const WaveParams& P, int grid, int nee_grid, cudaStream_t st, unsigned long long& launches) {
     if (!(sc->kind_mask & (1u << K))) return;
     // no LumoTexture record in the scene: the texture-free instantiations (shade.cuh LUMO_K_SOLID)
+    const int pgrid = nee_grid / 2 + 1;     // 256-thread blocks
     if (sc->has_textures) {
         k_scatter<K><<<grid, 128, 0, st>>>(sc->S, W, P);
-        k_nee_a<true><<<nee_grid, 128, 0, st>>>(sc->S, W, P, (uint32_t)K);
-        k_nee_b<K><<<nee_grid, 128, 0, st>>>(sc->S, W, P);
+        k_nee_pick<<<pgrid, 256, 0, st>>>(sc->S, W, P, (uint32_t)K);
+        for (uint32_t bin = 0; bin < 2; bin++) { k_nee_a<true><<<nee_grid, 128, 0, st>>>(sc->S, W, P, (uint32_t)K, bin); k_nee_b<K><<<nee_grid, 128, 0, st>>>(sc->S, W, P, bin); }
         k_nee_eval<K><<<nee_grid, 128, 0, st>>>(sc->S, W, P);
     } else {
         k_scatter<K | LUMO_K_SOLID><<<grid, 128, 0, st>>>(sc->S, W, P);
-        k_nee_a<false><<<nee_grid, 128, 0, st>>>(sc->S, W, P, (uint32_t)K);
-        k_nee_b<K | LUMO_K_SOLID><<<nee_grid, 128, 0, st>>>(sc->S, W, P);
+        k_nee_pick<<<pgrid, 256, 0, st>>>(sc->S, W, P, (uint32_t)K);
+        for (uint32_t bin = 0; bin < 2; bin++) { k_nee_a<false><<<nee_grid, 128, 0, st>>>(sc->S, W, P, (uint32_t)K, bin); k_nee_b<K | LUMO_K_SOLID><<<nee_grid, 128, 0, st>>>(sc->S, W, P, bin); }
         k_nee_eval<K | LUMO_K_SOLID><<<nee_grid, 128, 0, st>>>(sc->S, W, P);
     }
     k_terms_reset<<<1, 1, 0, st>>>(W.it);
-    launches += 5;
+    launches += 8;
 }
 
 // Runs waves until the work counter is exhausted and no path is alive.
@@ -635,7 +641,7 @@ static int32_t run_wave(lumo_scene* sc, const Wave& W, WaveParams P, uint64_t& i
             k_retire<<<rgrid, 256, 0, st>>>(sc->S, W, P);
             k_compact<<<rgrid, 256, 0, st>>>(W);
             CU(cudaEventRecord(ev[1], st));
-            if (ctx->closest_faithful) {
+            if (ctx->closest_faithful || sc->tiny) {
                 if (ctx->count_visits) k_wave_trace<true><<<tgrid, 128, 0, st>>>(sc->S, W, P.cur, ctx->d_visit);
                 else k_wave_trace<false><<<tgrid, 128, 0, st>>>(sc->S, W, P.cur, nullptr);
             } else {
@@ -652,7 +658,7 @@ static int32_t run_wave(lumo_scene* sc, const Wave& W, WaveParams P, uint64_t& i
             launch_shade_kind<LMAT_MFCONDUCTOR>(sc, W, P, sgrid, ngrid, st, ctx->launches);
             launch_shade_kind<LMAT_MFDIELECTRIC>(sc, W, P, sgrid, ngrid, st, ctx->launches);
             CU(cudaEventRecord(ev[3], st));
-            if (ctx->occl_faithful) {
+            if (ctx->occl_faithful || (sc->tiny && !ctx->occl_check)) {
                 if (ctx->count_visits) k_wave_occlude<true><<<tgrid, 128, 0, st>>>(sc->S, W, ctx->d_visit + 1, nullptr, nullptr);
                 else k_wave_occlude<false><<<tgrid, 128, 0, st>>>(sc->S, W, nullptr, nullptr, nullptr);
                 ctx->launches++;
