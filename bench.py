@@ -242,6 +242,10 @@ def measure(name, args, env, steps, warmup, full):
     world, rank, dev, ctx, stream, flush = env["world"], env["rank"], env["dev"], env["ctx"], env["stream"], env["flush"]
     prog, blob, integrator, spp = build_workload(name)
     if args.spp and name == args.workload: spp = args.spp
+    strong = bool(args.total_spp) and name == args.workload
+    if strong:
+        assert args.total_spp % world == 0, "--total-spp must be a multiple of the number of GPUs"
+        spp = args.total_spp // world
     total_spp = spp * world
     s0, s1 = rank * spp, (rank + 1) * spp
     ctx.set_stream(stream.cuda_stream)
@@ -333,8 +337,8 @@ def measure(name, args, env, steps, warmup, full):
 
     # ---- rank 0 only from here: counting pass, rooflines, cpu baseline ------------------------------------------------------------
     line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": steps, "warmup": warmup,
-            "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config_of(name, integrator, spp, world, (W, H)),
+            "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": dict(config_of(name, integrator, spp, world, (W, H)), **({"total_spp_per_step": total_spp} if strong else {})),
             "msamples_per_s": paths / (ms_total * 1e-3) / 1e6, "rays_per_sample": rays / max(paths, 1),
             "rays": {"closest_hit": closest, "occlusion": occl, "camera_paths": paths, "reference_style_cost": tot["cost"]},
             "gpu_launches": int(launches), "clocks": clk, "e2e": e2e}
@@ -445,6 +449,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="bistro", choices=list(WORKLOADS))
     ap.add_argument("--spp", type=int, default=0, help="samples per pixel per step and per GPU (0 = workload default)")
+    ap.add_argument("--total-spp", type=int, default=0, help="fixed job (strong scaling): this many samples per pixel per step in total, split evenly over the GPUs")
     ap.add_argument("--wave-paths", type=int, default=0)
     ap.add_argument("--other-workloads", default="cornell,bunny,dragon,caustics_bdpt,conference", help="comma list measured after the main workload with fewer steps ('' = none); N = 1 only")
     ap.add_argument("--other-steps", type=int, default=2)

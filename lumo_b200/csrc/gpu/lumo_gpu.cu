@@ -291,7 +291,7 @@ static bool validate_blob(const uint8_t* b, uint64_t len, LumoBlobHeader& H, std
     }
     const LumoSceneParams& P = H.params;
     if (P.n_objects == 0 || P.n_lights == 0) { why = "scene needs at least one object and one light"; return false; }
-    if (P.n_lights >= (1u << 24) || P.n_shadow_rays == 0 || P.n_shadow_rays > 64) { why = "more than 2^24 lights, or a shadow-ray count outside [1, 64]"; return false; }   // the NEE pick queue packs light | sample << 24
+    if (P.n_lights >= (1u << 24) || P.n_shadow_rays == 0 || P.n_shadow_rays > 64) { why = "more than 2^24 lights, or a shadow-ray count outside [1, 64]"; return false; }
     if (H.sec[LSEC_OBJECTS].count != (uint64_t)P.n_objects + P.n_lights || H.sec[LSEC_LIGHTS].count != P.n_lights) { why = "object / light counts disagree with sections"; return false; }
     if (P.camera.res_x == 0 || P.camera.res_y == 0) { why = "camera resolution is zero"; return false; }
     // index ranges (a malformed blob must not make a kernel read out of bounds)
@@ -581,7 +581,6 @@ static void carve_wave(Wave& W, Carver& c, uint32_t N, uint32_t shadow_cap, uint
     { NeeTermQueue& T = W.tq; T.ox = c.take<double>(C); T.oy = c.take<double>(C); T.oz = c.take<double>(C); T.dx = c.take<double>(C); T.dy = c.take<double>(C); T.dz = c.take<double>(C);
       T.wx = c.take<double>(C); T.wy = c.take<double>(C); T.wz = c.take<double>(C); T.tmax = c.take<double>(C); T.p_lig = c.take<double>(C); T.pdf_light = c.take<double>(C);
       T.le = c.take<double>(4 * C); T.slot = c.take<uint32_t>(C); }
-    for (int b = 0; b < 2; b++) { W.pk_slot[b] = c.take<uint32_t>(C / 2 + 32); W.pk_li[b] = c.take<uint32_t>(C / 2 + 32); }
     W.it = c.take<IterCounters>(1); W.run = c.take<RunCounters>(1); W.qc = c.take<QueueCounters>(1);
     W.tile_delta = c.take<double>(n_tiles); W.tile_delta_next = c.take<double>(n_tiles);
     W.pilot_lum = c.take<double>((size_t)n_tiles * LUMO_PILOT_N); W.pilot_cost = c.take<uint32_t>((size_t)n_tiles * LUMO_PILOT_N);
@@ -595,20 +594,19 @@ template <int K>
 static void launch_shade_kind(lumo_scene* sc, const Wave& W, const WaveParams& P, int grid, int nee_grid, cudaStream_t st, unsigned long long& launches) {
     if (!(sc->kind_mask & (1u << K))) return;
     // no LumoTexture record in the scene: the texture-free instantiations (shade.cuh LUMO_K_SOLID)
-    const int pgrid = nee_grid / 2 + 1;     // 256-thread blocks
     if (sc->has_textures) {
         k_scatter<K><<<grid, 128, 0, st>>>(sc->S, W, P);
-        k_nee_pick<<<pgrid, 256, 0, st>>>(sc->S, W, P, (uint32_t)K);
-        for (uint32_t bin = 0; bin < 2; bin++) { k_nee_a<true><<<nee_grid, 128, 0, st>>>(sc->S, W, P, (uint32_t)K, bin); k_nee_b<K><<<nee_grid, 128, 0, st>>>(sc->S, W, P, bin); }
+        k_nee_a<true><<<nee_grid, 128, 0, st>>>(sc->S, W, P, (uint32_t)K);
+        k_nee_b<K><<<nee_grid, 128, 0, st>>>(sc->S, W, P);
         k_nee_eval<K><<<nee_grid, 128, 0, st>>>(sc->S, W, P);
     } else {
         k_scatter<K | LUMO_K_SOLID><<<grid, 128, 0, st>>>(sc->S, W, P);
-        k_nee_pick<<<pgrid, 256, 0, st>>>(sc->S, W, P, (uint32_t)K);
-        for (uint32_t bin = 0; bin < 2; bin++) { k_nee_a<false><<<nee_grid, 128, 0, st>>>(sc->S, W, P, (uint32_t)K, bin); k_nee_b<K | LUMO_K_SOLID><<<nee_grid, 128, 0, st>>>(sc->S, W, P, bin); }
+        k_nee_a<false><<<nee_grid, 128, 0, st>>>(sc->S, W, P, (uint32_t)K);
+        k_nee_b<K | LUMO_K_SOLID><<<nee_grid, 128, 0, st>>>(sc->S, W, P);
         k_nee_eval<K | LUMO_K_SOLID><<<nee_grid, 128, 0, st>>>(sc->S, W, P);
     }
     k_terms_reset<<<1, 1, 0, st>>>(W.it);
-    launches += 8;
+    launches += 5;
 }
 
 // Runs waves until the work counter is exhausted and no path is alive.

@@ -36,7 +36,7 @@ struct IterCounters {   // zeroed before every iteration
     uint32_t n_shadow, trace_next, occl_next, n_active;
     uint32_t n_class[LUMO_N_CLASSES], pad[3];
     uint32_t occl[8];   // OcclQueues::counters of the occlusion-BVH kernels (occlude.cuh)
-    uint32_t n_terms, n_pick[2], pad2;   // NEE term queue; light picks per bin (0: triangle / rectangle lights, 1: sphere lights)
+    uint32_t n_terms, pad2[3];   // NEE term queue
     uint32_t closest[4];         // ClosestScratch::counters of the closest-hit pipeline (closest.cuh)
 };
 // Counters that live across iterations (double-buffered by the parity of the iteration): done[p] = slots whose
@@ -73,8 +73,7 @@ struct Wave {
     // shadow queue (SoA)
     double *sox, *soy, *soz, *sdx, *sdy, *sdz, *stmax, *sc; uint32_t* sslot;
     double *ch_t1, *ch_tl; uint32_t *ch_o1, *ch_ol, *ch_flags, *ch_fb;   // closest-hit pipeline: per-ray scratch of k_closest_bvh, fallback queue (capacity n_slots)
-    double* nee_ctx; uint32_t* nee_meta; NeeTermQueue tq;
-    uint32_t *pk_slot[2], *pk_li[2];   // NEE light picks, binned by the kind of the picked light: slot, light | sample << 24   // NEE: per-slot shading context [k * n_slots + slot] (17 doubles), term queue
+    double* nee_ctx; uint32_t* nee_meta; NeeTermQueue tq;   // NEE: per-slot shading context [k * n_slots + slot] (17 doubles), term queue
     uint32_t *oq_i, *oq_obj, *oq_fb; uint8_t* occ_record;   // occlusion-BVH pipeline: confirm queue, fallback queue; verdicts (LUMO_OCCLUDE_CHECK only)
     IterCounters* it; RunCounters* run; QueueCounters* qc;
     // film + RR thresholds
@@ -508,11 +507,10 @@ __global__ void __launch_bounds__(128, LUMO_SCATTER_BLOCKS) k_scatter(const __gr
 // and the worst-running piece of the pipeline: 16 k SASS instructions (37 % of the stall samples waiting for instruction
 // fetch), 128 registers, and terms that end early (A below the horizon, B missing the light) thinning the warps.  Now:
 //   k_scatter<K>   (already there) also leaves the bounce's shading context — reconstructed Hit, shading normals — in HBM
-//   k_nee_pick     one thread per (path, sample): the light pick, binned by the kind of the light (sphere / everything else)
-//   k_nee_a        per pick of a bin: point on the light, the two sign tests, the light's own intersection test, its pdf
-//                  and emission                                             -> term queue      (no material code at all)
-//   k_nee_b<K>     per pick of a bin: BSDF sample of material family K, the chosen light's intersection test, its pdf
-//                  and emission                                             -> term queue      (only BxDF::sample of K)
+//   k_nee_a        one thread per (path, sample): light pick, point on the light, the two sign tests, the light's own
+//                  intersection test, its pdf and emission                  -> term queue      (no material code at all)
+//   k_nee_b<K>     one thread per (path, sample): BSDF sample of material family K, the chosen light's intersection
+//                  test, its pdf and emission                               -> term queue      (only BxDF::sample of K)
 //   k_nee_eval<K>  one thread per surviving term: BSDF pdf and value, MIS weight, contribution -> shadow queue
 // Every function is called with the arguments the single kernel passed, so the arithmetic — and the film — is unchanged.
 #define LUMO_NEE_CTX_DOUBLES 17   /* p, fp_error, ng, ns, shading normal after the normal map, u, v */
@@ -553,35 +551,19 @@ __device__ __forceinline__ bool nee_item(const Wave& W, uint32_t klass, unsigned
 #ifndef LUMO_NEE_A_BLOCKS
 #define LUMO_NEE_A_BLOCKS 4
 #endif
-// BVH::sample_light (bvh.rs:67-77) for every (path, shadow sample) of one material family, binned by the kind of the light
-// that was picked: sampling a point on a sphere (the environment light: 61 % of the picks on the street scene) and on a
-// triangle are different code, and so is what follows for the BSDF-sampled term (a sphere around the scene is always hit,
-// a lamp triangle almost never).  With the picks binned, the warps of the two kernels below each run one of the two.
-__global__ void __launch_bounds__(256) k_nee_pick(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P, uint32_t klass) {
-    const uint32_t nq = W.it->n_class[klass], cur = P.cur, ns = S.P.n_shadow_rays;
+// the light-sampled term, up to the point where the material comes in (integrator.rs:96-110)
+template <bool TEX>
+__global__ void __launch_bounds__(128, LUMO_NEE_A_BLOCKS) k_nee_a(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P, uint32_t klass) {
+    const uint32_t N = W.n_slots, nq = W.it->n_class[klass], cur = P.cur, ns = S.P.n_shadow_rays;
     const unsigned long long padded = (unsigned long long)((nq + 31u) / 32u) * 32ull * ns;
     for (unsigned long long it = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; it < padded; it += (unsigned long long)gridDim.x * blockDim.x) {
+        __syncwarp();                                 // a lane whose item ended early waits here instead of running ahead into its next one
         uint32_t slot, i;
         if (!nee_item(W, klass, it, ns, nq, slot, i)) continue;
+        DevHit ho; D3 nb; nee_ctx_load(W, slot, ho, nb);
         // draws of this bounce: 3 for the scatter sample, then 6 per shadow sample: light pick, light point (2), BSDF sample (3)
         Rng rng = rng_make(P.seed, W.pixel[slot], W.sample[slot], 0u, W.draws[cur][slot] + 3u + 6u * i);
         const uint32_t li = sample_light(S, rng_float(rng));
-        const uint32_t bin = S.objects[S.P.n_objects + li].kind == LOBJ_SPHERE ? 1u : 0u;
-        const uint32_t j = agg_inc(&W.it->n_pick[bin]);
-        W.pk_slot[bin][j] = slot; W.pk_li[bin][j] = li | (i << 24);
-    }
-}
-// the light-sampled term, up to the point where the material comes in (integrator.rs:96-110); dense over one bin of picks
-template <bool TEX>
-__global__ void __launch_bounds__(128, LUMO_NEE_A_BLOCKS) k_nee_a(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P, uint32_t klass, uint32_t bin) {
-    const uint32_t N = W.n_slots, n = W.it->n_pick[bin], cur = P.cur;
-    const uint32_t n_pad = (n + 31u) & ~31u;
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n_pad; t += gridDim.x * blockDim.x) {
-        __syncwarp();                                 // a lane whose item ended early waits here instead of running ahead into its next one
-        if (t >= n) continue;
-        const uint32_t slot = W.pk_slot[bin][t], pk = W.pk_li[bin][t], li = pk & 0xFFFFFFu, i = pk >> 24;
-        DevHit ho; D3 nb; nee_ctx_load(W, slot, ho, nb);
-        Rng rng = rng_make(P.seed, W.pixel[slot], W.sample[slot], 0u, W.draws[cur][slot] + 3u + 6u * i + 1u);   // draw 0 was the light pick
         const uint32_t lobj = S.P.n_objects + li;
         const LumoObject lo = S.objects[lobj];
         const double r0 = rng_float(rng), r1 = rng_float(rng);
@@ -604,19 +586,22 @@ __global__ void __launch_bounds__(128, LUMO_NEE_A_BLOCKS) k_nee_a(const __grid_c
         push_term(W, slot, false, ri, wi, hi.t - LUMO_EPS, p_lig, S.lights[li].pdf, le);
     }
 }
-// the BSDF-sampled term up to the same point (integrator.rs:112-134); dense over one bin of picks
+// the BSDF-sampled term up to the same point (integrator.rs:112-134)
 template <int K>
-__global__ void __launch_bounds__(128, LUMO_NEE_A_BLOCKS) k_nee_b(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P, uint32_t bin) {
-    const uint32_t N = W.n_slots, n = W.it->n_pick[bin], cur = P.cur;
-    const uint32_t n_pad = (n + 31u) & ~31u;
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n_pad; t += gridDim.x * blockDim.x) {
+__global__ void __launch_bounds__(128, LUMO_NEE_A_BLOCKS) k_nee_b(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P) {
+    const uint32_t N = W.n_slots, nq = W.it->n_class[K & 7], cur = P.cur, ns = S.P.n_shadow_rays;
+    const unsigned long long padded = (unsigned long long)((nq + 31u) / 32u) * 32ull * ns;
+    for (unsigned long long it = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; it < padded; it += (unsigned long long)gridDim.x * blockDim.x) {
         __syncwarp();
-        if (t >= n) continue;
-        const uint32_t slot = W.pk_slot[bin][t], pk = W.pk_li[bin][t], li = pk & 0xFFFFFFu, i = pk >> 24;
+        uint32_t slot, i;
+        if (!nee_item(W, K & 7, it, ns, nq, slot, i)) continue;
         DevHit ho; D3 nb; nee_ctx_load(W, slot, ho, nb);
         const Mat& m = S.materials[ho.material];
+        const uint32_t pixel = W.pixel[slot], sample = W.sample[slot], d0 = W.draws[cur][slot] + 3u + 6u * i;
+        Rng rng = rng_make(P.seed, pixel, sample, 0u, d0);
+        const uint32_t li = sample_light(S, rng_float(rng));
         const uint32_t lobj = S.P.n_objects + li;
-        Rng rng = rng_make(P.seed, W.pixel[slot], W.sample[slot], 0u, W.draws[cur][slot] + 3u + 6u * i + 3u);
+        rng = rng_make(P.seed, pixel, sample, 0u, d0 + 3u);
         const double ru = rng_float(rng), r0 = rng_float(rng), r1 = rng_float(rng);
         Lam lam; for (int k = 0; k < 4; k++) lam.l[k] = W.lam[(size_t)k * N + slot];
         const Onb uvw = onb_new(nb);
@@ -666,7 +651,7 @@ __global__ void __launch_bounds__(128, LUMO_NEE_BLOCKS) k_nee_eval(const __grid_
         push_shadow(W, slot, ri, T.tmax[ti], load_c4(W.gathered[cur], N, slot) * (c / T.pdf_light[ti]) / ns);
     }
 }
-__global__ void k_terms_reset(IterCounters* it) { it->n_terms = 0u; it->n_pick[0] = 0u; it->n_pick[1] = 0u; }
+__global__ void k_terms_reset(IterCounters* it) { it->n_terms = 0u; }
 
 // RR threshold of a tile from its 64 pilot paths, summed in index order (task.rs:42-53 applied to
 // the pilot set): var = sum f^2 - (sum f)^2 / n; delta = var <= 0 ? 1e-5 : sqrt(var / sum cost)
