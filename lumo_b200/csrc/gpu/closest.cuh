@@ -197,20 +197,20 @@ __global__ void __launch_bounds__(128, LUMO_BVH_BLOCKS) k_closest_bvh(const __gr
     if (CNT) { atomicAdd(&gc->nodes, cnt.nodes); atomicAdd(&gc->prims, cnt.prims); atomicAdd(&gc->tris, cnt.tris); atomicAdd(&gc->spheres, cnt.spheres); }
 }
 
-// the box tests of the object-BVH nodes above `obj` (bvh.rs:333-335).  When the reference reaches them its bound tt is
-// at least `tt_low` (every other object's hits are beyond it), so passing with tt = tt_low implies passing with the reference's tt.
+// The box tests of the object-BVH nodes above `obj` (bvh.rs:333-335).  When the reference reaches them its bound tt is at least
+// `tt_low` (every other object's hits are beyond it), so passing with tt = tt_low implies passing with the reference's tt.
+// Only the LEAF that lists the object has to be tested: an inner node's box is the exact min / max merge of its children's
+// (bvh.rs:282-309), and AaBoundingBox::intersect is monotone in the box — subtraction of the origin, multiplication by 1 / d and
+// min / max are all monotone under rounding, and a NaN dropped by min / max (0 * inf on a coinciding plane) only removes a
+// constraint — so every node above the leaf starts no later and ends no earlier than the leaf does.
 template <bool CNT>
 __device__ __forceinline__ bool ch_path_ok(const DevScene& S, uint32_t obj, const RayCtx& w, double tt_low, Counters* c) {
-    const uint32_t p0 = S.obj_path_off[obj], p1 = S.obj_path_off[obj + 1];
-    for (uint32_t p = p0; p < p1; p++) {
-        const LumoTlasNode* node = S.tlas + S.obj_path[p];
-        LUMO_CNT(tlas);
-        double t_start, t_end;
-        box_intersect(node->lo, node->hi, w.r.o, w.inv, t_start, t_end);
-        t_start = fmax(t_start, 0.0); t_end = fmin(t_end, tt_low);
-        if (!(t_start <= t_end)) return false;
-    }
-    return true;
+    const LumoTlasNode* node = S.tlas + S.obj_path[S.obj_path_off[obj + 1] - 1u];
+    LUMO_CNT(tlas);
+    double t_start, t_end;
+    box_intersect(node->lo, node->hi, w.r.o, w.inv, t_start, t_end);
+    t_start = fmax(t_start, 0.0); t_end = fmin(t_end, tt_low);
+    return t_start <= t_end;
 }
 __device__ __forceinline__ bool same_bits(double a, double b) { return __double_as_longlong(a) == __double_as_longlong(b); }
 

@@ -349,7 +349,7 @@ static bool validate_blob(const uint8_t* b, uint64_t len, LumoBlobHeader& H, std
         }
         const uint32_t* po = (const uint32_t*)(b + H.sec[LSEC_OBJ_PATH_OFF].offset); const uint32_t* pn = (const uint32_t*)(b + H.sec[LSEC_OBJ_PATH].offset);
         if (H.sec[LSEC_OBJ_PATH_OFF].count != n_obj + 1) { why = "object path offsets: wrong count"; return false; }
-        for (uint64_t i = 0; i < n_obj; i++) if (po[i] > po[i + 1] || po[i + 1] > H.sec[LSEC_OBJ_PATH].count) { why = "object path offsets out of range"; return false; }
+        for (uint64_t i = 0; i < n_obj; i++) if (po[i] >= po[i + 1] || po[i + 1] > H.sec[LSEC_OBJ_PATH].count) { why = "object path offsets out of range (every object sits under at least one BVH node)"; return false; }
         for (uint64_t i = 0; i < H.sec[LSEC_OBJ_PATH].count; i++) if (pn[i] >= H.sec[LSEC_TLAS_NODES].count) { why = "object path node out of range"; return false; }
     }
     for (uint64_t i = 0; i < H.sec[LSEC_MATERIALS].count; i++) {

@@ -181,9 +181,8 @@ __device__ __forceinline__ double ah_prim_test(const DevScene& S, uint32_t prim,
 template <bool CNT>
 __device__ __forceinline__ bool ah_confirm(const DevScene& S, uint32_t obj, const Ray& ray, double t_max, Counters* c) {
     RayCtx w; make_ctx(ray, w);
-    const uint32_t p0 = S.obj_path_off[obj], p1 = S.obj_path_off[obj + 1];
-    for (uint32_t p = p0; p < p1; p++) {
-        const LumoTlasNode* node = S.tlas + S.obj_path[p];
+    {   // the leaf that lists the object; the nodes above it pass whenever it does (closest.cuh: ch_path_ok gives the argument)
+        const LumoTlasNode* node = S.tlas + S.obj_path[S.obj_path_off[obj + 1] - 1u];
         LUMO_CNT(tlas);
         double t_start, t_end;
         box_intersect(node->lo, node->hi, w.r.o, w.inv, t_start, t_end);

@@ -10,4 +10,7 @@ ctx = native.GpuContext(0)
 sc = native.GpuScene(ctx, blob)
 _, _, cnt, _, ms = sc.render(integrator=integrator, spp=spp, seed=3, rr_delta=float(os.environ.get("PROF_RR_DELTA", "0")))
 print(name, spp, "spp:", ms, "ms", cnt, ctx.kernel_times())
+if os.environ.get("PROF_ITERLOG"):
+    import json
+    json.dump({"workload": name, "spp": spp, "iterations": ctx.iter_log(), "counters": cnt}, open(os.environ["PROF_ITERLOG"], "w"))
 sc.close(); ctx.close()
