@@ -403,7 +403,7 @@ def measure(name, args, env, steps, warmup, full):
     fp = env.get("fp64")
     if fp and "roofline" in line: line["roofline"]["fp64_peak"] = fp
 
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:
         try:
             line["cpu_baseline"] = cpu_measure(prog, integrator, spp, args.cpu_seconds if full else min(args.cpu_seconds, 6.0))
             line["vs_cpu"] = {"mrays_ratio_e2e": e2e["value"] / line["cpu_baseline"]["value"], "msamples_ratio": line["msamples_per_s"] / line["cpu_baseline"]["msamples_per_s"],
@@ -412,7 +412,7 @@ def measure(name, args, env, steps, warmup, full):
         except Exception as e:
             line["cpu_baseline"] = {"error": str(e)}
 
-    if full:
+    if full and world == 1:
         try: line["micro"] = micro_trace(scene, dev, torch, np)
         except Exception as e: line["micro"] = {"error": str(e)}
         # film finalisation kernel (Film::rgb_image on the device): 56 B read + 3 B written per pixel, HBM bound; L2 flushed before each launch
@@ -473,8 +473,14 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     ctx = native.GpuContext(local)
+    # Everything — the library's kernels, torch's copies and the NCCL reduce — is ordered on ONE non-default stream.  (The default
+    # stream's handle is NULL, which lumo_gpu_ctx_set_stream reads as "use the context's own stream": the next render's memset of
+    # the film would then race with the NCCL reduce / the copy of the previous step that torch ordered on its default stream.)
+    side = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(side)
+    assert side.cuda_stream != 0
     env = {"torch": torch, "np": np, "native": native, "dist": dist, "world": world, "rank": rank, "local": local, "dev": dev, "ctx": ctx,
-           "stream": torch.cuda.current_stream(), "flush": torch.empty(256 << 20, dtype=torch.uint8, device=dev)}
+           "stream": side, "flush": torch.empty(256 << 20, dtype=torch.uint8, device=dev)}
     if rank == 0:
         try: env["fp64"] = ctx.fp64_peak()
         except Exception as e: env["fp64"] = {"error": str(e)}

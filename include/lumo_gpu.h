@@ -79,7 +79,8 @@ typedef struct lumo_film_accum {
 int32_t lumo_gpu_device_count(int32_t* n);
 int32_t lumo_gpu_ctx_create(int32_t device, lumo_ctx** ctx);
 int32_t lumo_gpu_ctx_destroy(lumo_ctx* ctx);
-/* Run this context's later calls on the caller's CUDA stream (a cudaStream_t); NULL = the context's own. */
+/* Run this context's later calls on the caller's CUDA stream (a cudaStream_t); NULL = the context's own, which is
+   non-blocking, i.e. NOT ordered against the legacy default stream — a caller working on stream 0 passes cudaStreamLegacy. */
 int32_t lumo_gpu_ctx_set_stream(lumo_ctx* ctx, void* cuda_stream);
 
 /* Upload a scene blob (built once on the host from lumo's own kd-tree / BVH build; layout in

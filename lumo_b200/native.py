@@ -199,6 +199,9 @@ class GpuContext:
             gpu_lib().lumo_gpu_ctx_destroy(self.h); self.h = None
 
     def set_stream(self, cuda_stream_ptr):
+        """Order the context's work on the caller's stream.  A NULL handle — which is what torch's DEFAULT stream reports as
+        `.cuda_stream` — selects the context's own non-blocking stream, which is NOT ordered against the default stream: a caller
+        that also touches the film with torch ops or NCCL must run on a side stream and pass that (bench.py does)."""
         _check(gpu_lib().lumo_gpu_ctx_set_stream(self.h, C.c_void_p(cuda_stream_ptr)), "lumo_gpu_ctx_set_stream")
 
     def count_visits(self, enable):
