@@ -577,7 +577,7 @@ static void carve_wave(Wave& W, Carver& c, uint32_t N, uint32_t shadow_cap, uint
     W.stmax = c.take<double>(C); W.sc = c.take<double>(4 * C); W.sslot = c.take<uint32_t>(C);
     W.oq_i = c.take<uint32_t>(C); W.oq_obj = c.take<uint32_t>(C); W.oq_fb = c.take<uint32_t>(C); W.occ_record = c.take<uint8_t>(C);
     W.ch_t1 = c.take<double>(N); W.ch_tl = c.take<double>(N); W.ch_o1 = c.take<uint32_t>(N); W.ch_ol = c.take<uint32_t>(N); W.ch_flags = c.take<uint32_t>(N); W.ch_fb = c.take<uint32_t>(N);
-    W.nee_ctx = c.take<double>((size_t)LUMO_NEE_CTX_DOUBLES * N); W.nee_meta = c.take<uint32_t>(N);
+    W.nee_ctx = c.take<double>((size_t)LUMO_NEE_CTX_DOUBLES * N); W.nee_meta = c.take<uint32_t>(N); W.neeq = c.take<uint32_t>(N);
     { NeeTermQueue& T = W.tq; T.ox = c.take<double>(C); T.oy = c.take<double>(C); T.oz = c.take<double>(C); T.dx = c.take<double>(C); T.dy = c.take<double>(C); T.dz = c.take<double>(C);
       T.wx = c.take<double>(C); T.wy = c.take<double>(C); T.wz = c.take<double>(C); T.tmax = c.take<double>(C); T.p_lig = c.take<double>(C); T.pdf_light = c.take<double>(C);
       T.le = c.take<double>(4 * C); T.slot = c.take<uint32_t>(C); }

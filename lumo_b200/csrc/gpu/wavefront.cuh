@@ -36,7 +36,7 @@ struct IterCounters {   // zeroed before every iteration
     uint32_t n_shadow, trace_next, occl_next, n_active;
     uint32_t n_class[LUMO_N_CLASSES], pad[3];
     uint32_t occl[8];   // OcclQueues::counters of the occlusion-BVH kernels (occlude.cuh)
-    uint32_t n_terms, pad2[3];   // NEE term queue
+    uint32_t n_terms, n_nee, pad2[2];   // NEE term queue; bounces of the current material family that run NEE (Wave::neeq)
     uint32_t closest[4];         // ClosestScratch::counters of the closest-hit pipeline (closest.cuh)
 };
 // Counters that live across iterations (double-buffered by the parity of the iteration): done[p] = slots whose
@@ -74,6 +74,7 @@ struct Wave {
     double *sox, *soy, *soz, *sdx, *sdy, *sdz, *stmax, *sc; uint32_t* sslot;
     double *ch_t1, *ch_tl; uint32_t *ch_o1, *ch_ol, *ch_flags, *ch_fb;   // closest-hit pipeline: per-ray scratch of k_closest_bvh, fallback queue (capacity n_slots)
     double* nee_ctx; uint32_t* nee_meta; NeeTermQueue tq;   // NEE: per-slot shading context [k * n_slots + slot] (17 doubles), term queue
+    uint32_t* neeq;                                          // slots of the current material family whose bounce runs NEE (dense; written by k_scatter)
     uint32_t *oq_i, *oq_obj, *oq_fb; uint8_t* occ_record;   // occlusion-BVH pipeline: confirm queue, fallback queue; verdicts (LUMO_OCCLUDE_CHECK only)
     IterCounters* it; RunCounters* run; QueueCounters* qc;
     // film + RR thresholds
@@ -496,6 +497,7 @@ __global__ void __launch_bounds__(128, LUMO_SCATTER_BLOCKS) k_scatter(const __gr
         }
         if ((K & 7) == LMAT_MFDIELECTRIC) for (int k = 1; k < 4; k++) W.lam[(size_t)k * N + slot] = lam.l[k];
         W.flags[slot] = (done ? PF_DONE : f) | (nee ? PF_NEE : 0u);
+        if (nee) W.neeq[agg_inc(&W.it->n_nee)] = slot;
         if (done) W.done[cur][agg_inc(&W.qc->n_done[cur])] = slot;
         else agg_inc(&W.qc->n_active[nxt]);
     }
@@ -538,63 +540,105 @@ __device__ __forceinline__ void push_term(const Wave& W, uint32_t slot, bool ter
     T.tmax[i] = t_max; T.p_lig[i] = p_lig; T.pdf_light[i] = pdf_light; T.slot[i] = slot | (term_b ? 0x80000000u : 0u);
     for (int k = 0; k < 4; k++) T.le[(size_t)k * W.shadow_cap + i] = le.s[k];
 }
-// (path, shadow sample) of a thread: 32 consecutive queue entries of class `klass` share a warp and a sample index
-__device__ __forceinline__ bool nee_item(const Wave& W, uint32_t klass, unsigned long long it, uint32_t ns, uint32_t nq, uint32_t& slot, uint32_t& i) {
+// (path, shadow sample) of a thread: 32 consecutive entries of the family's NEE queue share a warp and a sample index
+__device__ __forceinline__ bool nee_item(const Wave& W, unsigned long long it, uint32_t ns, uint32_t nq, uint32_t& slot, uint32_t& i) {
     const unsigned long long grp = it / (32ull * ns);
     i = (uint32_t)((it / 32ull) % ns);
     const uint32_t qi = (uint32_t)(grp * 32ull + (it % 32ull));
     if (qi >= nq) return false;
-    slot = W.cls[klass][qi];
-    return (W.flags[slot] & PF_NEE) != 0u;
+    slot = W.neeq[qi];
+    return true;
 }
 // (same-box A/B, bistro 4 spp, shade class ms: 4 CTAs per SM 245.6, 5: 250.6, 6: 265.9)
 #ifndef LUMO_NEE_A_BLOCKS
 #define LUMO_NEE_A_BLOCKS 4
 #endif
-// the light-sampled term, up to the point where the material comes in (integrator.rs:96-110)
+// the light-sampled term, up to the point where the material comes in (integrator.rs:96-110).
+// Half of the light-sampled directions fail the two sign tests; the survivors of a warp are collected in shared memory and
+// the expensive second half (the light's own intersection test, its pdf and emission) runs on 32 of them at a time.
+#ifndef LUMO_NEE_A_COMPACT
+#define LUMO_NEE_A_COMPACT 1
+#endif
+struct NeeASurvivor { uint32_t slot, li; double wx, wy, wz; };
+template <bool TEX>
+__device__ __forceinline__ void nee_a_finish(const DevScene& S, const Wave& W, uint32_t slot, uint32_t li, D3 wi) {
+    const uint32_t N = W.n_slots, lobj = S.P.n_objects + li;
+    DevHit ho; D3 nb; nee_ctx_load(W, slot, ho, nb);
+    const Ray ri = hit_generate_ray(ho, wi);
+    DevHit hi;
+    if (!light_hit<TEX>(S, lobj, ri, hi)) return;
+    const double p_lig = light_sample_towards_pdf(S, S.objects[lobj], ri, hi.p, hi.ng);
+    Lam lam; for (int k = 0; k < 4; k++) lam.l[k] = W.lam[(size_t)k * N + slot];   // already terminated by k_scatter if dispersive
+    const C4 le = mat_emit<TEX ? -1 : LUMO_K_SOLID>(S, S.materials[hi.material], lam, hi);
+    push_term(W, slot, false, ri, wi, hi.t - LUMO_EPS, p_lig, S.lights[li].pdf, le);
+}
 template <bool TEX>
 __global__ void __launch_bounds__(128, LUMO_NEE_A_BLOCKS) k_nee_a(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P, uint32_t klass) {
-    const uint32_t N = W.n_slots, nq = W.it->n_class[klass], cur = P.cur, ns = S.P.n_shadow_rays;
+    const uint32_t nq = W.it->n_nee, cur = P.cur, ns = S.P.n_shadow_rays;
     const unsigned long long padded = (unsigned long long)((nq + 31u) / 32u) * 32ull * ns;
+#if LUMO_NEE_A_COMPACT
+    __shared__ NeeASurvivor s_buf[4][64];
+    NeeASurvivor* buf = s_buf[threadIdx.x >> 5];
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t held = 0;                               // survivors waiting in this warp's buffer (warp-uniform, < 32 between rounds)
+#endif
+    // every lane of a warp makes the same number of trips (padded is a multiple of 32)
     for (unsigned long long it = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; it < padded; it += (unsigned long long)gridDim.x * blockDim.x) {
         __syncwarp();                                 // a lane whose item ended early waits here instead of running ahead into its next one
-        uint32_t slot, i;
-        if (!nee_item(W, klass, it, ns, nq, slot, i)) continue;
-        DevHit ho; D3 nb; nee_ctx_load(W, slot, ho, nb);
-        // draws of this bounce: 3 for the scatter sample, then 6 per shadow sample: light pick, light point (2), BSDF sample (3)
-        Rng rng = rng_make(P.seed, W.pixel[slot], W.sample[slot], 0u, W.draws[cur][slot] + 3u + 6u * i);
-        const uint32_t li = sample_light(S, rng_float(rng));
-        const uint32_t lobj = S.P.n_objects + li;
-        const LumoObject lo = S.objects[lobj];
-        const double r0 = rng_float(rng), r1 = rng_float(rng);
-        const D3 wi = light_sample_towards(S, lo, ho.p, r0, r1);
-        // mis_sample returns black when either pdf is zero (integrator.rs:150-152) whatever the light test says.  For the
-        // reflection-only BxDFs the pdf starts with two sign tests (bsdf.rs:88-90, bxdf.rs:136-139, scatter.rs:14-17):
-        // a light-sampled direction below the surface stops here, before any light or microfacet arithmetic.
-        if (klass != LMAT_MFDIELECTRIC) {
-            const D3 wo = d3(-W.dx[cur][slot], -W.dy[cur][slot], -W.dz[cur][slot]);
-            if (!is_reflection(wo, wi, ho.ng)) continue;
-            const Onb uvw = onb_new(nb);
-            if (!same_hemisphere(to_local(uvw, wo), to_local(uvw, wi))) continue;
+        uint32_t slot = 0, i, li = 0;
+        D3 wi = d3(0, 0, 0);
+        bool alive = nee_item(W, it, ns, nq, slot, i);
+        if (alive) {
+            const D3 xo = d3(W.nee_ctx[slot], W.nee_ctx[(size_t)W.n_slots + slot], W.nee_ctx[2 * (size_t)W.n_slots + slot]);
+            // draws of this bounce: 3 for the scatter sample, then 6 per shadow sample: light pick, light point (2), BSDF sample (3)
+            Rng rng = rng_make(P.seed, W.pixel[slot], W.sample[slot], 0u, W.draws[cur][slot] + 3u + 6u * i);
+            li = sample_light(S, rng_float(rng));
+            const LumoObject lo = S.objects[S.P.n_objects + li];
+            const double r0 = rng_float(rng), r1 = rng_float(rng);
+            wi = light_sample_towards(S, lo, xo, r0, r1);
+            // mis_sample returns black when either pdf is zero (integrator.rs:150-152) whatever the light test says.  For the
+            // reflection-only BxDFs the pdf starts with two sign tests (bsdf.rs:88-90, bxdf.rs:136-139, scatter.rs:14-17):
+            // a light-sampled direction below the surface stops here, before any light or microfacet arithmetic.
+            if (klass != LMAT_MFDIELECTRIC) {
+                const size_t N = W.n_slots; const double* c = W.nee_ctx + slot;
+                const D3 ng = d3(c[6 * N], c[7 * N], c[8 * N]), nb = d3(c[12 * N], c[13 * N], c[14 * N]);
+                const D3 wo = d3(-W.dx[cur][slot], -W.dy[cur][slot], -W.dz[cur][slot]);
+                if (!is_reflection(wo, wi, ng)) alive = false;
+                else {
+                    const Onb uvw = onb_new(nb);
+                    if (!same_hemisphere(to_local(uvw, wo), to_local(uvw, wi))) alive = false;
+                }
+            }
         }
-        const Ray ri = hit_generate_ray(ho, wi);
-        DevHit hi;
-        if (!light_hit<TEX>(S, lobj, ri, hi)) continue;
-        const double p_lig = light_sample_towards_pdf(S, lo, ri, hi.p, hi.ng);
-        Lam lam; for (int k = 0; k < 4; k++) lam.l[k] = W.lam[(size_t)k * N + slot];   // already terminated by k_scatter if dispersive
-        const C4 le = mat_emit<TEX ? -1 : LUMO_K_SOLID>(S, S.materials[hi.material], lam, hi);
-        push_term(W, slot, false, ri, wi, hi.t - LUMO_EPS, p_lig, S.lights[li].pdf, le);
+#if LUMO_NEE_A_COMPACT
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, alive);
+        if (alive) { NeeASurvivor& e = buf[held + __popc(m & ((1u << lane) - 1u))]; e.slot = slot; e.li = li; e.wx = wi.x; e.wy = wi.y; e.wz = wi.z; }
+        held += __popc(m);
+        __syncwarp();
+        if (held >= 32u) {
+            held -= 32u;
+            const NeeASurvivor e = buf[held + lane];
+            __syncwarp();
+            nee_a_finish<TEX>(S, W, e.slot, e.li, d3(e.wx, e.wy, e.wz));
+        }
+#else
+        if (alive) nee_a_finish<TEX>(S, W, slot, li, wi);
+#endif
     }
+#if LUMO_NEE_A_COMPACT
+    __syncwarp();
+    if (lane < held) { const NeeASurvivor e = buf[lane]; nee_a_finish<TEX>(S, W, e.slot, e.li, d3(e.wx, e.wy, e.wz)); }
+#endif
 }
 // the BSDF-sampled term up to the same point (integrator.rs:112-134)
 template <int K>
 __global__ void __launch_bounds__(128, LUMO_NEE_A_BLOCKS) k_nee_b(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P) {
-    const uint32_t N = W.n_slots, nq = W.it->n_class[K & 7], cur = P.cur, ns = S.P.n_shadow_rays;
+    const uint32_t N = W.n_slots, nq = W.it->n_nee, cur = P.cur, ns = S.P.n_shadow_rays;
     const unsigned long long padded = (unsigned long long)((nq + 31u) / 32u) * 32ull * ns;
     for (unsigned long long it = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; it < padded; it += (unsigned long long)gridDim.x * blockDim.x) {
         __syncwarp();
         uint32_t slot, i;
-        if (!nee_item(W, K & 7, it, ns, nq, slot, i)) continue;
+        if (!nee_item(W, it, ns, nq, slot, i)) continue;
         DevHit ho; D3 nb; nee_ctx_load(W, slot, ho, nb);
         const Mat& m = S.materials[ho.material];
         const uint32_t pixel = W.pixel[slot], sample = W.sample[slot], d0 = W.draws[cur][slot] + 3u + 6u * i;
@@ -651,7 +695,7 @@ __global__ void __launch_bounds__(128, LUMO_NEE_BLOCKS) k_nee_eval(const __grid_
         push_shadow(W, slot, ri, T.tmax[ti], load_c4(W.gathered[cur], N, slot) * (c / T.pdf_light[ti]) / ns);
     }
 }
-__global__ void k_terms_reset(IterCounters* it) { it->n_terms = 0u; }
+__global__ void k_terms_reset(IterCounters* it) { it->n_terms = 0u; it->n_nee = 0u; }   // after each material family
 
 // RR threshold of a tile from its 64 pilot paths, summed in index order (task.rs:42-53 applied to
 // the pilot set): var = sum f^2 - (sum f)^2 / n; delta = var <= 0 ? 1e-5 : sqrt(var / sum cost)
