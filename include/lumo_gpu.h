@@ -71,7 +71,8 @@ typedef struct lumo_film_accum {
                                 [8] BDPT subpaths cut because the device ran out of vertex storage (the reference
                                 caps a subpath at 1024 vertices, bd_path_trace.rs:7; 0 unless the overflow pool is
                                 exhausted), [9] shadow rays on which the occlusion BVH and the reference traversal
-                                disagreed (occlusion mode 2 only; must be 0) */
+                                disagreed, plus NEE light tests that passed outside the light's bounding sphere
+                                (occlusion mode 2 only; must be 0) */
     double* tile_deltas;     /* optional [ceil(W/16)*ceil(H/16)]: RR threshold used per 16x16 tile */
     double device_ms;        /* CUDA-event time of the render on the context's stream */
 } lumo_film_accum;

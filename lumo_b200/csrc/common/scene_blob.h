@@ -10,7 +10,7 @@
 #include <stdint.h>
 
 #define LUMO_BLOB_MAGIC 0x31424F4C424D554CULL /* "LUMBLOB1" */
-#define LUMO_BLOB_VERSION 5u
+#define LUMO_BLOB_VERSION 6u
 #define LUMO_NONE 0xFFFFFFFFu
 
 enum LumoSection {
@@ -122,9 +122,13 @@ struct LumoMaterial {          // 128 B
     uint32_t bump_tex;         // LUMO_NONE or the LTEX_BUMP record of the normal map
     uint64_t pad;
 };
-struct LumoLight {             // 32 B  (bvh.rs:24-25 alias_table / alias_pdf)
+struct LumoLight {             // 64 B  (bvh.rs:24-25 alias_table / alias_pdf)
     double alias_prob, pdf, area;
     uint32_t alias, pad;
+    // World-space sphere that contains the light with room to spare (centre of its bounding box, half diagonal padded by
+    // 1e-4 of itself + 1e-6 of the coordinates' magnitude): a ray whose line misses it cannot pass the light's intersection
+    // test, so the BSDF-sampled NEE term skips that test (k_nee_b).  Not part of the reference's data; never changes a result.
+    double bound_c[3], bound_r;
 };
 
 struct LumoCamera {

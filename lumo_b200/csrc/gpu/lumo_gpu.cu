@@ -857,6 +857,7 @@ static int32_t render_impl(lumo_scene* sc, const lumo_render_params* rp, double*
     P.seed = rp->seed; P.integrator = (uint32_t)rp->integrator; P.sampler = (uint32_t)rp->sampler; P.tone_map = (uint32_t)rp->tone_map; P.tone_map_arg = rp->tone_map_arg;
     P.spp_begin = rp->spp_begin; P.spp_count = spp; P.total_spp = rp->total_spp; P.tiles_x = tiles_x; P.tiles_y = tiles_y;
     { const char* e = std::getenv("LUMO_DEBUG_PIXEL"); P.debug_pixel = e ? (uint32_t)std::atoll(e) : LUMO_NONE; }
+    P.check = ctx->occl_check ? 1u : 0u;
     uint64_t iterations = 0;
     const bool bdpt = rp->integrator == LUMO_BD_PATH_TRACE;
     BdptStorage bs;
@@ -889,7 +890,7 @@ static int32_t render_impl(lumo_scene* sc, const lumo_render_params* rp, double*
         counters[4] = ctx->launches - launches0; counters[5] = hc->run.max_depth; counters[6] = iterations; counters[7] = hc->run.nonfinite;
         counters[8] = bdpt ? hc->run.shadow_dropped : 0ull;   // BDPT: subpaths cut for lack of vertex storage
         counters[9] = 0;
-        if (ctx->occl_check) { AhCounters ac; CU(cudaMemcpy(&ac, ctx->d_ah, sizeof ac, cudaMemcpyDeviceToHost)); counters[9] = ac.mismatches; }
+        if (ctx->occl_check) { AhCounters ac; CU(cudaMemcpy(&ac, ctx->d_ah, sizeof ac, cudaMemcpyDeviceToHost)); counters[9] = ac.mismatches + hc->run.prereject_bad; }
     }
     return LUMO_OK;
 }

@@ -47,7 +47,7 @@ struct IterCounters {   // zeroed before every iteration
 struct QueueCounters { uint32_t n_active[2], n_done[2]; };
 struct RunCounters {    // zeroed once per render
     unsigned long long next_work, camera_paths, closest, occlusion, cost, shadow_queued, shadow_dropped, nonfinite;
-    uint32_t max_depth, pad;
+    uint32_t max_depth, prereject_bad;   // prereject_bad: WaveParams::check only — BSDF-sampled NEE terms whose light test passed although the light's bounding sphere said it could not
 };
 
 // Path state, structure of arrays.  Ray, throughput and RNG position are double-buffered: the scatter
@@ -88,6 +88,7 @@ struct WaveParams {
     double tone_map_arg;
     uint32_t spp_begin, spp_count, total_spp, pilot_round;
     uint32_t tiles_x, tiles_y, debug_pixel, cur;   // debug_pixel: LUMO_DEBUG_PIXEL env (printf trace of one pixel's paths), LUMO_NONE = off
+    uint32_t check, pad[3];                        // check: the context's cross-check mode (lumo_gpu_ctx_occlusion_mode 2) — shortcuts are verified and disagreements counted
 };                                                  // cur: which half of the double-buffered state holds this iteration's rays
 
 __device__ __forceinline__ uint32_t agg_inc(uint32_t* ctr) {   // warp-aggregated atomicAdd(ctr, 1)
@@ -554,81 +555,45 @@ __device__ __forceinline__ bool nee_item(const Wave& W, unsigned long long it, u
 #define LUMO_NEE_A_BLOCKS 4
 #endif
 // the light-sampled term, up to the point where the material comes in (integrator.rs:96-110).
-// Half of the light-sampled directions fail the two sign tests; the survivors of a warp are collected in shared memory and
-// the expensive second half (the light's own intersection test, its pdf and emission) runs on 32 of them at a time.
-#ifndef LUMO_NEE_A_COMPACT
-#define LUMO_NEE_A_COMPACT 1
+// (Measured and dropped: collecting the survivors of the two sign tests per warp in shared memory and running the second half
+// on 32 of them at a time.  Lanes per instruction went from 12 to 19 and the shade class from 209.0 to 217.6 ms on bistro
+// 4 spp — the kernel waits on instruction fetch (39 % of its stall samples) and f64 latency, not on issue slots.)
+#ifndef LUMO_NEE_B_PREREJECT
+#define LUMO_NEE_B_PREREJECT 1
 #endif
-struct NeeASurvivor { uint32_t slot, li; double wx, wy, wz; };
-template <bool TEX>
-__device__ __forceinline__ void nee_a_finish(const DevScene& S, const Wave& W, uint32_t slot, uint32_t li, D3 wi) {
-    const uint32_t N = W.n_slots, lobj = S.P.n_objects + li;
-    DevHit ho; D3 nb; nee_ctx_load(W, slot, ho, nb);
-    const Ray ri = hit_generate_ray(ho, wi);
-    DevHit hi;
-    if (!light_hit<TEX>(S, lobj, ri, hi)) return;
-    const double p_lig = light_sample_towards_pdf(S, S.objects[lobj], ri, hi.p, hi.ng);
-    Lam lam; for (int k = 0; k < 4; k++) lam.l[k] = W.lam[(size_t)k * N + slot];   // already terminated by k_scatter if dispersive
-    const C4 le = mat_emit<TEX ? -1 : LUMO_K_SOLID>(S, S.materials[hi.material], lam, hi);
-    push_term(W, slot, false, ri, wi, hi.t - LUMO_EPS, p_lig, S.lights[li].pdf, le);
-}
 template <bool TEX>
 __global__ void __launch_bounds__(128, LUMO_NEE_A_BLOCKS) k_nee_a(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P, uint32_t klass) {
-    const uint32_t nq = W.it->n_nee, cur = P.cur, ns = S.P.n_shadow_rays;
+    const uint32_t N = W.n_slots, nq = W.it->n_nee, cur = P.cur, ns = S.P.n_shadow_rays;
     const unsigned long long padded = (unsigned long long)((nq + 31u) / 32u) * 32ull * ns;
-#if LUMO_NEE_A_COMPACT
-    __shared__ NeeASurvivor s_buf[4][64];
-    NeeASurvivor* buf = s_buf[threadIdx.x >> 5];
-    const uint32_t lane = threadIdx.x & 31u;
-    uint32_t held = 0;                               // survivors waiting in this warp's buffer (warp-uniform, < 32 between rounds)
-#endif
-    // every lane of a warp makes the same number of trips (padded is a multiple of 32)
     for (unsigned long long it = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; it < padded; it += (unsigned long long)gridDim.x * blockDim.x) {
         __syncwarp();                                 // a lane whose item ended early waits here instead of running ahead into its next one
-        uint32_t slot = 0, i, li = 0;
-        D3 wi = d3(0, 0, 0);
-        bool alive = nee_item(W, it, ns, nq, slot, i);
-        if (alive) {
-            const D3 xo = d3(W.nee_ctx[slot], W.nee_ctx[(size_t)W.n_slots + slot], W.nee_ctx[2 * (size_t)W.n_slots + slot]);
-            // draws of this bounce: 3 for the scatter sample, then 6 per shadow sample: light pick, light point (2), BSDF sample (3)
-            Rng rng = rng_make(P.seed, W.pixel[slot], W.sample[slot], 0u, W.draws[cur][slot] + 3u + 6u * i);
-            li = sample_light(S, rng_float(rng));
-            const LumoObject lo = S.objects[S.P.n_objects + li];
-            const double r0 = rng_float(rng), r1 = rng_float(rng);
-            wi = light_sample_towards(S, lo, xo, r0, r1);
-            // mis_sample returns black when either pdf is zero (integrator.rs:150-152) whatever the light test says.  For the
-            // reflection-only BxDFs the pdf starts with two sign tests (bsdf.rs:88-90, bxdf.rs:136-139, scatter.rs:14-17):
-            // a light-sampled direction below the surface stops here, before any light or microfacet arithmetic.
-            if (klass != LMAT_MFDIELECTRIC) {
-                const size_t N = W.n_slots; const double* c = W.nee_ctx + slot;
-                const D3 ng = d3(c[6 * N], c[7 * N], c[8 * N]), nb = d3(c[12 * N], c[13 * N], c[14 * N]);
-                const D3 wo = d3(-W.dx[cur][slot], -W.dy[cur][slot], -W.dz[cur][slot]);
-                if (!is_reflection(wo, wi, ng)) alive = false;
-                else {
-                    const Onb uvw = onb_new(nb);
-                    if (!same_hemisphere(to_local(uvw, wo), to_local(uvw, wi))) alive = false;
-                }
-            }
+        uint32_t slot, i;
+        if (!nee_item(W, it, ns, nq, slot, i)) continue;
+        DevHit ho; D3 nb; nee_ctx_load(W, slot, ho, nb);
+        // draws of this bounce: 3 for the scatter sample, then 6 per shadow sample: light pick, light point (2), BSDF sample (3)
+        Rng rng = rng_make(P.seed, W.pixel[slot], W.sample[slot], 0u, W.draws[cur][slot] + 3u + 6u * i);
+        const uint32_t li = sample_light(S, rng_float(rng));
+        const uint32_t lobj = S.P.n_objects + li;
+        const LumoObject lo = S.objects[lobj];
+        const double r0 = rng_float(rng), r1 = rng_float(rng);
+        const D3 wi = light_sample_towards(S, lo, ho.p, r0, r1);
+        // mis_sample returns black when either pdf is zero (integrator.rs:150-152) whatever the light test says.  For the
+        // reflection-only BxDFs the pdf starts with two sign tests (bsdf.rs:88-90, bxdf.rs:136-139, scatter.rs:14-17):
+        // a light-sampled direction below the surface stops here, before any light or microfacet arithmetic.
+        if (klass != LMAT_MFDIELECTRIC) {
+            const D3 wo = d3(-W.dx[cur][slot], -W.dy[cur][slot], -W.dz[cur][slot]);
+            if (!is_reflection(wo, wi, ho.ng)) continue;
+            const Onb uvw = onb_new(nb);
+            if (!same_hemisphere(to_local(uvw, wo), to_local(uvw, wi))) continue;
         }
-#if LUMO_NEE_A_COMPACT
-        const uint32_t m = __ballot_sync(0xFFFFFFFFu, alive);
-        if (alive) { NeeASurvivor& e = buf[held + __popc(m & ((1u << lane) - 1u))]; e.slot = slot; e.li = li; e.wx = wi.x; e.wy = wi.y; e.wz = wi.z; }
-        held += __popc(m);
-        __syncwarp();
-        if (held >= 32u) {
-            held -= 32u;
-            const NeeASurvivor e = buf[held + lane];
-            __syncwarp();
-            nee_a_finish<TEX>(S, W, e.slot, e.li, d3(e.wx, e.wy, e.wz));
-        }
-#else
-        if (alive) nee_a_finish<TEX>(S, W, slot, li, wi);
-#endif
+        const Ray ri = hit_generate_ray(ho, wi);
+        DevHit hi;
+        if (!light_hit<TEX>(S, lobj, ri, hi)) continue;
+        const double p_lig = light_sample_towards_pdf(S, lo, ri, hi.p, hi.ng);
+        Lam lam; for (int k = 0; k < 4; k++) lam.l[k] = W.lam[(size_t)k * N + slot];   // already terminated by k_scatter if dispersive
+        const C4 le = mat_emit<TEX ? -1 : LUMO_K_SOLID>(S, S.materials[hi.material], lam, hi);
+        push_term(W, slot, false, ri, wi, hi.t - LUMO_EPS, p_lig, S.lights[li].pdf, le);
     }
-#if LUMO_NEE_A_COMPACT
-    __syncwarp();
-    if (lane < held) { const NeeASurvivor e = buf[lane]; nee_a_finish<TEX>(S, W, e.slot, e.li, d3(e.wx, e.wy, e.wz)); }
-#endif
 }
 // the BSDF-sampled term up to the same point (integrator.rs:112-134)
 template <int K>
@@ -654,11 +619,26 @@ __global__ void __launch_bounds__(128, LUMO_NEE_A_BLOCKS) k_nee_b(const __grid_c
         Lam l2 = lam;
         if (!bsdf_sample<K>(S, m, uvw, wo, ho, l2, ru, r0, r1, wi)) continue;
         const Ray ri = hit_generate_ray(ho, wi);
+        const LumoLight L = S.lights[li];
+#if LUMO_NEE_B_PREREJECT
+        // The BSDF-sampled direction nearly never points at the ONE light this shadow sample picked (1 of 4097 on the street):
+        // a line that stays outside the light's padded bounding sphere cannot pass its intersection test (scene_blob.h LumoLight).
+        bool far_off;
+        {
+            const D3 v = d3(L.bound_c[0], L.bound_c[1], L.bound_c[2]) - ri.o;
+            const double vv = dot(v, v), dd = dot(ri.d, ri.d), b = dot(v, ri.d);
+            far_off = vv * dd - b * b > (L.bound_r * L.bound_r + 1e-12 * vv) * dd;
+        }
+        if (far_off && !P.check) continue;
+#else
+        const bool far_off = false;
+#endif
         DevHit hi;
         if (!light_hit<LUMO_TEX(K)>(S, lobj, ri, hi)) continue;
+        if (far_off) atomicAdd(&W.run->prereject_bad, 1u);                            // check mode only: must never happen
         const double p_lig = light_sample_towards_pdf(S, S.objects[lobj], ri, hi.p, hi.ng);
         const C4 le = mat_emit<K>(S, S.materials[hi.material], lam, hi);
-        push_term(W, slot, true, ri, wi, hi.t - LUMO_EPS, p_lig, S.lights[li].pdf, le);
+        push_term(W, slot, true, ri, wi, hi.t - LUMO_EPS, p_lig, L.pdf, le);
     }
 }
 // BSDF pdf and value, MIS weight (integrator.rs:139-184), contribution -> shadow queue.  Dense over the term queue.

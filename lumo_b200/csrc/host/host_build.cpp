@@ -736,7 +736,17 @@ static bool run(const uint8_t* data, uint64_t len, std::vector<uint8_t>& out) {
         }
         while (is > 0) { is--; prob[small[is]] = 1.0; }
         while (il > 0) { il--; prob[large[il]] = 1.0; }
-        for (size_t i = 0; i < n; i++) { LumoLight L = {prob[i], ap[i], B.light_area[i], alias[i], 0}; B.lights.push_back(L); }
+        for (size_t i = 0; i < n; i++) {
+            LumoLight L; std::memset(&L, 0, sizeof L);
+            L.alias_prob = prob[i]; L.pdf = ap[i]; L.area = B.light_area[i]; L.alias = alias[i];
+            const Box& b = B.light_boxes[i];
+            const V3 c = center(b);
+            const double half = length(sub(b.hi, c));
+            const double mag = std::fmax(std::fmax(std::fabs(c.x), std::fabs(c.y)), std::fabs(c.z)) + half;
+            L.bound_c[0] = c.x; L.bound_c[1] = c.y; L.bound_c[2] = c.z;
+            L.bound_r = half * (1.0 + 1e-4) + 1e-6 * mag + 1e-12;
+            B.lights.push_back(L);
+        }
     }
 
     LumoSceneParams& P = B.params;

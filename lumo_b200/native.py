@@ -31,7 +31,7 @@ TEXTURE = np.dtype([("kind", "<u4"), ("a", "<u4"), ("b", "<u4"), ("width", "<u4"
 AH_NODE = np.dtype([("lo_x", "<f4", 4), ("lo_y", "<f4", 4), ("lo_z", "<f4", 4), ("hi_x", "<f4", 4), ("hi_y", "<f4", 4), ("hi_z", "<f4", 4),
                     ("child", "<u4", 4), ("pad", "<u4", 4)])
 AH_PRIM = np.dtype([("tri", "<u4"), ("obj", "<u4")])
-LIGHT = np.dtype([("alias_prob", "<f8"), ("pdf", "<f8"), ("area", "<f8"), ("alias", "<u4"), ("pad", "<u4")])
+LIGHT = np.dtype([("alias_prob", "<f8"), ("pdf", "<f8"), ("area", "<f8"), ("alias", "<u4"), ("pad", "<u4"), ("bound_c", "<f8", 3), ("bound_r", "<f8")])
 CAMERA = np.dtype([("screen_to_raster_m", "<f8", 16), ("screen_to_raster_inv", "<f8", 16), ("camera_to_screen_m", "<f8", 16),
                    ("camera_to_screen_inv", "<f8", 16), ("world_to_camera_m", "<f8", 16), ("world_to_camera_inv", "<f8", 16),
                    ("lens_radius", "<f8"), ("focal_length", "<f8"), ("image_plane_area", "<f8"), ("lens_area", "<f8"),

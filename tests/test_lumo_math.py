@@ -81,3 +81,4 @@ def test_device_bits_equal_host_bits(gpu_ctx, name):
     both_nan = np.isnan(dev) & np.isnan(host)
     same = (dev.view(np.uint64) == host.view(np.uint64)) | both_nan
     assert same.all(), (name, int((~same).sum()), x[~same][:5], dev[~same][:5], host[~same][:5])
+

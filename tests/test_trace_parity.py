@@ -172,6 +172,7 @@ def test_occlusion_bvh_counters_and_render_cross_check(gpu_ctx):
         finally:
             gpu_ctx.occlusion_mode(0)
         assert st["mismatches"] == 0, (name, st)
+        assert b[2]["occlusion_mismatches"] == 0, (name, b[2])      # also counts a light test passing outside the light's bounding sphere (k_nee_b)
         assert a[2]["occlusion"] == b[2]["occlusion"] == c[2]["occlusion"] > 0 and a[2]["closest"] == c[2]["closest"]
         assert np.allclose(a[0], c[0], rtol=1e-11, atol=1e-13) and np.allclose(a[0], b[0], rtol=1e-11, atol=1e-13), name
         gpu_ctx.count_visits(True)
