@@ -393,8 +393,13 @@ def measure(name, args, env, steps, warmup, full):
                           occl_bytes(ost, vis_occl, cntc["occlusion"]), cntc["occlusion"], "ray",
                           "60 B shadow-queue entry + 128 B per BVH node + 8 B per leaf primitive + 72 B per triangle test + 68 B per candidate + the confirming traversal's visits")
     if by["occlude"]: by["occlude"]["per_ray"] = {k: v / max(cntc["occlusion"], 1) for k, v in ost.items()}
-    by["shade"] = entry("k_terminal + k_scatter<K> + k_nee<K> (one bounce of the integrator)", "shade", bounces * (192 * 2 + 32 + 64) + 128.0 * cntc["occlusion"], bounces, "bounce",
-                        "SURVEY 8d: B_bounce = 2 x 192 B path state + 32 B hit record + 64 B material + 128 B per queued shadow ray (%.2f per bounce here)" % n_shadow_per_bounce)
+    sst = ctx.shade_stats()      # of the counting render just above
+    shade_bytes = bounces * (192 * 2 + 32 + 64) + sst["nee_bounces"] * (140 + 2 * 140) + sst["nee_terms"] * (2 * 132 + 140) + 92.0 * cntc["occlusion"]
+    by["shade"] = entry("k_terminal + k_scatter<K> + k_nee_a + k_nee_b<K> + k_nee_eval<K> (one bounce of the integrator)", "shade", shade_bytes, bounces, "bounce",
+                        "SURVEY 8d's B_bounce (2 x 192 B path state + 32 B hit record + 64 B material) + the queues of the three-stage NEE: 140 B shading context written once and read by two "
+                        "stages per NEE bounce (%.2f of the bounces), 132 B per NEE term written and read back + 140 B context per evaluated term (%.2f terms per bounce), 92 B per queued shadow ray "
+                        "(%.2f per bounce).  The class is FP64-latency and instruction-fetch bound, not HBM bound (profiles/README.md)" % (sst["nee_bounces"] / bounces, sst["nee_terms"] / bounces, n_shadow_per_bounce))
+    if by["shade"]: by["shade"]["per_bounce"] = {"nee_bounces": sst["nee_bounces"] / bounces, "nee_terms": sst["nee_terms"] / bounces, "shadow_rays": n_shadow_per_bounce, "survey_8d_bytes": 480 + 128.0 * n_shadow_per_bounce}
     by = {k: v for k, v in by.items() if v}
     dominant = max(by, key=lambda k: by[k]["ms_per_step"]) if by else None
     if dominant:

@@ -156,6 +156,9 @@ int32_t lumo_gpu_ctx_visits(lumo_ctx* ctx, uint64_t* out12);   /* 6 for the clos
  * stats has FOURTEEN entries. */
 int32_t lumo_gpu_ctx_closest_mode(lumo_ctx* ctx, int32_t mode);
 int32_t lumo_gpu_ctx_closest_stats(lumo_ctx* ctx, uint64_t* stats14);
+/* Work of the shading stage in the context's last PathTrace / DirectLight render (bench.py's byte count of the NEE queues):
+ * [0] bounces that ran next-event estimation, [1] NEE terms evaluated, [2] shadow rays queued, [3] bounces shaded. */
+int32_t lumo_gpu_ctx_shade_stats(lumo_ctx* ctx, uint64_t* stats4);
 /* Shadow rays are answered from an order-free occlusion BVH and confirmed by the reference's own per-object traversal
  * (csrc/gpu/occlude.cuh).  mode 0: that (default); 1: the reference's object BVH + kd-tree traversal for shadow rays too;
  * 2: both on every shadow ray of a render, disagreements counted in stats[7].  stats: [0] BVH nodes, [1] leaf primitives,

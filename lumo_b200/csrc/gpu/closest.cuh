@@ -273,13 +273,18 @@ __global__ void __launch_bounds__(128, LUMO_WAVE_TRACE_BLOCKS) k_closest_fallbac
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t n = Q.counters[2];
     Counters cnt = {0, 0, 0, 0, 0, 0};
+    // The queue is short (0.2 % of a launch's rays on the street scene) and every ray is a long chain of dependent loads whose
+    // lanes diverge: 32 of them in one warp run nearly one after the other.  So the rays are spread over all resident warps
+    // first — one ray per warp while there are fewer rays than warps — and the kernel's time is one ray's latency, not 32.
+    const uint32_t warps = gridDim.x * (blockDim.x >> 5);
+    const uint32_t per_warp = min(32u, max(1u, (n + warps - 1u) / warps));
     for (;;) {
         uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&Q.counters[3], 32u);
+        if (lane == 0) base = atomicAdd(&Q.counters[3], per_warp);
         base = __shfl_sync(0xFFFFFFFFu, base, 0);
         if (base >= n) break;
         const uint32_t j = base + lane;
-        if (j < n) {
+        if (lane < per_warp && j < n) {
             const uint32_t i = Q.fallback_i[j];
             Ray ray; double t_max; src.load(i, ray, t_max);
             HitRec h;

@@ -41,6 +41,7 @@ struct lumo_ctx {
     int closest_faithful = 0;      // LUMO_CLOSEST_FAITHFUL=1: Scene::hit replays the reference traversal for every ray (k_wave_trace) instead of closest.cuh
     void* occl_mem = nullptr; size_t occl_bytes = 0;   // queues of the batch occlusion entry point (lumo_gpu_trace_any)
     int occl_faithful = 0;         // LUMO_OCCLUDE_FAITHFUL=1: shadow rays replay the reference's object BVH + kd-trees (k_wave_occlude) instead of the occlusion BVH
+    uint64_t shade_stats[4] = {0, 0, 0, 0};   // of the last render: NEE bounces, NEE terms evaluated, shadow rays queued, bounces
     int occl_check = 0;            // LUMO_OCCLUDE_CHECK=1: run both on every shadow ray of a render and count disagreements (counters[9])
     uint32_t* d_iter_log = nullptr; uint32_t iter_log_n = 0;   // (closest-hit rays, shadow rays) per wave iteration of the last render's main pass
     // per-kernel-class device time of the last render (CUDA events on the launching stream)
@@ -161,6 +162,13 @@ extern "C" int32_t lumo_gpu_ctx_closest_stats(lumo_ctx* ctx, uint64_t* out6) {  
     CU(cudaStreamSynchronize(ctx->stream));
     ClosestCounters c; CU(cudaMemcpy(&c, ctx->d_ch, sizeof c, cudaMemcpyDeviceToHost));
     out6[0] = c.nodes; out6[1] = c.prims; out6[2] = c.tris; out6[3] = c.spheres; out6[4] = c.fallback; out6[5] = c.rays; for (int k = 0; k < 8; k++) out6[6 + k] = c.why[k];
+    return LUMO_OK;
+}
+// Work of the shading stage in the context's last PathTrace / DirectLight render: [0] bounces that ran next-event estimation,
+// [1] NEE terms that reached k_nee_eval (light- and BSDF-sampled), [2] shadow rays queued, [3] bounces shaded.
+extern "C" int32_t lumo_gpu_ctx_shade_stats(lumo_ctx* ctx, uint64_t* out4) {
+    if (!ctx || !out4) return fail(LUMO_ERR_INVALID, "shade_stats: null pointer");
+    for (int k = 0; k < 4; k++) out4[k] = ctx->shade_stats[k];
     return LUMO_OK;
 }
 // Counters of the occlusion-BVH kernels (occlude.cuh) since the last lumo_gpu_ctx_count_visits call: [0] BVH nodes visited,
@@ -889,6 +897,7 @@ static int32_t render_impl(lumo_scene* sc, const lumo_render_params* rp, double*
         counters[0] = hc->run.camera_paths; counters[1] = hc->run.closest; counters[2] = hc->run.occlusion; counters[3] = hc->run.cost;
         counters[4] = ctx->launches - launches0; counters[5] = hc->run.max_depth; counters[6] = iterations; counters[7] = hc->run.nonfinite;
         counters[8] = bdpt ? hc->run.shadow_dropped : 0ull;   // BDPT: subpaths cut for lack of vertex storage
+        ctx->shade_stats[0] = hc->run.nee_bounces; ctx->shade_stats[1] = hc->run.nee_terms; ctx->shade_stats[2] = hc->run.occlusion; ctx->shade_stats[3] = hc->run.closest;
         counters[9] = 0;
         if (ctx->occl_check) { AhCounters ac; CU(cudaMemcpy(&ac, ctx->d_ah, sizeof ac, cudaMemcpyDeviceToHost)); counters[9] = ac.mismatches + hc->run.prereject_bad; }
     }
@@ -946,7 +955,7 @@ __device__ __noinline__ uint32_t trc_apply(double c, int transfer) {
 //   tier 2: 1.9e-4 with powf (4 ulp)
 // of the f64 result (both curves are continuous at their knee to 1e-7, so the side of the knee does not matter).
 // A code is taken from tier 1 when the value is at least 1.5e-3 away from the neighbouring codes, else from tier 2 at
-// 5e-4; what is left (0.1 % of the values, everything below code 1, NaN, negative terms, weights or splat factors
+// 5e-4; what is left (0.1 % of the values, NaN, negative terms, weights or splat factors
 // outside the f32-safe range) takes the reference's f64 path.  tests/test_film_encode.py compares the result with the
 // f64-only kernel (LUMO_FILM_F64=1) byte for byte and walks every code boundary.
 template <bool ACCURATE>
@@ -962,6 +971,7 @@ __device__ __forceinline__ bool trc_estimate(float c, int transfer, uint32_t& co
     const float margin = ACCURATE ? 5e-4f : 1.5e-3f;
     const float fl = floorf(vf), fr = vf - fl;
     if (vf >= 1.0f && fr > margin && fr < 1.0f - margin) { code = (uint32_t)fl; return true; }
+    if (vf >= 0.0f && vf < 1.0f - margin) { code = 0u; return true; }   // dark pixels: the linear segment, absolute error below 1e-6
     return false;   // also NaN
 }
 __device__ __forceinline__ void film_pixel_rgb8(const double* __restrict__ px, const double* __restrict__ sp, size_t i, double splat_scale,

@@ -296,14 +296,17 @@ __global__ void __launch_bounds__(128, LUMO_WAVE_TRACE_BLOCKS) k_occl_confirm(co
     const uint32_t n = Q.counters[1];
     Counters cnt = {0, 0, 0, 0, 0, 0};
     unsigned long long n_conf = 0, n_fall = 0;
+    // short queues are spread over all resident warps (see k_closest_fallback): the kernel then costs one ray's latency
+    const uint32_t warps = gridDim.x * (blockDim.x >> 5);
+    const uint32_t per_warp = min(32u, max(1u, (n + warps - 1u) / warps));
     for (;;) {
         uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&Q.counters[3], 32u);
+        if (lane == 0) base = atomicAdd(&Q.counters[3], per_warp);
         base = __shfl_sync(0xFFFFFFFFu, base, 0);
         if (base >= n) break;
         const uint32_t j = base + lane;
         bool again = false; uint32_t i = 0;
-        if (j < n) {
+        if (lane < per_warp && j < n) {
             i = Q.confirm_i[j];
             Ray r; double t_max; src.load(i, r, t_max);
             if (ah_confirm<CNT>(S, Q.confirm_obj[j], r, t_max, &cnt)) { sink.verdict(i, true); n_conf++; }
@@ -328,13 +331,15 @@ __global__ void __launch_bounds__(128, LUMO_WAVE_TRACE_BLOCKS) k_occl_fallback(c
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t n = Q.counters[2];
     Counters cnt = {0, 0, 0, 0, 0, 0};
+    const uint32_t warps = gridDim.x * (blockDim.x >> 5);
+    const uint32_t per_warp = min(32u, max(1u, (n + warps - 1u) / warps));
     for (;;) {
         uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&Q.counters[4], 32u);
+        if (lane == 0) base = atomicAdd(&Q.counters[4], per_warp);
         base = __shfl_sync(0xFFFFFFFFu, base, 0);
         if (base >= n) break;
         const uint32_t j = base + lane;
-        if (j < n) {
+        if (lane < per_warp && j < n) {
             const uint32_t i = Q.fallback_i[j];
             Ray r; double t_max; src.load(i, r, t_max);
             sink.verdict(i, scene_occluded<CNT, LUMO_WAVE_KD_ROUND>(S, r, t_max, &cnt));

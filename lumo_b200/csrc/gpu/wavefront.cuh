@@ -47,6 +47,7 @@ struct IterCounters {   // zeroed before every iteration
 struct QueueCounters { uint32_t n_active[2], n_done[2]; };
 struct RunCounters {    // zeroed once per render
     unsigned long long next_work, camera_paths, closest, occlusion, cost, shadow_queued, shadow_dropped, nonfinite;
+    unsigned long long nee_bounces, nee_terms;   // bounces that ran NEE; terms that reached k_nee_eval (bench.py: designed queue traffic of the shading stage)
     uint32_t max_depth, prereject_bad;   // prereject_bad: WaveParams::check only — BSDF-sampled NEE terms whose light test passed although the light's bounding sphere said it could not
 };
 
@@ -648,6 +649,7 @@ __global__ void __launch_bounds__(128, LUMO_NEE_BLOCKS) k_nee_eval(const __grid_
     const uint32_t n = min(W.it->n_terms, C);
     const uint32_t n_pad = (n + 31u) & ~31u;
     const double ns = (double)S.P.n_shadow_rays;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && P.mode == WM_MAIN) { atomicAdd(&W.run->nee_terms, (unsigned long long)n); atomicAdd(&W.run->nee_bounces, (unsigned long long)W.it->n_nee); }
     const NeeTermQueue& T = W.tq;
     for (uint32_t ti = blockIdx.x * blockDim.x + threadIdx.x; ti < n_pad; ti += gridDim.x * blockDim.x) {
         __syncwarp();

@@ -163,6 +163,7 @@ def gpu_lib():
         L.lumo_gpu_render_multi.argtypes = [C.POINTER(vp), C.c_int32, C.POINTER(RenderParams), C.POINTER(FilmAccum)]
         L.lumo_gpu_ctx_closest_mode.argtypes = [vp, C.c_int32]; L.lumo_gpu_ctx_closest_mode.restype = C.c_int32
         L.lumo_gpu_ctx_closest_stats.argtypes = [vp, C.POINTER(C.c_uint64)]; L.lumo_gpu_ctx_closest_stats.restype = C.c_int32
+        L.lumo_gpu_ctx_shade_stats.argtypes = [vp, C.POINTER(C.c_uint64)]; L.lumo_gpu_ctx_shade_stats.restype = C.c_int32
         L.lumo_gpu_ctx_occlusion_mode.argtypes = [vp, C.c_int32]; L.lumo_gpu_ctx_occlusion_mode.restype = C.c_int32
         L.lumo_gpu_ctx_occlusion_stats.argtypes = [vp, C.POINTER(C.c_uint64)]; L.lumo_gpu_ctx_occlusion_stats.restype = C.c_int32
         L.lumo_gpu_fp64_peak.argtypes = [vp, dp, dp]; L.lumo_gpu_fp64_peak.restype = C.c_int32
@@ -217,6 +218,12 @@ class GpuContext:
     def closest_mode(self, mode):
         """0: world-space BVH + the reference traversal on the winning object, reference traversal where not provably equal (default); 1: reference traversal for every ray."""
         _check(gpu_lib().lumo_gpu_ctx_closest_mode(self.h, int(mode)), "lumo_gpu_ctx_closest_mode")
+
+    def shade_stats(self):
+        """of the last render: bounces that ran NEE, NEE terms evaluated, shadow rays queued, bounces shaded"""
+        out = (C.c_uint64 * 4)()
+        _check(gpu_lib().lumo_gpu_ctx_shade_stats(self.h, out), "lumo_gpu_ctx_shade_stats")
+        return dict(zip(("nee_bounces", "nee_terms", "shadow_queued", "bounces"), (int(v) for v in out)))
 
     def closest_stats(self):
         out = (C.c_uint64 * 14)()

@@ -75,6 +75,7 @@ extern "C" {
     pub fn lumo_gpu_ctx_visits(ctx: *mut lumo_ctx, out12: *mut u64) -> i32;
     pub fn lumo_gpu_ctx_closest_mode(ctx: *mut lumo_ctx, mode: i32) -> i32;
     pub fn lumo_gpu_ctx_closest_stats(ctx: *mut lumo_ctx, stats14: *mut u64) -> i32;
+    pub fn lumo_gpu_ctx_shade_stats(ctx: *mut lumo_ctx, stats4: *mut u64) -> i32;
     pub fn lumo_gpu_ctx_occlusion_mode(ctx: *mut lumo_ctx, mode: i32) -> i32;
     pub fn lumo_gpu_ctx_occlusion_stats(ctx: *mut lumo_ctx, stats9: *mut u64) -> i32;
     pub fn lumo_gpu_ctx_kernel_times(ctx: *mut lumo_ctx, ms4: *mut f64, launches4: *mut u64) -> i32;

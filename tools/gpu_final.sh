@@ -1,6 +1,13 @@
 #!/bin/bash
-# round-end check: film-encode tests first (new code), then the whole -m gpu suite, then one bench line
+# round-end check: the whole -m gpu suite, DRAM traffic per workload from ncu launch lists, then the full bench line
 mkdir -p gpurun_out
-timeout 240 python -m pytest tests/test_film_encode.py -m gpu -x -q > gpurun_out/final_film_tests.log 2>&1; echo "film tests rc=$?"; tail -4 gpurun_out/final_film_tests.log
-timeout 430 python -m pytest tests -m gpu -x -q --durations=12 --deselect tests/test_film_encode.py > gpurun_out/final_gpu_tests.log 2>&1; echo "gpu suite rc=$?"; tail -18 gpurun_out/final_gpu_tests.log
-timeout 170 python bench.py --other-scenes "" > gpurun_out/final_bench.json 2> gpurun_out/final_bench.err; echo "bench rc=$?"; tail -2 gpurun_out/final_bench.err | cut -c1-300; cut -c1-600 gpurun_out/final_bench.json
+timeout 900 python -m pytest tests -m gpu -x -q --durations=8 > gpurun_out/r2_final_gpu_tests.log 2>&1; echo "gpu suite rc=$?"; tail -14 gpurun_out/r2_final_gpu_tests.log
+export PROF_RR_DELTA=0.05
+for WS in "bistro 2" "bunny 8" "dragon 4" "conference 8" "cornell 32"; do
+  set -- $WS; W=$1; SPP=$2
+  PROF_ITERLOG=gpurun_out/r2_iterlog_$W.json timeout 300 python tools/prof_run.py $W $SPP > gpurun_out/r2_prof_$W.log 2>&1 || { echo "plain run of $W failed"; tail -3 gpurun_out/r2_prof_$W.log; continue; }
+  timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 1300 --csv --log-file gpurun_out/r2_launches_${W}_final.csv python tools/prof_run.py $W $SPP > /dev/null 2>&1
+  python tools/traffic_from_ncu.py gpurun_out/r2_launches_${W}_final.csv gpurun_out/r2_iterlog_$W.json $W profiles/traffic.json > /dev/null 2> gpurun_out/r2_traffic_$W.err || tail -3 gpurun_out/r2_traffic_$W.err
+done
+cp profiles/traffic.json gpurun_out/traffic.json
+timeout 900 python bench.py > gpurun_out/r2_bench_final.json 2> gpurun_out/r2_bench_final.err; echo "bench rc=$?"; tail -2 gpurun_out/r2_bench_final.err | cut -c1-300; cut -c1-700 gpurun_out/r2_bench_final.json
