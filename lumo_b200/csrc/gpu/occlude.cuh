@@ -204,6 +204,10 @@ struct OcclQueues {
 // whose ray is finished takes the next ray of the queue while the others continue (lanes are refilled once LUMO_AH_REFILL
 // of them are free), and the lanes of a warp alternate between the two kinds of work together: up to LUMO_AH_NODE_ROUND
 // inner-node steps, then one leaf primitive for every lane that holds one.
+// (Measured and dropped: a blocker cache for the wave's shadow rays — the classic shadow cache keyed by (light, cell of the origin in a 16^3 grid), 4 M lines,
+// the cached primitive tested ahead of the BVH root.  Verdicts are unchanged by construction, but on the street stand-in the
+// blockers are small triangles that rarely repeat: occlusion class 151.9 -> 181.1 ms on bistro 4 spp; 8^3 / 32^3 grids and
+// 16 M lines 177.9 / 183.1 / 191.1 ms; neutral on bunny, conference and dragon.)
 // resident CTAs per SM the two BVH walks are compiled for (register budget 65536 / (128 * blocks)) and launched with.
 // Same-box A/B on B200, bistro 4 spp, occlusion class ms: 4 CTAs (114 registers) 176.2, 5 (102) 155.3, 6 (85, spills) 161.4.
 #ifndef LUMO_BVH_BLOCKS

@@ -619,21 +619,25 @@ __global__ void __launch_bounds__(128, LUMO_NEE_A_BLOCKS) k_nee_b(const __grid_c
         D3 wi;
         Lam l2 = lam;
         if (!bsdf_sample<K>(S, m, uvw, wo, ho, l2, ru, r0, r1, wi)) continue;
-        const Ray ri = hit_generate_ray(ho, wi);
         const LumoLight L = S.lights[li];
 #if LUMO_NEE_B_PREREJECT
         // The BSDF-sampled direction nearly never points at the ONE light this shadow sample picked (1 of 4097 on the street):
         // a line that stays outside the light's padded bounding sphere cannot pass its intersection test (scene_blob.h LumoLight).
+        // Tested on the surface point itself, before the spawn offset and the normalisation of hit_generate_ray: the offset is
+        // at most |fp_error|_1 plus an ulp (hit.rs:85-111), added to the radius; the 1e-12 |v|^2 covers the direction's rounding.
         bool far_off;
         {
-            const D3 v = d3(L.bound_c[0], L.bound_c[1], L.bound_c[2]) - ri.o;
-            const double vv = dot(v, v), dd = dot(ri.d, ri.d), b = dot(v, ri.d);
-            far_off = vv * dd - b * b > (L.bound_r * L.bound_r + 1e-12 * vv) * dd;
+            const D3 v = d3(L.bound_c[0], L.bound_c[1], L.bound_c[2]) - ho.p;
+            const double pad = 2.0 * (fabs(ho.fp_error.x) + fabs(ho.fp_error.y) + fabs(ho.fp_error.z)) + 1e-14 * (fabs(ho.p.x) + fabs(ho.p.y) + fabs(ho.p.z));
+            const double R = L.bound_r + pad;
+            const double vv = dot(v, v), dd = dot(wi, wi), b = dot(v, wi);
+            far_off = vv * dd - b * b > (R * R + 1e-12 * vv) * dd;
         }
         if (far_off && !P.check) continue;
 #else
         const bool far_off = false;
 #endif
+        const Ray ri = hit_generate_ray(ho, wi);
         DevHit hi;
         if (!light_hit<LUMO_TEX(K)>(S, lobj, ri, hi)) continue;
         if (far_off) atomicAdd(&W.run->prereject_bad, 1u);                            // check mode only: must never happen
