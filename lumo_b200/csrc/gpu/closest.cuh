@@ -47,8 +47,10 @@ struct ClosestCounters { unsigned long long nodes, prims, tris, spheres, fallbac
 #endif
 
 // One inner-node step of the ordered walk: hit children are pushed with their entry distances, the nearest is walked next.
+// A stack entry is one 64-bit word — entry distance (f32 bits) above the node — so that a push or a pop is one local-memory access.
+__device__ __forceinline__ unsigned long long ch_entry(uint32_t node, float t) { return ((unsigned long long)__float_as_uint(t) << 32) | node; }
 template <bool CNT>
-__device__ __forceinline__ bool ch_node_step(const DevScene& S, const AhRay& a, uint32_t& node, uint32_t* stack, float* stack_t, int& sp, bool& over, ClosestCounters* c) {
+__device__ __forceinline__ bool ch_node_step(const DevScene& S, const AhRay& a, uint32_t& node, unsigned long long* stack, int& sp, bool& over, ClosestCounters* c) {
     if (CNT) c->nodes++;
     const float4* n4 = reinterpret_cast<const float4*>(S.ah_nodes + node);
     const float4 ax = __ldg(n4 + a.ox), bx = __ldg(n4 + 3 - a.ox);
@@ -65,25 +67,26 @@ __device__ __forceinline__ bool ch_node_step(const DevScene& S, const AhRay& a, 
     const float f3 = fminf(fminf(__fmaf_rn(bx.w, a.ix, a.fx), __fmaf_rn(by.w, a.iy, a.fy)), fminf(__fmaf_rn(bz.w, a.iz, a.fz), a.tmax));
     const float rel = 1.00000095367431640625f;   // 1 + 2^-20
     const bool h0 = n0 <= f0 * rel && ch.x != LUMO_NONE, h1 = n1 <= f1 * rel && ch.y != LUMO_NONE, h2 = n2 <= f2 * rel && ch.z != LUMO_NONE, h3 = n3 <= f3 * rel && ch.w != LUMO_NONE;
-    uint32_t next = LUMO_NONE; float best = 0.0f;
-#define LUMO_CH_TAKE(h, n, c)                                                                                                  \
-    if (h) {                                                                                                                   \
-        if (next == LUMO_NONE) { next = c; best = n; }                                                                         \
-        else if (sp >= LUMO_CH_STACK) over = true;                                                                             \
-        else if (n < best) { stack[sp] = next; stack_t[sp] = best; sp++; next = c; best = n; }                                 \
-        else { stack[sp] = c; stack_t[sp] = n; sp++; }                                                                         \
-    }
-    LUMO_CH_TAKE(h0, n0, ch.x) LUMO_CH_TAKE(h1, n1, ch.y) LUMO_CH_TAKE(h2, n2, ch.z) LUMO_CH_TAKE(h3, n3, ch.w)
-#undef LUMO_CH_TAKE
+    // the nearest hit child is walked next, the others go on the stack with their entry distances (in child order)
+    const float inf = __int_as_float(0x7F800000);
+    float best = h0 ? n0 : inf; uint32_t next = h0 ? ch.x : LUMO_NONE;
+    if (h1 && n1 < best) { best = n1; next = ch.y; } else if (h1 && next == LUMO_NONE) next = ch.y;
+    if (h2 && n2 < best) { best = n2; next = ch.z; } else if (h2 && next == LUMO_NONE) next = ch.z;
+    if (h3 && n3 < best) { best = n3; next = ch.w; } else if (h3 && next == LUMO_NONE) next = ch.w;
     if (next == LUMO_NONE) return false;
+    if (sp + 3 > LUMO_CH_STACK) { over = (int)h0 + (int)h1 + (int)h2 + (int)h3 - 1 + sp > LUMO_CH_STACK; if (over) return true; }
+    if (h0 && ch.x != next) stack[sp++] = ch_entry(ch.x, n0);
+    if (h1 && ch.y != next) stack[sp++] = ch_entry(ch.y, n1);
+    if (h2 && ch.z != next) stack[sp++] = ch_entry(ch.z, n2);
+    if (h3 && ch.w != next) stack[sp++] = ch_entry(ch.w, n3);
     node = next;
     return true;
 }
 // pops the next node that can still hold something at or below the current bound; false: the walk is over
-__device__ __forceinline__ bool ch_pop(const AhRay& a, uint32_t& node, const uint32_t* stack, const float* stack_t, int& sp) {
+__device__ __forceinline__ bool ch_pop(const AhRay& a, uint32_t& node, const unsigned long long* stack, int& sp) {
     while (sp > 0) {
-        --sp;
-        if (stack_t[sp] <= a.tmax * 1.00000095367431640625f) { node = stack[sp]; return true; }
+        const unsigned long long e = stack[--sp];
+        if (__uint_as_float((uint32_t)(e >> 32)) <= a.tmax * 1.00000095367431640625f) { node = (uint32_t)e; return true; }
     }
     return false;
 }
@@ -122,7 +125,7 @@ __global__ void __launch_bounds__(128, LUMO_BVH_BLOCKS) k_closest_bvh(const __gr
     const uint32_t n_objects = S.P.n_objects;
     ClosestCounters cnt = {};
     AhLocal L; L.slot = local_ctx + threadIdx.x; L.stride = 128; L.cur = -1;
-    uint32_t stack[LUMO_CH_STACK]; float stack_t[LUMO_CH_STACK];
+    unsigned long long stack[LUMO_CH_STACK];
     bool active = false, exhausted = false;
     uint32_t i = 0, node = 0, leaf_pos = 0, leaf_end = 0, o1 = LUMO_NONE, ol = LUMO_NONE, flags = 0;
     int sp = 0;
@@ -151,7 +154,7 @@ __global__ void __launch_bounds__(128, LUMO_BVH_BLOCKS) k_closest_bvh(const __gr
         for (int step = 0; step < LUMO_CH_NODE_ROUND; step++) {
             if (active && !done && leaf_pos == leaf_end && !(node & LUMO_AH_LEAF)) {
                 bool over = false;
-                if (!ch_node_step<CNT>(S, a, node, stack, stack_t, sp, over, &cnt)) { if (!ch_pop(a, node, stack, stack_t, sp)) done = true; }
+                if (!ch_node_step<CNT>(S, a, node, stack, sp, over, &cnt)) { if (!ch_pop(a, node, stack, sp)) done = true; }
                 if (over) { flags |= 4u; done = true; }
             }
         }
@@ -185,7 +188,7 @@ __global__ void __launch_bounds__(128, LUMO_BVH_BLOCKS) k_closest_bvh(const __gr
                     else sl = fmin(sl, t);
                 }
             }
-            if (leaf_pos == leaf_end) { if (!ch_pop(a, node, stack, stack_t, sp)) done = true; }
+            if (leaf_pos == leaf_end) { if (!ch_pop(a, node, stack, sp)) done = true; }
         }
         if (done) {
             if (o1 != LUMO_NONE && s1 <= ch_ext(t1)) flags |= 1u;

@@ -669,10 +669,12 @@ static int32_t run_wave(lumo_scene* sc, const Wave& W, WaveParams P, uint64_t& i
                 else k_wave_occlude<false><<<tgrid, 128, 0, st>>>(sc->S, W, nullptr, nullptr, nullptr);
                 ctx->launches++;
             } else {
-                WaveShadowSource src{W}; WaveShadowSink sink{W, ctx->occl_check ? W.occ_record : nullptr};
+                WaveShadowSource src{W}; WaveShadowSink sink{W, W.occ_record};
                 OcclQueues Q; Q.confirm_i = W.oq_i; Q.confirm_obj = W.oq_obj; Q.fallback_i = W.oq_fb; Q.counters = W.it->occl;
                 int32_t rc = launch_occlusion(sc, src, sink, Q, st); if (rc != LUMO_OK) return rc;
-                if (ctx->occl_check) { k_wave_occlude<false><<<tgrid, 128, 0, st>>>(sc->S, W, nullptr, W.occ_record, ctx->d_ah); ctx->launches++; }
+                if (ctx->occl_check) k_wave_occlude<false><<<tgrid, 128, 0, st>>>(sc->S, W, nullptr, W.occ_record, ctx->d_ah);
+                else k_shadow_apply<<<sgrid, 256, 0, st>>>(W, W.occ_record);
+                ctx->launches++;
             }
             CU(cudaEventRecord(ev[4], st));
             k_queue_reset<<<1, 1, 0, st>>>(W.qc, P.cur, W.it, P.mode == WM_MAIN ? ctx->d_iter_log : nullptr, main_iter, LUMO_ITER_LOG_CAP);

@@ -99,16 +99,19 @@ __device__ __forceinline__ bool ah_node_step(const DevScene& S, const AhRay& a, 
     const float rel = 1.00000095367431640625f;   // 1 + 2^-20
     // (an empty child has an inverted infinite box, which fails the test by itself — except for garbage rays whose 1/d is 0 or NaN)
     const bool h0 = n0 <= f0 * rel && ch.x != LUMO_NONE, h1 = n1 <= f1 * rel && ch.y != LUMO_NONE, h2 = n2 <= f2 * rel && ch.z != LUMO_NONE, h3 = n3 <= f3 * rel && ch.w != LUMO_NONE;
-    uint32_t next = LUMO_NONE; float best = 0.0f;
-#define LUMO_AH_TAKE(h, n, c)                                                                           \
-    if (h) {                                                                                            \
-        if (next == LUMO_NONE) { next = c; best = n; }                                                  \
-        else if (sp >= LUMO_AH_STACK) over = true;                                                      \
-        else if (n < best) { stack[sp++] = next; next = c; best = n; }                                  \
-        else stack[sp++] = c;                                                                           \
+    // the nearest hit child is walked next, the others go on the stack (in child order)
+    const float inf = __int_as_float(0x7F800000);
+    float best = h0 ? n0 : inf; uint32_t next = h0 ? ch.x : LUMO_NONE;
+    if (h1 && n1 < best) { best = n1; next = ch.y; } else if (h1 && next == LUMO_NONE) next = ch.y;
+    if (h2 && n2 < best) { best = n2; next = ch.z; } else if (h2 && next == LUMO_NONE) next = ch.z;
+    if (h3 && n3 < best) { best = n3; next = ch.w; } else if (h3 && next == LUMO_NONE) next = ch.w;
+    if (next != LUMO_NONE) {
+        if (sp + 3 > LUMO_AH_STACK && (int)h0 + (int)h1 + (int)h2 + (int)h3 - 1 + sp > LUMO_AH_STACK) { over = true; return true; }
+        if (h0 && ch.x != next) stack[sp++] = ch.x;
+        if (h1 && ch.y != next) stack[sp++] = ch.y;
+        if (h2 && ch.z != next) stack[sp++] = ch.z;
+        if (h3 && ch.w != next) stack[sp++] = ch.w;
     }
-    LUMO_AH_TAKE(h0, n0, ch.x) LUMO_AH_TAKE(h1, n1, ch.y) LUMO_AH_TAKE(h2, n2, ch.z) LUMO_AH_TAKE(h3, n3, ch.w)
-#undef LUMO_AH_TAKE
     if (next == LUMO_NONE) { if (sp == 0) return false; next = stack[--sp]; }
     node = next;
     return true;

@@ -367,16 +367,23 @@ struct WaveShadowSource {
         r.o = d3(W.sox[i], W.soy[i], W.soz[i]); r.d = d3(W.sdx[i], W.sdy[i], W.sdz[i]); t_max = W.stmax[i];
     }
 };
+// Verdicts are only noted here; the contributions of the unoccluded rays are added by the kernel that follows — k_shadow_apply, or
+// the faithful k_wave_occlude in check mode.  (Adding them from inside the walk made every lane of a warp wait for one lane's
+// cold loads of the colour and its four atomics: 12 % of k_occl_bvh's stall samples.)
 struct WaveShadowSink {
-    Wave W; uint8_t* record;     // record != nullptr (check mode): only note the verdict; the faithful kernel that follows adds the contributions
-    __device__ __forceinline__ void verdict(uint32_t i, bool occluded) const {
-        if (record) { record[i] = occluded ? 1 : 0; return; }
-        if (occluded) return;
-        const uint32_t slot = W.sslot[i]; const uint32_t N = W.n_slots, C = W.shadow_cap;
+    Wave W; uint8_t* record;
+    __device__ __forceinline__ void verdict(uint32_t i, bool occluded) const { record[i] = occluded ? 1 : 0; }
+    __device__ __forceinline__ void done(uint32_t) const {}
+};
+__global__ void __launch_bounds__(256) k_shadow_apply(const __grid_constant__ Wave W, const uint8_t* __restrict__ record) {
+    const uint32_t n = min(W.it->n_shadow, W.shadow_cap), N = W.n_slots, C = W.shadow_cap;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (record[i]) continue;
+        const uint32_t slot = W.sslot[i];
         for (int k = 0; k < 4; k++) { const double v = W.sc[(size_t)k * C + i]; if (v != 0.0) atomicAdd(&W.radiance[(size_t)k * N + slot], v); }
     }
-    __device__ __forceinline__ void done(uint32_t n) const { if (!record) atomicAdd(&W.run->occlusion, (unsigned long long)n); }
-};
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&W.run->occlusion, (unsigned long long)n);
+}
 // caller-supplied ray batches (lumo_gpu_trace_any)
 struct BatchShadowSource {
     const double *o, *d, *t_max; uint32_t count;
