@@ -211,6 +211,8 @@ struct OcclQueues {
 // the cached primitive tested ahead of the BVH root.  Verdicts are unchanged by construction, but on the street stand-in the
 // blockers are small triangles that rarely repeat: occlusion class 151.9 -> 181.1 ms on bistro 4 spp; 8^3 / 32^3 grids and
 // 16 M lines 177.9 / 183.1 / 191.1 ms; neutral on bunny, conference and dragon.)
+// (Measured and dropped: prefetch.global.L1 of a leaf's primitive records when the walk first sees the leaf, and of the next
+// primitive's vertices during a test: occlusion class 131.4 -> 138.5 ms on bistro 4 spp.)
 // resident CTAs per SM the two BVH walks are compiled for (register budget 65536 / (128 * blocks)) and launched with.
 // Same-box A/B on B200, bistro 4 spp, occlusion class ms: 4 CTAs (114 registers) 176.2, 5 (102) 155.3, 6 (85, spills) 161.4.
 #ifndef LUMO_BVH_BLOCKS
