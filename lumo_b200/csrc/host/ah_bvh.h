@@ -8,6 +8,7 @@
 // they let through is tested with the reference's own f64 triangle / sphere test in its object's frame, and a candidate
 // blocker is confirmed by the reference's own traversal of that one object (csrc/gpu/occlude.cuh).
 #pragma once
+#include <cstdlib>
 #include "host_math.h"
 #include "../common/scene_blob.h"
 #include <algorithm>
@@ -50,7 +51,13 @@ struct AhBuilder {
     void add(const Box& world, uint32_t tri, uint32_t obj) { boxes.push_back(ah_box(world)); LumoAhPrim p = {tri, obj}; prims.push_back(p); }
 
     static constexpr int BINS = 16;
-    static constexpr double C_TRAV = 1.0, C_ISECT = 1.5;   // one f64 triangle test costs about as much as one four-box node
+    static constexpr double C_TRAV = 1.0;
+    double C_ISECT = 1.5;              // cost of one f64 primitive test in units of one four-box node step (LUMO_AH_CISECT overrides: experiments)
+    uint32_t max_leaf = LUMO_AH_MAX_LEAF;
+    AhBuilder() {
+        if (const char* e = std::getenv("LUMO_AH_CISECT")) { const double v = std::atof(e); if (v > 0.0) C_ISECT = v; }
+        if (const char* e = std::getenv("LUMO_AH_MAXLEAF")) { const int v = std::atoi(e); if (v >= 1 && v <= LUMO_AH_MAX_LEAF) max_leaf = (uint32_t)v; }
+    }
 
     void build_binary() {
         const uint32_t n = (uint32_t)boxes.size();
@@ -97,7 +104,7 @@ struct AhBuilder {
                     if (cost < best) { best = cost; best_ax = ax; best_bin = b; }
                 }
             }
-            if (cnt <= LUMO_AH_MAX_LEAF && !(best < C_ISECT * cnt)) { make_leaf(); continue; }
+            if (cnt <= max_leaf && !(best < C_ISECT * cnt)) { make_leaf(); continue; }
             uint32_t mid;
             if (best_ax < 0) mid = j.begin + cnt / 2;             // all centres coincide: split the list in half
             else {
