@@ -389,7 +389,7 @@ def measure(name, args, env, steps, warmup, full):
     if by["trace"]:
         by["trace"]["bvh_per_ray"] = {k: v / max(cntc["closest"], 1) for k, v in cst.items() if k != "rays"}
         by["trace"]["reference_order_visits_per_ray"] = {k: v / max(cntc["closest"], 1) for k, v in vis_closest.items()}
-    by["occlude"] = entry("k_occl_bvh + k_occl_confirm + k_occl_fallback (order-free occlusion BVH, confirmed by the reference's per-object traversal)", "occlude",
+    by["occlude"] = entry("k_occl_bvh + k_occl_confirm + k_occl_fallback + k_shadow_apply (order-free occlusion BVH, confirmed by the reference's per-object traversal)", "occlude",
                           occl_bytes(ost, vis_occl, cntc["occlusion"]), cntc["occlusion"], "ray",
                           "60 B shadow-queue entry + 128 B per BVH node + 8 B per leaf primitive + 72 B per triangle test + 68 B per candidate + the confirming traversal's visits")
     if by["occlude"]: by["occlude"]["per_ray"] = {k: v / max(cntc["occlusion"], 1) for k, v in ost.items()}

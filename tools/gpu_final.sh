@@ -10,4 +10,4 @@ for WS in "bistro 2" "bunny 8" "dragon 4" "conference 8" "cornell 32"; do
   python tools/traffic_from_ncu.py gpurun_out/r2_launches_${W}_final.csv gpurun_out/r2_iterlog_$W.json $W profiles/traffic.json > /dev/null 2> gpurun_out/r2_traffic_$W.err || tail -3 gpurun_out/r2_traffic_$W.err
 done
 cp profiles/traffic.json gpurun_out/traffic.json
-timeout 900 python bench.py > gpurun_out/r2_bench_final.json 2> gpurun_out/r2_bench_final.err; echo "bench rc=$?"; tail -2 gpurun_out/r2_bench_final.err | cut -c1-300; cut -c1-700 gpurun_out/r2_bench_final.json
+timeout 900 python bench.py > gpurun_out/r2_bench_last.json 2> gpurun_out/r2_bench_last.err; echo "bench rc=$?"; tail -2 gpurun_out/r2_bench_last.err | cut -c1-300; cut -c1-700 gpurun_out/r2_bench_last.json

@@ -5,7 +5,7 @@ usage: python tools/traffic_from_ncu.py <launches.csv> <iterlog.json> <workload>
 import csv, json, re, sys, collections
 rows = list(csv.DictReader([l for l in open(sys.argv[1]) if not l.startswith("==")]))
 log = json.load(open(sys.argv[2])); workload = sys.argv[3]
-CLASS = [("trace", r"k_closest_|k_wave_classify|k_wave_trace"), ("occlude", r"k_occl_|k_wave_occlude"), ("shade", r"k_terminal|k_scatter|k_nee_|k_terms_reset"), ("regen", r"k_retire|k_compact")]
+CLASS = [("trace", r"k_closest_|k_wave_classify|k_wave_trace"), ("occlude", r"k_occl_|k_wave_occlude|k_shadow_apply"), ("shade", r"k_terminal|k_scatter|k_nee_|k_terms_reset"), ("regen", r"k_retire|k_compact")]
 per_id = collections.defaultdict(dict)
 for r in rows:
     v = float(r["Metric Value"].replace(",", "")); u = r["Metric Unit"]
