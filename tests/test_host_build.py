@@ -102,3 +102,33 @@ def test_builder_rejects_what_the_reference_rejects():
         native.build_blob(b"not a program....")
     with pytest.raises(AssertionError):
         CameraBuilder.new().vfov(180.0).build()                      # matrices.rs:5
+
+
+@pytest.mark.parametrize("name", list(SMALL))
+def test_light_bounding_spheres_contain_the_lights(name):
+    """LumoLight.bound_*: the sphere k_nee_b uses to skip a light's intersection test must contain every point of the light in
+    world space with room to spare — vertices of triangle / rectangle / mesh lights, the whole ball of a sphere light — through
+    the light's instance transform."""
+    prog, blob, _ = small_scene(name)
+    B = native.Blob(blob)
+    P = B.params
+    n_obj, n_l = int(P["n_objects"]), int(P["n_lights"])
+    assert len(B.lights) == n_l
+    rs = np.random.RandomState(3)
+    u = rs.randn(256, 3); u /= np.linalg.norm(u, axis=1, keepdims=True)
+    for li in range(n_l):
+        o = B.objects[n_obj + li]; L = B.lights[li]
+        kind, geom = int(o["kind"]), int(o["geom"])
+        if kind in (0, 1):                              # kd mesh; a rectangle is a two-triangle mesh
+            T = B.kd_trees[geom]; tv = B.tri_verts[int(T["tri_base"]):int(T["tri_base"]) + int(T["n_tris"])]
+            pts = np.concatenate([tv["a"], tv["b"], tv["c"]])
+        elif kind == 2: pts = u * float(B.spheres[geom]["radius"])
+        else: tv = B.tri_verts[geom:geom + 1]; pts = np.concatenate([tv["a"], tv["b"], tv["c"]])
+        if int(o["inst"]) >= 0:
+            m = B.instances[int(o["inst"])]["m"].reshape(3, 4)
+            pts = pts @ m[:, :3].T + m[:, 3]
+        c, r = np.asarray(L["bound_c"]), float(L["bound_r"])
+        d = np.linalg.norm(pts - c, axis=1).max()
+        assert np.isfinite(r) and r > 0.0
+        assert d <= r * (1.0 - 5e-5), (name, li, kind, d, r)          # padded by 1e-4 of the radius
+        assert r <= 1.8 * d + 1e-5 * (np.abs(c).max() + 1.0), (name, li, kind, d, r)   # and not uselessly large (half diagonal of the box <= sqrt(3) x the farthest point)
