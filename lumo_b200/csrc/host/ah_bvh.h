@@ -56,7 +56,7 @@ struct AhBuilder {
     uint32_t max_leaf = LUMO_AH_MAX_LEAF;
     AhBuilder() {
         if (const char* e = std::getenv("LUMO_AH_CISECT")) { const double v = std::atof(e); if (v > 0.0) C_ISECT = v; }
-        if (const char* e = std::getenv("LUMO_AH_MAXLEAF")) { const int v = std::atoi(e); if (v >= 1 && v <= LUMO_AH_MAX_LEAF) max_leaf = (uint32_t)v; }
+        if (const char* e = std::getenv("LUMO_AH_MAXLEAF")) { const int v = std::atoi(e); if (v >= 1 && v <= (int)LUMO_AH_MAX_LEAF) max_leaf = (uint32_t)v; }
     }
 
     void build_binary() {
