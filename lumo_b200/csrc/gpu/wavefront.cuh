@@ -36,7 +36,7 @@ struct IterCounters {   // zeroed before every iteration
     uint32_t n_shadow, trace_next, occl_next, n_active;
     uint32_t n_class[LUMO_N_CLASSES], pad[3];
     uint32_t occl[8];   // OcclQueues::counters of the occlusion-BVH kernels (occlude.cuh)
-    uint32_t n_terms, n_nee, pad2[2];   // NEE term queue; bounces of the current material family that run NEE (Wave::neeq)
+    uint32_t n_terms, n_nee, n_surv, pad2;   // NEE term queue; bounces of the current material family that run NEE (Wave::neeq); light-sampled terms that passed the sign tests (Wave::surv)
     uint32_t closest[4];         // ClosestScratch::counters of the closest-hit pipeline (closest.cuh)
 };
 // Counters that live across iterations (double-buffered by the parity of the iteration): done[p] = slots whose
@@ -56,6 +56,7 @@ struct RunCounters {    // zeroed once per render
 // still reads this bounce's values from buffer cur.
 struct NeeTermQueue;
 struct Wave;
+struct NeeSurvivors { uint32_t *slot, *li; double *wx, *wy, *wz; };    // k_nee_a1 -> k_nee_a; capacity shadow_cap / 2 = n_slots * n_shadow_rays
 struct NeeTermQueue {   // NEE stage 1 -> stage 2 (see k_nee_a): structure of arrays, capacity = shadow_cap; reused by one material family after the other
     double *ox, *oy, *oz, *dx, *dy, *dz, *wx, *wy, *wz, *tmax, *p_lig, *pdf_light, *le;   // le[k * cap + i]
     uint32_t* slot;     // bit 31: the BSDF-sampled term (B)
@@ -76,6 +77,7 @@ struct Wave {
     double *ch_t1, *ch_tl; uint32_t *ch_o1, *ch_ol, *ch_flags, *ch_fb;   // closest-hit pipeline: per-ray scratch of k_closest_bvh, fallback queue (capacity n_slots)
     double* nee_ctx; uint32_t* nee_meta; NeeTermQueue tq;   // NEE: per-slot shading context [k * n_slots + slot] (17 doubles), term queue
     uint32_t* neeq;                                          // slots of the current material family whose bounce runs NEE (dense; written by k_scatter)
+    NeeSurvivors surv;                                       // k_nee_a1 -> k_nee_a
     uint32_t *oq_i, *oq_obj, *oq_fb; uint8_t* occ_record;   // occlusion-BVH pipeline: confirm queue, fallback queue; verdicts (LUMO_OCCLUDE_CHECK only)
     IterCounters* it; RunCounters* run; QueueCounters* qc;
     // film + RR thresholds
@@ -569,6 +571,62 @@ __device__ __forceinline__ bool nee_item(const Wave& W, unsigned long long it, u
 #ifndef LUMO_NEE_B_PREREJECT
 #define LUMO_NEE_B_PREREJECT 1
 #endif
+// LUMO_NEE_A_SPLIT: the light-sampled term as two kernels — k_nee_a1 picks the light, samples the point and runs the two sign
+// tests; the survivors (half of the items) go through a queue in HBM to k_nee_a, which runs the light's intersection test, pdf
+// and emission on dense warps.  Each kernel carries half of the code.
+#ifndef LUMO_NEE_A_SPLIT
+#define LUMO_NEE_A_SPLIT 1
+#endif
+#if LUMO_NEE_A_SPLIT
+__global__ void __launch_bounds__(128, LUMO_NEE_A_BLOCKS) k_nee_a1(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P, uint32_t klass) {
+    const uint32_t N = W.n_slots, nq = W.it->n_nee, cur = P.cur, ns = S.P.n_shadow_rays;
+    const unsigned long long padded = (unsigned long long)((nq + 31u) / 32u) * 32ull * ns;
+    for (unsigned long long it = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; it < padded; it += (unsigned long long)gridDim.x * blockDim.x) {
+        __syncwarp();
+        uint32_t slot, i;
+        if (!nee_item(W, it, ns, nq, slot, i)) continue;
+        const double* c = W.nee_ctx + slot;
+        const D3 xo = d3(c[0], c[(size_t)N], c[2 * (size_t)N]);
+        // draws of this bounce: 3 for the scatter sample, then 6 per shadow sample: light pick, light point (2), BSDF sample (3)
+        Rng rng = rng_make(P.seed, W.pixel[slot], W.sample[slot], 0u, W.draws[cur][slot] + 3u + 6u * i);
+        const uint32_t li = sample_light(S, rng_float(rng));
+        const LumoObject lo = S.objects[S.P.n_objects + li];
+        const double r0 = rng_float(rng), r1 = rng_float(rng);
+        const D3 wi = light_sample_towards(S, lo, xo, r0, r1);
+        // mis_sample returns black when either pdf is zero (integrator.rs:150-152) whatever the light test says.  For the
+        // reflection-only BxDFs the pdf starts with two sign tests (bsdf.rs:88-90, bxdf.rs:136-139, scatter.rs:14-17):
+        // a light-sampled direction below the surface stops here, before any light or microfacet arithmetic.
+        if (klass != LMAT_MFDIELECTRIC) {
+            const D3 ng = d3(c[6 * (size_t)N], c[7 * (size_t)N], c[8 * (size_t)N]), nb = d3(c[12 * (size_t)N], c[13 * (size_t)N], c[14 * (size_t)N]);
+            const D3 wo = d3(-W.dx[cur][slot], -W.dy[cur][slot], -W.dz[cur][slot]);
+            if (!is_reflection(wo, wi, ng)) continue;
+            const Onb uvw = onb_new(nb);
+            if (!same_hemisphere(to_local(uvw, wo), to_local(uvw, wi))) continue;
+        }
+        const uint32_t j = agg_inc(&W.it->n_surv);
+        W.surv.slot[j] = slot; W.surv.li[j] = li; W.surv.wx[j] = wi.x; W.surv.wy[j] = wi.y; W.surv.wz[j] = wi.z;
+    }
+}
+template <bool TEX>
+__global__ void __launch_bounds__(128, LUMO_NEE_A_BLOCKS) k_nee_a(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P, uint32_t klass) {
+    const uint32_t N = W.n_slots, n = W.it->n_surv;
+    const uint32_t n_pad = (n + 31u) & ~31u;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_pad; j += gridDim.x * blockDim.x) {
+        __syncwarp();
+        if (j >= n) continue;
+        const uint32_t slot = W.surv.slot[j], li = W.surv.li[j], lobj = S.P.n_objects + li;
+        const D3 wi = d3(W.surv.wx[j], W.surv.wy[j], W.surv.wz[j]);
+        DevHit ho; D3 nb; nee_ctx_load(W, slot, ho, nb);
+        const Ray ri = hit_generate_ray(ho, wi);
+        DevHit hi;
+        if (!light_hit<TEX>(S, lobj, ri, hi)) continue;
+        const double p_lig = light_sample_towards_pdf(S, S.objects[lobj], ri, hi.p, hi.ng);
+        Lam lam; for (int k = 0; k < 4; k++) lam.l[k] = W.lam[(size_t)k * N + slot];   // already terminated by k_scatter if dispersive
+        const C4 le = mat_emit<TEX ? -1 : LUMO_K_SOLID>(S, S.materials[hi.material], lam, hi);
+        push_term(W, slot, false, ri, wi, hi.t - LUMO_EPS, p_lig, S.lights[li].pdf, le);
+    }
+}
+#else
 template <bool TEX>
 __global__ void __launch_bounds__(128, LUMO_NEE_A_BLOCKS) k_nee_a(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P, uint32_t klass) {
     const uint32_t N = W.n_slots, nq = W.it->n_nee, cur = P.cur, ns = S.P.n_shadow_rays;
@@ -603,6 +661,7 @@ __global__ void __launch_bounds__(128, LUMO_NEE_A_BLOCKS) k_nee_a(const __grid_c
         push_term(W, slot, false, ri, wi, hi.t - LUMO_EPS, p_lig, S.lights[li].pdf, le);
     }
 }
+#endif
 // the BSDF-sampled term up to the same point (integrator.rs:112-134)
 template <int K>
 __global__ void __launch_bounds__(128, LUMO_NEE_A_BLOCKS) k_nee_b(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P) {
@@ -688,7 +747,7 @@ __global__ void __launch_bounds__(128, LUMO_NEE_BLOCKS) k_nee_eval(const __grid_
         push_shadow(W, slot, ri, T.tmax[ti], load_c4(W.gathered[cur], N, slot) * (c / T.pdf_light[ti]) / ns);
     }
 }
-__global__ void k_terms_reset(IterCounters* it) { it->n_terms = 0u; it->n_nee = 0u; }   // after each material family
+__global__ void k_terms_reset(IterCounters* it) { it->n_terms = 0u; it->n_nee = 0u; it->n_surv = 0u; }   // after each material family
 
 // RR threshold of a tile from its 64 pilot paths, summed in index order (task.rs:42-53 applied to
 // the pilot set): var = sum f^2 - (sum f)^2 / n; delta = var <= 0 ? 1e-5 : sqrt(var / sum cost)
