@@ -589,7 +589,7 @@ static void carve_wave(Wave& W, Carver& c, uint32_t N, uint32_t shadow_cap, uint
     { NeeTermQueue& T = W.tq; T.ox = c.take<double>(C); T.oy = c.take<double>(C); T.oz = c.take<double>(C); T.dx = c.take<double>(C); T.dy = c.take<double>(C); T.dz = c.take<double>(C);
       T.wx = c.take<double>(C); T.wy = c.take<double>(C); T.wz = c.take<double>(C); T.tmax = c.take<double>(C); T.p_lig = c.take<double>(C); T.pdf_light = c.take<double>(C);
       T.le = c.take<double>(4 * C); T.slot = c.take<uint32_t>(C); }
-    { NeeSurvivors& V = W.surv; const size_t H = C / 2 + 1; V.slot = c.take<uint32_t>(H); V.li = c.take<uint32_t>(H); V.wx = c.take<double>(H); V.wy = c.take<double>(H); V.wz = c.take<double>(H); }
+    { NeeSurvivors& V = W.surv; const size_t H = C + 1; V.slot = c.take<uint32_t>(H); V.li = c.take<uint32_t>(H); V.wx = c.take<double>(H); V.wy = c.take<double>(H); V.wz = c.take<double>(H); }
     W.it = c.take<IterCounters>(1); W.run = c.take<RunCounters>(1); W.qc = c.take<QueueCounters>(1);
     W.tile_delta = c.take<double>(n_tiles); W.tile_delta_next = c.take<double>(n_tiles);
     W.pilot_lum = c.take<double>((size_t)n_tiles * LUMO_PILOT_N); W.pilot_cost = c.take<uint32_t>((size_t)n_tiles * LUMO_PILOT_N);
@@ -607,17 +607,23 @@ static void launch_shade_kind(lumo_scene* sc, const Wave& W, const WaveParams& P
         k_scatter<K><<<grid, 128, 0, st>>>(sc->S, W, P);
 #if LUMO_NEE_A_SPLIT
         k_nee_a1<<<nee_grid, 128, 0, st>>>(sc->S, W, P, (uint32_t)K); launches++;
-#endif
+        k_nee_b<K><<<nee_grid, 128, 0, st>>>(sc->S, W, P);
+        k_nee_a<true><<<nee_grid, 128, 0, st>>>(sc->S, W, P, (uint32_t)K);
+#else
         k_nee_a<true><<<nee_grid, 128, 0, st>>>(sc->S, W, P, (uint32_t)K);
         k_nee_b<K><<<nee_grid, 128, 0, st>>>(sc->S, W, P);
+#endif
         k_nee_eval<K><<<nee_grid, 128, 0, st>>>(sc->S, W, P);
     } else {
         k_scatter<K | LUMO_K_SOLID><<<grid, 128, 0, st>>>(sc->S, W, P);
 #if LUMO_NEE_A_SPLIT
         k_nee_a1<<<nee_grid, 128, 0, st>>>(sc->S, W, P, (uint32_t)K); launches++;
-#endif
+        k_nee_b<K | LUMO_K_SOLID><<<nee_grid, 128, 0, st>>>(sc->S, W, P);
+        k_nee_a<false><<<nee_grid, 128, 0, st>>>(sc->S, W, P, (uint32_t)K);
+#else
         k_nee_a<false><<<nee_grid, 128, 0, st>>>(sc->S, W, P, (uint32_t)K);
         k_nee_b<K | LUMO_K_SOLID><<<nee_grid, 128, 0, st>>>(sc->S, W, P);
+#endif
         k_nee_eval<K | LUMO_K_SOLID><<<nee_grid, 128, 0, st>>>(sc->S, W, P);
     }
     k_terms_reset<<<1, 1, 0, st>>>(W.it);

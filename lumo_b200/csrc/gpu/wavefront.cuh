@@ -56,7 +56,7 @@ struct RunCounters {    // zeroed once per render
 // still reads this bounce's values from buffer cur.
 struct NeeTermQueue;
 struct Wave;
-struct NeeSurvivors { uint32_t *slot, *li; double *wx, *wy, *wz; };    // k_nee_a1 -> k_nee_a; capacity shadow_cap / 2 = n_slots * n_shadow_rays
+struct NeeSurvivors { uint32_t *slot, *li; double *wx, *wy, *wz; };    // k_nee_a1, k_nee_b -> k_nee_a; capacity shadow_cap = 2 * n_slots * n_shadow_rays; li: bit 31 term B, bit 30 check-mode flag
 struct NeeTermQueue {   // NEE stage 1 -> stage 2 (see k_nee_a): structure of arrays, capacity = shadow_cap; reused by one material family after the other
     double *ox, *oy, *oz, *dx, *dy, *dz, *wx, *wy, *wz, *tmax, *p_lig, *pdf_light, *le;   // le[k * cap + i]
     uint32_t* slot;     // bit 31: the BSDF-sampled term (B)
@@ -571,9 +571,10 @@ __device__ __forceinline__ bool nee_item(const Wave& W, unsigned long long it, u
 #ifndef LUMO_NEE_B_PREREJECT
 #define LUMO_NEE_B_PREREJECT 1
 #endif
-// LUMO_NEE_A_SPLIT: the light-sampled term as two kernels — k_nee_a1 picks the light, samples the point and runs the two sign
-// tests; the survivors (half of the items) go through a queue in HBM to k_nee_a, which runs the light's intersection test, pdf
-// and emission on dense warps.  Each kernel carries half of the code.
+// LUMO_NEE_A_SPLIT: the light side of both terms is one kernel of its own.  k_nee_a1 picks the light, samples the point and runs the
+// two sign tests of the light-sampled term; k_nee_b<K> samples the BSDF and tests the line against the light's bounding sphere; the
+// survivors of both (half of the A items, a tenth of the B items) go through a queue in HBM to k_nee_a, which runs the light's
+// intersection test, pdf and emission on dense warps.  Each kernel carries a fraction of the code.
 #ifndef LUMO_NEE_A_SPLIT
 #define LUMO_NEE_A_SPLIT 1
 #endif
@@ -614,16 +615,18 @@ __global__ void __launch_bounds__(128, LUMO_NEE_A_BLOCKS) k_nee_a(const __grid_c
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_pad; j += gridDim.x * blockDim.x) {
         __syncwarp();
         if (j >= n) continue;
-        const uint32_t slot = W.surv.slot[j], li = W.surv.li[j], lobj = S.P.n_objects + li;
+        const uint32_t slot = W.surv.slot[j], lf = W.surv.li[j], li = lf & 0x00FFFFFFu, lobj = S.P.n_objects + li;   // n_lights < 2^24 (validate_blob)
+        const bool term_b = (lf & 0x80000000u) != 0u, far_off = (lf & 0x40000000u) != 0u;
         const D3 wi = d3(W.surv.wx[j], W.surv.wy[j], W.surv.wz[j]);
         DevHit ho; D3 nb; nee_ctx_load(W, slot, ho, nb);
         const Ray ri = hit_generate_ray(ho, wi);
         DevHit hi;
         if (!light_hit<TEX>(S, lobj, ri, hi)) continue;
+        if (far_off) atomicAdd(&W.run->prereject_bad, 1u);                            // check mode only: must never happen
         const double p_lig = light_sample_towards_pdf(S, S.objects[lobj], ri, hi.p, hi.ng);
         Lam lam; for (int k = 0; k < 4; k++) lam.l[k] = W.lam[(size_t)k * N + slot];   // already terminated by k_scatter if dispersive
         const C4 le = mat_emit<TEX ? -1 : LUMO_K_SOLID>(S, S.materials[hi.material], lam, hi);
-        push_term(W, slot, false, ri, wi, hi.t - LUMO_EPS, p_lig, S.lights[li].pdf, le);
+        push_term(W, slot, term_b, ri, wi, hi.t - LUMO_EPS, p_lig, S.lights[li].pdf, le);
     }
 }
 #else
@@ -676,7 +679,9 @@ __global__ void __launch_bounds__(128, LUMO_NEE_A_BLOCKS) k_nee_b(const __grid_c
         const uint32_t pixel = W.pixel[slot], sample = W.sample[slot], d0 = W.draws[cur][slot] + 3u + 6u * i;
         Rng rng = rng_make(P.seed, pixel, sample, 0u, d0);
         const uint32_t li = sample_light(S, rng_float(rng));
+#if !LUMO_NEE_A_SPLIT
         const uint32_t lobj = S.P.n_objects + li;
+#endif
         rng = rng_make(P.seed, pixel, sample, 0u, d0 + 3u);
         const double ru = rng_float(rng), r0 = rng_float(rng), r1 = rng_float(rng);
         Lam lam; for (int k = 0; k < 4; k++) lam.l[k] = W.lam[(size_t)k * N + slot];
@@ -703,6 +708,11 @@ __global__ void __launch_bounds__(128, LUMO_NEE_A_BLOCKS) k_nee_b(const __grid_c
 #else
         const bool far_off = false;
 #endif
+#if LUMO_NEE_A_SPLIT
+        // the light's intersection test, pdf and emission are k_nee_a's (the second stage of both terms): bit 31 marks the BSDF-sampled term
+        { const uint32_t j = agg_inc(&W.it->n_surv);
+          W.surv.slot[j] = slot; W.surv.li[j] = li | 0x80000000u | (far_off ? 0x40000000u : 0u); W.surv.wx[j] = wi.x; W.surv.wy[j] = wi.y; W.surv.wz[j] = wi.z; }
+#else
         const Ray ri = hit_generate_ray(ho, wi);
         DevHit hi;
         if (!light_hit<LUMO_TEX(K)>(S, lobj, ri, hi)) continue;
@@ -710,6 +720,7 @@ __global__ void __launch_bounds__(128, LUMO_NEE_A_BLOCKS) k_nee_b(const __grid_c
         const double p_lig = light_sample_towards_pdf(S, S.objects[lobj], ri, hi.p, hi.ng);
         const C4 le = mat_emit<K>(S, S.materials[hi.material], lam, hi);
         push_term(W, slot, true, ri, wi, hi.t - LUMO_EPS, p_lig, L.pdf, le);
+#endif
     }
 }
 // BSDF pdf and value, MIS weight (integrator.rs:139-184), contribution -> shadow queue.  Dense over the term queue.
