@@ -394,10 +394,10 @@ def measure(name, args, env, steps, warmup, full):
                           "60 B shadow-queue entry + 128 B per BVH node + 8 B per leaf primitive + 72 B per triangle test + 68 B per candidate + the confirming traversal's visits")
     if by["occlude"]: by["occlude"]["per_ray"] = {k: v / max(cntc["occlusion"], 1) for k, v in ost.items()}
     sst = ctx.shade_stats()      # of the counting render just above
-    shade_bytes = bounces * (192 * 2 + 32 + 64) + sst["nee_bounces"] * (140 + 2 * 140) + sst["nee_terms"] * (2 * 132 + 140) + 92.0 * cntc["occlusion"]
-    by["shade"] = entry("k_terminal + k_scatter<K> + k_nee_a + k_nee_b<K> + k_nee_eval<K> (one bounce of the integrator)", "shade", shade_bytes, bounces, "bounce",
+    shade_bytes = bounces * (192 * 2 + 32 + 64) + sst["nee_bounces"] * (140 + 2 * 140) + sst["nee_terms"] * (2 * 36 + 140 + 2 * 132 + 140) + 92.0 * cntc["occlusion"]
+    by["shade"] = entry("k_terminal + k_scatter<K> + k_nee_a1 + k_nee_b<K> + k_nee_a + k_nee_eval<K> (one bounce of the integrator)", "shade", shade_bytes, bounces, "bounce",
                         "SURVEY 8d's B_bounce (2 x 192 B path state + 32 B hit record + 64 B material) + the queues of the three-stage NEE: 140 B shading context written once and read by two "
-                        "stages per NEE bounce (%.2f of the bounces), 132 B per NEE term written and read back + 140 B context per evaluated term (%.2f terms per bounce), 92 B per queued shadow ray "
+                        "stages per NEE bounce (%.2f of the bounces), per NEE term 36 B of survivor queue written and read + 140 B context in the light-side stage, 132 B of term queue written and read back + 140 B context in the evaluation (%.2f terms per bounce), 92 B per queued shadow ray "
                         "(%.2f per bounce).  The class is FP64-latency and instruction-fetch bound, not HBM bound (profiles/README.md)" % (sst["nee_bounces"] / bounces, sst["nee_terms"] / bounces, n_shadow_per_bounce))
     if by["shade"]: by["shade"]["per_bounce"] = {"nee_bounces": sst["nee_bounces"] / bounces, "nee_terms": sst["nee_terms"] / bounces, "shadow_rays": n_shadow_per_bounce, "survey_8d_bytes": 480 + 128.0 * n_shadow_per_bounce}
     by = {k: v for k, v in by.items() if v}
