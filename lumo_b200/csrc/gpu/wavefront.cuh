@@ -607,12 +607,13 @@ __global__ void __launch_bounds__(128, LUMO_NEE_A_BLOCKS) k_nee_a1(const __grid_
             if (!same_hemisphere(to_local(uvw, wo), to_local(uvw, wi))) continue;
         }
         const uint32_t j = agg_inc(&W.it->n_surv);
+        if (j >= W.shadow_cap) { atomicAdd(&W.run->shadow_dropped, 1ull); continue; }     // cannot happen unless shadow_cap was clamped (render fails loudly)
         W.surv.slot[j] = slot; W.surv.li[j] = li; W.surv.wx[j] = wi.x; W.surv.wy[j] = wi.y; W.surv.wz[j] = wi.z;
     }
 }
 template <bool TEX>
 __global__ void __launch_bounds__(128, LUMO_NEE_A_BLOCKS) k_nee_a(const __grid_constant__ DevScene S, const __grid_constant__ Wave W, const __grid_constant__ WaveParams P, uint32_t klass) {
-    const uint32_t N = W.n_slots, n = W.it->n_surv;
+    const uint32_t N = W.n_slots, n = min(W.it->n_surv, W.shadow_cap);
     const uint32_t n_pad = (n + 31u) & ~31u;
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_pad; j += gridDim.x * blockDim.x) {
         __syncwarp();
@@ -713,6 +714,7 @@ __global__ void __launch_bounds__(128, LUMO_NEE_A_BLOCKS) k_nee_b(const __grid_c
 #if LUMO_NEE_A_SPLIT
         // the light's intersection test, pdf and emission are k_nee_a's (the second stage of both terms): bit 31 marks the BSDF-sampled term
         { const uint32_t j = agg_inc(&W.it->n_surv);
+          if (j >= W.shadow_cap) { atomicAdd(&W.run->shadow_dropped, 1ull); continue; }
           W.surv.slot[j] = slot; W.surv.li[j] = li | 0x80000000u | (far_off ? 0x40000000u : 0u); W.surv.wx[j] = wi.x; W.surv.wy[j] = wi.y; W.surv.wz[j] = wi.z; }
 #else
         const Ray ri = hit_generate_ray(ho, wi);
