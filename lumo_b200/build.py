@@ -30,7 +30,7 @@ def _sources(sub, exts):
 def build_host(force=False, verbose=False):
     srcs = _sources("host", (".cpp", ".h"))
     if force or _stale(HOST_SO, srcs):
-        cmd = ["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-Wall", "-Wno-unused-function",
+        cmd = ["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-pthread", "-Wall", "-Wno-unused-function",
                "-o", HOST_SO] + [s for s in srcs if s.endswith(".cpp")]
         if verbose:
             print(" ".join(cmd))

@@ -15,6 +15,9 @@
 #include "ah_bvh.h"
 #include "srgb_table.h"
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <deque>
@@ -90,6 +93,8 @@ struct Builder {
     std::vector<Box> object_boxes, light_boxes;
     std::vector<LumoInstance> instances;
     std::vector<LumoKdTree> kd_trees; std::vector<LumoKdNode> kd_nodes; std::vector<uint32_t> kd_leaf;
+    struct KdJob { uint32_t tri_base, n, tree; };
+    std::vector<KdJob> kd_jobs;                      // trees requested while the program is read; built together by finish_kd_trees
     std::vector<LumoTriVerts> tri_verts; std::vector<LumoTriShade> tri_shade;
     std::vector<double> normals, uvs;
     std::vector<LumoRect> rects; std::vector<LumoSphere> spheres;
@@ -128,12 +133,31 @@ static double kd_cost(const Box& box, int ax, double point, size_t nl, size_t np
     return c1 < c2 ? c1 : c2;
 }
 
-// Builds one tree over triangles [tri_base, tri_base + n) of B.tri_verts; appends nodes / leaf lists.
+static double g_kd_seconds = 0.0;   // LUMO_HOST_TIMING
+// Registers one tree over triangles [tri_base, tri_base + n) of B.tri_verts: its record (root box, triangle range) exists at
+// once — the object that owns it only needs the box — while nodes and leaf lists are built by finish_kd_trees.
 static uint32_t build_kd(Builder& B, uint32_t tri_base, uint32_t n) {
-    std::vector<Box> tb(n);
     Box root_box = Box::empty();
     for (uint32_t i = 0; i < n; i++) {
         const LumoTriVerts& t = B.tri_verts[tri_base + i];
+        V3 a = v3(t.a[0], t.a[1], t.a[2]), b = v3(t.b[0], t.b[1], t.b[2]), c = v3(t.c[0], t.c[1], t.c[2]);
+        Box tb; tb.lo = vmin(a, vmin(b, c)); tb.hi = vmax(a, vmax(b, c));                        // triangle.rs:199-204
+        root_box = merge(root_box, tb);
+    }
+    LumoKdTree rec;
+    rec.lo[0] = root_box.lo.x; rec.lo[1] = root_box.lo.y; rec.lo[2] = root_box.lo.z;
+    rec.hi[0] = root_box.hi.x; rec.hi[1] = root_box.hi.y; rec.hi[2] = root_box.hi.z;
+    rec.root = 0; rec.tri_base = tri_base; rec.n_tris = n; rec.pad = 0;
+    B.kd_trees.push_back(rec);
+    B.kd_jobs.push_back({tri_base, n, (uint32_t)B.kd_trees.size() - 1});
+    return (uint32_t)B.kd_trees.size() - 1;
+}
+// One tree into `nodes` / `leaf` (indices local to the tree: child links from node 0, leaf lists from entry 0).
+static void build_kd_local(const std::vector<LumoTriVerts>& tri_verts, uint32_t tri_base, uint32_t n, std::vector<LumoKdNode>& nodes, std::vector<uint32_t>& leafs) {
+    std::vector<Box> tb(n);
+    Box root_box = Box::empty();
+    for (uint32_t i = 0; i < n; i++) {
+        const LumoTriVerts& t = tri_verts[tri_base + i];
         V3 a = v3(t.a[0], t.a[1], t.a[2]), b = v3(t.b[0], t.b[1], t.b[2]), c = v3(t.c[0], t.c[1], t.c[2]);
         tb[i].lo = vmin(a, vmin(b, c)); tb[i].hi = vmax(a, vmax(b, c));                       // triangle.rs:199-204
         root_box = merge(root_box, tb[i]);
@@ -153,13 +177,10 @@ static uint32_t build_kd(Builder& B, uint32_t tri_base, uint32_t n) {
     std::vector<Work> stack;
     stack.push_back(Work{std::move(events), n, root_box, LUMO_NONE});
     std::vector<uint8_t> side(n, 0);
-    const uint32_t node_base = (uint32_t)B.kd_nodes.size();
-    const uint32_t leaf_base = (uint32_t)B.kd_leaf.size();
-    (void)leaf_base;
     while (!stack.empty()) {
         Work w = std::move(stack.back()); stack.pop_back();
-        const uint32_t self = (uint32_t)B.kd_nodes.size();
-        if (w.patch != LUMO_NONE) B.kd_nodes[w.patch].a = self;
+        const uint32_t self = (uint32_t)nodes.size();
+        if (w.patch != LUMO_NONE) nodes[w.patch].a = self;
         // sweep (node.rs:125-194)
         double best_cost = kInf, best_point = kInf; int best_axis = 0;
         size_t nl[3] = {0, 0, 0}, nr[3] = {w.prims, w.prims, w.prims};
@@ -175,12 +196,12 @@ static uint32_t build_kd(Builder& B, uint32_t tri_base, uint32_t n) {
             nl[ax] += cnt[EV_START]; nl[ax] += cnt[EV_PLANAR];
         }
         if (best_cost > KD_INTERSECT * (double)w.prims) {                                         // node.rs:245-257
-            LumoKdNode leaf; leaf.point = kInf; leaf.a = (uint32_t)B.kd_leaf.size();
+            LumoKdNode leaf; leaf.point = kInf; leaf.a = (uint32_t)leafs.size();
             uint32_t count = 0;
-            for (const Ev& e : ev) if (!side[e.idx]) { side[e.idx] = 1; B.kd_leaf.push_back(e.idx); count++; }
-            for (uint32_t k = 0; k < count; k++) side[B.kd_leaf[leaf.a + k]] = 0;
+            for (const Ev& e : ev) if (!side[e.idx]) { side[e.idx] = 1; leafs.push_back(e.idx); count++; }
+            for (uint32_t k = 0; k < count; k++) side[leafs[leaf.a + k]] = 0;
             leaf.b = 0x80000000u | count;
-            B.kd_nodes.push_back(leaf);
+            nodes.push_back(leaf);
             continue;
         }
         // classify (node.rs:198-230): 1 left only, 2 right only, 0 both; later events overwrite
@@ -202,18 +223,41 @@ static uint32_t build_kd(Builder& B, uint32_t tri_base, uint32_t n) {
         for (const Ev& e : ev) side[e.idx] = 0;
         split_box(w.box, best_axis, best_point, L.box, R.box);
         LumoKdNode inner; inner.point = best_point; inner.a = LUMO_NONE; inner.b = (uint32_t)best_axis;
-        B.kd_nodes.push_back(inner);
+        nodes.push_back(inner);
         w.ev.clear(); w.ev.shrink_to_fit();
         L.patch = LUMO_NONE; R.patch = self;
         stack.push_back(std::move(R));   // right is visited after the whole left subtree -> pre-order
         stack.push_back(std::move(L));
     }
-    LumoKdTree rec;
-    rec.lo[0] = root_box.lo.x; rec.lo[1] = root_box.lo.y; rec.lo[2] = root_box.lo.z;
-    rec.hi[0] = root_box.hi.x; rec.hi[1] = root_box.hi.y; rec.hi[2] = root_box.hi.z;
-    rec.root = node_base; rec.tri_base = tri_base; rec.n_tris = n; rec.pad = 0;
-    B.kd_trees.push_back(rec);
-    return (uint32_t)B.kd_trees.size() - 1;
+}
+// Builds every registered tree — the trees are independent, so they are spread over the host's threads — and appends them in
+// the order they were registered: the node and leaf arrays are exactly what building them one after the other gives.
+static void finish_kd_trees(Builder& B) {
+    const auto t0 = std::chrono::steady_clock::now();
+    const size_t nj = B.kd_jobs.size();
+    std::vector<std::vector<LumoKdNode>> nodes(nj); std::vector<std::vector<uint32_t>> leafs(nj);
+    unsigned threads = std::thread::hardware_concurrency(); if (threads == 0) threads = 1; if (threads > 32) threads = 32;
+    if (const char* e = std::getenv("LUMO_HOST_THREADS")) { const int v = std::atoi(e); if (v >= 1 && v <= 256) threads = (unsigned)v; }
+    {
+        std::atomic<size_t> next{0};
+        auto worker = [&]() { for (;;) { const size_t k = next.fetch_add(1); if (k >= nj) break; build_kd_local(B.tri_verts, B.kd_jobs[k].tri_base, B.kd_jobs[k].n, nodes[k], leafs[k]); } };
+        const unsigned T = (unsigned)std::min<size_t>(threads, nj);
+        if (T <= 1) worker();
+        else { std::vector<std::thread> th; th.reserve(T); for (unsigned t = 0; t < T; t++) th.emplace_back(worker); for (auto& x : th) x.join(); }
+    }
+    for (size_t k = 0; k < nj; k++) {
+        const uint32_t node_base = (uint32_t)B.kd_nodes.size(), leaf_base = (uint32_t)B.kd_leaf.size();
+        for (LumoKdNode nd : nodes[k]) {
+            if (nd.b & 0x80000000u) nd.a += leaf_base;           // leaf: first entry of its list
+            else nd.a += node_base;                              // inner: right child
+            B.kd_nodes.push_back(nd);
+        }
+        B.kd_leaf.insert(B.kd_leaf.end(), leafs[k].begin(), leafs[k].end());
+        B.kd_trees[B.kd_jobs[k].tree].root = node_base;
+        std::vector<LumoKdNode>().swap(nodes[k]); std::vector<uint32_t>().swap(leafs[k]);
+    }
+    B.kd_jobs.clear();
+    g_kd_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
 // fan triangulation + degenerate drop (triangle_mesh.rs:58-96); returns [first, count) in tri arrays
@@ -670,6 +714,7 @@ static bool run(const uint8_t* data, uint64_t len, std::vector<uint8_t>& out) {
     if (B.light_objects.empty() && !B.have_env) { g_err = "scene has no lights"; return false; }      // renderer.rs:42
     for (const LumoObject& o : B.objects) if (o.material < 0 || o.material >= (int32_t)B.materials.size()) { g_err = "object without material"; return false; }
 
+    finish_kd_trees(B);
     // Scene::build (scene.rs:33-52)
     const uint32_t obj_root = build_bvh(B, B.object_boxes);
     (void)obj_root;
@@ -785,7 +830,15 @@ static bool run(const uint8_t* data, uint64_t len, std::vector<uint8_t>& out) {
             }
         }
         if (ah.prims.size() >= (1u << 27)) { g_err = "too many primitives for the occlusion BVH (2^27)"; return false; }
-        ah.build_binary(); ah.collapse();
+        const bool timing = std::getenv("LUMO_HOST_TIMING") != nullptr;
+        const auto t0 = std::chrono::steady_clock::now();
+        ah.build_binary();
+        const auto t1 = std::chrono::steady_clock::now();
+        ah.collapse();
+        const auto t2 = std::chrono::steady_clock::now();
+        if (timing) std::fprintf(stderr, "[lumo_host] kd-trees %.2f s; world-space BVH over %zu primitives: binary build %.2f s, collapse %.2f s\n", g_kd_seconds, ah.prims.size(),
+                                 std::chrono::duration<double>(t1 - t0).count(), std::chrono::duration<double>(t2 - t1).count());
+        g_kd_seconds = 0.0;
     }
     // per object: its chain of object-BVH nodes, root first (the confirming traversal re-runs the reference's box tests on it)
     std::vector<uint32_t> path_off(all_objects.size() + 1, 0), path_nodes;

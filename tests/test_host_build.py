@@ -132,3 +132,19 @@ def test_light_bounding_spheres_contain_the_lights(name):
         assert np.isfinite(r) and r > 0.0
         assert d <= r * (1.0 - 5e-5), (name, li, kind, d, r)          # padded by 1e-4 of the radius
         assert r <= 1.8 * d + 1e-5 * (np.abs(c).max() + 1.0), (name, li, kind, d, r)   # and not uselessly large (half diagonal of the box <= sqrt(3) x the farthest point)
+
+
+@pytest.mark.parametrize("name", ["bunny", "bistro", "conference"])
+def test_blob_does_not_depend_on_the_number_of_host_threads(name, monkeypatch):
+    """kd-trees are built in parallel (one tree per task) and the world-space BVH in parallel (big nodes: their passes over the
+    primitives; then independent subtrees): the blob must be byte for byte what one thread builds."""
+    from lumo_b200 import scenes
+    kw = dict(SMALL[name])
+    if name == "bunny": kw["n_tris"] = 90000          # more than 2^16 primitives: the top phase of the BVH build splits its passes over the threads
+    s, cam, _ = scenes.CONFIGS[name](**kw)
+    prog = s._program(cam)
+    blobs = []
+    for threads in ("1", "3", "8"):
+        monkeypatch.setenv("LUMO_HOST_THREADS", threads)
+        blobs.append(bytes(native.build_blob(prog)))
+    assert blobs[0] == blobs[1] == blobs[2]
