@@ -152,8 +152,80 @@ static uint32_t build_kd(Builder& B, uint32_t tri_base, uint32_t n) {
     B.kd_jobs.push_back({tri_base, n, (uint32_t)B.kd_trees.size() - 1});
     return (uint32_t)B.kd_trees.size() - 1;
 }
-// One tree into `nodes` / `leaf` (indices local to the tree: child links from node 0, leaf lists from entry 0).
-static void build_kd_local(const std::vector<LumoTriVerts>& tri_verts, uint32_t tri_base, uint32_t n, std::vector<LumoKdNode>& nodes, std::vector<uint32_t>& leafs) {
+// One node of the build (node.rs:125-294): the sweep over the sorted events, then either a leaf (its triangle list) or the split
+// plane and the two children's event lists.  `side` is scratch of one byte per triangle of the tree, all zero between calls.
+struct KdWork { std::vector<Ev> ev; size_t prims; Box box; };
+static bool kd_node(KdWork& w, std::vector<uint8_t>& side, double& point, int& axis_out, KdWork& L, KdWork& R, std::vector<uint32_t>& leaf_list) {
+    // sweep (node.rs:125-194)
+    double best_cost = kInf, best_point = kInf; int best_axis = 0;
+    size_t nl[3] = {0, 0, 0}, nr[3] = {w.prims, w.prims, w.prims};
+    const std::vector<Ev>& ev = w.ev;
+    for (size_t i = 0; i < ev.size();) {
+        const double p = ev[i].p; const int ax = ev[i].ax;
+        size_t cnt[3] = {0, 0, 0};
+        for (int ty = EV_END; ty <= EV_START; ty++)
+            while (i < ev.size() && ev[i].ax == ax && ev[i].p == p && ev[i].type == ty) { cnt[ty]++; i++; }
+        nr[ax] -= cnt[EV_PLANAR]; nr[ax] -= cnt[EV_END];
+        double c = kd_cost(w.box, ax, p, nl[ax], cnt[EV_PLANAR], nr[ax]);
+        if (c < best_cost) { best_cost = c; best_point = p; best_axis = ax; }
+        nl[ax] += cnt[EV_START]; nl[ax] += cnt[EV_PLANAR];
+    }
+    if (best_cost > KD_INTERSECT * (double)w.prims) {                                         // node.rs:245-257
+        leaf_list.clear();
+        for (const Ev& e : ev) if (!side[e.idx]) { side[e.idx] = 1; leaf_list.push_back(e.idx); }
+        for (uint32_t t : leaf_list) side[t] = 0;
+        return false;
+    }
+    // classify (node.rs:198-230): 1 left only, 2 right only, 0 both; later events overwrite
+    for (const Ev& e : ev) {
+        if (e.ax != best_axis) continue;
+        if (e.type == EV_END) { if (e.p <= best_point) side[e.idx] = 1; }
+        else if (e.type == EV_START) { if (e.p >= best_point) side[e.idx] = 2; }
+        else { if (e.p < best_point) side[e.idx] = 1; else if (e.p > best_point) side[e.idx] = 2; }
+    }
+    L.ev.clear(); R.ev.clear();
+    L.ev.reserve(ev.size()); R.ev.reserve(ev.size());
+    L.prims = R.prims = 0;
+    for (const Ev& e : ev) {                                                                 // node.rs:269-294
+        const uint8_t sd = side[e.idx];
+        const bool counts = e.ax == 0 && (e.type == EV_PLANAR || e.type == EV_START);
+        if (sd != 2) { L.ev.push_back(e); L.prims += counts; }
+        if (sd != 1) { R.ev.push_back(e); R.prims += counts; }
+    }
+    for (const Ev& e : ev) side[e.idx] = 0;
+    split_box(w.box, best_axis, best_point, L.box, R.box);
+    point = best_point; axis_out = best_axis;
+    return true;
+}
+// The subtree under `root` in pre-order into nodes / leafs (appended; child links and leaf-list starts are absolute in them).
+static void kd_subtree(KdWork&& root, uint32_t n, std::vector<LumoKdNode>& nodes, std::vector<uint32_t>& leafs) {
+    struct Item { KdWork w; uint32_t patch; };
+    std::vector<Item> stack;
+    stack.push_back(Item{std::move(root), LUMO_NONE});
+    std::vector<uint8_t> side(n, 0);
+    std::vector<uint32_t> leaf_list;
+    while (!stack.empty()) {
+        Item it = std::move(stack.back()); stack.pop_back();
+        const uint32_t self = (uint32_t)nodes.size();
+        if (it.patch != LUMO_NONE) nodes[it.patch].a = self;
+        double point; int ax; KdWork L, R;
+        if (!kd_node(it.w, side, point, ax, L, R, leaf_list)) {
+            LumoKdNode leaf; leaf.point = kInf; leaf.a = (uint32_t)leafs.size(); leaf.b = 0x80000000u | (uint32_t)leaf_list.size();
+            leafs.insert(leafs.end(), leaf_list.begin(), leaf_list.end());
+            nodes.push_back(leaf);
+            continue;
+        }
+        LumoKdNode inner; inner.point = point; inner.a = LUMO_NONE; inner.b = (uint32_t)ax;
+        nodes.push_back(inner);
+        it.w.ev.clear(); it.w.ev.shrink_to_fit();
+        stack.push_back(Item{std::move(R), self});   // right is visited after the whole left subtree -> pre-order
+        stack.push_back(Item{std::move(L), LUMO_NONE});
+    }
+}
+// One tree into `nodes` / `leafs` (indices local to the tree: child links from node 0, leaf lists from entry 0).  A large tree
+// (one mesh of hundreds of thousands of triangles) is opened from the root down to a few dozen subtrees, which are built on
+// `threads` threads and put back in pre-order: the arrays are the ones the one-thread walk produces.
+static void build_kd_local(const std::vector<LumoTriVerts>& tri_verts, uint32_t tri_base, uint32_t n, std::vector<LumoKdNode>& nodes, std::vector<uint32_t>& leafs, unsigned threads) {
     std::vector<Box> tb(n);
     Box root_box = Box::empty();
     for (uint32_t i = 0; i < n; i++) {
@@ -173,61 +245,64 @@ static void build_kd_local(const std::vector<LumoTriVerts>& tri_verts, uint32_t 
         if (x.ax != y.ax) return x.ax < y.ax;
         return x.type < y.type;
     });
-    struct Work { std::vector<Ev> ev; size_t prims; Box box; uint32_t patch; };
-    std::vector<Work> stack;
-    stack.push_back(Work{std::move(events), n, root_box, LUMO_NONE});
+    KdWork root{std::move(events), n, root_box};
+    nodes.clear(); leafs.clear();
+    if (threads <= 1 || n < 65536u) { kd_subtree(std::move(root), n, nodes, leafs); return; }
+    // top of the tree: nodes are opened level by level until there are enough open subtrees
+    struct Top { bool leaf = false, open = false; LumoKdNode node; int left = -1, right = -1; std::vector<uint32_t> list; KdWork w; size_t sub = 0; };
+    std::vector<Top> top(1);
+    top[0].open = true; top[0].w = std::move(root);
     std::vector<uint8_t> side(n, 0);
-    while (!stack.empty()) {
-        Work w = std::move(stack.back()); stack.pop_back();
+    for (int level = 0; level < 16; level++) {
+        size_t n_open = 0; for (const Top& t : top) n_open += t.open;
+        if (n_open >= (size_t)threads * 4u) break;
+        bool any = false;
+        const size_t cur = top.size();
+        for (size_t k = 0; k < cur; k++) {
+            if (!top[k].open || top[k].w.ev.size() < 32768u) continue;       // small ranges stay open: they are built in the parallel phase
+            double point; int ax; KdWork L, R; std::vector<uint32_t> list;
+            KdWork w = std::move(top[k].w);
+            top[k].open = false; any = true;
+            if (!kd_node(w, side, point, ax, L, R, list)) { top[k].leaf = true; top[k].list = std::move(list); continue; }
+            top[k].node.point = point; top[k].node.a = LUMO_NONE; top[k].node.b = (uint32_t)ax;
+            Top l, r; l.open = r.open = true; l.w = std::move(L); r.w = std::move(R);
+            top[k].left = (int)top.size(); top.push_back(std::move(l));
+            top[k].right = (int)top.size(); top.push_back(std::move(r));
+        }
+        if (!any) break;
+    }
+    std::vector<size_t> open_ids;
+    for (size_t k = 0; k < top.size(); k++) if (top[k].open) { top[k].sub = open_ids.size(); open_ids.push_back(k); }
+    std::vector<std::vector<LumoKdNode>> sn(open_ids.size()); std::vector<std::vector<uint32_t>> sl(open_ids.size());
+    {
+        std::atomic<size_t> next{0};
+        auto worker = [&]() { for (;;) { const size_t k = next.fetch_add(1); if (k >= open_ids.size()) break; kd_subtree(std::move(top[open_ids[k]].w), n, sn[k], sl[k]); } };
+        const unsigned T = (unsigned)std::min<size_t>(threads, open_ids.size());
+        if (T <= 1) worker();
+        else { std::vector<std::thread> th; th.reserve(T); for (unsigned t = 0; t < T; t++) th.emplace_back(worker); for (auto& x : th) x.join(); }
+    }
+    // pre-order assembly
+    struct Fr { int id; uint32_t patch; };
+    std::vector<Fr> st; st.push_back({0, LUMO_NONE});
+    while (!st.empty()) {
+        const Fr f = st.back(); st.pop_back();
         const uint32_t self = (uint32_t)nodes.size();
-        if (w.patch != LUMO_NONE) nodes[w.patch].a = self;
-        // sweep (node.rs:125-194)
-        double best_cost = kInf, best_point = kInf; int best_axis = 0;
-        size_t nl[3] = {0, 0, 0}, nr[3] = {w.prims, w.prims, w.prims};
-        const std::vector<Ev>& ev = w.ev;
-        for (size_t i = 0; i < ev.size();) {
-            const double p = ev[i].p; const int ax = ev[i].ax;
-            size_t cnt[3] = {0, 0, 0};
-            for (int ty = EV_END; ty <= EV_START; ty++)
-                while (i < ev.size() && ev[i].ax == ax && ev[i].p == p && ev[i].type == ty) { cnt[ty]++; i++; }
-            nr[ax] -= cnt[EV_PLANAR]; nr[ax] -= cnt[EV_END];
-            double c = kd_cost(w.box, ax, p, nl[ax], cnt[EV_PLANAR], nr[ax]);
-            if (c < best_cost) { best_cost = c; best_point = p; best_axis = ax; }
-            nl[ax] += cnt[EV_START]; nl[ax] += cnt[EV_PLANAR];
-        }
-        if (best_cost > KD_INTERSECT * (double)w.prims) {                                         // node.rs:245-257
-            LumoKdNode leaf; leaf.point = kInf; leaf.a = (uint32_t)leafs.size();
-            uint32_t count = 0;
-            for (const Ev& e : ev) if (!side[e.idx]) { side[e.idx] = 1; leafs.push_back(e.idx); count++; }
-            for (uint32_t k = 0; k < count; k++) side[leafs[leaf.a + k]] = 0;
-            leaf.b = 0x80000000u | count;
+        if (f.patch != LUMO_NONE) nodes[f.patch].a = self;
+        Top& t = top[(size_t)f.id];
+        if (t.open) {
+            const uint32_t nb = (uint32_t)nodes.size(), lb = (uint32_t)leafs.size();
+            for (LumoKdNode nd : sn[t.sub]) { nd.a += (nd.b & 0x80000000u) ? lb : nb; nodes.push_back(nd); }
+            leafs.insert(leafs.end(), sl[t.sub].begin(), sl[t.sub].end());
+            std::vector<LumoKdNode>().swap(sn[t.sub]); std::vector<uint32_t>().swap(sl[t.sub]);
+        } else if (t.leaf) {
+            LumoKdNode leaf; leaf.point = kInf; leaf.a = (uint32_t)leafs.size(); leaf.b = 0x80000000u | (uint32_t)t.list.size();
+            leafs.insert(leafs.end(), t.list.begin(), t.list.end());
             nodes.push_back(leaf);
-            continue;
+        } else {
+            nodes.push_back(t.node);
+            st.push_back({t.right, self});
+            st.push_back({t.left, LUMO_NONE});
         }
-        // classify (node.rs:198-230): 1 left only, 2 right only, 0 both; later events overwrite
-        for (const Ev& e : ev) {
-            if (e.ax != best_axis) continue;
-            if (e.type == EV_END) { if (e.p <= best_point) side[e.idx] = 1; }
-            else if (e.type == EV_START) { if (e.p >= best_point) side[e.idx] = 2; }
-            else { if (e.p < best_point) side[e.idx] = 1; else if (e.p > best_point) side[e.idx] = 2; }
-        }
-        Work L, R;
-        L.ev.reserve(ev.size()); R.ev.reserve(ev.size());
-        L.prims = R.prims = 0;
-        for (const Ev& e : ev) {                                                                 // node.rs:269-294
-            const uint8_t s = side[e.idx];
-            const bool counts = e.ax == 0 && (e.type == EV_PLANAR || e.type == EV_START);
-            if (s != 2) { L.ev.push_back(e); L.prims += counts; }
-            if (s != 1) { R.ev.push_back(e); R.prims += counts; }
-        }
-        for (const Ev& e : ev) side[e.idx] = 0;
-        split_box(w.box, best_axis, best_point, L.box, R.box);
-        LumoKdNode inner; inner.point = best_point; inner.a = LUMO_NONE; inner.b = (uint32_t)best_axis;
-        nodes.push_back(inner);
-        w.ev.clear(); w.ev.shrink_to_fit();
-        L.patch = LUMO_NONE; R.patch = self;
-        stack.push_back(std::move(R));   // right is visited after the whole left subtree -> pre-order
-        stack.push_back(std::move(L));
     }
 }
 // Builds every registered tree — the trees are independent, so they are spread over the host's threads — and appends them in
@@ -240,7 +315,7 @@ static void finish_kd_trees(Builder& B) {
     if (const char* e = std::getenv("LUMO_HOST_THREADS")) { const int v = std::atoi(e); if (v >= 1 && v <= 256) threads = (unsigned)v; }
     {
         std::atomic<size_t> next{0};
-        auto worker = [&]() { for (;;) { const size_t k = next.fetch_add(1); if (k >= nj) break; build_kd_local(B.tri_verts, B.kd_jobs[k].tri_base, B.kd_jobs[k].n, nodes[k], leafs[k]); } };
+        auto worker = [&]() { for (;;) { const size_t k = next.fetch_add(1); if (k >= nj) break; build_kd_local(B.tri_verts, B.kd_jobs[k].tri_base, B.kd_jobs[k].n, nodes[k], leafs[k], threads); } };
         const unsigned T = (unsigned)std::min<size_t>(threads, nj);
         if (T <= 1) worker();
         else { std::vector<std::thread> th; th.reserve(T); for (unsigned t = 0; t < T; t++) th.emplace_back(worker); for (auto& x : th) x.join(); }
